@@ -1,0 +1,247 @@
+/*
+ * ppg.h — C-ABI of the B200-native batched PredPreyGrass environment step.
+ *
+ * This is the drop-in boundary for the one hot path of doesburg11/PredPreyGrass:
+ * `PredPreyGrass.reset()/step()` of the RLlib MultiAgentEnv classes.  The reference is pure
+ * Python and has no FFI of its own; each entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   BASE = predpreygrass/non_evolutionary/base_environment/predpreygrass_rllib_env.py
+ *   ADD  = predpreygrass/non_evolutionary/project_reward_shaping/
+ *            base_environment_dense_rewards_additive/predpreygrass_rllib_env.py
+ *   ECO  = predpreygrass/evolutionary/eco_evolutionary/predpreygrass_rllib_env.py
+ *   STAG = predpreygrass/evolutionary/stag_hunt_forward_view_nature_nurture/predpreygrass_rllib_env.py
+ *
+ * Plain pointers and sizes only; no torch types.  A handle owns the state of `n_envs`
+ * independent environment instances on one CUDA device (structure-of-arrays in HBM) and the
+ * output buffers of the last step.  A handle is not thread-safe; all work is stream-ordered
+ * on the stream passed to the call and no call synchronises the host unless it says so.
+ *
+ * Row model (replaces the reference's per-agent dicts, BASE:451-463): every step produces,
+ * per species, a compact batch of ROWS, one per agent that appears in that step's
+ * observation dict.  Rows [0, n_old) are agents that were alive when the step started, grouped
+ * by environment (ascending env index) and, inside an environment, in the reference's
+ * observation-dict order (BASE: lexicographic agent-id string order, BASE:459,468).  Rows
+ * [n_old, n_old+n_new) are this step's newborns, grouped by environment, in birth order
+ * (BASE:398,427 append them after the sorted survivors).  An agent's action for the next
+ * step is read from `actions[species][row]` of the row it occupied in THIS step's output,
+ * so `actions = policy(obs)` needs no gather.
+ */
+#ifndef PPG_H_
+#define PPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPG_ABI_VERSION 1
+
+/* species index used throughout */
+#define PPG_PREDATOR 0
+#define PPG_PREY 1
+
+/* which reference env class the handle reproduces */
+enum {
+  PPG_VARIANT_BASE = 0, /* BASE / project_reward_shaping family (one kernel, reward_mode flag) */
+  PPG_VARIANT_ECO = 1,  /* ECO: heritable speed trait, 25 actions, ageing, carcasses */
+  PPG_VARIANT_STAG = 2  /* STAG: two prey types, join_hunt team capture, forward view */
+};
+
+/* reward_mode (BASE family): which project_reward_shaping variant */
+enum {
+  PPG_REWARD_SPARSE = 0,         /* BASE:288,322,328,341,365,375,409,438 (also plus_eating: constants only) */
+  PPG_REWARD_DENSE = 1,          /* base_environment_dense_rewards/...:244,291,329,446-449 */
+  PPG_REWARD_DENSE_ADDITIVE = 2, /* ADD:256,308,346,419,450,468-471 */
+  PPG_REWARD_SPARSE_KICKBACK = 3 /* base_environment_sparse_rewards_plus_kickback/...:434-449 */
+};
+
+/* per-row flag bits (ppg_buffers.flags) */
+#define PPG_ROW_TERMINATED 0x01u /* terminations[agent] == True (BASE:289,332) */
+#define PPG_ROW_TRUNCATED 0x02u  /* truncations[agent] == True (BASE:232; ECO:452-472) */
+#define PPG_ROW_NEWBORN 0x04u    /* born this step (BASE:396-414) */
+#define PPG_ROW_FOUNDER 0x08u    /* row produced by reset(), not by step() (BASE:215) */
+#define PPG_ROW_ATE 0x10u        /* member of agents_just_ate (BASE:319,362) */
+
+/* per-env flag bits (ppg_buffers.env_flags), describe the step that just ran */
+#define PPG_ENV_TERMINATED 0x01u /* terminations["__all__"] (BASE:466) */
+#define PPG_ENV_TRUNCATED 0x02u  /* truncations["__all__"]: step counter reached max_steps (BASE:228-238) */
+#define PPG_ENV_RESET 0x04u      /* this call performed reset() for the env instead of step() */
+#define PPG_ENV_IDLE 0x08u       /* episode over, autoreset off: env produced no rows */
+
+/* sticky per-env status bits (ppg_buffers.env_status) — in-kernel conditions the reference
+ * would raise on (SURVEY §5 "failure detection") */
+#define PPG_STATUS_SLOT_OVERFLOW 0x01u  /* live agents of a species exceeded cap_live: birth suppressed */
+#define PPG_STATUS_NO_SPAWN_CELL 0x02u  /* no free cell for a newborn (reference: TypeError, BASE:766) */
+#define PPG_STATUS_TAPE_EXHAUSTED 0x04u /* replay tape ran out; Philox stream used instead */
+#define PPG_STATUS_BAD_ACTION 0x08u     /* action outside the action space (reference: KeyError, BASE:502) */
+
+/* error codes */
+#define PPG_OK 0
+#define PPG_ERR_INVALID 1  /* bad argument / config (reference: ValueError, BASE:167-168) */
+#define PPG_ERR_CUDA 2     /* CUDA runtime error, see ppg_last_error */
+#define PPG_ERR_NO_DEVICE 3
+#define PPG_ERR_STATE 4    /* call not valid in the handle's current state */
+
+/*
+ * Flattened `config_env` dict (BASE:22-61; base_environment/config_env.py:1-38).  Index [0] is
+ * the predator value, [1] the prey value of the corresponding `*_predator` / `*_prey` key.
+ */
+typedef struct ppg_config {
+  uint32_t struct_size; /* sizeof(ppg_config), ABI check */
+  int32_t variant;      /* PPG_VARIANT_* */
+  int32_t reward_mode;  /* PPG_REWARD_* */
+  int32_t grid_size;    /* "grid_size" */
+  int32_t max_steps;    /* "max_steps" */
+  int32_t num_obs_channels; /* "num_obs_channels" (4 for BASE: wall, predator, prey, grass) */
+  int32_t obs_range[2];     /* "predator_obs_range", "prey_obs_range" (odd) */
+  int32_t n_possible[2];    /* "n_possible_predators", "n_possible_prey" (agent-id pool) */
+  int32_t n_initial[2];     /* "n_initial_active_predator", "n_initial_active_prey" */
+  int32_t n_grass;          /* "initial_num_grass" */
+  int32_t cap_live[2];      /* device slot capacity per env and species (multiple of 32) */
+  int32_t autoreset;        /* 1: an env whose episode ended resets itself on the next ppg_step */
+  double energy_loss[2];        /* "energy_loss_per_step_*" */
+  double creation_threshold[2]; /* "*_creation_energy_threshold" */
+  double initial_energy[2];     /* "initial_energy_*" */
+  double initial_energy_grass;  /* "initial_energy_grass" (also the regrowth cap, BASE:253-255) */
+  double energy_gain_grass;     /* "energy_gain_per_step_grass" */
+  double reward_predator_catch_prey;
+  double reward_prey_eat_grass;
+  double reward_predator_step;
+  double reward_prey_step;
+  double penalty_prey_caught;
+  double reproduction_reward[2]; /* "reproduction_reward_*" */
+  double kickback_reward[2];     /* "kickback_reward_*" (plus_kickback variant only) */
+  uint64_t seed;                 /* Philox key for normal (non-replay) runs */
+} ppg_config;
+
+/*
+ * Replay tape: the random draws of the reference, captured from its numpy RNG, consumed by the
+ * device in the reference's consumption order (SURVEY §8c "Tape contents").  Per env two
+ * streams; env e owns cells[cell_off[e] .. cell_off[e+1]) and reals[real_off[e] .. real_off[e+1]).
+ *   cells: BASE reset — n_initial[0]+n_initial[1]+n_grass cells `x*grid_size+y` in the order
+ *          predators, prey, grass (BASE:185-187); then one cell per spawn fallback draw (BASE:764).
+ *   reals: unused by BASE; ECO/STAG trait and capture draws.
+ * All pointers are HOST pointers; the call copies.  When a stream is exhausted the env sets
+ * PPG_STATUS_TAPE_EXHAUSTED and continues on the Philox stream.
+ */
+typedef struct ppg_tape {
+  const int32_t* cells;
+  const int64_t* cell_off; /* [n_envs+1] */
+  const double* reals;
+  const int64_t* real_off; /* [n_envs+1] */
+} ppg_tape;
+
+/* Device pointers to the outputs of the last ppg_step/ppg_reset; owned by the handle and valid
+ * until the next call on it.  [s] = species. */
+typedef struct ppg_buffers {
+  float* obs[2];         /* [row_capacity[s]][C][R_s][R_s] fp32, index order [c][x][y] (BASE:518-524) */
+  int32_t* row_env[2];   /* env index of each row */
+  int32_t* row_agent[2]; /* numeric agent id: row is f"predator_{id}" / f"prey_{id}" (BASE:70-72) */
+  float* reward[2];      /* rewards[agent] (BASE:460) */
+  uint8_t* flags[2];     /* PPG_ROW_* */
+  int32_t* old_off[2];   /* [n_envs+1] row range of each env inside [0, n_old) */
+  int32_t* new_off[2];   /* [n_envs+1] row range of each env inside [n_old, n_old+n_new), absolute rows */
+  int32_t* n_rows;       /* [4] = n_old[0], n_old[1], n_new[0], n_new[1] */
+  uint8_t* env_flags;    /* [n_envs] PPG_ENV_* */
+  uint8_t* env_status;   /* [n_envs] PPG_STATUS_* (sticky until reset of the env) */
+  int32_t* env_step;     /* [n_envs] current_step after the call (BASE:471) */
+  int32_t* env_count;    /* [n_envs][2] live predators, prey after the call (BASE:210-211) */
+  int64_t row_capacity[2];
+  int32_t obs_row_elems[2]; /* C*R_s*R_s */
+  int32_t n_envs;
+} ppg_buffers;
+
+/* Aggregate statistics since ppg_create / last ppg_stats_clear, reduced over the handle's envs on
+ * the device (one block-reduce kernel); fixed-size so ranks can all-reduce it. */
+#define PPG_N_STATS 16
+enum {
+  PPG_STAT_ENV_STEPS = 0,     /* real env steps executed (reset calls excluded) */
+  PPG_STAT_AGENT_STEPS = 1,   /* agents that acted (alive at step start) summed over env steps */
+  PPG_STAT_EPISODES = 2,      /* episodes finished (terminated or truncated) */
+  PPG_STAT_EPISODE_STEPS = 3, /* sum of lengths of finished episodes */
+  PPG_STAT_BIRTHS_PRED = 4,
+  PPG_STAT_BIRTHS_PREY = 5,
+  PPG_STAT_STARVED_PRED = 6,
+  PPG_STAT_STARVED_PREY = 7,
+  PPG_STAT_EATEN_PREY = 8,
+  PPG_STAT_GRASS_EATEN = 9,
+  PPG_STAT_TRUNCATED = 10,  /* episodes that ended by max_steps */
+  PPG_STAT_ROWS_PRED = 11,  /* observation rows written */
+  PPG_STAT_ROWS_PREY = 12,
+  PPG_STAT_SPAWN_FALLBACK = 13,
+  PPG_STAT_STATUS_ENVS = 14, /* envs with a non-zero status word right now */
+  PPG_STAT_RESERVED = 15
+};
+
+typedef struct ppg_handle_s* ppg_handle;
+
+/* PredPreyGrass.__init__(config) (BASE:18-127) for n_envs instances on CUDA device `device`.
+ * Validates the config (PPG_ERR_INVALID ~ ValueError BASE:167-168). */
+int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle* out);
+int ppg_destroy(ppg_handle h);
+
+/* Fills a config with base_environment/config_env.py:1-38 defaults. */
+void ppg_default_config(ppg_config* cfg);
+
+/* Loads a replay tape (host pointers), resets the cursors. NULL tape clears it. */
+int ppg_load_tape(ppg_handle h, const ppg_tape* tape);
+
+/* PredPreyGrass.reset(seed=...) (BASE:129-217) for every env with mask[e] != 0 (mask NULL = all).
+ * seeds (host, [n_envs], may be NULL) re-key the env's Philox stream (BASE:135,170).
+ * Writes the founders' observation rows (PPG_ROW_FOUNDER) for the reset envs; envs not in the mask
+ * produce no rows in this call. */
+int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cuda_stream);
+
+/* PredPreyGrass.step(action_dict) (BASE:219-473) for all envs in lockstep.
+ * actions_pred / actions_prey: DEVICE int32 arrays indexed by the rows of the previous call's
+ * output (rows of terminated agents are ignored).  Each live agent must have an action — the
+ * contract RLlib's env runner fulfils (an agent missing from action_dict would neither decay nor
+ * move, BASE:244,259; that case is not supported).  Movement order inside an env = row order of
+ * the previous output (= the observation-dict order a caller iterates, BASE:259). */
+int ppg_step(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, void* cuda_stream);
+
+/* Same step with HOST buffers end to end: copies actions host->device, steps, copies the row
+ * batch (obs, ids, rewards, flags, offsets) device->host into `out` (host pointers, pinned
+ * recommended, capacities in out->row_capacity) and synchronises the stream.  n_rows_out[4]. */
+int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey,
+                  ppg_buffers* out, int32_t* n_rows_out, void* cuda_stream);
+
+/* Uniform random actions for the rows of the last output (synthetic rollouts: bench, tests).
+ * Philox keyed (seed, env, agent id, step) so the choice does not depend on row layout. */
+int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32_t* actions_prey,
+                       void* cuda_stream);
+
+int ppg_get_buffers(ppg_handle h, ppg_buffers* out);
+
+/* get_state_snapshot()/restore_state_snapshot() (BASE:768-804): the whole SoA slab incl. RNG
+ * counters and tape cursors as an opaque host blob.  ppg_snapshot_size gives the byte count. */
+size_t ppg_snapshot_size(ppg_handle h);
+int ppg_snapshot(ppg_handle h, void* host_blob, size_t bytes, void* cuda_stream);
+int ppg_restore(ppg_handle h, const void* host_blob, size_t bytes, void* cuda_stream);
+
+/* Readable state of one env for renderers / tests (BASE attributes agent_positions,
+ * agent_energies, grass_positions, grass_energies; random_policy.py:32-39).  Host arrays sized
+ * cap_live[s] / n_grass; counts returned in n_live[2]. Synchronises. */
+int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, int32_t* xy_pred,
+                 double* energy_pred, int32_t* ids_prey, int32_t* xy_prey, double* energy_prey,
+                 int32_t* xy_grass, double* energy_grass);
+
+/* Device-side reduction of the per-env counters into PPG_N_STATS int64 values (host out).
+ * Synchronises the stream. ppg_stats_device leaves them on the device for an NCCL all-reduce. */
+int ppg_stats(ppg_handle h, int64_t* out, void* cuda_stream);
+int ppg_stats_device(ppg_handle h, int64_t** dev_out, void* cuda_stream);
+int ppg_stats_clear(ppg_handle h, void* cuda_stream);
+
+/* Kernel launches issued by this handle since creation (bench `gpu_launches`). */
+int64_t ppg_launch_count(ppg_handle h);
+
+const char* ppg_last_error(ppg_handle h);
+int ppg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPG_H_ */

@@ -1,0 +1,168 @@
+"""`config_env` dict  <->  the POD `ppg_config` of include/ppg.h.
+
+The reference envs read a plain dict with per-key defaults (BASE:22-61,
+base_environment/config_env.py:1-38).  The same dict, unchanged, configures this package; it is
+flattened once into the C struct the kernels read.
+"""
+import ctypes as C
+
+VARIANT_BASE, VARIANT_ECO, VARIANT_STAG = 0, 1, 2
+REWARD_SPARSE, REWARD_DENSE, REWARD_DENSE_ADDITIVE, REWARD_SPARSE_KICKBACK = 0, 1, 2, 3
+
+REWARD_MODES = {
+    "sparse": REWARD_SPARSE,
+    "eating": REWARD_SPARSE,  # sparse_rewards_plus_eating: same code as BASE, constants differ
+    "dense": REWARD_DENSE,
+    "additive": REWARD_DENSE_ADDITIVE,
+    "kickback": REWARD_SPARSE_KICKBACK,
+}
+
+ROW_TERMINATED, ROW_TRUNCATED, ROW_NEWBORN, ROW_FOUNDER, ROW_ATE = 0x01, 0x02, 0x04, 0x08, 0x10
+ENV_TERMINATED, ENV_TRUNCATED, ENV_RESET, ENV_IDLE = 0x01, 0x02, 0x04, 0x08
+STATUS_SLOT_OVERFLOW, STATUS_NO_SPAWN_CELL, STATUS_TAPE_EXHAUSTED, STATUS_BAD_ACTION = 0x01, 0x02, 0x04, 0x08
+N_STATS = 16
+STAT_NAMES = [
+    "env_steps", "agent_steps", "episodes", "episode_steps", "births_pred", "births_prey", "starved_pred",
+    "starved_prey", "eaten_prey", "grass_eaten", "truncated", "rows_pred", "rows_prey", "spawn_fallback",
+    "status_envs", "reserved",
+]
+
+
+class PpgConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("variant", C.c_int32),
+        ("reward_mode", C.c_int32),
+        ("grid_size", C.c_int32),
+        ("max_steps", C.c_int32),
+        ("num_obs_channels", C.c_int32),
+        ("obs_range", C.c_int32 * 2),
+        ("n_possible", C.c_int32 * 2),
+        ("n_initial", C.c_int32 * 2),
+        ("n_grass", C.c_int32),
+        ("cap_live", C.c_int32 * 2),
+        ("autoreset", C.c_int32),
+        ("energy_loss", C.c_double * 2),
+        ("creation_threshold", C.c_double * 2),
+        ("initial_energy", C.c_double * 2),
+        ("initial_energy_grass", C.c_double),
+        ("energy_gain_grass", C.c_double),
+        ("reward_predator_catch_prey", C.c_double),
+        ("reward_prey_eat_grass", C.c_double),
+        ("reward_predator_step", C.c_double),
+        ("reward_prey_step", C.c_double),
+        ("penalty_prey_caught", C.c_double),
+        ("reproduction_reward", C.c_double * 2),
+        ("kickback_reward", C.c_double * 2),
+        ("seed", C.c_uint64),
+    ]
+
+
+class PpgTape(C.Structure):
+    _fields_ = [
+        ("cells", C.POINTER(C.c_int32)),
+        ("cell_off", C.POINTER(C.c_int64)),
+        ("reals", C.POINTER(C.c_double)),
+        ("real_off", C.POINTER(C.c_int64)),
+    ]
+
+
+class PpgBuffers(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p * 2),
+        ("row_env", C.c_void_p * 2),
+        ("row_agent", C.c_void_p * 2),
+        ("reward", C.c_void_p * 2),
+        ("flags", C.c_void_p * 2),
+        ("old_off", C.c_void_p * 2),
+        ("new_off", C.c_void_p * 2),
+        ("n_rows", C.c_void_p),
+        ("env_flags", C.c_void_p),
+        ("env_status", C.c_void_p),
+        ("env_step", C.c_void_p),
+        ("env_count", C.c_void_p),
+        ("row_capacity", C.c_int64 * 2),
+        ("obs_row_elems", C.c_int32 * 2),
+        ("n_envs", C.c_int32),
+    ]
+
+
+def _round32(n):
+    return max(32, (int(n) + 31) // 32 * 32)
+
+
+def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_live=None, autoreset=True, seed=0):
+    """Flatten a reference `config_env` dict (missing keys take the reference's own defaults,
+    BASE:22-61) into a PpgConfig."""
+    cfg = dict(config or {})
+    g = cfg.get
+    c = PpgConfig()
+    c.struct_size = C.sizeof(PpgConfig)
+    c.variant = variant
+    c.reward_mode = REWARD_MODES[reward_mode] if isinstance(reward_mode, str) else int(reward_mode)
+    c.grid_size = g("grid_size", 10)
+    c.max_steps = g("max_steps", 10000)
+    c.num_obs_channels = g("num_obs_channels", 4)
+    c.obs_range[0] = g("predator_obs_range", 7)
+    c.obs_range[1] = g("prey_obs_range", 5)
+    c.n_possible[0] = g("n_possible_predators", 50)
+    c.n_possible[1] = g("n_possible_prey", 50)
+    c.n_initial[0] = g("n_initial_active_predator", 6)
+    c.n_initial[1] = g("n_initial_active_prey", 8)
+    c.n_grass = g("initial_num_grass", 25)
+    if cap_live is None:
+        # enough for every cell of the grid to hold one agent of the species (the reference cannot
+        # place a newborn without a free cell, BASE:754-766), bounded by the id pool
+        cells = c.grid_size * c.grid_size
+        cap_live = (min(_round32(cells), _round32(c.n_possible[0])), min(_round32(cells), _round32(c.n_possible[1])))
+    c.cap_live[0], c.cap_live[1] = _round32(cap_live[0]), _round32(cap_live[1])
+    c.autoreset = 1 if autoreset else 0
+    c.energy_loss[0] = g("energy_loss_per_step_predator", 0.15)
+    c.energy_loss[1] = g("energy_loss_per_step_prey", 0.05)
+    c.creation_threshold[0] = g("predator_creation_energy_threshold", 12.0)
+    c.creation_threshold[1] = g("prey_creation_energy_threshold", 8.0)
+    c.initial_energy[0] = g("initial_energy_predator", 5.0)
+    c.initial_energy[1] = g("initial_energy_prey", 3.0)
+    c.initial_energy_grass = g("initial_energy_grass", 2.0)
+    c.energy_gain_grass = g("energy_gain_per_step_grass", 0.2)
+    c.reward_predator_catch_prey = g("reward_predator_catch_prey", 0.0)
+    c.reward_prey_eat_grass = g("reward_prey_eat_grass", 0.0)
+    c.reward_predator_step = g("reward_predator_step", 0.0)
+    c.reward_prey_step = g("reward_prey_step", 0.0)
+    c.penalty_prey_caught = g("penalty_prey_caught", 0.0)
+    c.reproduction_reward[0] = g("reproduction_reward_predator", 10.0)
+    c.reproduction_reward[1] = g("reproduction_reward_prey", 10.0)
+    c.kickback_reward[0] = g("kickback_reward_predator", 10.0)
+    c.kickback_reward[1] = g("kickback_reward_prey", 10.0)
+    c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return c
+
+
+# base_environment/config_env.py:1-38 — the BASELINE configs 1 and 2
+BASE_CONFIG = {
+    "max_steps": 1000,
+    "grid_size": 25,
+    "num_obs_channels": 4,
+    "predator_obs_range": 7,
+    "prey_obs_range": 9,
+    "reward_predator_catch_prey": 0.0,
+    "reward_prey_eat_grass": 0.0,
+    "reward_predator_step": 0.0,
+    "reward_prey_step": 0.0,
+    "penalty_prey_caught": 0.0,
+    "reproduction_reward_predator": 10.0,
+    "reproduction_reward_prey": 10.0,
+    "energy_loss_per_step_predator": 0.15,
+    "energy_loss_per_step_prey": 0.05,
+    "predator_creation_energy_threshold": 12.0,
+    "prey_creation_energy_threshold": 8.0,
+    "n_possible_predators": 2000,
+    "n_possible_prey": 2000,
+    "n_initial_active_predator": 6,
+    "n_initial_active_prey": 8,
+    "initial_energy_predator": 5.0,
+    "initial_energy_prey": 3.0,
+    "initial_num_grass": 100,
+    "initial_energy_grass": 2.0,
+    "energy_gain_per_step_grass": 0.04,
+}

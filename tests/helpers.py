@@ -1,0 +1,50 @@
+"""Shared helpers of the parity tests."""
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from predpreygrass_b200.config import REWARD_MODES, make_config
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases(prefixes=("base", "eating", "dense", "additive", "kickback")):
+    out = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        name = os.path.basename(p)[:-4]
+        if name.split("_")[0] in prefixes:
+            out.append(name)
+    return out
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    return z, cfg
+
+
+def config_from_golden(cfg, **kw):
+    variant = cfg.get("variant", "sparse")
+    kw.setdefault("cap_live", (cfg.get("n_possible_predators", 50), cfg.get("n_possible_prey", 50)))
+    return make_config(cfg, reward_mode=REWARD_MODES[variant], **kw)
+
+
+def sha_f64(arrs):
+    h = hashlib.sha1()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+def dict_order_rows(out, env=0):
+    """Rows of one env in the reference's observation-dict order:
+    old predators, old prey, newborn predators, newborn prey (BASE:459 over self.agents)."""
+    rows = []
+    for group in ("old", "new"):
+        for s in range(2):
+            off = out[f"{group}_off{s}"]
+            rows += [(s, r) for r in range(int(off[env]), int(off[env + 1]))]
+    return rows

@@ -1,0 +1,56 @@
+"""The oracle against trajectories recorded from the unmodified reference (tests/golden/*.npz).
+
+Bit-exact on everything: ids, dict orders, positions, float64 energies/rewards, the float64
+observation bytes (sha1) and the persistent grid (sha1)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from tests.helpers import config_from_golden, dict_order_rows, golden_cases, load_golden, sha_f64
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_replays_reference(name):
+    z, cfg = load_golden(name)
+    c = config_from_golden(cfg, autoreset=False)
+    o = Oracle(c, 1)
+    o.load_tape([z["fallback_cells"]])
+    out = o.env_reset_cells(0, z["init_cells"])
+    rows = dict_order_rows(out)
+    assert [s for s, _ in rows] == list(z["reset_row_s"])
+    assert [int(out[f"row_agent{s}"][r]) for s, r in rows] == list(z["reset_row_id"])
+    assert np.array_equal(sha_f64([out[f"obs64_{s}"][r] for s, r in rows]), z["reset_sha"])
+
+    T = len(z["steps"])
+    for t in range(T):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        out = o.env_step_ordered(0, z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])
+        rows = dict_order_rows(out)
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        assert [s for s, _ in rows] == list(z["row_s"][r0:r1]), (name, t)
+        assert [int(out[f"row_agent{s}"][r]) for s, r in rows] == list(z["row_id"][r0:r1]), (name, t)
+        rew = np.array([out[f"reward64_{s}"][r] for s, r in rows])
+        assert np.array_equal(rew, z["row_rew"][r0:r1]), (name, t, rew, z["row_rew"][r0:r1])
+        fl = np.array([out[f"flags{s}"][r] for s, r in rows], np.uint8)
+        assert np.array_equal(fl & 1, z["row_term"][r0:r1]), (name, t)
+        assert np.array_equal((fl >> 1) & 1, z["row_trunc"][r0:r1]), (name, t)
+        assert np.array_equal(sha_f64([out[f"obs64_{s}"][r] for s, r in rows]), z["obs_sha"][t]), (name, t)
+        assert bool(out["env_flags"][0] & 1) == bool(z["all_term"][t]), (name, t)
+        assert bool(out["env_flags"][0] & 2) == bool(z["all_trunc"][t]), (name, t)
+        assert int(out["env_step"][0]) == int(z["steps"][t])
+        # state after the step
+        st = o.read_env(0)
+        s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+        for s in range(2):
+            m = z["st_s"][s0:s1] == s
+            assert np.array_equal(st["ids"][s], z["st_id"][s0:s1][m]), (name, t, s)
+            assert np.array_equal(st["xy"][s][:, 0], z["st_x"][s0:s1][m]), (name, t, s)
+            assert np.array_equal(st["xy"][s][:, 1], z["st_y"][s0:s1][m]), (name, t, s)
+            assert np.array_equal(st["energy"][s], z["st_e"][s0:s1][m]), (name, t, s)
+        assert np.array_equal(st["grass_energy"], z["grass_e"][t]), (name, t)
+        assert np.array_equal(sha_f64([o.read_grid(0)]), z["grid_sha"][t]), (name, t)
+        g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
+        ags, agi = o.env_agents(0)
+        assert list(ags) == list(z["ag_s"][g0:g1]) and list(agi) == list(z["ag_id"][g0:g1]), (name, t)
+    assert int(out["env_status"][0]) == 0
+    o.close()
