@@ -1,0 +1,523 @@
+// ppg_api.cu — the C-ABI of include/ppg.h over the CUDA kernels (host side, no torch).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ppg_device.cuh"
+
+namespace ppg {
+cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
+cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, int32_t* off0, int32_t* off1, int slot, cudaStream_t s);
+cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
+cudaError_t launch_relabel_rows(const StepParams& p, cudaStream_t s);
+cudaError_t launch_mark_reset(EnvHdr* hdr, int B, const unsigned long long* seeds, const uint8_t* mask, cudaStream_t s);
+cudaError_t launch_set_tape(EnvHdr* hdr, int B, const long long* cell_off, cudaStream_t s);
+cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1,
+                                  const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
+                                  unsigned n_actions, int blocks, cudaStream_t s);
+cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s);
+}  // namespace ppg
+
+using namespace ppg;
+
+struct ppg_handle_s {
+  ppg_config cfg;
+  int B = 0, device = 0;
+  StepParams P;
+  int warps_per_cta = 4, n_cta = 0;
+  size_t smem_bytes = 0;
+  unsigned long long launches_step = 0;  // step-kernel launches so far (ticket base / epoch)
+  unsigned long long calls = 0;          // ppg_reset(all)/ppg_step calls (ppg_random_actions key)
+  int64_t launch_count = 0;
+  std::vector<void*> allocs;
+  unsigned long long* d_stats = nullptr;
+  int32_t* d_tape_cells = nullptr;
+  long long* d_tape_off = nullptr;
+  uint8_t* d_mask = nullptr;
+  unsigned long long* d_seeds = nullptr;
+  int32_t* d_act[2] = {nullptr, nullptr};  // staging for ppg_step_host
+  int32_t h_n_rows[4] = {0, 0, 0, 0};
+  bool h_n_rows_valid = false;
+  ppg_buffers bufs;
+  size_t state_bytes = 0;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+      return PPG_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+static cudaError_t dalloc(ppg_handle h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return e;
+}
+
+static int str_cmp_ids(const void* a, const void* b) {
+  char sa[16], sb[16];
+  snprintf(sa, sizeof sa, "%d", *(const int*)a);
+  snprintf(sb, sizeof sb, "%d", *(const int*)b);
+  return strcmp(sa, sb);
+}
+
+// rank of str(id) among the species' id strings: the order Python's list.sort() gives (BASE:468)
+static std::vector<uint16_t> lexrank_table(int n) {
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) ids[i] = i;
+  qsort(ids.data(), (size_t)n, sizeof(int), str_cmp_ids);
+  std::vector<uint16_t> r(std::max(n, 1));
+  for (int i = 0; i < n; ++i) r[ids[i]] = (uint16_t)i;
+  return r;
+}
+
+extern "C" {
+
+int ppg_abi_version(void) { return PPG_ABI_VERSION; }
+
+void ppg_default_config(ppg_config* c) {
+  memset(c, 0, sizeof *c);
+  c->struct_size = sizeof *c;
+  c->variant = PPG_VARIANT_BASE;
+  c->reward_mode = PPG_REWARD_SPARSE;
+  c->grid_size = 25; c->max_steps = 1000; c->num_obs_channels = 4;
+  c->obs_range[0] = 7; c->obs_range[1] = 9;
+  c->n_possible[0] = 2000; c->n_possible[1] = 2000;
+  c->n_initial[0] = 6; c->n_initial[1] = 8;
+  c->n_grass = 100;
+  c->cap_live[0] = 64; c->cap_live[1] = 192;
+  c->autoreset = 1;
+  c->energy_loss[0] = 0.15; c->energy_loss[1] = 0.05;
+  c->creation_threshold[0] = 12.0; c->creation_threshold[1] = 8.0;
+  c->initial_energy[0] = 5.0; c->initial_energy[1] = 3.0;
+  c->initial_energy_grass = 2.0; c->energy_gain_grass = 0.04;
+  c->reproduction_reward[0] = 10.0; c->reproduction_reward[1] = 10.0;
+  c->kickback_reward[0] = 10.0; c->kickback_reward[1] = 10.0;
+  c->seed = 0;
+}
+
+const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
+  if (!c || c->struct_size != sizeof(ppg_config)) { err = "ppg_config.struct_size mismatch"; return PPG_ERR_INVALID; }
+  if (n_envs <= 0) { err = "n_envs must be positive"; return PPG_ERR_INVALID; }
+  if (c->variant != PPG_VARIANT_BASE) { err = "variant not supported by this build"; return PPG_ERR_INVALID; }
+  if (c->reward_mode < 0 || c->reward_mode > PPG_REWARD_SPARSE_KICKBACK) { err = "bad reward_mode"; return PPG_ERR_INVALID; }
+  if (c->grid_size < 2 || c->grid_size > 255) { err = "grid_size must be in [2,255]"; return PPG_ERR_INVALID; }
+  if (c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
+  for (int s = 0; s < 2; ++s) {
+    if (c->obs_range[s] < 1 || (c->obs_range[s] & 1) == 0 || c->obs_range[s] > 255) { err = "obs_range must be odd"; return PPG_ERR_INVALID; }
+    if (c->num_obs_channels * c->obs_range[s] * c->obs_range[s] > 4 * 128) { err = "observation row too large for this build"; return PPG_ERR_INVALID; }
+    if (c->n_possible[s] < c->n_initial[s] || c->n_possible[s] > 65535) { err = "n_possible out of range"; return PPG_ERR_INVALID; }
+    if (c->cap_live[s] < c->n_initial[s] || c->cap_live[s] <= 0 || c->cap_live[s] > 32768) { err = "cap_live out of range"; return PPG_ERR_INVALID; }
+    if (c->n_initial[s] < 0) { err = "n_initial negative"; return PPG_ERR_INVALID; }
+  }
+  if (c->n_grass < 0 || c->n_grass > 254) { err = "n_grass must be in [0,254]"; return PPG_ERR_INVALID; }
+  // "Cannot place more unique positions than grid cells." (BASE:167-168)
+  if (c->n_initial[0] + c->n_initial[1] + c->n_grass > c->grid_size * c->grid_size) { err = "Cannot place more unique positions than grid cells."; return PPG_ERR_INVALID; }
+  return PPG_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle* out) {
+  if (!out) return PPG_ERR_INVALID;
+  *out = nullptr;
+  int rc = validate(cfg, n_envs, g_err);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device"; return PPG_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) { g_err = "bad device index"; return PPG_ERR_INVALID; }
+  ppg_handle h = new ppg_handle_s();
+  h->cfg = *cfg;
+  h->B = n_envs;
+  h->device = device;
+  auto fail = [&](int code) { g_err = h->err; ppg_destroy(h); return code; };
+#define CKC(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(PPG_ERR_CUDA); } \
+  } while (0)
+  CKC(cudaSetDevice(device));
+  const ppg_config& c = h->cfg;
+  StepParams& P = h->P;
+  memset(&P, 0, sizeof P);
+  const int B = n_envs, G = c.grid_size, GG = G * G;
+  P.B = B; P.G = G; P.GG = GG; P.C = c.num_obs_channels;
+  for (int s = 0; s < 2; ++s) {
+    P.R[s] = c.obs_range[s]; P.off[s] = (c.obs_range[s] - 1) / 2; P.elems[s] = c.num_obs_channels * c.obs_range[s] * c.obs_range[s];
+    P.cap[s] = c.cap_live[s]; P.n_init[s] = c.n_initial[s]; P.n_possible[s] = c.n_possible[s];
+    P.loss[s] = c.energy_loss[s]; P.thr[s] = c.creation_threshold[s]; P.init_e[s] = c.initial_energy[s];
+    P.r_repro[s] = c.reproduction_reward[s]; P.r_kick[s] = c.kickback_reward[s];
+  }
+  P.n_grass = c.n_grass; P.max_steps = c.max_steps; P.reward_mode = c.reward_mode; P.autoreset = c.autoreset;
+  P.grass_cap = c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
+  P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
+  P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;
+
+  // shared-memory layout of one env
+  size_t o = 0;
+  auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return (int)r; };
+  for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(8 * (size_t)P.cap[s], 8); }
+  P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
+  P.so_grid = take(4 * 3 * (size_t)GG, 16);
+  for (int s = 0; s < 2; ++s) {
+    P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
+    P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
+    P.so_par[s] = take(2 * (size_t)P.cap[s], 2);
+  }
+  P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
+  for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(P.cap[s], 1); }
+  P.so_gmap = take(GG, 1);
+  P.smem_per_env = (int)align_up(o, 16);
+  const size_t smem_max = 227 * 1024 - 1024;
+  if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
+  int W = 4;
+  if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
+  if (W != 1 && W != 2 && W != 4 && W != 8) W = 4;
+  while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
+  h->warps_per_cta = W;
+  h->n_cta = (B + W - 1) / W;
+  h->smem_bytes = (size_t)W * P.smem_per_env;
+
+  // state
+  CKC(dalloc(h, &P.hdr, (size_t)B));
+  for (int s = 0; s < 2; ++s) {
+    const size_t n = (size_t)B * P.cap[s];
+    CKC(dalloc(h, &P.ag_id[s], n)); CKC(dalloc(h, &P.ag_pos[s], n)); CKC(dalloc(h, &P.ag_e[s], n));
+    CKC(dalloc(h, &P.ag_prow[s], n)); CKC(dalloc(h, &P.ag_par[s], c.reward_mode == PPG_REWARD_SPARSE_KICKBACK ? n : 1));
+    std::vector<uint16_t> lr = lexrank_table(c.n_possible[s]);
+    uint16_t* d = nullptr;
+    CKC(dalloc(h, &d, lr.size()));
+    CKC(cudaMemcpy(d, lr.data(), lr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    P.lexrank[s] = d;
+    CKC(dalloc(h, &P.next_off[s], (size_t)B + 3));
+  }
+  CKC(dalloc(h, &P.gr_pos, (size_t)B * std::max(1, P.n_grass)));
+  CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
+  CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
+  CKC(dalloc(h, &P.desc, (size_t)h->n_cta * 4));
+  CKC(dalloc(h, &P.ticket, 1));
+  CKC(dalloc(h, &P.error, 1));
+  CKC(dalloc(h, &h->d_stats, PPG_N_STATS));
+  CKC(dalloc(h, &h->d_mask, (size_t)B));
+  CKC(dalloc(h, &h->d_seeds, (size_t)B));
+  // outputs
+  ppg_buffers& b = h->bufs;
+  memset(&b, 0, sizeof b);
+  for (int s = 0; s < 2; ++s) {
+    const size_t rows = (size_t)B * P.cap[s];
+    b.row_capacity[s] = (int64_t)rows;
+    b.obs_row_elems[s] = P.elems[s];
+    void* q = nullptr;
+    CKC(cudaMalloc(&q, rows * (size_t)P.elems[s] * sizeof(float)));  // not cleared: only valid rows are ever read
+    h->allocs.push_back(q);
+    P.obs[s] = b.obs[s] = static_cast<float*>(q);
+    CKC(dalloc(h, &P.row_env[s], rows)); CKC(dalloc(h, &P.row_agent[s], rows));
+    CKC(dalloc(h, &P.reward[s], rows)); CKC(dalloc(h, &P.flags[s], rows));
+    CKC(dalloc(h, &P.old_off[s], (size_t)B + 1)); CKC(dalloc(h, &P.new_off[s], (size_t)B + 1));
+    CKC(dalloc(h, &h->d_act[s], rows));
+    b.row_env[s] = P.row_env[s]; b.row_agent[s] = P.row_agent[s]; b.reward[s] = P.reward[s]; b.flags[s] = P.flags[s];
+    b.old_off[s] = P.old_off[s]; b.new_off[s] = P.new_off[s];
+  }
+  CKC(dalloc(h, &P.n_rows, 4)); CKC(dalloc(h, &P.env_flags, (size_t)B)); CKC(dalloc(h, &P.env_status, (size_t)B));
+  CKC(dalloc(h, &P.env_step, (size_t)B)); CKC(dalloc(h, &P.env_count, (size_t)B * 2));
+  b.n_rows = P.n_rows; b.env_flags = P.env_flags; b.env_status = P.env_status; b.env_step = P.env_step; b.env_count = P.env_count;
+  b.n_envs = B;
+  CKC(launch_init_hdr(P.hdr, B, c.seed, 0));
+  h->launch_count++;
+  CKC(cudaDeviceSynchronize());
+  *out = h;
+  return PPG_OK;
+#undef CKC
+}
+
+int ppg_destroy(ppg_handle h) {
+  if (!h) return PPG_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->d_tape_cells) cudaFree(h->d_tape_cells);
+  if (h->d_tape_off) cudaFree(h->d_tape_off);
+  delete h;
+  return PPG_OK;
+}
+
+int ppg_load_tape(ppg_handle h, const ppg_tape* t) {
+  if (!h) return PPG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  if (h->d_tape_cells) { cudaFree(h->d_tape_cells); h->d_tape_cells = nullptr; }
+  if (h->d_tape_off) { cudaFree(h->d_tape_off); h->d_tape_off = nullptr; }
+  h->P.tape_cells = nullptr;
+  if (t && t->cells && t->cell_off) {
+    const int64_t total = t->cell_off[h->B];
+    CK(cudaMalloc(&h->d_tape_cells, sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1)));
+    CK(cudaMalloc(&h->d_tape_off, sizeof(long long) * ((size_t)h->B + 1)));
+    CK(cudaMemcpy(h->d_tape_cells, t->cells, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_tape_off, t->cell_off, sizeof(long long) * ((size_t)h->B + 1), cudaMemcpyHostToDevice));
+    h->P.tape_cells = h->d_tape_cells;
+  }
+  CK(launch_set_tape(h->P.hdr, h->B, h->d_tape_off, 0));
+  h->launch_count++;
+  CK(cudaDeviceSynchronize());
+  return PPG_OK;
+}
+
+static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, cudaStream_t st) {
+  StepParams& P = h->P;
+  P.actions[0] = a0; P.actions[1] = a1;
+  P.ticket_base = h->launches_step * (unsigned long long)h->n_cta;
+  P.epoch = (unsigned)(h->launches_step + 1);
+  CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
+  h->launches_step++;
+  h->launch_count++;
+  h->calls++;
+  h->h_n_rows_valid = false;
+  return PPG_OK;
+}
+
+int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cuda_stream) {
+  if (!h) return PPG_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  const unsigned long long* dseeds = nullptr;
+  if (seeds) { CK(cudaMemcpyAsync(h->d_seeds, seeds, sizeof(uint64_t) * (size_t)h->B, cudaMemcpyHostToDevice, st)); dseeds = h->d_seeds; }
+  const uint8_t* dmask = nullptr;
+  if (mask) { CK(cudaMemcpyAsync(h->d_mask, mask, (size_t)h->B, cudaMemcpyHostToDevice, st)); dmask = h->d_mask; }
+  CK(launch_mark_reset(h->P.hdr, h->B, dseeds, dmask, st));
+  // first-old-row offsets of the next output: totals slot = parity of the next launch's epoch
+  CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.next_off[0], h->P.next_off[1],
+                            (int)((h->launches_step + 1) & 1), st));
+  h->launch_count += 2;
+  if (mask) return PPG_OK;  // partial reset: performed by the next ppg_step
+  int rc = run_step_kernel(h, nullptr, nullptr, st);
+  if (rc) return rc;
+  h->h_n_rows[0] = h->B * h->P.n_init[0]; h->h_n_rows[1] = h->B * h->P.n_init[1];
+  h->h_n_rows[2] = h->h_n_rows[3] = 0;
+  h->h_n_rows_valid = true;
+  return PPG_OK;
+}
+
+int ppg_step(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, void* cuda_stream) {
+  if (!h) return PPG_ERR_INVALID;
+  if (!actions_pred || !actions_prey) { h->err = "ppg_step: NULL actions"; return PPG_ERR_INVALID; }
+  if (h->launches_step == 0) { h->err = "ppg_step before ppg_reset"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  return run_step_kernel(h, actions_pred, actions_prey, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, ppg_buffers* out,
+                  int32_t* n_rows_out, void* cuda_stream) {
+  if (!h || !out) return PPG_ERR_INVALID;
+  if (h->launches_step == 0) { h->err = "ppg_step_host before ppg_reset"; return PPG_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  if (!h->h_n_rows_valid) {
+    CK(cudaMemcpyAsync(h->h_n_rows, h->P.n_rows, sizeof h->h_n_rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  const int32_t* src[2] = {actions_pred, actions_prey};
+  for (int s = 0; s < 2; ++s) {
+    const size_t n = (size_t)h->h_n_rows[s] + (size_t)h->h_n_rows[2 + s];
+    if (n) CK(cudaMemcpyAsync(h->d_act[s], src[s], n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  int rc = run_step_kernel(h, h->d_act[0], h->d_act[1], st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_n_rows, h->P.n_rows, sizeof h->h_n_rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->h_n_rows_valid = true;
+  for (int s = 0; s < 2; ++s) {
+    const size_t n = (size_t)h->h_n_rows[s] + (size_t)h->h_n_rows[2 + s];
+    if ((int64_t)n > out->row_capacity[s]) { h->err = "ppg_step_host: host row_capacity too small"; return PPG_ERR_INVALID; }
+    if (n) {
+      if (out->obs[s]) CK(cudaMemcpyAsync(out->obs[s], h->P.obs[s], n * (size_t)h->P.elems[s] * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (out->row_env[s]) CK(cudaMemcpyAsync(out->row_env[s], h->P.row_env[s], n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (out->row_agent[s]) CK(cudaMemcpyAsync(out->row_agent[s], h->P.row_agent[s], n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (out->reward[s]) CK(cudaMemcpyAsync(out->reward[s], h->P.reward[s], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (out->flags[s]) CK(cudaMemcpyAsync(out->flags[s], h->P.flags[s], n, cudaMemcpyDeviceToHost, st));
+    }
+    if (out->old_off[s]) CK(cudaMemcpyAsync(out->old_off[s], h->P.old_off[s], ((size_t)h->B + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out->new_off[s]) CK(cudaMemcpyAsync(out->new_off[s], h->P.new_off[s], ((size_t)h->B + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (out->env_flags) CK(cudaMemcpyAsync(out->env_flags, h->P.env_flags, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+  if (out->env_status) CK(cudaMemcpyAsync(out->env_status, h->P.env_status, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+  if (out->env_step) CK(cudaMemcpyAsync(out->env_step, h->P.env_step, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out->env_count) CK(cudaMemcpyAsync(out->env_count, h->P.env_count, (size_t)h->B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_rows_out) memcpy(n_rows_out, h->h_n_rows, sizeof h->h_n_rows);
+  if (out->n_rows) memcpy(out->n_rows, h->h_n_rows, sizeof h->h_n_rows);
+  return PPG_OK;
+}
+
+int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32_t* actions_prey, void* cuda_stream) {
+  if (!h || !actions_pred || !actions_prey) return PPG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const StepParams& P = h->P;
+  CK(launch_random_actions(P.n_rows, P.row_env[0], P.row_agent[0], P.row_env[1], P.row_agent[1], actions_pred, actions_prey,
+                           seed, (unsigned)h->calls, 9u, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
+  h->launch_count++;
+  return PPG_OK;
+}
+
+int ppg_get_buffers(ppg_handle h, ppg_buffers* out) {
+  if (!h || !out) return PPG_ERR_INVALID;
+  *out = h->bufs;
+  return PPG_OK;
+}
+
+// ---- snapshot / restore: the SoA slab as one host blob -----------------------------------------
+struct Seg { void* p; size_t bytes; };
+static std::vector<Seg> state_segments(ppg_handle h) {
+  const StepParams& P = h->P;
+  std::vector<Seg> v;
+  v.push_back({P.hdr, sizeof(EnvHdr) * (size_t)h->B});
+  for (int s = 0; s < 2; ++s) {
+    const size_t n = (size_t)h->B * P.cap[s];
+    v.push_back({P.ag_id[s], n * 2}); v.push_back({P.ag_pos[s], n * 2}); v.push_back({P.ag_e[s], n * 8});
+    v.push_back({P.ag_prow[s], n * 4});
+    if (P.reward_mode == PPG_REWARD_SPARSE_KICKBACK) v.push_back({P.ag_par[s], n * 2});
+  }
+  v.push_back({P.gr_pos, (size_t)h->B * std::max(1, P.n_grass) * 2});
+  v.push_back({P.gr_e, (size_t)h->B * std::max(1, P.n_grass) * 8});
+  v.push_back({P.counters, (size_t)h->B * PPG_N_STATS * 4});
+  return v;
+}
+
+size_t ppg_snapshot_size(ppg_handle h) {
+  if (!h) return 0;
+  size_t t = 16;
+  for (const Seg& s : state_segments(h)) t += s.bytes;
+  return t;
+}
+
+int ppg_snapshot(ppg_handle h, void* blob, size_t bytes, void* cuda_stream) {
+  if (!h || !blob || bytes < ppg_snapshot_size(h)) return PPG_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  char* q = static_cast<char*>(blob);
+  unsigned long long head[2] = {h->calls, 0x50504753ULL};
+  memcpy(q, head, 16);
+  q += 16;
+  for (const Seg& s : state_segments(h)) { CK(cudaMemcpyAsync(q, s.p, s.bytes, cudaMemcpyDeviceToHost, st)); q += s.bytes; }
+  CK(cudaStreamSynchronize(st));
+  return PPG_OK;
+}
+
+int ppg_restore(ppg_handle h, const void* blob, size_t bytes, void* cuda_stream) {
+  if (!h || !blob || bytes < ppg_snapshot_size(h)) return PPG_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  const char* q = static_cast<const char*>(blob);
+  unsigned long long head[2];
+  memcpy(head, q, 16);
+  if (head[1] != 0x50504753ULL) { h->err = "ppg_restore: not a snapshot blob"; return PPG_ERR_INVALID; }
+  h->calls = head[0];
+  q += 16;
+  for (const Seg& s : state_segments(h)) { CK(cudaMemcpyAsync(s.p, q, s.bytes, cudaMemcpyHostToDevice, st)); q += s.bytes; }
+  CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.next_off[0], h->P.next_off[1],
+                            (int)((h->launches_step + 1) & 1), st));
+  CK(launch_relabel_rows(h->P, st));
+  h->launch_count += 2;
+  CK(cudaStreamSynchronize(st));
+  h->h_n_rows_valid = false;
+  return PPG_OK;
+}
+
+int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, int32_t* xy_pred, double* energy_pred,
+                 int32_t* ids_prey, int32_t* xy_prey, double* energy_prey, int32_t* xy_grass, double* energy_grass) {
+  if (!h || env < 0 || env >= h->B || !n_live) return PPG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const StepParams& P = h->P;
+  EnvHdr hd;
+  CK(cudaMemcpy(&hd, P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
+  int32_t* ids[2] = {ids_pred, ids_prey};
+  int32_t* xy[2] = {xy_pred, xy_prey};
+  double* en[2] = {energy_pred, energy_prey};
+  for (int s = 0; s < 2; ++s) {
+    const int n = hd.n_list[s];
+    n_live[s] = n;
+    std::vector<uint16_t> id(std::max(n, 1)), pos(std::max(n, 1));
+    std::vector<double> e(std::max(n, 1));
+    const size_t b = (size_t)env * P.cap[s];
+    if (n) {
+      CK(cudaMemcpy(id.data(), P.ag_id[s] + b, n * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(pos.data(), P.ag_pos[s] + b, n * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(e.data(), P.ag_e[s] + b, n * 8, cudaMemcpyDeviceToHost));
+    }
+    // report in agent_positions insertion order = ascending id (BASE:190-200,401)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b2) { return id[a] < id[b2]; });
+    for (int i = 0; i < n; ++i) {
+      const int j = order[i];
+      if (ids[s]) ids[s][i] = id[j];
+      if (xy[s]) { xy[s][2 * i] = pos[j] >> 8; xy[s][2 * i + 1] = pos[j] & 255; }
+      if (en[s]) en[s][i] = e[j];
+    }
+  }
+  const int ng = P.n_grass;
+  if (ng) {
+    std::vector<uint16_t> gp(ng);
+    std::vector<double> ge(ng);
+    CK(cudaMemcpy(gp.data(), P.gr_pos + (size_t)env * ng, ng * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ge.data(), P.gr_e + (size_t)env * ng, ng * 8, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < ng; ++g) {
+      if (xy_grass) { xy_grass[2 * g] = gp[g] >> 8; xy_grass[2 * g + 1] = gp[g] & 255; }
+      if (energy_grass) energy_grass[g] = ge[g];
+    }
+  }
+  return PPG_OK;
+}
+
+int ppg_stats_device(ppg_handle h, int64_t** dev_out, void* cuda_stream) {
+  if (!h || !dev_out) return PPG_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * PPG_N_STATS, st));
+  CK(launch_stats(h->P.counters, h->P.hdr, h->B, h->d_stats, st));
+  h->launch_count++;
+  *dev_out = reinterpret_cast<int64_t*>(h->d_stats);
+  return PPG_OK;
+}
+
+int ppg_stats(ppg_handle h, int64_t* out, void* cuda_stream) {
+  if (!h || !out) return PPG_ERR_INVALID;
+  int64_t* d = nullptr;
+  int rc = ppg_stats_device(h, &d, cuda_stream);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaMemcpyAsync(out, d, sizeof(int64_t) * PPG_N_STATS, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  unsigned err = 0;
+  CK(cudaMemcpy(&err, h->P.error, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) { h->err = "device error word set (row allocation look-back wedged)"; return PPG_ERR_STATE; }
+  return PPG_OK;
+}
+
+int ppg_stats_clear(ppg_handle h, void* cuda_stream) {
+  if (!h) return PPG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->P.counters, 0, (size_t)h->B * PPG_N_STATS * sizeof(uint32_t), static_cast<cudaStream_t>(cuda_stream)));
+  return PPG_OK;
+}
+
+int64_t ppg_launch_count(ppg_handle h) { return h ? h->launch_count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// ppg_device.cuh — device-side data layout shared by the kernels and the C-ABI host code.
+//
+// Data layout in HBM (one handle = B env instances on one GPU), structure of arrays:
+//   per env          EnvHdr (64 B): step counter, list lengths, id counters, RNG/tape cursors, flags
+//   per env, species ag_id u16[cap], ag_pos u16[cap] (x<<8|y), ag_energy f64[cap], ag_prow i32[cap]
+//                    (+ ag_parent u16[cap], kickback reward only) — a COMPACT list in the reference's
+//                    `self.agents` order (BASE:73,468): position in the list = iteration order
+//   per env          gr_pos u16[n_grass], gr_energy f64[n_grass]
+//   per env          counters u32[16] (PPG_STAT_*)
+// The float64 grid of the reference (`grid_world_state`, BASE:124) is NOT stored: it is rebuilt in
+// shared memory (fp32) at the start of every step from the lists (see DESIGN.md "grid rebuild").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ppg.h"
+#include "../../include/ppg_philox.h"
+
+namespace ppg {
+
+struct __align__(16) EnvHdr {
+  unsigned long long seed_key;  // Philox key of this env (ppg_reset seeds)
+  long long tape_pos, tape_end; // replay-tape cursor into tape_cells
+  int step;                     // current_step (BASE:134,471)
+  unsigned episode;             // Philox counter word
+  unsigned spawn_draws;         // Philox draw index of the spawn-fallback stream
+  unsigned short n_list[2];     // live agents per species = list length
+  unsigned short next_idx[2];   // _next_predator_idx / _next_prey_idx (BASE:66-67)
+  unsigned char state;          // ST_*
+  unsigned char status;         // PPG_STATUS_* (sticky until reset)
+  unsigned char sortflag;       // bit s: list of species s is not in lexicographic order yet
+  unsigned char first_step;     // 1 right after reset(): engagement order is the founders' numeric order
+  int pad[3];
+};
+static_assert(sizeof(EnvHdr) == 64, "EnvHdr must be 64 bytes");
+
+enum : unsigned char { ST_NEEDS_RESET = 1, ST_IDLE = 2 };
+
+// per-slot flag bits, shared memory only
+enum : unsigned char {
+  F_ALIVE = 1,    // in agent_positions
+  F_DIED = 2,     // terminated this step
+  F_ATE = 4,      // agents_just_ate
+  F_REPRO = 8,    // reproduced this step
+  F_NEWBORN = 16, // born this step
+  F_CAUGHT = 32   // died by being eaten (reward differs from starvation)
+};
+
+struct StepParams {
+  // ---- config ----
+  int B, G, GG, C;
+  int R[2], off[2], elems[2];
+  int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
+  double loss[2], thr[2], init_e[2], grass_cap, grass_gain;
+  double r_catch, r_eat, r_pstep, r_qstep, pen_caught, r_repro[2], r_kick[2];
+  // ---- state ----
+  EnvHdr* hdr;
+  uint16_t* ag_id[2];
+  uint16_t* ag_pos[2];
+  double* ag_e[2];
+  int32_t* ag_prow[2];
+  uint16_t* ag_par[2];
+  uint16_t* gr_pos;
+  double* gr_e;
+  const uint16_t* lexrank[2];
+  const int32_t* tape_cells;
+  uint32_t* counters;  // [B][PPG_N_STATS]
+  // ---- cross-CTA row allocation (decoupled look-back) ----
+  unsigned long long* desc;  // [n_cta][4]
+  unsigned long long* ticket;
+  unsigned long long ticket_base;
+  unsigned epoch;
+  unsigned* error;  // device error word (bit0: look-back wedged)
+  int32_t* next_off[2];  // [s] -> [B+3]: first old row of each env in the NEXT output; [B+1],[B+2] = totals (ping-pong by epoch parity)
+  // ---- io ----
+  const int32_t* actions[2];
+  float* obs[2];
+  int32_t* row_env[2];
+  int32_t* row_agent[2];
+  float* reward[2];
+  uint8_t* flags[2];
+  int32_t* old_off[2];
+  int32_t* new_off[2];
+  int32_t* n_rows;
+  uint8_t* env_flags;
+  uint8_t* env_status;
+  int32_t* env_step;
+  int32_t* env_count;
+  // ---- shared-memory layout, byte offsets inside one env's region ----
+  int so_E[2], so_E0[2], so_gE, so_grid, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2], so_gpos;
+  int so_act[2], so_flg[2], so_aux[2], so_gmap;
+  int smem_per_env;
+};
+
+}  // namespace ppg
