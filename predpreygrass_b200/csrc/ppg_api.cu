@@ -186,7 +186,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(P.cap[s], 1); }
   P.so_gmap = take(GG, 1);
   P.smem_per_env = (int)align_up(o, 16);
-  const size_t smem_max = 227 * 1024 - 1024;
+  const size_t smem_max = 227 * 1024 - 2048;  // static __shared__ of the kernel comes on top
   if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
   int W = 4;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);

@@ -712,9 +712,10 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
 
   // ---------------------------------------------------------------- write the state back
   if (mode != 0) {
-    if (over) {
-      h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;
+    if (over && p.autoreset) {
+      h.state = ST_NEEDS_RESET;  // the lists are dead: the next call resets the env
     } else {
+      if (over) h.state = ST_IDLE;  // final state stays readable (renderers, ppg_read_env)
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const size_t b = (size_t)env * p.cap[s];
@@ -908,11 +909,11 @@ __global__ void ppg_stats_kernel(const uint32_t* __restrict__ counters, const En
 // ------------------------------------------------------------------------------------------------
 template <int W>
 static cudaError_t launch_w(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static size_t attr_bytes = 0;  // opt in to > 48 KB of dynamic shared memory (grows monotonically)
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_bytes = smem;
   }
   ppg_step_base_kernel<W><<<n_cta, W * 32, smem, stream>>>(p);
   return cudaGetLastError();

@@ -86,6 +86,7 @@ def lockstep_parity(cfg, n_envs, steps, *, tape=None, seeds=None, action_seed=12
                 continue
             assert gs[k] == os_[k], (k, gs[k], os_[k])
         torch.cuda.synchronize()
+        gs["status_or"] = int(np.bitwise_or.reduce(ora.outputs()["env_status"]))
         return gs
     finally:
         gpu.close()

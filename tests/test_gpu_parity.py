@@ -30,7 +30,7 @@ def test_replay_4096_envs_300_steps():
     every output array of every step compared with the oracle."""
     cfg = make_config(BASE_CONFIG, cap_live=(64, 192), seed=11)
     st = lockstep_parity(cfg, 4096, 300, tape=_reset_tape(4096), state_envs=(0, 1000, 4095), check_every=1)
-    assert st["status_envs"] == 0
+    assert st["status_or"] & ~4 == 0  # only TAPE_EXHAUSTED (second episodes run on the Philox stream)
     assert st["env_steps"] > 4096 * 250
 
 
