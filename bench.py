@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s (incl. observation generation) of the batched PredPreyGrass env step.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, for N > 1
+launched under torchrun (one rank per GPU).  Prints ONE JSON line on rank 0.
+
+A "step" is one lockstep `step()` of every env instance the rank owns (BASELINE configs[1]:
+base_environment, 4096 envs per GPU, uniform random actions from the device-side Philox action
+generator, auto-reset).  `value` = agent-steps/s over all ranks with everything resident in HBM;
+`e2e` = the same through `ppg_step_host` (actions from pinned host memory, whole row batch copied
+back to pinned host memory every step).  `roofline` is the step kernel's algorithmic bytes over its
+CUDA-event duration against MEASURED_PEAKS.json.  `cpu_baseline` is the CPU oracle (a C port of the
+reference's Python step; the Python reference itself cannot travel to the GPU box) on host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent_steps_per_s_incl_obs"
+UNIT = "agent-steps/s"
+S_AGENT = 42  # bytes of per-agent state + io per agent-step: pos 2 + energy 8 + id 4 (read+write = 28), action 4, reward 4 + flags 2 + id 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="env instances per GPU (BASELINE configs[1])")
+    ap.add_argument("--reward-mode", default="sparse")
+    ap.add_argument("--cap", type=int, nargs=2, default=[64, 192])
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-envs", type=int, default=512)
+    ap.add_argument("--cpu-steps", type=int, default=150)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return f"base_environment default config_env, {args.envs} envs per GPU, uniform random actions, auto-reset, reward={args.reward_mode}"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(args, threads, steps, warmup):
+    """agent-steps/s of the CPU oracle (C port of the reference step) on `threads` host threads."""
+    import numpy as np
+
+    from oracle.oracle import Oracle
+    from predpreygrass_b200.config import BASE_CONFIG, make_config
+
+    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=12345)
+    o = Oracle(cfg, args.cpu_envs, threads=threads)
+    o.reset()
+    rng = np.random.default_rng(0)
+    pool = rng.integers(0, 9, size=args.cpu_envs * (args.cap[0] + args.cap[1]) + 16, dtype=np.int32)
+
+    def run(k):
+        t = 0.0
+        for _ in range(k):
+            t0 = time.perf_counter()
+            o.step(pool, pool)  # any action value is valid for any row; sampling is not timed
+            t += time.perf_counter() - t0
+        return t
+
+    run(warmup)
+    s0 = o.stats()
+    dt = run(steps)
+    s1 = o.stats()
+    o.close()
+    agent_steps = int(s1[1] - s0[1])
+    env_steps = int(s1[0] - s0[0])
+    return agent_steps / dt, env_steps / dt, dt
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, env_rate, dt = cpu_oracle_rate(args, threads, args.steps, max(3, args.warmup))
+    sample = f"{args.cpu_envs} envs x {args.steps} steps of the same workload, {threads} threads (envs partitioned over threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "reference arm = CPU oracle (C port of the reference's Python step; the Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "env_steps_per_s": env_rate, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return main_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from predpreygrass_b200.batched import BatchedPredPreyGrass
+    from predpreygrass_b200.config import BASE_CONFIG, STAT_NAMES, make_config
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(3, args.warmup), args.steps
+
+    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=1000 + rank)
+    env = BatchedPredPreyGrass(cfg, args.envs, device=local_rank)
+    env.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rollout(k):
+        for _ in range(k):
+            a0, a1 = env.random_actions(4242)
+            env.step(a0, a1)
+
+    rollout(W)
+    stats0 = env.stats_device().clone()
+    launches0 = env.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    rollout(K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = env.launch_count() - launches0
+    stats1 = env.stats_device().clone()
+    d = (stats1 - stats0).to(torch.float64)  # this rank's env/agent steps, rows, births... in the timed region
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        # the one collective of this path: the small all-reduce of episode/population statistics
+        dist.all_reduce(d, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    tot = dict(zip(STAT_NAMES, d.tolist()))
+    value = tot["agent_steps"] / (ms_max * 1e-3)
+    env_rate = tot["env_steps"] / (ms_max * 1e-3)
+
+    # ---- step kernel alone: CUDA events around each step launch (same stream), rank-local
+    KR = min(K, 200)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KR)]
+    sk0 = env.stats_device().clone()
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a0, a1 = env.random_actions(4242)
+        a.record()
+        env.step(a0, a1)
+        b.record()
+    torch.cuda.synchronize()
+    sk1 = env.stats_device().clone()
+    kd = dict(zip(STAT_NAMES, (sk1 - sk0).tolist()))
+    k_ms = sum(a.elapsed_time(b) for a, b in evs) / KR
+    row_bytes = [4 * cfg.num_obs_channels * cfg.obs_range[s] ** 2 for s in range(2)]
+    alg_bytes = (kd["rows_pred"] * row_bytes[0] + kd["rows_prey"] * row_bytes[1] + kd["agent_steps"] * S_AGENT
+                 + kd["env_steps"] * (cfg.n_grass * 16 + 64)) / KR
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "ppg_step_base_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+
+    # ---- e2e through the C-ABI with host buffers (rank-local rate, summed over ranks)
+    e2e = None
+    if not args.no_e2e:
+        host = env.make_host_buffers(pinned=True)
+        pool = torch.randint(0, 9, (max(env.row_capacity) + 4096,), dtype=torch.int32).pin_memory()
+        h2d = d2h = 0
+        n0, n1 = env.out.counts()
+        e0 = env.stats_device().clone()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            off = (i * 61) % 4096
+            host["actions0"][:n0].copy_(pool[off:off + n0])  # host->pinned staging of this step's inputs
+            host["actions1"][:n1].copy_(pool[off:off + n1])
+            h2d += 4 * (n0 + n1)
+            n0, n1 = env.step_host(host)
+            d2h += n0 * (row_bytes[0] + 13) + n1 * (row_bytes[1] + 13) + 4 * (args.envs + 1) * 4 + args.envs * 14 + 16
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e1 = env.stats_device().clone()
+        ed = (e1 - e0).to(torch.float64)
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ed, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(ed[1].item()) / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d // args.e2e_steps,
+               "d2h_bytes_per_step": d2h // args.e2e_steps, "steps": args.e2e_steps,
+               "api": "ppg_step_host (pinned host actions in, full row batch incl. observations out)"}
+
+    final = env.stats()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r, er, dt = cpu_oracle_rate(args, threads, args.cpu_steps, 20)
+        cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_envs} envs x {args.cpu_steps} steps of the same workload ({dt:.1f} s), oracle/ C port of the reference step, {threads} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "cap_live": args.cap,
+                       "l2": "each step writes ~%.0f MB of observation rows (> 126 MB L2) to fresh addresses; no explicit flush" % (alg_bytes / 1e6),
+                       "state": "fp64 energies in HBM, fp32 observations/rewards out"},
+            "env_steps_per_s": env_rate,
+            "mean_live_agents_per_env": tot["agent_steps"] / max(tot["env_steps"], 1.0),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "status_envs": final["status_envs"],
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,7 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   for (int s = 0; s < 2; ++s) {
     if (c->obs_range[s] < 1 || (c->obs_range[s] & 1) == 0 || c->obs_range[s] > 255) { err = "obs_range must be odd"; return PPG_ERR_INVALID; }
     if (c->num_obs_channels * c->obs_range[s] * c->obs_range[s] > 4 * 128) { err = "observation row too large for this build"; return PPG_ERR_INVALID; }
+    if (((c->obs_range[s] - 1) / 2) * (c->grid_size + c->obs_range[s]) > 32000) { err = "observation window too large"; return PPG_ERR_INVALID; }
     if (c->n_possible[s] < c->n_initial[s] || c->n_possible[s] > 65535) { err = "n_possible out of range"; return PPG_ERR_INVALID; }
     if (c->cap_live[s] < c->n_initial[s] || c->cap_live[s] <= 0 || c->cap_live[s] > 32768) { err = "cap_live out of range"; return PPG_ERR_INVALID; }
     if (c->n_initial[s] < 0) { err = "n_initial negative"; return PPG_ERR_INVALID; }
@@ -171,30 +172,68 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
   P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;
 
+  // padded grid geometry (ppg_base.cu "Observation rows from the PADDED grid")
+  P.P = std::max(P.off[0], P.off[1]);
+  P.PS = G + P.P;
+  P.CH = (int)align_up((size_t)P.P + (size_t)(G + 2 * P.P) * P.PS, 4);
+  const bool dense = c.reward_mode == PPG_REWARD_DENSE || c.reward_mode == PPG_REWARD_DENSE_ADDITIVE;
+  const bool kick = c.reward_mode == PPG_REWARD_SPARSE_KICKBACK;
+
   // shared-memory layout of one env
   size_t o = 0;
   auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return (int)r; };
-  for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(8 * (size_t)P.cap[s], 8); }
+  for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(dense ? 8 * (size_t)P.cap[s] : 0, 8); }
   P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
-  P.so_grid = take(4 * 3 * (size_t)GG, 16);
+  P.so_grid = take(4 * 3 * (size_t)P.CH, 16);
+  if (3 * P.CH < GG + (P.n_init[0] + P.n_init[1] + P.n_grass)) { h->err = "internal: reset scratch does not fit the grid area"; return fail(PPG_ERR_INVALID); }
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
-    P.so_par[s] = take(2 * (size_t)P.cap[s], 2);
+    P.so_par[s] = take(kick ? 2 * (size_t)P.cap[s] : 0, 2);
   }
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
-  for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(P.cap[s], 1); }
-  P.so_gmap = take(GG, 1);
+  for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(kick ? P.cap[s] : 0, 1); }
+  P.so_gmap = take(align_up(GG, 4), 4);
   P.smem_per_env = (int)align_up(o, 16);
+  const size_t wall_bytes = 4 * (size_t)P.CH;
   const size_t smem_max = 227 * 1024 - 2048;  // static __shared__ of the kernel comes on top
-  if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
+  if ((size_t)P.smem_per_env + wall_bytes > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
   int W = 4;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
   if (W != 1 && W != 2 && W != 4 && W != 8) W = 4;
-  while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
+  while (W > 1 && (size_t)W * P.smem_per_env + wall_bytes > smem_max) W >>= 1;
   h->warps_per_cta = W;
   h->n_cta = (B + W - 1) / W;
-  h->smem_bytes = (size_t)W * P.smem_per_env;
+  h->smem_bytes = (size_t)W * P.smem_per_env + wall_bytes;
+
+  // per-lane window offsets and the channel-0 ("outside the grid") table
+  {
+    std::vector<int> rel(2 * 4 * 32 * 4, 0x7FFFFFFF);
+    for (int s = 0; s < 2; ++s) {
+      const int R = P.R[s], RR = R * R, nvec = P.elems[s] / 4;
+      for (int it = 0; it < 4; ++it)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int q = it * 32 + lane;
+          if (q >= nvec) continue;
+          for (int k = 0; k < 4; ++k) {
+            const int e = 4 * q + k, ch = e / RR, i = (e % RR) / R, j = e % R;
+            const int sp = (i - P.off[s]) * P.PS + (j - P.off[s]);
+            rel[(size_t)((s * 4 + it) * 32 + lane) * 4 + k] = (ch << 16) | (sp & 0xFFFF);
+          }
+        }
+    }
+    int* d_rel = nullptr;
+    CKC(dalloc(h, &d_rel, rel.size()));
+    CKC(cudaMemcpy(d_rel, rel.data(), rel.size() * sizeof(int), cudaMemcpyHostToDevice));
+    P.obs_rel = d_rel;
+    std::vector<float> wall((size_t)P.CH, 1.0f);
+    for (int x = 0; x < G; ++x)
+      for (int y = 0; y < G; ++y) wall[(size_t)P.P + (size_t)(x + P.P) * P.PS + y] = 0.0f;
+    float* d_wall = nullptr;
+    CKC(dalloc(h, &d_wall, wall.size()));
+    CKC(cudaMemcpy(d_wall, wall.data(), wall.size() * sizeof(float), cudaMemcpyHostToDevice));
+    P.wall_tab = d_wall;
+  }
 
   // state
   CKC(dalloc(h, &P.hdr, (size_t)B));

@@ -32,7 +32,7 @@ struct EnvSmem {
   double* E[2];
   double* E0[2];
   double* gE;
-  float* grid;  // [3][GG]: predator, prey, grass energies (channels 1..3 of BASE:123)
+  float* grid;  // [3][CH] padded: predator, prey, grass energies (channels 1..3 of BASE:123)
   uint16_t* id[2];
   uint16_t* pos[2];
   uint16_t* ord[2];  // ord[k] = slot of the k-th agent in engagement order
@@ -67,57 +67,53 @@ __device__ __forceinline__ EnvSmem carve(unsigned char* base, const StepParams& 
   return s;
 }
 
-// per-lane description of the float4 groups of an observation row this lane writes:
-// group q = it*32 + lane covers elements 4q..4q+3 of the [C][R][R] row; packed (c<<16 | i<<8 | j)
-struct ObsLanes {
-  unsigned d[2][4];
+// Observation rows from the PADDED grid.
+// The shared-memory grid of an env has a halo of P = max((R-1)/2) zero cells around the G x G
+// field, stored with row stride PS = G + P (the P-wide gap after a row doubles as the left halo of
+// the next row) and P leading pad cells:  IDX(x, y) = P + (x + P) * PS + y,  CH cells per channel.
+// A window element (c, i, j) of an agent at (x, y) is then simply  grid[c-1][IDX(x,y) + (i-off)*PS +
+// (j-off)]  with no bounds test; channel 0 ("outside the grid", BASE:522-523) reads a per-CTA
+// constant table of the same shape (1 in halo/gap cells, 0 on the field).  Per lane the relative
+// offsets of the <= 16 elements it writes are precomputed on the host (obs_rel table).
+struct RowRel {
+  int rel[4][4];   // float offset from &grid[IDX(x,y)] for float4 group `it`, element k
+  unsigned valid;  // bit it: group it*32+lane exists
 };
 
-__device__ __forceinline__ ObsLanes make_obs_lanes(const StepParams& p, int lane) {
-  ObsLanes o;
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int R = p.R[s], RR = R * R, nvec = p.elems[s] >> 2;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      int q = it * 32 + lane;
-      if (q < nvec) {
-        int e = q * 4, c = e / RR, rem = e - c * RR, i = rem / R, j = rem - i * R;
-        o.d[s][it] = (unsigned)(c << 16 | i << 8 | j);
-      } else {
-        o.d[s][it] = 0xFFFFFFFFu;
-      }
-    }
-  }
-  return o;
-}
-
-// _get_observation (BASE:511-539): one [C][R][R] fp32 row, warp-cooperative, 16-byte stores.
-// channel 0 = 1 outside the grid / 0 inside (BASE:522-523), channels 1.. = grid window (BASE:524).
-__device__ __forceinline__ void write_obs_row(float* __restrict__ dst, const float* __restrict__ grid,
-                                              int x, int y, int s, const StepParams& p,
-                                              const ObsLanes& ol, int lane) {
-  const int R = p.R[s], off = p.off[s], G = p.G, GG = p.GG;
-  const int x0 = x - off, y0 = y - off;
+__device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, int lane, int wall_delta) {
+  RowRel r;
+  r.valid = 0;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const unsigned d = s ? ol.d[1][it] : ol.d[0][it];
-    if (d != 0xFFFFFFFFu) {
-      int c = d >> 16, i = (d >> 8) & 0xFF, j = d & 0xFF;
-      float v[4];
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p.obs_rel) + (s * 4 + it) * 32 + lane);
+    const int e[4] = {v.x, v.y, v.z, v.w};
+    if (v.x != 0x7FFFFFFF) r.valid |= 1u << it;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int xi = x0 + i, yj = y0 + j;
-        const bool inb = (unsigned)xi < (unsigned)G && (unsigned)yj < (unsigned)G;
-        float val;
-        if (c == 0) val = inb ? 0.f : 1.f;
-        else val = inb ? grid[(c - 1) * GG + xi * G + yj] : 0.f;
-        v[k] = val;
-        if (++j == R) { j = 0; if (++i == R) { i = 0; ++c; } }
-      }
-      __stcs(reinterpret_cast<float4*>(dst) + (it * 32 + lane), make_float4(v[0], v[1], v[2], v[3]));
+    for (int k = 0; k < 4; ++k) {
+      const int c = e[k] >> 16, sp = (int)(short)(e[k] & 0xFFFF);
+      r.rel[it][k] = (c == 0 ? wall_delta : (c - 1) * p.CH) + sp;
     }
   }
+  return r;
+}
+
+// _get_observation (BASE:511-539): one [C][R][R] fp32 row, warp-cooperative, 16-byte streaming stores
+__device__ __forceinline__ void write_row(float* __restrict__ dst, const float* __restrict__ cell0,
+                                          const RowRel& r, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (r.valid & (1u << it)) {
+      const float4 v = make_float4(cell0[r.rel[it][0]], cell0[r.rel[it][1]], cell0[r.rel[it][2]], cell0[r.rel[it][3]]);
+      __stcs(reinterpret_cast<float4*>(dst) + (it * 32 + lane), v);
+    }
+  }
+}
+
+// rare path (rows of agents that die mid-step, BASE:287,327): same, offsets decoded on the fly
+__device__ __noinline__ void write_row_slow(float* __restrict__ dst, const float* __restrict__ cell0,
+                                            const StepParams& p, int s, int lane, int wall_delta) {
+  const RowRel r = load_rel(p, s, lane, wall_delta);
+  write_row(dst, cell0, r, lane);
 }
 
 // any live agent (either species, newborns included) on cell `pos`?  = `pos in set(agent_positions.values())` (BASE:399,754)
@@ -141,6 +137,8 @@ __device__ __forceinline__ void vstore(unsigned long long* p, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // the step kernel: W warps per CTA, one env per warp
 // ------------------------------------------------------------------------------------------------
+#define IDX(ps) (PP + (int)(((ps) >> 8) + PP) * PS + (int)((ps)&255u))
+
 template <int W>
 __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -151,14 +149,20 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_ticket = (unsigned)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+  // per-CTA constant "outside the grid" channel (BASE:522-523) in the padded layout
+  float* wall = reinterpret_cast<float*>(smem_raw + (size_t)W * p.smem_per_env);
+  for (int i = threadIdx.x; i < p.CH; i += W * 32) wall[i] = __ldg(p.wall_tab + i);
   __syncthreads();
   const unsigned cta = s_ticket;
   const int env = (int)cta * W + warp;
   const bool active = env < p.B;
   const EnvSmem S = carve(smem_raw + (size_t)warp * p.smem_per_env, p);
-  const ObsLanes ol = make_obs_lanes(p, lane);
-  const int G = p.G, GG = p.GG;
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS, CH = p.CH;
+  const int wall_delta = (int)(wall - S.grid);
   const int totals_rd = p.epoch & 1;
+  const int mode_r = p.reward_mode;
+  const bool dense = mode_r == PPG_REWARD_DENSE || mode_r == PPG_REWARD_DENSE_ADDITIVE;
+  const bool kick = mode_r == PPG_REWARD_SPARSE_KICKBACK;
 
   // per-env registers (warp-uniform)
   int n[2] = {0, 0};        // list length at step start (= old rows)
@@ -168,9 +172,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
   int mode = 0;             // 0 none/idle, 1 reset, 2 step
   EnvHdr h;
   unsigned env_flags = 0;
-  unsigned st[PPG_N_STATS];
-#pragma unroll
-  for (int k = 0; k < PPG_N_STATS; ++k) st[k] = 0;
+  unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
   int cur[2] = {0, 0};
   bool over = false, trunc = false;
 
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     h.state = 0;
     const int n_total = p.n_init[0] + p.n_init[1] + p.n_grass;
     // cells in the order predators, prey, grass (BASE:185-187); staged in the (not yet built) grid area
-    int* cells = reinterpret_cast<int*>(S.grid);             // [n_total] fits: n_total <= GG
+    int* cells = reinterpret_cast<int*>(S.grid);                 // [n_total], n_total <= GG
     unsigned* first = reinterpret_cast<unsigned*>(S.grid) + GG;  // [GG] draw index that claimed the cell
     bool from_tape = false;
     if (p.tape_cells != nullptr) {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           S.pos[s][i] = (uint16_t)(((c / G) << 8) | (c % G));
           S.E[s][i] = p.init_e[s];
           S.flg[s][i] = F_ALIVE;
-          S.par[s][i] = 0xFFFF;
+          if (kick) S.par[s][i] = 0xFFFF;
           S.ord[s][i] = (uint16_t)i;
         }
         k0 += p.n_init[s];
@@ -265,18 +267,12 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     }
     __syncwarp();
     // build the grid (BASE:195,200,208)
-    for (int i = lane; i < 3 * GG; i += 32) S.grid[i] = 0.f;
+    for (int i = lane; i < (3 * CH) / 4; i += 32) reinterpret_cast<float4*>(S.grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < 2; ++s)
-      for (int i = lane; i < n[s]; i += 32) {
-        const unsigned ps = S.pos[s][i];
-        S.grid[s * GG + (ps >> 8) * G + (ps & 255)] = (float)p.init_e[s];
-      }
-    for (int g = lane; g < p.n_grass; g += 32) {
-      const unsigned ps = S.gpos[g];
-      S.grid[2 * GG + (ps >> 8) * G + (ps & 255)] = (float)p.grass_cap;
-    }
+      for (int i = lane; i < n[s]; i += 32) S.grid[s * CH + IDX((unsigned)S.pos[s][i])] = (float)p.init_e[s];
+    for (int g = lane; g < p.n_grass; g += 32) S.grid[2 * CH + IDX((unsigned)S.gpos[g])] = (float)p.grass_cap;
     __syncwarp();
     cur[0] = n[0]; cur[1] = n[1];
     next_live[0] = n[0]; next_live[1] = n[1];
@@ -284,9 +280,11 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
   } else if (mode == 2) {
     // ------------------------------------------------------------------ step() (BASE:219-473)
     n[0] = h.n_list[0]; n[1] = h.n_list[1];
-    st[PPG_STAT_ENV_STEPS] = 1;
-    st[PPG_STAT_AGENT_STEPS] = n[0] + n[1];
+    // clear the grid while the loads are in flight
+    for (int i = lane; i < (3 * CH) / 4; i += 32) reinterpret_cast<float4*>(S.grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.gmap)[i] = 0u;
     // load the lists (list order = action-dict order = row order of the previous output)
+    unsigned bad = 0;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const size_t b = (size_t)env * p.cap[s];
@@ -295,28 +293,25 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         S.pos[s][i] = p.ag_pos[s][b + i];
         const double e = p.ag_e[s][b + i];
         int a = p.actions[s][p.ag_prow[s][b + i]];
-        if ((unsigned)a > 8u) { a = 4; h.status |= PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
-        S.E0[s][i] = e;                 // energy_before (ADD:256)
+        if ((unsigned)a > 8u) { a = 4; bad = PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
+        if (dense) S.E0[s][i] = e;      // energy_before (ADD:256)
         S.E[s][i] = e - p.loss[s];      // Step 1 (BASE:244-250)
         S.act[s][i] = (uint8_t)a;
         S.flg[s][i] = F_ALIVE;
-        S.aux[s][i] = 0;
         S.ord[s][i] = (uint16_t)i;
         S.rnk[s][i] = (uint16_t)i;
-        if (p.reward_mode == PPG_REWARD_SPARSE_KICKBACK) S.par[s][i] = p.ag_par[s][b + i];
+        if (kick) { S.par[s][i] = p.ag_par[s][b + i]; S.aux[s][i] = 0; }
       }
     }
-    h.status |= (unsigned char)__reduce_or_sync(FULL, (unsigned)h.status);
+    h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
     for (int g = lane; g < p.n_grass; g += 32) {
       const size_t b = (size_t)env * p.n_grass;
       S.gpos[g] = p.gr_pos[b + g];
       const double v = p.gr_e[b + g] + p.grass_gain;  // regrowth (BASE:252-256)
       S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
     }
-    // rebuild the grid as it stands after Step 1 (see DESIGN.md: equals the persistent grid)
-    for (int i = lane; i < 3 * GG; i += 32) S.grid[i] = 0.f;
-    for (int i = lane; i < GG; i += 32) S.gmap[i] = 0;
     __syncwarp();
+    // rebuild the grid as it stands after Step 1 (see DESIGN.md: equals the persistent grid)
 #pragma unroll
     for (int s = 0; s < 2; ++s)
       for (int b0 = 0; b0 < n[s]; b0 += 32) {
@@ -327,15 +322,14 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           const unsigned ps = S.pos[s][i];
           const unsigned grp = __match_any_sync(m, ps);
           // agents sharing a cell: the one latest in dict order wrote last (BASE:247,250)
-          if (lane == 31 - __clz(grp)) S.grid[s * GG + (ps >> 8) * G + (ps & 255)] = (float)S.E[s][i];
+          if (lane == 31 - __clz(grp)) S.grid[s * CH + IDX(ps)] = (float)S.E[s][i];
         }
         __syncwarp();
       }
     for (int g = lane; g < p.n_grass; g += 32) {
       const unsigned ps = S.gpos[g];
-      const int c = (ps >> 8) * G + (ps & 255);
-      S.grid[2 * GG + c] = (float)S.gE[g];
-      S.gmap[c] = (uint8_t)(g + 1);
+      S.grid[2 * CH + IDX(ps)] = (float)S.gE[g];
+      S.gmap[(ps >> 8) * G + (ps & 255)] = (uint8_t)(g + 1);
     }
     __syncwarp();
 
@@ -343,17 +337,17 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     // Warp-uniform: every lane replays the same chain, so no intra-warp sync is needed.
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      float* gr = S.grid + s * GG;
+      float* gr = S.grid + s * CH;
       for (int j = 0; j < n[s]; ++j) {
         const unsigned ps = S.pos[s][j];
         const int a = S.act[s][j];
         const int x = ps >> 8, y = ps & 255;
         const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
         const int nx0 = min(max(x + ax - 1, 0), G - 1), ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
-        const bool blocked = gr[nx0 * G + ny0] > 0.f;  // own-species channel occupied (BASE:506)
+        const bool blocked = gr[PP + (nx0 + PP) * PS + ny0] > 0.f;  // own-species channel occupied (BASE:506)
         const int nx = blocked ? x : nx0, ny = blocked ? y : ny0;
-        gr[x * G + y] = 0.f;                       // BASE:268,272
-        gr[nx * G + ny] = (float)S.E[s][j];        // BASE:269,273
+        gr[PP + (x + PP) * PS + y] = 0.f;                       // BASE:268,272
+        gr[PP + (nx + PP) * PS + ny] = (float)S.E[s][j];        // BASE:269,273
         S.pos[s][j] = (uint16_t)((nx << 8) | ny);
       }
     }
@@ -381,15 +375,15 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     for (int k = 0; k < n[0]; ++k) {
       const int slot = S.ord[0][k];
       const unsigned ps = S.pos[0][slot];
-      const int cell = (ps >> 8) * G + (ps & 255);
+      const int cell = IDX(ps);
       double e = S.E[0][slot];
       if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
         __syncwarp();
-        write_obs_row(p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], S.grid, ps >> 8, ps & 255, 0, p, ol, lane);
+        write_row_slow(p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], S.grid + cell, p, 0, lane, wall_delta);
         __syncwarp();
         S.grid[cell] = 0.f;
         S.flg[0][slot] = F_DIED;
-        st[PPG_STAT_STARVED_PRED]++;
+        st_starved[0]++;
         continue;
       }
       // first prey in agent_positions order (= lowest id) on my cell (BASE:305-312)
@@ -404,11 +398,11 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         S.grid[cell] = (float)e;  // BASE:325
         S.flg[0][slot] |= F_ATE;
         __syncwarp();
-        write_obs_row(p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], S.grid, ps >> 8, ps & 255, 1, p, ol, lane);  // BASE:327
+        write_row_slow(p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], S.grid + cell, p, 1, lane, wall_delta);  // BASE:327
         __syncwarp();
-        S.grid[GG + cell] = 0.f;  // BASE:335
+        S.grid[CH + cell] = 0.f;  // BASE:335
         S.flg[1][q] = F_DIED | F_CAUGHT;
-        st[PPG_STAT_EATEN_PREY]++;
+        st_eaten++;
       }
     }
     // Step 3b: prey in engagement order (BASE:347-380)
@@ -416,26 +410,26 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       const int slot = S.ord[1][k];
       if (!(S.flg[1][slot] & F_ALIVE)) continue;  // caught above (BASE:281)
       const unsigned ps = S.pos[1][slot];
-      const int cell = (ps >> 8) * G + (ps & 255);
+      const int cell = IDX(ps);
       double e = S.E[1][slot];
       if (e <= 0.0) {
         __syncwarp();
-        write_obs_row(p.obs[1] + (size_t)(old_base[1] + k) * p.elems[1], S.grid, ps >> 8, ps & 255, 1, p, ol, lane);
+        write_row_slow(p.obs[1] + (size_t)(old_base[1] + k) * p.elems[1], S.grid + cell, p, 1, lane, wall_delta);
         __syncwarp();
-        S.grid[GG + cell] = 0.f;
+        S.grid[CH + cell] = 0.f;
         S.flg[1][slot] = F_DIED;
-        st[PPG_STAT_STARVED_PREY]++;
+        st_starved[1]++;
         continue;
       }
-      const int g = S.gmap[cell];
+      const int g = S.gmap[(ps >> 8) * G + (ps & 255)];
       if (g) {  // BASE:351-372 (a patch with energy 0 is still "eaten")
         e += S.gE[g - 1];
         S.E[1][slot] = e;
-        S.grid[GG + cell] = (float)e;
-        S.grid[2 * GG + cell] = 0.f;
+        S.grid[CH + cell] = (float)e;
+        S.grid[2 * CH + cell] = 0.f;
         S.gE[g - 1] = 0.0;
         S.flg[1][slot] |= F_ATE;
-        st[PPG_STAT_GRASS_EATEN]++;
+        st_grass++;
       }
     }
 
@@ -471,7 +465,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             }
           }
           if (sx < 0) {
-            st[PPG_STAT_SPAWN_FALLBACK]++;
+            st_fallback++;
             if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
               const int c = p.tape_cells[h.tape_pos++];  // recorded np.random.randint choice (BASE:764)
               sx = c / G; sy = c % G;
@@ -519,18 +513,16 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           S.id[s][cs] = (uint16_t)child_id;
           S.pos[s][cs] = (uint16_t)((sx << 8) | sy);
           S.E[s][cs] = p.init_e[s];           // BASE:403
-          S.E0[s][cs] = 0.0;
           S.flg[s][cs] = F_ALIVE | F_NEWBORN;
-          S.aux[s][cs] = 0;
-          S.par[s][cs] = S.id[s][ps_slot];    // KICK:434
           const double pe = S.E[s][ps_slot] - p.init_e[s];  // BASE:404
           S.E[s][ps_slot] = pe;
-          S.grid[s * GG + sx * G + sy] = (float)p.init_e[s];  // BASE:405
-          S.grid[s * GG + px * G + py] = (float)pe;            // BASE:406
+          S.grid[s * CH + PP + (sx + PP) * PS + sy] = (float)p.init_e[s];  // BASE:405
+          S.grid[s * CH + PP + (px + PP) * PS + py] = (float)pe;            // BASE:406
           S.flg[s][ps_slot] |= F_REPRO;
-          S.aux[s][ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
-          st[s == 0 ? PPG_STAT_BIRTHS_PRED : PPG_STAT_BIRTHS_PREY]++;
-          if (p.reward_mode == PPG_REWARD_SPARSE_KICKBACK) {  // KICK:439-449
+          if (kick) {  // KICK:434-449
+            S.aux[s][cs] = 0;
+            S.par[s][cs] = S.id[s][ps_slot];
+            S.aux[s][ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
             const unsigned gp = S.par[s][ps_slot];
             if (gp != 0xFFFFu) {
               int gs = -1;
@@ -558,9 +550,6 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     over = all_term || trunc;
     env_flags = (all_term ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
     if (over) {
-      st[PPG_STAT_EPISODES] = 1;
-      st[PPG_STAT_EPISODE_STEPS] = h.step;
-      st[PPG_STAT_TRUNCATED] = trunc ? 1 : 0;
       if (p.autoreset) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
     } else {
       next_live[0] = cur[0]; next_live[1] = cur[1];
@@ -605,7 +594,8 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         if (!__all_sync(FULL, ok)) {
           // a predecessor has not published yet; it is resident (tickets are handed out in start
           // order), so this terminates — the cap only protects the box from a wedged launch
-          if (++spins > (1u << 24)) { if (lane == 0) atomicOr(p.error, 1u); break; }
+          if (++spins > (1u << 22)) { if (lane == 0) atomicOr(p.error, 1u); break; }
+          __nanosleep(100);
           continue;
         }
 #pragma unroll
@@ -653,95 +643,79 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     }
   }
 
-  // ---------------------------------------------------------------- rows: metadata + observations
+  // ------------------------------------------------- rows: metadata, observations, state write-back
   if (mode != 0) {
-    const int mode_r = p.reward_mode;
-    const bool dense = mode_r == PPG_REWARD_DENSE || mode_r == PPG_REWARD_DENSE_ADDITIVE;
+    const bool keep = !(over && p.autoreset);  // lists of a finished env are dead when it auto-resets
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
+      const RowRel rr = load_rel(p, s, lane, wall_delta);
       const int tot = n[s] + births[s];
-      for (int k = lane; k < tot; k += 32) {
-        const bool newborn = k >= n[s];
-        const int slot = newborn ? k : S.ord[s][k];
-        const int row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
-        const unsigned f = S.flg[s][slot];
-        double rew = 0.0;
-        if (mode == 2 && !newborn) {
-          const double e = S.E[s][slot], e0 = S.E0[s][slot];
-          if (dense) {
-            if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
-            else rew = (e - e0) + ((mode_r == PPG_REWARD_DENSE_ADDITIVE && (f & F_REPRO)) ? p.r_repro[s] : 0.0);  // ADD:468-471
-          } else {
-            if (f & F_DIED) rew = (f & F_CAUGHT) ? p.pen_caught : 0.0;  // BASE:288,328
-            else {
-              rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);  // BASE:322,341,365,375
-              if (f & F_REPRO) rew = p.r_repro[s];  // BASE:409,438 overwrites
-              for (int q = S.aux[s][slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
+      const size_t sb = (size_t)env * p.cap[s];
+      float* obs_s = p.obs[s];
+      const int elems = p.elems[s];
+      int wpos = 0;
+      for (int b0 = 0; b0 < tot; b0 += 32) {
+        const int k = b0 + lane;
+        int cellidx = -1, row = 0, slot = 0;
+        if (k < tot) {
+          const bool newborn = k >= n[s];
+          slot = newborn ? k : S.ord[s][k];
+          row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
+          const unsigned f = S.flg[s][slot];
+          const double e = S.E[s][slot];
+          double rew = 0.0;
+          if (mode == 2 && !newborn) {
+            if (dense) {
+              const double e0 = S.E0[s][slot];
+              if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
+              else rew = (e - e0) + ((mode_r == PPG_REWARD_DENSE_ADDITIVE && (f & F_REPRO)) ? p.r_repro[s] : 0.0);  // ADD:468-471
+            } else {
+              if (f & F_DIED) rew = (f & F_CAUGHT) ? p.pen_caught : 0.0;  // BASE:288,328
+              else {
+                rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);  // BASE:322,341,365,375
+                if (f & F_REPRO) rew = p.r_repro[s];  // BASE:409,438 overwrites
+                if (kick) for (int q = S.aux[s][slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
+              }
             }
           }
+          unsigned rf = 0;
+          if (f & F_DIED) rf |= PPG_ROW_TERMINATED;
+          if ((f & F_ALIVE) && trunc) rf |= PPG_ROW_TRUNCATED;
+          if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
+          if (mode == 1) rf |= PPG_ROW_FOUNDER;
+          if (f & F_ATE) rf |= PPG_ROW_ATE;
+          p.row_env[s][row] = env;
+          p.row_agent[s][row] = S.id[s][slot];
+          p.reward[s][row] = (float)rew;
+          p.flags[s][row] = (uint8_t)rf;
+          if (f & F_ALIVE) cellidx = IDX((unsigned)S.pos[s][slot]);
         }
-        unsigned rf = 0;
-        if (f & F_DIED) rf |= PPG_ROW_TERMINATED;
-        if ((f & F_ALIVE) && trunc) rf |= PPG_ROW_TRUNCATED;
-        if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
-        if (mode == 1) rf |= PPG_ROW_FOUNDER;
-        if (f & F_ATE) rf |= PPG_ROW_ATE;
-        p.row_env[s][row] = env;
-        p.row_agent[s][row] = S.id[s][slot];
-        p.reward[s][row] = (float)rew;
-        p.flags[s][row] = (uint8_t)rf;
-      }
-    }
-    __syncwarp();
-    // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int tot = n[s] + births[s];
-      for (int k = 0; k < tot; ++k) {
-        const bool newborn = k >= n[s];
-        const int slot = newborn ? k : S.ord[s][k];
-        if (!(S.flg[s][slot] & F_ALIVE)) continue;
-        const int row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
-        const unsigned ps = S.pos[s][slot];
-        write_obs_row(p.obs[s] + (size_t)row * p.elems[s], S.grid, ps >> 8, ps & 255, s, p, ol, lane);
-      }
-    }
-    st[PPG_STAT_ROWS_PRED] = n[0] + births[0];
-    st[PPG_STAT_ROWS_PREY] = n[1] + births[1];
-  }
-
-  // ---------------------------------------------------------------- write the state back
-  if (mode != 0) {
-    if (over && p.autoreset) {
-      h.state = ST_NEEDS_RESET;  // the lists are dead: the next call resets the env
-    } else {
-      if (over) h.state = ST_IDLE;  // final state stays readable (renderers, ppg_read_env)
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const size_t b = (size_t)env * p.cap[s];
-        int wpos = 0;
+        unsigned m = __ballot_sync(FULL, cellidx >= 0);
         // survivors in engagement order (= `self.agents` after the sort), then newborns (BASE:398,468)
-        for (int b0 = 0; b0 < n[s] + births[s]; b0 += 32) {
-          const int k = b0 + lane;
-          bool alive = false;
-          int slot = 0;
-          if (k < n[s] + births[s]) {
-            slot = k >= n[s] ? k : S.ord[s][k];
-            alive = S.flg[s][slot] & F_ALIVE;
-          }
-          const unsigned m = __ballot_sync(FULL, alive);
-          if (alive) {
-            const int dst = wpos + __popc(m & ((1u << lane) - 1));
-            p.ag_id[s][b + dst] = S.id[s][slot];
-            p.ag_pos[s][b + dst] = S.pos[s][slot];
-            p.ag_e[s][b + dst] = S.E[s][slot];
-            p.ag_prow[s][b + dst] = k >= n[s] ? new_base[s] + (k - n[s]) : old_base[s] + k;
-            if (p.reward_mode == PPG_REWARD_SPARSE_KICKBACK) p.ag_par[s][b + dst] = S.par[s][slot];
-          }
-          wpos += __popc(m);
+        if (keep && cellidx >= 0) {
+          const int dst = wpos + __popc(m & ((1u << lane) - 1));
+          p.ag_id[s][sb + dst] = S.id[s][slot];
+          p.ag_pos[s][sb + dst] = S.pos[s][slot];
+          p.ag_e[s][sb + dst] = S.E[s][slot];
+          p.ag_prow[s][sb + dst] = row;
+          if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
         }
-        h.n_list[s] = (unsigned short)wpos;
+        wpos += __popc(m);
+        // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const int ci = __shfl_sync(FULL, cellidx, l);
+          const int r = __shfl_sync(FULL, row, l);
+          write_row(obs_s + (size_t)r * elems, S.grid + ci, rr, lane);
+        }
       }
+      if (keep) h.n_list[s] = (unsigned short)wpos;
+    }
+    if (over) {
+      h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;  // idle: final state stays readable
+    }
+    if (keep) {
       unsigned char sf = 0;
       if (mode == 2) {
         if (births[0] > 0 || h.first_step) sf |= 1;
@@ -756,12 +730,29 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       }
     }
     if (lane == 0) p.hdr[env] = h;
-    // per-env counters
-    {
+    // per-env counters (PPG_STAT_*)
+    if (lane < PPG_N_STATS) {
       unsigned add = 0;
-#pragma unroll
-      for (int k = 0; k < PPG_N_STATS; ++k) add = lane == k ? st[k] : add;
-      if (lane < PPG_N_STATS && add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
+      if (mode == 2) {
+        switch (lane) {
+          case PPG_STAT_ENV_STEPS: add = 1; break;
+          case PPG_STAT_AGENT_STEPS: add = n[0] + n[1]; break;
+          case PPG_STAT_EPISODES: add = over; break;
+          case PPG_STAT_EPISODE_STEPS: add = over ? h.step : 0; break;
+          case PPG_STAT_BIRTHS_PRED: add = births[0]; break;
+          case PPG_STAT_BIRTHS_PREY: add = births[1]; break;
+          case PPG_STAT_STARVED_PRED: add = st_starved[0]; break;
+          case PPG_STAT_STARVED_PREY: add = st_starved[1]; break;
+          case PPG_STAT_EATEN_PREY: add = st_eaten; break;
+          case PPG_STAT_GRASS_EATEN: add = st_grass; break;
+          case PPG_STAT_TRUNCATED: add = trunc; break;
+          case PPG_STAT_SPAWN_FALLBACK: add = st_fallback; break;
+          default: break;
+        }
+      }
+      if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
+      if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
+      if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
     }
   }
   if (lane == 0) {

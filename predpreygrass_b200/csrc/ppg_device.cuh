@@ -49,6 +49,9 @@ enum : unsigned char {
 struct StepParams {
   // ---- config ----
   int B, G, GG, C;
+  int P, PS, CH;          // padded grid: halo width, row stride, cells per channel (see ppg_base.cu)
+  const int* obs_rel;     // [2][4][32][4] per-lane window offsets, (channel << 16) | (int16 spatial offset)
+  const float* wall_tab;  // [CH] channel-0 table: 1 outside the field, 0 inside
   int R[2], off[2], elems[2];
   int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
   double loss[2], thr[2], init_e[2], grass_cap, grass_gain;
