@@ -22,8 +22,8 @@
  * observation dict.  Rows [0, n_old) are agents that were alive when the step started, grouped
  * by environment (ascending env index) and, inside an environment, in the reference's
  * observation-dict order (BASE: lexicographic agent-id string order, BASE:459,468).  Rows
- * [n_old, n_old+n_new) are this step's newborns, grouped by environment, in birth order
- * (BASE:398,427 append them after the sorted survivors).  An agent's action for the next
+ * [n_old, n_old+n_new) are this step's newborns, grouped by environment (ascending env index), in
+ * birth order (BASE:398,427 append them after the sorted survivors).  An agent's action for the next
  * step is read from `actions[species][row]` of the row it occupied in THIS step's output,
  * so `actions = policy(obs)` needs no gather.
  */
@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 1
+#define PPG_ABI_VERSION 2
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -143,7 +143,8 @@ typedef struct ppg_buffers {
   float* reward[2];      /* rewards[agent] (BASE:460) */
   uint8_t* flags[2];     /* PPG_ROW_* */
   int32_t* old_off[2];   /* [n_envs+1] row range of each env inside [0, n_old) */
-  int32_t* new_off[2];   /* [n_envs+1] row range of each env inside [n_old, n_old+n_new), absolute rows */
+  int32_t* new_off[2];   /* [n_envs] first newborn row of the env (absolute row, >= n_old); defined where new_cnt > 0 */
+  int32_t* new_cnt[2];   /* [n_envs] newborn rows of the env: rows [new_off, new_off + new_cnt) */
   int32_t* n_rows;       /* [4] = n_old[0], n_old[1], n_new[0], n_new[1] */
   uint8_t* env_flags;    /* [n_envs] PPG_ENV_* */
   uint8_t* env_status;   /* [n_envs] PPG_STATUS_* (sticky until reset of the env) */
@@ -202,6 +203,14 @@ int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cu
  * move, BASE:244,259; that case is not supported).  Movement order inside an env = row order of
  * the previous output (= the observation-dict order a caller iterates, BASE:259). */
 int ppg_step(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, void* cuda_stream);
+
+/* ppg_step with an explicit action-dict iteration order (BASE:244,259 iterate `action_dict.items()`):
+ * order_pred / order_prey are DEVICE int32 arrays indexed like the actions; order[row] = position of
+ * that agent among its env's acting agents of the same species (a permutation of 0..n-1 per env and
+ * species; only the relative order inside a species can change an outcome, BASE:506).  An env whose
+ * order is not a permutation falls back to row order and raises PPG_STATUS_BAD_ACTION.  NULL = row order. */
+int ppg_step_ordered(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, const int32_t* order_pred,
+                     const int32_t* order_prey, void* cuda_stream);
 
 /* Same step with HOST buffers end to end: copies actions host->device, steps, copies the row
  * batch (obs, ids, rewards, flags, offsets) device->host into `out` (host pointers, pinned

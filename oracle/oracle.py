@@ -144,7 +144,8 @@ class Oracle:
             out[f"reward64_{s}"] = _np(b.reward64[s], (n,), np.float64)
             out[f"flags{s}"] = _np(b.f.flags[s], (n,), np.uint8)
             out[f"old_off{s}"] = _np(b.f.old_off[s], (self.n_envs + 1,), np.int32)
-            out[f"new_off{s}"] = _np(b.f.new_off[s], (self.n_envs + 1,), np.int32)
+            out[f"new_off{s}"] = _np(b.f.new_off[s], (self.n_envs,), np.int32)
+            out[f"new_cnt{s}"] = _np(b.f.new_cnt[s], (self.n_envs,), np.int32)
         out["env_flags"] = _np(b.f.env_flags, (self.n_envs,), np.uint8)
         out["env_status"] = _np(b.f.env_status, (self.n_envs,), np.uint8)
         out["env_step"] = _np(b.f.env_step, (self.n_envs,), np.int32)

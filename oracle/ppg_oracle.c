@@ -604,6 +604,7 @@ ppgo_batch* ppgo_create(const ppg_config* cfg, int32_t n_envs) {
     b->out.f.flags[s] = (uint8_t*)malloc(n);
     b->out.f.old_off[s] = (int32_t*)calloc((size_t)n_envs + 1, sizeof(int32_t));
     b->out.f.new_off[s] = (int32_t*)calloc((size_t)n_envs + 1, sizeof(int32_t));
+    b->out.f.new_cnt[s] = (int32_t*)calloc((size_t)n_envs + 1, sizeof(int32_t));
     b->out.f.row_capacity[s] = b->cap[s];
     b->out.f.obs_row_elems[s] = elems;
     b->prev_row[s] = (int32_t*)malloc((size_t)n_envs * (size_t)cfg->n_possible[s] * sizeof(int32_t));
@@ -624,7 +625,7 @@ void ppgo_destroy(ppgo_batch* b) {
   for (int s = 0; s < 2; ++s) {
     free(b->lexrank[s]); free(b->out.f.obs[s]); free(b->out.obs64[s]); free(b->out.f.row_env[s]);
     free(b->out.f.row_agent[s]); free(b->out.f.reward[s]); free(b->out.reward64[s]);
-    free(b->out.f.flags[s]); free(b->out.f.old_off[s]); free(b->out.f.new_off[s]); free(b->prev_row[s]);
+    free(b->out.f.flags[s]); free(b->out.f.old_off[s]); free(b->out.f.new_off[s]); free(b->out.f.new_cnt[s]); free(b->prev_row[s]);
   }
   free(b->out.f.env_flags); free(b->out.f.env_status); free(b->out.f.env_step); free(b->out.f.env_count);
   free(b->tape_cells); free(b->tape_off);
@@ -670,6 +671,8 @@ static void export_rows(ppgo_batch* b) {
       if (v->has_obs[i] && v->newborn[i]) n_new[KEY_S(v->agents[i])]++;
   }
   for (int s = 0; s < 2; ++s) b->out.f.new_off[s][b->n_envs] = n_old[s] + n_new[s];
+  for (int s = 0; s < 2; ++s) /* (start, count) form of include/ppg.h: start is 0 where the env has no newborn rows */
+    for (int e = 0; e < b->n_envs; ++e) b->out.f.new_cnt[s][e] = b->out.f.new_off[s][e + 1] - b->out.f.new_off[s][e];
   b->n_rows[0] = n_old[0]; b->n_rows[1] = n_old[1]; b->n_rows[2] = n_new[0]; b->n_rows[3] = n_new[1];
 
   for (int e = 0; e < b->n_envs; ++e) {
@@ -704,6 +707,9 @@ static void export_rows(ppgo_batch* b) {
     b->out.f.env_count[2 * e] = v->cur_num[0];
     b->out.f.env_count[2 * e + 1] = v->cur_num[1];
   }
+  for (int s = 0; s < 2; ++s)
+    for (int e = 0; e < b->n_envs; ++e)
+      if (b->out.f.new_cnt[s][e] == 0) b->out.f.new_off[s][e] = 0;
 }
 
 int ppgo_reset(ppgo_batch* b, const uint64_t* seeds, const uint8_t* mask) {
@@ -751,8 +757,9 @@ static void step_range(job* j) {
     int n = 0;
     for (int pass = 0; pass < 2; ++pass)     /* pass 0: old rows, pass 1: newborn rows */
       for (int s = 0; s < 2; ++s) {
-        const int32_t* off = pass == 0 ? b->out.f.old_off[s] : b->out.f.new_off[s];
-        for (int32_t row = off[e]; row < off[e + 1]; ++row) {
+        const int32_t r0 = pass == 0 ? b->out.f.old_off[s][e] : b->out.f.new_off[s][e];
+        const int32_t r1 = pass == 0 ? b->out.f.old_off[s][e + 1] : r0 + b->out.f.new_cnt[s][e];
+        for (int32_t row = r0; row < r1; ++row) {
           if (b->out.f.flags[s][row] & PPG_ROW_TERMINATED) continue;
           as[n] = s; aid[n] = b->out.f.row_agent[s][row]; av[n] = j->act[s][row]; ++n;
         }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libppg_b200.so")
 # every symbol include/ppg.h declares
 SYMBOLS = [
     "ppg_abi_version", "ppg_default_config", "ppg_create", "ppg_destroy", "ppg_load_tape", "ppg_reset", "ppg_step",
-    "ppg_step_host", "ppg_random_actions", "ppg_get_buffers", "ppg_snapshot_size", "ppg_snapshot", "ppg_restore",
+    "ppg_step_ordered", "ppg_step_host", "ppg_random_actions", "ppg_get_buffers", "ppg_snapshot_size", "ppg_snapshot", "ppg_restore",
     "ppg_read_env", "ppg_stats", "ppg_stats_device", "ppg_stats_clear", "ppg_launch_count", "ppg_last_error",
 ]
 
@@ -47,6 +47,7 @@ def load():
     L.ppg_load_tape.argtypes = [vp, C.POINTER(PpgTape)]
     L.ppg_reset.argtypes = [vp, vp, vp, vp]
     L.ppg_step.argtypes = [vp, vp, vp, vp]
+    L.ppg_step_ordered.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ppg_step_host.argtypes = [vp, vp, vp, C.POINTER(PpgBuffers), vp, vp]
     L.ppg_random_actions.argtypes = [vp, u64, vp, vp, vp]
     L.ppg_get_buffers.argtypes = [vp, C.POINTER(PpgBuffers)]

@@ -43,7 +43,8 @@ class StepOutput:
     reward: tuple       # fp32 [cap]
     flags: tuple        # uint8 [cap]  ROW_* bits
     old_off: tuple      # int32 [B+1]
-    new_off: tuple      # int32 [B+1]
+    new_off: tuple      # int32 [B]  first newborn row of the env (defined where new_cnt > 0)
+    new_cnt: tuple      # int32 [B]  newborn rows of the env
     n_rows: torch.Tensor   # int32 [4] on device: n_old_pred, n_old_prey, n_new_pred, n_new_prey
     env_flags: torch.Tensor
     env_status: torch.Tensor
@@ -81,7 +82,8 @@ class BatchedPredPreyGrass:
             reward=tuple(_view(b.reward[s], (cap[s],), torch.float32, d) for s in range(2)),
             flags=tuple(_view(b.flags[s], (cap[s],), torch.uint8, d) for s in range(2)),
             old_off=tuple(_view(b.old_off[s], (B + 1,), torch.int32, d) for s in range(2)),
-            new_off=tuple(_view(b.new_off[s], (B + 1,), torch.int32, d) for s in range(2)),
+            new_off=tuple(_view(b.new_off[s], (B,), torch.int32, d) for s in range(2)),
+            new_cnt=tuple(_view(b.new_cnt[s], (B,), torch.int32, d) for s in range(2)),
             n_rows=_view(b.n_rows, (4,), torch.int32, d),
             env_flags=_view(b.env_flags, (B,), torch.uint8, d),
             env_status=_view(b.env_status, (B,), torch.uint8, d),
@@ -134,6 +136,16 @@ class BatchedPredPreyGrass:
         _lib.check(self.L.ppg_step(self.h, a0.data_ptr(), a1.data_ptr(), self._stream()), self.h)
         return self.out
 
+    def step_ordered(self, actions_pred, actions_prey, order_pred, order_prey):
+        """step() with an explicit action-dict iteration order: order_*[row] = position of the row's agent
+        among its env's acting agents of that species (int32 CUDA tensors, a permutation per env)."""
+        for t in (actions_pred, actions_prey, order_pred, order_prey):
+            assert t.dtype == torch.int32 and t.is_cuda
+        rc = self.L.ppg_step_ordered(self.h, actions_pred.data_ptr(), actions_prey.data_ptr(), order_pred.data_ptr(),
+                                     order_prey.data_ptr(), self._stream())
+        _lib.check(rc, self.h)
+        return self.out
+
     def random_actions(self, seed, out_pred=None, out_prey=None):
         a0 = self.actions[0] if out_pred is None else out_pred
         a1 = self.actions[1] if out_prey is None else out_prey
@@ -152,7 +164,8 @@ class BatchedPredPreyGrass:
             t[f"reward{s}"] = mk((cap[s],), torch.float32)
             t[f"flags{s}"] = mk((cap[s],), torch.uint8)
             t[f"old_off{s}"] = mk((B + 1,), torch.int32)
-            t[f"new_off{s}"] = mk((B + 1,), torch.int32)
+            t[f"new_off{s}"] = mk((B,), torch.int32)
+            t[f"new_cnt{s}"] = mk((B,), torch.int32)
             t[f"actions{s}"] = torch.zeros((cap[s],), dtype=torch.int32, pin_memory=pinned)
         t["env_flags"] = mk((B,), torch.uint8)
         t["env_status"] = mk((B,), torch.uint8)
@@ -164,7 +177,7 @@ class BatchedPredPreyGrass:
             b.obs[s] = t[f"obs{s}"].data_ptr(); b.row_env[s] = t[f"row_env{s}"].data_ptr()
             b.row_agent[s] = t[f"row_agent{s}"].data_ptr(); b.reward[s] = t[f"reward{s}"].data_ptr()
             b.flags[s] = t[f"flags{s}"].data_ptr(); b.old_off[s] = t[f"old_off{s}"].data_ptr()
-            b.new_off[s] = t[f"new_off{s}"].data_ptr(); b.row_capacity[s] = cap[s]
+            b.new_off[s] = t[f"new_off{s}"].data_ptr(); b.new_cnt[s] = t[f"new_cnt{s}"].data_ptr(); b.row_capacity[s] = cap[s]
         b.env_flags = t["env_flags"].data_ptr(); b.env_status = t["env_status"].data_ptr()
         b.env_step = t["env_step"].data_ptr(); b.env_count = t["env_count"].data_ptr()
         b.n_rows = t["n_rows"].data_ptr()
@@ -234,6 +247,7 @@ class BatchedPredPreyGrass:
             res[f"flags{s}"] = o.flags[s][:k].cpu().numpy()
             res[f"old_off{s}"] = o.old_off[s].cpu().numpy()
             res[f"new_off{s}"] = o.new_off[s].cpu().numpy()
+            res[f"new_cnt{s}"] = o.new_cnt[s].cpu().numpy()
         res["env_flags"] = o.env_flags.cpu().numpy()
         res["env_status"] = o.env_status.cpu().numpy()
         res["env_step"] = o.env_step.cpu().numpy()

@@ -76,6 +76,7 @@ class PpgBuffers(C.Structure):
         ("flags", C.c_void_p * 2),
         ("old_off", C.c_void_p * 2),
         ("new_off", C.c_void_p * 2),
+        ("new_cnt", C.c_void_p * 2),
         ("n_rows", C.c_void_p),
         ("env_flags", C.c_void_p),
         ("env_status", C.c_void_p),

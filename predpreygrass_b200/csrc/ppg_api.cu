@@ -12,9 +12,12 @@
 
 namespace ppg {
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, int32_t* off0, int32_t* off1, int slot, cudaStream_t s);
+cudaError_t step_base_occupancy(int warps_per_cta, size_t smem, int* blocks_per_sm);
+cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
+                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s);
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
-cudaError_t launch_relabel_rows(const StepParams& p, cudaStream_t s);
+cudaError_t launch_relabel_rows(const StepParams& p, const unsigned long long* cntA, const unsigned long long* sum1,
+                                const unsigned long long* sum2, const int32_t* totals4, cudaStream_t s);
 cudaError_t launch_mark_reset(EnvHdr* hdr, int B, const unsigned long long* seeds, const uint8_t* mask, cudaStream_t s);
 cudaError_t launch_set_tape(EnvHdr* hdr, int B, const long long* cell_off, cudaStream_t s);
 cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1,
@@ -31,7 +34,8 @@ struct ppg_handle_s {
   StepParams P;
   int warps_per_cta = 4, n_cta = 0;
   size_t smem_bytes = 0;
-  unsigned long long launches_step = 0;  // step-kernel launches so far (ticket base / epoch)
+  unsigned long long launches_step = 0;  // step-kernel launches so far (epoch)
+  unsigned long long ticket_next = 0;    // value the device ticket counter has after all launches so far
   unsigned long long calls = 0;          // ppg_reset(all)/ppg_step calls (ppg_random_actions key)
   int64_t launch_count = 0;
   std::vector<void*> allocs;
@@ -124,7 +128,6 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   for (int s = 0; s < 2; ++s) {
     if (c->obs_range[s] < 1 || (c->obs_range[s] & 1) == 0 || c->obs_range[s] > 255) { err = "obs_range must be odd"; return PPG_ERR_INVALID; }
     if (c->num_obs_channels * c->obs_range[s] * c->obs_range[s] > 4 * 128) { err = "observation row too large for this build"; return PPG_ERR_INVALID; }
-    if (((c->obs_range[s] - 1) / 2) * (c->grid_size + c->obs_range[s]) > 32000) { err = "observation window too large"; return PPG_ERR_INVALID; }
     if (c->n_possible[s] < c->n_initial[s] || c->n_possible[s] > 65535) { err = "n_possible out of range"; return PPG_ERR_INVALID; }
     if (c->cap_live[s] < c->n_initial[s] || c->cap_live[s] <= 0 || c->cap_live[s] > 32768) { err = "cap_live out of range"; return PPG_ERR_INVALID; }
     if (c->n_initial[s] < 0) { err = "n_initial negative"; return PPG_ERR_INVALID; }
@@ -172,67 +175,49 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
   P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;
 
-  // padded grid geometry (ppg_base.cu "Observation rows from the PADDED grid")
-  P.P = std::max(P.off[0], P.off[1]);
-  P.PS = G + P.P;
-  P.CH = (int)align_up((size_t)P.P + (size_t)(G + 2 * P.P) * P.PS, 4);
   const bool dense = c.reward_mode == PPG_REWARD_DENSE || c.reward_mode == PPG_REWARD_DENSE_ADDITIVE;
   const bool kick = c.reward_mode == PPG_REWARD_SPARSE_KICKBACK;
 
-  // shared-memory layout of one env
+  // shared-memory layout of one env (see EnvSmem in ppg_base.cu)
   size_t o = 0;
   auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return (int)r; };
   for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(dense ? 8 * (size_t)P.cap[s] : 0, 8); }
   P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
-  P.so_grid = take(4 * 3 * (size_t)P.CH, 16);
-  if (3 * P.CH < GG + (P.n_init[0] + P.n_init[1] + P.n_grass)) { h->err = "internal: reset scratch does not fit the grid area"; return fail(PPG_ERR_INVALID); }
+  P.stage_elems = (int)align_up((size_t)std::max(P.elems[0], P.elems[1]), 4);
+  P.so_ent = take(8 * (size_t)(P.cap[0] + P.cap[1] + P.n_grass), 16);
+  P.so_stage = take(2 * 4 * (size_t)P.stage_elems, 16);
+  // reset() stages n_total cells + a GG-entry claim table in the entity + staging area
+  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass + GG) * 4 > (size_t)(P.so_stage + 8 * P.stage_elems - P.so_ent)) {
+    h->err = "internal: reset scratch does not fit the entity/staging area"; return fail(PPG_ERR_INVALID);
+  }
+  P.so_scr = take(align_up(GG, 4), 4);
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_par[s] = take(kick ? 2 * (size_t)P.cap[s] : 0, 2);
+    P.so_own[s] = take(2 * align_up(GG, 2), 4);
   }
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
   for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(kick ? P.cap[s] : 0, 1); }
   P.so_gmap = take(align_up(GG, 4), 4);
-  P.smem_per_env = (int)align_up(o, 16);
-  const size_t wall_bytes = 4 * (size_t)P.CH;
-  const size_t smem_max = 227 * 1024 - 2048;  // static __shared__ of the kernel comes on top
-  if ((size_t)P.smem_per_env + wall_bytes > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
-  int W = 4;
+  P.so_gtag = take(std::max(1, P.n_grass), 1);
+  P.smem_per_env = (int)align_up(o, 128);
+  const size_t smem_max = 227 * 1024;
+  if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
+  int W = 1;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
-  if (W != 1 && W != 2 && W != 4 && W != 8) W = 4;
-  while (W > 1 && (size_t)W * P.smem_per_env + wall_bytes > smem_max) W >>= 1;
+  if (W != 1 && W != 2 && W != 4) W = 1;
+  while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
   h->warps_per_cta = W;
-  h->n_cta = (B + W - 1) / W;
-  h->smem_bytes = (size_t)W * P.smem_per_env + wall_bytes;
-
-  // per-lane window offsets and the channel-0 ("outside the grid") table
+  h->smem_bytes = (size_t)W * P.smem_per_env;
   {
-    std::vector<int> rel(2 * 4 * 32 * 4, 0x7FFFFFFF);
-    for (int s = 0; s < 2; ++s) {
-      const int R = P.R[s], RR = R * R, nvec = P.elems[s] / 4;
-      for (int it = 0; it < 4; ++it)
-        for (int lane = 0; lane < 32; ++lane) {
-          const int q = it * 32 + lane;
-          if (q >= nvec) continue;
-          for (int k = 0; k < 4; ++k) {
-            const int e = 4 * q + k, ch = e / RR, i = (e % RR) / R, j = e % R;
-            const int sp = (i - P.off[s]) * P.PS + (j - P.off[s]);
-            rel[(size_t)((s * 4 + it) * 32 + lane) * 4 + k] = (ch << 16) | (sp & 0xFFFF);
-          }
-        }
-    }
-    int* d_rel = nullptr;
-    CKC(dalloc(h, &d_rel, rel.size()));
-    CKC(cudaMemcpy(d_rel, rel.data(), rel.size() * sizeof(int), cudaMemcpyHostToDevice));
-    P.obs_rel = d_rel;
-    std::vector<float> wall((size_t)P.CH, 1.0f);
-    for (int x = 0; x < G; ++x)
-      for (int y = 0; y < G; ++y) wall[(size_t)P.P + (size_t)(x + P.P) * P.PS + y] = 0.0f;
-    float* d_wall = nullptr;
-    CKC(dalloc(h, &d_wall, wall.size()));
-    CKC(cudaMemcpy(d_wall, wall.data(), wall.size() * sizeof(float), cudaMemcpyHostToDevice));
-    P.wall_tab = d_wall;
+    // persistent warps: as many CTAs as fit on the device, never more than there are envs
+    int per_sm = 0, n_sm = 0;
+    CKC(step_base_occupancy(W, h->smem_bytes, &per_sm));
+    CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
+    h->n_cta = std::min((B + W - 1) / W, per_sm * n_sm);
+    if (const char* ev = getenv("PPG_MAX_CTAS")) h->n_cta = std::max(1, std::min(h->n_cta, atoi(ev)));
   }
 
   // state
@@ -246,12 +231,19 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &d, lr.size()));
     CKC(cudaMemcpy(d, lr.data(), lr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     P.lexrank[s] = d;
-    CKC(dalloc(h, &P.next_off[s], (size_t)B + 3));
+  }
+  {
+    const size_t n_blk = ((size_t)B + 31) / 32, n_grp = ((size_t)B + 1023) / 1024;
+    for (int q = 0; q < 2; ++q) {
+      CKC(dalloc(h, &P.cntA[q], (size_t)B)); CKC(dalloc(h, &P.cntB[q], (size_t)B));
+      CKC(dalloc(h, &P.sum1[q], n_blk * 4)); CKC(dalloc(h, &P.sum2[q], n_grp * 4));
+    }
+    CKC(dalloc(h, &P.done1, n_blk)); CKC(dalloc(h, &P.done2, n_grp)); CKC(dalloc(h, &P.done3, 1));
+    CKC(dalloc(h, &P.totals, 8));
   }
   CKC(dalloc(h, &P.gr_pos, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
-  CKC(dalloc(h, &P.desc, (size_t)h->n_cta * 4));
   CKC(dalloc(h, &P.ticket, 1));
   CKC(dalloc(h, &P.error, 1));
   CKC(dalloc(h, &h->d_stats, PPG_N_STATS));
@@ -271,9 +263,10 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.row_env[s], rows)); CKC(dalloc(h, &P.row_agent[s], rows));
     CKC(dalloc(h, &P.reward[s], rows)); CKC(dalloc(h, &P.flags[s], rows));
     CKC(dalloc(h, &P.old_off[s], (size_t)B + 1)); CKC(dalloc(h, &P.new_off[s], (size_t)B + 1));
+    CKC(dalloc(h, &P.new_cnt[s], (size_t)B + 1));
     CKC(dalloc(h, &h->d_act[s], rows));
     b.row_env[s] = P.row_env[s]; b.row_agent[s] = P.row_agent[s]; b.reward[s] = P.reward[s]; b.flags[s] = P.flags[s];
-    b.old_off[s] = P.old_off[s]; b.new_off[s] = P.new_off[s];
+    b.old_off[s] = P.old_off[s]; b.new_off[s] = P.new_off[s]; b.new_cnt[s] = P.new_cnt[s];
   }
   CKC(dalloc(h, &P.n_rows, 4)); CKC(dalloc(h, &P.env_flags, (size_t)B)); CKC(dalloc(h, &P.env_status, (size_t)B));
   CKC(dalloc(h, &P.env_step, (size_t)B)); CKC(dalloc(h, &P.env_count, (size_t)B * 2));
@@ -318,10 +311,23 @@ int ppg_load_tape(ppg_handle h, const ppg_tape* t) {
   return PPG_OK;
 }
 
-static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, cudaStream_t st) {
+// publish the rows every env needs in the next output under the tag of the launch that "just ran"
+static int prepare_offsets(ppg_handle h, cudaStream_t st) {
+  const unsigned prev_epoch = (unsigned)h->launches_step;
+  const int q = (int)(prev_epoch & 1u);
+  CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.cntA[q], h->P.sum1[q], h->P.sum2[q],
+                            h->P.totals + 4 * q, prev_epoch, st));
+  h->launch_count++;
+  return PPG_OK;
+}
+
+static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, const int32_t* o0, const int32_t* o1, cudaStream_t st) {
   StepParams& P = h->P;
   P.actions[0] = a0; P.actions[1] = a1;
-  P.ticket_base = h->launches_step * (unsigned long long)h->n_cta;
+  P.order[0] = o0; P.order[1] = o1;
+  // every launch draws B tickets plus one terminating draw per warp
+  P.ticket_base = h->ticket_next;
+  h->ticket_next += (unsigned long long)h->B + (unsigned long long)h->n_cta * h->warps_per_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
   CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
   h->launches_step++;
@@ -340,12 +346,11 @@ int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cu
   const uint8_t* dmask = nullptr;
   if (mask) { CK(cudaMemcpyAsync(h->d_mask, mask, (size_t)h->B, cudaMemcpyHostToDevice, st)); dmask = h->d_mask; }
   CK(launch_mark_reset(h->P.hdr, h->B, dseeds, dmask, st));
-  // first-old-row offsets of the next output: totals slot = parity of the next launch's epoch
-  CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.next_off[0], h->P.next_off[1],
-                            (int)((h->launches_step + 1) & 1), st));
-  h->launch_count += 2;
+  h->launch_count++;
+  int rc = prepare_offsets(h, st);
+  if (rc) return rc;
   if (mask) return PPG_OK;  // partial reset: performed by the next ppg_step
-  int rc = run_step_kernel(h, nullptr, nullptr, st);
+  rc = run_step_kernel(h, nullptr, nullptr, nullptr, nullptr, st);
   if (rc) return rc;
   h->h_n_rows[0] = h->B * h->P.n_init[0]; h->h_n_rows[1] = h->B * h->P.n_init[1];
   h->h_n_rows[2] = h->h_n_rows[3] = 0;
@@ -358,7 +363,16 @@ int ppg_step(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_p
   if (!actions_pred || !actions_prey) { h->err = "ppg_step: NULL actions"; return PPG_ERR_INVALID; }
   if (h->launches_step == 0) { h->err = "ppg_step before ppg_reset"; return PPG_ERR_STATE; }
   CK(cudaSetDevice(h->device));
-  return run_step_kernel(h, actions_pred, actions_prey, static_cast<cudaStream_t>(cuda_stream));
+  return run_step_kernel(h, actions_pred, actions_prey, nullptr, nullptr, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int ppg_step_ordered(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, const int32_t* order_pred,
+                     const int32_t* order_prey, void* cuda_stream) {
+  if (!h) return PPG_ERR_INVALID;
+  if (!actions_pred || !actions_prey) { h->err = "ppg_step_ordered: NULL actions"; return PPG_ERR_INVALID; }
+  if (h->launches_step == 0) { h->err = "ppg_step_ordered before ppg_reset"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  return run_step_kernel(h, actions_pred, actions_prey, order_pred, order_prey, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* actions_prey, ppg_buffers* out,
@@ -376,7 +390,7 @@ int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* acti
     const size_t n = (size_t)h->h_n_rows[s] + (size_t)h->h_n_rows[2 + s];
     if (n) CK(cudaMemcpyAsync(h->d_act[s], src[s], n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
-  int rc = run_step_kernel(h, h->d_act[0], h->d_act[1], st);
+  int rc = run_step_kernel(h, h->d_act[0], h->d_act[1], nullptr, nullptr, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->h_n_rows, h->P.n_rows, sizeof h->h_n_rows, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -392,7 +406,8 @@ int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* acti
       if (out->flags[s]) CK(cudaMemcpyAsync(out->flags[s], h->P.flags[s], n, cudaMemcpyDeviceToHost, st));
     }
     if (out->old_off[s]) CK(cudaMemcpyAsync(out->old_off[s], h->P.old_off[s], ((size_t)h->B + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (out->new_off[s]) CK(cudaMemcpyAsync(out->new_off[s], h->P.new_off[s], ((size_t)h->B + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out->new_off[s]) CK(cudaMemcpyAsync(out->new_off[s], h->P.new_off[s], (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out->new_cnt[s]) CK(cudaMemcpyAsync(out->new_cnt[s], h->P.new_cnt[s], (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   }
   if (out->env_flags) CK(cudaMemcpyAsync(out->env_flags, h->P.env_flags, (size_t)h->B, cudaMemcpyDeviceToHost, st));
   if (out->env_status) CK(cudaMemcpyAsync(out->env_status, h->P.env_status, (size_t)h->B, cudaMemcpyDeviceToHost, st));
@@ -469,10 +484,13 @@ int ppg_restore(ppg_handle h, const void* blob, size_t bytes, void* cuda_stream)
   h->calls = head[0];
   q += 16;
   for (const Seg& s : state_segments(h)) { CK(cudaMemcpyAsync(s.p, q, s.bytes, cudaMemcpyHostToDevice, st)); q += s.bytes; }
-  CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.next_off[0], h->P.next_off[1],
-                            (int)((h->launches_step + 1) & 1), st));
-  CK(launch_relabel_rows(h->P, st));
-  h->launch_count += 2;
+  {
+    int rc = prepare_offsets(h, st);
+    if (rc) return rc;
+    const int q = (int)(h->launches_step & 1ULL);
+    CK(launch_relabel_rows(h->P, h->P.cntA[q], h->P.sum1[q], h->P.sum2[q], h->P.totals + 4 * q, st));
+    h->launch_count++;
+  }
   CK(cudaStreamSynchronize(st));
   h->h_n_rows_valid = false;
   return PPG_OK;
@@ -546,7 +564,7 @@ int ppg_stats(ppg_handle h, int64_t* out, void* cuda_stream) {
   CK(cudaStreamSynchronize(st));
   unsigned err = 0;
   CK(cudaMemcpy(&err, h->P.error, sizeof err, cudaMemcpyDeviceToHost));
-  if (err) { h->err = "device error word set (row allocation look-back wedged)"; return PPG_ERR_STATE; }
+  if (err) { h->err = "device error word set (row allocation: bit0 prefix wait wedged, bit1 stale counts)"; return PPG_ERR_STATE; }
   return PPG_OK;
 }
 

@@ -1,22 +1,39 @@
-// ppg_base.cu — the BASE-family environment step as one fused sm_100a kernel.
+// ppg_base.cu — the BASE-family environment step as one fused, persistent sm_100a kernel (v3).
 //
 // Reproduces, for B independent env instances in lockstep, `PredPreyGrass.step()` and `reset()` of
 //   BASE = predpreygrass/non_evolutionary/base_environment/predpreygrass_rllib_env.py
 // and its reward variants (dense_rewards, dense_rewards_additive, sparse_rewards_plus_eating,
 // sparse_rewards_plus_kickback; see include/ppg.h PPG_REWARD_*).
 //
-// Mapping: one warp owns one env for the whole step.  The env's agent lists, grass and an fp32
-// copy of the grid live in that warp's slice of shared memory; order-dependent phases (movement in
-// action-dict order BASE:259-273, engagements over the sorted `self.agents` BASE:279-380, births
-// BASE:389-448) run as warp-uniform sequential loops, everything order-free (decay, regrowth,
-// lookups "first prey on my cell", occupancy tests, observation windows, row output) runs
-// lane-parallel.  Observation rows are written straight to their final place in the compact
-// per-species batch with 16-byte streaming stores; rows of agents that die are written at the
-// moment of death because the reference captures them then (BASE:287,327).
+// Mapping: one warp owns one env for the whole step; warps are persistent and draw env indices
+// from a global ticket counter, so envs of very different population sizes balance over the SMs.
+// The env's agent lists, grass and per-species OWNER maps live in the warp's slice of shared
+// memory.  The reference's float grid (`grid_world_state`, BASE:124) is never materialised: a
+// non-zero grid cell always equals the current energy of the agent that wrote it last, so
+// `own[s][cell] = slot + 1` (0 = the reference wrote 0 there) carries the same information in
+// 2 bytes per cell and the value is looked up in the energy list.
 //
-// Row allocation across envs: old rows of a step are allocated by the previous step (the live
-// counts are known then), newborn rows by a single-pass decoupled look-back over CTAs at the end
-// of the logic phase — no second kernel, no host round trip, deterministic layout.
+// Order-dependent phases keep the reference's semantics but run lane-parallel wherever agents
+// cannot interact:
+//   movement (dict order, BASE:259-273): chunks of 32 agents; an agent whose old or target cell
+//     is touched by any other agent of the chunk is replayed sequentially in order, the rest
+//     commit in parallel (ordered-claim round with shared-memory touch counters);
+//   predators (BASE:279-346): skipped entirely when no predator starved and no prey shares a
+//     cell with a predator, else the exact sequential loop;
+//   prey (BASE:347-380): 32 prey at a time eat in parallel unless one of them starved or two
+//     share a grass patch, else the exact sequential loop for that chunk;
+//   births (BASE:389-448): ballot over eligible parents, sequential per birth (rare).
+// Observation rows (BASE:511-539) are assembled in a shared-memory staging buffer by scattering
+// the env's visible entities (a few dozen) into a zero-filled window, and leave the SM as ONE
+// bulk asynchronous copy per row (cp.async.bulk shared -> global, 784 / 1296 contiguous bytes),
+// double buffered so assembling row r+1 overlaps the store of row r.
+//
+// Row allocation across envs is deterministic and needs no second kernel: every env publishes
+// its live/birth counts; the last finisher of each 32-env block / 1024-env group publishes block
+// and group sums (threadfence + counter pattern).  An env derives the first row of its old rows
+// from the PREVIOUS launch's sums (complete by construction) and the first row of its newborn
+// rows from THIS launch's sums, which it only waits for if it has newborns, after all its other
+// work is done.
 #include <cuda_runtime.h>
 
 #include "ppg_device.cuh"
@@ -32,17 +49,21 @@ struct EnvSmem {
   double* E[2];
   double* E0[2];
   double* gE;
-  float* grid;  // [3][CH] padded: predator, prey, grass energies (channels 1..3 of BASE:123)
+  uint2* ent;      // visible entities: x = channel << 16 | pos, y = float bits
+  float* stage;    // 2 row buffers of stage_elems floats
+  uint8_t* scr;    // [GG rounded to 4] touch counters / predator marks; all zero between uses
   uint16_t* id[2];
   uint16_t* pos[2];
   uint16_t* ord[2];  // ord[k] = slot of the k-th agent in engagement order
   uint16_t* rnk[2];  // inverse of ord
   uint16_t* par[2];
+  uint16_t* own[2];  // [GG] owner map: slot + 1 of the agent whose energy the reference grid shows, 0 = empty
   uint16_t* gpos;
   uint8_t* act[2];
   uint8_t* flg[2];
   uint8_t* aux[2];  // kickback count
   uint8_t* gmap;    // cell -> grass index + 1
+  uint8_t* gtag;    // [n_grass] scratch for the prey chunk conflict test
 };
 
 __device__ __forceinline__ EnvSmem carve(unsigned char* base, const StepParams& p) {
@@ -56,64 +77,136 @@ __device__ __forceinline__ EnvSmem carve(unsigned char* base, const StepParams& 
     s.ord[k] = reinterpret_cast<uint16_t*>(base + p.so_ord[k]);
     s.rnk[k] = reinterpret_cast<uint16_t*>(base + p.so_rnk[k]);
     s.par[k] = reinterpret_cast<uint16_t*>(base + p.so_par[k]);
+    s.own[k] = reinterpret_cast<uint16_t*>(base + p.so_own[k]);
     s.act[k] = base + p.so_act[k];
     s.flg[k] = base + p.so_flg[k];
     s.aux[k] = base + p.so_aux[k];
   }
   s.gE = reinterpret_cast<double*>(base + p.so_gE);
-  s.grid = reinterpret_cast<float*>(base + p.so_grid);
+  s.ent = reinterpret_cast<uint2*>(base + p.so_ent);
+  s.stage = reinterpret_cast<float*>(base + p.so_stage);
+  s.scr = base + p.so_scr;
   s.gpos = reinterpret_cast<uint16_t*>(base + p.so_gpos);
   s.gmap = base + p.so_gmap;
+  s.gtag = base + p.so_gtag;
   return s;
 }
 
-// Observation rows from the PADDED grid.
-// The shared-memory grid of an env has a halo of P = max((R-1)/2) zero cells around the G x G
-// field, stored with row stride PS = G + P (the P-wide gap after a row doubles as the left halo of
-// the next row) and P leading pad cells:  IDX(x, y) = P + (x + P) * PS + y,  CH cells per channel.
-// A window element (c, i, j) of an agent at (x, y) is then simply  grid[c-1][IDX(x,y) + (i-off)*PS +
-// (j-off)]  with no bounds test; channel 0 ("outside the grid", BASE:522-523) reads a per-CTA
-// constant table of the same shape (1 in halo/gap cells, 0 on the field).  Per lane the relative
-// offsets of the <= 16 elements it writes are precomputed on the host (obs_rel table).
-struct RowRel {
-  int rel[4][4];   // float offset from &grid[IDX(x,y)] for float4 group `it`, element k
-  unsigned valid;  // bit it: group it*32+lane exists
-};
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: bulk asynchronous shared -> global copy (TMA engine, SASS UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, int lane, int wall_delta) {
-  RowRel r;
-  r.valid = 0;
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long long v) {
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+#define TAG(epoch, val) (((unsigned long long)(epoch) << 32) | (unsigned long long)(unsigned)(val))
+
+#define CELL(ps) ((int)((ps) >> 8) * G + (int)((ps)&255u))
+
+// ------------------------------------------------------------------------------------------------
+// observation rows
+// ------------------------------------------------------------------------------------------------
+// The entities the reference grid shows right now (BASE:123-124 channels 1..3): an agent is visible
+// iff it owns its cell; a grass patch iff its energy is non-zero.  Returns the entity count.
+__device__ __noinline__ int build_entities(unsigned char* base, const StepParams& p, int nt0, int nt1, int lane) {
+  const EnvSmem S = carve(base, p);
+  const int G = p.G;
+  int n_ent = 0;
+  const int nt[2] = {nt0, nt1};
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int4 v = __ldg(reinterpret_cast<const int4*>(p.obs_rel) + (s * 4 + it) * 32 + lane);
-    const int e[4] = {v.x, v.y, v.z, v.w};
-    if (v.x != 0x7FFFFFFF) r.valid |= 1u << it;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = e[k] >> 16, sp = (int)(short)(e[k] & 0xFFFF);
-      r.rel[it][k] = (c == 0 ? wall_delta : (c - 1) * p.CH) + sp;
+  for (int s = 0; s < 2; ++s)
+    for (int b0 = 0; b0 < nt[s]; b0 += 32) {
+      const int i = b0 + lane;
+      bool vis = false;
+      unsigned ps = 0;
+      if (i < nt[s] && (S.flg[s][i] & F_ALIVE)) {
+        ps = S.pos[s][i];
+        vis = S.own[s][CELL(ps)] == (unsigned)(i + 1);
+      }
+      const unsigned m = __ballot_sync(FULL, vis);
+      if (vis) S.ent[n_ent + __popc(m & ((1u << lane) - 1))] = make_uint2(((unsigned)(s + 1) << 16) | ps, __float_as_uint((float)S.E[s][i]));
+      n_ent += __popc(m);
     }
+  for (int b0 = 0; b0 < p.n_grass; b0 += 32) {
+    const int g = b0 + lane;
+    float v = 0.f;
+    if (g < p.n_grass) v = (float)S.gE[g];
+    const bool vis = v != 0.f;
+    const unsigned m = __ballot_sync(FULL, vis);
+    if (vis) S.ent[n_ent + __popc(m & ((1u << lane) - 1))] = make_uint2((3u << 16) | S.gpos[g], __float_as_uint(v));
+    n_ent += __popc(m);
   }
-  return r;
+  __syncwarp();
+  return n_ent;
 }
 
-// _get_observation (BASE:511-539): one [C][R][R] fp32 row, warp-cooperative, 16-byte streaming stores
-__device__ __forceinline__ void write_row(float* __restrict__ dst, const float* __restrict__ cell0,
-                                          const RowRel& r, int lane) {
+// _get_observation (BASE:511-539) of an agent at `apos` into global row `dst`: zero-fill a staging
+// row, mark channel 0 outside the grid (BASE:522-523), scatter the visible entities that fall into
+// the window, hand the row to the bulk-copy engine.
+__device__ __forceinline__ void emit_row(const StepParams& p, const EnvSmem& S, float* dst, unsigned apos, int s, int n_ent,
+                                         unsigned& rowctr, const unsigned (&wq)[4], int lane) {
+  float* buf = S.stage + (rowctr & 1u) * p.stage_elems;
+  ++rowctr;
+  if (lane == 0) bulk_wait_read<1>();  // the copy issued two rows ago has finished reading `buf`
+  __syncwarp();
+  const int R = p.R[s], off = p.off[s], G = p.G;
+  const int nvec = p.elems[s] >> 2;
+  for (int q = lane; q < nvec; q += 32) reinterpret_cast<float4*>(buf)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const int ax = apos >> 8, ay = apos & 255;
+  if (ax < off || ay < off || ax + off >= G || ay + off >= G) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    if (r.valid & (1u << it)) {
-      const float4 v = make_float4(cell0[r.rel[it][0]], cell0[r.rel[it][1]], cell0[r.rel[it][2]], cell0[r.rel[it][3]]);
-      __stcs(reinterpret_cast<float4*>(dst) + (it * 32 + lane), v);
+    for (int jj = 0; jj < 4; ++jj) {
+      const unsigned w = wq[jj];
+      if (w != 0xFFFFFFFFu) {
+        const int i = w >> 8, j = w & 255;
+        if ((unsigned)(ax - off + i) >= (unsigned)G || (unsigned)(ay - off + j) >= (unsigned)G) buf[lane + 32 * jj] = 1.f;
+      }
     }
+  }
+  const int lo = (int)apos - ((off << 8) | off);
+  for (int e = lane; e < n_ent; e += 32) {
+    const uint2 en = S.ent[e];
+    const int d = (int)(en.x & 0xFFFFu) - lo;
+    const unsigned ty = (unsigned)d & 255u, tx = (unsigned)(d >> 8);
+    if (ty < (unsigned)R && tx < (unsigned)R) buf[((int)(en.x >> 16) * R + (int)tx) * R + (int)ty] = __uint_as_float(en.y);
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(dst, buf, (unsigned)p.elems[s] * 4u);
+    bulk_commit();
   }
 }
 
-// rare path (rows of agents that die mid-step, BASE:287,327): same, offsets decoded on the fly
-__device__ __noinline__ void write_row_slow(float* __restrict__ dst, const float* __restrict__ cell0,
-                                            const StepParams& p, int s, int lane, int wall_delta) {
-  const RowRel r = load_rel(p, s, lane, wall_delta);
-  write_row(dst, cell0, r, lane);
+// rows of agents that die mid-step: the reference captures them at that moment (BASE:287,327)
+__device__ __noinline__ void emit_row_now(unsigned char* base, const StepParams& p, float* dst, unsigned apos, int s, int nt0, int nt1,
+                                          unsigned* rowctr, int lane) {
+  const EnvSmem S = carve(base, p);
+  const int n_ent = build_entities(base, p, nt0, nt1, lane);
+  unsigned wq[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int q = lane + 32 * jj, R = p.R[s];
+    wq[jj] = q < R * R ? (unsigned)(((q / R) << 8) | (q % R)) : 0xFFFFFFFFu;
+  }
+  unsigned rc = *rowctr;
+  emit_row(p, S, dst, apos, s, n_ent, rc, wq, lane);
+  *rowctr = rc;
 }
 
 // any live agent (either species, newborns included) on cell `pos`?  = `pos in set(agent_positions.values())` (BASE:399,754)
@@ -125,368 +218,498 @@ __device__ __forceinline__ bool any_agent_at(const EnvSmem& S, const int nl[2], 
   return __any_sync(FULL, hit);
 }
 
-__device__ __forceinline__ unsigned long long vload(const unsigned long long* p) {
-  return *reinterpret_cast<const volatile unsigned long long*>(p);
+// exclusive prefix, over the envs before `env`, of two 16-bit-packed per-env counts.
+//   cnt : per-env words (value pair in bits 31..16 / 15..0), sum1/sum2: per-block / per-group sums at [.][4] + v0, + v0 + 1
+// `epoch` = tag the words must carry; wait = poll until they do (this launch's counts) or trust them (previous launch's).
+__device__ __forceinline__ bool prefix_before(const unsigned long long* cnt, const unsigned long long* sum1, const unsigned long long* sum2,
+                                              int v0, int env, unsigned epoch, bool wait, int lane, int& out0, int& out1) {
+  const int blk = env >> 5, grp = env >> 10;
+  unsigned spins = 0;
+  for (;;) {
+    int a0 = 0, a1 = 0;
+    bool ok = true;
+    if (lane < (env & 31)) {
+      const unsigned long long w = ld_volatile(cnt + (blk << 5) + lane);
+      ok &= (unsigned)(w >> 32) == epoch;
+      a0 += (int)((w >> 16) & 0xFFFFu);
+      a1 += (int)(w & 0xFFFFu);
+    }
+    if (lane < (blk & 31)) {
+      const unsigned long long* q = sum1 + (size_t)((grp << 5) + lane) * 4 + v0;
+      const unsigned long long w0 = ld_volatile(q), w1 = ld_volatile(q + 1);
+      ok &= (unsigned)(w0 >> 32) == epoch && (unsigned)(w1 >> 32) == epoch;
+      a0 += (int)(unsigned)w0;
+      a1 += (int)(unsigned)w1;
+    }
+    for (int g = lane; g < grp; g += 32) {
+      const unsigned long long* q = sum2 + (size_t)g * 4 + v0;
+      const unsigned long long w0 = ld_volatile(q), w1 = ld_volatile(q + 1);
+      ok &= (unsigned)(w0 >> 32) == epoch && (unsigned)(w1 >> 32) == epoch;
+      a0 += (int)(unsigned)w0;
+      a1 += (int)(unsigned)w1;
+    }
+    if (__all_sync(FULL, ok) || !wait) {
+      out0 = __reduce_add_sync(FULL, a0);
+      out1 = __reduce_add_sync(FULL, a1);
+      return __all_sync(FULL, ok);
+    }
+    // predecessors hold lower tickets, so they are running or done: this terminates.  The cap only
+    // protects the box from a wedged launch.
+    if (++spins > (1u << 22)) return false;
+    __nanosleep(200);
+  }
 }
-__device__ __forceinline__ void vstore(unsigned long long* p, unsigned long long v) {
-  *reinterpret_cast<volatile unsigned long long*>(p) = v;
-}
-
-#define DESC(flag, epoch, val) (((unsigned long long)(flag) << 62) | ((unsigned long long)((epoch)&0x3FFFFFFFu) << 32) | (unsigned long long)(unsigned)(val))
 
 // ------------------------------------------------------------------------------------------------
-// the step kernel: W warps per CTA, one env per warp
+// the step kernel: W persistent warps per CTA, one env per warp at a time
 // ------------------------------------------------------------------------------------------------
-#define IDX(ps) (PP + (int)(((ps) >> 8) + PP) * PS + (int)((ps)&255u))
-
 template <int W>
 __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_constant__ StepParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_cnt[W][4];
-  __shared__ int s_base[W][4];
-  __shared__ int s_incl[4];
-  __shared__ unsigned s_ticket;
-
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_ticket = (unsigned)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-  // per-CTA constant "outside the grid" channel (BASE:522-523) in the padded layout
-  float* wall = reinterpret_cast<float*>(smem_raw + (size_t)W * p.smem_per_env);
-  for (int i = threadIdx.x; i < p.CH; i += W * 32) wall[i] = __ldg(p.wall_tab + i);
-  __syncthreads();
-  const unsigned cta = s_ticket;
-  const int env = (int)cta * W + warp;
-  const bool active = env < p.B;
-  const EnvSmem S = carve(smem_raw + (size_t)warp * p.smem_per_env, p);
-  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS, CH = p.CH;
-  const int wall_delta = (int)(wall - S.grid);
-  const int totals_rd = p.epoch & 1;
+  unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
+  const EnvSmem S = carve(sbase, p);
+  const int G = p.G, GG = p.GG;
+  const unsigned epoch = p.epoch;
+  const int par = (int)(epoch & 1u);
   const int mode_r = p.reward_mode;
   const bool dense = mode_r == PPG_REWARD_DENSE || mode_r == PPG_REWARD_DENSE_ADDITIVE;
   const bool kick = mode_r == PPG_REWARD_SPARSE_KICKBACK;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  // per-env registers (warp-uniform)
-  int n[2] = {0, 0};        // list length at step start (= old rows)
-  int births[2] = {0, 0};
-  int old_base[2] = {0, 0};
-  int next_live[2] = {0, 0};
-  int mode = 0;             // 0 none/idle, 1 reset, 2 step
-  EnvHdr h;
-  unsigned env_flags = 0;
-  unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
-  int cur[2] = {0, 0};
-  bool over = false, trunc = false;
+  // channel-0 window coordinates handled by this lane, per species (elements lane + 32*jj of the row)
+  unsigned wq[2][4];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int q = lane + 32 * jj, R = p.R[s];
+      wq[s][jj] = q < R * R ? (unsigned)(((q / R) << 8) | (q % R)) : 0xFFFFFFFFu;
+    }
+  for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.scr)[i] = 0u;
+  unsigned rowctr = 0;
+  const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
+  const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
+  __syncwarp();
 
-  if (active) {
-    h = p.hdr[env];
-    old_base[0] = p.next_off[0][env];
-    old_base[1] = p.next_off[1][env];
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    env = __shfl_sync(FULL, env, 0);
+    if (env >= p.B) break;
+
+    // per-env registers (warp-uniform)
+    int n[2] = {0, 0};  // list length at step start (= old rows)
+    int births[2] = {0, 0};
+    int old_base[2] = {0, 0};
+    int next_live[2] = {0, 0};
+    int mode = 0;  // 0 idle, 1 reset, 2 step
+    unsigned env_flags = 0;
+    unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
+    int cur[2] = {0, 0};
+    bool over = false, trunc = false;
+
+    EnvHdr h = p.hdr[env];
+    // first old row of this env: the previous launch published how many rows every env needs now
+    if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
+      if (lane == 0) atomicOr(p.error, 2u);  // the host did not prepare the counts of the previous output
+    }
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
-  }
 
-  if (mode == 1) {
-    // ------------------------------------------------------------------ reset() (BASE:129-217)
-    h.episode += 1;
-    h.step = 0;
-    h.spawn_draws = 0;
-    h.status = 0;
-    h.sortflag = 0;
-    h.first_step = 1;
-    h.state = 0;
-    const int n_total = p.n_init[0] + p.n_init[1] + p.n_grass;
-    // cells in the order predators, prey, grass (BASE:185-187); staged in the (not yet built) grid area
-    int* cells = reinterpret_cast<int*>(S.grid);                 // [n_total], n_total <= GG
-    unsigned* first = reinterpret_cast<unsigned*>(S.grid) + GG;  // [GG] draw index that claimed the cell
-    bool from_tape = false;
-    if (p.tape_cells != nullptr) {
-      if (h.tape_pos + n_total <= h.tape_end) {
-        for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
-        h.tape_pos += n_total;
-        from_tape = true;
-      } else {
-        h.status |= PPG_STATUS_TAPE_EXHAUSTED;
-      }
-    }
-    if (!from_tape) {
-      // Philox rejection draws, accepted in draw order until n_total unique cells (law of BASE:156-177)
-      for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
+    if (mode == 1) {
+      // ------------------------------------------------------------------ reset() (BASE:129-217)
+      h.episode += 1;
+      h.step = 0;
+      h.spawn_draws = 0;
+      h.status = 0;
+      h.sortflag = 0;
+      h.first_step = 1;
+      h.state = 0;
+      if (lane == 0) bulk_wait_read<0>();  // the scratch below aliases the row staging buffers
       __syncwarp();
-      int accepted = 0;
-      for (unsigned batch = 0; accepted < n_total; ++batch) {
-        const unsigned idx0 = batch * 128u + 4u * lane;
-        const ppg_u32x4 r = ppg_philox4x32((unsigned)env, h.episode, idx0 >> 2, PPG_STREAM_PLACEMENT,
-                                           (unsigned)h.seed_key, (unsigned)(h.seed_key >> 32));
-        unsigned cell[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          cell[k] = ppg_bounded(r.v[k], (unsigned)GG);
-          atomicMin(&first[cell[k]], idx0 + k);
+      const int n_total = p.n_init[0] + p.n_init[1] + p.n_grass;
+      // cells in the order predators, prey, grass (BASE:185-187); staged in the entity/staging area
+      int* cells = reinterpret_cast<int*>(S.ent);         // [n_total]
+      unsigned* first = reinterpret_cast<unsigned*>(S.ent) + n_total;  // [GG] draw index that claimed the cell
+      bool from_tape = false;
+      if (p.tape_cells != nullptr) {
+        if (h.tape_pos + n_total <= h.tape_end) {
+          for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
+          h.tape_pos += n_total;
+          from_tape = true;
+        } else {
+          h.status |= PPG_STATUS_TAPE_EXHAUSTED;
         }
-        __syncwarp();
-        int mine = 0;
-        bool ok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k; mine += ok[k]; }
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-        int posn = accepted + incl - mine;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (ok[k]) { if (posn < n_total) cells[posn] = (int)cell[k]; ++posn; }
-        accepted += __shfl_sync(FULL, incl, 31);
-        __syncwarp();
       }
-    }
-    __syncwarp();
-    // founders: slots in numeric id order (BASE:143-145,190-200)
-    {
-      int k0 = 0;
+      if (!from_tape) {
+        // Philox rejection draws, accepted in draw order until n_total unique cells (law of BASE:156-177)
+        for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        int accepted = 0;
+        for (unsigned batch = 0; accepted < n_total; ++batch) {
+          const unsigned idx0 = batch * 128u + 4u * lane;
+          const ppg_u32x4 r = ppg_philox4x32((unsigned)env, h.episode, idx0 >> 2, PPG_STREAM_PLACEMENT,
+                                             (unsigned)h.seed_key, (unsigned)(h.seed_key >> 32));
+          unsigned cell[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            cell[k] = ppg_bounded(r.v[k], (unsigned)GG);
+            atomicMin(&first[cell[k]], idx0 + k);
+          }
+          __syncwarp();
+          int mine = 0;
+          bool ok[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k; mine += ok[k]; }
+          int incl = mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+          int posn = accepted + incl - mine;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (ok[k]) { if (posn < n_total) cells[posn] = (int)cell[k]; ++posn; }
+          accepted += __shfl_sync(FULL, incl, 31);
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < GG; i += 32) { S.own[0][i] = 0; S.own[1][i] = 0; }
+      __syncwarp();
+      // founders: slots in numeric id order (BASE:143-145,190-200)
+      {
+        int k0 = 0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          for (int i = lane; i < p.n_init[s]; i += 32) {
+            const int c = cells[k0 + i];
+            S.id[s][i] = (uint16_t)i;
+            S.pos[s][i] = (uint16_t)(((c / G) << 8) | (c % G));
+            S.E[s][i] = p.init_e[s];
+            S.flg[s][i] = F_ALIVE;
+            if (kick) S.par[s][i] = 0xFFFF;
+            S.ord[s][i] = (uint16_t)i;
+            S.own[s][c] = (uint16_t)(i + 1);  // BASE:195,200 (cells are unique)
+          }
+          k0 += p.n_init[s];
+          n[s] = p.n_init[s];
+          h.n_list[s] = (unsigned short)p.n_init[s];
+          h.n_sorted[s] = (unsigned short)p.n_init[s];
+          h.next_idx[s] = (unsigned short)p.n_init[s];
+        }
+        for (int g = lane; g < p.n_grass; g += 32) {
+          const int c = cells[k0 + g];
+          S.gpos[g] = (uint16_t)(((c / G) << 8) | (c % G));
+          S.gE[g] = p.grass_cap;  // BASE:203-208
+        }
+      }
+      __syncwarp();
+      cur[0] = n[0]; cur[1] = n[1];
+      next_live[0] = n[0]; next_live[1] = n[1];
+      env_flags = PPG_ENV_RESET;
+    } else if (mode == 2) {
+      // ------------------------------------------------------------------ step() (BASE:219-473)
+      n[0] = h.n_list[0]; n[1] = h.n_list[1];
+      // clear the maps while the loads are in flight
+      for (int i = lane; i < (GG + 1) / 2; i += 32) {
+        reinterpret_cast<unsigned*>(S.own[0])[i] = 0u;
+        reinterpret_cast<unsigned*>(S.own[1])[i] = 0u;
+      }
+      for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.gmap)[i] = 0u;
+      // load the lists; list order = action-dict order (default: row order of the previous output)
+      unsigned bad = 0;
+      bool resort[2] = {false, false};
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        for (int i = lane; i < p.n_init[s]; i += 32) {
-          const int c = cells[k0 + i];
-          S.id[s][i] = (uint16_t)i;
-          S.pos[s][i] = (uint16_t)(((c / G) << 8) | (c % G));
-          S.E[s][i] = p.init_e[s];
-          S.flg[s][i] = F_ALIVE;
-          if (kick) S.par[s][i] = 0xFFFF;
-          S.ord[s][i] = (uint16_t)i;
-        }
-        k0 += p.n_init[s];
-        n[s] = p.n_init[s];
-        h.n_list[s] = (unsigned short)p.n_init[s];
-        h.next_idx[s] = (unsigned short)p.n_init[s];
-      }
-      for (int g = lane; g < p.n_grass; g += 32) {
-        const int c = cells[k0 + g];
-        S.gpos[g] = (uint16_t)(((c / G) << 8) | (c % G));
-        S.gE[g] = p.grass_cap;
-      }
-    }
-    __syncwarp();
-    // build the grid (BASE:195,200,208)
-    for (int i = lane; i < (3 * CH) / 4; i += 32) reinterpret_cast<float4*>(S.grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      for (int i = lane; i < n[s]; i += 32) S.grid[s * CH + IDX((unsigned)S.pos[s][i])] = (float)p.init_e[s];
-    for (int g = lane; g < p.n_grass; g += 32) S.grid[2 * CH + IDX((unsigned)S.gpos[g])] = (float)p.grass_cap;
-    __syncwarp();
-    cur[0] = n[0]; cur[1] = n[1];
-    next_live[0] = n[0]; next_live[1] = n[1];
-    env_flags = PPG_ENV_RESET;
-  } else if (mode == 2) {
-    // ------------------------------------------------------------------ step() (BASE:219-473)
-    n[0] = h.n_list[0]; n[1] = h.n_list[1];
-    // clear the grid while the loads are in flight
-    for (int i = lane; i < (3 * CH) / 4; i += 32) reinterpret_cast<float4*>(S.grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.gmap)[i] = 0u;
-    // load the lists (list order = action-dict order = row order of the previous output)
-    unsigned bad = 0;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const size_t b = (size_t)env * p.cap[s];
-      for (int i = lane; i < n[s]; i += 32) {
-        S.id[s][i] = p.ag_id[s][b + i];
-        S.pos[s][i] = p.ag_pos[s][b + i];
-        const double e = p.ag_e[s][b + i];
-        int a = p.actions[s][p.ag_prow[s][b + i]];
-        if ((unsigned)a > 8u) { a = 4; bad = PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
-        if (dense) S.E0[s][i] = e;      // energy_before (ADD:256)
-        S.E[s][i] = e - p.loss[s];      // Step 1 (BASE:244-250)
-        S.act[s][i] = (uint8_t)a;
-        S.flg[s][i] = F_ALIVE;
-        S.ord[s][i] = (uint16_t)i;
-        S.rnk[s][i] = (uint16_t)i;
-        if (kick) { S.par[s][i] = p.ag_par[s][b + i]; S.aux[s][i] = 0; }
-      }
-    }
-    h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
-    for (int g = lane; g < p.n_grass; g += 32) {
-      const size_t b = (size_t)env * p.n_grass;
-      S.gpos[g] = p.gr_pos[b + g];
-      const double v = p.gr_e[b + g] + p.grass_gain;  // regrowth (BASE:252-256)
-      S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
-    }
-    __syncwarp();
-    // rebuild the grid as it stands after Step 1 (equals the persistent grid)
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      for (int b0 = 0; b0 < n[s]; b0 += 32) {
-        const int i = b0 + lane;
-        const bool v = i < n[s];
-        const unsigned m = __ballot_sync(FULL, v);
-        if (v) {
-          const unsigned ps = S.pos[s][i];
-          const unsigned grp = __match_any_sync(m, ps);
-          // agents sharing a cell: the one latest in dict order wrote last (BASE:247,250)
-          if (lane == 31 - __clz(grp)) S.grid[s * CH + IDX(ps)] = (float)S.E[s][i];
-        }
-        __syncwarp();
-      }
-    for (int g = lane; g < p.n_grass; g += 32) {
-      const unsigned ps = S.gpos[g];
-      S.grid[2 * CH + IDX(ps)] = (float)S.gE[g];
-      S.gmap[(ps >> 8) * G + (ps & 255)] = (uint8_t)(g + 1);
-    }
-    __syncwarp();
-
-    // Step 2: movements, sequential in dict order per species (BASE:259-273,495-509).
-    // Warp-uniform: every lane replays the same chain, so no intra-warp sync is needed.
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      float* gr = S.grid + s * CH;
-      for (int j = 0; j < n[s]; ++j) {
-        const unsigned ps = S.pos[s][j];
-        const int a = S.act[s][j];
-        const int x = ps >> 8, y = ps & 255;
-        const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
-        const int nx0 = min(max(x + ax - 1, 0), G - 1), ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
-        const bool blocked = gr[PP + (nx0 + PP) * PS + ny0] > 0.f;  // own-species channel occupied (BASE:506)
-        const int nx = blocked ? x : nx0, ny = blocked ? y : ny0;
-        gr[PP + (x + PP) * PS + y] = 0.f;                       // BASE:268,272
-        gr[PP + (nx + PP) * PS + ny] = (float)S.E[s][j];        // BASE:269,273
-        S.pos[s][j] = (uint16_t)((nx << 8) | ny);
-      }
-    }
-
-    // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (h.sortflag & (1 << s)) {
-        const uint16_t* lr = p.lexrank[s];
-        for (int i = lane; i < n[s]; i += 32) S.ord[s][i] = __ldg(lr + S.id[s][i]);
-        __syncwarp();
-        for (int i = lane; i < n[s]; i += 32) {
-          const unsigned key = S.ord[s][i];
-          int r = 0;
-          for (int k = 0; k < n[s]; ++k) r += S.ord[s][k] < key;
-          S.rnk[s][i] = (uint16_t)r;
-        }
-        __syncwarp();
-        for (int i = lane; i < n[s]; i += 32) S.ord[s][S.rnk[s][i]] = (uint16_t)i;
-        __syncwarp();
-      }
-    }
-
-    // Step 3a: predators in engagement order (BASE:279-346)
-    for (int k = 0; k < n[0]; ++k) {
-      const int slot = S.ord[0][k];
-      const unsigned ps = S.pos[0][slot];
-      const int cell = IDX(ps);
-      double e = S.E[0][slot];
-      if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
-        __syncwarp();
-        write_row_slow(p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], S.grid + cell, p, 0, lane, wall_delta);
-        __syncwarp();
-        S.grid[cell] = 0.f;
-        S.flg[0][slot] = F_DIED;
-        st_starved[0]++;
-        continue;
-      }
-      // first prey in agent_positions order (= lowest id) on my cell (BASE:305-312)
-      unsigned best = 0xFFFFFFFFu;
-      for (int i = lane; i < n[1]; i += 32)
-        if ((S.flg[1][i] & F_ALIVE) && S.pos[1][i] == ps) best = min(best, ((unsigned)S.id[1][i] << 16) | (unsigned)i);
-      best = __reduce_min_sync(FULL, best);
-      if (best != 0xFFFFFFFFu) {
-        const int q = best & 0xFFFF;
-        e += S.E[1][q];  // BASE:324 (also when the prey's energy is <= 0)
-        S.E[0][slot] = e;
-        S.grid[cell] = (float)e;  // BASE:325
-        S.flg[0][slot] |= F_ATE;
-        __syncwarp();
-        write_row_slow(p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], S.grid + cell, p, 1, lane, wall_delta);  // BASE:327
-        __syncwarp();
-        S.grid[CH + cell] = 0.f;  // BASE:335
-        S.flg[1][q] = F_DIED | F_CAUGHT;
-        st_eaten++;
-      }
-    }
-    // Step 3b: prey in engagement order (BASE:347-380)
-    for (int k = 0; k < n[1]; ++k) {
-      const int slot = S.ord[1][k];
-      if (!(S.flg[1][slot] & F_ALIVE)) continue;  // caught above (BASE:281)
-      const unsigned ps = S.pos[1][slot];
-      const int cell = IDX(ps);
-      double e = S.E[1][slot];
-      if (e <= 0.0) {
-        __syncwarp();
-        write_row_slow(p.obs[1] + (size_t)(old_base[1] + k) * p.elems[1], S.grid + cell, p, 1, lane, wall_delta);
-        __syncwarp();
-        S.grid[CH + cell] = 0.f;
-        S.flg[1][slot] = F_DIED;
-        st_starved[1]++;
-        continue;
-      }
-      const int g = S.gmap[(ps >> 8) * G + (ps & 255)];
-      if (g) {  // BASE:351-372 (a patch with energy 0 is still "eaten")
-        e += S.gE[g - 1];
-        S.E[1][slot] = e;
-        S.grid[CH + cell] = (float)e;
-        S.grid[2 * CH + cell] = 0.f;
-        S.gE[g - 1] = 0.0;
-        S.flg[1][slot] |= F_ATE;
-        st_grass++;
-      }
-    }
-
-    // Step 5: births in engagement order, predators then prey (BASE:389-448)
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      for (int b0 = 0; b0 < n[s]; b0 += 32) {
-        const int k = b0 + lane;
-        int slot = 0;
-        bool elig = false;
-        if (k < n[s]) {
-          slot = S.ord[s][k];
-          elig = (S.flg[s][slot] & F_ALIVE) && S.E[s][slot] >= p.thr[s];
-        }
-        unsigned m = __ballot_sync(FULL, elig);
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const int ps_slot = __shfl_sync(FULL, slot, l);
-          if (h.next_idx[s] >= p.n_possible[s]) continue;  // id pool empty (BASE:395,424)
-          if (n[s] + births[s] >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
-          const unsigned pp = S.pos[s][ps_slot];
-          const int px = pp >> 8, py = pp & 255;
-          int nl[2] = {n[0] + births[0], n[1] + births[1]};
-          // _find_available_spawn_position (BASE:738-766)
-          int sx = -1, sy = -1;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int cx = px + (c == 0 ? -1 : (c == 1 ? 1 : 0));
-            const int cy = py + (c == 2 ? -1 : (c == 3 ? 1 : 0));
-            if (sx < 0 && cx >= 0 && cx < G && cy >= 0 && cy < G) {
-              if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
-            }
+        const size_t b = (size_t)env * p.cap[s];
+        const int32_t* ordp = p.order[s];
+        bool use_order = ordp != nullptr;
+        if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to row order
+          bool ok = true;
+          for (int i = lane; i < n[s]; i += 32) {
+            const int d = ordp[p.ag_prow[s][b + i]];
+            if ((unsigned)d < (unsigned)n[s]) S.rnk[s][d] = (uint16_t)i; else ok = false;
           }
-          if (sx < 0) {
-            st_fallback++;
-            if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
-              const int c = p.tape_cells[h.tape_pos++];  // recorded np.random.randint choice (BASE:764)
-              sx = c / G; sy = c % G;
-            } else {
-              if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
-              // uniformly random free cell, ascending cell order, Philox draw
-              int n_free = 0;
-              for (int c0 = 0; c0 < GG; c0 += 32) {
-                const int c = c0 + lane;
-                bool fr = c < GG;
-                if (fr) {
-                  const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-                  for (int s2 = 0; s2 < 2; ++s2)
-                    for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
-                }
-                n_free += __popc(__ballot_sync(FULL, fr));
+          __syncwarp();
+          for (int i = lane; i < n[s]; i += 32) {
+            const int d = ordp[p.ag_prow[s][b + i]];
+            if ((unsigned)d < (unsigned)n[s]) ok &= S.rnk[s][d] == (uint16_t)i;
+          }
+          use_order = __all_sync(FULL, ok);
+          if (!use_order) bad = PPG_STATUS_BAD_ACTION;
+          __syncwarp();
+        }
+        resort[s] = use_order;
+        for (int i = lane; i < n[s]; i += 32) {
+          const int prow = p.ag_prow[s][b + i];
+          const int d = use_order ? ordp[prow] : i;
+          const double e = p.ag_e[s][b + i];
+          int a = p.actions[s][prow];
+          if ((unsigned)a > 8u) { a = 4; bad = PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
+          S.id[s][d] = p.ag_id[s][b + i];
+          S.pos[s][d] = p.ag_pos[s][b + i];
+          if (dense) S.E0[s][d] = e;  // energy_before (ADD:256)
+          S.E[s][d] = e - p.loss[s];  // Step 1 (BASE:244-250)
+          S.act[s][d] = (uint8_t)a;
+          S.flg[s][d] = F_ALIVE;
+          S.ord[s][d] = (uint16_t)d;
+          S.rnk[s][d] = (uint16_t)d;
+          if (kick) { S.par[s][d] = p.ag_par[s][b + i]; S.aux[s][d] = 0; }
+        }
+      }
+      h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
+      for (int g = lane; g < p.n_grass; g += 32) {
+        const size_t b = (size_t)env * p.n_grass;
+        S.gpos[g] = p.gr_pos[b + g];
+        const double v = p.gr_e[b + g] + p.grass_gain;  // regrowth (BASE:252-256)
+        S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+      }
+      __syncwarp();
+      // owner maps as the grid stands after Step 1: of agents sharing a cell the one latest in dict
+      // order wrote last (BASE:247,250)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+          const int i = b0 + lane;
+          const bool v = i < n[s];
+          int cell = 0;
+          if (v) { cell = CELL((unsigned)S.pos[s][i]); S.own[s][cell] = (uint16_t)(i + 1); }
+          __syncwarp();
+          bool need = v && S.own[s][cell] < (unsigned)(i + 1);
+          while (__any_sync(FULL, need)) {
+            if (need) S.own[s][cell] = (uint16_t)(i + 1);
+            __syncwarp();
+            need = v && S.own[s][cell] < (unsigned)(i + 1);
+          }
+        }
+      for (int g = lane; g < p.n_grass; g += 32) S.gmap[CELL((unsigned)S.gpos[g])] = (uint8_t)(g + 1);
+      __syncwarp();
+
+      // Step 2: movements, sequential semantics in dict order per species (BASE:259-273,495-509)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        uint16_t* own = S.own[s];
+        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+          const int j = b0 + lane;
+          const bool v = j < n[s];
+          int oc = 0, tc = 0, x = 0, y = 0, nx0 = 0, ny0 = 0;
+          if (v) {
+            const unsigned ps = S.pos[s][j];
+            const int a = S.act[s][j];
+            x = ps >> 8; y = ps & 255;
+            const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
+            nx0 = min(max(x + ax - 1, 0), G - 1); ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
+            oc = x * G + y; tc = nx0 * G + ny0;
+            atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
+            if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+          }
+          __syncwarp();
+          const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);
+          __syncwarp();
+          if (v) { S.scr[oc] = 0; S.scr[tc] = 0; }
+          if (v && !dirty) {
+            // nobody else in this chunk touches my cells: the outcome does not depend on the order
+            const unsigned ow = own[tc];
+            const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;  // own-species channel occupied (BASE:506)
+            const int nc = blocked ? oc : tc;
+            own[oc] = 0;                    // BASE:268,272
+            own[nc] = (uint16_t)(j + 1);    // BASE:269,273
+            if (!blocked) S.pos[s][j] = (uint16_t)((nx0 << 8) | ny0);
+          }
+          __syncwarp();
+          unsigned dm = __ballot_sync(FULL, dirty);
+          while (dm) {  // warp-uniform replay, in dict order, of the agents that may interact
+            const int jj = b0 + __ffs(dm) - 1;
+            dm &= dm - 1;
+            const unsigned ps = S.pos[s][jj];
+            const int a = S.act[s][jj];
+            const int xx = ps >> 8, yy = ps & 255;
+            const int ax = (a * 11) >> 5;
+            const int tx = min(max(xx + ax - 1, 0), G - 1), ty = min(max(yy + (a - 3 * ax) - 1, 0), G - 1);
+            const unsigned ow = own[tx * G + ty];
+            const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;
+            const int nx = blocked ? xx : tx, ny = blocked ? yy : ty;
+            __syncwarp();
+            own[xx * G + yy] = 0;
+            own[nx * G + ny] = (uint16_t)(jj + 1);
+            S.pos[s][jj] = (uint16_t)((nx << 8) | ny);
+            __syncwarp();
+          }
+        }
+      }
+
+      // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order.  The list is
+      // the sorted survivors followed by last step's newborns, so only the newborns have to be ranked in.
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (resort[s] || (h.sortflag & (1 << s))) {
+          const uint16_t* lr = p.lexrank[s];
+          const bool by_id = h.first_step != 0;  // right after reset() self.agents is in numeric order (BASE:143-145)
+          const int ns = resort[s] ? 0 : min((int)h.n_sorted[s], n[s]);
+          for (int i = lane; i < n[s]; i += 32) S.ord[s][i] = by_id ? S.id[s][i] : __ldg(lr + S.id[s][i]);
+          __syncwarp();
+          for (int i = lane; i < n[s]; i += 32) {
+            const unsigned key = S.ord[s][i];
+            int r = i < ns ? i : 0;
+            for (int k = (i < ns ? ns : 0); k < n[s]; ++k) r += S.ord[s][k] < key;
+            S.rnk[s][i] = (uint16_t)r;
+          }
+          __syncwarp();
+          for (int i = lane; i < n[s]; i += 32) S.ord[s][S.rnk[s][i]] = (uint16_t)i;
+          __syncwarp();
+        }
+      }
+
+      // Step 3a: predators in engagement order (BASE:279-346).  Nothing happens unless a predator
+      // starved or some prey (any energy) stands on a live predator's cell.
+      bool ev = false;
+      for (int i = lane; i < n[0]; i += 32) {
+        if (S.E[0][i] <= 0.0) ev = true;
+        else S.scr[CELL((unsigned)S.pos[0][i])] = 1;
+      }
+      __syncwarp();
+      for (int i = lane; i < n[1]; i += 32) ev |= S.scr[CELL((unsigned)S.pos[1][i])] != 0;
+      __syncwarp();
+      for (int i = lane; i < n[0]; i += 32) S.scr[CELL((unsigned)S.pos[0][i])] = 0;
+      __syncwarp();
+      if (__any_sync(FULL, ev)) {
+        for (int k = 0; k < n[0]; ++k) {
+          const int slot = S.ord[0][k];
+          const unsigned ps = S.pos[0][slot];
+          const int cell = CELL(ps);
+          double e = S.E[0][slot];
+          if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
+            emit_row_now(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], ps, 0, n[0], n[1], &rowctr, lane);
+            S.own[0][cell] = 0;  // BASE:293
+            S.flg[0][slot] = F_DIED;
+            st_starved[0]++;
+            __syncwarp();
+            continue;
+          }
+          // first prey in agent_positions order (= lowest id) on my cell (BASE:305-312)
+          unsigned best = 0xFFFFFFFFu;
+          for (int i = lane; i < n[1]; i += 32)
+            if ((S.flg[1][i] & F_ALIVE) && S.pos[1][i] == ps) best = min(best, ((unsigned)S.id[1][i] << 16) | (unsigned)i);
+          best = __reduce_min_sync(FULL, best);
+          if (best != 0xFFFFFFFFu) {
+            const int q = best & 0xFFFF;
+            e += S.E[1][q];  // BASE:324 (also when the prey's energy is <= 0)
+            __syncwarp();
+            S.E[0][slot] = e;
+            S.own[0][cell] = (uint16_t)(slot + 1);  // BASE:325
+            S.flg[0][slot] |= F_ATE;
+            __syncwarp();
+            emit_row_now(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], ps, 1, n[0], n[1], &rowctr, lane);  // BASE:327
+            S.own[1][cell] = 0;  // BASE:335
+            S.flg[1][q] = F_DIED | F_CAUGHT;
+            st_eaten++;
+            __syncwarp();
+          }
+        }
+      }
+
+      // Step 3b: prey in engagement order (BASE:347-380)
+      for (int b0 = 0; b0 < n[1]; b0 += 32) {
+        const int k = b0 + lane;
+        int slot = 0, cell = 0, g = 0;
+        bool alive = false, starved = false;
+        double e = 0.0;
+        if (k < n[1]) {
+          slot = S.ord[1][k];
+          alive = (S.flg[1][slot] & F_ALIVE) != 0;  // not caught above (BASE:281)
+          e = S.E[1][slot];
+          starved = alive && e <= 0.0;
+          cell = CELL((unsigned)S.pos[1][slot]);
+          g = S.gmap[cell];
+        }
+        const bool eat = alive && !starved && g != 0;
+        if (eat) S.gtag[g - 1] = (uint8_t)lane;
+        __syncwarp();
+        const bool clash = eat && S.gtag[g - 1] != (uint8_t)lane;  // two prey of this chunk on one patch
+        if (!__any_sync(FULL, starved || clash)) {
+          if (eat) {  // BASE:351-372 (a patch with energy 0 is still "eaten")
+            S.E[1][slot] = e + S.gE[g - 1];
+            S.own[1][cell] = (uint16_t)(slot + 1);
+            S.gE[g - 1] = 0.0;
+            S.flg[1][slot] |= F_ATE;
+          }
+          st_grass += __popc(__ballot_sync(FULL, eat));
+          __syncwarp();
+          continue;
+        }
+        __syncwarp();
+        const int kend = min(b0 + 32, n[1]);
+        for (int kk = b0; kk < kend; ++kk) {  // exact sequential order for this chunk
+          const int sl = S.ord[1][kk];
+          if (!(S.flg[1][sl] & F_ALIVE)) continue;
+          const unsigned ps = S.pos[1][sl];
+          const int cl = CELL(ps);
+          const double ee = S.E[1][sl];
+          if (ee <= 0.0) {  // BASE:284-301
+            emit_row_now(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], ps, 1, n[0], n[1], &rowctr, lane);
+            S.own[1][cl] = 0;
+            S.flg[1][sl] = F_DIED;
+            st_starved[1]++;
+            __syncwarp();
+            continue;
+          }
+          const int gg = S.gmap[cl];
+          if (gg) {
+            const double en = ee + S.gE[gg - 1];
+            __syncwarp();
+            S.E[1][sl] = en;
+            S.own[1][cl] = (uint16_t)(sl + 1);
+            S.gE[gg - 1] = 0.0;
+            S.flg[1][sl] |= F_ATE;
+            st_grass++;
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+
+      // Step 5: births in engagement order, predators then prey (BASE:389-448)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+          const int k = b0 + lane;
+          int slot = 0;
+          bool elig = false;
+          if (k < n[s]) {
+            slot = S.ord[s][k];
+            elig = (S.flg[s][slot] & F_ALIVE) && S.E[s][slot] >= p.thr[s];
+          }
+          unsigned m = __ballot_sync(FULL, elig);
+          while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int ps_slot = __shfl_sync(FULL, slot, l);
+            if (h.next_idx[s] >= p.n_possible[s]) continue;  // id pool empty (BASE:395,424)
+            if (n[s] + births[s] >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
+            const unsigned pp = S.pos[s][ps_slot];
+            const int px = pp >> 8, py = pp & 255;
+            int nl[2] = {n[0] + births[0], n[1] + births[1]};
+            // _find_available_spawn_position (BASE:738-766)
+            int sx = -1, sy = -1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cx = px + (c == 0 ? -1 : (c == 1 ? 1 : 0));
+              const int cy = py + (c == 2 ? -1 : (c == 3 ? 1 : 0));
+              if (sx < 0 && cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
               }
-              if (n_free > 0) {
-                int kth = (int)ppg_bounded(ppg_draw_u32(h.seed_key, (unsigned)env, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), (unsigned)n_free);
-                h.spawn_draws++;
-                for (int c0 = 0; c0 < GG && sx < 0; c0 += 32) {
+            }
+            if (sx < 0) {
+              st_fallback++;
+              if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
+                const int c = p.tape_cells[h.tape_pos++];  // recorded np.random.randint choice (BASE:764)
+                sx = c / G; sy = c % G;
+              } else {
+                if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+                // uniformly random free cell, ascending cell order, Philox draw
+                int n_free = 0;
+                for (int c0 = 0; c0 < GG; c0 += 32) {
                   const int c = c0 + lane;
                   bool fr = c < GG;
                   if (fr) {
@@ -494,329 +717,398 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
                     for (int s2 = 0; s2 < 2; ++s2)
                       for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
                   }
-                  const unsigned fm = __ballot_sync(FULL, fr);
-                  const int cnt = __popc(fm);
-                  if (kth < cnt) {
-                    const int c = c0 + (int)__fns(fm, 0, kth + 1);
-                    sx = c / G; sy = c % G;
-                  } else {
-                    kth -= cnt;
+                  n_free += __popc(__ballot_sync(FULL, fr));
+                }
+                if (n_free > 0) {
+                  int kth = (int)ppg_bounded(ppg_draw_u32(h.seed_key, (unsigned)env, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), (unsigned)n_free);
+                  h.spawn_draws++;
+                  for (int c0 = 0; c0 < GG && sx < 0; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool fr = c < GG;
+                    if (fr) {
+                      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
+                      for (int s2 = 0; s2 < 2; ++s2)
+                        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
+                    }
+                    const unsigned fm = __ballot_sync(FULL, fr);
+                    const int cnt = __popc(fm);
+                    if (kth < cnt) {
+                      const int c = c0 + (int)__fns(fm, 0, kth + 1);
+                      sx = c / G; sy = c % G;
+                    } else {
+                      kth -= cnt;
+                    }
                   }
                 }
               }
+              if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises here
             }
-            if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises here
-          }
-          const int cs = n[s] + births[s];
-          births[s]++;
-          const int child_id = h.next_idx[s]++;  // BASE:396-397
-          S.id[s][cs] = (uint16_t)child_id;
-          S.pos[s][cs] = (uint16_t)((sx << 8) | sy);
-          S.E[s][cs] = p.init_e[s];           // BASE:403
-          S.flg[s][cs] = F_ALIVE | F_NEWBORN;
-          const double pe = S.E[s][ps_slot] - p.init_e[s];  // BASE:404
-          S.E[s][ps_slot] = pe;
-          S.grid[s * CH + PP + (sx + PP) * PS + sy] = (float)p.init_e[s];  // BASE:405
-          S.grid[s * CH + PP + (px + PP) * PS + py] = (float)pe;            // BASE:406
-          S.flg[s][ps_slot] |= F_REPRO;
-          if (kick) {  // KICK:434-449
-            S.aux[s][cs] = 0;
-            S.par[s][cs] = S.id[s][ps_slot];
-            S.aux[s][ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
-            const unsigned gp = S.par[s][ps_slot];
-            if (gp != 0xFFFFu) {
-              int gs = -1;
-              for (int i = lane; i < n[s] + births[s]; i += 32)
-                if ((S.flg[s][i] & F_ALIVE) && S.id[s][i] == gp) gs = i;
-              gs = __reduce_max_sync(FULL, gs);
-              if (gs >= 0) S.aux[s][gs]++;
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-
-    // counts, termination, truncation (BASE:456-471)
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      int c = 0;
-      for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
-      cur[s] = __reduce_add_sync(FULL, c);
-    }
-    h.step += 1;
-    const bool all_term = cur[1] <= 0 || cur[0] <= 0;
-    trunc = !all_term && h.step >= p.max_steps;  // BASE's extra truncation call (BASE:228-238) folded in
-    over = all_term || trunc;
-    env_flags = (all_term ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
-    if (over) {
-      if (p.autoreset) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
-    } else {
-      next_live[0] = cur[0]; next_live[1] = cur[1];
-    }
-  } else if (active) {
-    env_flags = PPG_ENV_IDLE;
-  }
-
-  // ---------------------------------------------------------------- row allocation across CTAs
-  if (lane == 0) {
-    s_cnt[warp][0] = next_live[0]; s_cnt[warp][1] = next_live[1];
-    s_cnt[warp][2] = births[0];    s_cnt[warp][3] = births[1];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    int agg[4], excl[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      int a = 0;
-#pragma unroll
-      for (int w = 0; w < W; ++w) a += s_cnt[w][v];
-      agg[v] = a;
-      excl[v] = 0;
-    }
-    unsigned long long* my = p.desc + (size_t)cta * 4;
-    const int my_agg = lane == 0 ? agg[0] : lane == 1 ? agg[1] : lane == 2 ? agg[2] : agg[3];
-    if (cta > 0) {
-      if (lane < 4) vstore(my + lane, DESC(1, p.epoch, my_agg));
-      unsigned done = 0;
-      int posn = (int)cta - 1;
-      unsigned spins = 0;
-      while (done != 0xF) {
-        const int pred = posn - lane;
-        unsigned long long w[4];
-        bool ok = true;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          w[v] = pred >= 0 ? vload(p.desc + (size_t)pred * 4 + v) : DESC(2, p.epoch, 0);
-          const bool valid = ((unsigned)(w[v] >> 32) & 0x3FFFFFFFu) == (p.epoch & 0x3FFFFFFFu) && (w[v] >> 62) != 0;
-          ok &= valid || ((done >> v) & 1);
-        }
-        if (!__all_sync(FULL, ok)) {
-          // a predecessor has not published yet; it is resident (tickets are handed out in start
-          // order), so this terminates — the cap only protects the box from a wedged launch
-          if (++spins > (1u << 22)) { if (lane == 0) atomicOr(p.error, 1u); break; }
-          __nanosleep(100);
-          continue;
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if ((done >> v) & 1) continue;
-          const unsigned pm = __ballot_sync(FULL, (w[v] >> 62) == 2);
-          const int fp = pm ? __ffs(pm) - 1 : 32;
-          const int contrib = lane <= fp ? (int)(unsigned)w[v] : 0;
-          excl[v] += __reduce_add_sync(FULL, contrib);
-          if (fp < 32) done |= 1u << v;
-        }
-        posn -= 32;
-      }
-    }
-    if (lane < 4) {
-      const int e = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : excl[3];
-      vstore(my + lane, DESC(2, p.epoch, e + my_agg));
-      s_incl[lane] = e + my_agg;
-      int run = e;
-      for (int w = 0; w < W; ++w) { s_base[w][lane] = run; run += s_cnt[w][lane]; }
-    }
-  }
-  __syncthreads();
-
-  const int n_old_total[2] = {p.next_off[0][p.B + 1 + totals_rd], p.next_off[1][p.B + 1 + totals_rd]};
-  if (cta == gridDim.x - 1 && warp == 0 && lane < 2) {
-    // last CTA in ticket order: totals of this output and of the next one
-    const int s = lane;
-    p.n_rows[s] = n_old_total[s];
-    p.n_rows[2 + s] = s_incl[2 + s];
-    p.old_off[s][p.B] = n_old_total[s];
-    p.new_off[s][p.B] = n_old_total[s] + s_incl[2 + s];
-    p.next_off[s][p.B + 1 + (totals_rd ^ 1)] = s_incl[s];
-  }
-  if (!active) return;
-
-  int new_base[2];
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    new_base[s] = n_old_total[s] + s_base[warp][2 + s];
-    if (lane == 0) {
-      p.old_off[s][env] = old_base[s];
-      p.new_off[s][env] = new_base[s];
-      p.next_off[s][env] = s_base[warp][s];
-    }
-  }
-
-  // ------------------------------------------------- rows: metadata, observations, state write-back
-  if (mode != 0) {
-    const bool keep = !(over && p.autoreset);  // lists of a finished env are dead when it auto-resets
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const RowRel rr = load_rel(p, s, lane, wall_delta);
-      const int tot = n[s] + births[s];
-      const size_t sb = (size_t)env * p.cap[s];
-      float* obs_s = p.obs[s];
-      const int elems = p.elems[s];
-      int wpos = 0;
-      for (int b0 = 0; b0 < tot; b0 += 32) {
-        const int k = b0 + lane;
-        int cellidx = -1, row = 0, slot = 0;
-        if (k < tot) {
-          const bool newborn = k >= n[s];
-          slot = newborn ? k : S.ord[s][k];
-          row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
-          const unsigned f = S.flg[s][slot];
-          const double e = S.E[s][slot];
-          double rew = 0.0;
-          if (mode == 2 && !newborn) {
-            if (dense) {
-              const double e0 = S.E0[s][slot];
-              if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
-              else rew = (e - e0) + ((mode_r == PPG_REWARD_DENSE_ADDITIVE && (f & F_REPRO)) ? p.r_repro[s] : 0.0);  // ADD:468-471
-            } else {
-              if (f & F_DIED) rew = (f & F_CAUGHT) ? p.pen_caught : 0.0;  // BASE:288,328
-              else {
-                rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);  // BASE:322,341,365,375
-                if (f & F_REPRO) rew = p.r_repro[s];  // BASE:409,438 overwrites
-                if (kick) for (int q = S.aux[s][slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
+            const int cs = n[s] + births[s];
+            births[s]++;
+            const int child_id = h.next_idx[s]++;  // BASE:396-397
+            const double pe = S.E[s][ps_slot] - p.init_e[s];  // BASE:404
+            __syncwarp();
+            S.id[s][cs] = (uint16_t)child_id;
+            S.pos[s][cs] = (uint16_t)((sx << 8) | sy);
+            S.E[s][cs] = p.init_e[s];  // BASE:403
+            S.flg[s][cs] = F_ALIVE | F_NEWBORN;
+            S.E[s][ps_slot] = pe;
+            S.own[s][sx * G + sy] = (uint16_t)(cs + 1);       // BASE:405
+            S.own[s][px * G + py] = (uint16_t)(ps_slot + 1);  // BASE:406
+            S.flg[s][ps_slot] |= F_REPRO;
+            if (kick) {  // KICK:434-449
+              S.aux[s][cs] = 0;
+              S.par[s][cs] = S.id[s][ps_slot];
+              S.aux[s][ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
+              const unsigned gp = S.par[s][ps_slot];
+              __syncwarp();
+              if (gp != 0xFFFFu) {
+                int gs = -1;
+                for (int i = lane; i < n[s] + births[s]; i += 32)
+                  if ((S.flg[s][i] & F_ALIVE) && S.id[s][i] == gp) gs = i;
+                gs = __reduce_max_sync(FULL, gs);
+                if (gs >= 0) {
+                  const uint8_t cnt = S.aux[s][gs];
+                  __syncwarp();
+                  S.aux[s][gs] = (uint8_t)(cnt + 1);
+                }
               }
             }
+            __syncwarp();
           }
-          unsigned rf = 0;
-          if (f & F_DIED) rf |= PPG_ROW_TERMINATED;
-          if ((f & F_ALIVE) && trunc) rf |= PPG_ROW_TRUNCATED;
-          if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
-          if (mode == 1) rf |= PPG_ROW_FOUNDER;
-          if (f & F_ATE) rf |= PPG_ROW_ATE;
-          p.row_env[s][row] = env;
-          p.row_agent[s][row] = S.id[s][slot];
-          p.reward[s][row] = (float)rew;
-          p.flags[s][row] = (uint8_t)rf;
-          if (f & F_ALIVE) cellidx = IDX((unsigned)S.pos[s][slot]);
-        }
-        unsigned m = __ballot_sync(FULL, cellidx >= 0);
-        // survivors in engagement order (= `self.agents` after the sort), then newborns (BASE:398,468)
-        if (keep && cellidx >= 0) {
-          const int dst = wpos + __popc(m & ((1u << lane) - 1));
-          p.ag_id[s][sb + dst] = S.id[s][slot];
-          p.ag_pos[s][sb + dst] = S.pos[s][slot];
-          p.ag_e[s][sb + dst] = S.E[s][slot];
-          p.ag_prow[s][sb + dst] = row;
-          if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
-        }
-        wpos += __popc(m);
-        // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const int ci = __shfl_sync(FULL, cellidx, l);
-          const int r = __shfl_sync(FULL, row, l);
-          write_row(obs_s + (size_t)r * elems, S.grid + ci, rr, lane);
         }
       }
-      if (keep) h.n_list[s] = (unsigned short)wpos;
-    }
-    if (over) {
-      h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;  // idle: final state stays readable
-    }
-    if (keep) {
-      unsigned char sf = 0;
-      if (mode == 2) {
-        if (births[0] > 0 || h.first_step) sf |= 1;
-        if (births[1] > 0 || h.first_step) sf |= 2;
-        h.first_step = 0;
+      __syncwarp();
+
+      // counts, termination, truncation (BASE:456-471)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        int c = 0;
+        for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
+        cur[s] = __reduce_add_sync(FULL, c);
       }
-      h.sortflag = sf;
-      const size_t gb = (size_t)env * p.n_grass;
-      for (int g = lane; g < p.n_grass; g += 32) {
-        p.gr_e[gb + g] = S.gE[g];
-        if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
+      h.step += 1;
+      const bool all_term = cur[1] <= 0 || cur[0] <= 0;
+      trunc = !all_term && h.step >= p.max_steps;  // BASE's extra truncation call (BASE:228-238) folded in
+      over = all_term || trunc;
+      env_flags = (all_term ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
+      if (over) {
+        if (p.autoreset) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+      } else {
+        next_live[0] = cur[0]; next_live[1] = cur[1];
       }
+    } else {
+      env_flags = PPG_ENV_IDLE;
     }
-    if (lane == 0) p.hdr[env] = h;
-    // per-env counters (PPG_STAT_*)
-    if (lane < PPG_N_STATS) {
-      unsigned add = 0;
-      if (mode == 2) {
-        switch (lane) {
-          case PPG_STAT_ENV_STEPS: add = 1; break;
-          case PPG_STAT_AGENT_STEPS: add = n[0] + n[1]; break;
-          case PPG_STAT_EPISODES: add = over; break;
-          case PPG_STAT_EPISODE_STEPS: add = over ? h.step : 0; break;
-          case PPG_STAT_BIRTHS_PRED: add = births[0]; break;
-          case PPG_STAT_BIRTHS_PREY: add = births[1]; break;
-          case PPG_STAT_STARVED_PRED: add = st_starved[0]; break;
-          case PPG_STAT_STARVED_PREY: add = st_starved[1]; break;
-          case PPG_STAT_EATEN_PREY: add = st_eaten; break;
-          case PPG_STAT_GRASS_EATEN: add = st_grass; break;
-          case PPG_STAT_TRUNCATED: add = trunc; break;
-          case PPG_STAT_SPAWN_FALLBACK: add = st_fallback; break;
-          default: break;
+
+    // ---------------------------------------------------------------- publish the counts
+    {
+      const int blk = env >> 5, grp = env >> 10;
+      bool last = false;
+      if (lane == 0) {
+        st_volatile(p.cntA[par] + env, TAG(epoch, (next_live[0] << 16) | next_live[1]));
+        st_volatile(p.cntB[par] + env, TAG(epoch, (births[0] << 16) | births[1]));
+        __threadfence();
+        const unsigned bsz = (unsigned)min(32, p.B - (blk << 5));
+        last = (atomicAdd(p.done1 + blk, 1u) + 1u) % bsz == 0u;
+      }
+      if (__shfl_sync(FULL, last, 0)) {  // last env of its 32-env block: block sums
+        __threadfence();
+        const int e2 = (blk << 5) + lane;
+        unsigned long long a = 0, b = 0;
+        if (e2 < p.B) { a = ld_volatile(p.cntA[par] + e2); b = ld_volatile(p.cntB[par] + e2); }
+        int v[4] = {(int)((a >> 16) & 0xFFFF), (int)(a & 0xFFFF), (int)((b >> 16) & 0xFFFF), (int)(b & 0xFFFF)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __reduce_add_sync(FULL, v[q]);
+        if (lane < 4) st_volatile(p.sum1[par] + (size_t)blk * 4 + lane, TAG(epoch, lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3]));
+        __threadfence();
+        __syncwarp();
+        bool last2 = false;
+        if (lane == 0) {
+          const unsigned gsz = (unsigned)min(32, n_blk - (grp << 5));
+          last2 = (atomicAdd(p.done2 + grp, 1u) + 1u) % gsz == 0u;
+        }
+        if (__shfl_sync(FULL, last2, 0)) {  // last block of its group: group sums
+          __threadfence();
+          const int b2 = (grp << 5) + lane;
+          int w[4] = {0, 0, 0, 0};
+          if (b2 < n_blk) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = (int)(unsigned)ld_volatile(p.sum1[par] + (size_t)b2 * 4 + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = __reduce_add_sync(FULL, w[q]);
+          if (lane < 4) st_volatile(p.sum2[par] + (size_t)grp * 4 + lane, TAG(epoch, lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]));
+          __threadfence();
+          __syncwarp();
+          bool last3 = false;
+          if (lane == 0) {
+            last3 = (atomicAdd(p.done3, 1u) + 1u) % (unsigned)n_grp == 0u;
+          }
+          if (__shfl_sync(FULL, last3, 0)) {  // last group: totals of this output and of the next one
+            __threadfence();
+            int t[4] = {0, 0, 0, 0};
+            for (int g = lane; g < n_grp; g += 32) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) t[q] += (int)(unsigned)ld_volatile(p.sum2[par] + (size_t)g * 4 + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = __reduce_add_sync(FULL, t[q]);
+            if (lane < 2) {
+              const int s = lane;
+              p.totals[par * 4 + s] = s == 0 ? t[0] : t[1];
+              p.totals[par * 4 + 2 + s] = s == 0 ? t[2] : t[3];
+              p.n_rows[s] = n_old_total[s];
+              p.n_rows[2 + s] = s == 0 ? t[2] : t[3];
+              p.old_off[s][p.B] = n_old_total[s];
+            }
+          }
         }
       }
-      if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
-      if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
-      if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
     }
+
+    // ------------------------------------------------- rows: metadata, observations, state write-back
+    if (lane == 0) {
+      p.old_off[0][env] = old_base[0];
+      p.old_off[1][env] = old_base[1];
+    }
+    if (mode != 0) {
+      const bool keep = !(over && p.autoreset);  // lists of a finished env are dead when it auto-resets
+      const int n_ent = build_entities(sbase, p, n[0] + births[0], n[1] + births[1], lane);
+      int wpos[2] = {0, 0};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const size_t sb = (size_t)env * p.cap[s];
+        float* obs_s = p.obs[s];
+        const int elems = p.elems[s];
+        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+          const int k = b0 + lane;
+          int row = 0, slot = 0;
+          unsigned apos = 0;
+          bool alive = false;
+          if (k < n[s]) {
+            slot = S.ord[s][k];
+            row = old_base[s] + k;
+            const unsigned f = S.flg[s][slot];
+            const double e = S.E[s][slot];
+            double rew = 0.0;
+            if (mode == 2) {
+              if (dense) {
+                const double e0 = S.E0[s][slot];
+                if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
+                else rew = (e - e0) + ((mode_r == PPG_REWARD_DENSE_ADDITIVE && (f & F_REPRO)) ? p.r_repro[s] : 0.0);  // ADD:468-471
+              } else {
+                if (f & F_DIED) rew = (f & F_CAUGHT) ? p.pen_caught : 0.0;  // BASE:288,328
+                else {
+                  rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);  // BASE:322,341,365,375
+                  if (f & F_REPRO) rew = p.r_repro[s];  // BASE:409,438 overwrites
+                  if (kick) for (int q = S.aux[s][slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
+                }
+              }
+            }
+            unsigned rf = 0;
+            if (f & F_DIED) rf |= PPG_ROW_TERMINATED;
+            if ((f & F_ALIVE) && trunc) rf |= PPG_ROW_TRUNCATED;
+            if (mode == 1) rf |= PPG_ROW_FOUNDER;
+            if (f & F_ATE) rf |= PPG_ROW_ATE;
+            p.row_env[s][row] = env;
+            p.row_agent[s][row] = S.id[s][slot];
+            p.reward[s][row] = (float)rew;
+            p.flags[s][row] = (uint8_t)rf;
+            alive = (f & F_ALIVE) != 0;
+            apos = S.pos[s][slot];
+          }
+          unsigned m = __ballot_sync(FULL, alive);
+          // survivors in engagement order (= `self.agents` after the sort), newborns follow (BASE:398,468)
+          if (keep && alive) {
+            const int dst = wpos[s] + __popc(m & lt_mask);
+            p.ag_id[s][sb + dst] = S.id[s][slot];
+            p.ag_pos[s][sb + dst] = (uint16_t)apos;
+            p.ag_e[s][sb + dst] = S.E[s][slot];
+            p.ag_prow[s][sb + dst] = row;
+            if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
+          }
+          wpos[s] += __popc(m);
+          // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
+          while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned ap = __shfl_sync(FULL, apos, l);
+            const int r = __shfl_sync(FULL, row, l);
+            emit_row(p, S, obs_s + (size_t)r * elems, ap, s, n_ent, rowctr, wq[s], lane);
+          }
+        }
+      }
+      // newborn rows: their first row depends on the births of every env before this one
+      int new_base[2] = {0, 0};
+      if (births[0] + births[1] > 0) {
+        int nb0 = 0, nb1 = 0;
+        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+          if (lane == 0) atomicOr(p.error, 1u);
+        }
+        new_base[0] = n_old_total[0] + nb0;
+        new_base[1] = n_old_total[1] + nb1;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const size_t sb = (size_t)env * p.cap[s];
+          for (int b0 = 0; b0 < births[s]; b0 += 32) {
+            const int j = b0 + lane;
+            unsigned apos = 0;
+            int row = 0;
+            const bool v = j < births[s];
+            if (v) {
+              const int slot = n[s] + j;
+              row = new_base[s] + j;
+              apos = S.pos[s][slot];
+              p.row_env[s][row] = env;
+              p.row_agent[s][row] = S.id[s][slot];
+              p.reward[s][row] = 0.f;  // BASE:408,437
+              p.flags[s][row] = (uint8_t)(PPG_ROW_NEWBORN | (trunc ? PPG_ROW_TRUNCATED : 0));
+              if (keep) {
+                const int dst = wpos[s] + j;
+                p.ag_id[s][sb + dst] = S.id[s][slot];
+                p.ag_pos[s][sb + dst] = (uint16_t)apos;
+                p.ag_e[s][sb + dst] = S.E[s][slot];
+                p.ag_prow[s][sb + dst] = row;
+                if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
+              }
+            }
+            unsigned m = __ballot_sync(FULL, v);
+            while (m) {
+              const int l = __ffs(m) - 1;
+              m &= m - 1;
+              const unsigned ap = __shfl_sync(FULL, apos, l);
+              const int r = __shfl_sync(FULL, row, l);
+              emit_row(p, S, p.obs[s] + (size_t)r * p.elems[s], ap, s, n_ent, rowctr, wq[s], lane);
+            }
+          }
+        }
+      }
+      if (lane < 2) {
+        const int nb = lane == 0 ? births[0] : births[1];
+        p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
+        p.new_cnt[lane][env] = nb;
+      }
+      if (keep) {
+        h.n_sorted[0] = (unsigned short)wpos[0];
+        h.n_sorted[1] = (unsigned short)wpos[1];
+        h.n_list[0] = (unsigned short)(wpos[0] + births[0]);
+        h.n_list[1] = (unsigned short)(wpos[1] + births[1]);
+        unsigned char sf = 0;
+        if (mode == 2) {
+          if (births[0] > 0 || h.first_step) sf |= 1;
+          if (births[1] > 0 || h.first_step) sf |= 2;
+          if (h.first_step) { h.n_sorted[0] = 0; h.n_sorted[1] = 0; }  // founders' numeric order is not the sorted order
+          h.first_step = 0;
+        }
+        h.sortflag = sf;
+        const size_t gb = (size_t)env * p.n_grass;
+        for (int g = lane; g < p.n_grass; g += 32) {
+          p.gr_e[gb + g] = S.gE[g];
+          if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
+        }
+      }
+      if (over) h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;  // idle: final state stays readable
+      if (lane == 0) p.hdr[env] = h;
+      // per-env counters (PPG_STAT_*)
+      if (lane < PPG_N_STATS) {
+        unsigned add = 0;
+        if (mode == 2) {
+          switch (lane) {
+            case PPG_STAT_ENV_STEPS: add = 1; break;
+            case PPG_STAT_AGENT_STEPS: add = n[0] + n[1]; break;
+            case PPG_STAT_EPISODES: add = over; break;
+            case PPG_STAT_EPISODE_STEPS: add = over ? h.step : 0; break;
+            case PPG_STAT_BIRTHS_PRED: add = births[0]; break;
+            case PPG_STAT_BIRTHS_PREY: add = births[1]; break;
+            case PPG_STAT_STARVED_PRED: add = st_starved[0]; break;
+            case PPG_STAT_STARVED_PREY: add = st_starved[1]; break;
+            case PPG_STAT_EATEN_PREY: add = st_eaten; break;
+            case PPG_STAT_GRASS_EATEN: add = st_grass; break;
+            case PPG_STAT_TRUNCATED: add = trunc; break;
+            case PPG_STAT_SPAWN_FALLBACK: add = st_fallback; break;
+            default: break;
+          }
+        }
+        if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
+        if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
+        if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
+      }
+    } else if (lane < 2) {
+      p.new_off[lane][env] = 0;
+      p.new_cnt[lane][env] = 0;
+    }
+    if (lane == 0) {
+      p.env_flags[env] = (uint8_t)env_flags;
+      p.env_status[env] = h.status;
+      p.env_step[env] = h.step;
+      p.env_count[2 * env] = mode == 0 ? h.n_list[0] : cur[0];
+      p.env_count[2 * env + 1] = mode == 0 ? h.n_list[1] : cur[1];
+    }
+    __syncwarp();
   }
-  if (lane == 0) {
-    p.env_flags[env] = (uint8_t)env_flags;
-    p.env_status[env] = h.status;
-    p.env_step[env] = h.step;
-    p.env_count[2 * env] = mode == 0 ? h.n_list[0] : cur[0];
-    p.env_count[2 * env + 1] = mode == 0 ? h.n_list[1] : cur[1];
-  }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the engine has read it
 }
 
 // ------------------------------------------------------------------------------------------------
 // small helper kernels
 // ------------------------------------------------------------------------------------------------
 
-// exclusive scan of the live counts -> first old row of every env in the next output.
-// Single CTA; used after ppg_create / ppg_reset / ppg_restore (the step kernel maintains it itself).
-__global__ void ppg_prepare_offsets_kernel(const EnvHdr* __restrict__ hdr, int B, int n_init0, int n_init1,
-                                           int32_t* off0, int32_t* off1, int totals_slot) {
-  __shared__ int s_part[2][1024];
+// Publishes, as if by a launch with tag `epoch`, the rows every env needs in the next output (per-env
+// words, block sums, group sums, totals).  Single CTA; used after ppg_create / ppg_reset /
+// ppg_restore (the step kernel maintains them itself).
+__global__ void ppg_prepare_offsets_kernel(const EnvHdr* __restrict__ hdr, int B, int n_init0, int n_init1, unsigned long long* cntA,
+                                           unsigned long long* sum1, unsigned long long* sum2, int32_t* totals4, unsigned epoch) {
   const int t = threadIdx.x, T = blockDim.x;
-  const int per = (B + T - 1) / T;
-  const int lo = min(t * per, B), hi = min(lo + per, B);
-  int a0 = 0, a1 = 0;
-  for (int e = lo; e < hi; ++e) {
+  const int n_blk = (B + 31) >> 5, n_grp = (B + 1023) >> 10;
+  for (int e = t; e < B; e += T) {
     const EnvHdr h = hdr[e];
     const bool rs = h.state & ST_NEEDS_RESET, idle = (h.state & ST_IDLE) && !rs;
-    a0 += idle ? 0 : (rs ? n_init0 : h.n_list[0]);
-    a1 += idle ? 0 : (rs ? n_init1 : h.n_list[1]);
+    const int a0 = idle ? 0 : (rs ? n_init0 : h.n_list[0]), a1 = idle ? 0 : (rs ? n_init1 : h.n_list[1]);
+    cntA[e] = TAG(epoch, (a0 << 16) | a1);
   }
-  s_part[0][t] = a0; s_part[1][t] = a1;
+  __syncthreads();
+  for (int b = t; b < n_blk; b += T) {
+    int a0 = 0, a1 = 0;
+    for (int e = b << 5; e < min(B, (b + 1) << 5); ++e) { a0 += (int)((cntA[e] >> 16) & 0xFFFF); a1 += (int)(cntA[e] & 0xFFFF); }
+    sum1[(size_t)b * 4 + 0] = TAG(epoch, a0); sum1[(size_t)b * 4 + 1] = TAG(epoch, a1);
+    sum1[(size_t)b * 4 + 2] = TAG(epoch, 0);  sum1[(size_t)b * 4 + 3] = TAG(epoch, 0);
+  }
+  __syncthreads();
+  for (int g = t; g < n_grp; g += T) {
+    int a0 = 0, a1 = 0;
+    for (int b = g << 5; b < min(n_blk, (g + 1) << 5); ++b) { a0 += (int)(unsigned)sum1[(size_t)b * 4]; a1 += (int)(unsigned)sum1[(size_t)b * 4 + 1]; }
+    sum2[(size_t)g * 4 + 0] = TAG(epoch, a0); sum2[(size_t)g * 4 + 1] = TAG(epoch, a1);
+    sum2[(size_t)g * 4 + 2] = TAG(epoch, 0);  sum2[(size_t)g * 4 + 3] = TAG(epoch, 0);
+  }
   __syncthreads();
   if (t == 0) {
-    int r0 = 0, r1 = 0;
-    for (int i = 0; i < T; ++i) { int x0 = s_part[0][i], x1 = s_part[1][i]; s_part[0][i] = r0; s_part[1][i] = r1; r0 += x0; r1 += x1; }
-    off0[B + 1 + totals_slot] = r0; off1[B + 1 + totals_slot] = r1;
-    off0[B] = r0; off1[B] = r1;
-  }
-  __syncthreads();
-  int r0 = s_part[0][t], r1 = s_part[1][t];
-  for (int e = lo; e < hi; ++e) {
-    const EnvHdr h = hdr[e];
-    const bool rs = h.state & ST_NEEDS_RESET, idle = (h.state & ST_IDLE) && !rs;
-    off0[e] = r0; off1[e] = r1;
-    r0 += idle ? 0 : (rs ? n_init0 : h.n_list[0]);
-    r1 += idle ? 0 : (rs ? n_init1 : h.n_list[1]);
+    int a0 = 0, a1 = 0;
+    for (int g = 0; g < n_grp; ++g) { a0 += (int)(unsigned)sum2[(size_t)g * 4]; a1 += (int)(unsigned)sum2[(size_t)g * 4 + 1]; }
+    totals4[0] = a0; totals4[1] = a1; totals4[2] = 0; totals4[3] = 0;
   }
 }
 
 // after ppg_restore: define the "previous output" of the restored state as each env's list laid out
 // densely in list order, so that actions for the next step can be indexed by row again
-__global__ void ppg_relabel_rows_kernel(StepParams p) {
+__global__ void ppg_relabel_rows_kernel(StepParams p, const unsigned long long* cntA, const unsigned long long* sum1,
+                                        const unsigned long long* sum2, const int32_t* totals4) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.B) return;
   const EnvHdr h = p.hdr[e];
   const bool live = !(h.state & (ST_NEEDS_RESET | ST_IDLE));
+  const int blk = e >> 5, grp = e >> 10;
   for (int s = 0; s < 2; ++s) {
-    const int base = p.next_off[s][e];
+    int base = 0;
+    for (int i = blk << 5; i < e; ++i) base += (int)((cntA[i] >> (s == 0 ? 16 : 0)) & 0xFFFF);
+    for (int b = grp << 5; b < blk; ++b) base += (int)(unsigned)sum1[(size_t)b * 4 + s];
+    for (int g = 0; g < grp; ++g) base += (int)(unsigned)sum2[(size_t)g * 4 + s];
     p.old_off[s][e] = base;
-    p.new_off[s][e] = p.next_off[s][p.B];
+    p.new_off[s][e] = 0;
+    p.new_cnt[s][e] = 0;
     if (e == 0) {
-      p.old_off[s][p.B] = p.next_off[s][p.B];
-      p.new_off[s][p.B] = p.next_off[s][p.B];
-      p.n_rows[s] = p.next_off[s][p.B];
+      p.old_off[s][p.B] = totals4[s];
+      p.n_rows[s] = totals4[s];
       p.n_rows[2 + s] = 0;
     }
     if (!live) continue;
@@ -915,17 +1207,34 @@ cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, 
     case 1: return launch_w<1>(p, n_cta, smem, stream);
     case 2: return launch_w<2>(p, n_cta, smem, stream);
     case 4: return launch_w<4>(p, n_cta, smem, stream);
-    case 8: return launch_w<8>(p, n_cta, smem, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
-cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, int32_t* off0, int32_t* off1, int slot, cudaStream_t s) {
-  ppg_prepare_offsets_kernel<<<1, 1024, 0, s>>>(hdr, B, n0, n1, off0, off1, slot);
+template <int W>
+static cudaError_t occupancy_w(size_t smem, int* blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W>, W * 32, smem);
+}
+
+cudaError_t step_base_occupancy(int warps_per_cta, size_t smem, int* blocks_per_sm) {
+  switch (warps_per_cta) {
+    case 1: return occupancy_w<1>(smem, blocks_per_sm);
+    case 2: return occupancy_w<2>(smem, blocks_per_sm);
+    case 4: return occupancy_w<4>(smem, blocks_per_sm);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
+                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s) {
+  ppg_prepare_offsets_kernel<<<1, 1024, 0, s>>>(hdr, B, n0, n1, cntA, sum1, sum2, totals4, epoch);
   return cudaGetLastError();
 }
-cudaError_t launch_relabel_rows(const StepParams& p, cudaStream_t s) {
-  ppg_relabel_rows_kernel<<<(p.B + 127) / 128, 128, 0, s>>>(p);
+cudaError_t launch_relabel_rows(const StepParams& p, const unsigned long long* cntA, const unsigned long long* sum1,
+                                const unsigned long long* sum2, const int32_t* totals4, cudaStream_t s) {
+  ppg_relabel_rows_kernel<<<(p.B + 127) / 128, 128, 0, s>>>(p, cntA, sum1, sum2, totals4);
   return cudaGetLastError();
 }
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s) {

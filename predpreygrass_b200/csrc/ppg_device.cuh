@@ -7,8 +7,10 @@
 //                    `self.agents` order (BASE:73,468): position in the list = iteration order
 //   per env          gr_pos u16[n_grass], gr_energy f64[n_grass]
 //   per env          counters u32[16] (PPG_STAT_*)
-// The float64 grid of the reference (`grid_world_state`, BASE:124) is NOT stored: it is rebuilt in
-// shared memory (fp32) at the start of every step from the lists (see DESIGN.md "grid rebuild").
+// The float64 grid of the reference (`grid_world_state`, BASE:124) is NOT stored, neither in HBM nor
+// in shared memory: a non-zero cell of the reference grid always holds the current energy of the
+// agent that wrote it last, so the kernels keep per-species OWNER maps (cell -> list slot + 1) in
+// shared memory and look the value up (see DESIGN.md "owner maps").
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,7 +32,8 @@ struct __align__(16) EnvHdr {
   unsigned char status;         // PPG_STATUS_* (sticky until reset)
   unsigned char sortflag;       // bit s: list of species s is not in lexicographic order yet
   unsigned char first_step;     // 1 right after reset(): engagement order is the founders' numeric order
-  int pad[3];
+  unsigned short n_sorted[2];   // length of the lexicographically sorted prefix of the list (rest: last step's newborns)
+  int pad[2];
 };
 static_assert(sizeof(EnvHdr) == 64, "EnvHdr must be 64 bytes");
 
@@ -49,9 +52,6 @@ enum : unsigned char {
 struct StepParams {
   // ---- config ----
   int B, G, GG, C;
-  int P, PS, CH;          // padded grid: halo width, row stride, cells per channel (see ppg_base.cu)
-  const int* obs_rel;     // [2][4][32][4] per-lane window offsets, (channel << 16) | (int16 spatial offset)
-  const float* wall_tab;  // [CH] channel-0 table: 1 outside the field, 0 inside
   int R[2], off[2], elems[2];
   int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
   double loss[2], thr[2], init_e[2], grass_cap, grass_gain;
@@ -68,13 +68,24 @@ struct StepParams {
   const uint16_t* lexrank[2];
   const int32_t* tape_cells;
   uint32_t* counters;  // [B][PPG_N_STATS]
-  // ---- cross-CTA row allocation (decoupled look-back) ----
-  unsigned long long* desc;  // [n_cta][4]
-  unsigned long long* ticket;
-  unsigned long long ticket_base;
-  unsigned epoch;
-  unsigned* error;  // device error word (bit0: look-back wedged)
-  int32_t* next_off[2];  // [s] -> [B+3]: first old row of each env in the NEXT output; [B+1],[B+2] = totals (ping-pong by epoch parity)
+  // ---- dynamic env scheduling + deterministic row allocation (hierarchical counts, see ppg_base.cu) ----
+  unsigned long long* ticket;      // env ticket counter (monotonic over launches)
+  unsigned long long ticket_base;  // value of *ticket at launch
+  unsigned epoch;                  // launch number (1-based); tags every published word
+  unsigned* error;                 // device error word (bit0: prefix wait wedged)
+  // published per env / per 32-env block / per 1024-env group, ping-pong by epoch parity:
+  //   cntA = epoch<<32 | live_pred<<16 | live_prey   (rows the env needs in the NEXT output)
+  //   cntB = epoch<<32 | births_pred<<16 | births_prey (newborn rows of THIS output)
+  //   sum1/sum2 [.][4] = epoch<<32 | sum of {live_pred, live_prey, births_pred, births_prey}
+  unsigned long long* cntA[2];
+  unsigned long long* cntB[2];
+  unsigned long long* sum1[2];
+  unsigned long long* sum2[2];
+  unsigned* done1;   // [n_blk] finished envs per block (monotonic)
+  unsigned* done2;   // [n_grp] finished blocks per group (monotonic)
+  unsigned* done3;   // [1] finished groups (monotonic)
+  int32_t* totals;   // [2][4] per parity: total {live_pred, live_prey, births_pred, births_prey}
+  const int32_t* order[2];  // optional: rank of each row inside its env+species in the action dict (ppg_step_ordered)
   // ---- io ----
   const int32_t* actions[2];
   float* obs[2];
@@ -84,14 +95,16 @@ struct StepParams {
   uint8_t* flags[2];
   int32_t* old_off[2];
   int32_t* new_off[2];
+  int32_t* new_cnt[2];
   int32_t* n_rows;
   uint8_t* env_flags;
   uint8_t* env_status;
   int32_t* env_step;
   int32_t* env_count;
   // ---- shared-memory layout, byte offsets inside one env's region ----
-  int so_E[2], so_E0[2], so_gE, so_grid, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2], so_gpos;
-  int so_act[2], so_flg[2], so_aux[2], so_gmap;
+  int so_E[2], so_E0[2], so_gE, so_ent, so_stage, so_scr, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2];
+  int so_own[2], so_gpos, so_act[2], so_flg[2], so_aux[2], so_gmap, so_gtag;
+  int stage_elems;  // floats per staging row buffer (max over species, multiple of 4)
   int smem_per_env;
 };
 

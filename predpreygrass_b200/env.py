@@ -171,10 +171,11 @@ class PredPreyGrass(_Base):
         self._state = None
         if self._trunc_pending is not None:
             # BASE:228-238 — the call after max_steps real steps: same state, everybody truncated
-            obs = self._trunc_pending
+            pend = self._trunc_pending
             self._trunc_pending = None
             self._done = True
-            self.agents = [a for a in self.agents if a in obs]  # BASE:222-225
+            self.agents = [a for a in self.agents if a in pend]  # BASE:222-225
+            obs = {a: pend[a] for a in self.agents}              # BASE:229 iterates the sorted self.agents
             rewards = {a: 0.0 for a in obs}
             trunc = {a: True for a in obs}
             term = {a: False for a in obs}
@@ -221,8 +222,12 @@ class PredPreyGrass(_Base):
         self.agents_just_ate = set()
         for group in ("old", "new"):
             for s in range(2):
-                off = out[f"{group}_off{s}"]
-                for r in range(int(off[0]), int(off[1])):
+                if group == "old":
+                    r0, r1 = int(out[f"old_off{s}"][0]), int(out[f"old_off{s}"][1])
+                else:
+                    r0 = int(out[f"new_off{s}"][0])
+                    r1 = r0 + int(out[f"new_cnt{s}"][0])
+                for r in range(r0, r1):
                     name = f"{_SPECIES[s]}_{int(out[f'row_agent{s}'][r])}"
                     f = int(out[f"flags{s}"][r])
                     obs[name] = out[f"obs{s}"][r].astype(np.float64)

@@ -43,8 +43,10 @@ def dict_order_rows(out, env=0):
     """Rows of one env in the reference's observation-dict order:
     old predators, old prey, newborn predators, newborn prey (BASE:459 over self.agents)."""
     rows = []
-    for group in ("old", "new"):
-        for s in range(2):
-            off = out[f"{group}_off{s}"]
-            rows += [(s, r) for r in range(int(off[env]), int(off[env + 1]))]
+    for s in range(2):
+        off = out[f"old_off{s}"]
+        rows += [(s, r) for r in range(int(off[env]), int(off[env + 1]))]
+    for s in range(2):
+        r0 = int(out[f"new_off{s}"][env])
+        rows += [(s, r) for r in range(r0, r0 + int(out[f"new_cnt{s}"][env]))]
     return rows

@@ -4,7 +4,7 @@ Used by the `-m gpu` tests, by __graft_entry__.smoke() and by bench.py's correct
 import numpy as np
 
 
-EXACT_KEYS = ("row_env", "row_agent", "flags", "old_off", "new_off")
+EXACT_KEYS = ("row_env", "row_agent", "flags", "old_off", "new_off", "new_cnt")
 
 
 def compare_outputs(g, o, where="", obs_rtol=0.0, reward_rtol=0.0):

@@ -60,10 +60,11 @@ def test_no_autoreset_goes_idle():
     lockstep_parity(cfg, 32, 40)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_cases() if "shuffle" not in n])
+@pytest.mark.parametrize("name", golden_cases())
 def test_golden_trajectories_on_gpu(name):
     """Golden trajectories of the unmodified reference replayed on the GPU (one env, tape-driven):
-    ids, dict order, rewards, terminations bit-exact; float64 energies bit-exact."""
+    ids, dict order, rewards, terminations bit-exact; float64 energies bit-exact.  The `shuffle`
+    cases pass their action dicts in a random key order (ppg_step_ordered)."""
     from predpreygrass_b200.batched import BatchedPredPreyGrass
 
     z, cfg = load_golden(name)
@@ -81,16 +82,27 @@ def test_golden_trajectories_on_gpu(name):
         if z["all_trunc"][t] and t == T - 1 and int(z["steps"][t]) == int(z["steps"][t - 1]):
             break  # BASE's extra truncation call: folded into the previous step on the device
         a0, a1 = z["act_off"][t], z["act_off"][t + 1]
-        act = {(int(s), int(i)): int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        act, rank, seen = {}, {}, [0, 0]
+        for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1]):
+            act[(int(s), int(i))] = int(v)
+            rank[(int(s), int(i))] = seen[int(s)]  # position among the species' keys of the action dict
+            seen[int(s)] += 1
         import torch
+        orders = []
         for s in range(2):
             n = out["n"][s]
             a = np.full(max(n, 1), 4, np.int32)
+            o = np.zeros(max(n, 1), np.int32)
             for r in range(n):
                 if not (out[f"flags{s}"][r] & 1):
                     a[r] = act[(s, int(out[f"row_agent{s}"][r]))]
+                    o[r] = rank[(s, int(out[f"row_agent{s}"][r]))]
             g.actions[s][: len(a)].copy_(torch.from_numpy(a))
-        g.step()
+            orders.append(torch.from_numpy(o).cuda())
+        if "shuffle" in name:
+            g.step_ordered(g.actions[0], g.actions[1], orders[0], orders[1])
+        else:
+            g.step()
         out = g.outputs_numpy()
         rows = dict_order_rows(out)
         r0, r1 = z["row_off"][t], z["row_off"][t + 1]
@@ -203,3 +215,56 @@ def test_full_size_properties_16384_envs():
     st = a.stats()
     assert st["status_envs"] == 0
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["base_default_s1", "base_default_s7_shuffle", "base_trunc_s2", "additive_default_s1", "kickback_default_s6"])
+def test_dict_adapter_replays_reference_episode(name):
+    """`PredPreyGrass` (the MultiAgentEnv-shaped adapter) against an episode recorded from the reference
+    through the same dict API: reset(seed) placement, observation-dict key order, rewards,
+    terminations, truncations (incl. BASE's extra truncation call, BASE:228-238), `agents`, state."""
+    from predpreygrass_b200.env import PredPreyGrass
+
+    z, cfg = load_golden(name)
+    if len(z["fallback_cells"]):
+        pytest.skip("episode uses the global-numpy spawn fallback draw (BASE:764), which the device replaces by Philox")
+    variant = cfg.pop("variant")
+    cfg = dict(cfg, reward_variant=variant, cap_live=(min(cfg["n_possible_predators"], 320), min(cfg["n_possible_prey"], 320)))
+    env = PredPreyGrass(cfg)
+    obs, infos = env.reset(seed=int(z["seed"]))
+    assert infos == {}
+    G = env.grid_size
+    names = ("predator", "prey")
+    assert list(obs) == [f"{names[s]}_{i}" for s, i in zip(z["reset_row_s"], z["reset_row_id"])]
+    pos = env.agent_positions
+    cells = [pos[a][0] * G + pos[a][1] for a in env.agents] + [p[0] * G + p[1] for p in env.grass_positions.values()]
+    assert cells == list(z["init_cells"])  # numpy PCG64 + set order reproduced on the host (BASE:156-187)
+    for a, o in obs.items():
+        assert o.dtype == np.float64 and o.shape == env.observation_spaces[a].shape
+    T = len(z["steps"])
+    for t in range(T):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {f"{names[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        obs, rew, term, trunc, infos = env.step(acts)
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        keys = [f"{names[s]}_{i}" for s, i in zip(z["row_s"][r0:r1], z["row_id"][r0:r1])]
+        assert list(obs) == keys, (name, t)
+        assert list(rew) == keys and [k for k in term if k != "__all__"] == keys
+        assert np.array_equal(np.array([rew[k] for k in keys], np.float32), z["row_rew"][r0:r1].astype(np.float32)), (name, t)
+        assert [int(term[k]) for k in keys] == list(z["row_term"][r0:r1]), (name, t)
+        assert [int(trunc[k]) for k in keys] == list(z["row_trunc"][r0:r1]), (name, t)
+        assert term["__all__"] == bool(z["all_term"][t]) and trunc["__all__"] == bool(z["all_trunc"][t]), (name, t)
+        assert env.current_step == int(z["steps"][t])
+        g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
+        assert env.agents == [f"{names[s]}_{i}" for s, i in zip(z["ag_s"][g0:g1], z["ag_id"][g0:g1])], (name, t)
+        if not (term["__all__"] or trunc["__all__"]):
+            s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+            want = {f"{names[s]}_{i}": ((int(x), int(y)), float(e)) for s, i, x, y, e in
+                    zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_x"][s0:s1], z["st_y"][s0:s1], z["st_e"][s0:s1])}
+            got_p, got_e = env.agent_positions, env.agent_energies
+            assert sorted(got_p) == sorted(want), (name, t)
+            assert all(got_p[k] == want[k][0] and got_e[k] == want[k][1] for k in want), (name, t)
+    with pytest.raises(KeyError):
+        e2 = PredPreyGrass(cfg)
+        e2.reset(seed=1)
+        e2.step({"predator_1999": 0})
+    env.close()
