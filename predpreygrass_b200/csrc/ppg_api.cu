@@ -12,7 +12,7 @@
 
 namespace ppg {
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_base_occupancy(int warps_per_cta, size_t smem, int* blocks_per_sm);
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, size_t smem, int* blocks_per_sm);
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
                                    unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s);
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
@@ -178,32 +178,68 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   const bool dense = c.reward_mode == PPG_REWARD_DENSE || c.reward_mode == PPG_REWARD_DENSE_ADDITIVE;
   const bool kick = c.reward_mode == PPG_REWARD_SPARSE_KICKBACK;
 
+  // padded map geometry (ppg_base.cu): halo as wide as the largest observation window
+  P.P = std::max(P.off[0], P.off[1]);
+  P.PS = G + P.P;
+  P.CH = (int)align_up((size_t)P.P + (size_t)(G + 2 * P.P) * P.PS + P.P, 4);
+  P.map_bytes = (P.cap[0] <= 253 && P.cap[1] <= 253 && P.n_grass <= 253) ? 1 : 2;
+  P.wall_idx = P.cap[0] + 1;
+  for (int s = 0; s < 2; ++s) P.nj[s] = (P.elems[s] + 31) / 32;
+  if (P.nj[0] > PPG_MAX_NJ || P.nj[1] > PPG_MAX_NJ) { h->err = "observation row too large for this build"; return fail(PPG_ERR_INVALID); }
+
   // shared-memory layout of one env (see EnvSmem in ppg_base.cu)
   size_t o = 0;
   auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return (int)r; };
   for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(dense ? 8 * (size_t)P.cap[s] : 0, 8); }
   P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
   P.stage_elems = (int)align_up((size_t)std::max(P.elems[0], P.elems[1]), 4);
-  P.so_ent = take(8 * (size_t)(P.cap[0] + P.cap[1] + P.n_grass), 16);
+  P.so_wt = take(4 * (size_t)(P.cap[0] + 2), 4);
+  // value tables and staging rows are contiguous: reset() stages n_total cells + a GG-entry claim table there
+  P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
+  P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
+  P.so_vt[2] = take(4 * (size_t)(P.n_grass + 1), 4);
   P.so_stage = take(2 * 4 * (size_t)P.stage_elems, 16);
-  // reset() stages n_total cells + a GG-entry claim table in the entity + staging area
-  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass + GG) * 4 > (size_t)(P.so_stage + 8 * P.stage_elems - P.so_ent)) {
-    h->err = "internal: reset scratch does not fit the entity/staging area"; return fail(PPG_ERR_INVALID);
+  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass + GG) * 4 > (size_t)(P.so_stage + 8 * P.stage_elems - P.so_vt[0])) {
+    h->err = "internal: reset scratch does not fit the table/staging area"; return fail(PPG_ERR_INVALID);
   }
-  P.so_scr = take(align_up(GG, 4), 4);
+  P.so_scr = take((size_t)P.CH, 4);
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_par[s] = take(kick ? 2 * (size_t)P.cap[s] : 0, 2);
-    P.so_own[s] = take(2 * align_up(GG, 2), 4);
   }
+  for (int m = 0; m < 3; ++m) P.so_map[m] = take((size_t)P.map_bytes * P.CH, 4);
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
   for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(kick ? P.cap[s] : 0, 1); }
-  P.so_gmap = take(align_up(GG, 4), 4);
   P.so_gtag = take(std::max(1, P.n_grass), 1);
   P.smem_per_env = (int)align_up(o, 128);
   const size_t smem_max = 227 * 1024;
   if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
+  {
+    // per-lane gather constants: element q = lane + 32 j of a row is channel c, window cell (i, jj);
+    // BASE channels: 0 = outside the grid (predator map halo -> wall table), 1 predators, 2 prey, 3 grass
+    std::vector<int> rel((size_t)2 * PPG_MAX_NJ * 32 * 2, 0);
+    for (int s = 0; s < 2; ++s) {
+      const int R = P.R[s], RR = R * R;
+      for (int j = 0; j < P.nj[s]; ++j)
+        for (int lane = 0; lane < 32; ++lane) {
+          const size_t at0 = ((size_t)(s * PPG_MAX_NJ + j) * 32 + lane) * 2;
+          rel[at0] = 0; rel[at0 + 1] = P.so_wt;  // lanes past the end of the row: a harmless in-range read, never stored
+          const int q = j * 32 + lane;
+          if (q >= P.elems[s]) continue;
+          const int ch = q / RR, i = (q % RR) / R, jj = q % R;
+          const int m = ch == 0 ? 0 : ch - 1;
+          const int cellrel = (i - P.off[s]) * P.PS + (jj - P.off[s]);
+          const size_t at = ((size_t)(s * PPG_MAX_NJ + j) * 32 + lane) * 2;
+          rel[at] = (P.so_map[m] - P.so_map[0]) + cellrel * P.map_bytes;
+          rel[at + 1] = ch == 0 ? P.so_wt : P.so_vt[ch - 1];
+        }
+    }
+    int* d_rel = nullptr;
+    CKC(dalloc(h, &d_rel, rel.size()));
+    CKC(cudaMemcpy(d_rel, rel.data(), rel.size() * sizeof(int), cudaMemcpyHostToDevice));
+    P.obs_rel = reinterpret_cast<const int2*>(d_rel);
+  }
   int W = 1;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
   if (W != 1 && W != 2 && W != 4) W = 1;
@@ -213,7 +249,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    CKC(step_base_occupancy(W, h->smem_bytes, &per_sm));
+    CKC(step_base_occupancy(W, P.map_bytes, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
     h->n_cta = std::min((B + W - 1) / W, per_sm * n_sm);

@@ -1,4 +1,4 @@
-// ppg_base.cu — the BASE-family environment step as one fused, persistent sm_100a kernel (v3).
+// ppg_base.cu — the BASE-family environment step as one fused, persistent sm_100a kernel (v4).
 //
 // Reproduces, for B independent env instances in lockstep, `PredPreyGrass.step()` and `reset()` of
 //   BASE = predpreygrass/non_evolutionary/base_environment/predpreygrass_rllib_env.py
@@ -7,11 +7,15 @@
 //
 // Mapping: one warp owns one env for the whole step; warps are persistent and draw env indices
 // from a global ticket counter, so envs of very different population sizes balance over the SMs.
-// The env's agent lists, grass and per-species OWNER maps live in the warp's slice of shared
+// The env's agent lists, grass and three small index MAPS live in the warp's slice of shared
 // memory.  The reference's float grid (`grid_world_state`, BASE:124) is never materialised: a
 // non-zero grid cell always equals the current energy of the agent that wrote it last, so
-// `own[s][cell] = slot + 1` (0 = the reference wrote 0 there) carries the same information in
-// 2 bytes per cell and the value is looked up in the energy list.
+// `map[s][cell] = slot + 1` (0 = the reference wrote 0 there) carries the same information in one
+// byte per cell, and `map[2][cell] = grass index + 1`.  The maps have a halo as wide as the largest
+// observation window (index(x,y) = P + (x+P)*PS + y, the gap after a row doubles as the next row's
+// left halo), so a window element is `map[index(agent) + const]` with no bounds test; the halo of
+// the predator map holds a WALL index, which makes channel 0 ("outside the grid", BASE:522-523)
+// just another table lookup.
 //
 // Order-dependent phases keep the reference's semantics but run lane-parallel wherever agents
 // cannot interact:
@@ -23,10 +27,11 @@
 //   prey (BASE:347-380): 32 prey at a time eat in parallel unless one of them starved or two
 //     share a grass patch, else the exact sequential loop for that chunk;
 //   births (BASE:389-448): ballot over eligible parents, sequential per birth (rare).
-// Observation rows (BASE:511-539) are assembled in a shared-memory staging buffer by scattering
-// the env's visible entities (a few dozen) into a zero-filled window, and leave the SM as ONE
-// bulk asynchronous copy per row (cp.async.bulk shared -> global, 784 / 1296 contiguous bytes),
-// double buffered so assembling row r+1 overlaps the store of row r.
+// Observation rows (BASE:511-539): lane l produces elements l, l+32, ... of the [C][R][R] row, each
+// by two dependent shared-memory loads (map entry -> fp32 value table) at per-lane constant offsets,
+// conflict-free, into a staging row that leaves the SM as ONE bulk asynchronous copy
+// (cp.async.bulk shared -> global, 784 / 1296 contiguous bytes), double buffered so gathering row
+// r+1 overlaps the store of row r.
 //
 // Row allocation across envs is deterministic and needs no second kernel: every env publishes
 // its live/birth counts; the last finisher of each 32-env block / 1024-env group publishes block
@@ -45,29 +50,31 @@ namespace ppg {
 // ------------------------------------------------------------------------------------------------
 // shared-memory view of one env
 // ------------------------------------------------------------------------------------------------
+template <typename MapT>
 struct EnvSmem {
   double* E[2];
   double* E0[2];
   double* gE;
-  uint2* ent;      // visible entities: x = channel << 16 | pos, y = float bits
+  float* wt;       // wall table: 1.0 at wall_idx, else 0 (constant)
+  float* vt[3];    // fp32 value tables: predators [cap0+2], prey [cap1+1], grass [n_grass+1]; entry 0 = 0
   float* stage;    // 2 row buffers of stage_elems floats
-  uint8_t* scr;    // [GG rounded to 4] touch counters / predator marks; all zero between uses
+  uint8_t* scr;    // [CH] touch counters / predator marks; all zero between uses
   uint16_t* id[2];
   uint16_t* pos[2];
   uint16_t* ord[2];  // ord[k] = slot of the k-th agent in engagement order
   uint16_t* rnk[2];  // inverse of ord
   uint16_t* par[2];
-  uint16_t* own[2];  // [GG] owner map: slot + 1 of the agent whose energy the reference grid shows, 0 = empty
+  MapT* map[3];      // padded: [0],[1] owner maps (slot + 1 of the agent the reference grid shows, 0 = empty), [2] grass index + 1
   uint16_t* gpos;
   uint8_t* act[2];
   uint8_t* flg[2];
   uint8_t* aux[2];  // kickback count
-  uint8_t* gmap;    // cell -> grass index + 1
   uint8_t* gtag;    // [n_grass] scratch for the prey chunk conflict test
 };
 
-__device__ __forceinline__ EnvSmem carve(unsigned char* base, const StepParams& p) {
-  EnvSmem s;
+template <typename MapT>
+__device__ __forceinline__ EnvSmem<MapT> carve(unsigned char* base, const StepParams& p) {
+  EnvSmem<MapT> s;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     s.E[k] = reinterpret_cast<double*>(base + p.so_E[k]);
@@ -77,27 +84,30 @@ __device__ __forceinline__ EnvSmem carve(unsigned char* base, const StepParams& 
     s.ord[k] = reinterpret_cast<uint16_t*>(base + p.so_ord[k]);
     s.rnk[k] = reinterpret_cast<uint16_t*>(base + p.so_rnk[k]);
     s.par[k] = reinterpret_cast<uint16_t*>(base + p.so_par[k]);
-    s.own[k] = reinterpret_cast<uint16_t*>(base + p.so_own[k]);
     s.act[k] = base + p.so_act[k];
     s.flg[k] = base + p.so_flg[k];
     s.aux[k] = base + p.so_aux[k];
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    s.map[k] = reinterpret_cast<MapT*>(base + p.so_map[k]);
+    s.vt[k] = reinterpret_cast<float*>(base + p.so_vt[k]);
+  }
   s.gE = reinterpret_cast<double*>(base + p.so_gE);
-  s.ent = reinterpret_cast<uint2*>(base + p.so_ent);
+  s.wt = reinterpret_cast<float*>(base + p.so_wt);
   s.stage = reinterpret_cast<float*>(base + p.so_stage);
   s.scr = base + p.so_scr;
   s.gpos = reinterpret_cast<uint16_t*>(base + p.so_gpos);
-  s.gmap = base + p.so_gmap;
   s.gtag = base + p.so_gtag;
   return s;
 }
 
 // ------------------------------------------------------------------------------------------------
-// PTX helpers: bulk asynchronous shared -> global copy (TMA engine, SASS UBLKCP)
+// PTX helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
-               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+// bulk asynchronous shared -> global copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc32, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)), "r"(ssrc32), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -106,7 +116,6 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -115,76 +124,89 @@ __device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long
 }
 #define TAG(epoch, val) (((unsigned long long)(epoch) << 32) | (unsigned long long)(unsigned)(val))
 
-#define CELL(ps) ((int)((ps) >> 8) * G + (int)((ps)&255u))
+// padded map index of a packed position (x << 8 | y)
+#define CELLP(ps) (PP + ((int)((ps) >> 8) + PP) * PS + (int)((ps)&255u))
+#define CELLXY(x, y) (PP + ((x) + PP) * PS + (y))
 
 // ------------------------------------------------------------------------------------------------
 // observation rows
 // ------------------------------------------------------------------------------------------------
-// The entities the reference grid shows right now (BASE:123-124 channels 1..3): an agent is visible
-// iff it owns its cell; a grass patch iff its energy is non-zero.  Returns the entity count.
-__device__ __noinline__ int build_entities(unsigned char* base, const StepParams& p, int nt0, int nt1, int lane) {
-  const EnvSmem S = carve(base, p);
-  const int G = p.G;
-  int n_ent = 0;
-  const int nt[2] = {nt0, nt1};
+// per-lane gather constants of one species (obs_rel table of the host)
+struct RowRel {
+  int relb[PPG_MAX_NJ];  // byte offset of the map entry from the agent's own map-0 entry
+  int tbl[PPG_MAX_NJ];   // byte offset of the value table inside the env's shared-memory slice
+};
+
+__device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, int lane) {
+  RowRel r;
 #pragma unroll
-  for (int s = 0; s < 2; ++s)
-    for (int b0 = 0; b0 < nt[s]; b0 += 32) {
-      const int i = b0 + lane;
-      bool vis = false;
-      unsigned ps = 0;
-      if (i < nt[s] && (S.flg[s][i] & F_ALIVE)) {
-        ps = S.pos[s][i];
-        vis = S.own[s][CELL(ps)] == (unsigned)(i + 1);
-      }
-      const unsigned m = __ballot_sync(FULL, vis);
-      if (vis) S.ent[n_ent + __popc(m & ((1u << lane) - 1))] = make_uint2(((unsigned)(s + 1) << 16) | ps, __float_as_uint((float)S.E[s][i]));
-      n_ent += __popc(m);
+  for (int j = 0; j < PPG_MAX_NJ; ++j) {
+    r.relb[j] = 0; r.tbl[j] = 0;
+    if (j < p.nj[s]) {
+      const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
+      r.relb[j] = v.x; r.tbl[j] = v.y;  // lanes past the end of the row (last iteration only) get a harmless in-range pair
     }
-  for (int b0 = 0; b0 < p.n_grass; b0 += 32) {
-    const int g = b0 + lane;
-    float v = 0.f;
-    if (g < p.n_grass) v = (float)S.gE[g];
-    const bool vis = v != 0.f;
-    const unsigned m = __ballot_sync(FULL, vis);
-    if (vis) S.ent[n_ent + __popc(m & ((1u << lane) - 1))] = make_uint2((3u << 16) | S.gpos[g], __float_as_uint(v));
-    n_ent += __popc(m);
   }
-  __syncwarp();
-  return n_ent;
+  return r;
 }
 
-// _get_observation (BASE:511-539) of an agent at `apos` into global row `dst`: zero-fill a staging
-// row, mark channel 0 outside the grid (BASE:522-523), scatter the visible entities that fall into
-// the window, hand the row to the bulk-copy engine.
-__device__ __forceinline__ void emit_row(const StepParams& p, const EnvSmem& S, float* dst, unsigned apos, int s, int n_ent,
-                                         unsigned& rowctr, const unsigned (&wq)[4], int lane) {
-  float* buf = S.stage + (rowctr & 1u) * p.stage_elems;
+// fp32 copies of the energies the observation channels show (float64 state -> float32 row values)
+template <typename MapT>
+__device__ __forceinline__ void refresh_tables(const EnvSmem<MapT>& S, const StepParams& p, int nt0, int nt1, int lane) {
+  for (int i = lane; i < nt0; i += 32) S.vt[0][1 + i] = (float)S.E[0][i];
+  for (int i = lane; i < nt1; i += 32) S.vt[1][1 + i] = (float)S.E[1][i];
+  for (int g = lane; g < p.n_grass; g += 32) S.vt[2][1 + g] = (float)S.gE[g];
+  if (lane == 0) S.vt[0][0] = 0.f;
+  if (lane == 1) S.vt[1][0] = 0.f;
+  if (lane == 2) S.vt[2][0] = 0.f;
+  if (lane == 3) S.vt[0][p.wall_idx] = 0.f;
+  __syncwarp();
+}
+
+// shared-memory accesses by 32-bit shared address (PTX keeps them in the order written: all map loads of a
+// row, then all table loads, then all stores, so the hardware sees 2 dependent latencies per row)
+template <typename MapT>
+__device__ __forceinline__ unsigned lds_map(unsigned a);
+template <>
+__device__ __forceinline__ unsigned lds_map<uint8_t>(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <>
+__device__ __forceinline__ unsigned lds_map<uint16_t>(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+// _get_observation (BASE:511-539) of the agent whose padded cell index is `cellp` into global row `dst`:
+// element lane + 32 j = table[map[cell + const]], NJ = ceil(row elements / 32) iterations.
+template <typename MapT, int NJ>
+__device__ __forceinline__ void emit_row_nj(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
+                                            unsigned& rowctr, int lane) {
+  const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
   ++rowctr;
   if (lane == 0) bulk_wait_read<1>();  // the copy issued two rows ago has finished reading `buf`
   __syncwarp();
-  const int R = p.R[s], off = p.off[s], G = p.G;
-  const int nvec = p.elems[s] >> 2;
-  for (int q = lane; q < nvec; q += 32) reinterpret_cast<float4*>(buf)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
-  const int ax = apos >> 8, ay = apos & 255;
-  if (ax < off || ay < off || ax + off >= G || ay + off >= G) {
+  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
+  const unsigned o0 = buf + 4u * lane;
+  const bool tail_ok = lane + 32 * (NJ - 1) < p.elems[s];
+  unsigned idx[NJ];
+  float val[NJ];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const unsigned w = wq[jj];
-      if (w != 0xFFFFFFFFu) {
-        const int i = w >> 8, j = w & 255;
-        if ((unsigned)(ax - off + i) >= (unsigned)G || (unsigned)(ay - off + j) >= (unsigned)G) buf[lane + 32 * jj] = 1.f;
-      }
-    }
-  }
-  const int lo = (int)apos - ((off << 8) | off);
-  for (int e = lane; e < n_ent; e += 32) {
-    const uint2 en = S.ent[e];
-    const int d = (int)(en.x & 0xFFFFu) - lo;
-    const unsigned ty = (unsigned)d & 255u, tx = (unsigned)(d >> 8);
-    if (ty < (unsigned)R && tx < (unsigned)R) buf[((int)(en.x >> 16) * R + (int)tx) * R + (int)ty] = __uint_as_float(en.y);
-  }
+  for (int j = 0; j < NJ; ++j) idx[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) val[j] = lds_f32(sb32 + (unsigned)r.tbl[j] + 4u * idx[j]);
+#pragma unroll
+  for (int j = 0; j < NJ - 1; ++j) sts_f32(o0 + 128u * j, val[j]);
+  if (tail_ok) sts_f32(o0 + 128u * (NJ - 1), val[NJ - 1]);
   fence_async_smem();
   __syncwarp();
   if (lane == 0) {
@@ -193,24 +215,52 @@ __device__ __forceinline__ void emit_row(const StepParams& p, const EnvSmem& S, 
   }
 }
 
-// rows of agents that die mid-step: the reference captures them at that moment (BASE:287,327)
-__device__ __noinline__ void emit_row_now(unsigned char* base, const StepParams& p, float* dst, unsigned apos, int s, int nt0, int nt1,
-                                          unsigned* rowctr, int lane) {
-  const EnvSmem S = carve(base, p);
-  const int n_ent = build_entities(base, p, nt0, nt1, lane);
-  unsigned wq[4];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int q = lane + 32 * jj, R = p.R[s];
-    wq[jj] = q < R * R ? (unsigned)(((q / R) << 8) | (q % R)) : 0xFFFFFFFFu;
+template <typename MapT>
+__device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
+                                         unsigned& rowctr, int lane) {
+  switch (p.nj[s]) {  // warp-uniform; the row sizes of the reference's env family get straight-line code
+    case 7: emit_row_nj<MapT, 7>(p, sb32, dst, cellp, s, r, rowctr, lane); break;    // (4,7,7)
+    case 11: emit_row_nj<MapT, 11>(p, sb32, dst, cellp, s, r, rowctr, lane); break;  // (4,9,9)
+    case 13: emit_row_nj<MapT, 13>(p, sb32, dst, cellp, s, r, rowctr, lane); break;  // (5,9,9)
+    default: {
+      // any other shape: same thing, one element at a time
+      const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
+      ++rowctr;
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
+#pragma unroll 1
+      for (int j = 0; j < p.nj[s]; ++j) {
+        if (lane + 32 * j < p.elems[s]) {
+          const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
+          const unsigned idx = lds_map<MapT>(a0 + (unsigned)v.x);
+          sts_f32(buf + 4u * (lane + 32 * j), lds_f32(sb32 + (unsigned)v.y + 4u * idx));
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(dst, buf, (unsigned)p.elems[s] * 4u);
+        bulk_commit();
+      }
+    }
   }
-  unsigned rc = *rowctr;
-  emit_row(p, S, dst, apos, s, n_ent, rc, wq, lane);
-  *rowctr = rc;
+}
+
+// rows of agents that die mid-step: the reference captures them at that moment (BASE:287,327)
+template <typename MapT>
+__device__ __noinline__ unsigned emit_row_now(unsigned char* base, const StepParams& p, float* dst, int cellp, int s, int nt0, int nt1,
+                                              unsigned rowctr, int lane) {
+  const EnvSmem<MapT> S = carve<MapT>(base, p);
+  refresh_tables(S, p, nt0, nt1, lane);
+  const RowRel r = load_rel(p, s, lane);
+  emit_row<MapT>(p, (unsigned)__cvta_generic_to_shared(base), dst, cellp, s, r, rowctr, lane);
+  return rowctr;
 }
 
 // any live agent (either species, newborns included) on cell `pos`?  = `pos in set(agent_positions.values())` (BASE:399,754)
-__device__ __forceinline__ bool any_agent_at(const EnvSmem& S, const int nl[2], unsigned pos, int lane) {
+template <typename MapT>
+__device__ __forceinline__ bool any_agent_at(const EnvSmem<MapT>& S, const int nl[2], unsigned pos, int lane) {
   bool hit = false;
 #pragma unroll
   for (int s = 0; s < 2; ++s)
@@ -260,16 +310,88 @@ __device__ __forceinline__ bool prefix_before(const unsigned long long* cnt, con
   }
 }
 
+// reset(): n_total unique cells in draw order (law of BASE:156-177) from the env's Philox placement stream
+__device__ __noinline__ void philox_placement(int* cells, unsigned* first, int n_total, int GG, unsigned env, unsigned episode,
+                                              unsigned long long seed_key, int lane) {
+  for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
+  __syncwarp();
+  int accepted = 0;
+  for (unsigned batch = 0; accepted < n_total; ++batch) {
+    const unsigned idx0 = batch * 128u + 4u * lane;
+    const ppg_u32x4 r = ppg_philox4x32(env, episode, idx0 >> 2, PPG_STREAM_PLACEMENT, (unsigned)seed_key, (unsigned)(seed_key >> 32));
+    unsigned cell[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cell[k] = ppg_bounded(r.v[k], (unsigned)GG);
+      atomicMin(&first[cell[k]], idx0 + k);
+    }
+    __syncwarp();
+    int mine = 0;
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k; mine += ok[k]; }
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    int posn = accepted + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) { if (posn < n_total) cells[posn] = (int)cell[k]; ++posn; }
+    accepted += __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+  }
+}
+
+// spawn fallback (BASE:760-764): the k-th free cell in ascending cell order, k from the env's Philox spawn stream.
+// Returns x << 8 | y, or -1 if no cell is free.
+template <typename MapT>
+__device__ __noinline__ int philox_free_cell(unsigned char* base, const StepParams& p, int nl0, int nl1, unsigned draw, int lane) {
+  const EnvSmem<MapT> S = carve<MapT>(base, p);
+  const int G = p.G, GG = p.GG;
+  const int nl[2] = {nl0, nl1};
+  int n_free = 0;
+  for (int c0 = 0; c0 < GG; c0 += 32) {
+    const int c = c0 + lane;
+    bool fr = c < GG;
+    if (fr) {
+      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
+    }
+    n_free += __popc(__ballot_sync(FULL, fr));
+  }
+  if (n_free == 0) return -1;
+  int kth = (int)ppg_bounded(draw, (unsigned)n_free);
+  for (int c0 = 0; c0 < GG; c0 += 32) {
+    const int c = c0 + lane;
+    bool fr = c < GG;
+    if (fr) {
+      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
+    }
+    const unsigned fm = __ballot_sync(FULL, fr);
+    const int cnt = __popc(fm);
+    if (kth < cnt) {
+      const int c = c0 + (int)__fns(fm, 0, kth + 1);
+      return ((c / G) << 8) | (c % G);
+    }
+    kth -= cnt;
+  }
+  return -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the step kernel: W persistent warps per CTA, one env per warp at a time
 // ------------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_constant__ StepParams p) {
+template <int W, typename MapT>
+__global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
-  const EnvSmem S = carve(sbase, p);
-  const int G = p.G, GG = p.GG;
+  const EnvSmem<MapT> S = carve<MapT>(sbase, p);
+  const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS, CH = p.CH;
   const unsigned epoch = p.epoch;
   const int par = (int)(epoch & 1u);
   const int mode_r = p.reward_mode;
@@ -277,23 +399,24 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
   const bool kick = mode_r == PPG_REWARD_SPARSE_KICKBACK;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // channel-0 window coordinates handled by this lane, per species (elements lane + 32*jj of the row)
-  unsigned wq[2][4];
-#pragma unroll
-  for (int s = 0; s < 2; ++s)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int q = lane + 32 * jj, R = p.R[s];
-      wq[s][jj] = q < R * R ? (unsigned)(((q / R) << 8) | (q % R)) : 0xFFFFFFFFu;
-    }
-  for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.scr)[i] = 0u;
+  // one-time set-up of this warp's slice: empty maps (predator map: WALL outside the field), wall table,
+  // touch counters.  Every env leaves the maps empty again (it un-writes the cells it wrote).
+  for (int i = lane; i < CH; i += 32) {
+    const int xx = (i - PP) / PS - PP, yy = (i - PP) % PS;
+    const bool field = i >= PP && xx >= 0 && xx < G && yy < G;
+    S.map[0][i] = (MapT)(field ? 0 : p.wall_idx);
+    S.map[1][i] = 0;
+    S.map[2][i] = 0;
+    S.scr[i] = 0;
+  }
+  for (int i = lane; i <= p.wall_idx; i += 32) S.wt[i] = i == p.wall_idx ? 1.f : 0.f;
   unsigned rowctr = 0;
   const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
   const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
   __syncwarp();
 
   for (;;) {
-    int env = 0;
+    int env = 0;  // PHASE: ticket+hdr
     if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
     env = __shfl_sync(FULL, env, 0);
     if (env >= p.B) break;
@@ -318,7 +441,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
 
-    if (mode == 1) {
+    if (mode == 1) {  // PHASE: reset
       // ------------------------------------------------------------------ reset() (BASE:129-217)
       h.episode += 1;
       h.step = 0;
@@ -327,12 +450,12 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       h.sortflag = 0;
       h.first_step = 1;
       h.state = 0;
-      if (lane == 0) bulk_wait_read<0>();  // the scratch below aliases the row staging buffers
+      if (lane == 0) bulk_wait_read<0>();  // the scratch below aliases the value tables and the row staging buffers
       __syncwarp();
       const int n_total = p.n_init[0] + p.n_init[1] + p.n_grass;
-      // cells in the order predators, prey, grass (BASE:185-187); staged in the entity/staging area
-      int* cells = reinterpret_cast<int*>(S.ent);         // [n_total]
-      unsigned* first = reinterpret_cast<unsigned*>(S.ent) + n_total;  // [GG] draw index that claimed the cell
+      // cells in the order predators, prey, grass (BASE:185-187)
+      int* cells = reinterpret_cast<int*>(S.vt[0]);                    // [n_total]
+      unsigned* first = reinterpret_cast<unsigned*>(S.vt[0]) + n_total;  // [GG] draw index that claimed the cell
       bool from_tape = false;
       if (p.tape_cells != nullptr) {
         if (h.tape_pos + n_total <= h.tape_end) {
@@ -343,39 +466,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           h.status |= PPG_STATUS_TAPE_EXHAUSTED;
         }
       }
-      if (!from_tape) {
-        // Philox rejection draws, accepted in draw order until n_total unique cells (law of BASE:156-177)
-        for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
-        __syncwarp();
-        int accepted = 0;
-        for (unsigned batch = 0; accepted < n_total; ++batch) {
-          const unsigned idx0 = batch * 128u + 4u * lane;
-          const ppg_u32x4 r = ppg_philox4x32((unsigned)env, h.episode, idx0 >> 2, PPG_STREAM_PLACEMENT,
-                                             (unsigned)h.seed_key, (unsigned)(h.seed_key >> 32));
-          unsigned cell[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            cell[k] = ppg_bounded(r.v[k], (unsigned)GG);
-            atomicMin(&first[cell[k]], idx0 + k);
-          }
-          __syncwarp();
-          int mine = 0;
-          bool ok[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k; mine += ok[k]; }
-          int incl = mine;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-          int posn = accepted + incl - mine;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (ok[k]) { if (posn < n_total) cells[posn] = (int)cell[k]; ++posn; }
-          accepted += __shfl_sync(FULL, incl, 31);
-          __syncwarp();
-        }
-      }
-      __syncwarp();
-      for (int i = lane; i < GG; i += 32) { S.own[0][i] = 0; S.own[1][i] = 0; }
+      if (!from_tape) philox_placement(cells, first, n_total, GG, (unsigned)env, h.episode, h.seed_key, lane);
       __syncwarp();
       // founders: slots in numeric id order (BASE:143-145,190-200)
       {
@@ -384,13 +475,14 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         for (int s = 0; s < 2; ++s) {
           for (int i = lane; i < p.n_init[s]; i += 32) {
             const int c = cells[k0 + i];
+            const int cx = c / G, cy = c % G;
             S.id[s][i] = (uint16_t)i;
-            S.pos[s][i] = (uint16_t)(((c / G) << 8) | (c % G));
+            S.pos[s][i] = (uint16_t)((cx << 8) | cy);
             S.E[s][i] = p.init_e[s];
             S.flg[s][i] = F_ALIVE;
             if (kick) S.par[s][i] = 0xFFFF;
             S.ord[s][i] = (uint16_t)i;
-            S.own[s][c] = (uint16_t)(i + 1);  // BASE:195,200 (cells are unique)
+            S.map[s][CELLXY(cx, cy)] = (MapT)(i + 1);  // BASE:195,200 (cells are unique)
           }
           k0 += p.n_init[s];
           n[s] = p.n_init[s];
@@ -400,8 +492,10 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         }
         for (int g = lane; g < p.n_grass; g += 32) {
           const int c = cells[k0 + g];
-          S.gpos[g] = (uint16_t)(((c / G) << 8) | (c % G));
+          const int cx = c / G, cy = c % G;
+          S.gpos[g] = (uint16_t)((cx << 8) | cy);
           S.gE[g] = p.grass_cap;  // BASE:203-208
+          S.map[2][CELLXY(cx, cy)] = (MapT)(g + 1);
         }
       }
       __syncwarp();
@@ -410,13 +504,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       env_flags = PPG_ENV_RESET;
     } else if (mode == 2) {
       // ------------------------------------------------------------------ step() (BASE:219-473)
-      n[0] = h.n_list[0]; n[1] = h.n_list[1];
-      // clear the maps while the loads are in flight
-      for (int i = lane; i < (GG + 1) / 2; i += 32) {
-        reinterpret_cast<unsigned*>(S.own[0])[i] = 0u;
-        reinterpret_cast<unsigned*>(S.own[1])[i] = 0u;
-      }
-      for (int i = lane; i < (GG + 3) / 4; i += 32) reinterpret_cast<unsigned*>(S.gmap)[i] = 0u;
+      n[0] = h.n_list[0]; n[1] = h.n_list[1];  // PHASE: load+decay+maps
       // load the lists; list order = action-dict order (default: row order of the previous output)
       unsigned bad = 0;
       bool resort[2] = {false, false};
@@ -461,9 +549,11 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
       for (int g = lane; g < p.n_grass; g += 32) {
         const size_t b = (size_t)env * p.n_grass;
-        S.gpos[g] = p.gr_pos[b + g];
+        const unsigned gp = p.gr_pos[b + g];
+        S.gpos[g] = (uint16_t)gp;
         const double v = p.gr_e[b + g] + p.grass_gain;  // regrowth (BASE:252-256)
         S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+        S.map[2][CELLP(gp)] = (MapT)(g + 1);
       }
       __syncwarp();
       // owner maps as the grid stands after Step 1: of agents sharing a cell the one latest in dict
@@ -474,33 +564,32 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           const int i = b0 + lane;
           const bool v = i < n[s];
           int cell = 0;
-          if (v) { cell = CELL((unsigned)S.pos[s][i]); S.own[s][cell] = (uint16_t)(i + 1); }
+          if (v) { cell = CELLP((unsigned)S.pos[s][i]); S.map[s][cell] = (MapT)(i + 1); }
           __syncwarp();
-          bool need = v && S.own[s][cell] < (unsigned)(i + 1);
+          bool need = v && S.map[s][cell] < (unsigned)(i + 1);
           while (__any_sync(FULL, need)) {
-            if (need) S.own[s][cell] = (uint16_t)(i + 1);
+            if (need) S.map[s][cell] = (MapT)(i + 1);
             __syncwarp();
-            need = v && S.own[s][cell] < (unsigned)(i + 1);
+            need = v && S.map[s][cell] < (unsigned)(i + 1);
           }
         }
-      for (int g = lane; g < p.n_grass; g += 32) S.gmap[CELL((unsigned)S.gpos[g])] = (uint8_t)(g + 1);
       __syncwarp();
 
-      // Step 2: movements, sequential semantics in dict order per species (BASE:259-273,495-509)
+      // Step 2: movements, sequential semantics in dict order per species (BASE:259-273,495-509)  // PHASE: movement
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        uint16_t* own = S.own[s];
+        MapT* own = S.map[s];
         for (int b0 = 0; b0 < n[s]; b0 += 32) {
           const int j = b0 + lane;
           const bool v = j < n[s];
-          int oc = 0, tc = 0, x = 0, y = 0, nx0 = 0, ny0 = 0;
+          int oc = 0, tc = 0, nx0 = 0, ny0 = 0;
           if (v) {
             const unsigned ps = S.pos[s][j];
             const int a = S.act[s][j];
-            x = ps >> 8; y = ps & 255;
+            const int x = ps >> 8, y = ps & 255;
             const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
             nx0 = min(max(x + ax - 1, 0), G - 1); ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
-            oc = x * G + y; tc = nx0 * G + ny0;
+            oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
             atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
             if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
           }
@@ -513,8 +602,8 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             const unsigned ow = own[tc];
             const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;  // own-species channel occupied (BASE:506)
             const int nc = blocked ? oc : tc;
-            own[oc] = 0;                    // BASE:268,272
-            own[nc] = (uint16_t)(j + 1);    // BASE:269,273
+            own[oc] = 0;               // BASE:268,272
+            own[nc] = (MapT)(j + 1);   // BASE:269,273
             if (!blocked) S.pos[s][j] = (uint16_t)((nx0 << 8) | ny0);
           }
           __syncwarp();
@@ -527,19 +616,19 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             const int xx = ps >> 8, yy = ps & 255;
             const int ax = (a * 11) >> 5;
             const int tx = min(max(xx + ax - 1, 0), G - 1), ty = min(max(yy + (a - 3 * ax) - 1, 0), G - 1);
-            const unsigned ow = own[tx * G + ty];
+            const unsigned ow = own[CELLXY(tx, ty)];
             const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;
             const int nx = blocked ? xx : tx, ny = blocked ? yy : ty;
             __syncwarp();
-            own[xx * G + yy] = 0;
-            own[nx * G + ny] = (uint16_t)(jj + 1);
+            own[CELLXY(xx, yy)] = 0;
+            own[CELLXY(nx, ny)] = (MapT)(jj + 1);
             S.pos[s][jj] = (uint16_t)((nx << 8) | ny);
             __syncwarp();
           }
         }
       }
 
-      // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order.  The list is
+      // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order.  The list is  // PHASE: sort
       // the sorted survivors followed by last step's newborns, so only the newborns have to be ranked in.
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -561,27 +650,27 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         }
       }
 
-      // Step 3a: predators in engagement order (BASE:279-346).  Nothing happens unless a predator
+      // Step 3a: predators in engagement order (BASE:279-346).  Nothing happens unless a predator  // PHASE: predators
       // starved or some prey (any energy) stands on a live predator's cell.
       bool ev = false;
       for (int i = lane; i < n[0]; i += 32) {
         if (S.E[0][i] <= 0.0) ev = true;
-        else S.scr[CELL((unsigned)S.pos[0][i])] = 1;
+        else S.scr[CELLP((unsigned)S.pos[0][i])] = 1;
       }
       __syncwarp();
-      for (int i = lane; i < n[1]; i += 32) ev |= S.scr[CELL((unsigned)S.pos[1][i])] != 0;
+      for (int i = lane; i < n[1]; i += 32) ev |= S.scr[CELLP((unsigned)S.pos[1][i])] != 0;
       __syncwarp();
-      for (int i = lane; i < n[0]; i += 32) S.scr[CELL((unsigned)S.pos[0][i])] = 0;
+      for (int i = lane; i < n[0]; i += 32) S.scr[CELLP((unsigned)S.pos[0][i])] = 0;
       __syncwarp();
       if (__any_sync(FULL, ev)) {
         for (int k = 0; k < n[0]; ++k) {
           const int slot = S.ord[0][k];
           const unsigned ps = S.pos[0][slot];
-          const int cell = CELL(ps);
+          const int cell = CELLP(ps);
           double e = S.E[0][slot];
           if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
-            emit_row_now(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], ps, 0, n[0], n[1], &rowctr, lane);
-            S.own[0][cell] = 0;  // BASE:293
+            rowctr = emit_row_now<MapT>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, n[0], n[1], rowctr, lane);
+            S.map[0][cell] = 0;  // BASE:293
             S.flg[0][slot] = F_DIED;
             st_starved[0]++;
             __syncwarp();
@@ -597,11 +686,11 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             e += S.E[1][q];  // BASE:324 (also when the prey's energy is <= 0)
             __syncwarp();
             S.E[0][slot] = e;
-            S.own[0][cell] = (uint16_t)(slot + 1);  // BASE:325
+            S.map[0][cell] = (MapT)(slot + 1);  // BASE:325
             S.flg[0][slot] |= F_ATE;
             __syncwarp();
-            emit_row_now(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], ps, 1, n[0], n[1], &rowctr, lane);  // BASE:327
-            S.own[1][cell] = 0;  // BASE:335
+            rowctr = emit_row_now<MapT>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, n[0], n[1], rowctr, lane);  // BASE:327
+            S.map[1][cell] = 0;  // BASE:335
             S.flg[1][q] = F_DIED | F_CAUGHT;
             st_eaten++;
             __syncwarp();
@@ -609,7 +698,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         }
       }
 
-      // Step 3b: prey in engagement order (BASE:347-380)
+      // Step 3b: prey in engagement order (BASE:347-380)  // PHASE: prey
       for (int b0 = 0; b0 < n[1]; b0 += 32) {
         const int k = b0 + lane;
         int slot = 0, cell = 0, g = 0;
@@ -620,8 +709,8 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           alive = (S.flg[1][slot] & F_ALIVE) != 0;  // not caught above (BASE:281)
           e = S.E[1][slot];
           starved = alive && e <= 0.0;
-          cell = CELL((unsigned)S.pos[1][slot]);
-          g = S.gmap[cell];
+          cell = CELLP((unsigned)S.pos[1][slot]);
+          g = S.map[2][cell];
         }
         const bool eat = alive && !starved && g != 0;
         if (eat) S.gtag[g - 1] = (uint8_t)lane;
@@ -630,7 +719,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         if (!__any_sync(FULL, starved || clash)) {
           if (eat) {  // BASE:351-372 (a patch with energy 0 is still "eaten")
             S.E[1][slot] = e + S.gE[g - 1];
-            S.own[1][cell] = (uint16_t)(slot + 1);
+            S.map[1][cell] = (MapT)(slot + 1);
             S.gE[g - 1] = 0.0;
             S.flg[1][slot] |= F_ATE;
           }
@@ -643,23 +732,22 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
         for (int kk = b0; kk < kend; ++kk) {  // exact sequential order for this chunk
           const int sl = S.ord[1][kk];
           if (!(S.flg[1][sl] & F_ALIVE)) continue;
-          const unsigned ps = S.pos[1][sl];
-          const int cl = CELL(ps);
+          const int cl = CELLP((unsigned)S.pos[1][sl]);
           const double ee = S.E[1][sl];
           if (ee <= 0.0) {  // BASE:284-301
-            emit_row_now(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], ps, 1, n[0], n[1], &rowctr, lane);
-            S.own[1][cl] = 0;
+            rowctr = emit_row_now<MapT>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, n[0], n[1], rowctr, lane);
+            S.map[1][cl] = 0;
             S.flg[1][sl] = F_DIED;
             st_starved[1]++;
             __syncwarp();
             continue;
           }
-          const int gg = S.gmap[cl];
+          const int gg = S.map[2][cl];
           if (gg) {
             const double en = ee + S.gE[gg - 1];
             __syncwarp();
             S.E[1][sl] = en;
-            S.own[1][cl] = (uint16_t)(sl + 1);
+            S.map[1][cl] = (MapT)(sl + 1);
             S.gE[gg - 1] = 0.0;
             S.flg[1][sl] |= F_ATE;
             st_grass++;
@@ -669,7 +757,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       }
       __syncwarp();
 
-      // Step 5: births in engagement order, predators then prey (BASE:389-448)
+      // Step 5: births in engagement order, predators then prey (BASE:389-448)  // PHASE: births
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         for (int b0 = 0; b0 < n[s]; b0 += 32) {
@@ -708,38 +796,9 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
               } else {
                 if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
                 // uniformly random free cell, ascending cell order, Philox draw
-                int n_free = 0;
-                for (int c0 = 0; c0 < GG; c0 += 32) {
-                  const int c = c0 + lane;
-                  bool fr = c < GG;
-                  if (fr) {
-                    const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-                    for (int s2 = 0; s2 < 2; ++s2)
-                      for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
-                  }
-                  n_free += __popc(__ballot_sync(FULL, fr));
-                }
-                if (n_free > 0) {
-                  int kth = (int)ppg_bounded(ppg_draw_u32(h.seed_key, (unsigned)env, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), (unsigned)n_free);
-                  h.spawn_draws++;
-                  for (int c0 = 0; c0 < GG && sx < 0; c0 += 32) {
-                    const int c = c0 + lane;
-                    bool fr = c < GG;
-                    if (fr) {
-                      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-                      for (int s2 = 0; s2 < 2; ++s2)
-                        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
-                    }
-                    const unsigned fm = __ballot_sync(FULL, fr);
-                    const int cnt = __popc(fm);
-                    if (kth < cnt) {
-                      const int c = c0 + (int)__fns(fm, 0, kth + 1);
-                      sx = c / G; sy = c % G;
-                    } else {
-                      kth -= cnt;
-                    }
-                  }
-                }
+                const int c = philox_free_cell<MapT>(sbase, p, nl[0], nl[1],
+                                                     ppg_draw_u32(h.seed_key, (unsigned)env, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), lane);
+                if (c >= 0) { h.spawn_draws++; sx = c >> 8; sy = c & 255; }
               }
               if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises here
             }
@@ -753,8 +812,8 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             S.E[s][cs] = p.init_e[s];  // BASE:403
             S.flg[s][cs] = F_ALIVE | F_NEWBORN;
             S.E[s][ps_slot] = pe;
-            S.own[s][sx * G + sy] = (uint16_t)(cs + 1);       // BASE:405
-            S.own[s][px * G + py] = (uint16_t)(ps_slot + 1);  // BASE:406
+            S.map[s][CELLXY(sx, sy)] = (MapT)(cs + 1);       // BASE:405
+            S.map[s][CELLXY(px, py)] = (MapT)(ps_slot + 1);  // BASE:406
             S.flg[s][ps_slot] |= F_REPRO;
             if (kick) {  // KICK:434-449
               S.aux[s][cs] = 0;
@@ -780,7 +839,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       }
       __syncwarp();
 
-      // counts, termination, truncation (BASE:456-471)
+      // counts, termination, truncation (BASE:456-471)  // PHASE: counts
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         int c = 0;
@@ -801,7 +860,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       env_flags = PPG_ENV_IDLE;
     }
 
-    // ---------------------------------------------------------------- publish the counts
+    // ---------------------------------------------------------------- publish the counts  // PHASE: publish
     {
       const int blk = env >> 5, grp = env >> 10;
       bool last = false;
@@ -842,9 +901,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           __threadfence();
           __syncwarp();
           bool last3 = false;
-          if (lane == 0) {
-            last3 = (atomicAdd(p.done3, 1u) + 1u) % (unsigned)n_grp == 0u;
-          }
+          if (lane == 0) last3 = (atomicAdd(p.done3, 1u) + 1u) % (unsigned)n_grp == 0u;
           if (__shfl_sync(FULL, last3, 0)) {  // last group: totals of this output and of the next one
             __threadfence();
             int t[4] = {0, 0, 0, 0};
@@ -867,32 +924,48 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
       }
     }
 
-    // ------------------------------------------------- rows: metadata, observations, state write-back
+    // ------------------------------------------------- rows: metadata, observations, state write-back  // PHASE: rows pass1
     if (lane == 0) {
       p.old_off[0][env] = old_base[0];
       p.old_off[1][env] = old_base[1];
     }
     if (mode != 0) {
       const bool keep = !(over && p.autoreset);  // lists of a finished env are dead when it auto-resets
-      const int n_ent = build_entities(sbase, p, n[0] + births[0], n[1] + births[1], lane);
+      refresh_tables(S, p, n[0] + births[0], n[1] + births[1], lane);
       int wpos[2] = {0, 0};
+      int new_base[2] = {0, 0};
+      for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
+      if (pass == 1) {
+        if (births[0] + births[1] == 0) break;
+        // newborn rows: their first row depends on the births of every env before this one; by now
+        // (all other work of this env is done) the predecessors have normally published theirs
+        int nb0 = 0, nb1 = 0;
+        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+          if (lane == 0) atomicOr(p.error, 1u);
+        }
+        new_base[0] = n_old_total[0] + nb0;
+        new_base[1] = n_old_total[1] + nb1;
+      }
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const size_t sb = (size_t)env * p.cap[s];
         float* obs_s = p.obs[s];
         const int elems = p.elems[s];
-        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+        const int k_lo = pass == 0 ? 0 : n[s], tot = pass == 0 ? n[s] : n[s] + births[s];
+        if (k_lo >= tot) continue;
+        const RowRel rr = load_rel(p, s, lane);
+        for (int b0 = k_lo; b0 < tot; b0 += 32) {
           const int k = b0 + lane;
-          int row = 0, slot = 0;
-          unsigned apos = 0;
+          int row = 0, slot = 0, cellp = 0;
           bool alive = false;
-          if (k < n[s]) {
-            slot = S.ord[s][k];
-            row = old_base[s] + k;
+          if (k < tot) {
+            const bool newborn = k >= n[s];
+            slot = newborn ? k : S.ord[s][k];
+            row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
             const unsigned f = S.flg[s][slot];
             const double e = S.E[s][slot];
             double rew = 0.0;
-            if (mode == 2) {
+            if (mode == 2 && !newborn) {
               if (dense) {
                 const double e0 = S.E0[s][slot];
                 if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
@@ -909,6 +982,7 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             unsigned rf = 0;
             if (f & F_DIED) rf |= PPG_ROW_TERMINATED;
             if ((f & F_ALIVE) && trunc) rf |= PPG_ROW_TRUNCATED;
+            if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
             if (mode == 1) rf |= PPG_ROW_FOUNDER;
             if (f & F_ATE) rf |= PPG_ROW_ATE;
             p.row_env[s][row] = env;
@@ -916,14 +990,15 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
             p.reward[s][row] = (float)rew;
             p.flags[s][row] = (uint8_t)rf;
             alive = (f & F_ALIVE) != 0;
-            apos = S.pos[s][slot];
+            const unsigned apos = S.pos[s][slot];
+            cellp = CELLP(apos);
           }
           unsigned m = __ballot_sync(FULL, alive);
-          // survivors in engagement order (= `self.agents` after the sort), newborns follow (BASE:398,468)
+          // survivors in engagement order (= `self.agents` after the sort), then newborns (BASE:398,468)
           if (keep && alive) {
             const int dst = wpos[s] + __popc(m & lt_mask);
             p.ag_id[s][sb + dst] = S.id[s][slot];
-            p.ag_pos[s][sb + dst] = (uint16_t)apos;
+            p.ag_pos[s][sb + dst] = S.pos[s][slot];
             p.ag_e[s][sb + dst] = S.E[s][slot];
             p.ag_prow[s][sb + dst] = row;
             if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
@@ -933,67 +1008,31 @@ __global__ void __launch_bounds__(W * 32) ppg_step_base_kernel(const __grid_cons
           while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
-            const unsigned ap = __shfl_sync(FULL, apos, l);
+            const int cp = __shfl_sync(FULL, cellp, l);
             const int r = __shfl_sync(FULL, row, l);
-            emit_row(p, S, obs_s + (size_t)r * elems, ap, s, n_ent, rowctr, wq[s], lane);
+            emit_row<MapT>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane);
           }
         }
       }
-      // newborn rows: their first row depends on the births of every env before this one
-      int new_base[2] = {0, 0};
-      if (births[0] + births[1] > 0) {
-        int nb0 = 0, nb1 = 0;
-        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
-          if (lane == 0) atomicOr(p.error, 1u);
-        }
-        new_base[0] = n_old_total[0] + nb0;
-        new_base[1] = n_old_total[1] + nb1;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const size_t sb = (size_t)env * p.cap[s];
-          for (int b0 = 0; b0 < births[s]; b0 += 32) {
-            const int j = b0 + lane;
-            unsigned apos = 0;
-            int row = 0;
-            const bool v = j < births[s];
-            if (v) {
-              const int slot = n[s] + j;
-              row = new_base[s] + j;
-              apos = S.pos[s][slot];
-              p.row_env[s][row] = env;
-              p.row_agent[s][row] = S.id[s][slot];
-              p.reward[s][row] = 0.f;  // BASE:408,437
-              p.flags[s][row] = (uint8_t)(PPG_ROW_NEWBORN | (trunc ? PPG_ROW_TRUNCATED : 0));
-              if (keep) {
-                const int dst = wpos[s] + j;
-                p.ag_id[s][sb + dst] = S.id[s][slot];
-                p.ag_pos[s][sb + dst] = (uint16_t)apos;
-                p.ag_e[s][sb + dst] = S.E[s][slot];
-                p.ag_prow[s][sb + dst] = row;
-                if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
-              }
-            }
-            unsigned m = __ballot_sync(FULL, v);
-            while (m) {
-              const int l = __ffs(m) - 1;
-              m &= m - 1;
-              const unsigned ap = __shfl_sync(FULL, apos, l);
-              const int r = __shfl_sync(FULL, row, l);
-              emit_row(p, S, p.obs[s] + (size_t)r * p.elems[s], ap, s, n_ent, rowctr, wq[s], lane);
-            }
-          }
-        }
       }
-      if (lane < 2) {
+      if (lane < 2) {  // PHASE: tail
         const int nb = lane == 0 ? births[0] : births[1];
         p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
         p.new_cnt[lane][env] = nb;
       }
+      // leave the maps empty for the next env of this warp: un-write every cell that can hold an entry
+      // (a non-zero owner entry always has its owner standing on it)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        for (int i = lane; i < n[s] + births[s]; i += 32)
+          if (S.flg[s][i] & F_ALIVE) S.map[s][CELLP((unsigned)S.pos[s][i])] = 0;
+      for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
       if (keep) {
-        h.n_sorted[0] = (unsigned short)wpos[0];
-        h.n_sorted[1] = (unsigned short)wpos[1];
-        h.n_list[0] = (unsigned short)(wpos[0] + births[0]);
-        h.n_list[1] = (unsigned short)(wpos[1] + births[1]);
+        const int live0 = wpos[0] - births[0], live1 = wpos[1] - births[1];
+        h.n_sorted[0] = (unsigned short)live0;
+        h.n_sorted[1] = (unsigned short)live1;
+        h.n_list[0] = (unsigned short)wpos[0];
+        h.n_list[1] = (unsigned short)wpos[1];
         unsigned char sf = 0;
         if (mode == 2) {
           if (births[0] > 0 || h.first_step) sf |= 1;
@@ -1190,39 +1229,41 @@ __global__ void ppg_stats_kernel(const uint32_t* __restrict__ counters, const En
 // ------------------------------------------------------------------------------------------------
 // launch wrappers used by ppg_api.cu
 // ------------------------------------------------------------------------------------------------
-template <int W>
+template <int W, typename MapT>
 static cudaError_t launch_w(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;  // opt in to > 48 KB of dynamic shared memory (grows monotonically)
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_base_kernel<W><<<n_cta, W * 32, smem, stream>>>(p);
+  ppg_step_base_kernel<W, MapT><<<n_cta, W * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream) {
+  const bool m8 = p.map_bytes == 1;
   switch (warps_per_cta) {
-    case 1: return launch_w<1>(p, n_cta, smem, stream);
-    case 2: return launch_w<2>(p, n_cta, smem, stream);
-    case 4: return launch_w<4>(p, n_cta, smem, stream);
+    case 1: return m8 ? launch_w<1, uint8_t>(p, n_cta, smem, stream) : launch_w<1, uint16_t>(p, n_cta, smem, stream);
+    case 2: return m8 ? launch_w<2, uint8_t>(p, n_cta, smem, stream) : launch_w<2, uint16_t>(p, n_cta, smem, stream);
+    case 4: return m8 ? launch_w<4, uint8_t>(p, n_cta, smem, stream) : launch_w<4, uint16_t>(p, n_cta, smem, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
-template <int W>
+template <int W, typename MapT>
 static cudaError_t occupancy_w(size_t smem, int* blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W>, W * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W, MapT>, W * 32, smem);
 }
 
-cudaError_t step_base_occupancy(int warps_per_cta, size_t smem, int* blocks_per_sm) {
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, size_t smem, int* blocks_per_sm) {
+  const bool m8 = map_bytes == 1;
   switch (warps_per_cta) {
-    case 1: return occupancy_w<1>(smem, blocks_per_sm);
-    case 2: return occupancy_w<2>(smem, blocks_per_sm);
-    case 4: return occupancy_w<4>(smem, blocks_per_sm);
+    case 1: return m8 ? occupancy_w<1, uint8_t>(smem, blocks_per_sm) : occupancy_w<1, uint16_t>(smem, blocks_per_sm);
+    case 2: return m8 ? occupancy_w<2, uint8_t>(smem, blocks_per_sm) : occupancy_w<2, uint16_t>(smem, blocks_per_sm);
+    case 4: return m8 ? occupancy_w<4, uint8_t>(smem, blocks_per_sm) : occupancy_w<4, uint16_t>(smem, blocks_per_sm);
     default: return cudaErrorInvalidValue;
   }
 }

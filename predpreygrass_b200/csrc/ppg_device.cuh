@@ -20,6 +20,8 @@
 
 namespace ppg {
 
+#define PPG_MAX_NJ 13  // observation rows of up to 416 floats
+
 struct __align__(16) EnvHdr {
   unsigned long long seed_key;  // Philox key of this env (ppg_reset seeds)
   long long tape_pos, tape_end; // replay-tape cursor into tape_cells
@@ -102,10 +104,17 @@ struct StepParams {
   int32_t* env_step;
   int32_t* env_count;
   // ---- shared-memory layout, byte offsets inside one env's region ----
-  int so_E[2], so_E0[2], so_gE, so_ent, so_stage, so_scr, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2];
-  int so_own[2], so_gpos, so_act[2], so_flg[2], so_aux[2], so_gmap, so_gtag;
+  int so_E[2], so_E0[2], so_gE, so_wt, so_vt[3], so_stage, so_scr, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2];
+  int so_map[3], so_gpos, so_act[2], so_flg[2], so_aux[2], so_gtag;
   int stage_elems;  // floats per staging row buffer (max over species, multiple of 4)
   int smem_per_env;
+  // ---- padded map geometry and the observation gather tables (see ppg_base.cu) ----
+  int P, PS, CH;        // halo width, row stride, entries per map:  index(x, y) = P + (x + P) * PS + y
+  int map_bytes;        // sizeof(map entry): 1 (all capacities <= 253) or 2
+  int wall_idx;         // value the predator map holds outside the field (index of the 1.0 entry of the wall table)
+  int nj[2];            // gather iterations per species = ceil(elems / 32)
+  const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
+                        //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };
 
 }  // namespace ppg
