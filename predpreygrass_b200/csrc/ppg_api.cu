@@ -12,7 +12,7 @@
 
 namespace ppg {
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, size_t smem, int* blocks_per_sm);
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, size_t smem, int* blocks_per_sm);
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
                                    unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s);
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
@@ -184,7 +184,13 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.CH = (int)align_up((size_t)P.P + (size_t)(G + 2 * P.P) * P.PS + P.P, 4);
   P.map_bytes = (P.cap[0] <= 253 && P.cap[1] <= 253 && P.n_grass <= 253) ? 1 : 2;
   P.wall_idx = P.cap[0] + 1;
-  for (int s = 0; s < 2; ++s) P.nj[s] = (P.elems[s] + 31) / 32;
+  for (int s = 0; s < 2; ++s) {
+    P.obs_vec[s] = P.elems[s] % 4 == 0;
+    P.nj[s] = P.obs_vec[s] ? 4 * ((P.elems[s] / 4 + 31) / 32) : (P.elems[s] + 31) / 32;
+    P.emit_kind[s] = (P.obs_vec[s] && P.nj[s] == 8) ? 1 : (P.obs_vec[s] && P.nj[s] == 12) ? 2 : (!P.obs_vec[s] && P.nj[s] == 13) ? 3 : 0;
+  }
+  P.obs_bulk = 0;
+  if (const char* ev = getenv("PPG_OBS_BULK")) P.obs_bulk = atoi(ev) != 0;
   if (P.nj[0] > PPG_MAX_NJ || P.nj[1] > PPG_MAX_NJ) { h->err = "observation row too large for this build"; return fail(PPG_ERR_INVALID); }
 
   // shared-memory layout of one env (see EnvSmem in ppg_base.cu)
@@ -193,7 +199,6 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   for (int s = 0; s < 2; ++s) { P.so_E[s] = take(8 * (size_t)P.cap[s], 8); P.so_E0[s] = take(dense ? 8 * (size_t)P.cap[s] : 0, 8); }
   P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
   P.stage_elems = (int)align_up((size_t)std::max(P.elems[0], P.elems[1]), 4);
-  P.so_wt = take(4 * (size_t)(P.cap[0] + 2), 4);
   // value tables and staging rows are contiguous: reset() stages n_total cells + a GG-entry claim table there
   P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
   P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
@@ -202,13 +207,19 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass + GG) * 4 > (size_t)(P.so_stage + 8 * P.stage_elems - P.so_vt[0])) {
     h->err = "internal: reset scratch does not fit the table/staging area"; return fail(PPG_ERR_INVALID);
   }
-  P.so_scr = take((size_t)P.CH, 4);
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_par[s] = take(kick ? 2 * (size_t)P.cap[s] : 0, 2);
   }
-  for (int m = 0; m < 3; ++m) P.so_map[m] = take((size_t)P.map_bytes * P.CH, 4);
+  // maps, touch counters and wall table are contiguous: their initial contents are one image copied by every warp
+  P.so_map[0] = take((size_t)P.map_bytes * P.CH, 16);
+  P.so_map[1] = take((size_t)P.map_bytes * P.CH, 4);
+  P.so_map[2] = take((size_t)P.map_bytes * P.CH, 4);
+  P.so_scr = take((size_t)P.CH, 4);
+  P.so_wt = take(4 * (size_t)(P.cap[0] + 2), 4);
+  o = align_up(o, 16);
+  P.init_bytes = (int)(o - (size_t)P.so_map[0]);
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
   for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(kick ? P.cap[s] : 0, 1); }
   P.so_gtag = take(std::max(1, P.n_grass), 1);
@@ -218,6 +229,22 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   {
     // per-lane gather constants: element q = lane + 32 j of a row is channel c, window cell (i, jj);
     // BASE channels: 0 = outside the grid (predator map halo -> wall table), 1 predators, 2 prey, 3 grass
+    {
+      std::vector<unsigned char> img((size_t)P.init_bytes, 0);
+      for (int i = 0; i < P.CH; ++i) {
+        const int xx = i >= P.P ? (i - P.P) / P.PS - P.P : -1, yy = i >= P.P ? (i - P.P) % P.PS : 0;
+        const bool field = i >= P.P && xx >= 0 && xx < G && yy < G;
+        if (!field) {
+          if (P.map_bytes == 1) img[(size_t)i] = (unsigned char)P.wall_idx;
+          else reinterpret_cast<uint16_t*>(img.data())[i] = (uint16_t)P.wall_idx;
+        }
+      }
+      reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
+      unsigned char* d_img = nullptr;
+      CKC(dalloc(h, &d_img, img.size()));
+      CKC(cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+      P.init_image = d_img;
+    }
     std::vector<int> rel((size_t)2 * PPG_MAX_NJ * 32 * 2, 0);
     for (int s = 0; s < 2; ++s) {
       const int R = P.R[s], RR = R * R;
@@ -225,7 +252,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
         for (int lane = 0; lane < 32; ++lane) {
           const size_t at0 = ((size_t)(s * PPG_MAX_NJ + j) * 32 + lane) * 2;
           rel[at0] = 0; rel[at0 + 1] = P.so_wt;  // lanes past the end of the row: a harmless in-range read, never stored
-          const int q = j * 32 + lane;
+          const int q = P.obs_vec[s] ? 4 * (lane + 32 * (j / 4)) + (j % 4) : j * 32 + lane;
           if (q >= P.elems[s]) continue;
           const int ch = q / RR, i = (q % RR) / R, jj = q % R;
           const int m = ch == 0 ? 0 : ch - 1;
@@ -242,14 +269,14 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   }
   int W = 1;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
-  if (W != 1 && W != 2 && W != 4) W = 1;
+  if (W != 1 && W != 4) W = 1;
   while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    CKC(step_base_occupancy(W, P.map_bytes, h->smem_bytes, &per_sm));
+    CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
     h->n_cta = std::min((B + W - 1) / W, per_sm * n_sm);

@@ -186,75 +186,114 @@ __device__ __forceinline__ float lds_f32(unsigned a) {
 }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
-// _get_observation (BASE:511-539) of the agent whose padded cell index is `cellp` into global row `dst`:
-// element lane + 32 j = table[map[cell + const]], NJ = ceil(row elements / 32) iterations.
-template <typename MapT, int NJ>
-__device__ __forceinline__ void emit_row_nj(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
-                                            unsigned& rowctr, int lane) {
-  const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
-  ++rowctr;
-  if (lane == 0) bulk_wait_read<1>();  // the copy issued two rows ago has finished reading `buf`
-  __syncwarp();
+// _get_observation (BASE:511-539) of the agent whose padded cell index is `cellp` into global row `dst`.
+// Every lane produces N elements of the row, element = table[map[cell + const]]:
+//   VEC  (row length a multiple of 4): lane l owns the float4 groups l, l+32, ... (4 consecutive elements each;
+//        with byte maps the 32 lanes of one load still hit 32 different banks) and stores them with STG.128;
+//   !VEC: lane l owns elements l, l+32, ... and stores 32-bit words, 128 contiguous bytes per warp instruction.
+// BULK stages the row in shared memory and hands it to the bulk-copy engine instead (cp.async.bulk, one
+// 784/1296/1620-byte copy per row, double buffered); measured slower than direct streaming stores for rows this
+// small, kept selectable with PPG_OBS_BULK=1.
+template <typename MapT, int N, bool VEC, bool BULK>
+__device__ __forceinline__ void emit_row_t(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
+                                           unsigned& rowctr, int lane) {
   const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
-  const unsigned o0 = buf + 4u * lane;
-  const bool tail_ok = lane + 32 * (NJ - 1) < p.elems[s];
-  unsigned idx[NJ];
-  float val[NJ];
+  unsigned idx[N];
+  float val[N];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) idx[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
+  for (int j = 0; j < N; ++j) idx[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) val[j] = lds_f32(sb32 + (unsigned)r.tbl[j] + 4u * idx[j]);
+  for (int j = 0; j < N; ++j) val[j] = lds_f32(sb32 + (unsigned)r.tbl[j] + 4u * idx[j]);
+  const int elems = p.elems[s];
+  if (BULK) {
+    const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
+    ++rowctr;
+    if (lane == 0) bulk_wait_read<1>();  // the copy issued two rows ago has finished reading `buf`
+    __syncwarp();
+    if (VEC) {
 #pragma unroll
-  for (int j = 0; j < NJ - 1; ++j) sts_f32(o0 + 128u * j, val[j]);
-  if (tail_ok) sts_f32(o0 + 128u * (NJ - 1), val[NJ - 1]);
-  fence_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    bulk_store(dst, buf, (unsigned)p.elems[s] * 4u);
-    bulk_commit();
-  }
-}
-
-template <typename MapT>
-__device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
-                                         unsigned& rowctr, int lane) {
-  switch (p.nj[s]) {  // warp-uniform; the row sizes of the reference's env family get straight-line code
-    case 7: emit_row_nj<MapT, 7>(p, sb32, dst, cellp, s, r, rowctr, lane); break;    // (4,7,7)
-    case 11: emit_row_nj<MapT, 11>(p, sb32, dst, cellp, s, r, rowctr, lane); break;  // (4,9,9)
-    case 13: emit_row_nj<MapT, 13>(p, sb32, dst, cellp, s, r, rowctr, lane); break;  // (5,9,9)
-    default: {
-      // any other shape: same thing, one element at a time
-      const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
-      ++rowctr;
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
-#pragma unroll 1
-      for (int j = 0; j < p.nj[s]; ++j) {
-        if (lane + 32 * j < p.elems[s]) {
-          const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
-          const unsigned idx = lds_map<MapT>(a0 + (unsigned)v.x);
-          sts_f32(buf + 4u * (lane + 32 * j), lds_f32(sb32 + (unsigned)v.y + 4u * idx));
+      for (int v = 0; v < N / 4; ++v)
+        if (4 * (lane + 32 * v) < elems) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sts_f32(buf + 16u * (lane + 32 * v) + 4u * k, val[4 * v + k]);
         }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_store(dst, buf, (unsigned)p.elems[s] * 4u);
-        bulk_commit();
-      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (lane + 32 * j < elems) sts_f32(buf + 4u * (lane + 32 * j), val[j]);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store(dst, buf, (unsigned)elems * 4u);
+      bulk_commit();
+    }
+  } else {
+    if (VEC) {
+      float4* d = reinterpret_cast<float4*>(dst) + lane;
+#pragma unroll
+      for (int v = 0; v < N / 4; ++v)
+        if (4 * (lane + 32 * v) < elems) __stcs(d + 32 * v, make_float4(val[4 * v], val[4 * v + 1], val[4 * v + 2], val[4 * v + 3]));
+    } else {
+      float* d = dst + lane;
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (lane + 32 * j < elems) __stcs(d + 32 * j, val[j]);
     }
   }
 }
 
+// any row shape: one element at a time
+template <typename MapT, bool BULK>
+__device__ __noinline__ unsigned emit_row_generic(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, unsigned rowctr, int lane) {
+  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
+  const bool vec = p.obs_vec[s] != 0;
+  unsigned buf = 0;
+  if (BULK) {
+    buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
+    ++rowctr;
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int j = 0; j < p.nj[s]; ++j) {
+    const int q = vec ? 4 * (lane + 32 * (j >> 2)) + (j & 3) : lane + 32 * j;
+    if (q < p.elems[s]) {
+      const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
+      const float x = lds_f32(sb32 + (unsigned)v.y + 4u * lds_map<MapT>(a0 + (unsigned)v.x));
+      if (BULK) sts_f32(buf + 4u * q, x); else __stcs(dst + q, x);
+    }
+  }
+  if (BULK) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store(dst, buf, (unsigned)p.elems[s] * 4u);
+      bulk_commit();
+    }
+  }
+  return rowctr;
+}
+
+template <typename MapT, bool BULK>
+__device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
+                                         unsigned& rowctr, int lane) {
+  switch (p.emit_kind[s]) {  // warp-uniform; the row shapes of the reference's env family get straight-line code
+    case 1: emit_row_t<MapT, 8, true, BULK>(p, sb32, dst, cellp, s, r, rowctr, lane); break;    // (4,7,7): 49 float4
+    case 2: emit_row_t<MapT, 12, true, BULK>(p, sb32, dst, cellp, s, r, rowctr, lane); break;   // (4,9,9): 81 float4
+    case 3: emit_row_t<MapT, 13, false, BULK>(p, sb32, dst, cellp, s, r, rowctr, lane); break;  // (5,9,9): 405 floats
+    default: rowctr = emit_row_generic<MapT, BULK>(p, sb32, dst, cellp, s, rowctr, lane);
+  }
+}
+
 // rows of agents that die mid-step: the reference captures them at that moment (BASE:287,327)
-template <typename MapT>
+template <typename MapT, bool BULK>
 __device__ __noinline__ unsigned emit_row_now(unsigned char* base, const StepParams& p, float* dst, int cellp, int s, int nt0, int nt1,
                                               unsigned rowctr, int lane) {
   const EnvSmem<MapT> S = carve<MapT>(base, p);
   refresh_tables(S, p, nt0, nt1, lane);
   const RowRel r = load_rel(p, s, lane);
-  emit_row<MapT>(p, (unsigned)__cvta_generic_to_shared(base), dst, cellp, s, r, rowctr, lane);
+  emit_row<MapT, BULK>(p, (unsigned)__cvta_generic_to_shared(base), dst, cellp, s, r, rowctr, lane);
   return rowctr;
 }
 
@@ -384,14 +423,16 @@ __device__ __noinline__ int philox_free_cell(unsigned char* base, const StepPara
 // ------------------------------------------------------------------------------------------------
 // the step kernel: W persistent warps per CTA, one env per warp at a time
 // ------------------------------------------------------------------------------------------------
-template <int W, typename MapT>
+#define SEL(a) (s == 0 ? a[0] : a[1])
+
+template <int W, typename MapT, bool BULK>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
-  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS, CH = p.CH;
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const unsigned epoch = p.epoch;
   const int par = (int)(epoch & 1u);
   const int mode_r = p.reward_mode;
@@ -399,17 +440,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
   const bool kick = mode_r == PPG_REWARD_SPARSE_KICKBACK;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // one-time set-up of this warp's slice: empty maps (predator map: WALL outside the field), wall table,
-  // touch counters.  Every env leaves the maps empty again (it un-writes the cells it wrote).
-  for (int i = lane; i < CH; i += 32) {
-    const int xx = (i - PP) / PS - PP, yy = (i - PP) % PS;
-    const bool field = i >= PP && xx >= 0 && xx < G && yy < G;
-    S.map[0][i] = (MapT)(field ? 0 : p.wall_idx);
-    S.map[1][i] = 0;
-    S.map[2][i] = 0;
-    S.scr[i] = 0;
-  }
-  for (int i = lane; i <= p.wall_idx; i += 32) S.wt[i] = i == p.wall_idx ? 1.f : 0.f;
+  // one-time set-up of this warp's slice: empty maps (predator map: WALL outside the field), zeroed touch
+  // counters, wall table — copied from the image ppg_create built.  Every env leaves the maps empty again
+  // (it un-writes the cells it wrote).
+  for (int i = lane; i < p.init_bytes / 16; i += 32)
+    reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
   unsigned rowctr = 0;
   const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
   const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
@@ -508,42 +543,42 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       // load the lists; list order = action-dict order (default: row order of the previous output)
       unsigned bad = 0;
       bool resort[2] = {false, false};
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         const size_t b = (size_t)env * p.cap[s];
         const int32_t* ordp = p.order[s];
         bool use_order = ordp != nullptr;
         if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to row order
           bool ok = true;
-          for (int i = lane; i < n[s]; i += 32) {
+          for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
-            if ((unsigned)d < (unsigned)n[s]) S.rnk[s][d] = (uint16_t)i; else ok = false;
+            if ((unsigned)d < (unsigned)SEL(n)) SEL(S.rnk)[d] = (uint16_t)i; else ok = false;
           }
           __syncwarp();
-          for (int i = lane; i < n[s]; i += 32) {
+          for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
-            if ((unsigned)d < (unsigned)n[s]) ok &= S.rnk[s][d] == (uint16_t)i;
+            if ((unsigned)d < (unsigned)SEL(n)) ok &= SEL(S.rnk)[d] == (uint16_t)i;
           }
           use_order = __all_sync(FULL, ok);
           if (!use_order) bad = PPG_STATUS_BAD_ACTION;
           __syncwarp();
         }
-        resort[s] = use_order;
-        for (int i = lane; i < n[s]; i += 32) {
+        if (s == 0) resort[0] = use_order; else resort[1] = use_order;
+        for (int i = lane; i < SEL(n); i += 32) {
           const int prow = p.ag_prow[s][b + i];
           const int d = use_order ? ordp[prow] : i;
           const double e = p.ag_e[s][b + i];
           int a = p.actions[s][prow];
           if ((unsigned)a > 8u) { a = 4; bad = PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
-          S.id[s][d] = p.ag_id[s][b + i];
-          S.pos[s][d] = p.ag_pos[s][b + i];
-          if (dense) S.E0[s][d] = e;  // energy_before (ADD:256)
-          S.E[s][d] = e - p.loss[s];  // Step 1 (BASE:244-250)
-          S.act[s][d] = (uint8_t)a;
-          S.flg[s][d] = F_ALIVE;
-          S.ord[s][d] = (uint16_t)d;
-          S.rnk[s][d] = (uint16_t)d;
-          if (kick) { S.par[s][d] = p.ag_par[s][b + i]; S.aux[s][d] = 0; }
+          SEL(S.id)[d] = p.ag_id[s][b + i];
+          SEL(S.pos)[d] = p.ag_pos[s][b + i];
+          if (dense) SEL(S.E0)[d] = e;  // energy_before (ADD:256)
+          SEL(S.E)[d] = e - p.loss[s];  // Step 1 (BASE:244-250)
+          SEL(S.act)[d] = (uint8_t)a;
+          SEL(S.flg)[d] = F_ALIVE;
+          SEL(S.ord)[d] = (uint16_t)d;
+          SEL(S.rnk)[d] = (uint16_t)d;
+          if (kick) { SEL(S.par)[d] = p.ag_par[s][b + i]; SEL(S.aux)[d] = 0; }
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
@@ -558,34 +593,34 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       __syncwarp();
       // owner maps as the grid stands after Step 1: of agents sharing a cell the one latest in dict
       // order wrote last (BASE:247,250)
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s)
-        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
           const int i = b0 + lane;
-          const bool v = i < n[s];
+          const bool v = i < SEL(n);
           int cell = 0;
-          if (v) { cell = CELLP((unsigned)S.pos[s][i]); S.map[s][cell] = (MapT)(i + 1); }
+          if (v) { cell = CELLP((unsigned)SEL(S.pos)[i]); SEL(S.map)[cell] = (MapT)(i + 1); }
           __syncwarp();
-          bool need = v && S.map[s][cell] < (unsigned)(i + 1);
+          bool need = v && SEL(S.map)[cell] < (unsigned)(i + 1);
           while (__any_sync(FULL, need)) {
-            if (need) S.map[s][cell] = (MapT)(i + 1);
+            if (need) SEL(S.map)[cell] = (MapT)(i + 1);
             __syncwarp();
-            need = v && S.map[s][cell] < (unsigned)(i + 1);
+            need = v && SEL(S.map)[cell] < (unsigned)(i + 1);
           }
         }
       __syncwarp();
 
       // Step 2: movements, sequential semantics in dict order per species (BASE:259-273,495-509)  // PHASE: movement
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        MapT* own = S.map[s];
-        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+        MapT* own = SEL(S.map);
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
           const int j = b0 + lane;
-          const bool v = j < n[s];
+          const bool v = j < SEL(n);
           int oc = 0, tc = 0, nx0 = 0, ny0 = 0;
           if (v) {
-            const unsigned ps = S.pos[s][j];
-            const int a = S.act[s][j];
+            const unsigned ps = SEL(S.pos)[j];
+            const int a = SEL(S.act)[j];
             const int x = ps >> 8, y = ps & 255;
             const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
             nx0 = min(max(x + ax - 1, 0), G - 1); ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
@@ -600,29 +635,29 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           if (v && !dirty) {
             // nobody else in this chunk touches my cells: the outcome does not depend on the order
             const unsigned ow = own[tc];
-            const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;  // own-species channel occupied (BASE:506)
+            const bool blocked = ow != 0 && SEL(S.E)[ow - 1] > 0.0;  // own-species channel occupied (BASE:506)
             const int nc = blocked ? oc : tc;
             own[oc] = 0;               // BASE:268,272
             own[nc] = (MapT)(j + 1);   // BASE:269,273
-            if (!blocked) S.pos[s][j] = (uint16_t)((nx0 << 8) | ny0);
+            if (!blocked) SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
           }
           __syncwarp();
           unsigned dm = __ballot_sync(FULL, dirty);
           while (dm) {  // warp-uniform replay, in dict order, of the agents that may interact
             const int jj = b0 + __ffs(dm) - 1;
             dm &= dm - 1;
-            const unsigned ps = S.pos[s][jj];
-            const int a = S.act[s][jj];
+            const unsigned ps = SEL(S.pos)[jj];
+            const int a = SEL(S.act)[jj];
             const int xx = ps >> 8, yy = ps & 255;
             const int ax = (a * 11) >> 5;
             const int tx = min(max(xx + ax - 1, 0), G - 1), ty = min(max(yy + (a - 3 * ax) - 1, 0), G - 1);
             const unsigned ow = own[CELLXY(tx, ty)];
-            const bool blocked = ow != 0 && S.E[s][ow - 1] > 0.0;
+            const bool blocked = ow != 0 && SEL(S.E)[ow - 1] > 0.0;
             const int nx = blocked ? xx : tx, ny = blocked ? yy : ty;
             __syncwarp();
             own[CELLXY(xx, yy)] = 0;
             own[CELLXY(nx, ny)] = (MapT)(jj + 1);
-            S.pos[s][jj] = (uint16_t)((nx << 8) | ny);
+            SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
             __syncwarp();
           }
         }
@@ -630,22 +665,22 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
 
       // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order.  The list is  // PHASE: sort
       // the sorted survivors followed by last step's newborns, so only the newborns have to be ranked in.
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        if (resort[s] || (h.sortflag & (1 << s))) {
+        if (SEL(resort) || (h.sortflag & (1 << s))) {
           const uint16_t* lr = p.lexrank[s];
           const bool by_id = h.first_step != 0;  // right after reset() self.agents is in numeric order (BASE:143-145)
-          const int ns = resort[s] ? 0 : min((int)h.n_sorted[s], n[s]);
-          for (int i = lane; i < n[s]; i += 32) S.ord[s][i] = by_id ? S.id[s][i] : __ldg(lr + S.id[s][i]);
+          const int ns = SEL(resort) ? 0 : min((int)(s == 0 ? h.n_sorted[0] : h.n_sorted[1]), SEL(n));
+          for (int i = lane; i < SEL(n); i += 32) SEL(S.ord)[i] = by_id ? SEL(S.id)[i] : __ldg(lr + SEL(S.id)[i]);
           __syncwarp();
-          for (int i = lane; i < n[s]; i += 32) {
-            const unsigned key = S.ord[s][i];
+          for (int i = lane; i < SEL(n); i += 32) {
+            const unsigned key = SEL(S.ord)[i];
             int r = i < ns ? i : 0;
-            for (int k = (i < ns ? ns : 0); k < n[s]; ++k) r += S.ord[s][k] < key;
-            S.rnk[s][i] = (uint16_t)r;
+            for (int k = (i < ns ? ns : 0); k < SEL(n); ++k) r += SEL(S.ord)[k] < key;
+            SEL(S.rnk)[i] = (uint16_t)r;
           }
           __syncwarp();
-          for (int i = lane; i < n[s]; i += 32) S.ord[s][S.rnk[s][i]] = (uint16_t)i;
+          for (int i = lane; i < SEL(n); i += 32) SEL(S.ord)[SEL(S.rnk)[i]] = (uint16_t)i;
           __syncwarp();
         }
       }
@@ -669,7 +704,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           const int cell = CELLP(ps);
           double e = S.E[0][slot];
           if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
-            rowctr = emit_row_now<MapT>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, n[0], n[1], rowctr, lane);
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, n[0], n[1], rowctr, lane);
             S.map[0][cell] = 0;  // BASE:293
             S.flg[0][slot] = F_DIED;
             st_starved[0]++;
@@ -689,7 +724,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
             S.map[0][cell] = (MapT)(slot + 1);  // BASE:325
             S.flg[0][slot] |= F_ATE;
             __syncwarp();
-            rowctr = emit_row_now<MapT>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, n[0], n[1], rowctr, lane);  // BASE:327
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, n[0], n[1], rowctr, lane);  // BASE:327
             S.map[1][cell] = 0;  // BASE:335
             S.flg[1][q] = F_DIED | F_CAUGHT;
             st_eaten++;
@@ -735,7 +770,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           const int cl = CELLP((unsigned)S.pos[1][sl]);
           const double ee = S.E[1][sl];
           if (ee <= 0.0) {  // BASE:284-301
-            rowctr = emit_row_now<MapT>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, n[0], n[1], rowctr, lane);
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, n[0], n[1], rowctr, lane);
             S.map[1][cl] = 0;
             S.flg[1][sl] = F_DIED;
             st_starved[1]++;
@@ -758,24 +793,24 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       __syncwarp();
 
       // Step 5: births in engagement order, predators then prey (BASE:389-448)  // PHASE: births
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        for (int b0 = 0; b0 < n[s]; b0 += 32) {
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
           const int k = b0 + lane;
           int slot = 0;
           bool elig = false;
-          if (k < n[s]) {
-            slot = S.ord[s][k];
-            elig = (S.flg[s][slot] & F_ALIVE) && S.E[s][slot] >= p.thr[s];
+          if (k < SEL(n)) {
+            slot = SEL(S.ord)[k];
+            elig = (SEL(S.flg)[slot] & F_ALIVE) && SEL(S.E)[slot] >= p.thr[s];
           }
           unsigned m = __ballot_sync(FULL, elig);
           while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
             const int ps_slot = __shfl_sync(FULL, slot, l);
-            if (h.next_idx[s] >= p.n_possible[s]) continue;  // id pool empty (BASE:395,424)
-            if (n[s] + births[s] >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
-            const unsigned pp = S.pos[s][ps_slot];
+            if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) continue;  // id pool empty (BASE:395,424)
+            if (SEL(n) + SEL(births) >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
+            const unsigned pp = SEL(S.pos)[ps_slot];
             const int px = pp >> 8, py = pp & 255;
             int nl[2] = {n[0] + births[0], n[1] + births[1]};
             // _find_available_spawn_position (BASE:738-766)
@@ -802,34 +837,34 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
               }
               if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises here
             }
-            const int cs = n[s] + births[s];
-            births[s]++;
-            const int child_id = h.next_idx[s]++;  // BASE:396-397
-            const double pe = S.E[s][ps_slot] - p.init_e[s];  // BASE:404
+            const int cs = SEL(n) + SEL(births);
+            if (s == 0) births[0]++; else births[1]++;
+            const int child_id = s == 0 ? h.next_idx[0]++ : h.next_idx[1]++;  // BASE:396-397
+            const double pe = SEL(S.E)[ps_slot] - p.init_e[s];  // BASE:404
             __syncwarp();
-            S.id[s][cs] = (uint16_t)child_id;
-            S.pos[s][cs] = (uint16_t)((sx << 8) | sy);
-            S.E[s][cs] = p.init_e[s];  // BASE:403
-            S.flg[s][cs] = F_ALIVE | F_NEWBORN;
-            S.E[s][ps_slot] = pe;
-            S.map[s][CELLXY(sx, sy)] = (MapT)(cs + 1);       // BASE:405
-            S.map[s][CELLXY(px, py)] = (MapT)(ps_slot + 1);  // BASE:406
-            S.flg[s][ps_slot] |= F_REPRO;
+            SEL(S.id)[cs] = (uint16_t)child_id;
+            SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
+            SEL(S.E)[cs] = p.init_e[s];  // BASE:403
+            SEL(S.flg)[cs] = F_ALIVE | F_NEWBORN;
+            SEL(S.E)[ps_slot] = pe;
+            SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // BASE:405
+            SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // BASE:406
+            SEL(S.flg)[ps_slot] |= F_REPRO;
             if (kick) {  // KICK:434-449
-              S.aux[s][cs] = 0;
-              S.par[s][cs] = S.id[s][ps_slot];
-              S.aux[s][ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
-              const unsigned gp = S.par[s][ps_slot];
+              SEL(S.aux)[cs] = 0;
+              SEL(S.par)[cs] = SEL(S.id)[ps_slot];
+              SEL(S.aux)[ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
+              const unsigned gp = SEL(S.par)[ps_slot];
               __syncwarp();
               if (gp != 0xFFFFu) {
                 int gs = -1;
-                for (int i = lane; i < n[s] + births[s]; i += 32)
-                  if ((S.flg[s][i] & F_ALIVE) && S.id[s][i] == gp) gs = i;
+                for (int i = lane; i < SEL(n) + SEL(births); i += 32)
+                  if ((SEL(S.flg)[i] & F_ALIVE) && SEL(S.id)[i] == gp) gs = i;
                 gs = __reduce_max_sync(FULL, gs);
                 if (gs >= 0) {
-                  const uint8_t cnt = S.aux[s][gs];
+                  const uint8_t cnt = SEL(S.aux)[gs];
                   __syncwarp();
-                  S.aux[s][gs] = (uint8_t)(cnt + 1);
+                  SEL(S.aux)[gs] = (uint8_t)(cnt + 1);
                 }
               }
             }
@@ -946,12 +981,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         new_base[0] = n_old_total[0] + nb0;
         new_base[1] = n_old_total[1] + nb1;
       }
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         const size_t sb = (size_t)env * p.cap[s];
         float* obs_s = p.obs[s];
         const int elems = p.elems[s];
-        const int k_lo = pass == 0 ? 0 : n[s], tot = pass == 0 ? n[s] : n[s] + births[s];
+        const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
         if (k_lo >= tot) continue;
         const RowRel rr = load_rel(p, s, lane);
         for (int b0 = k_lo; b0 < tot; b0 += 32) {
@@ -959,15 +994,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           int row = 0, slot = 0, cellp = 0;
           bool alive = false;
           if (k < tot) {
-            const bool newborn = k >= n[s];
-            slot = newborn ? k : S.ord[s][k];
-            row = newborn ? new_base[s] + (k - n[s]) : old_base[s] + k;
-            const unsigned f = S.flg[s][slot];
-            const double e = S.E[s][slot];
+            const bool newborn = k >= SEL(n);
+            slot = newborn ? k : SEL(S.ord)[k];
+            row = newborn ? SEL(new_base) + (k - SEL(n)) : SEL(old_base) + k;
+            const unsigned f = SEL(S.flg)[slot];
+            const double e = SEL(S.E)[slot];
             double rew = 0.0;
             if (mode == 2 && !newborn) {
               if (dense) {
-                const double e0 = S.E0[s][slot];
+                const double e0 = SEL(S.E0)[slot];
                 if (f & F_DIED) rew = (f & F_CAUGHT) ? (0.0 - e0) : (e - e0);  // ADD:308,346
                 else rew = (e - e0) + ((mode_r == PPG_REWARD_DENSE_ADDITIVE && (f & F_REPRO)) ? p.r_repro[s] : 0.0);  // ADD:468-471
               } else {
@@ -975,7 +1010,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
                 else {
                   rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);  // BASE:322,341,365,375
                   if (f & F_REPRO) rew = p.r_repro[s];  // BASE:409,438 overwrites
-                  if (kick) for (int q = S.aux[s][slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
+                  if (kick) for (int q = SEL(S.aux)[slot]; q > 0; --q) rew += p.r_kick[s];  // KICK:446
                 }
               }
             }
@@ -986,31 +1021,31 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
             if (mode == 1) rf |= PPG_ROW_FOUNDER;
             if (f & F_ATE) rf |= PPG_ROW_ATE;
             p.row_env[s][row] = env;
-            p.row_agent[s][row] = S.id[s][slot];
+            p.row_agent[s][row] = SEL(S.id)[slot];
             p.reward[s][row] = (float)rew;
             p.flags[s][row] = (uint8_t)rf;
             alive = (f & F_ALIVE) != 0;
-            const unsigned apos = S.pos[s][slot];
+            const unsigned apos = SEL(S.pos)[slot];
             cellp = CELLP(apos);
           }
           unsigned m = __ballot_sync(FULL, alive);
           // survivors in engagement order (= `self.agents` after the sort), then newborns (BASE:398,468)
           if (keep && alive) {
-            const int dst = wpos[s] + __popc(m & lt_mask);
-            p.ag_id[s][sb + dst] = S.id[s][slot];
-            p.ag_pos[s][sb + dst] = S.pos[s][slot];
-            p.ag_e[s][sb + dst] = S.E[s][slot];
+            const int dst = SEL(wpos) + __popc(m & lt_mask);
+            p.ag_id[s][sb + dst] = SEL(S.id)[slot];
+            p.ag_pos[s][sb + dst] = SEL(S.pos)[slot];
+            p.ag_e[s][sb + dst] = SEL(S.E)[slot];
             p.ag_prow[s][sb + dst] = row;
-            if (kick) p.ag_par[s][sb + dst] = S.par[s][slot];
+            if (kick) p.ag_par[s][sb + dst] = SEL(S.par)[slot];
           }
-          wpos[s] += __popc(m);
+          if (s == 0) wpos[0] += __popc(m); else wpos[1] += __popc(m);
           // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
           while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
             const int cp = __shfl_sync(FULL, cellp, l);
             const int r = __shfl_sync(FULL, row, l);
-            emit_row<MapT>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane);
+            emit_row<MapT, BULK>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane);
           }
         }
       }
@@ -1229,43 +1264,47 @@ __global__ void ppg_stats_kernel(const uint32_t* __restrict__ counters, const En
 // ------------------------------------------------------------------------------------------------
 // launch wrappers used by ppg_api.cu
 // ------------------------------------------------------------------------------------------------
-template <int W, typename MapT>
+template <int W, typename MapT, bool BULK>
 static cudaError_t launch_w(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;  // opt in to > 48 KB of dynamic shared memory (grows monotonically)
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_base_kernel<W, MapT><<<n_cta, W * 32, smem, stream>>>(p);
+  ppg_step_base_kernel<W, MapT, BULK><<<n_cta, W * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream) {
-  const bool m8 = p.map_bytes == 1;
-  switch (warps_per_cta) {
-    case 1: return m8 ? launch_w<1, uint8_t>(p, n_cta, smem, stream) : launch_w<1, uint16_t>(p, n_cta, smem, stream);
-    case 2: return m8 ? launch_w<2, uint8_t>(p, n_cta, smem, stream) : launch_w<2, uint16_t>(p, n_cta, smem, stream);
-    case 4: return m8 ? launch_w<4, uint8_t>(p, n_cta, smem, stream) : launch_w<4, uint16_t>(p, n_cta, smem, stream);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-template <int W, typename MapT>
+template <int W, typename MapT, bool BULK>
 static cudaError_t occupancy_w(size_t smem, int* blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W, MapT>, W * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W, MapT, BULK>, W * 32, smem);
 }
 
-cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, size_t smem, int* blocks_per_sm) {
-  const bool m8 = map_bytes == 1;
-  switch (warps_per_cta) {
-    case 1: return m8 ? occupancy_w<1, uint8_t>(smem, blocks_per_sm) : occupancy_w<1, uint16_t>(smem, blocks_per_sm);
-    case 2: return m8 ? occupancy_w<2, uint8_t>(smem, blocks_per_sm) : occupancy_w<2, uint16_t>(smem, blocks_per_sm);
-    case 4: return m8 ? occupancy_w<4, uint8_t>(smem, blocks_per_sm) : occupancy_w<4, uint16_t>(smem, blocks_per_sm);
-    default: return cudaErrorInvalidValue;
-  }
+#define PPG_DISPATCH(FN, ...)                                                                     \
+  do {                                                                                            \
+    const bool m8 = map_bytes == 1;                                                               \
+    if (warps_per_cta == 1) {                                                                     \
+      if (bulk) return m8 ? FN<1, uint8_t, true>(__VA_ARGS__) : FN<1, uint16_t, true>(__VA_ARGS__); \
+      return m8 ? FN<1, uint8_t, false>(__VA_ARGS__) : FN<1, uint16_t, false>(__VA_ARGS__);       \
+    }                                                                                             \
+    if (warps_per_cta == 4) {                                                                     \
+      if (bulk) return m8 ? FN<4, uint8_t, true>(__VA_ARGS__) : FN<4, uint16_t, true>(__VA_ARGS__); \
+      return m8 ? FN<4, uint8_t, false>(__VA_ARGS__) : FN<4, uint16_t, false>(__VA_ARGS__);       \
+    }                                                                                             \
+    return cudaErrorInvalidValue;                                                                 \
+  } while (0)
+
+cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream) {
+  const int map_bytes = p.map_bytes;
+  const bool bulk = p.obs_bulk != 0;
+  PPG_DISPATCH(launch_w, p, n_cta, smem, stream);
+}
+
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, size_t smem, int* blocks_per_sm) {
+  PPG_DISPATCH(occupancy_w, smem, blocks_per_sm);
 }
 
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,

@@ -112,7 +112,13 @@ struct StepParams {
   int P, PS, CH;        // halo width, row stride, entries per map:  index(x, y) = P + (x + P) * PS + y
   int map_bytes;        // sizeof(map entry): 1 (all capacities <= 253) or 2
   int wall_idx;         // value the predator map holds outside the field (index of the 1.0 entry of the wall table)
-  int nj[2];            // gather iterations per species = ceil(elems / 32)
+  int nj[2];            // per-lane elements of a row per species (see obs_vec)
+  int obs_vec[2];       // 1: lane owns float4 groups (row length % 4 == 0, nj = 4 * ceil(elems / 128)); 0: lane owns
+                        //    elements lane + 32 j (nj = ceil(elems / 32))
+  int emit_kind[2];     // specialised row writer: 1 = (4,7,7), 2 = (4,9,9), 3 = (5,9,9), 0 = generic
+  int obs_bulk;         // 1: rows leave through shared-memory staging + cp.async.bulk; 0: direct streaming stores
+  const void* init_image;  // [init_bytes] initial contents of the maps / touch counters / wall table of a warp's slice
+  int init_bytes;
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
                         //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };
