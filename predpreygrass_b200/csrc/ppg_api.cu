@@ -178,6 +178,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   const bool dense = c.reward_mode == PPG_REWARD_DENSE || c.reward_mode == PPG_REWARD_DENSE_ADDITIVE;
   const bool kick = c.reward_mode == PPG_REWARD_SPARSE_KICKBACK;
 
+  P.obs_bulk = 0;
+  if (const char* ev = getenv("PPG_OBS_BULK")) P.obs_bulk = atoi(ev) != 0;
   // padded map geometry (ppg_base.cu): halo as wide as the largest observation window
   P.P = std::max(P.off[0], P.off[1]);
   P.PS = G + P.P;
@@ -189,8 +191,6 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.nj[s] = P.obs_vec[s] ? 4 * ((P.elems[s] / 4 + 31) / 32) : (P.elems[s] + 31) / 32;
     P.emit_kind[s] = (P.obs_vec[s] && P.nj[s] == 8) ? 1 : (P.obs_vec[s] && P.nj[s] == 12) ? 2 : (!P.obs_vec[s] && P.nj[s] == 13) ? 3 : 0;
   }
-  P.obs_bulk = 0;
-  if (const char* ev = getenv("PPG_OBS_BULK")) P.obs_bulk = atoi(ev) != 0;
   if (P.nj[0] > PPG_MAX_NJ || P.nj[1] > PPG_MAX_NJ) { h->err = "observation row too large for this build"; return fail(PPG_ERR_INVALID); }
 
   // shared-memory layout of one env (see EnvSmem in ppg_base.cu)
@@ -203,9 +203,11 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
   P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
   P.so_vt[2] = take(4 * (size_t)(P.n_grass + 1), 4);
-  P.so_stage = take(2 * 4 * (size_t)P.stage_elems, 16);
-  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass + GG) * 4 > (size_t)(P.so_stage + 8 * P.stage_elems - P.so_vt[0])) {
-    h->err = "internal: reset scratch does not fit the table/staging area"; return fail(PPG_ERR_INVALID);
+  P.so_stage = take(P.obs_bulk ? 2 * 4 * (size_t)P.stage_elems : 0, 16);  // row staging only for the bulk-copy writer
+  // reset() stages its n_total cells in the value tables and a GG-entry claim table over the energy arrays
+  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4 > (size_t)(P.so_stage - P.so_vt[0]) ||
+      (size_t)GG * 4 > (size_t)(P.so_vt[0] - P.so_E[0])) {
+    h->err = "internal: reset scratch does not fit (cap_live too small for this grid)"; return fail(PPG_ERR_INVALID);
   }
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
@@ -269,7 +271,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   }
   int W = 1;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
-  if (W != 1 && W != 4) W = 1;
+  if (W != 1 && W != 4 && W != 8) W = 1;
   while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
@@ -390,7 +392,9 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   P.order[0] = o0; P.order[1] = o1;
   // every launch draws B tickets plus one terminating draw per warp
   P.ticket_base = h->ticket_next;
-  h->ticket_next += (unsigned long long)h->B + (unsigned long long)h->n_cta * h->warps_per_cta;
+  // tickets: one per env (W == 1) or per group of W envs, plus one terminating draw per warp / CTA
+  h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
+                                          : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
   CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
   h->launches_step++;

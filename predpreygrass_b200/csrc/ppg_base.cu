@@ -133,18 +133,18 @@ __device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long
 // ------------------------------------------------------------------------------------------------
 // per-lane gather constants of one species (obs_rel table of the host)
 struct RowRel {
-  int relb[PPG_MAX_NJ];  // byte offset of the map entry from the agent's own map-0 entry
-  int tbl[PPG_MAX_NJ];   // byte offset of the value table inside the env's shared-memory slice
+  int relb[PPG_MAX_NJ];      // byte offset of the map entry from the agent's own map-0 entry
+  unsigned tbl[PPG_MAX_NJ];  // shared address of the value table
 };
 
-__device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, int lane) {
+__device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, unsigned sb32, int lane) {
   RowRel r;
 #pragma unroll
   for (int j = 0; j < PPG_MAX_NJ; ++j) {
     r.relb[j] = 0; r.tbl[j] = 0;
     if (j < p.nj[s]) {
       const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
-      r.relb[j] = v.x; r.tbl[j] = v.y;  // lanes past the end of the row (last iteration only) get a harmless in-range pair
+      r.relb[j] = v.x; r.tbl[j] = sb32 + (unsigned)v.y;  // lanes past the end of the row (last iteration only) get a harmless in-range pair
     }
   }
   return r;
@@ -203,7 +203,7 @@ __device__ __forceinline__ void emit_row_t(const StepParams& p, unsigned sb32, f
 #pragma unroll
   for (int j = 0; j < N; ++j) idx[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
 #pragma unroll
-  for (int j = 0; j < N; ++j) val[j] = lds_f32(sb32 + (unsigned)r.tbl[j] + 4u * idx[j]);
+  for (int j = 0; j < N; ++j) val[j] = lds_f32(r.tbl[j] + 4u * idx[j]);
   const int elems = p.elems[s];
   if (BULK) {
     const unsigned buf = sb32 + (unsigned)p.so_stage + (rowctr & 1u) * (unsigned)(p.stage_elems * 4);
@@ -292,8 +292,9 @@ __device__ __noinline__ unsigned emit_row_now(unsigned char* base, const StepPar
                                               unsigned rowctr, int lane) {
   const EnvSmem<MapT> S = carve<MapT>(base, p);
   refresh_tables(S, p, nt0, nt1, lane);
-  const RowRel r = load_rel(p, s, lane);
-  emit_row<MapT, BULK>(p, (unsigned)__cvta_generic_to_shared(base), dst, cellp, s, r, rowctr, lane);
+  const unsigned sb32 = (unsigned)__cvta_generic_to_shared(base);
+  const RowRel r = load_rel(p, s, sb32, lane);
+  emit_row<MapT, BULK>(p, sb32, dst, cellp, s, r, rowctr, lane);
   return rowctr;
 }
 
@@ -428,6 +429,7 @@ __device__ __noinline__ int philox_free_cell(unsigned char* base, const StepPara
 template <int W, typename MapT, bool BULK>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
@@ -452,9 +454,21 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
 
   for (;;) {
     int env = 0;  // PHASE: ticket+hdr
-    if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-    env = __shfl_sync(FULL, env, 0);
-    if (env >= p.B) break;
+    if (W == 1) {
+      if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      env = __shfl_sync(FULL, env, 0);
+      if (env >= p.B) break;
+    } else {
+      // the W warps of a CTA take W consecutive envs and start them together: warps of one CTA then run the
+      // same code at about the same time, which keeps the instruction cache warm (the kernel is far larger
+      // than the cache and every env walks through most of it once)
+      __syncthreads();
+      if (threadIdx.x == 0) s_env0 = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base) * W;
+      __syncthreads();
+      if (s_env0 >= p.B) break;
+      env = s_env0 + warp;
+      if (env >= p.B) continue;
+    }
 
     // per-env registers (warp-uniform)
     int n[2] = {0, 0};  // list length at step start (= old rows)
@@ -485,12 +499,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       h.sortflag = 0;
       h.first_step = 1;
       h.state = 0;
-      if (lane == 0) bulk_wait_read<0>();  // the scratch below aliases the value tables and the row staging buffers
-      __syncwarp();
       const int n_total = p.n_init[0] + p.n_init[1] + p.n_grass;
       // cells in the order predators, prey, grass (BASE:185-187)
-      int* cells = reinterpret_cast<int*>(S.vt[0]);                    // [n_total]
-      unsigned* first = reinterpret_cast<unsigned*>(S.vt[0]) + n_total;  // [GG] draw index that claimed the cell
+      int* cells = reinterpret_cast<int*>(S.vt[0]);          // [n_total], in the value tables (rebuilt before every use)
+      unsigned* first = reinterpret_cast<unsigned*>(S.E[0]);  // [GG] draw index that claimed the cell; dead before E is written
       bool from_tape = false;
       if (p.tape_cells != nullptr) {
         if (h.tape_pos + n_total <= h.tape_end) {
@@ -988,7 +1000,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         const int elems = p.elems[s];
         const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
         if (k_lo >= tot) continue;
-        const RowRel rr = load_rel(p, s, lane);
+        const RowRel rr = load_rel(p, s, sb32, lane);
         for (int b0 = k_lo; b0 < tot; b0 += 32) {
           const int k = b0 + lane;
           int row = 0, slot = 0, cellp = 0;
@@ -1293,6 +1305,10 @@ static cudaError_t occupancy_w(size_t smem, int* blocks_per_sm) {
     if (warps_per_cta == 4) {                                                                     \
       if (bulk) return m8 ? FN<4, uint8_t, true>(__VA_ARGS__) : FN<4, uint16_t, true>(__VA_ARGS__); \
       return m8 ? FN<4, uint8_t, false>(__VA_ARGS__) : FN<4, uint16_t, false>(__VA_ARGS__);       \
+    }                                                                                             \
+    if (warps_per_cta == 8) {                                                                     \
+      if (bulk) return m8 ? FN<8, uint8_t, true>(__VA_ARGS__) : FN<8, uint16_t, true>(__VA_ARGS__); \
+      return m8 ? FN<8, uint8_t, false>(__VA_ARGS__) : FN<8, uint16_t, false>(__VA_ARGS__);       \
     }                                                                                             \
     return cudaErrorInvalidValue;                                                                 \
   } while (0)
