@@ -156,7 +156,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), args.steps
 
-    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=1000 + rank)
+    # one Philox key for the whole job; env_index_base makes the trajectories independent of the sharding
+    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=1000, env_index_base=rank * args.envs)
     env = BatchedPredPreyGrass(cfg, args.envs, device=local_rank)
     env.reset()
 

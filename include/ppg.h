@@ -115,6 +115,10 @@ typedef struct ppg_config {
   double reproduction_reward[2]; /* "reproduction_reward_*" */
   double kickback_reward[2];     /* "kickback_reward_*" (plus_kickback variant only) */
   uint64_t seed;                 /* Philox key for normal (non-replay) runs */
+  int32_t env_index_base;        /* global index of this handle's env 0: the Philox streams are keyed by
+                                  * env_index_base + env, so a job sharded over several handles / GPUs
+                                  * produces the same trajectories as one handle owning all envs */
+  int32_t reserved0;
 } ppg_config;
 
 /*

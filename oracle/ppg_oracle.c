@@ -269,7 +269,7 @@ static void env_reset_auto(env_t* e) {
     uint8_t* taken = (uint8_t*)calloc((size_t)ncell, 1);
     int n = 0;
     for (uint32_t idx = 0; n < n_total; ++idx) {
-      uint32_t cell = ppg_bounded(ppg_draw_u32(e->seed_key, (uint32_t)e->env_index, e->episode,
+      uint32_t cell = ppg_bounded(ppg_draw_u32(e->seed_key, (uint32_t)(e->env_index + e->c->env_index_base), e->episode,
                                                PPG_STREAM_PLACEMENT, idx), (uint32_t)ncell);
       if (!taken[cell]) { taken[cell] = 1; cells[n++] = (int32_t)cell; }
     }
@@ -318,7 +318,7 @@ static int find_spawn(env_t* e, int px, int py, int* ox, int* oy) {
   int n_free = 0;
   for (int cell = 0; cell < G * G; ++cell) n_free += !occupied_by_agent(e, cell / G, cell % G);
   if (n_free == 0) return 0;
-  uint32_t k = ppg_bounded(ppg_draw_u32(e->seed_key, (uint32_t)e->env_index, e->episode,
+  uint32_t k = ppg_bounded(ppg_draw_u32(e->seed_key, (uint32_t)(e->env_index + e->c->env_index_base), e->episode,
                                         PPG_STREAM_SPAWN, e->spawn_draws++), (uint32_t)n_free);
   for (int cell = 0; cell < G * G; ++cell)
     if (!occupied_by_agent(e, cell / G, cell % G)) {
@@ -813,7 +813,7 @@ int ppgo_random_actions(ppgo_batch* b, uint64_t seed, int32_t* actions_pred, int
   for (int s = 0; s < 2; ++s) {
     int32_t n = b->n_rows[s] + b->n_rows[2 + s];
     for (int32_t row = 0; row < n; ++row) {
-      uint32_t env = (uint32_t)b->out.f.row_env[s][row], id = (uint32_t)b->out.f.row_agent[s][row];
+      uint32_t env = (uint32_t)(b->out.f.row_env[s][row] + b->cfg.env_index_base), id = (uint32_t)b->out.f.row_agent[s][row];
       uint32_t r = ppg_draw_u32(seed, env, (uint32_t)b->calls, PPG_STREAM_ACTION + 8u * (uint32_t)s, id);
       act[s][row] = (int32_t)ppg_bounded(r, 9u);
     }

@@ -55,6 +55,8 @@ class PpgConfig(C.Structure):
         ("reproduction_reward", C.c_double * 2),
         ("kickback_reward", C.c_double * 2),
         ("seed", C.c_uint64),
+        ("env_index_base", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -92,7 +94,8 @@ def _round32(n):
     return max(32, (int(n) + 31) // 32 * 32)
 
 
-def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_live=None, autoreset=True, seed=0):
+def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_live=None, autoreset=True, seed=0,
+                env_index_base=0):
     """Flatten a reference `config_env` dict (missing keys take the reference's own defaults,
     BASE:22-61) into a PpgConfig."""
     cfg = dict(config or {})
@@ -136,6 +139,7 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.kickback_reward[0] = g("kickback_reward_predator", 10.0)
     c.kickback_reward[1] = g("kickback_reward_prey", 10.0)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.env_index_base = int(env_index_base)
     return c
 
 

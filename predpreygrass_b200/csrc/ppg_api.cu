@@ -22,7 +22,7 @@ cudaError_t launch_mark_reset(EnvHdr* hdr, int B, const unsigned long long* seed
 cudaError_t launch_set_tape(EnvHdr* hdr, int B, const long long* cell_off, cudaStream_t s);
 cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1,
                                   const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
-                                  unsigned n_actions, int blocks, cudaStream_t s);
+                                  unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s);
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s);
 }  // namespace ppg
 
@@ -163,7 +163,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   StepParams& P = h->P;
   memset(&P, 0, sizeof P);
   const int B = n_envs, G = c.grid_size, GG = G * G;
-  P.B = B; P.G = G; P.GG = GG; P.C = c.num_obs_channels;
+  P.B = B; P.G = G; P.GG = GG; P.C = c.num_obs_channels; P.env_base = c.env_index_base;
   for (int s = 0; s < 2; ++s) {
     P.R[s] = c.obs_range[s]; P.off[s] = (c.obs_range[s] - 1) / 2; P.elems[s] = c.num_obs_channels * c.obs_range[s] * c.obs_range[s];
     P.cap[s] = c.cap_live[s]; P.n_init[s] = c.n_initial[s]; P.n_possible[s] = c.n_possible[s];
@@ -491,7 +491,7 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
   CK(cudaSetDevice(h->device));
   const StepParams& P = h->P;
   CK(launch_random_actions(P.n_rows, P.row_env[0], P.row_agent[0], P.row_env[1], P.row_agent[1], actions_pred, actions_prey,
-                           seed, (unsigned)h->calls, 9u, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
+                           seed, (unsigned)h->calls, 9u, (unsigned)P.env_base, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
   h->launch_count++;
   return PPG_OK;
 }

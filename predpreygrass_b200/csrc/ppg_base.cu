@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           h.status |= PPG_STATUS_TAPE_EXHAUSTED;
         }
       }
-      if (!from_tape) philox_placement(cells, first, n_total, GG, (unsigned)env, h.episode, h.seed_key, lane);
+      if (!from_tape) philox_placement(cells, first, n_total, GG, (unsigned)(env + p.env_base), h.episode, h.seed_key, lane);
       __syncwarp();
       // founders: slots in numeric id order (BASE:143-145,190-200)
       {
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
                 if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
                 // uniformly random free cell, ascending cell order, Philox draw
                 const int c = philox_free_cell<MapT>(sbase, p, nl[0], nl[1],
-                                                     ppg_draw_u32(h.seed_key, (unsigned)env, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), lane);
+                                                     ppg_draw_u32(h.seed_key, (unsigned)(env + p.env_base), h.episode, PPG_STREAM_SPAWN, h.spawn_draws), lane);
                 if (c >= 0) { h.spawn_draws++; sx = c >> 8; sy = c & 255; }
               }
               if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises here
@@ -1243,12 +1243,12 @@ __global__ void ppg_set_tape_kernel(EnvHdr* hdr, int B, const long long* cell_of
 __global__ void ppg_random_actions_kernel(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ row_env0,
                                           const int32_t* __restrict__ row_agent0, const int32_t* __restrict__ row_env1,
                                           const int32_t* __restrict__ row_agent1, int32_t* act0, int32_t* act1,
-                                          unsigned long long seed, unsigned call, unsigned n_actions) {
+                                          unsigned long long seed, unsigned call, unsigned n_actions, unsigned env_base) {
   const int n0 = n_rows[0] + n_rows[2], n1 = n_rows[1] + n_rows[3];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const int s = i >= n0;
     const int row = s ? i - n0 : i;
-    const unsigned env = (unsigned)(s ? row_env1[row] : row_env0[row]);
+    const unsigned env = (unsigned)(s ? row_env1[row] : row_env0[row]) + env_base;
     const unsigned id = (unsigned)(s ? row_agent1[row] : row_agent0[row]);
     const unsigned r = ppg_draw_u32(seed, env, call, PPG_STREAM_ACTION + 8u * (unsigned)s, id);
     (s ? act1 : act0)[row] = (int32_t)ppg_bounded(r, n_actions);
@@ -1347,8 +1347,8 @@ cudaError_t launch_set_tape(EnvHdr* hdr, int B, const long long* cell_off, cudaS
 }
 cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1,
                                   const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
-                                  unsigned n_actions, int blocks, cudaStream_t s) {
-  ppg_random_actions_kernel<<<blocks, 256, 0, s>>>(n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, n_actions);
+                                  unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s) {
+  ppg_random_actions_kernel<<<blocks, 256, 0, s>>>(n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, n_actions, env_base);
   return cudaGetLastError();
 }
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s) {

@@ -54,6 +54,7 @@ enum : unsigned char {
 struct StepParams {
   // ---- config ----
   int B, G, GG, C;
+  int env_base;           // ppg_config.env_index_base
   int R[2], off[2], elems[2];
   int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
   double loss[2], thr[2], init_e[2], grass_cap, grass_gain;
