@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 2
+#define PPG_ABI_VERSION 3
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -64,6 +64,7 @@ enum {
 #define PPG_ROW_NEWBORN 0x04u    /* born this step (BASE:396-414) */
 #define PPG_ROW_FOUNDER 0x08u    /* row produced by reset(), not by step() (BASE:215) */
 #define PPG_ROW_ATE 0x10u        /* member of agents_just_ate (BASE:319,362) */
+#define PPG_ROW_CARCASS 0x20u    /* ECO: member of dead_prey after the step (bitten, not fully eaten; ECO:826-845) */
 
 /* per-env flag bits (ppg_buffers.env_flags), describe the step that just ran */
 #define PPG_ENV_TERMINATED 0x01u /* terminations["__all__"] (BASE:466) */
@@ -77,6 +78,9 @@ enum {
 #define PPG_STATUS_NO_SPAWN_CELL 0x02u  /* no free cell for a newborn (reference: TypeError, BASE:766) */
 #define PPG_STATUS_TAPE_EXHAUSTED 0x04u /* replay tape ran out; Philox stream used instead */
 #define PPG_STATUS_BAD_ACTION 0x08u     /* action outside the action space (reference: KeyError, BASE:502) */
+#define PPG_STATUS_ID_POOL_EMPTY 0x10u  /* ECO: id pool exhausted, birth suppressed (reference: SystemExit, ECO:1104-1111) */
+#define PPG_STATUS_GHOST_CELL 0x20u     /* ECO: a prey that aged out this step was bitten with a finite intake cap; the reference
+                                         * leaves a stale grid value behind (ECO:826-832 after :1060-1090), the device does not */
 
 /* error codes */
 #define PPG_OK 0
@@ -119,15 +123,38 @@ typedef struct ppg_config {
                                   * env_index_base + env, so a job sharded over several handles / GPUs
                                   * produces the same trajectories as one handle owning all envs */
   int32_t reserved0;
+  /* ---- ECO (eco_evolutionary/config/config_env_eco_evolutionary.py:1-88; ECO:36-120).  Ignored by the BASE family. ---- */
+  int32_t action_range;           /* "action_range" (ECO:102, 5 -> 25 actions `a -> (a // R - d, a % R - d)`, ECO:225-232); BASE: 3 */
+  int32_t genome_enabled;         /* "genome_enabled" (ECO:103) */
+  int32_t include_speed_in_obs;   /* "include_speed_in_obs" (ECO:112): one extra constant plane after the grid channels (ECO:707-711) */
+  int32_t max_agent_age[2];       /* "max_agent_age" per role, -1 = None = unlimited (ECO:51-63,1042-1058) */
+  int32_t carcass_only_predator_age; /* "carcass_only_predator_age"["predator"], -1 = None (ECO:65-72,1060-1090) */
+  int32_t slow_max_move_distance; /* ECO:110 */
+  int32_t fast_max_move_distance; /* ECO:111 */
+  int32_t reserved1[2];
+  double move_cost_per_cell[2];   /* "movement_energy_cost_per_cell_*" (ECO:78-79,565-573) */
+  double move_speed_cost_exponent;/* "movement_speed_cost_exponent" (ECO:80,559-563) */
+  double max_energy_grass;        /* "max_energy_grass": regrowth cap (ECO:83,618-626) */
+  double max_energy_gain_per_grass; /* intake caps, +inf = none (ECO:909-911, ECO:812-814) */
+  double max_energy_gain_per_prey;
+  double founder_speed_mean[2];   /* "founder_genome"[role]["speed_mean"/"speed_std"] (genome.py:42-46) */
+  double founder_speed_std[2];
+  double mutation_rate;           /* "genome_mutation"["rate"/"std"] (genome.py:49-59) */
+  double mutation_std;
+  double speed_bounds[2];         /* "trait_bounds"["speed"] (genome.py:37-39); also the observation normalisation (ECO:113-115) */
+  double speed_distance_threshold;/* ECO:109,551-557 */
 } ppg_config;
 
 /*
  * Replay tape: the random draws of the reference, captured from its numpy RNG, consumed by the
  * device in the reference's consumption order (SURVEY §8c "Tape contents").  Per env two
  * streams; env e owns cells[cell_off[e] .. cell_off[e+1]) and reals[real_off[e] .. real_off[e+1]).
- *   cells: BASE reset — n_initial[0]+n_initial[1]+n_grass cells `x*grid_size+y` in the order
- *          predators, prey, grass (BASE:185-187); then one cell per spawn fallback draw (BASE:764).
- *   reals: unused by BASE; ECO/STAG trait and capture draws.
+ *   cells: reset — n_initial[0]+n_initial[1]+n_grass cells `x*grid_size+y` in the order
+ *          predators, prey, grass (BASE:185-187; ECO:1752-1762); then one cell per spawn fallback
+ *          draw (BASE:764; ECO:759-762).
+ *   reals: unused by BASE.  ECO: per reset the founders' speeds in `self.agents` order (predators,
+ *          prey; genome.py:42-46, only if genome_enabled), then per birth `u = rng.random()` and,
+ *          iff u < mutation_rate, `delta = rng.normal(0, std)` (genome.py:56-58).
  * All pointers are HOST pointers; the call copies.  When a stream is exhausted the env sets
  * PPG_STATUS_TAPE_EXHAUSTED and continues on the Philox stream.
  */
@@ -241,6 +268,11 @@ int ppg_restore(ppg_handle h, const void* host_blob, size_t bytes, void* cuda_st
 int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, int32_t* xy_pred,
                  double* energy_pred, int32_t* ids_prey, int32_t* xy_prey, double* energy_prey,
                  int32_t* xy_grass, double* energy_grass);
+
+/* ECO extras of one env (ECO attributes agent_ages, agent_genomes[..].speed, dead_prey,
+ * active_num_predators/prey), in the list order of ppg_read_env.  Any pointer may be NULL. Synchronises. */
+int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
+                     double* speed_prey, uint8_t* dead_prey, int32_t* active_num);
 
 /* Device-side reduction of the per-env counters into PPG_N_STATS int64 values (host out).
  * Synchronises the stream. ppg_stats_device leaves them on the device for an NCCL all-reduce. */

@@ -21,7 +21,8 @@ class OracleBuffers(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(HERE, f) for f in ("ppg_oracle.c", "ppg_oracle.h")]
+    src = [os.path.join(HERE, f) for f in ("ppg_oracle.c", "ppg_oracle_eco.c", "ppg_oracle.h", "ppg_oracle_int.h", "Makefile")]
+    src += [os.path.join(HERE, "..", "include", f) for f in ("ppg.h", "ppg_philox.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB_PATH
@@ -50,6 +51,9 @@ def lib():
         L.ppgo_env_step_ordered.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_cells.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ppgo_env_agents.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ppgo_env_reset_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ppgo_set_pow_libm.argtypes = [C.c_void_p, C.c_int32]
+        L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -62,19 +66,29 @@ def _np(ptr, shape, dtype):
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
-def make_tape(cells_per_env):
-    """cells_per_env: list of int sequences -> (PpgTape, keepalive)"""
-    off = np.zeros(len(cells_per_env) + 1, np.int64)
-    for i, c in enumerate(cells_per_env):
+def _flatten(seqs, dtype):
+    off = np.zeros(len(seqs) + 1, np.int64)
+    for i, c in enumerate(seqs):
         off[i + 1] = off[i] + len(c)
-    flat = np.concatenate([np.asarray(c, np.int32) for c in cells_per_env]) if off[-1] else np.zeros(1, np.int32)
-    flat = np.ascontiguousarray(flat, np.int32)
+    flat = np.concatenate([np.asarray(c, dtype) for c in seqs]) if off[-1] else np.zeros(1, dtype)
+    return np.ascontiguousarray(flat, dtype), off
+
+
+def make_tape(cells_per_env, reals_per_env=None):
+    """cells_per_env / reals_per_env: lists of sequences -> (PpgTape, keepalive)"""
+    flat, off = _flatten(cells_per_env, np.int32)
     t = PpgTape()
     t.cells = flat.ctypes.data_as(C.POINTER(C.c_int32))
     t.cell_off = off.ctypes.data_as(C.POINTER(C.c_int64))
     t.reals = None
     t.real_off = None
-    return t, (flat, off)
+    keep = [flat, off]
+    if reals_per_env is not None:
+        rflat, roff = _flatten(reals_per_env, np.float64)
+        t.reals = rflat.ctypes.data_as(C.POINTER(C.c_double))
+        t.real_off = roff.ctypes.data_as(C.POINTER(C.c_int64))
+        keep += [rflat, roff]
+    return t, keep
 
 
 class Oracle:
@@ -86,7 +100,8 @@ class Oracle:
         if not self.h:
             raise ValueError("ppgo_create rejected the config")
         lib().ppgo_set_threads(self.h, threads)
-        self.C = cfg.num_obs_channels
+        self.C = cfg.num_obs_channels + (1 if cfg.variant == 1 and cfg.include_speed_in_obs else 0)
+        self.grid_C = cfg.num_obs_channels
         self.R = (cfg.obs_range[0], cfg.obs_range[1])
         self._keep = None
 
@@ -101,9 +116,31 @@ class Oracle:
         except Exception:
             pass
 
-    def load_tape(self, cells_per_env):
-        t, keep = make_tape(cells_per_env)
+    def load_tape(self, cells_per_env, reals_per_env=None):
+        t, keep = make_tape(cells_per_env, reals_per_env)
         lib().ppgo_load_tape(self.h, C.byref(t))
+
+    def set_pow_libm(self, on):
+        lib().ppgo_set_pow_libm(self.h, 1 if on else 0)
+
+    def env_reset_eco(self, env, cells, founder_speed):
+        c = np.ascontiguousarray(cells, np.int32)
+        sp = np.ascontiguousarray(founder_speed if len(founder_speed) else [0.0], np.float64)
+        assert lib().ppgo_env_reset_eco(self.h, env, c.ctypes.data, sp.ctypes.data) == 0
+        return self.outputs()
+
+    def read_env_eco(self, env):
+        st = self.read_env(env)
+        n = (len(st["ids"][0]), len(st["ids"][1]))
+        age = [np.zeros(max(1, n[s]), np.int32) for s in range(2)]
+        sp = [np.zeros(max(1, n[s]), np.float64) for s in range(2)]
+        dead = np.zeros(max(1, n[1]), np.uint8)
+        act = np.zeros(2, np.int32)
+        assert lib().ppgo_read_env_eco(self.h, env, age[0].ctypes.data, sp[0].ctypes.data, age[1].ctypes.data,
+                                       sp[1].ctypes.data, dead.ctypes.data, act.ctypes.data) == 0
+        st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]],
+                  active_num=act)
+        return st
 
     def reset(self, seeds=None, mask=None):
         s = None if seeds is None else np.ascontiguousarray(seeds, np.uint64)
@@ -174,7 +211,7 @@ class Oracle:
 
     def read_grid(self, env):
         G = self.cfg.grid_size
-        g = np.zeros((self.C, G, G), np.float64)
+        g = np.zeros((getattr(self, "grid_C", self.C), G, G), np.float64)
         lib().ppgo_read_grid(self.h, env, g.ctypes.data)
         return g
 

@@ -13,7 +13,7 @@
  * Pinned against golden trajectories recorded from the unmodified reference
  * (tests/golden/make_golden.py -> tests/golden/base_*.npz, tests/test_oracle_golden.py).
  */
-#include "ppg_oracle.h"
+#include "ppg_oracle_int.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -22,84 +22,6 @@
 #include <string.h>
 
 #include "../include/ppg_philox.h"
-
-#define KEY(s, id) (((int32_t)(s) << 16) | (int32_t)(id))
-#define KEY_S(k) ((k) >> 16)
-#define KEY_ID(k) ((k)&0xFFFF)
-
-/* ------------------------------------------------------------------------------------------ */
-/* one environment instance                                                                    */
-/* ------------------------------------------------------------------------------------------ */
-typedef struct env_t {
-  const ppg_config* c;
-  int G, C;
-  int env_index;
-  /* dicts keyed by agent id: agent_positions / agent_energies (BASE:111-117) */
-  uint8_t* present[2];
-  int16_t* x[2];
-  int16_t* y[2];
-  double* energy[2];
-  int32_t* parent[2]; /* KICK:86-91 agent_parent, -1 = none */
-  /* self.agents (BASE:73), self._pending_removal (BASE:65) */
-  int32_t* agents;
-  int n_agents;
-  int32_t* pending;
-  int n_pending;
-  int next_idx[2]; /* BASE:66-67 */
-  int cur_num[2];  /* BASE:210-211 */
-  int current_step;
-  double* grid; /* [C][G][G] BASE:123-124 */
-  int16_t* gx;
-  int16_t* gy;
-  double* ge; /* grass_positions / grass_energies */
-  /* per-call dicts: observations / rewards / terminations, keyed by list index of self.agents */
-  double* obs;     /* [cap_rows][max_row_elems] */
-  double* rew;     /* rewards[agent] */
-  int8_t* has_rew;
-  int8_t* term;    /* -1 missing, 0 False, 1 True */
-  int8_t* trunc;
-  int8_t* has_obs;
-  uint8_t* ate;    /* agents_just_ate */
-  uint8_t* newborn;
-  double* e_before; /* ADD:256 energy_before */
-  double* bonus;    /* ADD:261 reproduction_bonus */
-  int32_t* list_index[2]; /* id -> index in self.agents during the call */
-  int n_rows;      /* rows produced by the last call (= len(self.agents) at output time) */
-  int cap_rows;
-  int row_elems[2];
-  int max_row_elems;
-  uint8_t all_term, all_trunc; /* "__all__" */
-  uint8_t env_flags;
-  /* lockstep layer */
-  int needs_reset, idle;
-  uint8_t status;
-  uint64_t seed_key;
-  uint32_t episode, spawn_draws;
-  const int32_t* tape_cells;
-  int64_t tape_pos, tape_end;
-  int64_t stats[PPG_N_STATS];
-  /* lexicographic rank of str(id): Python sorts agent-id strings (BASE:468) */
-  const int32_t* lexrank[2];
-} env_t;
-
-struct ppgo_batch {
-  ppg_config cfg;
-  int n_envs;
-  env_t* envs;
-  int32_t* lexrank[2];
-  /* tape copy */
-  int32_t* tape_cells;
-  int64_t* tape_off;
-  int has_tape;
-  /* flat outputs */
-  ppgo_buffers out;
-  int64_t cap[2];
-  int32_t n_rows[4];
-  uint64_t calls;
-  int n_threads;
-  /* row -> (list position) bookkeeping of the previous output, for action lookup */
-  int32_t* prev_row[2]; /* [env][id] flattened lazily: per env arrays */
-};
 
 static int cmp_lex(const void* a, const void* b) {
   char sa[16], sb[16];
@@ -174,9 +96,12 @@ static void env_alloc(env_t* e, const ppg_config* c, int env_index, int32_t* con
   e->obs = NULL;
   e->seed_key = c->seed;
   e->idle = 1; /* not reset yet */
+  if (c->variant == PPG_VARIANT_ECO) eco_env_alloc(e);
 }
 
 static void env_free(env_t* e) {
+  if (e->c->variant == PPG_VARIANT_ECO) eco_env_free(e);
+  free(e->carcass); free(e->born_obs);
   for (int s = 0; s < 2; ++s) {
     free(e->present[s]); free(e->x[s]); free(e->y[s]); free(e->energy[s]); free(e->parent[s]);
     free(e->list_index[s]);
@@ -200,7 +125,11 @@ static void ensure_rows(env_t* e, int need) {
   e->newborn = (uint8_t*)realloc(e->newborn, n);
   e->e_before = (double*)realloc(e->e_before, n * sizeof(double));
   e->bonus = (double*)realloc(e->bonus, n * sizeof(double));
+  e->carcass = (uint8_t*)realloc(e->carcass, n);
+  e->born_obs = (uint8_t*)realloc(e->born_obs, n);
 }
+
+void eco_ensure_rows(env_t* e, int need) { ensure_rows(e, need); }
 
 static void clear_row(env_t* e, int i) {
   e->rew[i] = 0.0; e->has_rew[i] = 0; e->term[i] = -1; e->trunc[i] = -1; e->has_obs[i] = 0;
@@ -256,6 +185,7 @@ static void env_reset_cells(env_t* e, const int32_t* cells) {
 /* normal-mode placement: Philox rejection draws until enough unique cells (same law as BASE:156-177) */
 static void env_reset_auto(env_t* e) {
   const ppg_config* c = e->c;
+  if (c->variant == PPG_VARIANT_ECO) { eco_env_reset_auto(e); return; }
   const int n_total = c->n_initial[0] + c->n_initial[1] + c->n_grass;
   const int ncell = e->G * e->G;
   int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_total);
@@ -343,6 +273,7 @@ static int cmp_agents_lex(const void* a, const void* b, void* ctx) {
 static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, const int32_t* a_val,
                     int lockstep) {
   const ppg_config* c = e->c;
+  if (c->variant == PPG_VARIANT_ECO) return eco_env_step(e, n_act, a_s, a_id, a_val);
   const int mode = c->reward_mode;
   const int dense = (mode == PPG_REWARD_DENSE || mode == PPG_REWARD_DENSE_ADDITIVE);
   e->env_flags = 0;
@@ -567,6 +498,7 @@ static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id
 
 /* finish the call: self.agents.sort() (BASE:468), after the rows have been exported */
 static void env_sort_agents(env_t* e) {
+  if (e->c->variant == PPG_VARIANT_ECO) return; /* ECO never sorts self.agents */
   /* insertion sort keeps it dependency-free (qsort_r is a GNU extension) */
   for (int i = 1; i < e->n_agents; ++i) {
     int32_t k = e->agents[i];
@@ -581,7 +513,7 @@ static void env_sort_agents(env_t* e) {
 /* ------------------------------------------------------------------------------------------ */
 ppgo_batch* ppgo_create(const ppg_config* cfg, int32_t n_envs) {
   if (!cfg || cfg->struct_size != sizeof(ppg_config) || n_envs <= 0) return NULL;
-  if (cfg->variant != PPG_VARIANT_BASE) return NULL;
+  if (cfg->variant != PPG_VARIANT_BASE && cfg->variant != PPG_VARIANT_ECO) return NULL;
   if (cfg->n_initial[0] + cfg->n_initial[1] + cfg->n_grass > cfg->grid_size * cfg->grid_size) return NULL; /* BASE:167 */
   ppgo_batch* b = (ppgo_batch*)calloc(1, sizeof *b);
   b->cfg = *cfg;
@@ -594,7 +526,7 @@ ppgo_batch* ppgo_create(const ppg_config* cfg, int32_t n_envs) {
     int cap = cfg->cap_live[s] > 0 ? cfg->cap_live[s] : cfg->n_possible[s];
     b->cap[s] = (int64_t)n_envs * cap;
     size_t n = (size_t)b->cap[s];
-    int elems = cfg->num_obs_channels * cfg->obs_range[s] * cfg->obs_range[s];
+    int elems = (cfg->num_obs_channels + (cfg->variant == PPG_VARIANT_ECO && cfg->include_speed_in_obs ? 1 : 0)) * cfg->obs_range[s] * cfg->obs_range[s];
     b->out.f.obs[s] = (float*)malloc(n * (size_t)elems * sizeof(float));
     b->out.obs64[s] = (double*)malloc(n * (size_t)elems * sizeof(double));
     b->out.f.row_env[s] = (int32_t*)malloc(n * sizeof(int32_t));
@@ -628,16 +560,31 @@ void ppgo_destroy(ppgo_batch* b) {
     free(b->out.f.flags[s]); free(b->out.f.old_off[s]); free(b->out.f.new_off[s]); free(b->out.f.new_cnt[s]); free(b->prev_row[s]);
   }
   free(b->out.f.env_flags); free(b->out.f.env_status); free(b->out.f.env_step); free(b->out.f.env_count);
-  free(b->tape_cells); free(b->tape_off);
+  free(b->tape_cells); free(b->tape_off); free(b->tape_reals); free(b->tape_real_off);
   free(b);
 }
 
 void ppgo_set_threads(ppgo_batch* b, int32_t n) { b->n_threads = n < 1 ? 1 : n; }
 
 int ppgo_load_tape(ppgo_batch* b, const ppg_tape* t) {
-  free(b->tape_cells); free(b->tape_off);
-  b->tape_cells = NULL; b->tape_off = NULL; b->has_tape = 0;
-  for (int e = 0; e < b->n_envs; ++e) { b->envs[e].tape_cells = NULL; b->envs[e].tape_pos = b->envs[e].tape_end = 0; }
+  free(b->tape_cells); free(b->tape_off); free(b->tape_reals); free(b->tape_real_off);
+  b->tape_cells = NULL; b->tape_off = NULL; b->tape_reals = NULL; b->tape_real_off = NULL; b->has_tape = 0;
+  for (int e = 0; e < b->n_envs; ++e) {
+    b->envs[e].tape_cells = NULL; b->envs[e].tape_pos = b->envs[e].tape_end = 0;
+    b->envs[e].tape_reals = NULL; b->envs[e].real_pos = b->envs[e].real_end = 0;
+  }
+  if (t && t->reals && t->real_off) {
+    int64_t total = t->real_off[b->n_envs];
+    b->tape_reals = (double*)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+    b->tape_real_off = (int64_t*)malloc(sizeof(int64_t) * ((size_t)b->n_envs + 1));
+    memcpy(b->tape_reals, t->reals, sizeof(double) * (size_t)total);
+    memcpy(b->tape_real_off, t->real_off, sizeof(int64_t) * ((size_t)b->n_envs + 1));
+    for (int e = 0; e < b->n_envs; ++e) {
+      b->envs[e].tape_reals = b->tape_reals;
+      b->envs[e].real_pos = b->tape_real_off[e];
+      b->envs[e].real_end = b->tape_real_off[e + 1];
+    }
+  }
   if (!t || !t->cells || !t->cell_off) return PPG_OK;
   int64_t total = t->cell_off[b->n_envs];
   b->tape_cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)(total > 0 ? total : 1));
@@ -660,15 +607,17 @@ static void export_rows(ppgo_batch* b) {
   for (int e = 0; e < b->n_envs; ++e) {
     env_t* v = &b->envs[e];
     for (int s = 0; s < 2; ++s) { b->out.f.old_off[s][e] = n_old[s]; }
+    const int32_t* keys = v->row_key ? v->row_key : v->agents;
     for (int i = 0; i < v->n_rows; ++i)
-      if (v->has_obs[i] && !v->newborn[i]) n_old[KEY_S(v->agents[i])]++;
+      if (v->has_obs[i] && !v->newborn[i]) n_old[KEY_S(keys[i])]++;
   }
   for (int s = 0; s < 2; ++s) b->out.f.old_off[s][b->n_envs] = n_old[s];
   for (int e = 0; e < b->n_envs; ++e) {
     env_t* v = &b->envs[e];
     for (int s = 0; s < 2; ++s) b->out.f.new_off[s][e] = n_old[s] + n_new[s];
+    const int32_t* keys = v->row_key ? v->row_key : v->agents;
     for (int i = 0; i < v->n_rows; ++i)
-      if (v->has_obs[i] && v->newborn[i]) n_new[KEY_S(v->agents[i])]++;
+      if (v->has_obs[i] && v->newborn[i]) n_new[KEY_S(keys[i])]++;
   }
   for (int s = 0; s < 2; ++s) b->out.f.new_off[s][b->n_envs] = n_old[s] + n_new[s];
   for (int s = 0; s < 2; ++s) /* (start, count) form of include/ppg.h: start is 0 where the env has no newborn rows */
@@ -679,9 +628,10 @@ static void export_rows(ppgo_batch* b) {
     env_t* v = &b->envs[e];
     int32_t po[2] = {b->out.f.old_off[0][e], b->out.f.old_off[1][e]};
     int32_t pn[2] = {b->out.f.new_off[0][e], b->out.f.new_off[1][e]};
+    const int32_t* keys = v->row_key ? v->row_key : v->agents;
     for (int i = 0; i < v->n_rows; ++i) {
       if (!v->has_obs[i]) continue;
-      int s = KEY_S(v->agents[i]), id = KEY_ID(v->agents[i]);
+      int s = KEY_S(keys[i]), id = KEY_ID(keys[i]);
       int32_t row = v->newborn[i] ? pn[s]++ : po[s]++;
       int elems = v->row_elems[s];
       const double* src = v->obs + (size_t)i * v->max_row_elems;
@@ -698,6 +648,7 @@ static void export_rows(ppgo_batch* b) {
       if (v->newborn[i]) fl |= PPG_ROW_NEWBORN;
       if (v->env_flags & PPG_ENV_RESET) fl |= PPG_ROW_FOUNDER;
       if (v->ate[i]) fl |= PPG_ROW_ATE;
+      if (v->row_key && v->carcass[i]) fl |= PPG_ROW_CARCASS;
       b->out.f.flags[s][row] = fl;
       b->prev_row[s][(size_t)e * c->n_possible[s] + id] = row;
     }
@@ -815,7 +766,7 @@ int ppgo_random_actions(ppgo_batch* b, uint64_t seed, int32_t* actions_pred, int
     for (int32_t row = 0; row < n; ++row) {
       uint32_t env = (uint32_t)(b->out.f.row_env[s][row] + b->cfg.env_index_base), id = (uint32_t)b->out.f.row_agent[s][row];
       uint32_t r = ppg_draw_u32(seed, env, (uint32_t)b->calls, PPG_STREAM_ACTION + 8u * (uint32_t)s, id);
-      act[s][row] = (int32_t)ppg_bounded(r, 9u);
+      act[s][row] = (int32_t)ppg_bounded(r, (uint32_t)(b->cfg.variant == PPG_VARIANT_ECO ? b->cfg.action_range * b->cfg.action_range : 9));
     }
   }
   return PPG_OK;
@@ -861,7 +812,43 @@ int ppgo_read_env(ppgo_batch* b, int32_t env, int32_t* n_live, int32_t* ids_pred
 int ppgo_read_grid(ppgo_batch* b, int32_t env, double* grid_out) {
   if (env < 0 || env >= b->n_envs) return PPG_ERR_INVALID;
   env_t* v = &b->envs[env];
+  if (b->cfg.variant == PPG_VARIANT_ECO) { eco_read_grid(v, grid_out); return PPG_OK; }
   memcpy(grid_out, v->grid, sizeof(double) * (size_t)v->C * v->G * v->G);
+  return PPG_OK;
+}
+
+/* ---- ECO extras ---- */
+int ppgo_env_reset_eco(ppgo_batch* b, int32_t env, const int32_t* cells, const double* founder_speed) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;
+  for (int e = 0; e < b->n_envs; ++e) if (e != env) b->envs[e].n_rows = 0;
+  b->envs[env].episode += 1;
+  b->envs[env].trait_draws = 0;
+  eco_env_reset_explicit(&b->envs[env], cells, founder_speed);
+  export_rows(b);
+  return PPG_OK;
+}
+
+void ppgo_set_pow_libm(ppgo_batch* b, int32_t on) {
+  for (int e = 0; e < b->n_envs; ++e) b->envs[e].pow_libm = on;
+}
+
+int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
+                      double* speed_prey, uint8_t* dead_prey, int32_t* active_num) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;
+  env_t* v = &b->envs[env];
+  int32_t* age[2] = {age_pred, age_prey};
+  double* sp[2] = {speed_pred, speed_prey};
+  for (int s = 0; s < 2; ++s) {
+    int n = 0;
+    for (int id = 0; id < v->next_idx[s]; ++id)
+      if (v->present[s][id]) {
+        if (age[s]) age[s][n] = v->age[s][id];
+        if (sp[s]) sp[s][n] = v->speed[s][id];
+        if (s == 1 && dead_prey) dead_prey[n] = v->dead[id];
+        ++n;
+      }
+  }
+  if (active_num) { active_num[0] = v->active[0]; active_num[1] = v->active[1]; }
   return PPG_OK;
 }
 

@@ -1,0 +1,113 @@
+/*
+ * ppg_oracle_int.h — internal types shared by the oracle's translation units (TEST INFRASTRUCTURE ONLY).
+ */
+#ifndef PPG_ORACLE_INT_H_
+#define PPG_ORACLE_INT_H_
+
+#include "ppg_oracle.h"
+
+#define KEY(s, id) (((int32_t)(s) << 16) | (int32_t)(id))
+#define KEY_S(k) ((k) >> 16)
+#define KEY_ID(k) ((k)&0xFFFF)
+
+/* ------------------------------------------------------------------------------------------ */
+/* one environment instance                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct env_t {
+  const ppg_config* c;
+  int G, C;
+  int env_index;
+  /* dicts keyed by agent id: agent_positions / agent_energies (BASE:111-117) */
+  uint8_t* present[2];
+  int16_t* x[2];
+  int16_t* y[2];
+  double* energy[2];
+  int32_t* parent[2]; /* KICK:86-91 agent_parent, -1 = none */
+  /* self.agents (BASE:73), self._pending_removal (BASE:65) */
+  int32_t* agents;
+  int n_agents;
+  int32_t* pending;
+  int n_pending;
+  int next_idx[2]; /* BASE:66-67 */
+  int cur_num[2];  /* BASE:210-211 */
+  int current_step;
+  double* grid; /* [C][G][G] BASE:123-124 */
+  int16_t* gx;
+  int16_t* gy;
+  double* ge; /* grass_positions / grass_energies */
+  /* per-call dicts: observations / rewards / terminations, keyed by list index of self.agents */
+  double* obs;     /* [cap_rows][max_row_elems] */
+  double* rew;     /* rewards[agent] */
+  int8_t* has_rew;
+  int8_t* term;    /* -1 missing, 0 False, 1 True */
+  int8_t* trunc;
+  int8_t* has_obs;
+  uint8_t* ate;    /* agents_just_ate */
+  uint8_t* newborn;
+  double* e_before; /* ADD:256 energy_before */
+  double* bonus;    /* ADD:261 reproduction_bonus */
+  int32_t* list_index[2]; /* id -> index in self.agents during the call */
+  int n_rows;      /* rows produced by the last call (= len(self.agents) at output time) */
+  int cap_rows;
+  int row_elems[2];
+  int max_row_elems;
+  uint8_t all_term, all_trunc; /* "__all__" */
+  uint8_t env_flags;
+  /* lockstep layer */
+  int needs_reset, idle;
+  uint8_t status;
+  uint64_t seed_key;
+  uint32_t episode, spawn_draws;
+  const int32_t* tape_cells;
+  int64_t tape_pos, tape_end;
+  int64_t stats[PPG_N_STATS];
+  /* lexicographic rank of str(id): Python sorts agent-id strings (BASE:468) */
+  const int32_t* lexrank[2];
+  /* ---- ECO (ppg_oracle_eco.c) ---- */
+  int32_t* row_key;   /* ECO: agent of output row i (BASE: row i is self.agents[i]); NULL for BASE */
+  uint8_t* carcass;   /* per row: in dead_prey after the step */
+  uint8_t* born_obs;  /* per row: observation captured at birth (ECO:1179) is still the one in self.observations */
+  float* gridf;       /* ECO grid_world_state is float32 [C][G][G] (ECO:222-224) */
+  int32_t* age[2];    /* agent_ages (ECO:153) */
+  double* speed[2];   /* agent_genomes[..].speed (ECO:177); < 0 = no genome */
+  uint8_t* termd[2];  /* self.terminations.get(agent) of the running step */
+  uint8_t* dead;      /* dead_prey membership by prey id (ECO:193) */
+  int active[2];      /* active_num_predators / active_num_prey (ECO:212-213) */
+  const double* tape_reals;
+  int64_t real_pos, real_end;
+  uint32_t trait_draws;
+  int pow_libm;       /* 1: speed ** exponent through libm pow like CPython (golden pinning); 0: device semantics */
+} env_t;
+
+struct ppgo_batch {
+  ppg_config cfg;
+  int n_envs;
+  env_t* envs;
+  int32_t* lexrank[2];
+  /* tape copy */
+  int32_t* tape_cells;
+  int64_t* tape_off;
+  double* tape_reals;
+  int64_t* tape_real_off;
+  int has_tape;
+  /* flat outputs */
+  ppgo_buffers out;
+  int64_t cap[2];
+  int32_t n_rows[4];
+  uint64_t calls;
+  int n_threads;
+  /* row -> (list position) bookkeeping of the previous output, for action lookup */
+  int32_t* prev_row[2]; /* [env][id] flattened lazily: per env arrays */
+};
+
+
+/* ---- ECO (ppg_oracle_eco.c) ---- */
+void eco_env_alloc(env_t* e);
+void eco_env_free(env_t* e);
+void eco_ensure_rows(env_t* e, int need);
+void eco_env_reset_auto(env_t* e);
+void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founder_speed);
+int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, const int32_t* a_val);
+void eco_read_grid(env_t* e, double* out);
+
+#endif

@@ -20,6 +20,8 @@ REWARD_MODES = {
 ROW_TERMINATED, ROW_TRUNCATED, ROW_NEWBORN, ROW_FOUNDER, ROW_ATE = 0x01, 0x02, 0x04, 0x08, 0x10
 ENV_TERMINATED, ENV_TRUNCATED, ENV_RESET, ENV_IDLE = 0x01, 0x02, 0x04, 0x08
 STATUS_SLOT_OVERFLOW, STATUS_NO_SPAWN_CELL, STATUS_TAPE_EXHAUSTED, STATUS_BAD_ACTION = 0x01, 0x02, 0x04, 0x08
+STATUS_ID_POOL_EMPTY, STATUS_GHOST_CELL = 0x10, 0x20
+ROW_CARCASS = 0x20
 N_STATS = 16
 STAT_NAMES = [
     "env_steps", "agent_steps", "episodes", "episode_steps", "births_pred", "births_prey", "starved_pred",
@@ -57,6 +59,26 @@ class PpgConfig(C.Structure):
         ("seed", C.c_uint64),
         ("env_index_base", C.c_int32),
         ("reserved0", C.c_int32),
+        # ---- ECO ----
+        ("action_range", C.c_int32),
+        ("genome_enabled", C.c_int32),
+        ("include_speed_in_obs", C.c_int32),
+        ("max_agent_age", C.c_int32 * 2),
+        ("carcass_only_predator_age", C.c_int32),
+        ("slow_max_move_distance", C.c_int32),
+        ("fast_max_move_distance", C.c_int32),
+        ("reserved1", C.c_int32 * 2),
+        ("move_cost_per_cell", C.c_double * 2),
+        ("move_speed_cost_exponent", C.c_double),
+        ("max_energy_grass", C.c_double),
+        ("max_energy_gain_per_grass", C.c_double),
+        ("max_energy_gain_per_prey", C.c_double),
+        ("founder_speed_mean", C.c_double * 2),
+        ("founder_speed_std", C.c_double * 2),
+        ("mutation_rate", C.c_double),
+        ("mutation_std", C.c_double),
+        ("speed_bounds", C.c_double * 2),
+        ("speed_distance_threshold", C.c_double),
     ]
 
 
@@ -111,7 +133,7 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.obs_range[1] = g("prey_obs_range", 5)
     c.n_possible[0] = g("n_possible_predators", 50)
     c.n_possible[1] = g("n_possible_prey", 50)
-    c.n_initial[0] = g("n_initial_active_predator", 6)
+    c.n_initial[0] = g("n_initial_active_predator", g("n_initial_active_predators", 6))
     c.n_initial[1] = g("n_initial_active_prey", 8)
     c.n_grass = g("initial_num_grass", 25)
     if cap_live is None:
@@ -134,13 +156,82 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.reward_predator_step = g("reward_predator_step", 0.0)
     c.reward_prey_step = g("reward_prey_step", 0.0)
     c.penalty_prey_caught = g("penalty_prey_caught", 0.0)
-    c.reproduction_reward[0] = g("reproduction_reward_predator", 10.0)
-    c.reproduction_reward[1] = g("reproduction_reward_prey", 10.0)
+    if variant != VARIANT_ECO:
+        c.reproduction_reward[0] = g("reproduction_reward_predator", 10.0)
+        c.reproduction_reward[1] = g("reproduction_reward_prey", 10.0)
     c.kickback_reward[0] = g("kickback_reward_predator", 10.0)
     c.kickback_reward[1] = g("kickback_reward_prey", 10.0)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     c.env_index_base = int(env_index_base)
+    c.action_range = 3
+    c.max_agent_age[0] = c.max_agent_age[1] = -1
+    c.carcass_only_predator_age = -1
+    c.slow_max_move_distance = c.fast_max_move_distance = 1
+    c.move_speed_cost_exponent = 2.0
+    c.max_energy_grass = c.initial_energy_grass  # BASE caps regrowth at the initial energy (BASE:253-255)
+    c.max_energy_gain_per_grass = c.max_energy_gain_per_prey = float("inf")
+    c.speed_bounds[0], c.speed_bounds[1] = 0.5, 2.0
+    c.speed_distance_threshold = 1.5
+    if variant == VARIANT_ECO:
+        _fill_eco(c, cfg)
     return c
+
+
+def _role(value, role, default=None):
+    """ECO `_get_role_specific` (ECO:1723-1731): a scalar, or a dict keyed by an agent-id prefix."""
+    if isinstance(value, dict):
+        for k, v in value.items():
+            if role.startswith(k):
+                return v
+        return default
+    return default if value is None else value
+
+
+def _age(value):
+    return -1 if value is None or not isinstance(value, (int, float)) or value < 0 else int(value)
+
+
+def _fill_eco(c, cfg):
+    """ECO `_initialize_from_config` (ECO:36-120) — same keys, same defaults."""
+    g = cfg.get
+    c.n_initial[0] = cfg["n_initial_active_predators"]
+    c.n_initial[1] = cfg["n_initial_active_prey"]
+    c.num_obs_channels = cfg["num_obs_channels"]
+    c.action_range = cfg["action_range"]
+    c.genome_enabled = 1 if g("genome_enabled", True) else 0
+    c.include_speed_in_obs = 1 if g("include_speed_in_obs", False) else 0
+    caps = {"predator": 120, "prey": 100}  # ECO:51-54 defaults for roles omitted from the dict
+    if isinstance(g("max_agent_age"), dict):
+        caps.update(g("max_agent_age"))
+    c.max_agent_age[0], c.max_agent_age[1] = _age(caps.get("predator")), _age(caps.get("prey"))
+    carc = g("carcass_only_predator_age")
+    c.carcass_only_predator_age = _age(carc.get("predator")) if isinstance(carc, dict) else -1
+    c.slow_max_move_distance = int(g("slow_max_move_distance", 1))
+    c.fast_max_move_distance = int(g("fast_max_move_distance", 2))
+    c.move_cost_per_cell[0] = float(g("movement_energy_cost_per_cell_predator", 0.0))
+    c.move_cost_per_cell[1] = float(g("movement_energy_cost_per_cell_prey", 0.0))
+    c.move_speed_cost_exponent = float(g("movement_speed_cost_exponent", 2.0))
+    c.max_energy_grass = float(cfg["max_energy_grass"])
+    c.max_energy_gain_per_grass = float(g("max_energy_gain_per_grass", float("inf")))
+    c.max_energy_gain_per_prey = float(g("max_energy_gain_per_prey", float("inf")))
+    for s, role in enumerate(("predator", "prey")):
+        f = g("founder_genome", {}).get(role, {})
+        c.founder_speed_mean[s] = float(f.get("speed_mean", 1.0))
+        c.founder_speed_std[s] = float(f.get("speed_std", 0.0))
+    m = g("genome_mutation", {})
+    c.mutation_rate, c.mutation_std = float(m.get("rate", 0.0)), float(m.get("std", 0.0))
+    b = g("trait_bounds", {}).get("speed", (0.5, 2.0))
+    c.speed_bounds[0], c.speed_bounds[1] = float(b[0]), float(b[1])
+    c.speed_distance_threshold = float(g("speed_distance_threshold", 1.5))
+    # ECO reads only the reproduction rewards and the lineage coefficient from the config (ECO:47-50);
+    # `_get_role_specific` finds no `*_config` attribute for the other reward keys and returns 0.0 (ECO:1724)
+    c.reward_predator_catch_prey = c.reward_prey_eat_grass = c.reward_predator_step = c.reward_prey_step = 0.0
+    c.penalty_prey_caught = 0.0
+    c.reproduction_reward[0] = float(_role(cfg["reproduction_reward_predator"], "predator", 0.0))
+    c.reproduction_reward[1] = float(_role(cfg["reproduction_reward_prey"], "prey", 0.0))
+    lin = cfg.get("lineage_reward_coeff", 0.0)
+    if any(float(_role(lin, r, 0.0) or 0.0) != 0.0 for r in ("predator", "prey")):
+        raise ValueError("lineage_reward_coeff != 0 is not supported (ECO:943-991 lineage survival rewards)")
 
 
 # base_environment/config_env.py:1-38 — the BASELINE configs 1 and 2
@@ -170,4 +261,53 @@ BASE_CONFIG = {
     "initial_num_grass": 100,
     "initial_energy_grass": 2.0,
     "energy_gain_per_step_grass": 0.04,
+}
+
+
+# eco_evolutionary/config/config_env_eco_evolutionary.py:1-88 — BASELINE config 4
+ECO_CONFIG = {
+    "seed": 41,
+    "max_steps": 1000,
+    "grid_size": 25,
+    "num_obs_channels": 3,
+    "predator_obs_range": 7,
+    "prey_obs_range": 9,
+    "action_range": 5,
+    "reproduction_reward_predator": {"predator": 10.0},
+    "reproduction_reward_prey": {"prey": 10.0},
+    "lineage_reward_coeff": {"predator": 0.0, "prey": 0.0},
+    "max_agent_age": {"predator": None, "prey": 400},
+    "carcass_only_predator_age": {"predator": None},
+    "energy_loss_per_step_predator": 0.20,
+    "energy_loss_per_step_prey": 0.05,
+    "movement_energy_cost_per_cell_predator": 0.05,
+    "movement_energy_cost_per_cell_prey": 0.02,
+    "predator_creation_energy_threshold": 12.0,
+    "prey_creation_energy_threshold": 8.0,
+    "initial_energy_predator": 5.0,
+    "initial_energy_prey": 3.0,
+    "genome_enabled": True,
+    "include_speed_in_obs": True,
+    "founder_genome": {"predator": {"speed_mean": 1.0, "speed_std": 0.2}, "prey": {"speed_mean": 1.0, "speed_std": 0.2}},
+    "genome_mutation": {"rate": 0.05, "std": 0.1},
+    "trait_bounds": {"speed": (0.5, 2.0)},
+    "speed_distance_threshold": 1.5,
+    "slow_max_move_distance": 1,
+    "fast_max_move_distance": 2,
+    "movement_speed_cost_exponent": 2.0,
+    "max_energy_gain_per_grass": float("inf"),
+    "max_energy_gain_per_prey": float("inf"),
+    "max_energy_grass": 2.0,
+    "n_possible_predators": 400,
+    "n_possible_prey": 1200,
+    "n_initial_active_predators": 10,
+    "n_initial_active_prey": 10,
+    "initial_num_grass": 100,
+    "initial_energy_grass": 2.0,
+    "energy_gain_per_step_grass": 0.04,
+    "verbose_engagement": False,
+    "verbose_movement": False,
+    "verbose_decay": False,
+    "verbose_reproduction": False,
+    "debug_mode": False,
 }

@@ -28,8 +28,27 @@ def load_golden(name):
 
 def config_from_golden(cfg, **kw):
     variant = cfg.get("variant", "sparse")
+    if variant == "eco":
+        from predpreygrass_b200.config import VARIANT_ECO
+
+        kw.setdefault("cap_live", (cfg["n_possible_predators"], cfg["n_possible_prey"]))
+        return make_config(cfg, variant=VARIANT_ECO, **kw)
     kw.setdefault("cap_live", (cfg.get("n_possible_predators", 50), cfg.get("n_possible_prey", 50)))
     return make_config(cfg, reward_mode=REWARD_MODES[variant], **kw)
+
+
+def sha_f32(arrs):
+    h = hashlib.sha1()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+def id_order_rows(out, env=0):
+    """Rows of one env sorted by (species, agent id): the order the ECO golden files use (the reference builds its
+    dicts from Python sets, ECO:413,424, so it has no order of its own)."""
+    rows = dict_order_rows(out, env)
+    return sorted(rows, key=lambda sr: (sr[0], int(out[f"row_agent{sr[0]}"][sr[1]])))
 
 
 def sha_f64(arrs):
