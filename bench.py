@@ -36,18 +36,43 @@ def parse():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="env instances per GPU (BASELINE configs[1])")
+    ap.add_argument("--variant", default="base", choices=["base", "eco"],
+                    help="base: BASELINE configs[1]/[2] (base_environment family); eco: configs[3] (eco_evolutionary, speed trait)")
+    ap.add_argument("--eco-rich", action="store_true", help="eco: reproduction-heavy override (thresholds 8/5, grass regrowth 0.3)")
     ap.add_argument("--reward-mode", default="sparse")
-    ap.add_argument("--cap", type=int, nargs=2, default=[64, 192])
+    ap.add_argument("--cap", type=int, nargs=2, default=None)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-envs", type=int, default=512)
     ap.add_argument("--cpu-steps", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.cap is None:
+        args.cap = [64, 192] if args.variant == "base" else ([128, 320] if args.eco_rich else [32, 96])
+    return args
 
 
 def workload_name(args):
+    if args.variant == "eco":
+        return (f"eco_evolutionary default config_env{' + reproduction-heavy override' if args.eco_rich else ''}, {args.envs} envs per GPU, "
+                "uniform random actions (25), auto-reset, Philox trait/mutation draws")
     return f"base_environment default config_env, {args.envs} envs per GPU, uniform random actions, auto-reset, reward={args.reward_mode}"
+
+
+def build_config(args, **kw):
+    from predpreygrass_b200.config import BASE_CONFIG, ECO_CONFIG, VARIANT_ECO, make_config
+
+    if args.variant == "eco":
+        d = dict(ECO_CONFIG)
+        if args.eco_rich:
+            d.update(energy_gain_per_step_grass=0.3, prey_creation_energy_threshold=5.0, predator_creation_energy_threshold=8.0,
+                     energy_loss_per_step_predator=0.1)
+        return make_config(d, variant=VARIANT_ECO, cap_live=tuple(args.cap), **kw)
+    return make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), **kw)
+
+
+def n_actions(args):
+    return 25 if args.variant == "eco" else 9
 
 
 class ClockSampler:
@@ -90,13 +115,12 @@ def cpu_oracle_rate(args, threads, steps, warmup):
     import numpy as np
 
     from oracle.oracle import Oracle
-    from predpreygrass_b200.config import BASE_CONFIG, make_config
 
-    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=12345)
+    cfg = build_config(args, seed=12345)
     o = Oracle(cfg, args.cpu_envs, threads=threads)
     o.reset()
     rng = np.random.default_rng(0)
-    pool = rng.integers(0, 9, size=args.cpu_envs * (args.cap[0] + args.cap[1]) + 16, dtype=np.int32)
+    pool = rng.integers(0, n_actions(args), size=args.cpu_envs * (args.cap[0] + args.cap[1]) + 16, dtype=np.int32)
 
     def run(k):
         t = 0.0
@@ -147,7 +171,7 @@ def main():
     import torch.distributed as dist
 
     from predpreygrass_b200.batched import BatchedPredPreyGrass
-    from predpreygrass_b200.config import BASE_CONFIG, STAT_NAMES, make_config
+    from predpreygrass_b200.config import STAT_NAMES
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -157,7 +181,7 @@ def main():
     W, K = max(3, args.warmup), args.steps
 
     # one Philox key for the whole job; env_index_base makes the trajectories independent of the sharding
-    cfg = make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), seed=1000, env_index_base=rank * args.envs)
+    cfg = build_config(args, seed=1000, env_index_base=rank * args.envs)
     env = BatchedPredPreyGrass(cfg, args.envs, device=local_rank)
     env.reset()
 
@@ -212,8 +236,9 @@ def main():
     sk1 = env.stats_device().clone()
     kd = dict(zip(STAT_NAMES, (sk1 - sk0).tolist()))
     k_ms = sum(a.elapsed_time(b) for a, b in evs) / KR
-    row_bytes = [4 * cfg.num_obs_channels * cfg.obs_range[s] ** 2 for s in range(2)]
-    alg_bytes = (kd["rows_pred"] * row_bytes[0] + kd["rows_prey"] * row_bytes[1] + kd["agent_steps"] * S_AGENT
+    row_bytes = [4 * env.C * cfg.obs_range[s] ** 2 for s in range(2)]
+    s_agent = S_AGENT + (20 if args.variant == "eco" else 0)  # + trait 8 (read+write 16), age 2+2
+    alg_bytes = (kd["rows_pred"] * row_bytes[0] + kd["rows_prey"] * row_bytes[1] + kd["agent_steps"] * s_agent
                  + kd["env_steps"] * (cfg.n_grass * 16 + 64)) / KR
     peaks = {}
     try:
@@ -224,18 +249,19 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        if args.variant == "base" and args.envs == 4096:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "ppg_step_base_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "ppg_step_eco_kernel" if args.variant == "eco" else "ppg_step_base_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
 
     # ---- e2e through the C-ABI with host buffers (rank-local rate, summed over ranks)
     e2e = None
     if not args.no_e2e:
         host = env.make_host_buffers(pinned=True)
-        pool = torch.randint(0, 9, (max(env.row_capacity) + 4096,), dtype=torch.int32).pin_memory()
+        pool = torch.randint(0, n_actions(args), (max(env.row_capacity) + 4096,), dtype=torch.int32).pin_memory()
         h2d = d2h = 0
         n0, n1 = env.out.counts()
         e0 = env.stats_device().clone()

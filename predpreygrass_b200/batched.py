@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config import N_STATS, STAT_NAMES, PpgBuffers, PpgConfig, PpgTape
+from .config import N_STATS, STAT_NAMES, VARIANT_ECO, PpgBuffers, PpgConfig, PpgTape
 
 
 class _DevPtr:
@@ -70,7 +70,8 @@ class BatchedPredPreyGrass:
         self.h = h
         b = PpgBuffers()
         _lib.check(self.L.ppg_get_buffers(self.h, C.byref(b)), self.h)
-        self.C = cfg.num_obs_channels
+        # row channels: the grid channels, plus ECO's own-speed plane (ECO:707-711)
+        self.C = cfg.num_obs_channels + (1 if cfg.variant == VARIANT_ECO and cfg.include_speed_in_obs else 0)
         self.R = (cfg.obs_range[0], cfg.obs_range[1])
         self.row_capacity = (int(b.row_capacity[0]), int(b.row_capacity[1]))
         d, B = self.device, self.n_envs
@@ -110,14 +111,24 @@ class BatchedPredPreyGrass:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ API
-    def load_tape(self, cells_per_env):
-        off = np.zeros(self.n_envs + 1, np.int64)
-        for i, c in enumerate(cells_per_env):
-            off[i + 1] = off[i] + len(c)
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in cells_per_env]) if off[-1] else np.zeros(1, np.int32))
+    def load_tape(self, cells_per_env, reals_per_env=None):
+        """Replay tape (include/ppg.h ppg_tape): per env the recorded cells and, for ECO, the recorded real draws."""
+
+        def flatten(seqs, dtype):
+            off = np.zeros(self.n_envs + 1, np.int64)
+            for i, c in enumerate(seqs):
+                off[i + 1] = off[i] + len(c)
+            flat = np.concatenate([np.asarray(c, dtype) for c in seqs]) if off[-1] else np.zeros(1, dtype)
+            return np.ascontiguousarray(flat, dtype), off
+
+        flat, off = flatten(cells_per_env, np.int32)
         t = PpgTape()
         t.cells = flat.ctypes.data_as(C.POINTER(C.c_int32))
         t.cell_off = off.ctypes.data_as(C.POINTER(C.c_int64))
+        if reals_per_env is not None:
+            rflat, roff = flatten(reals_per_env, np.float64)
+            t.reals = rflat.ctypes.data_as(C.POINTER(C.c_double))
+            t.real_off = roff.ctypes.data_as(C.POINTER(C.c_int64))
         _lib.check(self.L.ppg_load_tape(self.h, C.byref(t)), self.h)
 
     def reset(self, seeds=None, mask=None):
@@ -232,6 +243,20 @@ class BatchedPredPreyGrass:
         _lib.check(rc, self.h)
         return {"ids": (ids[0][: n[0]], ids[1][: n[1]]), "xy": (xy[0][: n[0]], xy[1][: n[1]]),
                 "energy": (en[0][: n[0]], en[1][: n[1]]), "grass_xy": gxy[: self.cfg.n_grass], "grass_energy": ge[: self.cfg.n_grass]}
+
+    def read_env_eco(self, env):
+        """read_env plus the ECO attributes agent_ages, genome speeds, dead_prey, active_num_* (ECO:153,177,193,212)."""
+        st = self.read_env(env)
+        n = (len(st["ids"][0]), len(st["ids"][1]))
+        age = [np.zeros(max(1, n[s]), np.int32) for s in range(2)]
+        sp = [np.zeros(max(1, n[s]), np.float64) for s in range(2)]
+        dead = np.zeros(max(1, n[1]), np.uint8)
+        act = np.zeros(2, np.int32)
+        rc = self.L.ppg_read_env_eco(self.h, env, age[0].ctypes.data, sp[0].ctypes.data, age[1].ctypes.data, sp[1].ctypes.data,
+                                     dead.ctypes.data, act.ctypes.data)
+        _lib.check(rc, self.h)
+        st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]], active_num=act)
+        return st
 
     def outputs_numpy(self):
         """Host copy (numpy) of the valid part of the last output."""

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,10 @@ cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, con
                                   const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
                                   unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s);
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s);
+// ppg_eco.cu
+cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
+cudaError_t step_eco_occupancy(int map_bytes, size_t smem, int* blocks_per_sm);
+cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
 }  // namespace ppg
 
 using namespace ppg;
@@ -42,6 +47,8 @@ struct ppg_handle_s {
   unsigned long long* d_stats = nullptr;
   int32_t* d_tape_cells = nullptr;
   long long* d_tape_off = nullptr;
+  double* d_tape_reals = nullptr;
+  long long* d_tape_real_off = nullptr;
   uint8_t* d_mask = nullptr;
   unsigned long long* d_seeds = nullptr;
   int32_t* d_act[2] = {nullptr, nullptr};  // staging for ppg_step_host
@@ -114,6 +121,16 @@ void ppg_default_config(ppg_config* c) {
   c->reproduction_reward[0] = 10.0; c->reproduction_reward[1] = 10.0;
   c->kickback_reward[0] = 10.0; c->kickback_reward[1] = 10.0;
   c->seed = 0;
+  // ECO fields: neutral values for the BASE family (config.make_config fills the same)
+  c->action_range = 3;
+  c->max_agent_age[0] = c->max_agent_age[1] = -1;
+  c->carcass_only_predator_age = -1;
+  c->slow_max_move_distance = c->fast_max_move_distance = 1;
+  c->move_speed_cost_exponent = 2.0;
+  c->max_energy_grass = c->initial_energy_grass;
+  c->max_energy_gain_per_grass = c->max_energy_gain_per_prey = HUGE_VAL;
+  c->speed_bounds[0] = 0.5; c->speed_bounds[1] = 2.0;
+  c->speed_distance_threshold = 1.5;
 }
 
 const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -121,13 +138,24 @@ const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_s
 static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   if (!c || c->struct_size != sizeof(ppg_config)) { err = "ppg_config.struct_size mismatch"; return PPG_ERR_INVALID; }
   if (n_envs <= 0) { err = "n_envs must be positive"; return PPG_ERR_INVALID; }
-  if (c->variant != PPG_VARIANT_BASE) { err = "variant not supported by this build"; return PPG_ERR_INVALID; }
+  if (c->variant != PPG_VARIANT_BASE && c->variant != PPG_VARIANT_ECO) { err = "variant not supported by this build"; return PPG_ERR_INVALID; }
+  const bool eco = c->variant == PPG_VARIANT_ECO;
   if (c->reward_mode < 0 || c->reward_mode > PPG_REWARD_SPARSE_KICKBACK) { err = "bad reward_mode"; return PPG_ERR_INVALID; }
   if (c->grid_size < 2 || c->grid_size > 255) { err = "grid_size must be in [2,255]"; return PPG_ERR_INVALID; }
-  if (c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
+  if (!eco && c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
+  if (eco) {
+    if (c->num_obs_channels != 3) { err = "ECO needs num_obs_channels == 3 (predators, prey, grass)"; return PPG_ERR_INVALID; }
+    if (c->reward_mode != PPG_REWARD_SPARSE) { err = "ECO has one reward mode"; return PPG_ERR_INVALID; }
+    if (c->action_range < 1 || (c->action_range & 1) == 0 || c->action_range > 15) { err = "action_range must be odd, <= 15"; return PPG_ERR_INVALID; }
+    if (c->n_possible[0] + c->n_possible[1] > 65535) { err = "ECO: n_possible_predators + n_possible_prey must be <= 65535"; return PPG_ERR_INVALID; }
+    if (c->max_steps > 65000) { err = "ECO: max_steps must be <= 65000 (16-bit ages)"; return PPG_ERR_INVALID; }
+    if (c->cap_live[0] > 32767 || c->cap_live[1] > 32767) { err = "ECO: cap_live must be <= 32767"; return PPG_ERR_INVALID; }
+    if (c->slow_max_move_distance < 0 || c->fast_max_move_distance < 0) { err = "max move distance negative"; return PPG_ERR_INVALID; }
+    if (!(c->speed_bounds[1] > c->speed_bounds[0])) { err = "speed bounds"; return PPG_ERR_INVALID; }
+  }
   for (int s = 0; s < 2; ++s) {
     if (c->obs_range[s] < 1 || (c->obs_range[s] & 1) == 0 || c->obs_range[s] > 255) { err = "obs_range must be odd"; return PPG_ERR_INVALID; }
-    if (c->num_obs_channels * c->obs_range[s] * c->obs_range[s] > 4 * 128) { err = "observation row too large for this build"; return PPG_ERR_INVALID; }
+    if ((c->num_obs_channels + (eco && c->include_speed_in_obs ? 1 : 0)) * c->obs_range[s] * c->obs_range[s] > 4 * 128) { err = "observation row too large for this build"; return PPG_ERR_INVALID; }
     if (c->n_possible[s] < c->n_initial[s] || c->n_possible[s] > 65535) { err = "n_possible out of range"; return PPG_ERR_INVALID; }
     if (c->cap_live[s] < c->n_initial[s] || c->cap_live[s] <= 0 || c->cap_live[s] > 32768) { err = "cap_live out of range"; return PPG_ERR_INVALID; }
     if (c->n_initial[s] < 0) { err = "n_initial negative"; return PPG_ERR_INVALID; }
@@ -163,15 +191,32 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   StepParams& P = h->P;
   memset(&P, 0, sizeof P);
   const int B = n_envs, G = c.grid_size, GG = G * G;
-  P.B = B; P.G = G; P.GG = GG; P.C = c.num_obs_channels; P.env_base = c.env_index_base;
+  const bool eco = c.variant == PPG_VARIANT_ECO;
+  const int row_channels = c.num_obs_channels + (eco && c.include_speed_in_obs ? 1 : 0);
+  P.B = B; P.G = G; P.GG = GG; P.C = row_channels; P.env_base = c.env_index_base;
+  P.variant = c.variant;
+  if (eco) {
+    P.action_range = c.action_range; P.n_actions = c.action_range * c.action_range; P.genome_enabled = c.genome_enabled != 0;
+    P.speed_in_obs = c.include_speed_in_obs != 0; P.max_age[0] = c.max_agent_age[0]; P.max_age[1] = c.max_agent_age[1];
+    P.carcass_age = c.carcass_only_predator_age; P.slow_dist = c.slow_max_move_distance; P.fast_dist = c.fast_max_move_distance;
+    P.pow_square = c.move_speed_cost_exponent == 2.0;
+    P.move_cost[0] = c.move_cost_per_cell[0]; P.move_cost[1] = c.move_cost_per_cell[1]; P.move_exp = c.move_speed_cost_exponent;
+    P.bite_cap_grass = c.max_energy_gain_per_grass; P.bite_cap_prey = c.max_energy_gain_per_prey;
+    for (int s = 0; s < 2; ++s) { P.f_mean[s] = c.founder_speed_mean[s]; P.f_std[s] = c.founder_speed_std[s]; }
+    P.mut_rate = c.mutation_rate; P.mut_std = c.mutation_std; P.sp_lo = c.speed_bounds[0]; P.sp_hi = c.speed_bounds[1];
+    P.sp_thr = c.speed_distance_threshold;
+  } else {
+    P.action_range = 3; P.n_actions = 9;
+  }
   for (int s = 0; s < 2; ++s) {
-    P.R[s] = c.obs_range[s]; P.off[s] = (c.obs_range[s] - 1) / 2; P.elems[s] = c.num_obs_channels * c.obs_range[s] * c.obs_range[s];
+    P.R[s] = c.obs_range[s]; P.off[s] = (c.obs_range[s] - 1) / 2; P.elems[s] = row_channels * c.obs_range[s] * c.obs_range[s];
     P.cap[s] = c.cap_live[s]; P.n_init[s] = c.n_initial[s]; P.n_possible[s] = c.n_possible[s];
     P.loss[s] = c.energy_loss[s]; P.thr[s] = c.creation_threshold[s]; P.init_e[s] = c.initial_energy[s];
     P.r_repro[s] = c.reproduction_reward[s]; P.r_kick[s] = c.kickback_reward[s];
   }
   P.n_grass = c.n_grass; P.max_steps = c.max_steps; P.reward_mode = c.reward_mode; P.autoreset = c.autoreset;
-  P.grass_cap = c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
+  P.grass_cap = eco ? c.max_energy_grass : c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
+  P.init_e_grass = c.initial_energy_grass;
   P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
   P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;
 
@@ -200,9 +245,14 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.so_gE = take(8 * (size_t)std::max(1, P.n_grass), 8);
   P.stage_elems = (int)align_up((size_t)std::max(P.elems[0], P.elems[1]), 4);
   // value tables and staging rows are contiguous: reset() stages n_total cells + a GG-entry claim table there
+  if (o - (size_t)P.so_E[0] < (size_t)GG * 4) take((size_t)GG * 4 - (o - (size_t)P.so_E[0]), 1);  // reset(): GG-entry claim table over the energy arrays
   P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
   P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
   P.so_vt[2] = take(4 * (size_t)(P.n_grass + 1), 4);
+  {
+    const size_t need = (size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4;  // reset(): the drawn cells are staged in the value tables
+    if (o - (size_t)P.so_vt[0] < need) take(need - (o - (size_t)P.so_vt[0]), 1);
+  }
   P.so_stage = take(P.obs_bulk ? 2 * 4 * (size_t)P.stage_elems : 0, 16);  // row staging only for the bulk-copy writer
   // reset() stages its n_total cells in the value tables and a GG-entry claim table over the energy arrays
   if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4 > (size_t)(P.so_stage - P.so_vt[0]) ||
@@ -225,6 +275,12 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
   for (int s = 0; s < 2; ++s) { P.so_act[s] = take(P.cap[s], 1); P.so_flg[s] = take(P.cap[s], 1); P.so_aux[s] = take(kick ? P.cap[s] : 0, 1); }
   P.so_gtag = take(std::max(1, P.n_grass), 1);
+  if (eco) {
+    for (int s = 0; s < 2; ++s) {
+      P.so_spd[s] = take(8 * (size_t)P.cap[s], 8); P.so_age[s] = take(2 * (size_t)P.cap[s], 2);
+      P.so_seq[s] = take(2 * (size_t)P.cap[s], 2); P.so_mord[s] = take(2 * (size_t)P.cap[s], 2);
+    }
+  }
   P.smem_per_env = (int)align_up(o, 128);
   const size_t smem_max = 227 * 1024;
   if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
@@ -236,18 +292,19 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
       for (int i = 0; i < P.CH; ++i) {
         const int xx = i >= P.P ? (i - P.P) / P.PS - P.P : -1, yy = i >= P.P ? (i - P.P) % P.PS : 0;
         const bool field = i >= P.P && xx >= 0 && xx < G && yy < G;
-        if (!field) {
+        if (!field && !eco) {  // ECO has no wall channel: out-of-grid window cells stay 0 (ECO:700-706)
           if (P.map_bytes == 1) img[(size_t)i] = (unsigned char)P.wall_idx;
           else reinterpret_cast<uint16_t*>(img.data())[i] = (uint16_t)P.wall_idx;
         }
       }
-      reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
+      if (!eco) reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
       unsigned char* d_img = nullptr;
       CKC(dalloc(h, &d_img, img.size()));
       CKC(cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice));
       P.init_image = d_img;
     }
     std::vector<int> rel((size_t)2 * PPG_MAX_NJ * 32 * 2, 0);
+    std::vector<unsigned> selfm(64, 0u);
     for (int s = 0; s < 2; ++s) {
       const int R = P.R[s], RR = R * R;
       for (int j = 0; j < P.nj[s]; ++j)
@@ -257,9 +314,15 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
           const int q = P.obs_vec[s] ? 4 * (lane + 32 * (j / 4)) + (j % 4) : j * 32 + lane;
           if (q >= P.elems[s]) continue;
           const int ch = q / RR, i = (q % RR) / R, jj = q % R;
-          const int m = ch == 0 ? 0 : ch - 1;
           const int cellrel = (i - P.off[s]) * P.PS + (jj - P.off[s]);
           const size_t at = ((size_t)(s * PPG_MAX_NJ + j) * 32 + lane) * 2;
+          if (eco) {  // ECO channels: 0 predators, 1 prey, 2 grass, 3 the agent's own speed (a constant plane, not a gather)
+            if (ch >= 3) { selfm[(size_t)s * 32 + lane] |= 1u << j; continue; }
+            rel[at] = (P.so_map[ch] - P.so_map[0]) + cellrel * P.map_bytes;
+            rel[at + 1] = P.so_vt[ch];
+            continue;
+          }
+          const int m = ch == 0 ? 0 : ch - 1;
           rel[at] = (P.so_map[m] - P.so_map[0]) + cellrel * P.map_bytes;
           rel[at + 1] = ch == 0 ? P.so_wt : P.so_vt[ch - 1];
         }
@@ -268,17 +331,25 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &d_rel, rel.size()));
     CKC(cudaMemcpy(d_rel, rel.data(), rel.size() * sizeof(int), cudaMemcpyHostToDevice));
     P.obs_rel = reinterpret_cast<const int2*>(d_rel);
+    if (eco) {
+      unsigned* d_self = nullptr;
+      CKC(dalloc(h, &d_self, selfm.size()));
+      CKC(cudaMemcpy(d_self, selfm.data(), selfm.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+      P.obs_self = d_self;
+    }
   }
   int W = 1;
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
   if (W != 1 && W != 4 && W != 8) W = 1;
   while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
+  if (eco) W = 1;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, h->smem_bytes, &per_sm));
+    if (eco) CKC(step_eco_occupancy(P.map_bytes, h->smem_bytes, &per_sm));
+    else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
     h->n_cta = std::min((B + W - 1) / W, per_sm * n_sm);
@@ -291,6 +362,9 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     const size_t n = (size_t)B * P.cap[s];
     CKC(dalloc(h, &P.ag_id[s], n)); CKC(dalloc(h, &P.ag_pos[s], n)); CKC(dalloc(h, &P.ag_e[s], n));
     CKC(dalloc(h, &P.ag_prow[s], n)); CKC(dalloc(h, &P.ag_par[s], c.reward_mode == PPG_REWARD_SPARSE_KICKBACK ? n : 1));
+    if (eco) {
+      CKC(dalloc(h, &P.ag_age[s], n)); CKC(dalloc(h, &P.ag_seq[s], n)); CKC(dalloc(h, &P.ag_spd[s], n)); CKC(dalloc(h, &P.ag_dead[s], n));
+    }
     std::vector<uint16_t> lr = lexrank_table(c.n_possible[s]);
     uint16_t* d = nullptr;
     CKC(dalloc(h, &d, lr.size()));
@@ -306,6 +380,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.done1, n_blk)); CKC(dalloc(h, &P.done2, n_grp)); CKC(dalloc(h, &P.done3, 1));
     CKC(dalloc(h, &P.totals, 8));
   }
+  if (eco) CKC(dalloc(h, &P.ehdr, (size_t)B));
   CKC(dalloc(h, &P.gr_pos, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
@@ -351,6 +426,8 @@ int ppg_destroy(ppg_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_tape_cells) cudaFree(h->d_tape_cells);
   if (h->d_tape_off) cudaFree(h->d_tape_off);
+  if (h->d_tape_reals) cudaFree(h->d_tape_reals);
+  if (h->d_tape_real_off) cudaFree(h->d_tape_real_off);
   delete h;
   return PPG_OK;
 }
@@ -372,6 +449,21 @@ int ppg_load_tape(ppg_handle h, const ppg_tape* t) {
   }
   CK(launch_set_tape(h->P.hdr, h->B, h->d_tape_off, 0));
   h->launch_count++;
+  if (h->P.variant == PPG_VARIANT_ECO) {
+    if (h->d_tape_reals) { cudaFree(h->d_tape_reals); h->d_tape_reals = nullptr; }
+    if (h->d_tape_real_off) { cudaFree(h->d_tape_real_off); h->d_tape_real_off = nullptr; }
+    h->P.tape_reals = nullptr;
+    if (t && t->reals && t->real_off) {
+      const int64_t total = t->real_off[h->B];
+      CK(cudaMalloc(&h->d_tape_reals, sizeof(double) * (size_t)std::max<int64_t>(total, 1)));
+      CK(cudaMalloc(&h->d_tape_real_off, sizeof(long long) * ((size_t)h->B + 1)));
+      CK(cudaMemcpy(h->d_tape_reals, t->reals, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(h->d_tape_real_off, t->real_off, sizeof(long long) * ((size_t)h->B + 1), cudaMemcpyHostToDevice));
+      h->P.tape_reals = h->d_tape_reals;
+    }
+    CK(launch_set_tape_reals(h->P.ehdr, h->B, h->d_tape_real_off, 0));
+    h->launch_count++;
+  }
   CK(cudaDeviceSynchronize());
   return PPG_OK;
 }
@@ -396,7 +488,8 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
                                           : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
-  CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
+  if (P.variant == PPG_VARIANT_ECO) CK(launch_step_eco(P, h->n_cta, h->smem_bytes, st));
+  else CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
   h->launches_step++;
   h->launch_count++;
   h->calls++;
@@ -491,7 +584,7 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
   CK(cudaSetDevice(h->device));
   const StepParams& P = h->P;
   CK(launch_random_actions(P.n_rows, P.row_env[0], P.row_agent[0], P.row_env[1], P.row_agent[1], actions_pred, actions_prey,
-                           seed, (unsigned)h->calls, 9u, (unsigned)P.env_base, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
+                           seed, (unsigned)h->calls, (unsigned)P.n_actions, (unsigned)P.env_base, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
   h->launch_count++;
   return PPG_OK;
 }
@@ -513,7 +606,11 @@ static std::vector<Seg> state_segments(ppg_handle h) {
     v.push_back({P.ag_id[s], n * 2}); v.push_back({P.ag_pos[s], n * 2}); v.push_back({P.ag_e[s], n * 8});
     v.push_back({P.ag_prow[s], n * 4});
     if (P.reward_mode == PPG_REWARD_SPARSE_KICKBACK) v.push_back({P.ag_par[s], n * 2});
+    if (P.variant == PPG_VARIANT_ECO) {
+      v.push_back({P.ag_age[s], n * 2}); v.push_back({P.ag_seq[s], n * 2}); v.push_back({P.ag_spd[s], n * 8}); v.push_back({P.ag_dead[s], n});
+    }
   }
+  if (P.variant == PPG_VARIANT_ECO) v.push_back({P.ehdr, sizeof(EcoHdr) * (size_t)h->B});
   v.push_back({P.gr_pos, (size_t)h->B * std::max(1, P.n_grass) * 2});
   v.push_back({P.gr_e, (size_t)h->B * std::max(1, P.n_grass) * 8});
   v.push_back({P.counters, (size_t)h->B * PPG_N_STATS * 4});
@@ -607,6 +704,39 @@ int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, 
       if (energy_grass) energy_grass[g] = ge[g];
     }
   }
+  return PPG_OK;
+}
+
+int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey, double* speed_prey,
+                     uint8_t* dead_prey, int32_t* active_num) {
+  if (!h || env < 0 || env >= h->B) return PPG_ERR_INVALID;
+  if (h->P.variant != PPG_VARIANT_ECO) { h->err = "ppg_read_env_eco: not an ECO handle"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const StepParams& P = h->P;
+  EnvHdr hd;
+  EcoHdr eh;
+  CK(cudaMemcpy(&hd, P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&eh, P.ehdr + env, sizeof eh, cudaMemcpyDeviceToHost));
+  int32_t* age[2] = {age_pred, age_prey};
+  double* sp[2] = {speed_pred, speed_prey};
+  for (int s = 0; s < 2; ++s) {  // the device list is in ascending id order = the order of ppg_read_env
+    const int n = hd.n_list[s];
+    if (!n) continue;
+    std::vector<uint16_t> a(n);
+    std::vector<double> v(n);
+    std::vector<uint8_t> d(n);
+    const size_t b = (size_t)env * P.cap[s];
+    CK(cudaMemcpy(a.data(), P.ag_age[s] + b, n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v.data(), P.ag_spd[s] + b, n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d.data(), P.ag_dead[s] + b, n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      if (age[s]) age[s][i] = a[i];
+      if (sp[s]) sp[s][i] = v[i];
+      if (s == 1 && dead_prey) dead_prey[i] = d[i];
+    }
+  }
+  if (active_num) { active_num[0] = eh.active[0]; active_num[1] = eh.active[1]; }
   return PPG_OK;
 }
 

@@ -41,6 +41,15 @@ static_assert(sizeof(EnvHdr) == 64, "EnvHdr must be 64 bytes");
 
 enum : unsigned char { ST_NEEDS_RESET = 1, ST_IDLE = 2 };
 
+// ECO only: second per-env header (32 B)
+struct __align__(16) EcoHdr {
+  long long real_pos, real_end;  // replay-tape cursor into tape_reals
+  int active[2];                 // active_num_predators / active_num_prey (ECO:212-213); the reference lets them drift
+  unsigned trait_draws;          // Philox counter of the trait stream
+  unsigned next_seq;             // insertion index of the next newborn in self.agents / agent_positions
+};
+static_assert(sizeof(EcoHdr) == 32, "EcoHdr must be 32 bytes");
+
 // per-slot flag bits, shared memory only
 enum : unsigned char {
   F_ALIVE = 1,    // in agent_positions
@@ -48,7 +57,9 @@ enum : unsigned char {
   F_ATE = 4,      // agents_just_ate
   F_REPRO = 8,    // reproduced this step
   F_NEWBORN = 16, // born this step
-  F_CAUGHT = 32   // died by being eaten (reward differs from starvation)
+  F_CAUGHT = 32,  // died by being eaten (reward differs from starvation)
+  F_CARC = 64,    // ECO: member of dead_prey (bitten, not fully eaten)
+  F_BORNROW = 128 // ECO: the newborn's row was written at birth (kept if the episode ends on this step, ECO:417-420)
 };
 
 struct StepParams {
@@ -57,7 +68,7 @@ struct StepParams {
   int env_base;           // ppg_config.env_index_base
   int R[2], off[2], elems[2];
   int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
-  double loss[2], thr[2], init_e[2], grass_cap, grass_gain;
+  double loss[2], thr[2], init_e[2], grass_cap, grass_gain, init_e_grass;
   double r_catch, r_eat, r_pstep, r_qstep, pen_caught, r_repro[2], r_kick[2];
   // ---- state ----
   EnvHdr* hdr;
@@ -120,6 +131,18 @@ struct StepParams {
   int obs_bulk;         // 1: rows leave through shared-memory staging + cp.async.bulk; 0: direct streaming stores
   const void* init_image;  // [init_bytes] initial contents of the maps / touch counters / wall table of a warp's slice
   int init_bytes;
+  // ---- ECO (ppg_eco.cu) ----
+  int variant, action_range, n_actions, genome_enabled, speed_in_obs, max_age[2], carcass_age, slow_dist, fast_dist;
+  int pow_square;  // movement_speed_cost_exponent == 2: speed * speed
+  double move_cost[2], move_exp, bite_cap_grass, bite_cap_prey, f_mean[2], f_std[2], mut_rate, mut_std, sp_lo, sp_hi, sp_thr;
+  EcoHdr* ehdr;
+  uint16_t* ag_age[2];
+  uint16_t* ag_seq[2];
+  double* ag_spd[2];
+  uint8_t* ag_dead[2];
+  const double* tape_reals;
+  int so_spd[2], so_age[2], so_seq[2], so_mord[2];
+  const unsigned* obs_self;  // [2][32] per-lane bit mask: element j of the lane lies in the agent's own-speed plane (ECO:707-711)
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
                         //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };

@@ -1,0 +1,824 @@
+// ppg_eco.cu — the ECO environment step as one fused, persistent sm_100a kernel.
+//
+// Reproduces, for B independent env instances in lockstep, `PredPreyGrass.step()` / `reset()` of
+//   ECO    = predpreygrass/evolutionary/eco_evolutionary/predpreygrass_rllib_env.py
+//   GENOME = predpreygrass/evolutionary/eco_evolutionary/utils/genome.py
+// (heritable speed trait, 5x5 action table with speed gating, locomotion cost, ageing, carcasses,
+// float32 grid, own-speed observation plane).  Same machinery as ppg_base.cu — one warp per env, owner
+// maps instead of a float grid, two-level gather for the observation rows, deterministic cross-env row
+// allocation (ppg_step_common.cuh) — with ECO's phase order (ECO:295-507):
+//   decay + ageing (ECO:582-616)  ->  age-outs in `self.agents` order  ->  grass regrowth (ECO:618-626)
+//   ->  movement in action order (ECO:628-695)  ->  starvation in `agent_energies` order (ECO:311-316)
+//   ->  prey eat grass (ECO:885-941)  ->  predators bite prey (ECO:786-883)  ->  removals
+//   ->  reproduction with trait mutation (ECO:1092-1275, GENOME:49-59)  ->  outputs (ECO:372-501).
+// List order = ascending agent id per species = the reference's `predator_positions` / `prey_positions`
+// insertion order (ids come from an ascending deque and are never reused, ECO:238-272); the order ACROSS
+// species (`self.agents`, `agent_energies`) is the per-agent insertion sequence number `seq`.
+// A non-zero cell of the reference's float32 grid always equals float32(current energy) of the agent that
+// wrote it last (every energy change is followed by a grid write: ECO:597,651-655,817,829,913,1154-1155), so
+// the blocked test `grid > 0` (ECO:690) is `owner != 0 && (float)E[owner] > 0`.
+#include <cuda_runtime.h>
+
+#include "ppg_step_common.cuh"
+
+namespace ppg {
+
+#define SEL(a) (s == 0 ? a[0] : a[1])
+
+template <typename MapT>
+struct EcoSmem {
+  double* spd[2];
+  uint16_t* age[2];
+  uint16_t* seq[2];
+  uint16_t* mord[2];  // mord[k] = slot of the k-th mover of the species (action-dict order, ECO:632)
+};
+
+template <typename MapT>
+__device__ __forceinline__ EcoSmem<MapT> carve_eco(unsigned char* base, const StepParams& p) {
+  EcoSmem<MapT> s;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    s.spd[k] = reinterpret_cast<double*>(base + p.so_spd[k]);
+    s.age[k] = reinterpret_cast<uint16_t*>(base + p.so_age[k]);
+    s.seq[k] = reinterpret_cast<uint16_t*>(base + p.so_seq[k]);
+    s.mord[k] = reinterpret_cast<uint16_t*>(base + p.so_mord[k]);
+  }
+  return s;
+}
+
+// own-speed plane value (ECO:707-711): float32((speed - lo) / (hi - lo)); 0 without a genome
+__device__ __forceinline__ float speed_plane(const StepParams& p, double spd) {
+  if (!p.speed_in_obs || spd < 0.0) return 0.f;
+  return (float)((spd - p.sp_lo) / (p.sp_hi - p.sp_lo));
+}
+
+// one tape-or-Philox real draw (uniform lanes)
+__device__ __forceinline__ bool take_real(const StepParams& p, EcoHdr& eh, EnvHdr& h, double& out) {
+  if (p.tape_reals != nullptr) {
+    if (eh.real_pos < eh.real_end) { out = p.tape_reals[eh.real_pos++]; return true; }
+    h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+  }
+  return false;
+}
+
+// smallest key > last among the agents selected by `pred` (key = seq << 16 | species << 15 | slot): the next agent in
+// `self.agents` order.  Returns 0xFFFFFFFF when there is none.
+template <typename F>
+__device__ __forceinline__ unsigned next_in_seq_order(const uint16_t* const seq[2], const int n[2], long long last, int lane, F pred) {
+  unsigned best = 0xFFFFFFFFu;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    for (int i = lane; i < n[s]; i += 32) {
+      const unsigned key = ((unsigned)seq[s][i] << 16) | ((unsigned)s << 15) | (unsigned)i;
+      if ((long long)key > last && pred(s, i)) best = min(best, key);
+    }
+  return __reduce_min_sync(FULL, best);
+}
+
+template <int W, typename MapT>
+__global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
+  const EnvSmem<MapT> S = carve<MapT>(sbase, p);
+  const EcoSmem<MapT> X = carve_eco<MapT>(sbase, p);
+  const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
+  const unsigned epoch = p.epoch;
+  const int par = (int)(epoch & 1u);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int AR = p.action_range, AD = (p.action_range - 1) / 2;
+
+  for (int i = lane; i < p.init_bytes / 16; i += 32)
+    reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
+  unsigned rowctr = 0;
+  const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
+  const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
+  __syncwarp();
+
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    env = __shfl_sync(FULL, env, 0);
+    if (env >= p.B) break;
+
+    int n[2] = {0, 0};
+    int births[2] = {0, 0};
+    int old_base[2] = {0, 0};
+    int new_base[2] = {0, 0};
+    int next_live[2] = {0, 0};
+    int mode = 0;
+    unsigned env_flags = 0;
+    unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
+    bool over = false, trunc = false, done = false, have_new_base = false;
+
+    EnvHdr h = p.hdr[env];
+    EcoHdr eh = p.ehdr[env];
+    if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
+      if (lane == 0) atomicOr(p.error, 2u);
+    }
+    if (h.state & ST_NEEDS_RESET) mode = 1;
+    else if (h.state & ST_IDLE) mode = 0;
+    else mode = 2;
+    const unsigned genv = (unsigned)(env + p.env_base);
+
+    if (mode == 1) {
+      // ------------------------------------------------------------------ reset() (ECO:274-293,123-223,1733-1792)
+      h.episode += 1;
+      h.step = 0;
+      h.spawn_draws = 0;
+      h.status = 0;
+      h.state = 0;
+      eh.trait_draws = 0;
+      const int n_f = p.n_init[0] + p.n_init[1], n_total = n_f + p.n_grass;
+      // founder genomes first (ECO:216-221 register the founders before the placement draw, ECO:1752)
+      if (p.genome_enabled) {
+        double* sp0 = X.spd[0];
+        double* sp1 = X.spd[1];
+        if (p.tape_reals != nullptr && eh.real_pos + n_f <= eh.real_end) {
+          for (int k = lane; k < n_f; k += 32) {
+            const double v = p.tape_reals[eh.real_pos + k];
+            const double c = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
+            if (k < p.n_init[0]) sp0[k] = c; else sp1[k - p.n_init[0]] = c;
+          }
+          eh.real_pos += n_f;
+        } else {
+          if (p.tape_reals != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+          // the polar method consumes a variable number of counters per draw: one lane, in founder order
+          unsigned ctr = eh.trait_draws;
+          if (lane == 0) {
+            for (int s = 0; s < 2; ++s)
+              for (int i = 0; i < p.n_init[s]; ++i) {
+                double v = p.f_mean[s];
+                if (p.f_std[s] > 0) v = p.f_mean[s] + p.f_std[s] * ppg_draw_normal(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &ctr);
+                SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
+              }
+          }
+          eh.trait_draws = __shfl_sync(FULL, ctr, 0);
+        }
+      }
+      __syncwarp();
+      int* cells = reinterpret_cast<int*>(S.vt[0]);
+      unsigned* first = reinterpret_cast<unsigned*>(S.E[0]);
+      bool from_tape = false;
+      if (p.tape_cells != nullptr) {
+        if (h.tape_pos + n_total <= h.tape_end) {
+          for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
+          h.tape_pos += n_total;
+          from_tape = true;
+        } else {
+          h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+        }
+      }
+      if (!from_tape) philox_placement(cells, first, n_total, GG, genv, h.episode, h.seed_key, lane);
+      __syncwarp();
+      {
+        int k0 = 0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          for (int i = lane; i < p.n_init[s]; i += 32) {
+            const int c = cells[k0 + i];
+            const int cx = c / G, cy = c % G;
+            S.id[s][i] = (uint16_t)i;
+            S.pos[s][i] = (uint16_t)((cx << 8) | cy);
+            S.flg[s][i] = F_ALIVE;
+            X.age[s][i] = (uint16_t)((s == 0 && p.carcass_age >= 0) ? p.carcass_age : 0);  // ECO:1060-1068
+            X.seq[s][i] = (uint16_t)(k0 + i);
+            if (!p.genome_enabled) X.spd[s][i] = -1.0;
+            S.map[s][CELLXY(cx, cy)] = (MapT)(i + 1);
+          }
+          k0 += p.n_init[s];
+          n[s] = p.n_init[s];
+          h.next_idx[s] = (unsigned short)p.n_init[s];
+        }
+        __syncwarp();  // `first` aliases the energy arrays: write the energies only after the placement is read
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          for (int i = lane; i < p.n_init[s]; i += 32) S.E[s][i] = p.init_e[s];
+        for (int g = lane; g < p.n_grass; g += 32) {
+          const int c = cells[k0 + g];
+          const int cx = c / G, cy = c % G;
+          S.gpos[g] = (uint16_t)((cx << 8) | cy);
+          S.gE[g] = p.init_e_grass;
+          S.map[2][CELLXY(cx, cy)] = (MapT)(g + 1);
+        }
+      }
+      __syncwarp();
+      eh.active[0] = p.n_init[0]; eh.active[1] = p.n_init[1];  // ECO:281-282
+      eh.next_seq = (unsigned)n_f;
+      next_live[0] = n[0]; next_live[1] = n[1];
+      env_flags = PPG_ENV_RESET;
+    } else if (mode == 2) {
+      // ------------------------------------------------------------------ step() (ECO:295-507)
+      n[0] = h.n_list[0]; n[1] = h.n_list[1];
+      unsigned bad = 0;
+      bool aged_any = false;
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        const size_t b = (size_t)env * p.cap[s];
+        const int32_t* ordp = p.order[s];
+        bool use_order = ordp != nullptr;
+        if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
+          bool ok = true;
+          for (int i = lane; i < SEL(n); i += 32) {
+            const int d = ordp[p.ag_prow[s][b + i]];
+            if ((unsigned)d < (unsigned)SEL(n)) SEL(X.mord)[d] = (uint16_t)i; else ok = false;
+          }
+          __syncwarp();
+          for (int i = lane; i < SEL(n); i += 32) {
+            const int d = ordp[p.ag_prow[s][b + i]];
+            if ((unsigned)d < (unsigned)SEL(n)) ok &= SEL(X.mord)[d] == (uint16_t)i;
+          }
+          use_order = __all_sync(FULL, ok);
+          if (!use_order) bad = PPG_STATUS_BAD_ACTION;
+          __syncwarp();
+        }
+        for (int i = lane; i < SEL(n); i += 32) {
+          const int prow = p.ag_prow[s][b + i];
+          int a = p.actions[s][prow];
+          if ((unsigned)a >= (unsigned)p.n_actions) { a = p.n_actions / 2; bad = PPG_STATUS_BAD_ACTION; }
+          const bool carc = p.ag_dead[s][b + i] != 0;
+          unsigned age = p.ag_age[s][b + i];
+          if (!carc) age += 1;  // carcasses do not age (ECO:600-601)
+          SEL(S.id)[i] = p.ag_id[s][b + i];
+          SEL(S.pos)[i] = p.ag_pos[s][b + i];
+          SEL(S.E)[i] = p.ag_e[s][b + i] - p.loss[s];  // ECO:596
+          SEL(X.spd)[i] = p.ag_spd[s][b + i];
+          SEL(X.age)[i] = (uint16_t)age;
+          SEL(X.seq)[i] = p.ag_seq[s][b + i];
+          SEL(S.act)[i] = (uint8_t)a;
+          SEL(S.flg)[i] = (uint8_t)(F_ALIVE | (carc ? F_CARC : 0));
+          if (!use_order) SEL(X.mord)[i] = (uint16_t)i;
+          if (!carc && p.max_age[s] >= 0 && (int)age >= p.max_age[s]) aged_any = true;  // ECO:1052-1058
+        }
+      }
+      h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
+      for (int g = lane; g < p.n_grass; g += 32) {
+        const size_t b = (size_t)env * p.n_grass;
+        const unsigned gp = p.gr_pos[b + g];
+        S.gpos[g] = (uint16_t)gp;
+        S.map[2][CELLP(gp)] = (MapT)(g + 1);
+      }
+      __syncwarp();
+      // owner maps as the grid stands after the decay loop: of agents sharing a cell the later one in list order wrote last
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s)
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
+          const int i = b0 + lane;
+          const bool v = i < SEL(n);
+          int cell = 0;
+          if (v) { cell = CELLP((unsigned)SEL(S.pos)[i]); SEL(S.map)[cell] = (MapT)(i + 1); }
+          __syncwarp();
+          bool need = v && SEL(S.map)[cell] < (unsigned)(i + 1);
+          while (__any_sync(FULL, need)) {
+            if (need) SEL(S.map)[cell] = (MapT)(i + 1);
+            __syncwarp();
+            need = v && SEL(S.map)[cell] < (unsigned)(i + 1);
+          }
+        }
+      __syncwarp();
+
+      // age-outs (ECO:602-616,1060-1090), in self.agents order; the grass channel still shows last step's energies
+      if (__any_sync(FULL, aged_any)) {
+        const size_t gb = (size_t)env * p.n_grass;
+        for (int g = lane; g < p.n_grass; g += 32) S.gE[g] = p.gr_e[gb + g];
+        __syncwarp();
+        long long last = -1;
+        for (;;) {
+          const unsigned key = next_in_seq_order(X.seq, n, last, lane, [&](int s, int i) {
+            return !(S.flg[s][i] & F_CARC) && p.max_age[s] >= 0 && (int)X.age[s][i] >= p.max_age[s];
+          });
+          if (key == 0xFFFFFFFFu) break;
+          last = (long long)key;
+          const int s = (key >> 15) & 1, slot = key & 0x7FFF;
+          const int cell = CELLP((unsigned)SEL(S.pos)[slot]);
+          rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[s] + (size_t)(SEL(old_base) + slot) * p.elems[s], cell, s, n[0], n[1], rowctr,
+                                                   lane, speed_plane(p, SEL(X.spd)[slot]));
+          __syncwarp();
+          SEL(S.map)[cell] = 0;
+          SEL(S.flg)[slot] = F_DIED;
+          if (s == 0) eh.active[0] = max(eh.active[0] - 1, 0); else eh.active[1] = max(eh.active[1] - 1, 0);
+          __syncwarp();
+        }
+      }
+      // grass regrowth (ECO:618-626)
+      for (int g = lane; g < p.n_grass; g += 32) {
+        const double v = p.gr_e[(size_t)env * p.n_grass + g] + p.grass_gain;
+        S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+      }
+      __syncwarp();
+
+      // movements in action-dict order per species (ECO:628-695)
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        MapT* own = SEL(S.map);
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
+          const int k = b0 + lane;
+          int j = 0, oc = 0, tc = 0, nx0 = 0, ny0 = 0, d2 = 0;
+          bool v = false;
+          if (k < SEL(n)) {
+            j = SEL(X.mord)[k];
+            const unsigned f = SEL(S.flg)[j];
+            v = (f & F_ALIVE) && !(f & F_CARC);  // terminated (ECO:633) and dead prey (ECO:636) do not move
+          }
+          if (v) {
+            const unsigned ps = SEL(S.pos)[j];
+            const int a = SEL(S.act)[j];
+            const int x = ps >> 8, y = ps & 255;
+            int dx = a / AR - AD, dy = a % AR - AD;  // ECO:225-232
+            const double sp = SEL(X.spd)[j];
+            const int maxd = (sp >= 0.0 && sp >= p.sp_thr) ? p.fast_dist : p.slow_dist;  // ECO:551-557
+            if (max(abs(dx), abs(dy)) > maxd) { dx = (dx > 0) - (dx < 0); dy = (dy > 0) - (dy < 0); dx *= maxd; dy *= maxd; }  // ECO:673-677
+            nx0 = min(max(x + dx, 0), G - 1); ny0 = min(max(y + dy, 0), G - 1);
+            d2 = (nx0 - x) * (nx0 - x) + (ny0 - y) * (ny0 - y);
+            oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
+            atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
+            if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+          }
+          __syncwarp();
+          const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);
+          __syncwarp();
+          if (v) { S.scr[oc] = 0; S.scr[tc] = 0; }
+          if (v && !dirty) {
+            const unsigned ow = own[tc];
+            const bool blocked = ow != 0 && (float)SEL(S.E)[ow - 1] > 0.f;  // float32 grid > 0 (ECO:690)
+            const int nc = blocked ? oc : tc;
+            if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
+              const double sp = SEL(X.spd)[j];
+              const double fac = sp < 0.0 ? 1.0 : (p.pow_square ? sp * sp : pow(sp, p.move_exp));
+              SEL(S.E)[j] = SEL(S.E)[j] - p.move_cost[s] * sqrt((double)d2) * fac;
+              SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
+            }
+            own[oc] = 0;              // ECO:653,657
+            own[nc] = (MapT)(j + 1);  // ECO:654,658
+          }
+          __syncwarp();
+          unsigned dm = __ballot_sync(FULL, dirty);
+          while (dm) {  // warp-uniform replay, in action order, of the agents that may interact
+            const int l = __ffs(dm) - 1;
+            dm &= dm - 1;
+            const int jj = __shfl_sync(FULL, j, l);
+            const unsigned ps = SEL(S.pos)[jj];
+            const int a = SEL(S.act)[jj];
+            const int xx = ps >> 8, yy = ps & 255;
+            int dx = a / AR - AD, dy = a % AR - AD;
+            const double sp = SEL(X.spd)[jj];
+            const int maxd = (sp >= 0.0 && sp >= p.sp_thr) ? p.fast_dist : p.slow_dist;
+            if (max(abs(dx), abs(dy)) > maxd) { dx = (dx > 0) - (dx < 0); dy = (dy > 0) - (dy < 0); dx *= maxd; dy *= maxd; }
+            const int tx = min(max(xx + dx, 0), G - 1), ty = min(max(yy + dy, 0), G - 1);
+            const unsigned ow = own[CELLXY(tx, ty)];
+            const bool blocked = ow != 0 && (float)SEL(S.E)[ow - 1] > 0.f;
+            const int nx = blocked ? xx : tx, ny = blocked ? yy : ty;
+            const int dd = (nx - xx) * (nx - xx) + (ny - yy) * (ny - yy);
+            double e = SEL(S.E)[jj];
+            if (dd > 0) {
+              const double fac = sp < 0.0 ? 1.0 : (p.pow_square ? sp * sp : pow(sp, p.move_exp));
+              e = e - p.move_cost[s] * sqrt((double)dd) * fac;
+            }
+            __syncwarp();
+            SEL(S.E)[jj] = e;
+            own[CELLXY(xx, yy)] = 0;
+            own[CELLXY(nx, ny)] = (MapT)(jj + 1);
+            SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
+            __syncwarp();
+          }
+        }
+      }
+
+      // Step 4a: starvation over agent_energies = self.agents order (ECO:311-316,766-784); agents that aged out above are
+      // handled again if their energy is <= 0 (no `terminations` guard: quirk 13)
+      {
+        bool sv = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          for (int i = lane; i < n[s]; i += 32) sv |= S.E[s][i] <= 0.0;
+        if (__any_sync(FULL, sv)) {
+          long long last = -1;
+          for (;;) {
+            const unsigned key = next_in_seq_order(X.seq, n, last, lane, [&](int s, int i) { return S.E[s][i] <= 0.0; });
+            if (key == 0xFFFFFFFFu) break;
+            last = (long long)key;
+            const int s = (key >> 15) & 1, slot = key & 0x7FFF;
+            const int cell = CELLP((unsigned)SEL(S.pos)[slot]);
+            rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[s] + (size_t)(SEL(old_base) + slot) * p.elems[s], cell, s, n[0], n[1],
+                                                     rowctr, lane, speed_plane(p, SEL(X.spd)[slot]));
+            __syncwarp();
+            SEL(S.map)[cell] = 0;
+            SEL(S.flg)[slot] = F_DIED;  // also drops F_CARC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
+            if (s == 0) { eh.active[0] -= 1; st_starved[0]++; } else { eh.active[1] -= 1; st_starved[1]++; }
+            __syncwarp();
+          }
+        }
+      }
+
+      // Step 4b: prey eat grass, prey_positions order (ECO:318-323,885-941)
+      for (int b0 = 0; b0 < n[1]; b0 += 32) {
+        const int slot = b0 + lane;
+        int cell = 0, g = 0;
+        bool act = false;
+        if (slot < n[1]) {
+          const unsigned f = S.flg[1][slot];
+          act = (f & F_ALIVE) && !(f & F_CARC);
+          cell = CELLP((unsigned)S.pos[1][slot]);
+          g = S.map[2][cell];
+        }
+        const bool eat = act && g != 0;
+        if (eat) S.gtag[g - 1] = (uint8_t)lane;
+        __syncwarp();
+        const bool clash = eat && S.gtag[g - 1] != (uint8_t)lane;
+        if (!__any_sync(FULL, clash)) {
+          if (eat) {
+            const double ge = S.gE[g - 1];
+            const double bite = ge < p.bite_cap_grass ? ge : p.bite_cap_grass;  // ECO:909-911
+            const double rem = ge - bite;
+            S.E[1][slot] = S.E[1][slot] + bite;
+            S.map[1][cell] = (MapT)(slot + 1);  // ECO:915
+            S.gE[g - 1] = rem > 0.0 ? rem : 0.0;
+            S.flg[1][slot] |= F_ATE;
+          }
+          st_grass += __popc(__ballot_sync(FULL, eat));
+          __syncwarp();
+          continue;
+        }
+        __syncwarp();
+        const int kend = min(b0 + 32, n[1]);
+        for (int sl = b0; sl < kend; ++sl) {  // two prey of this chunk share a patch: exact order
+          const unsigned f = S.flg[1][sl];
+          if (!(f & F_ALIVE) || (f & F_CARC)) continue;
+          const int cl = CELLP((unsigned)S.pos[1][sl]);
+          const int gg = S.map[2][cl];
+          if (gg) {
+            const double ge = S.gE[gg - 1];
+            const double bite = ge < p.bite_cap_grass ? ge : p.bite_cap_grass;
+            const double rem = ge - bite;
+            const double en = S.E[1][sl] + bite;
+            __syncwarp();
+            S.E[1][sl] = en;
+            S.map[1][cl] = (MapT)(sl + 1);
+            S.gE[gg - 1] = rem > 0.0 ? rem : 0.0;
+            S.flg[1][sl] = (uint8_t)(f | F_ATE);
+            st_grass++;
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+
+      // Step 4c: predators, predator_positions order (ECO:325-330,786-883).  Every prey still in agent_positions counts —
+      // also those terminated earlier in this step (removal is Step 5) and carcasses.
+      {
+        for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 1;
+        __syncwarp();
+        for (int b0 = 0; b0 < n[0]; b0 += 32) {
+          const int k = b0 + lane;
+          bool cand = false;
+          if (k < n[0]) cand = (S.flg[0][k] & F_ALIVE) && S.scr[CELLP((unsigned)S.pos[0][k])] != 0;
+          unsigned m = __ballot_sync(FULL, cand);
+          while (m) {
+            const int slot = b0 + __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned ps = S.pos[0][slot];
+            const int cell = CELLP(ps);
+            // first prey in agent_positions order on my cell = lowest id = lowest list slot (ECO:797-799)
+            unsigned best = 0xFFFFFFFFu;
+            for (int i = lane; i < n[1]; i += 32)
+              if (S.pos[1][i] == ps) best = min(best, (unsigned)i);
+            best = __reduce_min_sync(FULL, best);
+            if (best == 0xFFFFFFFFu) continue;
+            const int q = (int)best;
+            const unsigned qf = S.flg[1][q];
+            const bool was_dead = (qf & F_CARC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
+            if (!was_dead && p.carcass_age >= 0 && (int)X.age[0][slot] < p.carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
+            const double pe = S.E[1][q];
+            const double bite = pe < p.bite_cap_prey ? pe : p.bite_cap_prey;  // ECO:812-814
+            const double rem = pe - bite;
+            const double en = S.E[0][slot] + bite;
+            __syncwarp();
+            S.E[0][slot] = en;
+            S.map[0][cell] = (MapT)(slot + 1);  // ECO:817
+            S.flg[0][slot] |= F_ATE;
+            if (rem > 0.0) {  // carcass (ECO:826-845)
+              S.E[1][q] = rem;
+              S.map[1][cell] = (MapT)(q + 1);
+              if (qf & F_DIED) h.status |= PPG_STATUS_GHOST_CELL;  // aged out this step: the reference keeps a stale grid value
+              S.flg[1][q] = (uint8_t)(qf | F_CARC);
+              __syncwarp();
+            } else {  // fully eaten (ECO:846-866); its observation is captured now
+              __syncwarp();
+              rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[1] + (size_t)(old_base[1] + q) * p.elems[1], cell, 1, n[0], n[1], rowctr,
+                                                       lane, speed_plane(p, X.spd[1][q]));
+              __syncwarp();
+              S.map[1][cell] = 0;
+              S.flg[1][q] = (uint8_t)((qf & F_ATE) | F_DIED | F_CAUGHT);
+              eh.active[1] -= 1;  // also for a prey that already starved or aged out this step (quirk 4)
+              st_eaten++;
+              __syncwarp();
+            }
+          }
+        }
+        for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 0;
+        __syncwarp();
+      }
+
+      // Step 6: reproduction, predators then prey, snapshot order (ECO:353-367,1092-1275).  If the episode may end on this
+      // step the newborn rows are written at birth (ECO:1179 stays in self.observations, ECO:417-420).
+      const bool maybe_done = eh.active[0] <= 0 || eh.active[1] <= 0;
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        for (int b0 = 0; b0 < SEL(n); b0 += 32) {
+          const int k = b0 + lane;
+          bool elig = false;
+          if (k < SEL(n)) {
+            const unsigned f = SEL(S.flg)[k];
+            elig = (f & F_ALIVE) && !(f & F_CARC) && SEL(S.E)[k] >= p.thr[s];
+          }
+          unsigned m = __ballot_sync(FULL, elig);
+          while (m) {
+            const int ps_slot = b0 + __ffs(m) - 1;
+            m &= m - 1;
+            if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) { h.status |= PPG_STATUS_ID_POOL_EMPTY; continue; }  // ECO:1104-1111
+            if (SEL(n) + SEL(births) >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
+            // mutate_genome (GENOME:49-59): the draws precede the spawn search (ECO:1119 before :1136)
+            double spd = SEL(X.spd)[ps_slot];
+            if (p.genome_enabled && p.mut_rate > 0 && p.mut_std > 0) {
+              double u, d;
+              if (!take_real(p, eh, h, u)) u = ppg_draw_u01(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &eh.trait_draws);
+              if (u < p.mut_rate) {
+                if (!take_real(p, eh, h, d)) d = p.mut_std * ppg_draw_normal(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &eh.trait_draws);
+                const double v = spd + d;
+                spd = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
+              }
+            }
+            const unsigned pp = SEL(S.pos)[ps_slot];
+            const int px = pp >> 8, py = pp & 255;
+            int nl[2] = {n[0] + births[0], n[1] + births[1]};
+            int sx = -1, sy = -1;  // _find_available_spawn_position (ECO:732-764)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cx = px + (c == 0 ? -1 : (c == 1 ? 1 : 0));
+              const int cy = py + (c == 2 ? -1 : (c == 3 ? 1 : 0));
+              if (sx < 0 && cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
+              }
+            }
+            if (sx < 0) {
+              st_fallback++;
+              if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
+                const int c = p.tape_cells[h.tape_pos++];
+                sx = c / G; sy = c % G;
+              } else {
+                if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+                const int c = philox_free_cell<MapT>(sbase, p, nl[0], nl[1],
+                                                     ppg_draw_u32(h.seed_key, genv, h.episode, PPG_STREAM_SPAWN, h.spawn_draws), lane);
+                if (c >= 0) { h.spawn_draws++; sx = c >> 8; sy = c & 255; }
+              }
+              if (sx < 0) { h.status |= PPG_STATUS_NO_SPAWN_CELL; continue; }  // reference raises RuntimeError (ECO:1142-1143)
+            }
+            const int cs = SEL(n) + SEL(births);
+            if (s == 0) births[0]++; else births[1]++;
+            const int child_id = s == 0 ? h.next_idx[0]++ : h.next_idx[1]++;  // smallest never-used id (ECO:260-272)
+            const double pe = SEL(S.E)[ps_slot] - p.init_e[s];                // ECO:1150
+            __syncwarp();
+            SEL(S.id)[cs] = (uint16_t)child_id;
+            SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
+            SEL(S.E)[cs] = p.init_e[s];
+            SEL(S.flg)[cs] = (uint8_t)(F_ALIVE | F_NEWBORN | (maybe_done ? F_BORNROW : 0));
+            SEL(X.age)[cs] = 0;
+            SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
+            SEL(X.spd)[cs] = p.genome_enabled ? spd : -1.0;
+            SEL(S.E)[ps_slot] = pe;
+            SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // ECO:1154
+            SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // ECO:1155
+            SEL(S.flg)[ps_slot] |= F_REPRO;
+            eh.next_seq++;
+            if (s == 0) eh.active[0] += 1; else eh.active[1] += 1;  // ECO:1157
+            __syncwarp();
+            if (maybe_done) {
+              if (!have_new_base) {
+                int nb0 = 0, nb1 = 0;
+                if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+                  if (lane == 0) atomicOr(p.error, 1u);
+                }
+                new_base[0] = n_old_total[0] + nb0;
+                new_base[1] = n_old_total[1] + nb1;
+                have_new_base = true;
+              }
+              rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[s] + (size_t)(SEL(new_base) + cs - SEL(n)) * p.elems[s], CELLXY(sx, sy), s,
+                                                       n[0] + births[0], n[1] + births[1], rowctr, lane, speed_plane(p, SEL(X.spd)[cs]));
+              __syncwarp();
+            }
+          }
+        }
+      }
+      __syncwarp();
+
+      // Step 7: episode end (ECO:392), time limit (ECO:452)
+      done = eh.active[1] <= 0 || eh.active[0] <= 0;
+      h.step += 1;
+      trunc = !done && h.step >= p.max_steps;
+      over = done || trunc;
+      env_flags = (done ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
+      if (over) {
+        if (p.autoreset) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          int c = 0;
+          for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
+          next_live[s] = __reduce_add_sync(FULL, c);
+        }
+      }
+    } else {
+      env_flags = PPG_ENV_IDLE;
+    }
+
+    publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+
+    // ------------------------------------------------- rows: metadata, observations, state write-back
+    if (lane == 0) {
+      p.old_off[0][env] = old_base[0];
+      p.old_off[1][env] = old_base[1];
+    }
+    if (mode != 0) {
+      const bool keep = !(over && p.autoreset);
+      refresh_tables(S, p, n[0] + births[0], n[1] + births[1], lane);
+      int wpos[2] = {0, 0};
+      for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
+        if (pass == 1) {
+          if (births[0] + births[1] == 0) break;
+          if (!have_new_base) {
+            int nb0 = 0, nb1 = 0;
+            if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+              if (lane == 0) atomicOr(p.error, 1u);
+            }
+            new_base[0] = n_old_total[0] + nb0;
+            new_base[1] = n_old_total[1] + nb1;
+          }
+        }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          const size_t sb = (size_t)env * p.cap[s];
+          float* obs_s = p.obs[s];
+          const int elems = p.elems[s];
+          const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
+          if (k_lo >= tot) continue;
+          const RowRel rr = load_rel(p, s, sb32, lane);
+          for (int b0 = k_lo; b0 < tot; b0 += 32) {
+            const int slot = b0 + lane;
+            int row = 0, cellp = 0;
+            bool alive = false, emit = false;
+            float sv = 0.f;
+            if (slot < tot) {
+              const bool newborn = slot >= SEL(n);
+              row = newborn ? SEL(new_base) + (slot - SEL(n)) : SEL(old_base) + slot;
+              const unsigned f = SEL(S.flg)[slot];
+              alive = (f & F_ALIVE) != 0;
+              double rew = 0.0;
+              if (mode == 2 && !newborn) {
+                if (f & F_DIED) rew = (f & F_CAUGHT) ? p.pen_caught : 0.0;  // ECO:772,851 (aged out: rewards.get -> 0, ECO:1072)
+                else {
+                  rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);
+                  if (f & F_REPRO) rew = p.r_repro[s];  // ECO:1161 overwrites
+                }
+              }
+              unsigned rf = 0;
+              if ((f & F_DIED) || (alive && done)) rf |= PPG_ROW_TERMINATED;  // ECO:393-398
+              if (alive && trunc) rf |= PPG_ROW_TRUNCATED;                    // ECO:452-472
+              if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
+              if (mode == 1) rf |= PPG_ROW_FOUNDER;
+              if (f & F_ATE) rf |= PPG_ROW_ATE;
+              if (alive && (f & F_CARC)) rf |= PPG_ROW_CARCASS;
+              p.row_env[s][row] = env;
+              p.row_agent[s][row] = SEL(S.id)[slot];
+              p.reward[s][row] = (float)rew;
+              p.flags[s][row] = (uint8_t)rf;
+              cellp = CELLP((unsigned)SEL(S.pos)[slot]);
+              emit = alive && !(done && (f & F_BORNROW));  // a newborn of the episode's last step keeps its at-birth observation
+              sv = speed_plane(p, SEL(X.spd)[slot]);
+            }
+            const unsigned ma = __ballot_sync(FULL, alive);
+            if (keep && alive) {
+              const int dst = SEL(wpos) + __popc(ma & lt_mask);
+              p.ag_id[s][sb + dst] = SEL(S.id)[slot];
+              p.ag_pos[s][sb + dst] = SEL(S.pos)[slot];
+              p.ag_e[s][sb + dst] = SEL(S.E)[slot];
+              p.ag_prow[s][sb + dst] = row;
+              p.ag_age[s][sb + dst] = SEL(X.age)[slot];
+              p.ag_seq[s][sb + dst] = SEL(X.seq)[slot];
+              p.ag_spd[s][sb + dst] = SEL(X.spd)[slot];
+              p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
+            }
+            if (s == 0) wpos[0] += __popc(ma); else wpos[1] += __popc(ma);
+            unsigned m = __ballot_sync(FULL, emit);
+            while (m) {
+              const int l = __ffs(m) - 1;
+              m &= m - 1;
+              const int cp = __shfl_sync(FULL, cellp, l);
+              const int r = __shfl_sync(FULL, row, l);
+              const float selfv = __shfl_sync(FULL, sv, l);
+              emit_row<MapT, false, true>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane, selfv);
+            }
+          }
+        }
+      }
+      if (lane < 2) {
+        const int nb = lane == 0 ? births[0] : births[1];
+        p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
+        p.new_cnt[lane][env] = nb;
+      }
+      // leave the maps empty for the next env of this warp.  A carcass bitten after it aged out keeps an entry while its
+      // owner is gone, so every loaded slot is un-written, alive or not.
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        for (int i = lane; i < n[s] + births[s]; i += 32) S.map[s][CELLP((unsigned)S.pos[s][i])] = 0;
+      for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
+      if (keep) {
+        h.n_list[0] = (unsigned short)wpos[0];
+        h.n_list[1] = (unsigned short)wpos[1];
+        const size_t gb = (size_t)env * p.n_grass;
+        for (int g = lane; g < p.n_grass; g += 32) {
+          p.gr_e[gb + g] = S.gE[g];
+          if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
+        }
+      }
+      if (over) h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;
+      if (lane == 0) { p.hdr[env] = h; p.ehdr[env] = eh; }
+      if (lane < PPG_N_STATS) {
+        unsigned add = 0;
+        if (mode == 2) {
+          switch (lane) {
+            case PPG_STAT_ENV_STEPS: add = 1; break;
+            case PPG_STAT_AGENT_STEPS: add = n[0] + n[1]; break;
+            case PPG_STAT_EPISODES: add = over; break;
+            case PPG_STAT_EPISODE_STEPS: add = over ? h.step : 0; break;
+            case PPG_STAT_BIRTHS_PRED: add = births[0]; break;
+            case PPG_STAT_BIRTHS_PREY: add = births[1]; break;
+            case PPG_STAT_STARVED_PRED: add = st_starved[0]; break;
+            case PPG_STAT_STARVED_PREY: add = st_starved[1]; break;
+            case PPG_STAT_EATEN_PREY: add = st_eaten; break;
+            case PPG_STAT_GRASS_EATEN: add = st_grass; break;
+            case PPG_STAT_TRUNCATED: add = trunc; break;
+            case PPG_STAT_SPAWN_FALLBACK: add = st_fallback; break;
+            default: break;
+          }
+        }
+        if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
+        if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
+        if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
+      }
+    } else if (lane < 2) {
+      p.new_off[lane][env] = 0;
+      p.new_cnt[lane][env] = 0;
+    }
+    if (lane == 0) {
+      p.env_flags[env] = (uint8_t)env_flags;
+      p.env_status[env] = h.status;
+      p.env_step[env] = h.step;
+      p.env_count[2 * env] = eh.active[0];
+      p.env_count[2 * env + 1] = eh.active[1];
+    }
+    __syncwarp();
+  }
+}
+
+// reals cursor of the replay tape
+__global__ void ppg_set_tape_reals_kernel(EcoHdr* ehdr, int B, const long long* real_off) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  ehdr[e].real_pos = real_off ? real_off[e] : 0;
+  ehdr[e].real_end = real_off ? real_off[e + 1] : 0;
+}
+
+template <typename MapT>
+static cudaError_t launch_eco_t(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_bytes = smem;
+  }
+  ppg_step_eco_kernel<1, MapT><<<n_cta, 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
+  return p.map_bytes == 1 ? launch_eco_t<uint8_t>(p, n_cta, smem, stream) : launch_eco_t<uint16_t>(p, n_cta, smem, stream);
+}
+
+cudaError_t step_eco_occupancy(int map_bytes, size_t smem, int* blocks_per_sm) {
+  if (map_bytes == 1) {
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, uint8_t>, 32, smem);
+  }
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, uint16_t>, 32, smem);
+}
+
+cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s) {
+  ppg_set_tape_reals_kernel<<<(B + 255) / 256, 256, 0, s>>>(ehdr, B, real_off);
+  return cudaGetLastError();
+}
+
+}  // namespace ppg

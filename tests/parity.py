@@ -37,7 +37,14 @@ def compare_outputs(g, o, where="", obs_rtol=0.0, reward_rtol=0.0):
 
 
 def compare_env_state(gpu, oracle, env, where=""):
-    a, b = gpu.read_env(env), oracle.read_env(env)
+    eco = gpu.cfg.variant == 1
+    a, b = (gpu.read_env_eco(env), oracle.read_env_eco(env)) if eco else (gpu.read_env(env), oracle.read_env(env))
+    if eco:
+        for s in range(2):
+            assert np.array_equal(a["age"][s], b["age"][s]), (where, env, s, a["age"][s], b["age"][s])
+            assert np.array_equal(a["speed"][s], b["speed"][s]), (where, env, s)
+        assert np.array_equal(a["dead_prey"], b["dead_prey"]), (where, env)
+        assert np.array_equal(a["active_num"], b["active_num"]), (where, env)
     for s in range(2):
         assert np.array_equal(a["ids"][s], b["ids"][s]), (where, env, s, a["ids"][s], b["ids"][s])
         assert np.array_equal(a["xy"][s], b["xy"][s]), (where, env, s)
@@ -46,7 +53,7 @@ def compare_env_state(gpu, oracle, env, where=""):
     assert np.array_equal(a["grass_energy"], b["grass_energy"]), (where, env)
 
 
-def lockstep_parity(cfg, n_envs, steps, *, tape=None, seeds=None, action_seed=1234, threads=8, state_envs=(0,),
+def lockstep_parity(cfg, n_envs, steps, *, tape=None, reals=None, seeds=None, action_seed=1234, threads=8, state_envs=(0,),
                     check_every=1, device=0):
     """Run both sides for `steps` steps with identical Philox-keyed random actions; compare every
     `check_every` steps (always the last).  Returns the oracle's stats dict for reporting."""
@@ -60,8 +67,8 @@ def lockstep_parity(cfg, n_envs, steps, *, tape=None, seeds=None, action_seed=12
     ora = Oracle(cfg, n_envs, threads=threads)
     try:
         if tape is not None:
-            gpu.load_tape(tape)
-            ora.load_tape(tape)
+            gpu.load_tape(tape, reals)
+            ora.load_tape(tape, reals)
         gpu.reset(seeds)
         ora.reset(seeds)
         compare_outputs(gpu.outputs_numpy(), ora.outputs(), "reset")
