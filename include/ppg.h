@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 3
+#define PPG_ABI_VERSION 4
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -143,7 +143,45 @@ typedef struct ppg_config {
   double mutation_std;
   double speed_bounds[2];         /* "trait_bounds"["speed"] (genome.py:37-39); also the observation normalisation (ECO:113-115) */
   double speed_distance_threshold;/* ECO:109,551-557 */
+  /* ---- STAG (stag_hunt_forward_view_nature_nurture/config/config_env_stag_hunt_forward_view.py:1-105; STAG:19-266).
+   * Ignored by the other variants.  Index [t] = agent type t+1 (`type_1_*`, `type_2_*`); for STAG n_possible[s] /
+   * n_initial[s] above hold the sums over both types and a numeric agent id is FLAT: `type_1_<species>_k` -> k,
+   * `type_2_<species>_k` -> n_possible_t[s][0] + k (STAG:1768-1782 lists possible_agents in exactly this order).
+   * Species 1 holds both prey types (type 1 = mammoth, type 2 = rabbit: STAG:112-117 channels 2 and 3). ---- */
+  int32_t n_possible_t[2][2];      /* "n_possible_type_{t}_predators", "n_possible_type_{t}_prey" (STAG:26-29) */
+  int32_t n_initial_t[2][2];       /* "n_initial_active_type_{t}_predator", "..._prey" (STAG:31-34,373-380) */
+  int32_t type_action_range[2];    /* "type_1_action_range", "type_2_action_range" (STAG:178-193): moves a -> (a / R - d, a % R - d) */
+  int32_t team_capture_equal_split;/* STAG:132 */
+  int32_t coop_trait_enabled;      /* STAG:139 */
+  int32_t team_capture_success_model; /* PPG_CAPTURE_* (STAG:153-155) */
+  int32_t strict_rllib_output;     /* STAG:126; output assembly (STAG:562-580): when 0 the rewards of agents that ended
+                                    * this step (their death penalty) are dropped (STAG:577,609) */
+  double energy_loss_prey_t[2];        /* "energy_loss_per_step_prey"[type] (STAG:75-83) */
+  double creation_threshold_prey_t[2]; /* "energy_treshold_creation_prey"[type] (STAG:58-73) */
+  double initial_energy_prey_t[2];     /* "initial_energy_prey"[type] (STAG:38-53) */
+  double bite_size_prey_t[2];          /* "bite_size_prey"[type] (STAG:84-97,1459-1465) */
+  double reproduction_reward_t[2][2];  /* "reproduction_reward_predator"/"_prey" by type (STAG:103-104,2052-2059) */
+  double death_penalty[3];             /* predator, type_1_prey, type_2_prey (STAG:98-100,1999-2006) */
+  double team_capture_margin;          /* STAG:131,1118 */
+  double team_capture_join_cost;       /* STAG:133 */
+  double team_capture_scavenger_fraction; /* STAG:134-135 */
+  double team_capture_nature_weight;   /* STAG:147-148,1133 */
+  double team_capture_base_success_p0; /* STAG:156-157,1137 */
+  double team_capture_force_success_ratio; /* STAG:158-159,1139 */
+  double team_capture_min_success_prob;    /* STAG:160-161,1138 */
+  double coop_trait_init_mean;         /* STAG:140,1087 */
+  double coop_trait_init_std;          /* STAG:141 */
+  double coop_trait_mutation_std;      /* STAG:142,1095-1096 */
+  double coop_trait_mutation_rate;     /* STAG:143-144 */
 } ppg_config;
+
+/* ppg_config.team_capture_success_model (STAG:1141-1148) */
+enum { PPG_CAPTURE_DETERMINISTIC = 0, PPG_CAPTURE_PROBABILISTIC = 1, PPG_CAPTURE_HYBRID = 2 };
+
+/* STAG predator action = MultiDiscrete([n_moves, 2]) (STAG:1813-1816) packed into one int32:
+ * move | join_hunt << 8  (`_split_action`, STAG:771-799).  Prey: move only. */
+#define PPG_STAG_JOIN_SHIFT 8
+#define PPG_STAG_ACTION(move, join) ((int32_t)(move) | ((int32_t)((join) != 0) << PPG_STAG_JOIN_SHIFT))
 
 /*
  * Replay tape: the random draws of the reference, captured from its numpy RNG, consumed by the
@@ -155,6 +193,13 @@ typedef struct ppg_config {
  *   reals: unused by BASE.  ECO: per reset the founders' speeds in `self.agents` order (predators,
  *          prey; genome.py:42-46, only if genome_enabled), then per birth `u = rng.random()` and,
  *          iff u < mutation_rate, `delta = rng.normal(0, std)` (genome.py:56-58).
+ *   STAG cells: reset — the cells (predators, prey, grass; STAG:2140-2148), then one facing index 0..7 per founder
+ *          predator (`_predator_facing_options`, STAG:197-206,941,2168); then in consumption order the cell of each
+ *          spawn-fallback draw (STAG:1039-1042) and the facing index of each newborn predator (STAG:1559).
+ *   STAG reals: reset — the founders' cooperation traits BEFORE clipping (`rng.normal(mean, std)`, STAG:1087; only if
+ *          coop_trait_enabled); then per predator birth `u = rng.random()` (iff mutation_std > 0) and, iff
+ *          u < mutation_rate, `delta = rng.normal(0, std)` (STAG:1095-1096); per capture attempt `u = rng.random()`
+ *          iff the success model draws (STAG:1146,1148: probabilistic always, hybrid unless force-success).
  * All pointers are HOST pointers; the call copies.  When a stream is exhausted the env sets
  * PPG_STATUS_TAPE_EXHAUSTED and continues on the Philox stream.
  */
@@ -205,7 +250,7 @@ enum {
   PPG_STAT_ROWS_PREY = 12,
   PPG_STAT_SPAWN_FALLBACK = 13,
   PPG_STAT_STATUS_ENVS = 14, /* envs with a non-zero status word right now */
-  PPG_STAT_RESERVED = 15
+  PPG_STAT_CAPTURE_ATTEMPTS = 15 /* STAG team_capture_attempts (STAG:1178); 0 for the other variants */
 };
 
 typedef struct ppg_handle_s* ppg_handle;
@@ -273,6 +318,15 @@ int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, 
  * active_num_predators/prey), in the list order of ppg_read_env.  Any pointer may be NULL. Synchronises. */
 int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                      double* speed_prey, uint8_t* dead_prey, int32_t* active_num);
+
+/* STAG extras of one env (STAG attributes agent_ages, predator_facing as an index into `_predator_facing_options`
+ * STAG:197-206, predator_cooperation_trait), in the list order of ppg_read_env, plus the team-capture counters
+ * capture[12] = {successes, failures, coop_successes, coop_failures, mammoth_successes, mammoth_failures,
+ * rabbit_successes, rabbit_failures, attempts, helper_total, spawned_predators, spawned_prey} (STAG:237-254) and
+ * capture_real[3] = {last_success_prob, last_effort_ratio, success_prob_sum} (STAG:249-251).  Any pointer may be NULL.
+ * Synchronises. */
+int ppg_read_env_stag(ppg_handle h, int32_t env, int32_t* age_pred, int32_t* facing_pred, double* trait_pred,
+                      int32_t* age_prey, int64_t* capture, double* capture_real);
 
 /* Device-side reduction of the per-env counters into PPG_N_STATS int64 values (host out).
  * Synchronises the stream. ppg_stats_device leaves them on the device for an NCCL all-reduce. */

@@ -21,7 +21,7 @@ class OracleBuffers(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(HERE, f) for f in ("ppg_oracle.c", "ppg_oracle_eco.c", "ppg_oracle.h", "ppg_oracle_int.h", "Makefile")]
+    src = [os.path.join(HERE, f) for f in ("ppg_oracle.c", "ppg_oracle_eco.c", "ppg_oracle_stag.c", "ppg_oracle.h", "ppg_oracle_int.h", "Makefile")]
     src += [os.path.join(HERE, "..", "include", f) for f in ("ppg.h", "ppg_philox.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-s"])
@@ -54,6 +54,8 @@ def lib():
         L.ppgo_env_reset_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_set_pow_libm.argtypes = [C.c_void_p, C.c_int32]
         L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
+        L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -140,6 +142,26 @@ class Oracle:
                                        sp[1].ctypes.data, dead.ctypes.data, act.ctypes.data) == 0
         st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]],
                   active_num=act)
+        return st
+
+    def env_reset_stag(self, env, cells, facing, trait_raw):
+        c = np.ascontiguousarray(cells, np.int32)
+        f = np.ascontiguousarray(facing if len(facing) else [0], np.int32)
+        t = np.ascontiguousarray(trait_raw if len(trait_raw) else [0.0], np.float64)
+        assert lib().ppgo_env_reset_stag(self.h, env, c.ctypes.data, f.ctypes.data, t.ctypes.data) == 0
+        return self.outputs()
+
+    def read_env_stag(self, env):
+        st = self.read_env(env)
+        n = (len(st["ids"][0]), len(st["ids"][1]))
+        age = [np.zeros(max(1, n[s]), np.int32) for s in range(2)]
+        face = np.zeros(max(1, n[0]), np.int32)
+        trait = np.zeros(max(1, n[0]), np.float64)
+        cap = np.zeros(12, np.int64)
+        capr = np.zeros(3, np.float64)
+        assert lib().ppgo_read_env_stag(self.h, env, age[0].ctypes.data, face.ctypes.data, trait.ctypes.data, age[1].ctypes.data,
+                                        cap.ctypes.data, capr.ctypes.data) == 0
+        st.update(age=(age[0][: n[0]], age[1][: n[1]]), facing=face[: n[0]], trait=trait[: n[0]], capture=cap, capture_real=capr)
         return st
 
     def reset(self, seeds=None, mask=None):

@@ -97,10 +97,12 @@ static void env_alloc(env_t* e, const ppg_config* c, int env_index, int32_t* con
   e->seed_key = c->seed;
   e->idle = 1; /* not reset yet */
   if (c->variant == PPG_VARIANT_ECO) eco_env_alloc(e);
+  if (c->variant == PPG_VARIANT_STAG) stag_env_alloc(e);
 }
 
 static void env_free(env_t* e) {
   if (e->c->variant == PPG_VARIANT_ECO) eco_env_free(e);
+  if (e->c->variant == PPG_VARIANT_STAG) stag_env_free(e);
   free(e->carcass); free(e->born_obs);
   for (int s = 0; s < 2; ++s) {
     free(e->present[s]); free(e->x[s]); free(e->y[s]); free(e->energy[s]); free(e->parent[s]);
@@ -186,6 +188,7 @@ static void env_reset_cells(env_t* e, const int32_t* cells) {
 static void env_reset_auto(env_t* e) {
   const ppg_config* c = e->c;
   if (c->variant == PPG_VARIANT_ECO) { eco_env_reset_auto(e); return; }
+  if (c->variant == PPG_VARIANT_STAG) { stag_env_reset_auto(e); return; }
   const int n_total = c->n_initial[0] + c->n_initial[1] + c->n_grass;
   const int ncell = e->G * e->G;
   int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_total);
@@ -274,6 +277,7 @@ static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id
                     int lockstep) {
   const ppg_config* c = e->c;
   if (c->variant == PPG_VARIANT_ECO) return eco_env_step(e, n_act, a_s, a_id, a_val);
+  if (c->variant == PPG_VARIANT_STAG) return stag_env_step(e, n_act, a_s, a_id, a_val);
   const int mode = c->reward_mode;
   const int dense = (mode == PPG_REWARD_DENSE || mode == PPG_REWARD_DENSE_ADDITIVE);
   e->env_flags = 0;
@@ -498,7 +502,7 @@ static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id
 
 /* finish the call: self.agents.sort() (BASE:468), after the rows have been exported */
 static void env_sort_agents(env_t* e) {
-  if (e->c->variant == PPG_VARIANT_ECO) return; /* ECO never sorts self.agents */
+  if (e->c->variant != PPG_VARIANT_BASE) return; /* ECO and STAG never sort self.agents */
   /* insertion sort keeps it dependency-free (qsort_r is a GNU extension) */
   for (int i = 1; i < e->n_agents; ++i) {
     int32_t k = e->agents[i];
@@ -513,7 +517,8 @@ static void env_sort_agents(env_t* e) {
 /* ------------------------------------------------------------------------------------------ */
 ppgo_batch* ppgo_create(const ppg_config* cfg, int32_t n_envs) {
   if (!cfg || cfg->struct_size != sizeof(ppg_config) || n_envs <= 0) return NULL;
-  if (cfg->variant != PPG_VARIANT_BASE && cfg->variant != PPG_VARIANT_ECO) return NULL;
+  if (cfg->variant != PPG_VARIANT_BASE && cfg->variant != PPG_VARIANT_ECO && cfg->variant != PPG_VARIANT_STAG) return NULL;
+  if (cfg->n_possible[0] > 65535 || cfg->n_possible[1] > 65535) return NULL;
   if (cfg->n_initial[0] + cfg->n_initial[1] + cfg->n_grass > cfg->grid_size * cfg->grid_size) return NULL; /* BASE:167 */
   ppgo_batch* b = (ppgo_batch*)calloc(1, sizeof *b);
   b->cfg = *cfg;
@@ -766,6 +771,13 @@ int ppgo_random_actions(ppgo_batch* b, uint64_t seed, int32_t* actions_pred, int
     for (int32_t row = 0; row < n; ++row) {
       uint32_t env = (uint32_t)(b->out.f.row_env[s][row] + b->cfg.env_index_base), id = (uint32_t)b->out.f.row_agent[s][row];
       uint32_t r = ppg_draw_u32(seed, env, (uint32_t)b->calls, PPG_STREAM_ACTION + 8u * (uint32_t)s, id);
+      if (b->cfg.variant == PPG_VARIANT_STAG) { /* MultiDiscrete([n_moves, 2]) for predators, Discrete(n_moves) for prey (STAG:1802-1816) */
+        const int R = b->cfg.type_action_range[(int)id >= b->cfg.n_possible_t[s][0]];
+        const uint32_t mv = ppg_bounded(r, (uint32_t)(R > 0 ? R * R : 1));
+        const uint32_t jn = s == 0 ? (ppg_draw_u32(seed, env, (uint32_t)b->calls, PPG_STREAM_ACTION + 16u, id) & 1u) : 0u;
+        act[s][row] = (int32_t)(mv | (jn << PPG_STAG_JOIN_SHIFT));
+        continue;
+      }
       act[s][row] = (int32_t)ppg_bounded(r, (uint32_t)(b->cfg.variant == PPG_VARIANT_ECO ? b->cfg.action_range * b->cfg.action_range : 9));
     }
   }
@@ -791,6 +803,17 @@ int ppgo_read_env(ppgo_batch* b, int32_t env, int32_t* n_live, int32_t* ids_pred
   int32_t* ids[2] = {ids_pred, ids_prey};
   int32_t* xy[2] = {xy_pred, xy_prey};
   double* en[2] = {energy_pred, energy_prey};
+  if (b->cfg.variant == PPG_VARIANT_STAG) { /* agent_positions insertion order = self.agents order (flat ids are not monotonic) */
+    n_live[0] = n_live[1] = 0;
+    for (int i = 0; i < v->n_agents; ++i) {
+      const int s = KEY_S(v->agents[i]), id = KEY_ID(v->agents[i]);
+      if (!v->present[s][id]) continue;
+      const int n = n_live[s]++;
+      if (ids[s]) ids[s][n] = id;
+      if (xy[s]) { xy[s][2 * n] = v->x[s][id]; xy[s][2 * n + 1] = v->y[s][id]; }
+      if (en[s]) en[s][n] = v->energy[s][id];
+    }
+  } else
   for (int s = 0; s < 2; ++s) {
     int n = 0;
     for (int id = 0; id < v->next_idx[s]; ++id) /* agent_positions insertion order = id order */
@@ -812,7 +835,7 @@ int ppgo_read_env(ppgo_batch* b, int32_t env, int32_t* n_live, int32_t* ids_pred
 int ppgo_read_grid(ppgo_batch* b, int32_t env, double* grid_out) {
   if (env < 0 || env >= b->n_envs) return PPG_ERR_INVALID;
   env_t* v = &b->envs[env];
-  if (b->cfg.variant == PPG_VARIANT_ECO) { eco_read_grid(v, grid_out); return PPG_OK; }
+  if (b->cfg.variant != PPG_VARIANT_BASE) { eco_read_grid(v, grid_out); return PPG_OK; }
   memcpy(grid_out, v->grid, sizeof(double) * (size_t)v->C * v->G * v->G);
   return PPG_OK;
 }
@@ -849,6 +872,37 @@ int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* spe
       }
   }
   if (active_num) { active_num[0] = v->active[0]; active_num[1] = v->active[1]; }
+  return PPG_OK;
+}
+
+/* ---- STAG extras ---- */
+int ppgo_env_reset_stag(ppgo_batch* b, int32_t env, const int32_t* cells, const int32_t* facing, const double* trait_raw) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_STAG) return PPG_ERR_INVALID;
+  for (int e = 0; e < b->n_envs; ++e) if (e != env) b->envs[e].n_rows = 0;
+  b->envs[env].episode += 1;
+  b->envs[env].trait_draws = 0;
+  stag_env_reset_explicit(&b->envs[env], cells, facing, trait_raw);
+  export_rows(b);
+  return PPG_OK;
+}
+
+int ppgo_read_env_stag(ppgo_batch* b, int32_t env, int32_t* age_pred, int32_t* facing_pred, double* trait_pred,
+                       int32_t* age_prey, int64_t* capture, double* capture_real) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_STAG) return PPG_ERR_INVALID;
+  env_t* v = &b->envs[env];
+  int n[2] = {0, 0};
+  for (int i = 0; i < v->n_agents; ++i) {
+    const int s = KEY_S(v->agents[i]), id = KEY_ID(v->agents[i]);
+    if (!v->present[s][id]) continue;
+    const int k = n[s]++;
+    if (s == 0) {
+      if (age_pred) age_pred[k] = v->age[0][id];
+      if (facing_pred) facing_pred[k] = v->facing[id];
+      if (trait_pred) trait_pred[k] = v->trait[id];
+    } else if (age_prey) age_prey[k] = v->age[1][id];
+  }
+  if (capture) memcpy(capture, v->capture, sizeof v->capture);
+  if (capture_real) memcpy(capture_real, v->capture_real, sizeof v->capture_real);
   return PPG_OK;
 }
 

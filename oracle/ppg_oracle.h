@@ -73,6 +73,13 @@ void ppgo_set_pow_libm(ppgo_batch* b, int32_t on);
 int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                       double* speed_prey, uint8_t* dead_prey, int32_t* active_num);
 
+/* ---- STAG (ppg_oracle_stag.c) ---- */
+/* reset one env from explicit cells, founder facing indices and raw (unclipped) founder traits (STAG:2140,2168-2169) */
+int ppgo_env_reset_stag(ppgo_batch* b, int32_t env, const int32_t* cells, const int32_t* facing, const double* trait_raw);
+/* same layout as ppg_read_env_stag (include/ppg.h) */
+int ppgo_read_env_stag(ppgo_batch* b, int32_t env, int32_t* age_pred, int32_t* facing_pred, double* trait_pred,
+                       int32_t* age_prey, int64_t* capture, double* capture_real);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,14 @@ typedef struct env_t {
   int64_t real_pos, real_end;
   uint32_t trait_draws;
   int pow_libm;       /* 1: speed ** exponent through libm pow like CPython (golden pinning); 0: device semantics */
+  /* ---- STAG (ppg_oracle_stag.c) ---- */
+  int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
+  double* trait;      /* predator_cooperation_trait (STAG:230) */
+  uint8_t* join;      /* predator_join_intent of the running step: 0 / 1, 2 = no entry (defaults to True, STAG:1163) */
+  int next_idx_t[2][2]; /* head of the per-type id deques (STAG:2259-2291) */
+  int64_t capture[12];  /* team-capture counters in the order of ppg_read_env_stag (include/ppg.h) */
+  double capture_real[3];
+  uint32_t facing_draws, capture_draws;
 } env_t;
 
 struct ppgo_batch {
@@ -109,5 +117,13 @@ void eco_env_reset_auto(env_t* e);
 void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founder_speed);
 int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, const int32_t* a_val);
 void eco_read_grid(env_t* e, double* out);
+
+
+/* ---- STAG (ppg_oracle_stag.c) ---- */
+void stag_env_alloc(env_t* e);
+void stag_env_free(env_t* e);
+void stag_env_reset_auto(env_t* e);
+void stag_env_reset_explicit(env_t* e, const int32_t* cells, const int32_t* facing, const double* trait_raw);
+int stag_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, const int32_t* a_val);
 
 #endif

@@ -26,7 +26,7 @@ N_STATS = 16
 STAT_NAMES = [
     "env_steps", "agent_steps", "episodes", "episode_steps", "births_pred", "births_prey", "starved_pred",
     "starved_prey", "eaten_prey", "grass_eaten", "truncated", "rows_pred", "rows_prey", "spawn_fallback",
-    "status_envs", "reserved",
+    "status_envs", "capture_attempts",
 ]
 
 
@@ -79,6 +79,31 @@ class PpgConfig(C.Structure):
         ("mutation_std", C.c_double),
         ("speed_bounds", C.c_double * 2),
         ("speed_distance_threshold", C.c_double),
+        # ---- STAG ----
+        ("n_possible_t", (C.c_int32 * 2) * 2),
+        ("n_initial_t", (C.c_int32 * 2) * 2),
+        ("type_action_range", C.c_int32 * 2),
+        ("team_capture_equal_split", C.c_int32),
+        ("coop_trait_enabled", C.c_int32),
+        ("team_capture_success_model", C.c_int32),
+        ("strict_rllib_output", C.c_int32),
+        ("energy_loss_prey_t", C.c_double * 2),
+        ("creation_threshold_prey_t", C.c_double * 2),
+        ("initial_energy_prey_t", C.c_double * 2),
+        ("bite_size_prey_t", C.c_double * 2),
+        ("reproduction_reward_t", (C.c_double * 2) * 2),
+        ("death_penalty", C.c_double * 3),
+        ("team_capture_margin", C.c_double),
+        ("team_capture_join_cost", C.c_double),
+        ("team_capture_scavenger_fraction", C.c_double),
+        ("team_capture_nature_weight", C.c_double),
+        ("team_capture_base_success_p0", C.c_double),
+        ("team_capture_force_success_ratio", C.c_double),
+        ("team_capture_min_success_prob", C.c_double),
+        ("coop_trait_init_mean", C.c_double),
+        ("coop_trait_init_std", C.c_double),
+        ("coop_trait_mutation_std", C.c_double),
+        ("coop_trait_mutation_rate", C.c_double),
     ]
 
 
@@ -122,6 +147,8 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     BASE:22-61) into a PpgConfig."""
     cfg = dict(config or {})
     g = cfg.get
+    if variant == VARIANT_STAG:  # per-type dict values are read by _fill_stag
+        g = {k: v for k, v in cfg.items() if not isinstance(v, dict)}.get
     c = PpgConfig()
     c.struct_size = C.sizeof(PpgConfig)
     c.variant = variant
@@ -136,6 +163,7 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.n_initial[0] = g("n_initial_active_predator", g("n_initial_active_predators", 6))
     c.n_initial[1] = g("n_initial_active_prey", 8)
     c.n_grass = g("initial_num_grass", 25)
+    cap_live_given = cap_live is not None
     if cap_live is None:
         # enough for every cell of the grid to hold one agent of the species (the reference cannot
         # place a newborn without a free cell, BASE:754-766), bounded by the id pool
@@ -174,6 +202,8 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.speed_distance_threshold = 1.5
     if variant == VARIANT_ECO:
         _fill_eco(c, cfg)
+    if variant == VARIANT_STAG:
+        _fill_stag(c, cfg, cap_live_given)
     return c
 
 
@@ -232,6 +262,97 @@ def _fill_eco(c, cfg):
     lin = cfg.get("lineage_reward_coeff", 0.0)
     if any(float(_role(lin, r, 0.0) or 0.0) != 0.0 for r in ("predator", "prey")):
         raise ValueError("lineage_reward_coeff != 0 is not supported (ECO:943-991 lineage survival rewards)")
+
+
+CAPTURE_MODELS = {"deterministic": 0, "probabilistic": 1, "hybrid": 2}
+
+
+def _by_type(value, kind, default, fallback_key="type_1"):
+    """STAG per-type config values: a scalar applies to both types, a dict is keyed `type_1_<kind>` / `type_2_<kind>`
+    with the reference's own fallbacks (STAG:38-97)."""
+    if isinstance(value, dict):
+        return [float(value.get(f"type_{t}_{kind}", default)) for t in (1, 2)]
+    v = default if value is None else float(value)
+    return [v, v]
+
+
+def _fill_stag(c, cfg, cap_live_given):
+    """STAG `__init__` (STAG:19-266) — same keys, same defaults, same clamps."""
+    g = cfg.get
+    if g("manual_wall_positions") or g("num_walls", 0) and g("wall_placement_mode", "manual") != "manual":
+        raise ValueError("walls are not supported (STAG:2107-2127); the BASELINE stag_hunt config has none")
+    for k in ("mask_observation_with_visibility", "include_visibility_channel", "respect_los_for_movement"):
+        if g(k, False):
+            raise ValueError(f"{k} is not supported (line-of-sight masks, STAG:892-925,983-994)")
+    c.grid_size = g("grid_size", 0)
+    c.max_steps = g("max_steps", 0)
+    c.num_obs_channels = max(int(g("num_obs_channels", 0)), 5)  # STAG:118-119
+    c.obs_range[0], c.obs_range[1] = g("predator_obs_range", 0), g("prey_obs_range", 0)
+    for s, (poss, init) in enumerate((("n_possible_type_{}_predators", "n_initial_active_type_{}_predator"),
+                                      ("n_possible_type_{}_prey", "n_initial_active_type_{}_prey"))):
+        for t in (1, 2):
+            c.n_possible_t[s][t - 1] = int(g(poss.format(t), 0))
+            c.n_initial_t[s][t - 1] = int(g(init.format(t), 0))
+        c.n_possible[s] = c.n_possible_t[s][0] + c.n_possible_t[s][1]
+        c.n_initial[s] = c.n_initial_t[s][0] + c.n_initial_t[s][1]
+        if c.n_possible[s] > 65535:
+            raise ValueError("more than 65535 possible agents of one species")
+    if not cap_live_given:
+        cells = c.grid_size * c.grid_size
+        c.cap_live[0] = min(_round32(cells), _round32(c.n_possible[0]))
+        c.cap_live[1] = min(_round32(cells), _round32(c.n_possible[1]))
+    c.n_grass = g("initial_num_grass", 0)
+    c.type_action_range[0], c.type_action_range[1] = int(g("type_1_action_range", 0)), int(g("type_2_action_range", 0))
+    c.action_range = max(c.type_action_range[0], c.type_action_range[1])
+    c.energy_loss[0] = float(g("energy_loss_per_step_predator", 0.0))
+    loss = g("energy_loss_per_step_prey", 0.0)
+    c.energy_loss_prey_t[0], c.energy_loss_prey_t[1] = _by_type(loss, "prey", 0.0)
+    c.energy_loss[1] = c.energy_loss_prey_t[0]
+    c.creation_threshold[0] = float(g("energy_treshold_creation_predator", g("predator_creation_energy_threshold", 0.0)))
+    thr = g("energy_treshold_creation_prey", None)
+    if thr is None:
+        thr = g("prey_creation_energy_threshold", 0.0)
+    c.creation_threshold_prey_t[0], c.creation_threshold_prey_t[1] = _by_type(thr, "prey", 0.0)
+    c.creation_threshold[1] = c.creation_threshold_prey_t[0]
+    c.initial_energy[0] = float(g("initial_energy_predator", 0.0))
+    c.initial_energy_prey_t[0], c.initial_energy_prey_t[1] = _by_type(g("initial_energy_prey", 0.0), "prey", 0.0)
+    c.initial_energy[1] = c.initial_energy_prey_t[0]
+    c.bite_size_prey_t[0], c.bite_size_prey_t[1] = _by_type(g("bite_size_prey", float("inf")), "prey", float("inf"))
+    c.death_penalty[0] = float(g("death_penalty_predator", 0.0))
+    c.death_penalty[1] = float(g("death_penalty_type_1_prey", 0.0))
+    c.death_penalty[2] = float(g("death_penalty_type_2_prey", 0.0))
+    for s, (key, kind) in enumerate((("reproduction_reward_predator", "predator"), ("reproduction_reward_prey", "prey"))):
+        v = g(key, 0.0)
+        if isinstance(v, dict):  # `_get_type_specific` (STAG:2052-2059): first key the agent id starts with, else KeyError
+            for t in (1, 2):
+                hit = [val for k, val in v.items() if f"type_{t}_{kind}_0".startswith(k)]
+                if not hit and c.n_possible_t[s][t - 1] > 0:
+                    raise KeyError(f"Type-specific key 'type_{t}_{kind}' not found under '{key}'")
+                c.reproduction_reward_t[s][t - 1] = float(hit[0]) if hit else 0.0
+        else:
+            c.reproduction_reward_t[s][0] = c.reproduction_reward_t[s][1] = float(v)
+        c.reproduction_reward[s] = c.reproduction_reward_t[s][0]
+    clamp = lambda v, lo, hi: min(max(float(v), lo), hi)  # noqa: E731
+    c.team_capture_margin = float(g("team_capture_margin", 0.0))
+    c.team_capture_equal_split = 1 if g("team_capture_equal_split", False) else 0
+    c.team_capture_join_cost = max(0.0, float(g("team_capture_join_cost", 0.0)))
+    c.team_capture_scavenger_fraction = clamp(g("team_capture_scavenger_fraction", 0.0), 0.0, 1.0)
+    c.coop_trait_enabled = 1 if g("coop_trait_enabled", True) else 0
+    c.coop_trait_init_mean = float(g("coop_trait_init_mean", 0.6))
+    c.coop_trait_init_std = max(0.0, float(g("coop_trait_init_std", 0.12)))
+    c.coop_trait_mutation_std = max(0.0, float(g("coop_trait_mutation_std", 0.04)))
+    c.coop_trait_mutation_rate = clamp(g("coop_trait_mutation_rate", 1.0), 0.0, 1.0)
+    c.team_capture_nature_weight = clamp(g("team_capture_nature_weight", 0.75), 0.0, 1.0)
+    c.team_capture_success_model = CAPTURE_MODELS.get(str(g("team_capture_success_model", "hybrid")).lower(), 2)
+    c.team_capture_base_success_p0 = clamp(g("team_capture_base_success_p0", 0.6), 1e-6, 1.0 - 1e-6)
+    c.team_capture_force_success_ratio = max(float(g("team_capture_force_success_ratio", 1.05)), 0.0)
+    c.team_capture_min_success_prob = clamp(g("team_capture_min_success_prob", 0.0), 0.0, 1.0)
+    c.strict_rllib_output = 1 if g("strict_rllib_output", False) else 0
+    c.max_energy_grass = float(g("max_energy_grass", float("inf")))
+    c.initial_energy_grass = float(g("initial_energy_grass", 0.0))
+    c.energy_gain_grass = float(g("energy_gain_per_step_grass", 0.0))
+    c.reward_predator_catch_prey = c.reward_prey_eat_grass = c.reward_predator_step = c.reward_prey_step = 0.0
+    c.penalty_prey_caught = 0.0
 
 
 # base_environment/config_env.py:1-38 — the BASELINE configs 1 and 2
@@ -310,4 +431,62 @@ ECO_CONFIG = {
     "verbose_decay": False,
     "verbose_reproduction": False,
     "debug_mode": False,
+}
+
+
+# stag_hunt_forward_view_nature_nurture/config/config_env_stag_hunt_forward_view.py:1-105 — BASELINE config 5
+STAG_CONFIG = {
+    "seed": 41,
+    "max_steps": 1000,
+    "strict_rllib_output": True,
+    "grid_size": 30,
+    "num_obs_channels": 5,
+    "predator_obs_range": 9,
+    "prey_obs_range": 9,
+    "type_1_action_range": 3,
+    "type_2_action_range": 3,
+    "reproduction_reward_predator": {"type_1_predator": 10.0, "type_2_predator": 0.0},
+    "reproduction_reward_prey": {"type_1_prey": 10.0, "type_2_prey": 10.0},
+    "death_penalty_predator": 0.0,
+    "death_penalty_type_1_prey": 0.0,
+    "death_penalty_type_2_prey": 0.0,
+    "energy_loss_per_step_predator": 0.08,
+    "energy_loss_per_step_prey": {"type_1_prey": 0.1, "type_2_prey": 0.01},
+    "energy_treshold_creation_predator": 10.0,
+    "energy_treshold_creation_prey": {"type_1_prey": 18.0, "type_2_prey": 2.7},
+    "initial_energy_predator": 4.0,
+    "initial_energy_prey": {"type_1_prey": 10.0, "type_2_prey": 1.5},
+    "bite_size_prey": {"type_1_prey": 3.0, "type_2_prey": 0.3},
+    "team_capture_margin": 0.0,
+    "team_capture_equal_split": True,
+    "team_capture_join_cost": 0.01,
+    "team_capture_scavenger_fraction": 0.2,
+    "coop_trait_enabled": True,
+    "coop_trait_init_mean": 0.6,
+    "coop_trait_init_std": 0.12,
+    "coop_trait_mutation_std": 0.04,
+    "coop_trait_mutation_rate": 1.0,
+    "team_capture_nature_weight": 0.75,
+    "team_capture_success_model": "hybrid",
+    "team_capture_base_success_p0": 0.6,
+    "team_capture_force_success_ratio": 1.05,
+    "team_capture_min_success_prob": 0.0,
+    "max_energy_grass": 3.0,
+    "n_possible_type_1_predators": 2000,
+    "n_possible_type_2_predators": 0,
+    "n_possible_type_1_prey": 1000,
+    "n_possible_type_2_prey": 2000,
+    "n_initial_active_type_1_predator": 10,
+    "n_initial_active_type_2_predator": 0,
+    "n_initial_active_type_1_prey": 10,
+    "n_initial_active_type_2_prey": 10,
+    "initial_num_grass": 100,
+    "initial_energy_grass": 3.0,
+    "energy_gain_per_step_grass": 0.08,
+    "mask_observation_with_visibility": False,
+    "include_visibility_channel": False,
+    "respect_los_for_movement": False,
+    "wall_placement_mode": "manual",
+    "num_walls": 0,
+    "manual_wall_positions": (),
 }

@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
+    if (mode != 2) {
+      // reset / idle envs know their counts up front (founders, no births): publish them before doing any work, so
+      // that later envs waiting for their newborn-row prefix never wait for a reset
+      if (mode == 1) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+      publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    }
 
     if (mode == 1) {  // PHASE: reset
       // ------------------------------------------------------------------ reset() (BASE:129-217)
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
     }
 
     // ---------------------------------------------------------------- publish the counts  // PHASE: publish
-    publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    if (mode == 2) publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
 
     // ------------------------------------------------- rows: metadata, observations, state write-back  // PHASE: rows pass1
     if (lane == 0) {

@@ -120,6 +120,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
+    if (mode != 2) {
+      // reset / idle envs know their counts up front (founders, no births): publish them before doing any work, so
+      // that later envs waiting for their newborn-row prefix never wait for a reset
+      if (mode == 1) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+      publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    }
     const unsigned genv = (unsigned)(env + p.env_base);
 
     if (mode == 1) {
@@ -144,17 +150,20 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           eh.real_pos += n_f;
         } else {
           if (p.tape_reals != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
-          // the polar method consumes a variable number of counters per draw: one lane, in founder order
+          // the polar method consumes a variable number of counters per draw; 32 attempts are evaluated at once and the
+          // accepted ones handed to the founders in counter order (same stream as sequential draws)
           unsigned ctr = eh.trait_draws;
-          if (lane == 0) {
-            for (int s = 0; s < 2; ++s)
-              for (int i = 0; i < p.n_init[s]; ++i) {
-                double v = p.f_mean[s];
-                if (p.f_std[s] > 0) v = p.f_mean[s] + p.f_std[s] * ppg_draw_normal(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &ctr);
-                SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
-              }
+#pragma unroll 1
+          for (int s = 0; s < 2; ++s) {
+            if (p.f_std[s] > 0) {
+              ctr = draw_normals_batched(SEL(X.spd), p.n_init[s], p.f_mean[s], p.f_std[s], p.sp_lo, p.sp_hi, h.seed_key, genv, h.episode,
+                                         PPG_STREAM_TRAIT, ctr, lane);
+            } else {
+              const double v = p.f_mean[s];
+              for (int i = lane; i < p.n_init[s]; i += 32) SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
+            }
           }
-          eh.trait_draws = __shfl_sync(FULL, ctr, 0);
+          eh.trait_draws = ctr;
         }
       }
       __syncwarp();
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       env_flags = PPG_ENV_IDLE;
     }
 
-    publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    if (mode == 2) publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
 
     // ------------------------------------------------- rows: metadata, observations, state write-back
     if (lane == 0) {

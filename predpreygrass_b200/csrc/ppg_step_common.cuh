@@ -323,6 +323,38 @@ __device__ __forceinline__ bool prefix_before(const unsigned long long* cnt, con
   }
 }
 
+// `count` draws of clip(mean + std * N(0,1), lo, hi) into out[0..count), bit-identical to `count` sequential
+// ppg_draw_normal calls on the stream (one Philox counter per polar attempt, accepted attempts go to the draws in
+// counter order), but with the 32 lanes evaluating 32 consecutive attempts at once.  Returns the advanced counter.
+static __device__ __noinline__ unsigned draw_normals_batched(double* out, int count, double mean, double std, double lo, double hi,
+                                                             unsigned long long seed_key, unsigned env, unsigned episode, unsigned stream,
+                                                             unsigned ctr, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  int got = 0;
+  while (got < count) {
+    const ppg_u32x4 r = ppg_philox4x32(env, episode, ctr + (unsigned)lane, stream, (unsigned)seed_key, (unsigned)(seed_key >> 32));
+    const double a = 2.0 * ppg_u01(r.v[0], r.v[1]) - 1.0, b = 2.0 * ppg_u01(r.v[2], r.v[3]) - 1.0;
+    const double q = a * a + b * b;
+    const bool acc = q < 1.0 && q > 1e-300;
+    const unsigned m = __ballot_sync(FULL, acc);
+    const int k = got + __popc(m & lt);
+    if (acc && k < count) {
+      const double v = mean + std * (a * PPG_SQRT(-2.0 * ppg_log(q) / q));
+      out[k] = v < lo ? lo : (v > hi ? hi : v);
+    }
+    const int cnt = __popc(m);
+    if (got + cnt >= count) {
+      ctr += __fns(m, 0, count - got) + 1u;  // position after the attempt that produced the last draw
+      got = count;
+    } else {
+      got += cnt;
+      ctr += 32u;
+    }
+  }
+  __syncwarp();
+  return ctr;
+}
+
 // reset(): n_total unique cells in draw order (law of BASE:156-177) from the env's Philox placement stream
 static __device__ __noinline__ void philox_placement(int* cells, unsigned* first, int n_total, int GG, unsigned env, unsigned episode,
                                               unsigned long long seed_key, int lane) {

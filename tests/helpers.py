@@ -33,6 +33,12 @@ def config_from_golden(cfg, **kw):
 
         kw.setdefault("cap_live", (cfg["n_possible_predators"], cfg["n_possible_prey"]))
         return make_config(cfg, variant=VARIANT_ECO, **kw)
+    if variant == "stag":
+        from predpreygrass_b200.config import VARIANT_STAG
+
+        kw.setdefault("cap_live", (cfg.get("n_possible_type_1_predators", 0) + cfg.get("n_possible_type_2_predators", 0),
+                                   cfg.get("n_possible_type_1_prey", 0) + cfg.get("n_possible_type_2_prey", 0)))
+        return make_config(cfg, variant=VARIANT_STAG, **kw)
     kw.setdefault("cap_live", (cfg.get("n_possible_predators", 50), cfg.get("n_possible_prey", 50)))
     return make_config(cfg, reward_mode=REWARD_MODES[variant], **kw)
 
