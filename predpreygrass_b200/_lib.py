@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libppg_b200.so")
 SYMBOLS = [
     "ppg_abi_version", "ppg_default_config", "ppg_create", "ppg_destroy", "ppg_load_tape", "ppg_reset", "ppg_step",
     "ppg_step_ordered", "ppg_step_host", "ppg_random_actions", "ppg_get_buffers", "ppg_snapshot_size", "ppg_snapshot", "ppg_restore",
-    "ppg_read_env", "ppg_read_env_eco", "ppg_stats", "ppg_stats_device", "ppg_stats_clear", "ppg_launch_count", "ppg_last_error",
+    "ppg_read_env", "ppg_read_env_eco", "ppg_read_env_stag", "ppg_stats", "ppg_stats_device", "ppg_stats_clear", "ppg_launch_count", "ppg_last_error",
 ]
 
 _lib = None
@@ -57,6 +57,7 @@ def load():
     L.ppg_restore.argtypes = [vp, vp, C.c_size_t, vp]
     L.ppg_read_env.argtypes = [vp, i32] + [vp] * 9
     L.ppg_read_env_eco.argtypes = [vp, i32] + [vp] * 6
+    L.ppg_read_env_stag.argtypes = [vp, i32] + [vp] * 6
     L.ppg_stats.argtypes = [vp, vp, vp]
     L.ppg_stats_device.argtypes = [vp, C.POINTER(vp), vp]
     L.ppg_stats_clear.argtypes = [vp, vp]

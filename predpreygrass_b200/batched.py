@@ -258,6 +258,22 @@ class BatchedPredPreyGrass:
         st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]], active_num=act)
         return st
 
+    def read_env_stag(self, env):
+        """read_env (lists in `self.agents` insertion order) plus the STAG attributes agent_ages, predator_facing (index into
+        `_predator_facing_options`, STAG:197-206), predator_cooperation_trait and the team-capture counters (STAG:237-254)."""
+        st = self.read_env(env)
+        n = (len(st["ids"][0]), len(st["ids"][1]))
+        age = [np.zeros(max(1, n[s]), np.int32) for s in range(2)]
+        face = np.zeros(max(1, n[0]), np.int32)
+        trait = np.zeros(max(1, n[0]), np.float64)
+        cap = np.zeros(12, np.int64)
+        capr = np.zeros(3, np.float64)
+        rc = self.L.ppg_read_env_stag(self.h, env, age[0].ctypes.data, face.ctypes.data, trait.ctypes.data, age[1].ctypes.data,
+                                      cap.ctypes.data, capr.ctypes.data)
+        _lib.check(rc, self.h)
+        st.update(age=(age[0][: n[0]], age[1][: n[1]]), facing=face[: n[0]], trait=trait[: n[0]], capture=cap, capture_real=capr)
+        return st
+
     def outputs_numpy(self):
         """Host copy (numpy) of the valid part of the last output."""
         o = self.out

@@ -29,6 +29,13 @@ cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, uns
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
 cudaError_t step_eco_occupancy(int map_bytes, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
+// ppg_stag.cu
+cudaError_t launch_step_stag(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
+cudaError_t step_stag_occupancy(int map_bytes, size_t smem, int* blocks_per_sm);
+cudaError_t launch_set_tape_reals_stag(StagHdr* shdr, int B, const long long* real_off, cudaStream_t s);
+cudaError_t launch_random_actions_stag(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1, const int32_t* ra1,
+                                       int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call, unsigned env_base, int t2_pred,
+                                       int t2_prey, int ar0, int ar1, int blocks, cudaStream_t s);
 }  // namespace ppg
 
 using namespace ppg;
@@ -138,11 +145,25 @@ const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_s
 static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   if (!c || c->struct_size != sizeof(ppg_config)) { err = "ppg_config.struct_size mismatch"; return PPG_ERR_INVALID; }
   if (n_envs <= 0) { err = "n_envs must be positive"; return PPG_ERR_INVALID; }
-  if (c->variant != PPG_VARIANT_BASE && c->variant != PPG_VARIANT_ECO) { err = "variant not supported by this build"; return PPG_ERR_INVALID; }
-  const bool eco = c->variant == PPG_VARIANT_ECO;
+  if (c->variant != PPG_VARIANT_BASE && c->variant != PPG_VARIANT_ECO && c->variant != PPG_VARIANT_STAG) { err = "unknown variant"; return PPG_ERR_INVALID; }
+  const bool eco = c->variant == PPG_VARIANT_ECO, stag = c->variant == PPG_VARIANT_STAG;
   if (c->reward_mode < 0 || c->reward_mode > PPG_REWARD_SPARSE_KICKBACK) { err = "bad reward_mode"; return PPG_ERR_INVALID; }
   if (c->grid_size < 2 || c->grid_size > 255) { err = "grid_size must be in [2,255]"; return PPG_ERR_INVALID; }
-  if (!eco && c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
+  if (!eco && !stag && c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
+  if (stag) {
+    if (c->num_obs_channels < 5) { err = "STAG needs num_obs_channels >= 5 (walls, predators, mammoths, rabbits, grass)"; return PPG_ERR_INVALID; }
+    if (c->reward_mode != PPG_REWARD_SPARSE) { err = "STAG has one reward mode"; return PPG_ERR_INVALID; }
+    if (c->max_steps > 65000) { err = "STAG: max_steps must be <= 65000 (16-bit ages)"; return PPG_ERR_INVALID; }
+    if (c->cap_live[0] > 32767 || c->cap_live[1] > 32767) { err = "STAG: cap_live must be <= 32767"; return PPG_ERR_INVALID; }
+    for (int s = 0; s < 2; ++s) {
+      if (c->n_possible_t[s][0] < 0 || c->n_possible_t[s][1] < 0 || c->n_possible_t[s][0] + c->n_possible_t[s][1] != c->n_possible[s]) { err = "STAG: n_possible must be the sum over both types"; return PPG_ERR_INVALID; }
+      if (c->n_initial_t[s][0] < 0 || c->n_initial_t[s][1] < 0 || c->n_initial_t[s][0] + c->n_initial_t[s][1] != c->n_initial[s]) { err = "STAG: n_initial must be the sum over both types"; return PPG_ERR_INVALID; }
+      if (c->n_initial_t[s][0] > c->n_possible_t[s][0] || c->n_initial_t[s][1] > c->n_possible_t[s][1]) { err = "STAG: more founders than possible agents of a type"; return PPG_ERR_INVALID; }
+      if (c->type_action_range[s] < 0 || c->type_action_range[s] > 15 || (c->type_action_range[s] > 0 && (c->type_action_range[s] & 1) == 0)) { err = "STAG: type action range must be odd, <= 15"; return PPG_ERR_INVALID; }
+    }
+    if (c->team_capture_success_model < 0 || c->team_capture_success_model > PPG_CAPTURE_HYBRID) { err = "bad team_capture_success_model"; return PPG_ERR_INVALID; }
+    if (!(c->team_capture_base_success_p0 > 0.0 && c->team_capture_base_success_p0 < 1.0)) { err = "team_capture_base_success_p0 must lie in (0, 1)"; return PPG_ERR_INVALID; }
+  }
   if (eco) {
     if (c->num_obs_channels != 3) { err = "ECO needs num_obs_channels == 3 (predators, prey, grass)"; return PPG_ERR_INVALID; }
     if (c->reward_mode != PPG_REWARD_SPARSE) { err = "ECO has one reward mode"; return PPG_ERR_INVALID; }
@@ -191,7 +212,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   StepParams& P = h->P;
   memset(&P, 0, sizeof P);
   const int B = n_envs, G = c.grid_size, GG = G * G;
-  const bool eco = c.variant == PPG_VARIANT_ECO;
+  const bool eco = c.variant == PPG_VARIANT_ECO, stag = c.variant == PPG_VARIANT_STAG;
   const int row_channels = c.num_obs_channels + (eco && c.include_speed_in_obs ? 1 : 0);
   P.B = B; P.G = G; P.GG = GG; P.C = row_channels; P.env_base = c.env_index_base;
   P.variant = c.variant;
@@ -205,6 +226,21 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     for (int s = 0; s < 2; ++s) { P.f_mean[s] = c.founder_speed_mean[s]; P.f_std[s] = c.founder_speed_std[s]; }
     P.mut_rate = c.mutation_rate; P.mut_std = c.mutation_std; P.sp_lo = c.speed_bounds[0]; P.sp_hi = c.speed_bounds[1];
     P.sp_thr = c.speed_distance_threshold;
+  } else if (stag) {
+    P.action_range = std::max(c.type_action_range[0], c.type_action_range[1]); P.n_actions = P.action_range * P.action_range;
+    for (int s = 0; s < 2; ++s)
+      for (int t = 0; t < 2; ++t) { P.n_possible_t[s][t] = c.n_possible_t[s][t]; P.n_init_t[s][t] = c.n_initial_t[s][t]; P.r_repro_t[s][t] = c.reproduction_reward_t[s][t]; }
+    for (int t = 0; t < 2; ++t) {
+      P.type_ar[t] = c.type_action_range[t]; P.loss_prey_t[t] = c.energy_loss_prey_t[t]; P.thr_prey_t[t] = c.creation_threshold_prey_t[t];
+      P.init_e_prey_t[t] = c.initial_energy_prey_t[t]; P.bite_t[t] = c.bite_size_prey_t[t];
+    }
+    for (int k = 0; k < 3; ++k) P.death_pen[k] = c.death_penalty[k];
+    P.equal_split = c.team_capture_equal_split != 0; P.coop_enabled = c.coop_trait_enabled != 0; P.capture_model = c.team_capture_success_model;
+    P.strict_out = c.strict_rllib_output != 0;
+    P.cap_margin = c.team_capture_margin; P.join_cost = c.team_capture_join_cost; P.scav_frac = c.team_capture_scavenger_fraction;
+    P.nature_w = c.team_capture_nature_weight; P.p0 = c.team_capture_base_success_p0; P.force_ratio = c.team_capture_force_success_ratio;
+    P.min_prob = c.team_capture_min_success_prob; P.trait_mean = c.coop_trait_init_mean; P.trait_std = c.coop_trait_init_std;
+    P.trait_mut_std = c.coop_trait_mutation_std; P.trait_mut_rate = c.coop_trait_mutation_rate;
   } else {
     P.action_range = 3; P.n_actions = 9;
   }
@@ -215,7 +251,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.r_repro[s] = c.reproduction_reward[s]; P.r_kick[s] = c.kickback_reward[s];
   }
   P.n_grass = c.n_grass; P.max_steps = c.max_steps; P.reward_mode = c.reward_mode; P.autoreset = c.autoreset;
-  P.grass_cap = eco ? c.max_energy_grass : c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
+  P.grass_cap = (eco || stag) ? c.max_energy_grass : c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
   P.init_e_grass = c.initial_energy_grass;
   P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
   P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;
@@ -227,8 +263,10 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   if (const char* ev = getenv("PPG_OBS_BULK")) P.obs_bulk = atoi(ev) != 0;
   // padded map geometry (ppg_base.cu): halo as wide as the largest observation window
   P.P = std::max(P.off[0], P.off[1]);
-  P.PS = G + P.P;
-  P.CH = (int)align_up((size_t)P.P + (size_t)(G + 2 * P.P) * P.PS + P.P, 4);
+  P.PH = P.P;
+  if (stag) P.PH = std::max(2 * P.off[0], P.off[1]);  // forward view: the effective window centre lies up to off[0] cells past the far edge
+  P.PS = G + P.PH;
+  P.CH = (int)align_up((size_t)P.P + (size_t)(G + P.P + P.PH) * P.PS + P.P, 4);
   P.map_bytes = (P.cap[0] <= 253 && P.cap[1] <= 253 && P.n_grass <= 253) ? 1 : 2;
   P.wall_idx = P.cap[0] + 1;
   for (int s = 0; s < 2; ++s) {
@@ -268,6 +306,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.so_map[0] = take((size_t)P.map_bytes * P.CH, 16);
   P.so_map[1] = take((size_t)P.map_bytes * P.CH, 4);
   P.so_map[2] = take((size_t)P.map_bytes * P.CH, 4);
+  P.so_map[3] = take(stag ? (size_t)P.map_bytes * P.CH : 0, 4);  // STAG: rabbits (grid channel 3)
   P.so_scr = take((size_t)P.CH, 4);
   P.so_wt = take(4 * (size_t)(P.cap[0] + 2), 4);
   o = align_up(o, 16);
@@ -281,6 +320,11 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
       P.so_seq[s] = take(2 * (size_t)P.cap[s], 2); P.so_mord[s] = take(2 * (size_t)P.cap[s], 2);
     }
   }
+  if (stag) {
+    P.so_trait = take(8 * (size_t)P.cap[0], 8);
+    for (int s = 0; s < 2; ++s) { P.so_age[s] = take(2 * (size_t)P.cap[s], 2); P.so_mord[s] = take(2 * (size_t)P.cap[s], 2); }
+    P.so_face = take(P.cap[0], 1); P.so_join = take(P.cap[0], 1);
+  }
   P.smem_per_env = (int)align_up(o, 128);
   const size_t smem_max = 227 * 1024;
   if ((size_t)P.smem_per_env > smem_max) { h->err = "cap_live/grid too large for shared memory"; return fail(PPG_ERR_INVALID); }
@@ -292,12 +336,12 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
       for (int i = 0; i < P.CH; ++i) {
         const int xx = i >= P.P ? (i - P.P) / P.PS - P.P : -1, yy = i >= P.P ? (i - P.P) % P.PS : 0;
         const bool field = i >= P.P && xx >= 0 && xx < G && yy < G;
-        if (!field && !eco) {  // ECO has no wall channel: out-of-grid window cells stay 0 (ECO:700-706)
+        if (!field && !eco && !stag) {  // ECO has no wall channel; STAG's wall channel is empty (walls are rejected by the config layer): out-of-grid window cells stay 0 (ECO:700-706)
           if (P.map_bytes == 1) img[(size_t)i] = (unsigned char)P.wall_idx;
           else reinterpret_cast<uint16_t*>(img.data())[i] = (uint16_t)P.wall_idx;
         }
       }
-      if (!eco) reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
+      if (!eco && !stag) reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
       unsigned char* d_img = nullptr;
       CKC(dalloc(h, &d_img, img.size()));
       CKC(cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice));
@@ -316,6 +360,13 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
           const int ch = q / RR, i = (q % RR) / R, jj = q % R;
           const int cellrel = (i - P.off[s]) * P.PS + (jj - P.off[s]);
           const size_t at = ((size_t)(s * PPG_MAX_NJ + j) * 32 + lane) * 2;
+          if (stag) {  // STAG channels (STAG:112-117): 0 walls (none: an all-zero table), 1 predators, 2 mammoths, 3 rabbits, 4 grass
+            static const int map_of[5] = {0, 0, 1, 3, 2};
+            const int m = ch < 5 ? map_of[ch] : 0;
+            rel[at] = (P.so_map[m] - P.so_map[0]) + cellrel * P.map_bytes;
+            rel[at + 1] = ch == 1 ? P.so_vt[0] : (ch == 2 || ch == 3) ? P.so_vt[1] : ch == 4 ? P.so_vt[2] : P.so_wt;
+            continue;
+          }
           if (eco) {  // ECO channels: 0 predators, 1 prey, 2 grass, 3 the agent's own speed (a constant plane, not a gather)
             if (ch >= 3) { selfm[(size_t)s * 32 + lane] |= 1u << j; continue; }
             rel[at] = (P.so_map[ch] - P.so_map[0]) + cellrel * P.map_bytes;
@@ -342,13 +393,14 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   if (const char* ev = getenv("PPG_WARPS_PER_CTA")) W = atoi(ev);
   if (W != 1 && W != 4 && W != 8) W = 1;
   while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
-  if (eco) W = 1;
+  if (eco || stag) W = 1;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
     if (eco) CKC(step_eco_occupancy(P.map_bytes, h->smem_bytes, &per_sm));
+    else if (stag) CKC(step_stag_occupancy(P.map_bytes, h->smem_bytes, &per_sm));
     else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
@@ -364,6 +416,10 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.ag_prow[s], n)); CKC(dalloc(h, &P.ag_par[s], c.reward_mode == PPG_REWARD_SPARSE_KICKBACK ? n : 1));
     if (eco) {
       CKC(dalloc(h, &P.ag_age[s], n)); CKC(dalloc(h, &P.ag_seq[s], n)); CKC(dalloc(h, &P.ag_spd[s], n)); CKC(dalloc(h, &P.ag_dead[s], n));
+    }
+    if (stag) {
+      CKC(dalloc(h, &P.ag_age[s], n));
+      if (s == 0) { CKC(dalloc(h, &P.ag_face, n)); CKC(dalloc(h, &P.ag_trait, n)); }
     }
     std::vector<uint16_t> lr = lexrank_table(c.n_possible[s]);
     uint16_t* d = nullptr;
@@ -381,6 +437,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.totals, 8));
   }
   if (eco) CKC(dalloc(h, &P.ehdr, (size_t)B));
+  if (stag) CKC(dalloc(h, &P.shdr, (size_t)B));
   CKC(dalloc(h, &P.gr_pos, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
@@ -449,7 +506,7 @@ int ppg_load_tape(ppg_handle h, const ppg_tape* t) {
   }
   CK(launch_set_tape(h->P.hdr, h->B, h->d_tape_off, 0));
   h->launch_count++;
-  if (h->P.variant == PPG_VARIANT_ECO) {
+  if (h->P.variant == PPG_VARIANT_ECO || h->P.variant == PPG_VARIANT_STAG) {
     if (h->d_tape_reals) { cudaFree(h->d_tape_reals); h->d_tape_reals = nullptr; }
     if (h->d_tape_real_off) { cudaFree(h->d_tape_real_off); h->d_tape_real_off = nullptr; }
     h->P.tape_reals = nullptr;
@@ -461,7 +518,8 @@ int ppg_load_tape(ppg_handle h, const ppg_tape* t) {
       CK(cudaMemcpy(h->d_tape_real_off, t->real_off, sizeof(long long) * ((size_t)h->B + 1), cudaMemcpyHostToDevice));
       h->P.tape_reals = h->d_tape_reals;
     }
-    CK(launch_set_tape_reals(h->P.ehdr, h->B, h->d_tape_real_off, 0));
+    if (h->P.variant == PPG_VARIANT_ECO) CK(launch_set_tape_reals(h->P.ehdr, h->B, h->d_tape_real_off, 0));
+    else CK(launch_set_tape_reals_stag(h->P.shdr, h->B, h->d_tape_real_off, 0));
     h->launch_count++;
   }
   CK(cudaDeviceSynchronize());
@@ -489,6 +547,7 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
                                           : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
   if (P.variant == PPG_VARIANT_ECO) CK(launch_step_eco(P, h->n_cta, h->smem_bytes, st));
+  else if (P.variant == PPG_VARIANT_STAG) CK(launch_step_stag(P, h->n_cta, h->smem_bytes, st));
   else CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
   h->launches_step++;
   h->launch_count++;
@@ -583,6 +642,11 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
   if (!h || !actions_pred || !actions_prey) return PPG_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   const StepParams& P = h->P;
+  if (P.variant == PPG_VARIANT_STAG)
+    CK(launch_random_actions_stag(P.n_rows, P.row_env[0], P.row_agent[0], P.row_env[1], P.row_agent[1], actions_pred, actions_prey, seed,
+                                  (unsigned)h->calls, (unsigned)P.env_base, P.n_possible_t[0][0], P.n_possible_t[1][0], P.type_ar[0], P.type_ar[1],
+                                  148 * 4, static_cast<cudaStream_t>(cuda_stream)));
+  else
   CK(launch_random_actions(P.n_rows, P.row_env[0], P.row_agent[0], P.row_env[1], P.row_agent[1], actions_pred, actions_prey,
                            seed, (unsigned)h->calls, (unsigned)P.n_actions, (unsigned)P.env_base, 148 * 4, static_cast<cudaStream_t>(cuda_stream)));
   h->launch_count++;
@@ -609,7 +673,12 @@ static std::vector<Seg> state_segments(ppg_handle h) {
     if (P.variant == PPG_VARIANT_ECO) {
       v.push_back({P.ag_age[s], n * 2}); v.push_back({P.ag_seq[s], n * 2}); v.push_back({P.ag_spd[s], n * 8}); v.push_back({P.ag_dead[s], n});
     }
+    if (P.variant == PPG_VARIANT_STAG) {
+      v.push_back({P.ag_age[s], n * 2});
+      if (s == 0) { v.push_back({P.ag_face, n}); v.push_back({P.ag_trait, n * 8}); }
+    }
   }
+  if (P.variant == PPG_VARIANT_STAG) v.push_back({P.shdr, sizeof(StagHdr) * (size_t)h->B});
   if (P.variant == PPG_VARIANT_ECO) v.push_back({P.ehdr, sizeof(EcoHdr) * (size_t)h->B});
   v.push_back({P.gr_pos, (size_t)h->B * std::max(1, P.n_grass) * 2});
   v.push_back({P.gr_e, (size_t)h->B * std::max(1, P.n_grass) * 8});
@@ -685,7 +754,8 @@ int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, 
     // report in agent_positions insertion order = ascending id (BASE:190-200,401)
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a, int b2) { return id[a] < id[b2]; });
+    if (P.variant != PPG_VARIANT_STAG)  // STAG: the device list already is in insertion order (flat ids are not monotonic)
+      std::sort(order.begin(), order.end(), [&](int a, int b2) { return id[a] < id[b2]; });
     for (int i = 0; i < n; ++i) {
       const int j = order[i];
       if (ids[s]) ids[s][i] = id[j];
@@ -737,6 +807,42 @@ int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed
     }
   }
   if (active_num) { active_num[0] = eh.active[0]; active_num[1] = eh.active[1]; }
+  return PPG_OK;
+}
+
+int ppg_read_env_stag(ppg_handle h, int32_t env, int32_t* age_pred, int32_t* facing_pred, double* trait_pred, int32_t* age_prey,
+                      int64_t* capture, double* capture_real) {
+  if (!h || env < 0 || env >= h->B) return PPG_ERR_INVALID;
+  if (h->P.variant != PPG_VARIANT_STAG) { h->err = "ppg_read_env_stag: not a STAG handle"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const StepParams& P = h->P;
+  EnvHdr hd;
+  StagHdr sh;
+  CK(cudaMemcpy(&hd, P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&sh, P.shdr + env, sizeof sh, cudaMemcpyDeviceToHost));
+  int32_t* age[2] = {age_pred, age_prey};
+  for (int s = 0; s < 2; ++s) {  // the device list is in insertion order = the order of ppg_read_env
+    const int n = hd.n_list[s];
+    if (!n) continue;
+    std::vector<uint16_t> a(n);
+    const size_t b = (size_t)env * P.cap[s];
+    CK(cudaMemcpy(a.data(), P.ag_age[s] + b, n * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i)
+      if (age[s]) age[s][i] = a[i];
+    if (s == 0) {
+      std::vector<uint8_t> f(n);
+      std::vector<double> t(n);
+      CK(cudaMemcpy(f.data(), P.ag_face + b, n, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(t.data(), P.ag_trait + b, n * 8, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < n; ++i) {
+        if (facing_pred) facing_pred[i] = f[i];
+        if (trait_pred) trait_pred[i] = t[i];
+      }
+    }
+  }
+  if (capture) for (int k = 0; k < 12; ++k) capture[k] = sh.capture[k];
+  if (capture_real) for (int k = 0; k < 3; ++k) capture_real[k] = sh.capture_real[k];
   return PPG_OK;
 }
 

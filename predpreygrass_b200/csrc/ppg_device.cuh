@@ -50,6 +50,17 @@ struct __align__(16) EcoHdr {
 };
 static_assert(sizeof(EcoHdr) == 32, "EcoHdr must be 32 bytes");
 
+// STAG only: second per-env header (112 B)
+struct __align__(16) StagHdr {
+  long long real_pos, real_end;  // replay-tape cursor into tape_reals
+  double capture_real[3];        // last_success_prob, last_effort_ratio, success_prob_sum (STAG:249-251)
+  unsigned capture[12];          // team-capture counters in the order of ppg_read_env_stag (STAG:237-254)
+  unsigned trait_draws, facing_draws, capture_draws;  // Philox counters of the trait / facing / capture streams
+  unsigned short next_idx_t[2][2];                     // head of the per-type id deques (STAG:2259-2291)
+  unsigned pad;
+};
+static_assert(sizeof(StagHdr) == 112, "StagHdr must be 112 bytes");
+
 // per-slot flag bits, shared memory only
 enum : unsigned char {
   F_ALIVE = 1,    // in agent_positions
@@ -117,7 +128,7 @@ struct StepParams {
   int32_t* env_count;
   // ---- shared-memory layout, byte offsets inside one env's region ----
   int so_E[2], so_E0[2], so_gE, so_wt, so_vt[3], so_stage, so_scr, so_id[2], so_pos[2], so_ord[2], so_rnk[2], so_par[2];
-  int so_map[3], so_gpos, so_act[2], so_flg[2], so_aux[2], so_gtag;
+  int so_map[4], so_gpos, so_act[2], so_flg[2], so_aux[2], so_gtag;
   int stage_elems;  // floats per staging row buffer (max over species, multiple of 4)
   int smem_per_env;
   // ---- padded map geometry and the observation gather tables (see ppg_base.cu) ----
@@ -143,6 +154,16 @@ struct StepParams {
   const double* tape_reals;
   int so_spd[2], so_age[2], so_seq[2], so_mord[2];
   const unsigned* obs_self;  // [2][32] per-lane bit mask: element j of the lane lies in the agent's own-speed plane (ECO:707-711)
+  // ---- STAG (ppg_stag.cu); ag_age / so_age / so_mord above are shared with ECO ----
+  int n_possible_t[2][2], n_init_t[2][2], type_ar[2];
+  int equal_split, coop_enabled, capture_model, strict_out;
+  int PH;  // high-side halo of the padded maps (forward view: the predator window centre lies up to `off` cells outside)
+  double loss_prey_t[2], thr_prey_t[2], init_e_prey_t[2], bite_t[2], r_repro_t[2][2], death_pen[3];
+  double cap_margin, join_cost, scav_frac, nature_w, p0, force_ratio, min_prob, trait_mean, trait_std, trait_mut_std, trait_mut_rate;
+  StagHdr* shdr;
+  uint8_t* ag_face;   // [B][cap0] predator facing, index into _predator_facing_options (STAG:197-206)
+  double* ag_trait;   // [B][cap0] predator_cooperation_trait (STAG:230)
+  int so_trait, so_face, so_join;
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
                         //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };

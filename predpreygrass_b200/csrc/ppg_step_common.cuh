@@ -387,6 +387,26 @@ static __device__ __noinline__ void philox_placement(int* cells, unsigned* first
   }
 }
 
+// number of cells no live agent stands on (`all_positions - occupied_positions`, STAG:1037-1039)
+template <typename MapT>
+__device__ __noinline__ int count_free_cells(unsigned char* base, const StepParams& p, int nl0, int nl1, int lane) {
+  const EnvSmem<MapT> S = carve<MapT>(base, p);
+  const int G = p.G, GG = p.GG;
+  const int nl[2] = {nl0, nl1};
+  int n_free = 0;
+  for (int c0 = 0; c0 < GG; c0 += 32) {
+    const int c = c0 + lane;
+    bool fr = c < GG;
+    if (fr) {
+      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
+    }
+    n_free += __popc(__ballot_sync(FULL, fr));
+  }
+  return n_free;
+}
+
 // spawn fallback (BASE:760-764): the k-th free cell in ascending cell order, k from the env's Philox spawn stream.
 // Returns x << 8 | y, or -1 if no cell is free.
 template <typename MapT>

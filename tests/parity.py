@@ -37,8 +37,17 @@ def compare_outputs(g, o, where="", obs_rtol=0.0, reward_rtol=0.0):
 
 
 def compare_env_state(gpu, oracle, env, where=""):
-    eco = gpu.cfg.variant == 1
-    a, b = (gpu.read_env_eco(env), oracle.read_env_eco(env)) if eco else (gpu.read_env(env), oracle.read_env(env))
+    eco, stag = gpu.cfg.variant == 1, gpu.cfg.variant == 2
+    if stag:
+        a, b = gpu.read_env_stag(env), oracle.read_env_stag(env)
+        for s in range(2):
+            assert np.array_equal(a["age"][s], b["age"][s]), (where, env, s, a["age"][s], b["age"][s])
+        assert np.array_equal(a["facing"], b["facing"]), (where, env, a["facing"], b["facing"])
+        assert np.array_equal(a["trait"], b["trait"]), (where, env, a["trait"], b["trait"])
+        assert np.array_equal(a["capture"], b["capture"]), (where, env, a["capture"], b["capture"])
+        assert np.array_equal(a["capture_real"], b["capture_real"]), (where, env, a["capture_real"], b["capture_real"])
+    else:
+        a, b = (gpu.read_env_eco(env), oracle.read_env_eco(env)) if eco else (gpu.read_env(env), oracle.read_env(env))
     if eco:
         for s in range(2):
             assert np.array_equal(a["age"][s], b["age"][s]), (where, env, s, a["age"][s], b["age"][s])

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(_lib.SYMBOLS) == declared
-    assert _lib.load().ppg_abi_version() == 3
+    assert _lib.load().ppg_abi_version() == 4
 
 
 def test_struct_layout_matches_header():
@@ -40,7 +40,7 @@ def test_struct_layout_matches_header():
     for f, _ in PpgConfig._fields_:
         a, b = getattr(c, f), getattr(ref, f)
         if hasattr(a, "__len__"):
-            assert list(a) == list(b), f
+            assert bytes(a) == bytes(b), f
         else:
             assert a == b, f
 
