@@ -36,8 +36,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="env instances per GPU (BASELINE configs[1])")
-    ap.add_argument("--variant", default="base", choices=["base", "eco"],
-                    help="base: BASELINE configs[1]/[2] (base_environment family); eco: configs[3] (eco_evolutionary, speed trait)")
+    ap.add_argument("--variant", default="base", choices=["base", "eco", "stag"],
+                    help="base: BASELINE configs[1]/[2] (base_environment family); eco: configs[3] (eco_evolutionary, speed trait); "
+                         "stag: configs[4] (stag_hunt_forward_view_nature_nurture, team capture)")
     ap.add_argument("--eco-rich", action="store_true", help="eco: reproduction-heavy override (thresholds 8/5, grass regrowth 0.3)")
     ap.add_argument("--reward-mode", default="sparse")
     ap.add_argument("--cap", type=int, nargs=2, default=None)
@@ -48,11 +49,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.cap is None:
-        args.cap = [64, 192] if args.variant == "base" else ([128, 320] if args.eco_rich else [32, 96])
+        args.cap = {"base": [64, 192], "eco": [128, 320] if args.eco_rich else [32, 96], "stag": [64, 192]}[args.variant]
     return args
 
 
 def workload_name(args):
+    if args.variant == "stag":
+        return (f"stag_hunt_forward_view_nature_nurture default config_env, {args.envs} envs per GPU, uniform random actions "
+                "(predators [9, 2], prey 9), auto-reset, Philox facing/trait/capture draws")
     if args.variant == "eco":
         return (f"eco_evolutionary default config_env{' + reproduction-heavy override' if args.eco_rich else ''}, {args.envs} envs per GPU, "
                 "uniform random actions (25), auto-reset, Philox trait/mutation draws")
@@ -60,8 +64,10 @@ def workload_name(args):
 
 
 def build_config(args, **kw):
-    from predpreygrass_b200.config import BASE_CONFIG, ECO_CONFIG, VARIANT_ECO, make_config
+    from predpreygrass_b200.config import BASE_CONFIG, ECO_CONFIG, STAG_CONFIG, VARIANT_ECO, VARIANT_STAG, make_config
 
+    if args.variant == "stag":
+        return make_config(STAG_CONFIG, variant=VARIANT_STAG, cap_live=tuple(args.cap), **kw)
     if args.variant == "eco":
         d = dict(ECO_CONFIG)
         if args.eco_rich:
@@ -73,6 +79,17 @@ def build_config(args, **kw):
 
 def n_actions(args):
     return 25 if args.variant == "eco" else 9
+
+
+def action_pools(args, n, rng):
+    """host-side random actions (numpy int32) for n rows per species; STAG predators carry the join_hunt bit (include/ppg.h)"""
+    import numpy as np
+
+    a0 = rng.integers(0, n_actions(args), size=n, dtype=np.int32)
+    a1 = rng.integers(0, n_actions(args), size=n, dtype=np.int32)
+    if args.variant == "stag":
+        a0 = a0 | (rng.integers(0, 2, size=n, dtype=np.int32) << 8)
+    return a0, a1
 
 
 class ClockSampler:
@@ -120,13 +137,13 @@ def cpu_oracle_rate(args, threads, steps, warmup):
     o = Oracle(cfg, args.cpu_envs, threads=threads)
     o.reset()
     rng = np.random.default_rng(0)
-    pool = rng.integers(0, n_actions(args), size=args.cpu_envs * (args.cap[0] + args.cap[1]) + 16, dtype=np.int32)
+    pool0, pool1 = action_pools(args, args.cpu_envs * (args.cap[0] + args.cap[1]) + 16, rng)
 
     def run(k):
         t = 0.0
         for _ in range(k):
             t0 = time.perf_counter()
-            o.step(pool, pool)  # any action value is valid for any row; sampling is not timed
+            o.step(pool0, pool1)  # any action value is valid for any row; sampling is not timed
             t += time.perf_counter() - t0
         return t
 
@@ -237,7 +254,7 @@ def main():
     kd = dict(zip(STAT_NAMES, (sk1 - sk0).tolist()))
     k_ms = sum(a.elapsed_time(b) for a, b in evs) / KR
     row_bytes = [4 * env.C * cfg.obs_range[s] ** 2 for s in range(2)]
-    s_agent = S_AGENT + (20 if args.variant == "eco" else 0)  # + trait 8 (read+write 16), age 2+2
+    s_agent = S_AGENT + (20 if args.variant in ("eco", "stag") else 0)  # + trait 8 (read+write 16), age 2+2
     alg_bytes = (kd["rows_pred"] * row_bytes[0] + kd["rows_prey"] * row_bytes[1] + kd["agent_steps"] * s_agent
                  + kd["env_steps"] * (cfg.n_grass * 16 + 64)) / KR
     peaks = {}
@@ -254,14 +271,15 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "ppg_step_eco_kernel" if args.variant == "eco" else "ppg_step_base_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": {"eco": "ppg_step_eco_kernel", "stag": "ppg_step_stag_kernel"}.get(args.variant, "ppg_step_base_kernel"), "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
 
     # ---- e2e through the C-ABI with host buffers (rank-local rate, summed over ranks)
     e2e = None
     if not args.no_e2e:
         host = env.make_host_buffers(pinned=True)
-        pool = torch.randint(0, n_actions(args), (max(env.row_capacity) + 4096,), dtype=torch.int32).pin_memory()
+        p0, p1 = action_pools(args, max(env.row_capacity) + 4096, np.random.default_rng(1))
+        pool0, pool1 = torch.from_numpy(p0).pin_memory(), torch.from_numpy(p1).pin_memory()
         h2d = d2h = 0
         n0, n1 = env.out.counts()
         e0 = env.stats_device().clone()
@@ -269,8 +287,8 @@ def main():
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
             off = (i * 61) % 4096
-            host["actions0"][:n0].copy_(pool[off:off + n0])  # host->pinned staging of this step's inputs
-            host["actions1"][:n1].copy_(pool[off:off + n1])
+            host["actions0"][:n0].copy_(pool0[off:off + n0])  # host->pinned staging of this step's inputs
+            host["actions1"][:n1].copy_(pool1[off:off + n1])
             h2d += 4 * (n0 + n1)
             n0, n1 = env.step_host(host)
             d2h += n0 * (row_bytes[0] + 13) + n1 * (row_bytes[1] + 13) + 4 * (args.envs + 1) * 4 + args.envs * 14 + 16
