@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 4
+#define PPG_ABI_VERSION 5
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -336,6 +336,13 @@ int ppg_stats_clear(ppg_handle h, void* cuda_stream);
 
 /* Kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t ppg_launch_count(ppg_handle h);
+
+/* Per-kernel timing of the steps between the two calls (bench.py `roofline`): CUDA events are recorded on the
+ * step's own stream before the step kernel, between it and the observation kernel, and after the latter.
+ * ppg_profile_end synchronises and returns the summed durations in milliseconds and the number of steps timed
+ * (ms_obs_kernel = 0 when the handle runs the one-kernel step, PPG_OBS_SPLIT=0). */
+int ppg_profile_begin(ppg_handle h);
+int ppg_profile_end(ppg_handle h, double* ms_step_kernel, double* ms_obs_kernel, int32_t* n_steps);
 
 const char* ppg_last_error(ppg_handle h);
 int ppg_abi_version(void);

@@ -220,6 +220,16 @@ class BatchedPredPreyGrass:
     def launch_count(self):
         return int(self.L.ppg_launch_count(self.h))
 
+    def profile_begin(self):
+        """start timing the kernels of every step with CUDA events on the step's stream (include/ppg.h)"""
+        _lib.check(self.L.ppg_profile_begin(self.h), self.h)
+
+    def profile_end(self):
+        """-> (ms in the step kernel, ms in the observation kernel, steps timed), summed since profile_begin"""
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        _lib.check(self.L.ppg_profile_end(self.h, C.byref(a), C.byref(b), C.byref(n)), self.h)
+        return a.value, b.value, n.value
+
     def snapshot(self):
         n = self.L.ppg_snapshot_size(self.h)
         blob = np.empty(n, np.uint8)

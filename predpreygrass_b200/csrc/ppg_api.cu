@@ -13,7 +13,7 @@
 
 namespace ppg {
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, size_t smem, int* blocks_per_sm);
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, bool split, size_t smem, int* blocks_per_sm);
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
                                    unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s);
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
@@ -25,13 +25,16 @@ cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, con
                                   const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
                                   unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s);
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s);
+// ppg_obs.cu
+cudaError_t launch_obs(const StepParams& p, int n_cta, cudaStream_t stream);
+cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm);
 // ppg_eco.cu
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_eco_occupancy(int map_bytes, size_t smem, int* blocks_per_sm);
+cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
 // ppg_stag.cu
 cudaError_t launch_step_stag(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_stag_occupancy(int map_bytes, size_t smem, int* blocks_per_sm);
+cudaError_t step_stag_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals_stag(StagHdr* shdr, int B, const long long* real_off, cudaStream_t s);
 cudaError_t launch_random_actions_stag(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1, const int32_t* ra1,
                                        int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call, unsigned env_base, int t2_pred,
@@ -48,6 +51,10 @@ struct ppg_handle_s {
   size_t smem_bytes = 0;
   unsigned long long launches_step = 0;  // step-kernel launches so far (epoch)
   unsigned long long ticket_next = 0;    // value the device ticket counter has after all launches so far
+  unsigned long long obs_ticket_next = 0;  // same for the observation kernel's counter
+  int n_cta_obs = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // triples: before the step kernel, between the kernels, after the observation kernel
   unsigned long long calls = 0;          // ppg_reset(all)/ppg_step calls (ppg_random_actions key)
   int64_t launch_count = 0;
   std::vector<void*> allocs;
@@ -284,31 +291,38 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   P.stage_elems = (int)align_up((size_t)std::max(P.elems[0], P.elems[1]), 4);
   // value tables and staging rows are contiguous: reset() stages n_total cells + a GG-entry claim table there
   if (o - (size_t)P.so_E[0] < (size_t)GG * 4) take((size_t)GG * 4 - (o - (size_t)P.so_E[0]), 1);  // reset(): GG-entry claim table over the energy arrays
-  P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
-  P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
-  P.so_vt[2] = take(4 * (size_t)(P.n_grass + 1), 4);
-  {
-    const size_t need = (size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4;  // reset(): the drawn cells are staged in the value tables
-    if (o - (size_t)P.so_vt[0] < need) take(need - (o - (size_t)P.so_vt[0]), 1);
-  }
   P.so_stage = take(P.obs_bulk ? 2 * 4 * (size_t)P.stage_elems : 0, 16);  // row staging only for the bulk-copy writer
-  // reset() stages its n_total cells in the value tables and a GG-entry claim table over the energy arrays
-  if ((size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4 > (size_t)(P.so_stage - P.so_vt[0]) ||
-      (size_t)GG * 4 > (size_t)(P.so_vt[0] - P.so_E[0])) {
-    h->err = "internal: reset scratch does not fit (cap_live too small for this grid)"; return fail(PPG_ERR_INVALID);
-  }
   for (int s = 0; s < 2; ++s) {
     P.so_id[s] = take(2 * (size_t)P.cap[s], 2); P.so_pos[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_ord[s] = take(2 * (size_t)P.cap[s], 2); P.so_rnk[s] = take(2 * (size_t)P.cap[s], 2);
     P.so_par[s] = take(kick ? 2 * (size_t)P.cap[s] : 0, 2);
   }
-  // maps, touch counters and wall table are contiguous: their initial contents are one image copied by every warp
+  // ---- the env IMAGE (what the observation kernel needs): header, value tables, row descriptors, maps, wall table ----
+  P.so_ihdr = take(4 * (size_t)IH_INTS, 16);
+  P.so_img = P.so_ihdr;
+  P.so_vt[0] = take(4 * (size_t)(P.cap[0] + 2), 16);
+  P.so_vt[1] = take(4 * (size_t)(P.cap[1] + 1), 4);
+  P.so_vt[2] = take(4 * (size_t)(P.n_grass + 1), 4);
+  for (int s = 0; s < 2; ++s) P.so_dsx[s] = take((eco || stag) ? 4 * (size_t)P.cap[s] : 0, 4);
+  for (int s = 0; s < 2; ++s) P.so_dsc[s] = take(2 * (size_t)P.cap[s], 2);
+  {
+    const size_t need = (size_t)(P.n_init[0] + P.n_init[1] + P.n_grass) * 4;  // reset(): the drawn cells are staged in the value tables (and the descriptors behind them)
+    if (o - (size_t)P.so_vt[0] < need) take(need - (o - (size_t)P.so_vt[0]), 1);
+  }
+  // reset() stages its n_total cells in the value tables and a GG-entry claim table over the energy arrays
+  if ((size_t)GG * 4 > (size_t)(P.so_vt[0] - P.so_E[0])) {
+    h->err = "internal: reset scratch does not fit (cap_live too small for this grid)"; return fail(PPG_ERR_INVALID);
+  }
+  // maps, wall table and touch counters are contiguous: their initial contents are one image copied by every warp
   P.so_map[0] = take((size_t)P.map_bytes * P.CH, 16);
   P.so_map[1] = take((size_t)P.map_bytes * P.CH, 4);
   P.so_map[2] = take((size_t)P.map_bytes * P.CH, 4);
   P.so_map[3] = take(stag ? (size_t)P.map_bytes * P.CH : 0, 4);  // STAG: rabbits (grid channel 3)
-  P.so_scr = take((size_t)P.CH, 4);
   P.so_wt = take(4 * (size_t)(P.cap[0] + 2), 4);
+  o = align_up(o, 16);
+  P.img_bytes = (int)(o - (size_t)P.so_img);
+  P.img_stride = (int)align_up((size_t)P.img_bytes, 128);
+  P.so_scr = take((size_t)P.CH, 16);
   o = align_up(o, 16);
   P.init_bytes = (int)(o - (size_t)P.so_map[0]);
   P.so_gpos = take(2 * (size_t)std::max(1, P.n_grass), 2);
@@ -394,14 +408,18 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   if (W != 1 && W != 4 && W != 8) W = 1;
   while (W > 1 && (size_t)W * P.smem_per_env > smem_max) W >>= 1;
   if (eco || stag) W = 1;
+  // two-kernel step (default): the step kernel leaves env images, ppg_obs_kernel writes the observation rows
+  P.obs_split = 1;
+  if (const char* ev = getenv("PPG_OBS_SPLIT")) P.obs_split = atoi(ev) != 0;
+  if (W != 1 || P.obs_bulk || P.CH >= (int)DSC_ZERO) P.obs_split = 0;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    if (eco) CKC(step_eco_occupancy(P.map_bytes, h->smem_bytes, &per_sm));
-    else if (stag) CKC(step_stag_occupancy(P.map_bytes, h->smem_bytes, &per_sm));
-    else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, h->smem_bytes, &per_sm));
+    if (eco) CKC(step_eco_occupancy(P.map_bytes, P.obs_split != 0, h->smem_bytes, &per_sm));
+    else if (stag) CKC(step_stag_occupancy(P.map_bytes, P.obs_split != 0, h->smem_bytes, &per_sm));
+    else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, P.obs_split != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "step kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
     h->n_cta = std::min((B + W - 1) / W, per_sm * n_sm);
@@ -442,6 +460,19 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
   CKC(dalloc(h, &P.ticket, 1));
+  if (P.obs_split) {
+    void* q = nullptr;
+    CKC(cudaMalloc(&q, (size_t)B * (size_t)P.img_stride));  // not cleared: every launch writes every env's header
+    h->allocs.push_back(q);
+    P.obs_img = static_cast<unsigned char*>(q);
+    for (int s = 0; s < 2; ++s) CKC(dalloc(h, &P.nb_info[s], (size_t)B * P.cap[s]));
+    CKC(dalloc(h, &P.obs_ticket, 1));
+    int per_sm = 0, n_sm = 0;
+    CKC(obs_occupancy(P, &per_sm));
+    CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) { h->err = "observation kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
+    h->n_cta_obs = std::min(B, per_sm * n_sm);
+  }
   CKC(dalloc(h, &P.error, 1));
   CKC(dalloc(h, &h->d_stats, PPG_N_STATS));
   CKC(dalloc(h, &h->d_mask, (size_t)B));
@@ -481,6 +512,7 @@ int ppg_destroy(ppg_handle h) {
   if (!h) return PPG_OK;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->d_tape_cells) cudaFree(h->d_tape_cells);
   if (h->d_tape_off) cudaFree(h->d_tape_off);
   if (h->d_tape_reals) cudaFree(h->d_tape_reals);
@@ -546,11 +578,25 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
                                           : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
+  cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+  if (h->profiling) {
+    for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->prof_events.push_back(pe[k]); }
+    CK(cudaEventRecord(pe[0], st));
+  }
   if (P.variant == PPG_VARIANT_ECO) CK(launch_step_eco(P, h->n_cta, h->smem_bytes, st));
   else if (P.variant == PPG_VARIANT_STAG) CK(launch_step_stag(P, h->n_cta, h->smem_bytes, st));
   else CK(launch_step_base(P, h->warps_per_cta, h->n_cta, h->smem_bytes, st));
   h->launches_step++;
   h->launch_count++;
+  if (h->profiling) CK(cudaEventRecord(pe[1], st));
+  if (P.obs_split) {
+    // observation rows of this output: one CTA per env at a time, B tickets plus one terminating draw per CTA
+    P.obs_ticket_base = h->obs_ticket_next;
+    h->obs_ticket_next += (unsigned long long)h->B + (unsigned long long)h->n_cta_obs;
+    CK(launch_obs(P, h->n_cta_obs, st));
+    h->launch_count++;
+  }
+  if (h->profiling) CK(cudaEventRecord(pe[2], st));
   h->calls++;
   h->h_n_rows_valid = false;
   return PPG_OK;
@@ -879,5 +925,34 @@ int ppg_stats_clear(ppg_handle h, void* cuda_stream) {
 }
 
 int64_t ppg_launch_count(ppg_handle h) { return h ? h->launch_count : 0; }
+
+int ppg_profile_begin(ppg_handle h) {
+  if (!h) return PPG_ERR_INVALID;
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  h->profiling = true;
+  return PPG_OK;
+}
+
+int ppg_profile_end(ppg_handle h, double* ms_step_kernel, double* ms_obs_kernel, int32_t* n_steps) {
+  if (!h) return PPG_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  h->profiling = false;
+  double a = 0.0, b = 0.0;
+  const size_t n = h->prof_events.size() / 3;
+  for (size_t i = 0; i < n; ++i) {
+    CK(cudaEventSynchronize(h->prof_events[3 * i + 2]));
+    float x = 0.f, y = 0.f;
+    CK(cudaEventElapsedTime(&x, h->prof_events[3 * i], h->prof_events[3 * i + 1]));
+    CK(cudaEventElapsedTime(&y, h->prof_events[3 * i + 1], h->prof_events[3 * i + 2]));
+    a += x; b += y;
+  }
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  if (ms_step_kernel) *ms_step_kernel = a;
+  if (ms_obs_kernel) *ms_obs_kernel = b;
+  if (n_steps) *n_steps = (int32_t)n;
+  return PPG_OK;
+}
 
 }  // extern "C"

@@ -50,13 +50,14 @@ namespace ppg {
 // ------------------------------------------------------------------------------------------------
 #define SEL(a) (s == 0 ? a[0] : a[1])
 
-template <int W, typename MapT, bool BULK>
+template <int W, typename MapT, bool BULK, bool SPLIT>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
+  const RowDesc D = carve_desc(sbase, p);
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
   const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const unsigned epoch = p.epoch;
@@ -553,14 +554,18 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
       if (pass == 1) {
         if (births[0] + births[1] == 0) break;
-        // newborn rows: their first row depends on the births of every env before this one; by now
-        // (all other work of this env is done) the predecessors have normally published theirs
-        int nb0 = 0, nb1 = 0;
-        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
-          if (lane == 0) atomicOr(p.error, 1u);
+        if (!SPLIT) {
+          // newborn rows: their first row depends on the births of every env before this one; by now
+          // (all other work of this env is done) the predecessors have normally published theirs
+          int nb0 = 0, nb1 = 0;
+          if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+            if (lane == 0) atomicOr(p.error, 1u);
+          }
+          new_base[0] = n_old_total[0] + nb0;
+          new_base[1] = n_old_total[1] + nb1;
         }
-        new_base[0] = n_old_total[0] + nb0;
-        new_base[1] = n_old_total[1] + nb1;
+        // SPLIT: nobody waits — the observation kernel (which runs after every env has published its births) places the
+        // newborn rows and writes their labels (nb_info)
       }
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
@@ -569,11 +574,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         const int elems = p.elems[s];
         const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
         if (k_lo >= tot) continue;
-        const RowRel rr = load_rel(p, s, sb32, lane);
+        RowRel rr;
+        if (!SPLIT) rr = load_rel(p, s, sb32, lane);
         for (int b0 = k_lo; b0 < tot; b0 += 32) {
           const int k = b0 + lane;
           int row = 0, slot = 0, cellp = 0;
           bool alive = false;
+          unsigned nb_lab = 0;
           if (k < tot) {
             const bool newborn = k >= SEL(n);
             slot = newborn ? k : SEL(S.ord)[k];
@@ -601,41 +608,54 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
             if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
             if (mode == 1) rf |= PPG_ROW_FOUNDER;
             if (f & F_ATE) rf |= PPG_ROW_ATE;
-            p.row_env[s][row] = env;
-            p.row_agent[s][row] = SEL(S.id)[slot];
-            p.reward[s][row] = (float)rew;
-            p.flags[s][row] = (uint8_t)rf;
+            if (!(SPLIT && newborn)) {
+              p.row_env[s][row] = env;
+              p.row_agent[s][row] = SEL(S.id)[slot];
+              p.reward[s][row] = (float)rew;
+              p.flags[s][row] = (uint8_t)rf;
+            }
+            nb_lab = (unsigned)SEL(S.id)[slot] | (rf << 16);
             alive = (f & F_ALIVE) != 0;
             const unsigned apos = SEL(S.pos)[slot];
             cellp = CELLP(apos);
           }
           unsigned m = __ballot_sync(FULL, alive);
           // survivors in engagement order (= `self.agents` after the sort), then newborns (BASE:398,468)
+          int dst = 0xFFFF;
           if (keep && alive) {
-            const int dst = SEL(wpos) + __popc(m & lt_mask);
+            dst = SEL(wpos) + __popc(m & lt_mask);
             p.ag_id[s][sb + dst] = SEL(S.id)[slot];
             p.ag_pos[s][sb + dst] = SEL(S.pos)[slot];
             p.ag_e[s][sb + dst] = SEL(S.E)[slot];
-            p.ag_prow[s][sb + dst] = row;
+            p.ag_prow[s][sb + dst] = row;  // SPLIT: newborns get theirs from the observation kernel
             if (kick) p.ag_par[s][sb + dst] = SEL(S.par)[slot];
           }
           if (s == 0) wpos[0] += __popc(m); else wpos[1] += __popc(m);
           // Step 6: observations of everyone still present, from the end-of-step grid (BASE:451-453)
-          while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const int cp = __shfl_sync(FULL, cellp, l);
-            const int r = __shfl_sync(FULL, row, l);
-            emit_row<MapT, BULK>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane);
+          if (SPLIT) {
+            if (k < tot) {
+              // agents that died were observed at that moment (emit_row_now); the others by the observation kernel
+              SEL(D.dsc)[k] = (uint16_t)(alive ? (unsigned)cellp : DSC_SKIP);
+              if (pass == 1) p.nb_info[s][sb + (k - SEL(n))] = (unsigned long long)nb_lab | ((unsigned long long)(unsigned)dst << 32);
+            }
+          } else {
+            while (m) {
+              const int l = __ffs(m) - 1;
+              m &= m - 1;
+              const int cp = __shfl_sync(FULL, cellp, l);
+              const int r = __shfl_sync(FULL, row, l);
+              emit_row<MapT, BULK>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane);
+            }
           }
         }
       }
       }
       if (lane < 2) {  // PHASE: tail
         const int nb = lane == 0 ? births[0] : births[1];
-        p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
+        if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
         p.new_cnt[lane][env] = nb;
       }
+      if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
       // leave the maps empty for the next env of this warp: un-write every cell that can hold an entry
       // (a non-zero owner entry always has its owner standing on it)
 #pragma unroll
@@ -689,9 +709,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
         if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
       }
-    } else if (lane < 2) {
-      p.new_off[lane][env] = 0;
-      p.new_cnt[lane][env] = 0;
+    } else {
+      if (lane < 2) {
+        p.new_off[lane][env] = 0;
+        p.new_cnt[lane][env] = 0;
+      }
+      if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
       p.env_flags[env] = (uint8_t)env_flags;
@@ -845,50 +868,52 @@ __global__ void ppg_stats_kernel(const uint32_t* __restrict__ counters, const En
 // ------------------------------------------------------------------------------------------------
 // launch wrappers used by ppg_api.cu
 // ------------------------------------------------------------------------------------------------
-template <int W, typename MapT, bool BULK>
+template <int W, typename MapT, bool BULK, bool SPLIT>
 static cudaError_t launch_w(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;  // opt in to > 48 KB of dynamic shared memory (grows monotonically)
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_base_kernel<W, MapT, BULK><<<n_cta, W * 32, smem, stream>>>(p);
+  ppg_step_base_kernel<W, MapT, BULK, SPLIT><<<n_cta, W * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int W, typename MapT, bool BULK>
+template <int W, typename MapT, bool BULK, bool SPLIT>
 static cudaError_t occupancy_w(size_t smem, int* blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_base_kernel<W, MapT, BULK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W, MapT, BULK>, W * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_base_kernel<W, MapT, BULK, SPLIT>, W * 32, smem);
 }
 
+// SPLIT (two-kernel step) exists for one warp per CTA and direct stores only (ppg_create enforces it)
 #define PPG_DISPATCH(FN, ...)                                                                     \
   do {                                                                                            \
     const bool m8 = map_bytes == 1;                                                               \
+    if (split) return m8 ? FN<1, uint8_t, false, true>(__VA_ARGS__) : FN<1, uint16_t, false, true>(__VA_ARGS__); \
     if (warps_per_cta == 1) {                                                                     \
-      if (bulk) return m8 ? FN<1, uint8_t, true>(__VA_ARGS__) : FN<1, uint16_t, true>(__VA_ARGS__); \
-      return m8 ? FN<1, uint8_t, false>(__VA_ARGS__) : FN<1, uint16_t, false>(__VA_ARGS__);       \
+      if (bulk) return m8 ? FN<1, uint8_t, true, false>(__VA_ARGS__) : FN<1, uint16_t, true, false>(__VA_ARGS__); \
+      return m8 ? FN<1, uint8_t, false, false>(__VA_ARGS__) : FN<1, uint16_t, false, false>(__VA_ARGS__);       \
     }                                                                                             \
     if (warps_per_cta == 4) {                                                                     \
-      if (bulk) return m8 ? FN<4, uint8_t, true>(__VA_ARGS__) : FN<4, uint16_t, true>(__VA_ARGS__); \
-      return m8 ? FN<4, uint8_t, false>(__VA_ARGS__) : FN<4, uint16_t, false>(__VA_ARGS__);       \
+      if (bulk) return m8 ? FN<4, uint8_t, true, false>(__VA_ARGS__) : FN<4, uint16_t, true, false>(__VA_ARGS__); \
+      return m8 ? FN<4, uint8_t, false, false>(__VA_ARGS__) : FN<4, uint16_t, false, false>(__VA_ARGS__);       \
     }                                                                                             \
     if (warps_per_cta == 8) {                                                                     \
-      if (bulk) return m8 ? FN<8, uint8_t, true>(__VA_ARGS__) : FN<8, uint16_t, true>(__VA_ARGS__); \
-      return m8 ? FN<8, uint8_t, false>(__VA_ARGS__) : FN<8, uint16_t, false>(__VA_ARGS__);       \
+      if (bulk) return m8 ? FN<8, uint8_t, true, false>(__VA_ARGS__) : FN<8, uint16_t, true, false>(__VA_ARGS__); \
+      return m8 ? FN<8, uint8_t, false, false>(__VA_ARGS__) : FN<8, uint16_t, false, false>(__VA_ARGS__);       \
     }                                                                                             \
     return cudaErrorInvalidValue;                                                                 \
   } while (0)
 
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream) {
   const int map_bytes = p.map_bytes;
-  const bool bulk = p.obs_bulk != 0;
+  const bool bulk = p.obs_bulk != 0, split = p.obs_split != 0;
   PPG_DISPATCH(launch_w, p, n_cta, smem, stream);
 }
 
-cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, size_t smem, int* blocks_per_sm) {
+cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, bool split, size_t smem, int* blocks_per_sm) {
   PPG_DISPATCH(occupancy_w, smem, blocks_per_sm);
 }
 

@@ -73,6 +73,11 @@ enum : unsigned char {
   F_BORNROW = 128 // ECO: the newborn's row was written at birth (kept if the episode ends on this step, ECO:417-420)
 };
 
+// header of an env image (ints)
+enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_MODE, IH_KEEP, IH_INTS = 16 };
+#define DSC_SKIP 0xFFFFu  // the row was written by the step kernel (captured at the moment of death / birth)
+#define DSC_ZERO 0xFFFEu  // STAG: ended agents are observed as all-zero rows
+
 struct StepParams {
   // ---- config ----
   int B, G, GG, C;
@@ -164,6 +169,19 @@ struct StepParams {
   uint8_t* ag_face;   // [B][cap0] predator facing, index into _predator_facing_options (STAG:197-206)
   double* ag_trait;   // [B][cap0] predator_cooperation_trait (STAG:230)
   int so_trait, so_face, so_join;
+  // ---- two-kernel step (ppg_obs.cu): the step kernel leaves, per env, an IMAGE of what the observation writer needs ----
+  //   image = [16-int header][value tables][padded maps][wall table][row descriptors]: one contiguous range of the env's
+  //   shared-memory slice [so_img, so_img + img_bytes), dumped to obs_img + env * img_stride and fetched back by the
+  //   observation kernel with one bulk asynchronous copy (TMA engine) per env
+  int obs_split;            // 1: rows are written by ppg_obs_kernel after the step kernel; 0: by the step kernel itself
+  int so_img, img_bytes, img_stride;
+  int so_ihdr;              // header ints: IH_* below
+  int so_dsc[2];            // u16 [cap]: padded cell index of the window centre of the k-th row of the env, or DSC_SKIP / DSC_ZERO
+  int so_dsx[2];            // u32 [cap]: ECO own-speed plane value (float bits); STAG ihi | jhi << 8 (cut-off forward view)
+  unsigned char* obs_img;   // [B][img_stride]
+  unsigned long long* nb_info[2];  // [B][cap] per newborn of this launch: id | row flags << 16 | list position << 32 (0xFFFF: not kept)
+  unsigned long long* obs_ticket;  // env ticket counter of the observation kernel (monotonic over launches)
+  unsigned long long obs_ticket_base;
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
                         //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };

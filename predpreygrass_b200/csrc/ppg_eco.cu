@@ -75,13 +75,14 @@ __device__ __forceinline__ unsigned next_in_seq_order(const uint16_t* const seq[
   return __reduce_min_sync(FULL, best);
 }
 
-template <int W, typename MapT>
+template <int W, typename MapT, bool SPLIT>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
   const EcoSmem<MapT> X = carve_eco<MapT>(sbase, p);
+  const RowDesc D = carve_desc(sbase, p);
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
   const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const unsigned epoch = p.epoch;
@@ -655,7 +656,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
         if (pass == 1) {
           if (births[0] + births[1] == 0) break;
-          if (!have_new_base) {
+          // SPLIT: the observation kernel places the newborn rows (nobody waits here)
+          if (!SPLIT && !have_new_base) {
             int nb0 = 0, nb1 = 0;
             if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
               if (lane == 0) atomicOr(p.error, 1u);
@@ -671,12 +673,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           const int elems = p.elems[s];
           const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
           if (k_lo >= tot) continue;
-          const RowRel rr = load_rel(p, s, sb32, lane);
+          RowRel rr;
+          if (!SPLIT) rr = load_rel(p, s, sb32, lane);
           for (int b0 = k_lo; b0 < tot; b0 += 32) {
             const int slot = b0 + lane;
             int row = 0, cellp = 0;
             bool alive = false, emit = false;
             float sv = 0.f;
+            unsigned nb_lab = 0;
             if (slot < tot) {
               const bool newborn = slot >= SEL(n);
               row = newborn ? SEL(new_base) + (slot - SEL(n)) : SEL(old_base) + slot;
@@ -697,17 +701,21 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               if (mode == 1) rf |= PPG_ROW_FOUNDER;
               if (f & F_ATE) rf |= PPG_ROW_ATE;
               if (alive && (f & F_CARC)) rf |= PPG_ROW_CARCASS;
-              p.row_env[s][row] = env;
-              p.row_agent[s][row] = SEL(S.id)[slot];
-              p.reward[s][row] = (float)rew;
-              p.flags[s][row] = (uint8_t)rf;
+              if (!(SPLIT && newborn)) {
+                p.row_env[s][row] = env;
+                p.row_agent[s][row] = SEL(S.id)[slot];
+                p.reward[s][row] = (float)rew;
+                p.flags[s][row] = (uint8_t)rf;
+              }
+              nb_lab = (unsigned)SEL(S.id)[slot] | (rf << 16);
               cellp = CELLP((unsigned)SEL(S.pos)[slot]);
               emit = alive && !(done && (f & F_BORNROW));  // a newborn of the episode's last step keeps its at-birth observation
               sv = speed_plane(p, SEL(X.spd)[slot]);
             }
             const unsigned ma = __ballot_sync(FULL, alive);
+            int dst = 0xFFFF;
             if (keep && alive) {
-              const int dst = SEL(wpos) + __popc(ma & lt_mask);
+              dst = SEL(wpos) + __popc(ma & lt_mask);
               p.ag_id[s][sb + dst] = SEL(S.id)[slot];
               p.ag_pos[s][sb + dst] = SEL(S.pos)[slot];
               p.ag_e[s][sb + dst] = SEL(S.E)[slot];
@@ -718,23 +726,32 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
             }
             if (s == 0) wpos[0] += __popc(ma); else wpos[1] += __popc(ma);
-            unsigned m = __ballot_sync(FULL, emit);
-            while (m) {
-              const int l = __ffs(m) - 1;
-              m &= m - 1;
-              const int cp = __shfl_sync(FULL, cellp, l);
-              const int r = __shfl_sync(FULL, row, l);
-              const float selfv = __shfl_sync(FULL, sv, l);
-              emit_row<MapT, false, true>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane, selfv);
+            if (SPLIT) {
+              if (slot < tot) {
+                SEL(D.dsc)[slot] = (uint16_t)(emit ? (unsigned)cellp : DSC_SKIP);
+                SEL(D.dsx)[slot] = __float_as_uint(sv);
+                if (pass == 1) p.nb_info[s][sb + (slot - SEL(n))] = (unsigned long long)nb_lab | ((unsigned long long)(unsigned)dst << 32);
+              }
+            } else {
+              unsigned m = __ballot_sync(FULL, emit);
+              while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int cp = __shfl_sync(FULL, cellp, l);
+                const int r = __shfl_sync(FULL, row, l);
+                const float selfv = __shfl_sync(FULL, sv, l);
+                emit_row<MapT, false, true>(p, sb32, obs_s + (size_t)r * elems, cp, s, rr, rowctr, lane, selfv);
+              }
             }
           }
         }
       }
       if (lane < 2) {
         const int nb = lane == 0 ? births[0] : births[1];
-        p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
+        if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
         p.new_cnt[lane][env] = nb;
       }
+      if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
       // leave the maps empty for the next env of this warp.  A carcass bitten after it aged out keeps an entry while its
       // owner is gone, so every loaded slot is un-written, alive or not.
 #pragma unroll
@@ -775,9 +792,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
         if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
       }
-    } else if (lane < 2) {
-      p.new_off[lane][env] = 0;
-      p.new_cnt[lane][env] = 0;
+    } else {
+      if (lane < 2) {
+        p.new_off[lane][env] = 0;
+        p.new_cnt[lane][env] = 0;
+      }
+      if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
       p.env_flags[env] = (uint8_t)env_flags;
@@ -798,31 +818,33 @@ __global__ void ppg_set_tape_reals_kernel(EcoHdr* ehdr, int B, const long long* 
   ehdr[e].real_end = real_off ? real_off[e + 1] : 0;
 }
 
-template <typename MapT>
+template <typename MapT, bool SPLIT>
 static cudaError_t launch_eco_t(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_eco_kernel<1, MapT><<<n_cta, 32, smem, stream>>>(p);
+  ppg_step_eco_kernel<1, MapT, SPLIT><<<n_cta, 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  return p.map_bytes == 1 ? launch_eco_t<uint8_t>(p, n_cta, smem, stream) : launch_eco_t<uint16_t>(p, n_cta, smem, stream);
+  if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true>(p, n_cta, smem, stream);
+  return p.map_bytes == 1 ? launch_eco_t<uint8_t, false>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false>(p, n_cta, smem, stream);
 }
 
-cudaError_t step_eco_occupancy(int map_bytes, size_t smem, int* blocks_per_sm) {
-  if (map_bytes == 1) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, uint8_t>, 32, smem);
-  }
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <typename MapT, bool SPLIT>
+static cudaError_t occupancy_eco_t(size_t smem, int* blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, uint16_t>, 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, MapT, SPLIT>, 32, smem);
+}
+
+cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
+  if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true>(smem, blocks_per_sm);
+  return map_bytes == 1 ? occupancy_eco_t<uint8_t, false>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false>(smem, blocks_per_sm);
 }
 
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s) {

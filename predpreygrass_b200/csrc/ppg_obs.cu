@@ -1,0 +1,209 @@
+// ppg_obs.cu — the observation writer of the two-kernel step (all env variants).
+//
+// `_get_observation` (BASE:511-539, ECO:700-730, STAG:944-1008) produces > 90 % of the bytes of a step and has no
+// order dependence at all, while the rest of `step()` is a latency-bound walk through order-dependent phases.  The
+// step kernels (ppg_base.cu / ppg_eco.cu / ppg_stag.cu) therefore stop after the state update and leave, per env, an
+// IMAGE in HBM: [header | fp32 value tables | row descriptors | padded owner maps | wall table] — exactly the bytes
+// their in-kernel row writer would have gathered from.  This kernel turns images into observation rows:
+//
+//   * one CTA (4 warps) works on one env at a time; envs are drawn from a ticket counter (populations differ 10x);
+//   * the image (5–10 KB) arrives in shared memory as ONE bulk asynchronous copy (cp.async.bulk global -> shared,
+//     TMA engine, completion on an mbarrier), double buffered: the copy of the next env is in flight while the rows
+//     of the current one are written;
+//   * a warp writes whole rows: per lane 8–13 map-entry loads, then 8–13 value-table loads at per-lane constant
+//     offsets (emit_row_t, ppg_step_common.cuh), then 2–3 `st.global.cs.v4.f32` — every row is a contiguous 784 /
+//     1296 / 1620-byte streaming store;
+//   * it also PLACES the newborn rows: by now every env has published its birth count, so the exclusive prefix over
+//     the envs before is a plain read (the one-kernel design had every env with newborns spin-wait for its
+//     predecessors; that wait was 60 % of the ECO / STAG step kernels, profiles/r01_fused_*).  Row labels of the
+//     newborns, `new_off` and the newborns' `ag_prow` (the row their next action is read from) are written here.
+//
+// Rows of agents that died mid-step were captured by the step kernel at that moment (DSC_SKIP).
+#include <cuda_runtime.h>
+
+#include "ppg_step_common.cuh"
+
+namespace ppg {
+
+#define OBS_WARPS 4
+#define OBS_THREADS (OBS_WARPS * 32)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// bulk asynchronous global -> shared copy (TMA engine, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+               "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// KIND: 0 = BASE family, 1 = ECO (own-speed plane), 2 = STAG (cut-off forward view, all-zero rows of ended agents)
+template <typename MapT, int KIND>
+__global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ int s_tk[2];
+  __shared__ int s_nb[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned stride = (unsigned)p.img_stride, img_bytes = (unsigned)p.img_bytes;
+  const unsigned img0 = smem_u32(smem_img), bar0 = smem_u32(&s_bar[0]);
+  const unsigned epoch = p.epoch;
+  const int par = (int)(epoch & 1u);
+  const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
+
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    const int t = (int)(atomicAdd(p.obs_ticket, 1ULL) - p.obs_ticket_base);
+    s_tk[0] = t;
+    if (t < p.B) {
+      mbar_expect_tx(bar0, img_bytes);
+      bulk_load(img0, p.obs_img + (size_t)t * stride, img_bytes, bar0);
+    }
+  }
+  __syncthreads();
+  int env = s_tk[0];
+  unsigned stage = 0, phase = 0;  // bit s of phase: parity the barrier of buffer s completes next
+  unsigned rowctr = 0;
+
+  while (env < p.B) {
+    if (tid == 0) {
+      // next env: its image streams into the other buffer (all reads of that buffer ended before the last barrier)
+      const int t = (int)(atomicAdd(p.obs_ticket, 1ULL) - p.obs_ticket_base);
+      s_tk[stage ^ 1u] = t;
+      if (t < p.B) {
+        mbar_expect_tx(bar0 + 8u * (stage ^ 1u), img_bytes);
+        bulk_load(img0 + (stage ^ 1u) * stride, p.obs_img + (size_t)t * stride, img_bytes, bar0 + 8u * (stage ^ 1u));
+      }
+    }
+    mbar_wait(bar0 + 8u * stage, (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+
+    const unsigned char* ibp = smem_img + (size_t)stage * stride;
+    const unsigned vb32 = img0 + stage * stride - (unsigned)p.so_img;  // virtual base: so_* offsets address the image
+    const int* ih = reinterpret_cast<const int*>(ibp + (p.so_ihdr - p.so_img));
+    const int old_base[2] = {ih[IH_OLD_BASE0], ih[IH_OLD_BASE1]};
+    const int n[2] = {ih[IH_N0], ih[IH_N1]};
+    const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
+    int new_base[2] = {0, 0};
+
+    if (births[0] + births[1] > 0) {
+      // first newborn row of this env = old rows of all envs + births of the envs before it (all published)
+      if (warp == 0) {
+        int nb0 = 0, nb1 = 0;
+        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, false, lane, nb0, nb1)) {
+          if (lane == 0) atomicOr(p.error, 1u);
+        }
+        if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; }
+      }
+      __syncthreads();
+      new_base[0] = s_nb[0]; new_base[1] = s_nb[1];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const size_t sb = (size_t)env * p.cap[s];
+        for (int j = tid; j < births[s]; j += OBS_THREADS) {
+          const unsigned long long info = p.nb_info[s][sb + j];
+          const int row = new_base[s] + j;
+          p.row_env[s][row] = env;
+          p.row_agent[s][row] = (int)(info & 0xFFFFu);
+          p.reward[s][row] = 0.f;  // a newborn's first reward is 0 in every variant (BASE:443, ECO:1161, STAG:1573)
+          p.flags[s][row] = (uint8_t)((info >> 16) & 0xFFu);
+          const unsigned dst = (unsigned)(info >> 32) & 0xFFFFu;
+          if (dst != 0xFFFFu) p.ag_prow[s][sb + dst] = row;  // the newborn's first action is read from this row
+        }
+      }
+      if (tid < 2) p.new_off[tid][env] = births[tid] > 0 ? new_base[tid] : 0;
+    } else if (tid < 2) {
+      p.new_off[tid][env] = 0;
+    }
+
+    // rows: warp w takes every 4th row of the env (round robin across both species)
+    int rot = 0;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+      const int T = n[s] + births[s];
+      const int k0 = (warp + 4 * OBS_WARPS - rot) % OBS_WARPS;
+      rot = (rot + T) % OBS_WARPS;
+      if (k0 >= T) continue;
+      const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
+      const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
+      const RowRel rr = load_rel(p, s, vb32, lane);
+      const int elems = p.elems[s];
+      float* obs_s = p.obs[s];
+      for (int k = k0; k < T; k += OBS_WARPS) {
+        const unsigned d = dsc[k];
+        if (d == DSC_SKIP) continue;
+        const int row = k < n[s] ? old_base[s] + k : new_base[s] + (k - n[s]);
+        float* dst = obs_s + (size_t)row * elems;
+        if (KIND == 1) {
+          emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
+        } else if (KIND == 2) {
+          if (d == DSC_ZERO) { zero_row(dst, elems, lane); continue; }
+          const unsigned x = dsx[k];
+          const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
+          if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+          else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
+        } else {
+          emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+        }
+      }
+    }
+    __syncthreads();  // every read of this buffer is done; the ticket drawn at the top is visible
+    env = s_tk[stage ^ 1u];
+    stage ^= 1u;
+  }
+}
+
+template <typename MapT, int KIND>
+static cudaError_t launch_obs_t(const StepParams& p, int n_cta, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)p.img_stride;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_bytes = smem;
+  }
+  ppg_obs_kernel<MapT, KIND><<<n_cta, OBS_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename MapT, int KIND>
+static cudaError_t occupancy_obs_t(const StepParams& p, int* blocks_per_sm) {
+  const size_t smem = 2 * (size_t)p.img_stride;
+  cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_obs_kernel<MapT, KIND>, OBS_THREADS, smem);
+}
+
+#define PPG_OBS_DISPATCH(FN, ...)                                                                           \
+  do {                                                                                                      \
+    const bool m8 = p.map_bytes == 1;                                                                       \
+    if (p.variant == PPG_VARIANT_ECO) return m8 ? FN<uint8_t, 1>(__VA_ARGS__) : FN<uint16_t, 1>(__VA_ARGS__);  \
+    if (p.variant == PPG_VARIANT_STAG) return m8 ? FN<uint8_t, 2>(__VA_ARGS__) : FN<uint16_t, 2>(__VA_ARGS__); \
+    return m8 ? FN<uint8_t, 0>(__VA_ARGS__) : FN<uint16_t, 0>(__VA_ARGS__);                                 \
+  } while (0)
+
+cudaError_t launch_obs(const StepParams& p, int n_cta, cudaStream_t stream) { PPG_OBS_DISPATCH(launch_obs_t, p, n_cta, stream); }
+cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm) { PPG_OBS_DISPATCH(occupancy_obs_t, p, blocks_per_sm); }
+
+}  // namespace ppg

@@ -100,37 +100,14 @@ __device__ __forceinline__ int stag_view(const StepParams& p, int s, unsigned ps
   return CELLXY(x, y);
 }
 
-// a row whose window is cut off (saturated forward view): element (c, i, j) is zero unless i <= ihi and j <= jhi
-template <typename MapT>
-__device__ __noinline__ void emit_row_masked(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, int ihi, int jhi, int lane) {
-  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
-  const bool vec = p.obs_vec[s] != 0;
-  const int R = p.R[s], RR = R * R;
-#pragma unroll 1
-  for (int j = 0; j < p.nj[s]; ++j) {
-    const int q = vec ? 4 * (lane + 32 * (j >> 2)) + (j & 3) : lane + 32 * j;
-    if (q < p.elems[s]) {
-      const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
-      float x = lds_f32(sb32 + (unsigned)v.y + 4u * lds_map<MapT>(a0 + (unsigned)v.x));
-      const int r = q % RR;
-      if (r / R > ihi || r % R > jhi) x = 0.f;
-      __stcs(dst + q, x);
-    }
-  }
-}
-
-// ended agents are observed as all-zero rows (STAG:596-612)
-__device__ __forceinline__ void zero_row(float* dst, int elems, int lane) {
-  for (int q = lane; q < elems; q += 32) __stcs(dst + q, 0.f);
-}
-
-template <int W, typename MapT>
+template <int W, typename MapT, bool SPLIT>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
   const StagSmem<MapT> X = carve_stag<MapT>(sbase, p);
+  const RowDesc D = carve_desc(sbase, p);
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(sbase);
   const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const unsigned epoch = p.epoch;
@@ -797,12 +774,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
         if (pass == 1) {
           if (births[0] + births[1] == 0) break;
-          int nb0 = 0, nb1 = 0;
-          if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
-            if (lane == 0) atomicOr(p.error, 1u);
+          if (!SPLIT) {  // SPLIT: the observation kernel places the newborn rows (nobody waits here)
+            int nb0 = 0, nb1 = 0;
+            if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+              if (lane == 0) atomicOr(p.error, 1u);
+            }
+            new_base[0] = n_old_total[0] + nb0;
+            new_base[1] = n_old_total[1] + nb1;
           }
-          new_base[0] = n_old_total[0] + nb0;
-          new_base[1] = n_old_total[1] + nb1;
         }
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
@@ -811,11 +790,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
           const int elems = p.elems[s];
           const int k_lo = pass == 0 ? 0 : SEL(n), tot = pass == 0 ? SEL(n) : SEL(n) + SEL(births);
           if (k_lo >= tot) continue;
-          const RowRel rr = load_rel(p, s, sb32, lane);
+          RowRel rr;
+          if (!SPLIT) rr = load_rel(p, s, sb32, lane);
           for (int b0 = k_lo; b0 < tot; b0 += 32) {
             const int slot = b0 + lane;
             int row = 0, cellp = 0, ihi = 0, jhi = 0;
             bool alive = false, valid = false;
+            unsigned nb_lab = 0;
             if (slot < tot) {
               valid = true;
               const bool newborn = slot >= SEL(n);
@@ -834,15 +815,19 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
               if (mode == 1) rf |= PPG_ROW_FOUNDER;
               if (f & F_ATE) rf |= PPG_ROW_ATE;
-              p.row_env[s][row] = env;
-              p.row_agent[s][row] = SEL(S.id)[slot];
-              p.reward[s][row] = (float)rew;
-              p.flags[s][row] = (uint8_t)rf;
+              if (!(SPLIT && newborn)) {
+                p.row_env[s][row] = env;
+                p.row_agent[s][row] = SEL(S.id)[slot];
+                p.reward[s][row] = (float)rew;
+                p.flags[s][row] = (uint8_t)rf;
+              }
+              nb_lab = (unsigned)SEL(S.id)[slot] | (rf << 16);
               cellp = stag_view(p, s, SEL(S.pos)[slot], s == 0 ? (int)X.face[slot] : 0, PP, PS, ihi, jhi);
             }
             const unsigned ma = __ballot_sync(FULL, alive);
+            int dst = 0xFFFF;
             if (keep && alive) {
-              const int dst = SEL(wpos) + __popc(ma & lt_mask);
+              dst = SEL(wpos) + __popc(ma & lt_mask);
               p.ag_id[s][sb + dst] = SEL(S.id)[slot];
               p.ag_pos[s][sb + dst] = SEL(S.pos)[slot];
               p.ag_e[s][sb + dst] = SEL(S.E)[slot];
@@ -851,6 +836,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               if (s == 0) { p.ag_face[sb + dst] = X.face[slot]; p.ag_trait[sb + dst] = X.trait[slot]; }
             }
             if (s == 0) wpos[0] += __popc(ma); else wpos[1] += __popc(ma);
+            if (SPLIT) {
+              if (valid) {
+                SEL(D.dsc)[slot] = (uint16_t)(alive ? (unsigned)cellp : DSC_ZERO);  // ended: all-zero observation (STAG:596-612)
+                SEL(D.dsx)[slot] = (unsigned)ihi | ((unsigned)jhi << 8);
+                if (pass == 1) p.nb_info[s][sb + (slot - SEL(n))] = (unsigned long long)nb_lab | ((unsigned long long)(unsigned)dst << 32);
+              }
+              continue;
+            }
             unsigned m = __ballot_sync(FULL, valid);
             while (m) {
               const int l = __ffs(m) - 1;
@@ -868,9 +861,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       }
       if (lane < 2) {
         const int nb = lane == 0 ? births[0] : births[1];
-        p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
+        if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
         p.new_cnt[lane][env] = nb;
       }
+      if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
       // leave the maps empty for the next env of this warp: every loaded or born slot un-writes its cell in its channel
       for (int i = lane; i < n[0] + births[0]; i += 32) S.map[0][CELLP((unsigned)S.pos[0][i])] = 0;
       for (int i = lane; i < n[1] + births[1]; i += 32) prey_map(i)[CELLP((unsigned)S.pos[1][i])] = 0;
@@ -910,9 +904,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
         if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
       }
-    } else if (lane < 2) {
-      p.new_off[lane][env] = 0;
-      p.new_cnt[lane][env] = 0;
+    } else {
+      if (lane < 2) {
+        p.new_off[lane][env] = 0;
+        p.new_cnt[lane][env] = 0;
+      }
+      if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
       p.env_flags[env] = (uint8_t)env_flags;
@@ -956,31 +953,33 @@ __global__ void ppg_random_actions_stag_kernel(const int32_t* __restrict__ n_row
   }
 }
 
-template <typename MapT>
+template <typename MapT, bool SPLIT>
 static cudaError_t launch_stag_t(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_stag_kernel<1, MapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_stag_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_stag_kernel<1, MapT><<<n_cta, 32, smem, stream>>>(p);
+  ppg_step_stag_kernel<1, MapT, SPLIT><<<n_cta, 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_step_stag(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  return p.map_bytes == 1 ? launch_stag_t<uint8_t>(p, n_cta, smem, stream) : launch_stag_t<uint16_t>(p, n_cta, smem, stream);
+  if (p.obs_split) return p.map_bytes == 1 ? launch_stag_t<uint8_t, true>(p, n_cta, smem, stream) : launch_stag_t<uint16_t, true>(p, n_cta, smem, stream);
+  return p.map_bytes == 1 ? launch_stag_t<uint8_t, false>(p, n_cta, smem, stream) : launch_stag_t<uint16_t, false>(p, n_cta, smem, stream);
 }
 
-cudaError_t step_stag_occupancy(int map_bytes, size_t smem, int* blocks_per_sm) {
-  if (map_bytes == 1) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_stag_kernel<1, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_stag_kernel<1, uint8_t>, 32, smem);
-  }
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_stag_kernel<1, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <typename MapT, bool SPLIT>
+static cudaError_t occupancy_stag_t(size_t smem, int* blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_stag_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_stag_kernel<1, uint16_t>, 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_stag_kernel<1, MapT, SPLIT>, 32, smem);
+}
+
+cudaError_t step_stag_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
+  if (split) return map_bytes == 1 ? occupancy_stag_t<uint8_t, true>(smem, blocks_per_sm) : occupancy_stag_t<uint16_t, true>(smem, blocks_per_sm);
+  return map_bytes == 1 ? occupancy_stag_t<uint8_t, false>(smem, blocks_per_sm) : occupancy_stag_t<uint16_t, false>(smem, blocks_per_sm);
 }
 
 cudaError_t launch_set_tape_reals_stag(StagHdr* shdr, int B, const long long* real_off, cudaStream_t s) {

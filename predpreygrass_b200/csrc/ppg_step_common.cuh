@@ -66,6 +66,51 @@ __device__ __forceinline__ EnvSmem<MapT> carve(unsigned char* base, const StepPa
   return s;
 }
 
+// two-kernel step: row descriptors inside the env image and the image dump
+struct RowDesc {
+  uint16_t* dsc[2];  // padded cell index of the window centre of the k-th row (k < n: rows of the agents that acted, in
+                     // output order; k >= n: newborns in birth order), or DSC_SKIP / DSC_ZERO
+  unsigned* dsx[2];  // ECO: own-speed plane value (float bits); STAG: ihi | jhi << 8
+};
+__device__ __forceinline__ RowDesc carve_desc(unsigned char* base, const StepParams& p) {
+  RowDesc d;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    d.dsc[k] = reinterpret_cast<uint16_t*>(base + p.so_dsc[k]);
+    d.dsx[k] = reinterpret_cast<unsigned*>(base + p.so_dsx[k]);
+  }
+  return d;
+}
+
+// Writes the image header and copies the image range of the env's shared-memory slice to HBM (coalesced 16-byte
+// stores, default caching: the observation kernel reads it back from L2 a few microseconds later).  mode 0 (idle
+// env): header only, zero rows.
+__device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParams& p, int env, int mode, bool keep, const int old_base[2],
+                                           const int n[2], const int births[2], int lane) {
+  int* ih = reinterpret_cast<int*>(sbase + p.so_ihdr);
+  if (lane < IH_INTS) {
+    int v = 0;
+    switch (lane) {
+      case IH_OLD_BASE0: v = old_base[0]; break;
+      case IH_OLD_BASE1: v = old_base[1]; break;
+      case IH_N0: v = mode ? n[0] : 0; break;
+      case IH_N1: v = mode ? n[1] : 0; break;
+      case IH_BIRTHS0: v = mode ? births[0] : 0; break;
+      case IH_BIRTHS1: v = mode ? births[1] : 0; break;
+      case IH_MODE: v = mode; break;
+      case IH_KEEP: v = keep ? 1 : 0; break;
+      default: break;
+    }
+    ih[lane] = v;
+  }
+  __syncwarp();
+  const uint4* src = reinterpret_cast<const uint4*>(sbase + p.so_img);
+  uint4* dst = reinterpret_cast<uint4*>(p.obs_img + (size_t)env * p.img_stride);
+  const int n16 = mode ? p.img_bytes >> 4 : (IH_INTS * 4) >> 4;
+  for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
 // ------------------------------------------------------------------------------------------------
@@ -257,6 +302,30 @@ __device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, flo
     case 3: emit_row_t<MapT, 13, false, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;  // (5,9,9): 405 floats
     default: rowctr = emit_row_generic<MapT, BULK>(p, sb32, dst, cellp, s, rowctr, lane, SELF ? r.self : 0u, selfv);
   }
+}
+
+// a row whose window is cut off (saturated forward view): element (c, i, j) is zero unless i <= ihi and j <= jhi
+template <typename MapT>
+__device__ __noinline__ void emit_row_masked(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, int ihi, int jhi, int lane) {
+  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
+  const bool vec = p.obs_vec[s] != 0;
+  const int R = p.R[s], RR = R * R;
+#pragma unroll 1
+  for (int j = 0; j < p.nj[s]; ++j) {
+    const int q = vec ? 4 * (lane + 32 * (j >> 2)) + (j & 3) : lane + 32 * j;
+    if (q < p.elems[s]) {
+      const int2 v = __ldg(p.obs_rel + (s * PPG_MAX_NJ + j) * 32 + lane);
+      float x = lds_f32(sb32 + (unsigned)v.y + 4u * lds_map<MapT>(a0 + (unsigned)v.x));
+      const int r = q % RR;
+      if (r / R > ihi || r % R > jhi) x = 0.f;
+      __stcs(dst + q, x);
+    }
+  }
+}
+
+// ended agents are observed as all-zero rows (STAG:596-612)
+__device__ __forceinline__ void zero_row(float* dst, int elems, int lane) {
+  for (int q = lane; q < elems; q += 32) __stcs(dst + q, 0.f);
 }
 
 // rows of agents that die mid-step: the reference captures them at that moment (BASE:287,327)
