@@ -16,7 +16,7 @@ SYMBOLS = [
     "ppg_abi_version", "ppg_default_config", "ppg_create", "ppg_destroy", "ppg_load_tape", "ppg_reset", "ppg_step",
     "ppg_step_ordered", "ppg_step_host", "ppg_random_actions", "ppg_get_buffers", "ppg_snapshot_size", "ppg_snapshot", "ppg_restore",
     "ppg_read_env", "ppg_read_env_eco", "ppg_read_env_stag", "ppg_stats", "ppg_stats_device", "ppg_stats_clear", "ppg_launch_count", "ppg_last_error",
-    "ppg_profile_begin", "ppg_profile_end",
+    "ppg_profile_begin", "ppg_profile_end", "ppg_profile_env_cycles",
 ]
 
 _lib = None
@@ -65,6 +65,7 @@ def load():
     L.ppg_launch_count.argtypes = [vp]
     L.ppg_launch_count.restype = C.c_int64
     L.ppg_profile_begin.argtypes = [vp]
+    L.ppg_profile_env_cycles.argtypes = [vp, vp, vp, vp]
     L.ppg_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]
     L.ppg_last_error.argtypes = [vp]
     L.ppg_last_error.restype = C.c_char_p

@@ -220,6 +220,12 @@ class BatchedPredPreyGrass:
     def launch_count(self):
         return int(self.L.ppg_launch_count(self.h))
 
+    def profile_env_cycles(self):
+        """-> (cycles[n_envs], info[n_envs]) of the last step-kernel launch (include/ppg.h)"""
+        cyc, info = np.zeros(self.n_envs, np.uint32), np.zeros(self.n_envs, np.uint32)
+        _lib.check(self.L.ppg_profile_env_cycles(self.h, cyc.ctypes.data, info.ctypes.data, self._stream()), self.h)
+        return cyc, info
+
     def profile_begin(self):
         """start timing the kernels of every step with CUDA events on the step's stream (include/ppg.h)"""
         _lib.check(self.L.ppg_profile_begin(self.h), self.h)

@@ -411,7 +411,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   // two-kernel step (default): the step kernel leaves env images, ppg_obs_kernel writes the observation rows
   P.obs_split = 1;
   if (const char* ev = getenv("PPG_OBS_SPLIT")) P.obs_split = atoi(ev) != 0;
-  if (W != 1 || P.obs_bulk || P.CH >= (int)DSC_ZERO) P.obs_split = 0;
+  if (W != 1 || P.obs_bulk || P.CH >= (int)DSC_COPY) P.obs_split = 0;
   h->warps_per_cta = W;
   h->smem_bytes = (size_t)W * P.smem_per_env;
   {
@@ -460,6 +460,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.counters, (size_t)B * PPG_N_STATS));
   CKC(dalloc(h, &P.ticket, 1));
+  CKC(dalloc(h, &P.env_cycles, (size_t)B));
   if (P.obs_split) {
     void* q = nullptr;
     CKC(cudaMalloc(&q, (size_t)B * (size_t)P.img_stride));  // not cleared: every launch writes every env's header
@@ -467,6 +468,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.obs_img = static_cast<unsigned char*>(q);
     for (int s = 0; s < 2; ++s) CKC(dalloc(h, &P.nb_info[s], (size_t)B * P.cap[s]));
     CKC(dalloc(h, &P.obs_ticket, 1));
+    if (eco)
+      for (int s = 0; s < 2; ++s) CKC(dalloc(h, &P.born_obs[s], (size_t)B * PPG_BORN_K * (size_t)P.elems[s]));
     int per_sm = 0, n_sm = 0;
     CKC(obs_occupancy(P, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -925,6 +928,17 @@ int ppg_stats_clear(ppg_handle h, void* cuda_stream) {
 }
 
 int64_t ppg_launch_count(ppg_handle h) { return h ? h->launch_count : 0; }
+
+int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, void* cuda_stream) {
+  if (!h || !cycles) return PPG_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(h->device));
+  std::vector<uint2> tmp((size_t)h->B);
+  CK(cudaMemcpyAsync(tmp.data(), h->P.env_cycles, sizeof(uint2) * (size_t)h->B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int e = 0; e < h->B; ++e) { cycles[e] = tmp[(size_t)e].x; if (info) info[e] = tmp[(size_t)e].y; }
+  return PPG_OK;
+}
 
 int ppg_profile_begin(ppg_handle h) {
   if (!h) return PPG_ERR_INVALID;

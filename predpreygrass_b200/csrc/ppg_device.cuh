@@ -77,6 +77,8 @@ enum : unsigned char {
 enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_MODE, IH_KEEP, IH_INTS = 16 };
 #define DSC_SKIP 0xFFFFu  // the row was written by the step kernel (captured at the moment of death / birth)
 #define DSC_ZERO 0xFFFEu  // STAG: ended agents are observed as all-zero rows
+#define DSC_COPY 0xFFFDu  // ECO: the row was captured at birth into born_obs[env][dsx] (episode ended on this step, ECO:417-420)
+#define PPG_BORN_K 4      // at-birth rows kept per env and species; further ones take the (blocking) direct path
 
 struct StepParams {
   // ---- config ----
@@ -180,6 +182,8 @@ struct StepParams {
   int so_dsx[2];            // u32 [cap]: ECO own-speed plane value (float bits); STAG ihi | jhi << 8 (cut-off forward view)
   unsigned char* obs_img;   // [B][img_stride]
   unsigned long long* nb_info[2];  // [B][cap] per newborn of this launch: id | row flags << 16 | list position << 32 (0xFFFF: not kept)
+  float* born_obs[2];       // ECO: [B][PPG_BORN_K][elems] at-birth observations of newborns of an episode's last step
+  uint2* env_cycles;       // [B] profiling: x = SM cycles the step kernel spent on the env in the last launch, y = mode | births << 8 | agents << 16
   unsigned long long* obs_ticket;  // env ticket counter of the observation kernel (monotonic over launches)
   unsigned long long obs_ticket_base;
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2

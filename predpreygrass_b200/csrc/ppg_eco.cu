@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
     bool over = false, trunc = false, done = false, have_new_base = false;
 
+    const long long t_env0 = clock64();
     EnvHdr h = p.hdr[env];
     EcoHdr eh = p.ehdr[env];
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
@@ -603,7 +604,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             eh.next_seq++;
             if (s == 0) eh.active[0] += 1; else eh.active[1] += 1;  // ECO:1157
             __syncwarp();
-            if (maybe_done) {
+            if (SPLIT && maybe_done && cs - SEL(n) < PPG_BORN_K) {
+              // the at-birth observation waits in the env's scratch rows; the observation kernel moves it to its row
+              rowctr = emit_row_now<MapT, false, true>(sbase, p, p.born_obs[s] + ((size_t)env * PPG_BORN_K + (size_t)(cs - SEL(n))) * p.elems[s],
+                                                       CELLXY(sx, sy), s, n[0] + births[0], n[1] + births[1], rowctr, lane,
+                                                       speed_plane(p, SEL(X.spd)[cs]));
+              __syncwarp();
+            } else if (maybe_done) {
               if (!have_new_base) {
                 int nb0 = 0, nb1 = 0;
                 if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
@@ -728,8 +735,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (s == 0) wpos[0] += __popc(ma); else wpos[1] += __popc(ma);
             if (SPLIT) {
               if (slot < tot) {
-                SEL(D.dsc)[slot] = (uint16_t)(emit ? (unsigned)cellp : DSC_SKIP);
-                SEL(D.dsx)[slot] = __float_as_uint(sv);
+                const bool stashed = !emit && alive && slot >= SEL(n) && slot - SEL(n) < PPG_BORN_K;  // at-birth row in born_obs
+                SEL(D.dsc)[slot] = (uint16_t)(emit ? (unsigned)cellp : (stashed ? DSC_COPY : DSC_SKIP));
+                SEL(D.dsx)[slot] = stashed ? (unsigned)(slot - SEL(n)) : __float_as_uint(sv);
                 if (pass == 1) p.nb_info[s][sb + (slot - SEL(n))] = (unsigned long long)nb_lab | ((unsigned long long)(unsigned)dst << 32);
               }
             } else {
@@ -800,6 +808,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
+      p.env_cycles[env] = make_uint2((unsigned)(clock64() - t_env0), (unsigned)mode | ((unsigned)(births[0] + births[1]) << 8) | ((unsigned)(n[0] + n[1]) << 16));
       p.env_flags[env] = (uint8_t)env_flags;
       p.env_status[env] = h.status;
       p.env_step[env] = h.step;

@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_co
         const int row = k < n[s] ? old_base[s] + k : new_base[s] + (k - n[s]);
         float* dst = obs_s + (size_t)row * elems;
         if (KIND == 1) {
+          if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
+            const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
+            for (int q = lane; q < elems; q += 32) __stcs(dst + q, src[q]);
+            continue;
+          }
           emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
         } else if (KIND == 2) {
           if (d == DSC_ZERO) { zero_row(dst, elems, lane); continue; }

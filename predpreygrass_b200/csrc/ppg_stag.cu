@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
     unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0, st_attempts = 0;
     bool over = false, trunc = false, done = false;
 
+    const long long t_env0 = clock64();
     EnvHdr h = p.hdr[env];
     StagHdr sh = p.shdr[env];
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
@@ -912,6 +913,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
+      p.env_cycles[env] = make_uint2((unsigned)(clock64() - t_env0), (unsigned)mode | ((unsigned)(births[0] + births[1]) << 8) | ((unsigned)(n[0] + n[1]) << 16));
       p.env_flags[env] = (uint8_t)env_flags;
       p.env_status[env] = h.status;
       p.env_step[env] = h.step;

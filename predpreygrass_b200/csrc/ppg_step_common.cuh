@@ -456,23 +456,33 @@ static __device__ __noinline__ void philox_placement(int* cells, unsigned* first
   }
 }
 
+// Occupancy marks for the free-cell scans below: scr[cell] = 1 under every live agent (O(n / 32) per warp instead of
+// testing every cell against every agent).  scr is all zero outside its users; unmark_agents restores that.
+template <typename MapT>
+__device__ __forceinline__ void mark_agents(const EnvSmem<MapT>& S, const StepParams& p, const int nl[2], uint8_t v, int lane) {
+  const int PP = p.P, PS = p.PS;
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2)
+    for (int i = lane; i < nl[s2]; i += 32)
+      if (S.flg[s2][i] & F_ALIVE) S.scr[CELLP((unsigned)S.pos[s2][i])] = v;
+  __syncwarp();
+}
+
 // number of cells no live agent stands on (`all_positions - occupied_positions`, STAG:1037-1039)
 template <typename MapT>
 __device__ __noinline__ int count_free_cells(unsigned char* base, const StepParams& p, int nl0, int nl1, int lane) {
   const EnvSmem<MapT> S = carve<MapT>(base, p);
-  const int G = p.G, GG = p.GG;
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const int nl[2] = {nl0, nl1};
+  mark_agents(S, p, nl, 1, lane);
   int n_free = 0;
   for (int c0 = 0; c0 < GG; c0 += 32) {
     const int c = c0 + lane;
-    bool fr = c < GG;
-    if (fr) {
-      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-      for (int s2 = 0; s2 < 2; ++s2)
-        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
-    }
+    const bool fr = c < GG && S.scr[CELLXY(c / G, c % G)] == 0;
     n_free += __popc(__ballot_sync(FULL, fr));
   }
+  __syncwarp();
+  mark_agents(S, p, nl, 0, lane);
   return n_free;
 }
 
@@ -481,38 +491,34 @@ __device__ __noinline__ int count_free_cells(unsigned char* base, const StepPara
 template <typename MapT>
 __device__ __noinline__ int philox_free_cell(unsigned char* base, const StepParams& p, int nl0, int nl1, unsigned draw, int lane) {
   const EnvSmem<MapT> S = carve<MapT>(base, p);
-  const int G = p.G, GG = p.GG;
+  const int G = p.G, GG = p.GG, PP = p.P, PS = p.PS;
   const int nl[2] = {nl0, nl1};
+  mark_agents(S, p, nl, 1, lane);
   int n_free = 0;
   for (int c0 = 0; c0 < GG; c0 += 32) {
     const int c = c0 + lane;
-    bool fr = c < GG;
-    if (fr) {
-      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-      for (int s2 = 0; s2 < 2; ++s2)
-        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
-    }
+    const bool fr = c < GG && S.scr[CELLXY(c / G, c % G)] == 0;
     n_free += __popc(__ballot_sync(FULL, fr));
   }
-  if (n_free == 0) return -1;
-  int kth = (int)ppg_bounded(draw, (unsigned)n_free);
-  for (int c0 = 0; c0 < GG; c0 += 32) {
-    const int c = c0 + lane;
-    bool fr = c < GG;
-    if (fr) {
-      const unsigned cp = (unsigned)(((c / G) << 8) | (c % G));
-      for (int s2 = 0; s2 < 2; ++s2)
-        for (int i = 0; i < nl[s2]; ++i) fr &= !((S.flg[s2][i] & F_ALIVE) && S.pos[s2][i] == cp);
+  int found = -1;
+  if (n_free > 0) {
+    int kth = (int)ppg_bounded(draw, (unsigned)n_free);
+    for (int c0 = 0; c0 < GG; c0 += 32) {
+      const int c = c0 + lane;
+      const bool fr = c < GG && S.scr[CELLXY(c / G, c % G)] == 0;
+      const unsigned fm = __ballot_sync(FULL, fr);
+      const int cnt = __popc(fm);
+      if (kth < cnt) {
+        const int cc = c0 + (int)__fns(fm, 0, kth + 1);
+        found = ((cc / G) << 8) | (cc % G);
+        break;
+      }
+      kth -= cnt;
     }
-    const unsigned fm = __ballot_sync(FULL, fr);
-    const int cnt = __popc(fm);
-    if (kth < cnt) {
-      const int c = c0 + (int)__fns(fm, 0, kth + 1);
-      return ((c / G) << 8) | (c % G);
-    }
-    kth -= cnt;
   }
-  return -1;
+  __syncwarp();
+  mark_agents(S, p, nl, 0, lane);
+  return found;
 }
 
 
