@@ -343,8 +343,10 @@ int64_t ppg_launch_count(ppg_handle h);
  * (ms_obs_kernel = 0 when the handle runs the one-kernel step, PPG_OBS_SPLIT=0). */
 int ppg_profile_begin(ppg_handle h);
 /* SM cycles the step kernel spent on every env in the last launch (host out [n_envs]); info = mode (0 idle, 1 reset,
- * 2 step) | births << 8 | agents << 16.  One warp owns an env for a whole step, so this is the per-env step latency. */
-int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, void* cuda_stream);
+ * 2 step) | births << 8 | agents << 16; start_ns = low 32 bits of the GPU's nanosecond timer when the env was taken;
+ * sm = the SM it ran on (info, start_ns, sm may be NULL).  One warp owns an env for a whole step, so this is the
+ * per-env step latency and the kernel's schedule. */
+int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, uint32_t* start_ns, uint32_t* sm, void* cuda_stream);
 int ppg_profile_end(ppg_handle h, double* ms_step_kernel, double* ms_obs_kernel, int32_t* n_steps);
 
 const char* ppg_last_error(ppg_handle h);

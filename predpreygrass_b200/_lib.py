@@ -65,7 +65,7 @@ def load():
     L.ppg_launch_count.argtypes = [vp]
     L.ppg_launch_count.restype = C.c_int64
     L.ppg_profile_begin.argtypes = [vp]
-    L.ppg_profile_env_cycles.argtypes = [vp, vp, vp, vp]
+    L.ppg_profile_env_cycles.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ppg_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]
     L.ppg_last_error.argtypes = [vp]
     L.ppg_last_error.restype = C.c_char_p

@@ -221,10 +221,10 @@ class BatchedPredPreyGrass:
         return int(self.L.ppg_launch_count(self.h))
 
     def profile_env_cycles(self):
-        """-> (cycles[n_envs], info[n_envs]) of the last step-kernel launch (include/ppg.h)"""
-        cyc, info = np.zeros(self.n_envs, np.uint32), np.zeros(self.n_envs, np.uint32)
-        _lib.check(self.L.ppg_profile_env_cycles(self.h, cyc.ctypes.data, info.ctypes.data, self._stream()), self.h)
-        return cyc, info
+        """-> (cycles, info, start_ns, sm), each [n_envs], of the last step-kernel launch (include/ppg.h)"""
+        out = [np.zeros(self.n_envs, np.uint32) for _ in range(4)]
+        _lib.check(self.L.ppg_profile_env_cycles(self.h, *[a.ctypes.data for a in out], self._stream()), self.h)
+        return tuple(out)
 
     def profile_begin(self):
         """start timing the kernels of every step with CUDA events on the step's stream (include/ppg.h)"""

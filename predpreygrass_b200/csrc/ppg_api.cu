@@ -26,7 +26,7 @@ cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, con
                                   unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s);
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s);
 // ppg_obs.cu
-cudaError_t launch_obs(const StepParams& p, int n_cta, cudaStream_t stream);
+cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream);
 cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm);
 // ppg_eco.cu
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
@@ -53,6 +53,8 @@ struct ppg_handle_s {
   unsigned long long ticket_next = 0;    // value the device ticket counter has after all launches so far
   unsigned long long obs_ticket_next = 0;  // same for the observation kernel's counter
   int n_cta_obs = 0;
+  bool obs_overlap = true;               // observation kernel launched with programmatic stream serialization
+  unsigned long long q_next = 0;         // value the completion-queue tail has after all launches so far
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // triples: before the step kernel, between the kernels, after the observation kernel
   unsigned long long calls = 0;          // ppg_reset(all)/ppg_step calls (ppg_random_actions key)
@@ -468,6 +470,9 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.obs_img = static_cast<unsigned char*>(q);
     for (int s = 0; s < 2; ++s) CKC(dalloc(h, &P.nb_info[s], (size_t)B * P.cap[s]));
     CKC(dalloc(h, &P.obs_ticket, 1));
+    CKC(dalloc(h, &P.queue, (size_t)B));
+    CKC(dalloc(h, &P.q_tail, 1));
+    if (const char* ev = getenv("PPG_OBS_OVERLAP")) h->obs_overlap = atoi(ev) != 0;
     if (eco)
       for (int s = 0; s < 2; ++s) CKC(dalloc(h, &P.born_obs[s], (size_t)B * PPG_BORN_K * (size_t)P.elems[s]));
     int per_sm = 0, n_sm = 0;
@@ -475,6 +480,9 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (per_sm < 1) { h->err = "observation kernel does not fit on an SM"; return fail(PPG_ERR_INVALID); }
     h->n_cta_obs = std::min(B, per_sm * n_sm);
+    if (const char* ev = getenv("PPG_OBS_CTAS_PER_SM")) h->n_cta_obs = std::max(1, std::min(h->n_cta_obs, atoi(ev) * n_sm));
+    // overlap: leave room on every SM for observation CTAs next to the step kernel's persistent warps
+    if (const char* ev = getenv("PPG_STEP_CTAS_PER_SM")) h->n_cta = std::max(1, std::min(h->n_cta, atoi(ev) * n_sm));
   }
   CKC(dalloc(h, &P.error, 1));
   CKC(dalloc(h, &h->d_stats, PPG_N_STATS));
@@ -581,6 +589,8 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
                                           : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
+  P.q_base = h->q_next;
+  if (P.obs_split) h->q_next += (unsigned long long)h->B;  // every env pushes one completion-queue entry per launch
   cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
   if (h->profiling) {
     for (int k = 0; k < 3; ++k) { CK(cudaEventCreate(&pe[k])); h->prof_events.push_back(pe[k]); }
@@ -596,7 +606,7 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
     // observation rows of this output: one CTA per env at a time, B tickets plus one terminating draw per CTA
     P.obs_ticket_base = h->obs_ticket_next;
     h->obs_ticket_next += (unsigned long long)h->B + (unsigned long long)h->n_cta_obs;
-    CK(launch_obs(P, h->n_cta_obs, st));
+    CK(launch_obs(P, h->n_cta_obs, h->obs_overlap && !h->profiling, st));  // per-kernel timing needs the kernels back to back
     h->launch_count++;
   }
   if (h->profiling) CK(cudaEventRecord(pe[2], st));
@@ -929,14 +939,19 @@ int ppg_stats_clear(ppg_handle h, void* cuda_stream) {
 
 int64_t ppg_launch_count(ppg_handle h) { return h ? h->launch_count : 0; }
 
-int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, void* cuda_stream) {
+int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, uint32_t* start_ns, uint32_t* sm, void* cuda_stream) {
   if (!h || !cycles) return PPG_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CK(cudaSetDevice(h->device));
-  std::vector<uint2> tmp((size_t)h->B);
-  CK(cudaMemcpyAsync(tmp.data(), h->P.env_cycles, sizeof(uint2) * (size_t)h->B, cudaMemcpyDeviceToHost, st));
+  std::vector<uint4> tmp((size_t)h->B);
+  CK(cudaMemcpyAsync(tmp.data(), h->P.env_cycles, sizeof(uint4) * (size_t)h->B, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  for (int e = 0; e < h->B; ++e) { cycles[e] = tmp[(size_t)e].x; if (info) info[e] = tmp[(size_t)e].y; }
+  for (int e = 0; e < h->B; ++e) {
+    cycles[e] = tmp[(size_t)e].x;
+    if (info) info[e] = tmp[(size_t)e].y;
+    if (start_ns) start_ns[e] = tmp[(size_t)e].z;
+    if (sm) sm[e] = tmp[(size_t)e].w;
+  }
   return PPG_OK;
 }
 

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
   const RowDesc D = carve_desc(sbase, p);
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
     bool over = false, trunc = false;
 
     const long long t_env0 = clock64();
+    const unsigned t_ns0 = globaltimer_lo();
     EnvHdr h = p.hdr[env];
     // first old row of this env: the previous launch published how many rows every env needs now
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
@@ -718,7 +720,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       if (SPLIT) dump_image(sbase, p, env, 0, false, old_base, n, births, lane);  // header only: no rows
     }
     if (lane == 0) {
-      p.env_cycles[env] = make_uint2((unsigned)(clock64() - t_env0), (unsigned)mode | ((unsigned)(births[0] + births[1]) << 8) | ((unsigned)(n[0] + n[1]) << 16));
+      p.env_cycles[env] = make_uint4((unsigned)(clock64() - t_env0), (unsigned)mode | ((unsigned)(births[0] + births[1]) << 8) | ((unsigned)(n[0] + n[1]) << 16), t_ns0, smid());
       p.env_flags[env] = (uint8_t)env_flags;
       p.env_status[env] = h.status;
       p.env_step[env] = h.step;

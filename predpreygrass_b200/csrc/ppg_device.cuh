@@ -183,7 +183,11 @@ struct StepParams {
   unsigned char* obs_img;   // [B][img_stride]
   unsigned long long* nb_info[2];  // [B][cap] per newborn of this launch: id | row flags << 16 | list position << 32 (0xFFFF: not kept)
   float* born_obs[2];       // ECO: [B][PPG_BORN_K][elems] at-birth observations of newborns of an episode's last step
-  uint2* env_cycles;       // [B] profiling: x = SM cycles the step kernel spent on the env in the last launch, y = mode | births << 8 | agents << 16
+  uint4* env_cycles;       // [B] profiling: x = SM cycles the step kernel spent on the env in the last launch, y = mode | births << 8 | agents << 16,
+                           //     z = globaltimer (ns, low 32 bits) when the env was taken, w = SM id
+  unsigned long long* queue;       // [B] completion queue of the step kernel: epoch << 32 | env, in the order the images reached HBM
+  unsigned long long* q_tail;      // entries pushed so far (monotonic over launches); q_base = its value at launch
+  unsigned long long q_base;
   unsigned long long* obs_ticket;  // env ticket counter of the observation kernel (monotonic over launches)
   unsigned long long obs_ticket_base;
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2

@@ -55,13 +55,88 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsig
                : "memory");
 }
 
+#define OBS_MAX_DEFER 256
+
+// rows of one env from its image in shared memory.  k_lo/k_hi select old rows, newborn rows or both.
+template <typename MapT, int KIND>
+__device__ __forceinline__ void obs_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
+                                         const int n[2], const int births[2], const int new_base[2], bool do_old, bool do_new, int warp,
+                                         int lane, unsigned& rowctr) {
+  // warp w takes every 4th row of the env (round robin across both species)
+  int rot = 0;
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const int lo = do_old ? 0 : n[s], hi = do_new ? n[s] + births[s] : n[s];
+    const int T = hi - lo;
+    const int k0 = lo + (warp + 4 * OBS_WARPS - rot) % OBS_WARPS;
+    rot = (rot + (T > 0 ? T : 0)) % OBS_WARPS;
+    if (k0 >= hi) continue;
+    const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
+    const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
+    const RowRel rr = load_rel(p, s, vb32, lane);
+    const int elems = p.elems[s];
+    float* obs_s = p.obs[s];
+    for (int k = k0; k < hi; k += OBS_WARPS) {
+      const unsigned d = dsc[k];
+      if (d == DSC_SKIP) continue;
+      const int row = k < n[s] ? old_base[s] + k : new_base[s] + (k - n[s]);
+      float* dst = obs_s + (size_t)row * elems;
+      if (KIND == 1) {
+        if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
+          const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
+          for (int q = lane; q < elems; q += 32) __stcs(dst + q, __ldcg(src + q));  // L2: written by another SM during this launch
+          continue;
+        }
+        emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
+      } else if (KIND == 2) {
+        if (d == DSC_ZERO) { zero_row(dst, elems, lane); continue; }
+        const unsigned x = dsx[k];
+        const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
+        if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+        else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
+      } else {
+        emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+      }
+    }
+  }
+}
+
+// labels of the newborn rows, the rows their first actions are read from, new_off
+__device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env, const int births[2], const int new_base[2], int tid) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const size_t sb = (size_t)env * p.cap[s];
+    for (int j = tid; j < births[s]; j += OBS_THREADS) {
+      const unsigned long long info = __ldcg(p.nb_info[s] + sb + j);  // L2: written by another SM during this launch
+      const int row = new_base[s] + j;
+      p.row_env[s][row] = env;
+      p.row_agent[s][row] = (int)(info & 0xFFFFu);
+      p.reward[s][row] = 0.f;  // a newborn's first reward is 0 in every variant (BASE:443, ECO:1161, STAG:1573)
+      p.flags[s][row] = (uint8_t)((info >> 16) & 0xFFu);
+      const unsigned dst = (unsigned)(info >> 32) & 0xFFFFu;
+      if (dst != 0xFFFFu) p.ag_prow[s][sb + dst] = row;  // the newborn's first action is read from this row
+    }
+  }
+  if (tid < 2) p.new_off[tid][env] = births[tid] > 0 ? new_base[tid] : 0;
+}
+
 // KIND: 0 = BASE family, 1 = ECO (own-speed plane), 2 = STAG (cut-off forward view, all-zero rows of ended agents)
+//
+// Envs arrive through the COMPLETION QUEUE of the step kernel (queue[i] = epoch << 32 | env, pushed after the env's image
+// is in HBM), so this kernel may run WHILE the step kernel is still working: it is launched with programmatic stream
+// serialization and fills whatever the step kernel's persistent warps leave free on an SM, above all the step
+// kernel's long tail.  Correctness never depends on the overlap — launched after the step kernel has ended, every
+// queue entry is simply there already.
+// Newborn rows need the births of all envs before this one; if those are not all published yet when the env comes
+// by, its newborn rows are deferred to the end of this CTA's work (the image is fetched again).
 template <typename MapT, int KIND>
 __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
-  __shared__ int s_tk[2];
-  __shared__ int s_nb[2];
+  __shared__ int s_env[2];
+  __shared__ int s_nb[3];
+  __shared__ int s_ndefer;
+  __shared__ int s_defer[OBS_MAX_DEFER];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned stride = (unsigned)p.img_stride, img_bytes = (unsigned)p.img_bytes;
   const unsigned img0 = smem_u32(smem_img), bar0 = smem_u32(&s_bar[0]);
@@ -69,33 +144,44 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_co
   const int par = (int)(epoch & 1u);
   const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
 
+  // thread 0: ticket -> completion-queue entry -> env -> bulk copy of its image into buffer `st`.
+  // Returns the env (or B when the tickets are exhausted); -1 if the entry is not there yet and !block.
+  int tk_pending = -1;
+  auto fetch = [&](unsigned st, bool block) -> int {
+    if (tk_pending < 0) tk_pending = (int)(atomicAdd(p.obs_ticket, 1ULL) - p.obs_ticket_base);
+    if (tk_pending >= p.B) return p.B;
+    unsigned long long w = ld_volatile(p.queue + tk_pending);
+    while ((unsigned)(w >> 32) != epoch) {
+      if (!block) return -1;
+      __nanosleep(256);
+      w = ld_volatile(p.queue + tk_pending);
+    }
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");  // the image was written through the generic proxy of another SM
+    const int e = (int)(unsigned)w;
+    tk_pending = -1;
+    mbar_expect_tx(bar0 + 8u * st, img_bytes);
+    bulk_load(img0 + st * stride, p.obs_img + (size_t)e * stride, img_bytes, bar0 + 8u * st);
+    return e;
+  };
+
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
-    const int t = (int)(atomicAdd(p.obs_ticket, 1ULL) - p.obs_ticket_base);
-    s_tk[0] = t;
-    if (t < p.B) {
-      mbar_expect_tx(bar0, img_bytes);
-      bulk_load(img0, p.obs_img + (size_t)t * stride, img_bytes, bar0);
-    }
+    s_ndefer = 0;
+    s_env[0] = fetch(0, true);
   }
   __syncthreads();
-  int env = s_tk[0];
+  int env = s_env[0];
   unsigned stage = 0, phase = 0;  // bit s of phase: parity the barrier of buffer s completes next
   unsigned rowctr = 0;
 
   while (env < p.B) {
-    if (tid == 0) {
-      // next env: its image streams into the other buffer (all reads of that buffer ended before the last barrier)
-      const int t = (int)(atomicAdd(p.obs_ticket, 1ULL) - p.obs_ticket_base);
-      s_tk[stage ^ 1u] = t;
-      if (t < p.B) {
-        mbar_expect_tx(bar0 + 8u * (stage ^ 1u), img_bytes);
-        bulk_load(img0 + (stage ^ 1u) * stride, p.obs_img + (size_t)t * stride, img_bytes, bar0 + 8u * (stage ^ 1u));
-      }
-    }
+    // next env: its image streams into the other buffer (all reads of that buffer ended before the last barrier)
+    int nxt = -1;
+    if (tid == 0) nxt = fetch(stage ^ 1u, false);
     mbar_wait(bar0 + 8u * stage, (phase >> stage) & 1u);
     phase ^= 1u << stage;
 
@@ -106,81 +192,88 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_co
     const int n[2] = {ih[IH_N0], ih[IH_N1]};
     const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
     int new_base[2] = {0, 0};
+    bool do_new = false;
 
     if (births[0] + births[1] > 0) {
-      // first newborn row of this env = old rows of all envs + births of the envs before it (all published)
+      // first newborn row of this env = old rows of all envs + births of the envs before it
       if (warp == 0) {
         int nb0 = 0, nb1 = 0;
-        if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, false, lane, nb0, nb1)) {
-          if (lane == 0) atomicOr(p.error, 1u);
+        const bool ready = prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, false, lane, nb0, nb1);
+        if (lane == 0) {
+          int ok = ready ? 1 : 0;
+          if (!ready) {
+            if (s_ndefer < OBS_MAX_DEFER) s_defer[s_ndefer++] = env;
+            else ok = 2;  // list full: wait here, below (the step kernel never waits for this kernel, so the wait ends)
+          }
+          s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; s_nb[2] = ok;
         }
-        if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; }
       }
       __syncthreads();
-      new_base[0] = s_nb[0]; new_base[1] = s_nb[1];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const size_t sb = (size_t)env * p.cap[s];
-        for (int j = tid; j < births[s]; j += OBS_THREADS) {
-          const unsigned long long info = p.nb_info[s][sb + j];
-          const int row = new_base[s] + j;
-          p.row_env[s][row] = env;
-          p.row_agent[s][row] = (int)(info & 0xFFFFu);
-          p.reward[s][row] = 0.f;  // a newborn's first reward is 0 in every variant (BASE:443, ECO:1161, STAG:1573)
-          p.flags[s][row] = (uint8_t)((info >> 16) & 0xFFu);
-          const unsigned dst = (unsigned)(info >> 32) & 0xFFFFu;
-          if (dst != 0xFFFFu) p.ag_prow[s][sb + dst] = row;  // the newborn's first action is read from this row
+      if (s_nb[2] == 2) {
+        __syncthreads();
+        if (warp == 0) {
+          int nb0 = 0, nb1 = 0;
+          if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+            if (lane == 0) atomicOr(p.error, 1u);
+          }
+          if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; s_nb[2] = 1; }
         }
+        __syncthreads();
       }
-      if (tid < 2) p.new_off[tid][env] = births[tid] > 0 ? new_base[tid] : 0;
+      do_new = s_nb[2] != 0;
+      if (do_new) {
+        new_base[0] = s_nb[0]; new_base[1] = s_nb[1];
+        obs_newborn_labels(p, env, births, new_base, tid);
+      }
     } else if (tid < 2) {
       p.new_off[tid][env] = 0;
     }
 
-    // rows: warp w takes every 4th row of the env (round robin across both species)
-    int rot = 0;
-#pragma unroll 1
-    for (int s = 0; s < 2; ++s) {
-      const int T = n[s] + births[s];
-      const int k0 = (warp + 4 * OBS_WARPS - rot) % OBS_WARPS;
-      rot = (rot + T) % OBS_WARPS;
-      if (k0 >= T) continue;
-      const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
-      const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
-      const RowRel rr = load_rel(p, s, vb32, lane);
-      const int elems = p.elems[s];
-      float* obs_s = p.obs[s];
-      for (int k = k0; k < T; k += OBS_WARPS) {
-        const unsigned d = dsc[k];
-        if (d == DSC_SKIP) continue;
-        const int row = k < n[s] ? old_base[s] + k : new_base[s] + (k - n[s]);
-        float* dst = obs_s + (size_t)row * elems;
-        if (KIND == 1) {
-          if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
-            const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
-            for (int q = lane; q < elems; q += 32) __stcs(dst + q, src[q]);
-            continue;
-          }
-          emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
-        } else if (KIND == 2) {
-          if (d == DSC_ZERO) { zero_row(dst, elems, lane); continue; }
-          const unsigned x = dsx[k];
-          const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
-          if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-          else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
-        } else {
-          emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-        }
-      }
+    obs_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, births, new_base, true, do_new, warp, lane, rowctr);
+
+    if (tid == 0) {
+      if (nxt < 0) nxt = fetch(stage ^ 1u, true);
+      s_env[stage ^ 1u] = nxt;
     }
-    __syncthreads();  // every read of this buffer is done; the ticket drawn at the top is visible
-    env = s_tk[stage ^ 1u];
+    __syncthreads();  // every read of this buffer is done; the next env is known
+    env = s_env[stage ^ 1u];
+    stage ^= 1u;
+  }
+
+  // deferred newborn rows: by now (the completion queue is exhausted) every env has published its births or is about to
+  const int n_defer = s_ndefer;
+  for (int i = 0; i < n_defer; ++i) {
+    env = s_defer[i];
+    if (tid == 0) {
+      mbar_expect_tx(bar0 + 8u * stage, img_bytes);
+      bulk_load(img0 + stage * stride, p.obs_img + (size_t)env * stride, img_bytes, bar0 + 8u * stage);
+    }
+    if (warp == 0) {
+      int nb0 = 0, nb1 = 0;
+      if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+        if (lane == 0) atomicOr(p.error, 1u);
+      }
+      if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; }
+    }
+    mbar_wait(bar0 + 8u * stage, (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+    __syncthreads();
+    const unsigned char* ibp = smem_img + (size_t)stage * stride;
+    const unsigned vb32 = img0 + stage * stride - (unsigned)p.so_img;
+    const int* ih = reinterpret_cast<const int*>(ibp + (p.so_ihdr - p.so_img));
+    const int old_base[2] = {ih[IH_OLD_BASE0], ih[IH_OLD_BASE1]};
+    const int n[2] = {ih[IH_N0], ih[IH_N1]};
+    const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
+    const int new_base[2] = {s_nb[0], s_nb[1]};
+    obs_newborn_labels(p, env, births, new_base, tid);
+    obs_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, births, new_base, false, true, warp, lane, rowctr);
+    __syncthreads();
     stage ^= 1u;
   }
 }
 
 template <typename MapT, int KIND>
-static cudaError_t launch_obs_t(const StepParams& p, int n_cta, cudaStream_t stream) {
+static cudaError_t launch_obs_t(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)p.img_stride;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
@@ -188,8 +281,17 @@ static cudaError_t launch_obs_t(const StepParams& p, int n_cta, cudaStream_t str
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_obs_kernel<MapT, KIND><<<n_cta, OBS_THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_cta);
+  cfg.blockDim = dim3(OBS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ppg_obs_kernel<MapT, KIND>, p);
 }
 
 template <typename MapT, int KIND>
@@ -208,7 +310,7 @@ static cudaError_t occupancy_obs_t(const StepParams& p, int* blocks_per_sm) {
     return m8 ? FN<uint8_t, 0>(__VA_ARGS__) : FN<uint16_t, 0>(__VA_ARGS__);                                 \
   } while (0)
 
-cudaError_t launch_obs(const StepParams& p, int n_cta, cudaStream_t stream) { PPG_OBS_DISPATCH(launch_obs_t, p, n_cta, stream); }
+cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream) { PPG_OBS_DISPATCH(launch_obs_t, p, n_cta, overlap, stream); }
 cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm) { PPG_OBS_DISPATCH(occupancy_obs_t, p, blocks_per_sm); }
 
 }  // namespace ppg

@@ -11,6 +11,9 @@ namespace ppg {
 
 #define FULL 0xffffffffu
 
+__device__ __forceinline__ unsigned globaltimer_lo() { unsigned v; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(v)); return v; }
+__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory view of one env
 // ------------------------------------------------------------------------------------------------
@@ -66,6 +69,32 @@ __device__ __forceinline__ EnvSmem<MapT> carve(unsigned char* base, const StepPa
   return s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+// bulk asynchronous shared -> global copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc32, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)), "r"(ssrc32), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long long v) {
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+#define TAG(epoch, val) (((unsigned long long)(epoch) << 32) | (unsigned long long)(unsigned)(val))
+
+// padded map index of a packed position (x << 8 | y)
+#define CELLP(ps) (PP + ((int)((ps) >> 8) + PP) * PS + (int)((ps)&255u))
+#define CELLXY(x, y) (PP + ((x) + PP) * PS + (y))
+
 // two-kernel step: row descriptors inside the env image and the image dump
 struct RowDesc {
   uint16_t* dsc[2];  // padded cell index of the window centre of the k-th row (k < n: rows of the agents that acted, in
@@ -109,33 +138,17 @@ __device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParam
   const int n16 = mode ? p.img_bytes >> 4 : (IH_INTS * 4) >> 4;
   for (int i = lane; i < n16; i += 32) dst[i] = src[i];
   __syncwarp();
+  // completion queue: the observation kernel (possibly already running, see ppg_obs.cu) takes the env from here
+  if (lane == 0) {
+    __threadfence();
+    const unsigned long long slot = atomicAdd(p.q_tail, 1ULL) - p.q_base;
+    st_volatile(p.queue + slot, TAG(p.epoch, env));
+  }
+  __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------------
-// bulk asynchronous shared -> global copy (TMA engine, SASS UBLKCP)
-__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc32, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)), "r"(ssrc32), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
-  return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-__device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long long v) {
-  *reinterpret_cast<volatile unsigned long long*>(p) = v;
-}
-#define TAG(epoch, val) (((unsigned long long)(epoch) << 32) | (unsigned long long)(unsigned)(val))
-
-// padded map index of a packed position (x << 8 | y)
-#define CELLP(ps) (PP + ((int)((ps) >> 8) + PP) * PS + (int)((ps)&255u))
-#define CELLXY(x, y) (PP + ((x) + PP) * PS + (y))
+// lets a kernel launched with programmatic stream serialization (the observation kernel) start while this one runs
+__device__ __forceinline__ void allow_dependent_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // observation rows
