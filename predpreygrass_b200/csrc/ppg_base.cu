@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
   // one-time set-up of this warp's slice: empty maps (predator map: WALL outside the field), zeroed touch
   // counters, wall table — copied from the image ppg_create built.  Every env leaves the maps empty again
   // (it un-writes the cells it wrote).
+  #pragma unroll 1
   for (int i = lane; i < p.init_bytes / 16; i += 32)
     reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
   unsigned rowctr = 0;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       bool from_tape = false;
       if (p.tape_cells != nullptr) {
         if (h.tape_pos + n_total <= h.tape_end) {
+          #pragma unroll 1
           for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
           h.tape_pos += n_total;
           from_tape = true;
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         int k0 = 0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
+          #pragma unroll 1
           for (int i = lane; i < p.n_init[s]; i += 32) {
             const int c = cells[k0 + i];
             const int cx = c / G, cy = c % G;
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           h.n_sorted[s] = (unsigned short)p.n_init[s];
           h.next_idx[s] = (unsigned short)p.n_init[s];
         }
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           const int c = cells[k0 + g];
           const int cx = c / G, cy = c % G;
@@ -196,11 +200,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         bool use_order = ordp != nullptr;
         if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to row order
           bool ok = true;
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) SEL(S.rnk)[d] = (uint16_t)i; else ok = false;
           }
           __syncwarp();
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) ok &= SEL(S.rnk)[d] == (uint16_t)i;
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           __syncwarp();
         }
         if (s == 0) resort[0] = use_order; else resort[1] = use_order;
+        #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
           const int prow = p.ag_prow[s][b + i];
           const int d = use_order ? ordp[prow] : i;
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
         const size_t b = (size_t)env * p.n_grass;
         const unsigned gp = p.gr_pos[b + g];
@@ -317,8 +325,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           const uint16_t* lr = p.lexrank[s];
           const bool by_id = h.first_step != 0;  // right after reset() self.agents is in numeric order (BASE:143-145)
           const int ns = SEL(resort) ? 0 : min((int)(s == 0 ? h.n_sorted[0] : h.n_sorted[1]), SEL(n));
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) SEL(S.ord)[i] = by_id ? SEL(S.id)[i] : __ldg(lr + SEL(S.id)[i]);
           __syncwarp();
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const unsigned key = SEL(S.ord)[i];
             int r = i < ns ? i : 0;
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
             SEL(S.rnk)[i] = (uint16_t)r;
           }
           __syncwarp();
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) SEL(S.ord)[SEL(S.rnk)[i]] = (uint16_t)i;
           __syncwarp();
         }
@@ -334,13 +345,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       // Step 3a: predators in engagement order (BASE:279-346).  Nothing happens unless a predator  // PHASE: predators
       // starved or some prey (any energy) stands on a live predator's cell.
       bool ev = false;
+      #pragma unroll 1
       for (int i = lane; i < n[0]; i += 32) {
         if (S.E[0][i] <= 0.0) ev = true;
         else S.scr[CELLP((unsigned)S.pos[0][i])] = 1;
       }
       __syncwarp();
+      #pragma unroll 1
       for (int i = lane; i < n[1]; i += 32) ev |= S.scr[CELLP((unsigned)S.pos[1][i])] != 0;
       __syncwarp();
+      #pragma unroll 1
       for (int i = lane; i < n[0]; i += 32) S.scr[CELLP((unsigned)S.pos[0][i])] = 0;
       __syncwarp();
       if (__any_sync(FULL, ev)) {
@@ -359,6 +373,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
           }
           // first prey in agent_positions order (= lowest id) on my cell (BASE:305-312)
           unsigned best = 0xFFFFFFFFu;
+          #pragma unroll 1
           for (int i = lane; i < n[1]; i += 32)
             if ((S.flg[1][i] & F_ALIVE) && S.pos[1][i] == ps) best = min(best, ((unsigned)S.id[1][i] << 16) | (unsigned)i);
           best = __reduce_min_sync(FULL, best);
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
               __syncwarp();
               if (gp != 0xFFFFu) {
                 int gs = -1;
+                #pragma unroll 1
                 for (int i = lane; i < SEL(n) + SEL(births); i += 32)
                   if ((SEL(S.flg)[i] & F_ALIVE) && SEL(S.id)[i] == gp) gs = i;
                 gs = __reduce_max_sync(FULL, gs);
@@ -524,6 +540,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         int c = 0;
+        #pragma unroll 1
         for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
         cur[s] = __reduce_add_sync(FULL, c);
       }
@@ -663,8 +680,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
       // (a non-zero owner entry always has its owner standing on it)
 #pragma unroll
       for (int s = 0; s < 2; ++s)
+        #pragma unroll 1
         for (int i = lane; i < n[s] + births[s]; i += 32)
           if (S.flg[s][i] & F_ALIVE) S.map[s][CELLP((unsigned)S.pos[s][i])] = 0;
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
       if (keep) {
         const int live0 = wpos[0] - births[0], live1 = wpos[1] - births[1];
@@ -681,6 +700,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         }
         h.sortflag = sf;
         const size_t gb = (size_t)env * p.n_grass;
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           p.gr_e[gb + g] = S.gE[g];
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];

@@ -68,6 +68,7 @@ __device__ __forceinline__ unsigned next_in_seq_order(const uint16_t* const seq[
   unsigned best = 0xFFFFFFFFu;
 #pragma unroll
   for (int s = 0; s < 2; ++s)
+    #pragma unroll 1
     for (int i = lane; i < n[s]; i += 32) {
       const unsigned key = ((unsigned)seq[s][i] << 16) | ((unsigned)s << 15) | (unsigned)i;
       if ((long long)key > last && pred(s, i)) best = min(best, key);
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
   const unsigned lt_mask = (1u << lane) - 1u;
   const int AR = p.action_range, AD = (p.action_range - 1) / 2;
 
+  #pragma unroll 1
   for (int i = lane; i < p.init_bytes / 16; i += 32)
     reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
   unsigned rowctr = 0;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         double* sp0 = X.spd[0];
         double* sp1 = X.spd[1];
         if (p.tape_reals != nullptr && eh.real_pos + n_f <= eh.real_end) {
+          #pragma unroll 1
           for (int k = lane; k < n_f; k += 32) {
             const double v = p.tape_reals[eh.real_pos + k];
             const double c = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                                          PPG_STREAM_TRAIT, ctr, lane);
             } else {
               const double v = p.f_mean[s];
+              #pragma unroll 1
               for (int i = lane; i < p.n_init[s]; i += 32) SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
             }
           }
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       bool from_tape = false;
       if (p.tape_cells != nullptr) {
         if (h.tape_pos + n_total <= h.tape_end) {
+          #pragma unroll 1
           for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
           h.tape_pos += n_total;
           from_tape = true;
@@ -189,6 +194,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         int k0 = 0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
+          #pragma unroll 1
           for (int i = lane; i < p.n_init[s]; i += 32) {
             const int c = cells[k0 + i];
             const int cx = c / G, cy = c % G;
@@ -207,7 +213,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         __syncwarp();  // `first` aliases the energy arrays: write the energies only after the placement is read
 #pragma unroll
         for (int s = 0; s < 2; ++s)
+          #pragma unroll 1
           for (int i = lane; i < p.n_init[s]; i += 32) S.E[s][i] = p.init_e[s];
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           const int c = cells[k0 + g];
           const int cx = c / G, cy = c % G;
@@ -233,11 +241,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         bool use_order = ordp != nullptr;
         if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
           bool ok = true;
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) SEL(X.mord)[d] = (uint16_t)i; else ok = false;
           }
           __syncwarp();
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) ok &= SEL(X.mord)[d] == (uint16_t)i;
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           if (!use_order) bad = PPG_STATUS_BAD_ACTION;
           __syncwarp();
         }
+        #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
           const int prow = p.ag_prow[s][b + i];
           int a = p.actions[s][prow];
@@ -266,6 +277,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
         const size_t b = (size_t)env * p.n_grass;
         const unsigned gp = p.gr_pos[b + g];
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       }
       // grass regrowth (ECO:618-626)
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
         const double v = p.gr_e[(size_t)env * p.n_grass + g] + p.grass_gain;
         S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
@@ -404,6 +417,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         bool sv = false;
 #pragma unroll
         for (int s = 0; s < 2; ++s)
+          #pragma unroll 1
           for (int i = lane; i < n[s]; i += 32) sv |= S.E[s][i] <= 0.0;
         if (__any_sync(FULL, sv)) {
           long long last = -1;
@@ -480,6 +494,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       // Step 4c: predators, predator_positions order (ECO:325-330,786-883).  Every prey still in agent_positions counts —
       // also those terminated earlier in this step (removal is Step 5) and carcasses.
       {
+        #pragma unroll 1
         for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 1;
         __syncwarp();
         for (int b0 = 0; b0 < n[0]; b0 += 32) {
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int cell = CELLP(ps);
             // first prey in agent_positions order on my cell = lowest id = lowest list slot (ECO:797-799)
             unsigned best = 0xFFFFFFFFu;
+            #pragma unroll 1
             for (int i = lane; i < n[1]; i += 32)
               if (S.pos[1][i] == ps) best = min(best, (unsigned)i);
             best = __reduce_min_sync(FULL, best);
@@ -529,6 +545,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             }
           }
         }
+        #pragma unroll 1
         for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 0;
         __syncwarp();
       }
@@ -643,6 +660,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           int c = 0;
+          #pragma unroll 1
           for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
           next_live[s] = __reduce_add_sync(FULL, c);
         }
@@ -766,12 +784,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       // owner is gone, so every loaded slot is un-written, alive or not.
 #pragma unroll
       for (int s = 0; s < 2; ++s)
+        #pragma unroll 1
         for (int i = lane; i < n[s] + births[s]; i += 32) S.map[s][CELLP((unsigned)S.pos[s][i])] = 0;
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
       if (keep) {
         h.n_list[0] = (unsigned short)wpos[0];
         h.n_list[1] = (unsigned short)wpos[1];
         const size_t gb = (size_t)env * p.n_grass;
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           p.gr_e[gb + g] = S.gE[g];
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
   const unsigned lt_mask = (1u << lane) - 1u;
   const int T2[2] = {p.n_possible_t[0][0], p.n_possible_t[1][0]};  // first flat id of type 2 per species
 
+  #pragma unroll 1
   for (int i = lane; i < p.init_bytes / 16; i += 32)
     reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
   unsigned rowctr = 0;
@@ -178,7 +179,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       bool from_tape = false;
       if (p.tape_cells != nullptr) {
         if (h.tape_pos + n_total + n_pred <= h.tape_end) {  // the cells, then one facing index per founder predator
+          #pragma unroll 1
           for (int i = lane; i < n_total; i += 32) cells[i] = p.tape_cells[h.tape_pos + i];
+          #pragma unroll 1
           for (int i = lane; i < n_pred; i += 32) X.face[i] = (uint8_t)p.tape_cells[h.tape_pos + n_total + i];
           h.tape_pos += n_total + n_pred;
           from_tape = true;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       }
       if (!from_tape) {
         philox_placement(cells, first, n_total, GG, genv, h.episode, h.seed_key, lane);
+        #pragma unroll 1
         for (int i = lane; i < n_pred; i += 32)  // _random_predator_facing (STAG:939-942)
           X.face[i] = (uint8_t)ppg_bounded(ppg_draw_u32(h.seed_key, genv, h.episode, PPG_STREAM_FACING, (unsigned)i), 8u);
       }
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       // _sample_initial_predator_trait (STAG:1084-1088)
       if (p.coop_enabled) {
         if (p.tape_reals != nullptr && sh.real_pos + n_pred <= sh.real_end) {
+          #pragma unroll 1
           for (int k = lane; k < n_pred; k += 32) {
             const double v = p.tape_reals[sh.real_pos + k];
             X.trait[k] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
@@ -207,10 +212,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
                                                   PPG_STREAM_TRAIT, sh.trait_draws, lane);
           } else {
             const double v = p.trait_mean;
+            #pragma unroll 1
             for (int k = lane; k < n_pred; k += 32) X.trait[k] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
           }
         }
       } else {
+        #pragma unroll 1
         for (int k = lane; k < n_pred; k += 32) X.trait[k] = 1.0;
       }
       __syncwarp();
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         int k0 = 0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
+          #pragma unroll 1
           for (int i = lane; i < p.n_init[s]; i += 32) {
             const int c = cells[k0 + i];
             const int cx = c / G, cy = c % G;
@@ -235,8 +243,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
           n[s] = p.n_init[s];
         }
         __syncwarp();  // `first` aliases the energy arrays: write the energies only after the placement is read
+        #pragma unroll 1
         for (int i = lane; i < p.n_init[0]; i += 32) S.E[0][i] = p.init_e[0];
+        #pragma unroll 1
         for (int i = lane; i < p.n_init[1]; i += 32) S.E[1][i] = p.init_e_prey_t[i >= p.n_init_t[1][0]];
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           const int c = cells[k0 + g];
           const int cx = c / G, cy = c % G;
@@ -264,11 +275,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         bool use_order = ordp != nullptr;
         if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
           bool ok = true;
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) SEL(X.mord)[d] = (uint16_t)i; else ok = false;
           }
           __syncwarp();
+          #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
             const int d = ordp[p.ag_prow[s][b + i]];
             if ((unsigned)d < (unsigned)SEL(n)) ok &= SEL(X.mord)[d] == (uint16_t)i;
@@ -277,6 +290,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
           if (!use_order) bad = PPG_STATUS_BAD_ACTION;
           __syncwarp();
         }
+        #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
           const int prow = p.ag_prow[s][b + i];
           const int a = p.actions[s][prow];
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
       // grass regrowth (STAG:761-769)
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
         const size_t b = (size_t)env * p.n_grass;
         const unsigned gp = p.gr_pos[b + g];
@@ -419,6 +434,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         int c = 0;
+        #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32)
           if (SEL(S.E)[i] <= 0.0) {
             MapT* m = s == 0 ? S.map[0] : prey_map(i);
@@ -434,6 +450,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       // Step 4b: prey engagements in prey_positions order (STAG:456-460,1444-1500).  A prey can only be captured if a
       // live predator stands within Chebyshev distance 1; all other prey just eat grass and cannot interact with a
       // capture (they stand on different cells), so they go first, 32 at a time.
+      #pragma unroll 1
       for (int i = lane; i < n[0]; i += 32)
         if (S.flg[0][i] & F_ALIVE) {
           const int c = CELLP((unsigned)S.pos[0][i]);
@@ -570,6 +587,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               const double join_cost = p.join_cost;
               if (!success) {
                 if (join_cost != 0.0) {  // STAG:1185-1192
+                  #pragma unroll 1
                   for (int k = lane; k < nj; k += 32) S.E[0][X.jl[k]] -= join_cost;
                   __syncwarp();
                   if (lane == 0)
@@ -587,6 +605,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
                 const double scav_total = prey_energy * scav_frac;
                 const double pool = prey_energy - scav_total;
                 __syncwarp();
+                #pragma unroll 1
                 for (int k = lane; k < nj; k += 32) {  // STAG:1279-1297 (a joiner's snapshot energy is its energy right now)
                   const int pid = X.jl[k];
                   double e = S.E[0][pid];
@@ -600,6 +619,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
                 }
                 const double scav_share = nr ? scav_total / (double)nr : 0.0;  // STAG:1338-1348
                 if (scav_share != 0.0)
+                  #pragma unroll 1
                   for (int k = lane; k < nr; k += 32) {
                     const int pid = X.rl[k];
                     S.E[0][pid] += scav_share;
@@ -616,6 +636,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               }
               if (join_cost != 0.0) {  // joiners the cost starved (STAG:1238-1240,1402-1405)
                 int c = 0;
+                #pragma unroll 1
                 for (int k = lane; k < nj; k += 32) {
                   const int pid = X.jl[k];
                   if (S.E[0][pid] <= 0.0 && (S.flg[0][pid] & F_ALIVE)) {
@@ -647,6 +668,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
           }
         }
       }
+      #pragma unroll 1
       for (int i = lane; i < n[0]; i += 32) {  // un-mark (around every loaded predator: the counters are all zero between uses)
         const int c = CELLP((unsigned)S.pos[0][i]);
 #pragma unroll
@@ -746,6 +768,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         int c = 0;
+        #pragma unroll 1
         for (int i = lane; i < n[s] + births[s]; i += 32) c += (S.flg[s][i] & F_ALIVE) ? 1 : 0;
         live[s] = __reduce_add_sync(FULL, c);
       }
@@ -869,13 +892,17 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       }
       if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
       // leave the maps empty for the next env of this warp: every loaded or born slot un-writes its cell in its channel
+      #pragma unroll 1
       for (int i = lane; i < n[0] + births[0]; i += 32) S.map[0][CELLP((unsigned)S.pos[0][i])] = 0;
+      #pragma unroll 1
       for (int i = lane; i < n[1] + births[1]; i += 32) prey_map(i)[CELLP((unsigned)S.pos[1][i])] = 0;
+      #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
       if (keep) {
         h.n_list[0] = (unsigned short)wpos[0];
         h.n_list[1] = (unsigned short)wpos[1];
         const size_t gb = (size_t)env * p.n_grass;
+        #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           p.gr_e[gb + g] = S.gE[g];
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];

@@ -136,6 +136,7 @@ __device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParam
   const uint4* src = reinterpret_cast<const uint4*>(sbase + p.so_img);
   uint4* dst = reinterpret_cast<uint4*>(p.obs_img + (size_t)env * p.img_stride);
   const int n16 = mode ? p.img_bytes >> 4 : (IH_INTS * 4) >> 4;
+  #pragma unroll 1
   for (int i = lane; i < n16; i += 32) dst[i] = src[i];
   __syncwarp();
   // completion queue: the observation kernel (possibly already running, see ppg_obs.cu) takes the env from here
@@ -177,8 +178,11 @@ __device__ __forceinline__ RowRel load_rel(const StepParams& p, int s, unsigned 
 // fp32 copies of the energies the observation channels show (float64 state -> float32 row values)
 template <typename MapT>
 __device__ __forceinline__ void refresh_tables(const EnvSmem<MapT>& S, const StepParams& p, int nt0, int nt1, int lane) {
+  #pragma unroll 1
   for (int i = lane; i < nt0; i += 32) S.vt[0][1 + i] = (float)S.E[0][i];
+  #pragma unroll 1
   for (int i = lane; i < nt1; i += 32) S.vt[1][1 + i] = (float)S.E[1][i];
+  #pragma unroll 1
   for (int g = lane; g < p.n_grass; g += 32) S.vt[2][1 + g] = (float)S.gE[g];
   if (lane == 0) S.vt[0][0] = 0.f;
   if (lane == 1) S.vt[1][0] = 0.f;
@@ -338,6 +342,7 @@ __device__ __noinline__ void emit_row_masked(const StepParams& p, unsigned sb32,
 
 // ended agents are observed as all-zero rows (STAG:596-612)
 __device__ __forceinline__ void zero_row(float* dst, int elems, int lane) {
+  #pragma unroll 1
   for (int q = lane; q < elems; q += 32) __stcs(dst + q, 0.f);
 }
 
@@ -359,6 +364,7 @@ __device__ __forceinline__ bool any_agent_at(const EnvSmem<MapT>& S, const int n
   bool hit = false;
 #pragma unroll
   for (int s = 0; s < 2; ++s)
+    #pragma unroll 1
     for (int i = lane; i < nl[s]; i += 32) hit |= (S.flg[s][i] & F_ALIVE) && S.pos[s][i] == pos;
   return __any_sync(FULL, hit);
 }
@@ -386,6 +392,7 @@ __device__ __forceinline__ bool prefix_before(const unsigned long long* cnt, con
       a0 += (int)(unsigned)w0;
       a1 += (int)(unsigned)w1;
     }
+    #pragma unroll 1
     for (int g = lane; g < grp; g += 32) {
       const unsigned long long* q = sum2 + (size_t)g * 4 + v0;
       const unsigned long long w0 = ld_volatile(q), w1 = ld_volatile(q + 1);
@@ -440,6 +447,7 @@ static __device__ __noinline__ unsigned draw_normals_batched(double* out, int co
 // reset(): n_total unique cells in draw order (law of BASE:156-177) from the env's Philox placement stream
 static __device__ __noinline__ void philox_placement(int* cells, unsigned* first, int n_total, int GG, unsigned env, unsigned episode,
                                               unsigned long long seed_key, int lane) {
+  #pragma unroll 1
   for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
   __syncwarp();
   int accepted = 0;
@@ -476,6 +484,7 @@ __device__ __forceinline__ void mark_agents(const EnvSmem<MapT>& S, const StepPa
   const int PP = p.P, PS = p.PS;
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2)
+    #pragma unroll 1
     for (int i = lane; i < nl[s2]; i += 32)
       if (S.flg[s2][i] & F_ALIVE) S.scr[CELLP((unsigned)S.pos[s2][i])] = v;
   __syncwarp();
@@ -583,6 +592,7 @@ __device__ __forceinline__ void publish_counts(const StepParams& p, int env, int
           if (__shfl_sync(FULL, last3, 0)) {  // last group: totals of this output and of the next one
             __threadfence();
             int t[4] = {0, 0, 0, 0};
+            #pragma unroll 1
             for (int g = lane; g < n_grp; g += 32) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) t[q] += (int)(unsigned)ld_volatile(p.sum2[par] + (size_t)g * 4 + q);

@@ -1,0 +1,536 @@
+"""The reference's evolutionary env classes — dict API over the CUDA step.
+
+`PredPreyGrassEco`   ~ predpreygrass/evolutionary/eco_evolutionary/predpreygrass_rllib_env.py (ECO)
+`PredPreyGrassStag`  ~ predpreygrass/evolutionary/stag_hunt_forward_view_nature_nurture/predpreygrass_rllib_env.py (STAG)
+
+Same constructor (`config` dict with the reference's keys; ECO reads its mandatory keys with `config[...]`,
+ECO:36-120, so a missing one raises KeyError here as well), same `reset(*, seed, options)` / `step(action_dict)`
+returning agent-id string dicts with `"__all__"` (ECO:274-507, STAG:414-718), same spaces
+(ECO:1396-1418, STAG:1784-1816) and the attributes the reference's `random_policy.py` / evaluation scripts read
+(`agents`, `possible_agents`, `agent_positions`, `agent_energies`, `agent_ages`, `grass_positions`,
+`grass_energies`, `agents_just_ate`, `current_step`, `active_num_predators/prey`, ECO `agent_genomes`-style speeds,
+STAG `predator_facing`, `predator_cooperation_trait`, the team-capture counters).
+
+One object = one env instance of a 1-env `BatchedPredPreyGrass` handle; all simulation work is done by the CUDA
+kernels, this file converts the handle's row batch to the reference's dicts.  For throughput use
+`BatchedPredPreyGrass` (thousands of envs, tensors stay on the GPU).
+
+`reset(seed=s)` reproduces the reference's reset exactly: the numpy draws of the reference's reset
+(ECO:130,208-215,1752 — founder speeds then `rng.choice` cells; STAG:273,2140-2169 — `rng.choice` cells, then per
+founder predator a facing index and a raw cooperation trait) are made on the host from `np.random.default_rng(s)`
+and handed to the device as a replay tape (`reference_reset_tape_eco` / `_stag`, pinned against the golden
+recordings of the reference in tests/test_env_tapes.py).  Draws AFTER the reset (mutation, spawn fallback, capture
+success) come from the device's Philox stream unless `options={"ppg_tape": (ints, reals)}` supplies the
+reference's recorded draws (what the parity tests do).
+
+Dict key order: ECO builds its return dicts from Python sets (ECO:413,424 — hash order, different in every
+process), so this adapter uses (species, id) order.  STAG: live agents in `self.agents` order (STAG:551), then the
+agents that ended this step sorted by id string (STAG:567-568).
+"""
+import numpy as np
+
+from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO, VARIANT_STAG,
+                     make_config)
+from .env import Box, Discrete, _Base
+
+try:
+    from gymnasium.spaces import Dict as DictSpace
+    from gymnasium.spaces import MultiDiscrete
+except Exception:  # noqa: BLE001
+    class MultiDiscrete:
+        def __init__(self, nvec):
+            self.nvec = np.asarray(nvec, np.int64)
+            self.shape = self.nvec.shape
+            self._rng = np.random.default_rng()
+
+        def sample(self):
+            return (self._rng.random(self.nvec.shape) * self.nvec).astype(np.int64)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.nvec.shape and bool((x >= 0).all() and (x < self.nvec).all())
+
+    class DictSpace(dict):
+        @property
+        def spaces(self):
+            return self
+
+        def sample(self):
+            return {k: v.sample() for k, v in self.items()}
+
+FACING_OPTIONS = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]  # STAG:197-206
+
+
+# ---------------------------------------------------------------------------------------------- reset tapes
+def reference_reset_tape_eco(seed, config):
+    """The draws of ECO's `reset(seed)` in the tape layout of include/ppg.h: founders are registered first
+    (one `rng.normal(mean, std)` each where std > 0, predators then prey; ECO:208-215, genome.py:31-36,42-46), then
+    the cells come from one `rng.choice(G*G, n, replace=False)` (ECO:1752).  -> (cells int32, founder speeds f64)"""
+    rng = np.random.default_rng(seed)
+    G = config["grid_size"]
+    n_pred, n_prey = config["n_initial_active_predators"], config["n_initial_active_prey"]
+    speeds = []
+    if config.get("genome_enabled", True):
+        lo, hi = config.get("trait_bounds", {}).get("speed", (0.5, 2.0))
+        for role, n in (("predator", n_pred), ("prey", n_prey)):
+            f = config.get("founder_genome", {}).get(role, {})
+            mean, std = f.get("speed_mean", 1.0), f.get("speed_std", 0.0)
+            for _ in range(n):
+                v = mean if std <= 0 else float(rng.normal(mean, std))
+                speeds.append(float(np.clip(v, float(lo), float(hi))))
+    cells = rng.choice(G * G, size=n_pred + n_prey + config["initial_num_grass"], replace=False)
+    return np.asarray(cells, np.int32), np.asarray(speeds, np.float64)
+
+
+def reference_reset_tape_stag(seed, config):
+    """The draws of STAG's `reset(seed)`: `rng.choice(list(range(G*G)), n, replace=False)` (STAG:2140), then per
+    founder predator `rng.integers(8)` (facing, STAG:941) and, with the cooperation trait enabled,
+    `rng.normal(mean, std)` (STAG:1087).  -> (cells, facing indices, raw traits)"""
+    g = config.get
+    rng = np.random.default_rng(seed)
+    G = config["grid_size"]
+    n_pred = g("n_initial_active_type_1_predator", 0) + g("n_initial_active_type_2_predator", 0)
+    n_prey = g("n_initial_active_type_1_prey", 0) + g("n_initial_active_type_2_prey", 0)
+    cells = rng.choice(list(range(G * G)), size=n_pred + n_prey + g("initial_num_grass", 0), replace=False)
+    facing, traits = [], []
+    for _ in range(n_pred):
+        facing.append(int(rng.integers(8)))
+        if g("coop_trait_enabled", True):
+            traits.append(float(rng.normal(g("coop_trait_init_mean", 0.5), g("coop_trait_init_std", 0.1))))
+    return np.asarray(cells, np.int32), np.asarray(facing, np.int32), np.asarray(traits, np.float64)
+
+
+# ---------------------------------------------------------------------------------------------- common adapter
+class _RowDictEnv(_Base):
+    """rows of env 0 of a 1-env handle  <->  the reference's per-agent dicts"""
+
+    _variant = None
+    _stay = 0
+
+    def __init__(self, config=None):
+        super().__init__()
+        if config is None:
+            raise ValueError("Environment config must be provided explicitly.")  # ECO:21-22, STAG:21-22
+        from .batched import BatchedPredPreyGrass  # needs the CUDA extension; fails loudly without it
+
+        self.config = config
+        self._cfg = make_config(config, variant=self._variant, cap_live=config.get("cap_live"), autoreset=False,
+                                seed=config.get("seed") or 0)
+        self._batch = BatchedPredPreyGrass(self._cfg, 1, device=config.get("cuda_device", 0))
+        self.max_steps = config["max_steps"] if self._variant == VARIANT_ECO else config.get("max_steps", 10000)
+        self.grid_size = self._cfg.grid_size
+        self.num_obs_channels = self._cfg.num_obs_channels
+        self.predator_obs_range, self.prey_obs_range = self._cfg.obs_range[0], self._cfg.obs_range[1]
+        self.initial_num_grass = self._cfg.n_grass
+        self.grass_agents = [f"grass_{k}" for k in range(self.initial_num_grass)]
+        self.agents = []
+        self.agents_just_ate = set()
+        self.current_step = 0
+        self._rows = {}
+        self._done = True
+        self._state = None
+
+    # -- naming hooks
+    def _name(self, s, i):
+        raise NotImplementedError
+
+    def _key(self, agent):
+        raise NotImplementedError
+
+    def _action(self, s, value):
+        return int(value)
+
+    def _read(self):
+        raise NotImplementedError
+
+    # -- reset / step plumbing
+    def _reset_device(self, seed, cells, reals, options):
+        b = self._batch
+        extra = (options or {}).get("ppg_tape")
+        if extra is not None:
+            cells = np.concatenate([cells, np.asarray(extra[0], np.int32)])
+            reals = np.concatenate([reals, np.asarray(extra[1], np.float64)])
+        b.load_tape([cells], [reals])
+        b.reset(seeds=np.array([np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)], np.uint64))
+        self.current_step = 0
+        self._done = False
+        self._state = None
+        return b.outputs_numpy()
+
+    def _step_device(self, action_dict):
+        import torch
+
+        if self._done:
+            raise RuntimeError("step() called on a finished episode; call reset()")
+        self._state = None
+        b = self._batch
+        acts = [np.full(max(1, b.row_capacity[s]), self._stay, np.int32) for s in range(2)]
+        order = [np.zeros(max(1, b.row_capacity[s]), np.int32) for s in range(2)]
+        seen = [0, 0]
+        for agent, action in action_dict.items():
+            if agent not in self._rows:
+                self._unknown_actor(agent)
+                continue
+            s, row = self._rows[agent]
+            acts[s][row] = self._action(s, action)
+            order[s][row] = seen[s]
+            seen[s] += 1
+        if seen[0] + seen[1] != len(self._rows):
+            missing = [a for a in self._rows if a not in action_dict]
+            raise KeyError(f"action_dict misses live agents {missing[:4]} (every live agent must act)")
+        t = [torch.from_numpy(x).to(b.device) for x in acts + order]
+        b.step_ordered(t[0], t[1], t[2], t[3])
+        out = b.outputs_numpy()
+        self.current_step = int(out["env_step"][0])
+        return out
+
+    def _unknown_actor(self, agent):
+        raise KeyError(agent)
+
+    def _rows_of(self, out):
+        """[(name, species, row, flags)] of env 0: rows of the agents that acted, then the newborn rows"""
+        res = []
+        for group in ("old", "new"):
+            for s in range(2):
+                if group == "old":
+                    r0, r1 = int(out[f"old_off{s}"][0]), int(out[f"old_off{s}"][1])
+                else:
+                    r0 = int(out[f"new_off{s}"][0])
+                    r1 = r0 + int(out[f"new_cnt{s}"][0])
+                for r in range(r0, r1):
+                    res.append((self._name(s, int(out[f"row_agent{s}"][r])), s, r, int(out[f"flags{s}"][r])))
+        return res
+
+    # -- attributes read by renderers / random_policy.py (ECO random_policy.py:75-82)
+    @property
+    def agent_positions(self):
+        st = self._read()
+        return {self._name(s, int(i)): (int(x), int(y)) for s in range(2) for i, (x, y) in zip(st["ids"][s], st["xy"][s])}
+
+    @property
+    def predator_positions(self):
+        return {k: v for k, v in self.agent_positions.items() if "predator" in k}
+
+    @property
+    def prey_positions(self):
+        return {k: v for k, v in self.agent_positions.items() if "prey" in k}
+
+    @property
+    def agent_energies(self):
+        st = self._read()
+        return {self._name(s, int(i)): float(e) for s in range(2) for i, e in zip(st["ids"][s], st["energy"][s])}
+
+    @property
+    def agent_ages(self):
+        st = self._read()
+        return {self._name(s, int(i)): int(a) for s in range(2) for i, a in zip(st["ids"][s], st["age"][s])}
+
+    @property
+    def grass_positions(self):
+        st = self._read()
+        return {f"grass_{k}": (int(x), int(y)) for k, (x, y) in enumerate(st["grass_xy"])}
+
+    @property
+    def grass_energies(self):
+        st = self._read()
+        return {f"grass_{k}": float(e) for k, e in enumerate(st["grass_energy"])}
+
+    def get_state_snapshot(self):
+        return {"blob": self._batch.snapshot(), "current_step": self.current_step, "agents": list(self.agents),
+                "agents_just_ate": set(self.agents_just_ate), "done": self._done}
+
+    def restore_state_snapshot(self, snapshot):
+        self._batch.restore(snapshot["blob"])
+        self.current_step = snapshot["current_step"]
+        self.agents = list(snapshot["agents"])
+        self.agents_just_ate = set(snapshot["agents_just_ate"])
+        self._done = snapshot["done"]
+        self._state = None
+        out = self._batch.outputs_numpy()  # ppg_restore relabels the rows densely in list order
+        self._rows = {}
+        for s in range(2):
+            off = out[f"old_off{s}"]
+            for r in range(int(off[0]), int(off[1])):
+                self._rows[self._name(s, int(out[f"row_agent{s}"][r]))] = (s, r)
+
+    def close(self):
+        if getattr(self, "_batch", None) is not None:
+            self._batch.close()
+            self._batch = None
+
+
+# ---------------------------------------------------------------------------------------------- ECO
+class PredPreyGrassEco(_RowDictEnv):
+    """eco_evolutionary `PredPreyGrass(config)`: heritable speed trait, 25 actions, move cost, ageing, carcasses."""
+
+    _variant = VARIANT_ECO
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        c = self._cfg
+        self.n_possible_predators, self.n_possible_prey = config["n_possible_predators"], config["n_possible_prey"]
+        self.n_initial_active_predators, self.n_initial_active_prey = c.n_initial[0], c.n_initial[1]
+        self.action_range = config["action_range"]
+        self.genome_enabled = bool(c.genome_enabled)
+        self.include_speed_in_obs = bool(c.include_speed_in_obs)
+        self.speed_distance_threshold = c.speed_distance_threshold
+        self._stay = (self.action_range * self.action_range) // 2
+        self.possible_agents = [f"predator_{i}" for i in range(self.n_possible_predators)] + [
+            f"prey_{j}" for j in range(self.n_possible_prey)]  # ECO:1378-1394
+        C = self.num_obs_channels + (1 if self.include_speed_in_obs else 0)  # ECO:1396-1406
+        pred_space = Box(low=0, high=100.0, shape=(C, self.predator_obs_range, self.predator_obs_range), dtype=np.float32)
+        prey_space = Box(low=0, high=100.0, shape=(C, self.prey_obs_range, self.prey_obs_range), dtype=np.float32)
+        act = Discrete(self.action_range ** 2)
+        self.observation_spaces = {a: pred_space if "predator" in a else prey_space for a in self.possible_agents}
+        self.action_spaces = {a: act for a in self.possible_agents}
+        self.observation_space = DictSpace(self.observation_spaces)
+        self.action_space = DictSpace(self.action_spaces)
+        d = (self.action_range - 1) // 2  # ECO:225-232
+        self.action_to_move_tuple_agents = {i: (i // self.action_range - d, i % self.action_range - d) for i in range(self.action_range ** 2)}
+
+    def _name(self, s, i):
+        return f"predator_{i}" if s == 0 else f"prey_{i}"
+
+    def _read(self):
+        if self._state is None:
+            self._state = self._batch.read_env_eco(0)
+        return self._state
+
+    def reset(self, *, seed=None, options=None):
+        super().reset(seed=seed)
+        if seed is None:
+            seed = self.config["seed"]  # ECO:128-129
+        cells, speeds = reference_reset_tape_eco(seed, self.config)
+        out = self._reset_device(seed, cells, speeds, options)
+        obs, *_ = self._dicts(out)
+        self.agents = list(obs)
+        return obs, {}
+
+    def _dicts(self, out):
+        obs, rew, term, trunc = {}, {}, {}, {}
+        self._rows, self.agents_just_ate = {}, set()
+        rows = sorted(self._rows_of(out), key=lambda t: (t[1], int(t[0].rsplit("_", 1)[1])))
+        for name, s, r, f in rows:
+            obs[name] = out[f"obs{s}"][r]
+            rew[name] = float(out[f"reward{s}"][r])
+            term[name] = bool(f & ROW_TERMINATED)
+            trunc[name] = bool(f & ROW_TRUNCATED)
+            if f & ROW_ATE:
+                self.agents_just_ate.add(name)
+            if not f & (ROW_TERMINATED | ROW_TRUNCATED):
+                self._rows[name] = (s, r)
+        return obs, rew, term, trunc
+
+    def step(self, action_dict):
+        out = self._step_device(action_dict)
+        obs, rew, term, trunc = self._dicts(out)
+        flags = int(out["env_flags"][0])
+        infos = {a: {} for a in rew}
+        term["__all__"] = bool(flags & ENV_TERMINATED)   # ECO:392,408 extinction
+        trunc["__all__"] = bool(flags & ENV_TRUNCATED)   # ECO:452-486 time limit, same call
+        if flags & (ENV_TERMINATED | ENV_TRUNCATED):
+            self._done = True
+            self.agents = []  # ECO:495,500-501
+            self._rows = {}
+            infos["__all__"] = {"training_metrics": self.live_speed_metrics()}
+        else:
+            # `self.agents` keeps insertion order: survivors, then this step's newborns, predators first (ECO:353-367)
+            prev = set(self.agents)
+            self.agents = [a for a in self.agents if a in self._rows] + [a for a in self._rows if a not in prev]
+        return obs, rew, term, trunc, infos
+
+    # ECO attributes
+    @property
+    def active_num_predators(self):
+        return int(self._read()["active_num"][0])
+
+    @property
+    def active_num_prey(self):
+        return int(self._read()["active_num"][1])
+
+    @property
+    def agent_speeds(self):
+        """`{agent: agent_genomes[agent].speed}` (ECO:168,575-580)"""
+        st = self._read()
+        return {self._name(s, int(i)): float(v) for s in range(2) for i, v in zip(st["ids"][s], st["speed"][s])}
+
+    @property
+    def dead_prey(self):
+        st = self._read()
+        return {self._name(1, int(i)) for i, d in zip(st["ids"][1], st["dead_prey"]) if d}
+
+    def live_speed_metrics(self):
+        """speed distribution of the live population per role (ECO `_build_live_speed_metrics`, ECO:509-539)"""
+        st = self._read()
+        res = {}
+        for s, role in enumerate(("predator", "prey")):
+            v = np.asarray(st["speed"][s], np.float64)
+            res[f"{role}_count"] = int(v.size)
+            if v.size:
+                res[f"{role}_speed_mean"] = float(v.mean())
+                res[f"{role}_speed_std"] = float(v.std())
+                res[f"{role}_fraction_fast"] = float((v >= self.speed_distance_threshold).mean())
+        return res
+
+
+# ---------------------------------------------------------------------------------------------- STAG
+class PredPreyGrassStag(_RowDictEnv):
+    """stag_hunt_forward_view_nature_nurture `PredPreyGrass(config)`: mammoths and rabbits, join_hunt team capture,
+    forward-shifted predator view, heritable cooperation trait."""
+
+    _variant = VARIANT_STAG
+    _stay = 4
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        c, g = self._cfg, config.get
+        self.strict_rllib_output = bool(g("strict_rllib_output", True))
+        self._n1 = (c.n_possible_t[0][0], c.n_possible_t[1][0])
+        self.n_possible_type_1_predators, self.n_possible_type_2_predators = c.n_possible_t[0][0], c.n_possible_t[0][1]
+        self.n_possible_type_1_prey, self.n_possible_type_2_prey = c.n_possible_t[1][0], c.n_possible_t[1][1]
+        self.type_1_act_range, self.type_2_act_range = c.type_action_range[0], c.type_action_range[1]
+        self.coop_trait_enabled = bool(c.coop_trait_enabled)
+        self.possible_agents = ([f"type_1_predator_{i}" for i in range(c.n_possible_t[0][0])] +
+                                [f"type_2_predator_{i}" for i in range(c.n_possible_t[0][1])] +
+                                [f"type_1_prey_{i}" for i in range(c.n_possible_t[1][0])] +
+                                [f"type_2_prey_{i}" for i in range(c.n_possible_t[1][1])])  # STAG:1768-1782
+        C = self.num_obs_channels
+        pred_space = Box(low=0, high=100.0, shape=(C, self.predator_obs_range, self.predator_obs_range), dtype=np.float32)
+        prey_space = Box(low=0, high=100.0, shape=(C, self.prey_obs_range, self.prey_obs_range), dtype=np.float32)
+        self.observation_spaces = {a: pred_space if "predator" in a else prey_space for a in self.possible_agents}
+        sizes = {"type_1": max(1, self.type_1_act_range ** 2), "type_2": max(1, self.type_2_act_range ** 2)}
+        self.action_spaces = {a: MultiDiscrete([sizes[a[:6]], 2]) if "predator" in a else Discrete(sizes[a[:6]])
+                              for a in self.possible_agents}  # STAG:1800-1816
+        self.observation_space = DictSpace(self.observation_spaces)
+        self.action_space = DictSpace(self.action_spaces)
+        self.predator_join_intent = {}
+
+    def _name(self, s, i):
+        sp = "predator" if s == 0 else "prey"
+        n1 = self._n1[s]
+        return f"type_1_{sp}_{i}" if i < n1 else f"type_2_{sp}_{i - n1}"
+
+    def _action(self, s, value):
+        """`_split_action` (STAG:771-799): predators pass [move, join_hunt] as array / tuple / dict; join defaults to 1"""
+        if s == 1:
+            return int(np.asarray(value).reshape(-1)[0]) if not isinstance(value, (int, np.integer)) else int(value)
+        if isinstance(value, dict):
+            move, join = int(value.get("move", 0)), int(value.get("join_hunt", 1))
+        else:
+            v = np.asarray(value).reshape(-1)
+            move, join = int(v[0]), (int(v[1]) if v.size > 1 else 1)
+        return move | ((1 if join else 0) << 8)
+
+    def _unknown_actor(self, agent):
+        # STAG:806-807 skips actions of agents that are no longer positioned (the ids that ended in the previous
+        # step are still listed in `self.agents`, STAG:565-573, so callers do send them)
+        if agent not in self.possible_agents:
+            raise KeyError(agent)
+
+    def _read(self):
+        if self._state is None:
+            self._state = self._batch.read_env_stag(0)
+        return self._state
+
+    def reset(self, *, seed=None, options=None):
+        super().reset(seed=seed)
+        if seed is None:
+            seed = self.config.get("seed")
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, np.uint64)[0] >> 1)
+        cells, facing, traits = reference_reset_tape_stag(seed, self.config)
+        out = self._reset_device(seed, np.concatenate([cells, facing]), traits, options)
+        self.predator_join_intent = {}
+        obs = {}
+        self._rows = {}
+        for name, s, r, f in self._rows_of(out):  # founders: type_1/type_2 predators, type_1/type_2 prey (STAG:340-380)
+            obs[name] = out[f"obs{s}"][r]
+            self._rows[name] = (s, r)
+        self.agents = list(obs)
+        return obs, {}
+
+    def step(self, action_dict):
+        self.predator_join_intent = {}
+        for a, v in action_dict.items():
+            if "predator" in a and a in self._rows:
+                self.predator_join_intent[a] = bool(self._action(0, v) >> 8)
+        out = self._step_device({a: v for a, v in action_dict.items() if a in self._rows or a not in self.possible_agents})
+        flags = int(out["env_flags"][0])
+        rows = {name: (s, r, f) for name, s, r, f in self._rows_of(out)}
+        ended = lambda f: bool(f & (ROW_TERMINATED | ROW_TRUNCATED))  # noqa: E731
+        time_limit = bool(flags & ENV_TRUNCATED)
+        extinct = bool(flags & ENV_TERMINATED)
+        # self.agents: survivors in list order, then this step's newborns (predators, prey: STAG:490-496)
+        live = [a for a in self.agents if a in rows and not (rows[a][2] & ROW_TERMINATED)]
+        live += [a for a in rows if a not in self._rows and not (rows[a][2] & ROW_TERMINATED) and a not in live]
+        gone = sorted(a for a in rows if a not in live)  # STAG:567-568
+        obs, rew, term, trunc = {}, {}, {}, {}
+        self.agents_just_ate = set()
+        for a in live + gone:
+            s, r, f = rows[a]
+            obs[a] = out[f"obs{s}"][r]
+            rew[a] = float(out[f"reward{s}"][r])
+            term[a] = bool(f & ROW_TERMINATED)
+            trunc[a] = bool(f & ROW_TRUNCATED)
+            if f & ROW_ATE:
+                self.agents_just_ate.add(a)
+        self._rows = {a: rows[a][:2] for a in live if not ended(rows[a][2])}
+        self._state = None
+        infos = self._infos(live + gone)
+        term["__all__"] = extinct            # STAG:584-592
+        trunc["__all__"] = time_limit        # STAG:659-716
+        self.agents = live + gone if self.strict_rllib_output else live  # STAG:565-573
+        if extinct or time_limit:
+            self._done = True
+        return obs, rew, term, trunc, infos
+
+    def _infos(self, names):
+        """STAG:498-546: the team-capture counters in every agent's info and in infos["__all__"]"""
+        st = self._read()
+        cap, capr = st["capture"], st["capture_real"]
+        m_att, r_att = int(cap[4] + cap[5]), int(cap[6] + cap[7])
+        common = {
+            "team_capture_successes": int(cap[0]), "team_capture_failures": int(cap[1]),
+            "team_capture_coop_successes": int(cap[2]), "team_capture_coop_failures": int(cap[3]),
+            "team_capture_mammoth_successes": int(cap[4]), "team_capture_mammoth_failures": int(cap[5]),
+            "team_capture_mammoth_success_rate": int(cap[4]) / m_att if m_att else 0.0,
+            "team_capture_rabbit_successes": int(cap[6]), "team_capture_rabbit_failures": int(cap[7]),
+            "team_capture_rabbit_success_rate": int(cap[6]) / r_att if r_att else 0.0,
+        }
+        trait = {self._name(0, int(i)): float(v) for i, v in zip(st["ids"][0], st["trait"])}
+        infos = {}
+        for a in names:
+            info = dict(common)
+            if "predator" in a:
+                info["join_hunt"] = bool(self.predator_join_intent.get(a, True))
+                info["coop_trait"] = trait.get(a, 0.0)
+            infos[a] = info
+        g = dict(common)
+        g["team_capture_last_success_prob"] = float(capr[0])
+        g["team_capture_last_effort_ratio"] = float(capr[1])
+        g["team_capture_attempts"] = int(cap[8])
+        g["team_capture_avg_success_prob"] = float(capr[2]) / int(cap[8]) if cap[8] > 0 else 0.0
+        tv = np.asarray(st["trait"], np.float64)
+        g["predator_mean_coop_trait"] = float(tv.mean()) if tv.size and self.coop_trait_enabled else 0.0
+        g["predator_trait_variance"] = float(tv.var()) if tv.size and self.coop_trait_enabled else 0.0
+        infos["__all__"] = g
+        return infos
+
+    # STAG attributes
+    @property
+    def active_num_predators(self):
+        return len(self._read()["ids"][0])
+
+    @property
+    def active_num_prey(self):
+        return len(self._read()["ids"][1])
+
+    @property
+    def predator_facing(self):
+        st = self._read()
+        return {self._name(0, int(i)): FACING_OPTIONS[int(f)] for i, f in zip(st["ids"][0], st["facing"])}
+
+    @property
+    def predator_cooperation_trait(self):
+        st = self._read()
+        return {self._name(0, int(i)): float(v) for i, v in zip(st["ids"][0], st["trait"])}

@@ -1,0 +1,130 @@
+"""`PredPreyGrassEco` / `PredPreyGrassStag` (the reference's MultiAgentEnv dict API over the CUDA step) against the
+episodes recorded from the unmodified reference classes through that same API (`-m gpu`).  reset(seed) uses the
+adapter's own host-side reproduction of the reference's reset draws; the draws after the reset (mutation, spawn
+fallback, capture success) are the reference's recorded ones (`options={"ppg_tape": ...}`)."""
+import numpy as np
+import pytest
+
+from tests.helpers import golden_cases, load_golden, sha_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _caps(cfg, keys):
+    return tuple(min(sum(cfg.get(k, 0) for k in ks), lim) for ks, lim in zip(keys, (224, 416)))
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases(("eco",)) if "ghost" not in n])
+def test_eco_dict_adapter_replays_reference_episode(name):
+    from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
+
+    z, cfg = load_golden(name)
+    cfg.pop("variant")
+    cfg["cap_live"] = _caps(cfg, (("n_possible_predators",), ("n_possible_prey",)))
+    env = PredPreyGrassEco(cfg)
+    names = ("predator", "prey")
+    key = lambda s, i: f"{names[s]}_{i}"  # noqa: E731
+    obs, infos = env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    assert infos == {}
+    assert list(obs) == [key(s, i) for s, i in zip(z["reset_row_s"], z["reset_row_id"])]
+    assert np.array_equal(sha_f32([obs[k] for k in obs]), z["reset_sha"])
+    for a, o in obs.items():
+        assert o.dtype == np.float32 and o.shape == env.observation_spaces[a].shape
+    shuffle = str(z["order"]) == "shuffle"
+    for t in range(len(z["steps"])):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {key(s, i): int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        if not shuffle:  # the recording passed the actions in id order; the adapter's row order is the same
+            assert list(acts) == sorted(acts, key=lambda a: (a[:4] == "prey", int(a.rsplit("_", 1)[1])))
+        obs, rew, term, trunc, infos = env.step(acts)
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        keys = [key(s, i) for s, i in zip(z["row_s"][r0:r1], z["row_id"][r0:r1])]
+        assert list(obs) == keys and list(rew) == keys, (name, t)
+        assert np.array_equal(np.array([rew[k] for k in keys], np.float32), z["row_rew"][r0:r1].astype(np.float32)), (name, t)
+        assert [int(term[k]) for k in keys] == list(z["row_term"][r0:r1]), (name, t)
+        assert [int(trunc[k]) for k in keys] == list(z["row_trunc"][r0:r1]), (name, t)
+        assert np.array_equal(sha_f32([obs[k] for k in keys]), z["obs_sha"][t]), (name, t)
+        assert term["__all__"] == bool(z["all_term"][t]) and trunc["__all__"] == bool(z["all_trunc"][t]), (name, t)
+        assert set(infos) - {"__all__"} == set(keys)
+        assert env.current_step == int(z["steps"][t])
+        if term["__all__"] or trunc["__all__"]:
+            assert env.agents == []
+            break
+        g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
+        assert env.agents == [key(s, i) for s, i in zip(z["ag_s"][g0:g1], z["ag_id"][g0:g1])], (name, t)
+        s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+        want = {key(s, i): ((int(x), int(y)), float(e), int(a), float(v)) for s, i, x, y, e, a, v in
+                zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_x"][s0:s1], z["st_y"][s0:s1], z["st_e"][s0:s1],
+                    z["st_age"][s0:s1], z["st_speed"][s0:s1])}
+        pos, en, age, sp = env.agent_positions, env.agent_energies, env.agent_ages, env.agent_speeds
+        assert sorted(pos) == sorted(want), (name, t)
+        assert all((pos[k], en[k], age[k], sp[k]) == want[k] for k in want), (name, t)
+        assert (env.active_num_predators, env.active_num_prey) == tuple(z["active"][t])
+    with pytest.raises(KeyError):
+        env.reset(seed=1)
+        env.step({"predator_399": 0})
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_cases(("stag",)))
+def test_stag_dict_adapter_replays_reference_episode(name):
+    from predpreygrass_b200.env_evolutionary import FACING_OPTIONS, PredPreyGrassStag
+
+    z, cfg = load_golden(name)
+    cfg.pop("variant")
+    cfg["cap_live"] = _caps(cfg, (("n_possible_type_1_predators", "n_possible_type_2_predators"),
+                                  ("n_possible_type_1_prey", "n_possible_type_2_prey")))
+    env = PredPreyGrassStag(cfg)
+    n1 = (cfg.get("n_possible_type_1_predators", 0), cfg.get("n_possible_type_1_prey", 0))
+    sp = ("predator", "prey")
+    key = lambda s, i: f"type_1_{sp[s]}_{i}" if i < n1[s] else f"type_2_{sp[s]}_{i - n1[s]}"  # noqa: E731
+    obs, infos = env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["step_ints"], z["step_reals"])})
+    assert list(obs) == [key(s, i) for s, i in zip(z["reset_row_s"], z["reset_row_id"])] == env.agents
+    assert np.array_equal(sha_f32([obs[k] for k in obs]), z["reset_sha"])
+    rng = np.random.default_rng(0)
+    for t in range(len(z["steps"])):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {}
+        for s, i, mv, jn in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_move"][a0:a1], z["act_join"][a0:a1]):
+            if s == 1:
+                acts[key(s, i)] = int(mv)
+            else:  # the three accepted predator action forms (STAG:771-799)
+                form = rng.integers(3)
+                acts[key(s, i)] = (np.array([mv, jn]) if form == 0 else (int(mv), int(jn)) if form == 1
+                                   else {"move": int(mv), "join_hunt": int(jn)})
+        assert list(acts) == env.agents or str(z["order"]) == "shuffle", (name, t)  # the recording acted for self.agents
+        obs, rew, term, trunc, infos = env.step(acts)
+        g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
+        agents = [key(s, i) for s, i in zip(z["ag_s"][g0:g1], z["ag_id"][g0:g1])]
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        keys = [key(s, i) for s, i in zip(z["row_s"][r0:r1], z["row_id"][r0:r1])]
+        live = [k for k in agents if k in obs and not term[k]]
+        assert [k for k in obs if not term[k]] == live, (name, t)   # observation-dict order of the live agents (STAG:551)
+        assert set(obs) == set(keys) and set(rew) == set(keys), (name, t)
+        assert np.array_equal(np.array([rew[k] for k in keys], np.float32), z["row_rew"][r0:r1].astype(np.float32)), (name, t)
+        assert [int(term[k]) for k in keys] == list(z["row_term"][r0:r1]), (name, t)
+        assert [int(trunc[k]) for k in keys] == list(z["row_trunc"][r0:r1]), (name, t)
+        ordered = [obs[k] for k in keys if "predator" in k] + [obs[k] for k in keys if "prey" in k]
+        assert np.array_equal(sha_f32(ordered), z["obs_sha"][t]), (name, t)
+        assert term["__all__"] == bool(z["all_term"][t]) and trunc["__all__"] == bool(z["all_trunc"][t]), (name, t)
+        assert env.current_step == int(z["steps"][t])
+        # the recording kept the positioned part of `env.agents` (under strict_rllib_output the list also carries the
+        # ids that ended this step, STAG:565-573)
+        assert [a for a in env.agents if not term.get(a, False)] == agents, (name, t)
+        if cfg.get("strict_rllib_output", True):
+            assert sorted(env.agents) == sorted(keys), (name, t)
+        c = z["counters"][t]
+        assert infos["__all__"]["team_capture_successes"] == c[0] and infos["__all__"]["team_capture_attempts"] == c[8], (name, t)
+        if term["__all__"] or trunc["__all__"]:
+            break
+        s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+        want = {key(s, i): ((int(x), int(y)), float(e), int(a)) for s, i, x, y, e, a in
+                zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_x"][s0:s1], z["st_y"][s0:s1], z["st_e"][s0:s1], z["st_age"][s0:s1])}
+        pos, en, age = env.agent_positions, env.agent_energies, env.agent_ages
+        assert list(pos) != [] and sorted(pos) == sorted(want), (name, t)
+        assert all((pos[k], en[k], age[k]) == want[k] for k in want), (name, t)
+        face, trait = env.predator_facing, env.predator_cooperation_trait
+        for s, i, f, v in zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_face"][s0:s1], z["st_trait"][s0:s1]):
+            if s == 0:
+                assert face[key(s, i)] == FACING_OPTIONS[int(f)] and trait[key(s, i)] == float(v), (name, t)
+    env.close()
