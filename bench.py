@@ -49,7 +49,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.cap is None:
-        args.cap = {"base": [64, 192], "eco": [128, 320] if args.eco_rich else [32, 96], "stag": [64, 192]}[args.variant]
+        # slot capacity per env and species: large enough that no env of the rollout ever fills it (`status_envs` 0 —
+        # a full list would suppress births the reference allows); measured maxima: BASE 26 / 83, ECO 13 / 65,
+        # ECO reproduction-heavy 222 / 416+, STAG 127 / 416+ (scripts/status_diag.py)
+        args.cap = {"base": [64, 192], "eco": [256, 512] if args.eco_rich else [32, 96], "stag": [160, 640]}[args.variant]
     return args
 
 
@@ -72,7 +75,7 @@ def build_config(args, **kw):
         d = dict(ECO_CONFIG)
         if args.eco_rich:
             d.update(energy_gain_per_step_grass=0.3, prey_creation_energy_threshold=5.0, predator_creation_energy_threshold=8.0,
-                     energy_loss_per_step_predator=0.1)
+                     energy_loss_per_step_predator=0.1, n_possible_predators=8000, n_possible_prey=24000)
         return make_config(d, variant=VARIANT_ECO, cap_live=tuple(args.cap), **kw)
     return make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), **kw)
 

@@ -9,7 +9,7 @@ import os
 from .config import PpgBuffers, PpgConfig, PpgTape
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libppg_b200.so")
+LIB_PATH = os.environ.get("PPG_LIB") or os.path.join(HERE, "libppg_b200.so")  # PPG_LIB: an experimental build of the same ABI
 
 # every symbol include/ppg.h declares
 SYMBOLS = [

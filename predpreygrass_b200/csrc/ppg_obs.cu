@@ -21,12 +21,12 @@
 // Rows of agents that died mid-step were captured by the step kernel at that moment (DSC_SKIP).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ppg_step_common.cuh"
 
 namespace ppg {
 
-#define OBS_WARPS 4
-#define OBS_THREADS (OBS_WARPS * 32)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -58,11 +58,11 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsig
 #define OBS_MAX_DEFER 256
 
 // rows of one env from its image in shared memory.  k_lo/k_hi select old rows, newborn rows or both.
-template <typename MapT, int KIND>
+template <typename MapT, int KIND, int OBS_WARPS>
 __device__ __forceinline__ void obs_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
                                          const int n[2], const int births[2], const int new_base[2], bool do_old, bool do_new, int warp,
                                          int lane, unsigned& rowctr) {
-  // warp w takes every 4th row of the env (round robin across both species)
+  // warp w takes every OBS_WARPS-th row of the env (round robin across both species)
   int rot = 0;
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
@@ -102,6 +102,7 @@ __device__ __forceinline__ void obs_rows(const StepParams& p, const unsigned cha
 }
 
 // labels of the newborn rows, the rows their first actions are read from, new_off
+template <int OBS_THREADS>
 __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env, const int births[2], const int new_base[2], int tid) {
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
@@ -129,14 +130,15 @@ __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env,
 // queue entry is simply there already.
 // Newborn rows need the births of all envs before this one; if those are not all published yet when the env comes
 // by, its newborn rows are deferred to the end of this CTA's work (the image is fetched again).
-template <typename MapT, int KIND>
-__global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_constant__ StepParams p) {
+template <typename MapT, int KIND, int OBS_WARPS>
+__global__ void __launch_bounds__(OBS_WARPS * 32, 32 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ int s_env[2];
   __shared__ int s_nb[3];
   __shared__ int s_ndefer;
   __shared__ int s_defer[OBS_MAX_DEFER];
+  constexpr int OBS_THREADS = OBS_WARPS * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned stride = (unsigned)p.img_stride, img_bytes = (unsigned)p.img_bytes;
   const unsigned img0 = smem_u32(smem_img), bar0 = smem_u32(&s_bar[0]);
@@ -223,13 +225,13 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_co
       do_new = s_nb[2] != 0;
       if (do_new) {
         new_base[0] = s_nb[0]; new_base[1] = s_nb[1];
-        obs_newborn_labels(p, env, births, new_base, tid);
+        obs_newborn_labels<OBS_THREADS>(p, env, births, new_base, tid);
       }
     } else if (tid < 2) {
       p.new_off[tid][env] = 0;
     }
 
-    obs_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, births, new_base, true, do_new, warp, lane, rowctr);
+    obs_rows<MapT, KIND, OBS_WARPS>(p, ibp, vb32, env, old_base, n, births, new_base, true, do_new, warp, lane, rowctr);
 
     if (tid == 0) {
       if (nxt < 0) nxt = fetch(stage ^ 1u, true);
@@ -265,25 +267,25 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) ppg_obs_kernel(const __grid_co
     const int n[2] = {ih[IH_N0], ih[IH_N1]};
     const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
     const int new_base[2] = {s_nb[0], s_nb[1]};
-    obs_newborn_labels(p, env, births, new_base, tid);
-    obs_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, births, new_base, false, true, warp, lane, rowctr);
+    obs_newborn_labels<OBS_THREADS>(p, env, births, new_base, tid);
+    obs_rows<MapT, KIND, OBS_WARPS>(p, ibp, vb32, env, old_base, n, births, new_base, false, true, warp, lane, rowctr);
     __syncthreads();
     stage ^= 1u;
   }
 }
 
-template <typename MapT, int KIND>
+template <typename MapT, int KIND, int OBS_WARPS>
 static cudaError_t launch_obs_t(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)p.img_stride;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND, OBS_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_cta);
-  cfg.blockDim = dim3(OBS_THREADS);
+  cfg.blockDim = dim3(OBS_WARPS * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -291,26 +293,40 @@ static cudaError_t launch_obs_t(const StepParams& p, int n_cta, bool overlap, cu
   attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, ppg_obs_kernel<MapT, KIND>, p);
+  return cudaLaunchKernelEx(&cfg, ppg_obs_kernel<MapT, KIND, OBS_WARPS>, p);
 }
 
-template <typename MapT, int KIND>
+template <typename MapT, int KIND, int OBS_WARPS>
 static cudaError_t occupancy_obs_t(const StepParams& p, int* blocks_per_sm) {
   const size_t smem = 2 * (size_t)p.img_stride;
-  cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_obs_kernel<MapT, KIND, OBS_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_obs_kernel<MapT, KIND>, OBS_THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_obs_kernel<MapT, KIND, OBS_WARPS>, OBS_WARPS * 32, smem);
 }
 
-#define PPG_OBS_DISPATCH(FN, ...)                                                                           \
-  do {                                                                                                      \
-    const bool m8 = p.map_bytes == 1;                                                                       \
-    if (p.variant == PPG_VARIANT_ECO) return m8 ? FN<uint8_t, 1>(__VA_ARGS__) : FN<uint16_t, 1>(__VA_ARGS__);  \
-    if (p.variant == PPG_VARIANT_STAG) return m8 ? FN<uint8_t, 2>(__VA_ARGS__) : FN<uint16_t, 2>(__VA_ARGS__); \
-    return m8 ? FN<uint8_t, 0>(__VA_ARGS__) : FN<uint16_t, 0>(__VA_ARGS__);                                 \
+// Warps per CTA: 4 while eight double-buffered CTAs fit the SM's shared memory (images up to ~12 KB: BASE, ECO, STAG with
+// byte maps), else 8 — a big image (16-bit maps, cap_live > 254) halves the resident CTAs, and 8 warps per CTA keep the
+// SM's warp count up (STAG cap 160+640: 0.385 -> 0.293 ms per launch; BASE loses 12 % with 8, profiles/r01_final_summary.md)
+static inline bool obs_wide(const StepParams& p) {
+  if (const char* ev = getenv("PPG_OBS_WARPS")) return atoi(ev) >= 8;
+  return 2 * (size_t)p.img_stride * 8 > 200 * 1024;
+}
+
+#define PPG_OBS_DISPATCH_W(FN, NW, ...)                                                                            \
+  do {                                                                                                             \
+    const bool m8 = p.map_bytes == 1;                                                                              \
+    if (p.variant == PPG_VARIANT_ECO) return m8 ? FN<uint8_t, 1, NW>(__VA_ARGS__) : FN<uint16_t, 1, NW>(__VA_ARGS__);  \
+    if (p.variant == PPG_VARIANT_STAG) return m8 ? FN<uint8_t, 2, NW>(__VA_ARGS__) : FN<uint16_t, 2, NW>(__VA_ARGS__); \
+    return m8 ? FN<uint8_t, 0, NW>(__VA_ARGS__) : FN<uint16_t, 0, NW>(__VA_ARGS__);                                \
   } while (0)
 
-cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream) { PPG_OBS_DISPATCH(launch_obs_t, p, n_cta, overlap, stream); }
-cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm) { PPG_OBS_DISPATCH(occupancy_obs_t, p, blocks_per_sm); }
+cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_t stream) {
+  if (obs_wide(p)) PPG_OBS_DISPATCH_W(launch_obs_t, 8, p, n_cta, overlap, stream);
+  PPG_OBS_DISPATCH_W(launch_obs_t, 4, p, n_cta, overlap, stream);
+}
+cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm) {
+  if (obs_wide(p)) PPG_OBS_DISPATCH_W(occupancy_obs_t, 8, p, blocks_per_sm);
+  PPG_OBS_DISPATCH_W(occupancy_obs_t, 4, p, blocks_per_sm);
+}
 
 }  // namespace ppg
