@@ -52,7 +52,7 @@ def parse():
         # slot capacity per env and species: large enough that no env of the rollout ever fills it (`status_envs` 0 —
         # a full list would suppress births the reference allows); measured maxima: BASE 26 / 83, ECO 13 / 65,
         # ECO reproduction-heavy 222 / 416+, STAG 127 / 416+ (scripts/status_diag.py)
-        args.cap = {"base": [64, 192], "eco": [256, 512] if args.eco_rich else [32, 96], "stag": [160, 640]}[args.variant]
+        args.cap = {"base": [32, 128], "eco": [256, 512] if args.eco_rich else [32, 96], "stag": [160, 640]}[args.variant]
     return args
 
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 5
+#define PPG_ABI_VERSION 6
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -173,6 +173,13 @@ typedef struct ppg_config {
   double coop_trait_init_std;          /* STAG:141 */
   double coop_trait_mutation_std;      /* STAG:142,1095-1096 */
   double coop_trait_mutation_rate;     /* STAG:143-144 */
+  /* ---- seasonal grass regrowth of the BASE family (SEASON = predpreygrass/non_evolutionary/base_environment_seasonal/
+   * predpreygrass_rllib_env.py:63-67,224-234,268-271): `energy_gain_per_step_grass` is multiplied by season_multiplier[0]
+   * ("season_high_multiplier") while (current_step / season_length_steps) is even and by season_multiplier[1]
+   * ("season_low_multiplier") while it is odd.  season_length_steps = 0: no seasons (BASE). ---- */
+  double season_multiplier[2];
+  int32_t season_length_steps;         /* "season_length_steps" (SEASON:64) */
+  int32_t reserved2;
 } ppg_config;
 
 /* ppg_config.team_capture_success_model (STAG:1141-1148) */

@@ -330,8 +330,12 @@ static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id
     *G_AT(e, 1 + s, e->x[s][id], e->y[s][id]) = e->energy[s][id];
   }
   /* grass regrowth (BASE:252-256) */
+  /* base_environment_seasonal: gain * _current_season_multiplier() (SEASON:224-234,268-271; SEASON =
+   * predpreygrass/non_evolutionary/base_environment_seasonal/predpreygrass_rllib_env.py) */
+  double gain = c->energy_gain_grass;
+  if (c->season_length_steps > 0) gain = c->energy_gain_grass * c->season_multiplier[(e->current_step / c->season_length_steps) % 2];
   for (int g = 0; g < c->n_grass; ++g) {
-    double v = e->ge[g] + c->energy_gain_grass;
+    double v = e->ge[g] + gain;
     e->ge[g] = v < c->initial_energy_grass ? v : c->initial_energy_grass; /* min(a, b) */
     *G_AT(e, 3, e->gx[g], e->gy[g]) = e->ge[g];
   }

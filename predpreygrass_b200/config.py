@@ -15,6 +15,7 @@ REWARD_MODES = {
     "dense": REWARD_DENSE,
     "additive": REWARD_DENSE_ADDITIVE,
     "kickback": REWARD_SPARSE_KICKBACK,
+    "seasonal": REWARD_SPARSE,  # base_environment_seasonal: BASE rewards; the season keys of the config select the regrowth cycle
 }
 
 ROW_TERMINATED, ROW_TRUNCATED, ROW_NEWBORN, ROW_FOUNDER, ROW_ATE = 0x01, 0x02, 0x04, 0x08, 0x10
@@ -104,6 +105,9 @@ class PpgConfig(C.Structure):
         ("coop_trait_init_std", C.c_double),
         ("coop_trait_mutation_std", C.c_double),
         ("coop_trait_mutation_rate", C.c_double),
+        ("season_multiplier", C.c_double * 2),
+        ("season_length_steps", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -200,6 +204,14 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
     c.max_energy_gain_per_grass = c.max_energy_gain_per_prey = float("inf")
     c.speed_bounds[0], c.speed_bounds[1] = 0.5, 2.0
     c.speed_distance_threshold = 1.5
+    # base_environment_seasonal (SEASON:63-67): present only in that variant's config_env; 0 = no seasons
+    c.season_multiplier[0] = c.season_multiplier[1] = 1.0
+    if variant == VARIANT_BASE and "season_length_steps" in cfg:
+        c.season_length_steps = int(g("season_length_steps", 40))
+        if c.season_length_steps <= 0:
+            raise ValueError("season_length_steps must be positive (SEASON:232 divides by it)")
+        c.season_multiplier[0] = float(g("season_high_multiplier", 1.5))
+        c.season_multiplier[1] = float(g("season_low_multiplier", 0.5))
     if variant == VARIANT_ECO:
         _fill_eco(c, cfg)
     if variant == VARIANT_STAG:
@@ -383,6 +395,16 @@ BASE_CONFIG = {
     "initial_energy_grass": 2.0,
     "energy_gain_per_step_grass": 0.04,
 }
+
+
+# base_environment_seasonal/config_env.py:1-44 — BASE plus the square-wave regrowth cycle
+SEASONAL_CONFIG = dict(BASE_CONFIG, season_length_steps=40, season_high_multiplier=1.5, season_low_multiplier=0.5)
+
+
+def season_multiplier(config, current_step):
+    """`_current_season_multiplier` (SEASON:224-234) for a config dict"""
+    phase = (current_step // config.get("season_length_steps", 40)) % 2
+    return config.get("season_high_multiplier", 1.5) if phase == 0 else config.get("season_low_multiplier", 0.5)
 
 
 # eco_evolutionary/config/config_env_eco_evolutionary.py:1-88 — BASELINE config 4

@@ -147,6 +147,7 @@ void ppg_default_config(ppg_config* c) {
   c->max_energy_gain_per_grass = c->max_energy_gain_per_prey = HUGE_VAL;
   c->speed_bounds[0] = 0.5; c->speed_bounds[1] = 2.0;
   c->speed_distance_threshold = 1.5;
+  c->season_multiplier[0] = c->season_multiplier[1] = 1.0;  // season_length_steps = 0: no seasons
 }
 
 const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -158,6 +159,7 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   const bool eco = c->variant == PPG_VARIANT_ECO, stag = c->variant == PPG_VARIANT_STAG;
   if (c->reward_mode < 0 || c->reward_mode > PPG_REWARD_SPARSE_KICKBACK) { err = "bad reward_mode"; return PPG_ERR_INVALID; }
   if (c->grid_size < 2 || c->grid_size > 255) { err = "grid_size must be in [2,255]"; return PPG_ERR_INVALID; }
+  if (c->season_length_steps < 0 || (c->season_length_steps > 0 && (eco || stag))) { err = "season_length_steps: seasons exist in the BASE family only, >= 0"; return PPG_ERR_INVALID; }
   if (!eco && !stag && c->num_obs_channels != 4) { err = "BASE needs num_obs_channels == 4"; return PPG_ERR_INVALID; }
   if (stag) {
     if (c->num_obs_channels < 5) { err = "STAG needs num_obs_channels >= 5 (walls, predators, mammoths, rabbits, grass)"; return PPG_ERR_INVALID; }
@@ -261,6 +263,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   }
   P.n_grass = c.n_grass; P.max_steps = c.max_steps; P.reward_mode = c.reward_mode; P.autoreset = c.autoreset;
   P.grass_cap = (eco || stag) ? c.max_energy_grass : c.initial_energy_grass; P.grass_gain = c.energy_gain_grass;
+  P.season_len = (!eco && !stag) ? c.season_length_steps : 0;
+  for (int k = 0; k < 2; ++k) P.grass_gain_season[k] = c.energy_gain_grass * c.season_multiplier[k];  // the reference's fp64 product (SEASON:268)
   P.init_e_grass = c.initial_energy_grass;
   P.r_catch = c.reward_predator_catch_prey; P.r_eat = c.reward_prey_eat_grass; P.r_pstep = c.reward_predator_step;
   P.r_qstep = c.reward_prey_step; P.pen_caught = c.penalty_prey_caught;

@@ -43,6 +43,10 @@
 
 #include "ppg_step_common.cuh"
 
+#ifndef PPG_MIN_CTAS
+#define PPG_MIN_CTAS 20  // resident step warps per SM the register allocation is sized for
+#endif
+
 namespace ppg {
 
 // ------------------------------------------------------------------------------------------------
@@ -51,7 +55,7 @@ namespace ppg {
 #define SEL(a) (s == 0 ? a[0] : a[1])
 
 template <int W, typename MapT, bool BULK, bool SPLIT>
-__global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
+__global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel(const __grid_constant__ StepParams p) {  // PHASE: kernel prologue
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,6 +86,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
   for (;;) {
     int env = 0;  // PHASE: ticket+hdr
     if (W == 1) {
+      // (drawing the NEXT env's ticket ahead of time would hide the atomic's round trip, but with < 2 waves of envs it
+      // turns the dynamic schedule into a static two-envs-per-warp one and lengthens the tail)
       if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
       env = __shfl_sync(FULL, env, 0);
       if (env >= p.B) break;
@@ -235,12 +241,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
+      // base_environment_seasonal: square-wave multiplier on the regrowth, phase from the step counter (SEASON:224-234)
+      const double grass_gain = p.season_len > 0 ? p.grass_gain_season[(h.step / p.season_len) & 1] : p.grass_gain;
       #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
         const size_t b = (size_t)env * p.n_grass;
         const unsigned gp = p.gr_pos[b + g];
         S.gpos[g] = (uint16_t)gp;
-        const double v = p.gr_e[b + g] + p.grass_gain;  // regrowth (BASE:252-256)
+        const double v = p.gr_e[b + g] + grass_gain;  // regrowth (BASE:252-256)
         S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
         S.map[2][CELLP(gp)] = (MapT)(g + 1);
       }
@@ -730,7 +738,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_base_kernel(const __g
         }
         if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
-        if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
+        if (add) atomicAdd(p.counters + (size_t)env * PPG_N_STATS + lane, add);  // RED: nobody waits for the old value
       }
     } else {
       if (lane < 2) {

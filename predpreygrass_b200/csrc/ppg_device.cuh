@@ -87,6 +87,8 @@ struct StepParams {
   int R[2], off[2], elems[2];
   int cap[2], n_init[2], n_possible[2], n_grass, max_steps, reward_mode, autoreset;
   double loss[2], thr[2], init_e[2], grass_cap, grass_gain, init_e_grass;
+  double grass_gain_season[2];  // BASE family, seasonal regrowth: grass_gain * season multiplier (high, low); season_len = 0: none
+  int season_len;
   double r_catch, r_eat, r_pstep, r_qstep, pen_caught, r_repro[2], r_kick[2];
   // ---- state ----
   EnvHdr* hdr;

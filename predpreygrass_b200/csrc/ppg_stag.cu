@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         }
         if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
-        if (add) p.counters[(size_t)env * PPG_N_STATS + lane] += add;
+        if (add) atomicAdd(p.counters + (size_t)env * PPG_N_STATS + lane, add);  // RED: nobody waits for the old value
       }
     } else {
       if (lane < 2) {

@@ -340,6 +340,27 @@ class PredPreyGrassSparseRewardsPlusKickback(PredPreyGrass):
     reward_variant = "kickback"
 
 
+class PredPreyGrassSeasonal(PredPreyGrass):
+    """non_evolutionary/base_environment_seasonal: BASE with a square-wave multiplier on the grass regrowth
+    (`season_length_steps`, `season_high_multiplier`, `season_low_multiplier`; SEASON:63-67,224-234,268-271 with
+    SEASON = predpreygrass/non_evolutionary/base_environment_seasonal/predpreygrass_rllib_env.py)."""
+    reward_variant = "seasonal"
+
+    def __init__(self, config=None):
+        from .config import SEASONAL_CONFIG
+
+        config = dict(config or SEASONAL_CONFIG)
+        config.setdefault("season_length_steps", 40)  # the variant's own defaults (SEASON:64-66)
+        super().__init__(config)
+        self.season_length_steps = config["season_length_steps"]
+        self.season_high_multiplier = config.get("season_high_multiplier", 1.5)
+        self.season_low_multiplier = config.get("season_low_multiplier", 0.5)
+
+    def _current_season_multiplier(self):
+        phase = (self.current_step // self.season_length_steps) % 2
+        return self.season_high_multiplier if phase == 0 else self.season_low_multiplier
+
+
 def _default_config():
     from .config import BASE_CONFIG
 

@@ -37,6 +37,7 @@ MODULES = {
     "additive": RS + "base_environment_dense_rewards_additive",
     "kickback": RS + "base_environment_sparse_rewards_plus_kickback",
     "eating": RS + "base_environment_sparse_rewards_plus_eating",
+    "seasonal": NE + "base_environment_seasonal",
 }
 
 # small, crowded world: frequent births, blocked moves, co-located agents, spawn fallback draws
@@ -62,6 +63,12 @@ CASES = [
     ("additive_crowded_s2", "additive", CROWDED, 2, "dict", 200),
     ("kickback_crowded_s1", "kickback", CROWDED, 1, "dict", 200),
     ("kickback_default_s6", "kickback", {}, 6, "dict", 300),
+    # base_environment_seasonal: square-wave multiplier on the grass regrowth (season_length_steps, high / low multiplier)
+    ("seasonal_default_s1", "seasonal", {}, 1, "dict", 300),
+    ("seasonal_crowded_s2_shuffle", "seasonal", dict(CROWDED, season_length_steps=7, season_high_multiplier=2.0, season_low_multiplier=0.25),
+     2, "shuffle", 200),
+    ("seasonal_trunc_s3", "seasonal", {"max_steps": 25, "season_length_steps": 10}, 3, "dict", 60),
+    ("seasonal_default_s5", "seasonal", {"season_length_steps": 25, "season_high_multiplier": 2.5, "season_low_multiplier": 0.0}, 5, "dict", 400),
 ]
 
 

@@ -11,7 +11,7 @@ from predpreygrass_b200.config import REWARD_MODES, make_config
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases(prefixes=("base", "eating", "dense", "additive", "kickback")):
+def golden_cases(prefixes=("base", "eating", "dense", "additive", "kickback", "seasonal")):
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(p)[:-4]

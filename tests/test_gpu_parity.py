@@ -217,7 +217,8 @@ def test_full_size_properties_16384_envs():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("name", ["base_default_s1", "base_default_s7_shuffle", "base_trunc_s2", "additive_default_s1", "kickback_default_s6"])
+@pytest.mark.parametrize("name", ["base_default_s1", "base_default_s7_shuffle", "base_trunc_s2", "additive_default_s1", "kickback_default_s6",
+                                  "seasonal_default_s1", "seasonal_trunc_s3", "seasonal_default_s5"])
 def test_dict_adapter_replays_reference_episode(name):
     """`PredPreyGrass` (the MultiAgentEnv-shaped adapter) against an episode recorded from the reference
     through the same dict API: reset(seed) placement, observation-dict key order, rewards,
