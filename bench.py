@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "agent_steps_per_s_incl_obs"
 UNIT = "agent-steps/s"
+_REAL_STDOUT = 1
 S_AGENT = 42  # bytes of per-agent state + io per agent-step: pos 2 + energy 8 + id 4 (read+write = 28), action 4, reward 4 + flags 2 + id 4
 
 
@@ -175,11 +176,21 @@ def main_reference(args, rank):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "env_steps_per_s": env_rate, "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
+    # libraries print to stdout behind Python's back (NCCL: "NCCL version ..."): everything but the JSON line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -344,7 +355,7 @@ def main():
             "clocks": clocks,
             "status_envs": final["status_envs"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()
