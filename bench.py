@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--reward-mode", default="sparse")
     ap.add_argument("--cap", type=int, nargs=2, default=None)
     ap.add_argument("--e2e-steps", type=int, default=30)
-    ap.add_argument("--cpu-envs", type=int, default=512)
-    ap.add_argument("--cpu-steps", type=int, default=150)
+    ap.add_argument("--cpu-envs", type=int, default=2048, help="envs of the CPU sample (cpu_baseline and the reference arm)")
+    ap.add_argument("--cpu-steps", type=int, default=400, help="steps of the cpu_baseline sample (~10-20 s of host work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
