@@ -57,57 +57,80 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsig
 
 #define OBS_MAX_DEFER 256
 
-// rows of one env from its image in shared memory.  k_lo/k_hi select old rows, newborn rows or both.
-template <typename MapT, int KIND, int OBS_WARPS>
-__device__ __forceinline__ void obs_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
-                                         const int n[2], const int births[2], const int new_base[2], bool do_old, bool do_new, int warp,
-                                         int lane, unsigned& rowctr) {
-  // warp w takes every OBS_WARPS-th row of the env (round robin across both species)
-  int rot = 0;
-#pragma unroll 1
-  for (int s = 0; s < 2; ++s) {
-    const int lo = do_old ? 0 : n[s], hi = do_new ? n[s] + births[s] : n[s];
-    const int T = hi - lo;
-    const int k0 = lo + (warp + 4 * OBS_WARPS - rot) % OBS_WARPS;
-    rot = (rot + (T > 0 ? T : 0)) % OBS_WARPS;
-    if (k0 >= hi) continue;
-    const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
-    const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
-    const RowRel rr = load_rel(p, s, vb32, lane);
-    const int elems = p.elems[s];
-    float* obs_s = p.obs[s];
-    for (int k = k0; k < hi; k += OBS_WARPS) {
-      const unsigned d = dsc[k];
-      if (d == DSC_SKIP) continue;
-      const int row = k < n[s] ? old_base[s] + k : new_base[s] + (k - n[s]);
-      float* dst = obs_s + (size_t)row * elems;
-      if (KIND == 1) {
-        if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
-          const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
-          for (int q = lane; q < elems; q += 32) __stcs(dst + q, __ldcg(src + q));  // L2: written by another SM during this launch
-          continue;
-        }
-        emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
-      } else if (KIND == 2) {
-        if (d == DSC_ZERO) { zero_row(dst, elems, lane); continue; }
-        const unsigned x = dsx[k];
-        const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
-        if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-        else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
-      } else {
-        emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-      }
+// one observation row of an env from its image in shared memory: descriptor k of species s -> global row `row`
+template <typename MapT, int KIND>
+__device__ __forceinline__ void obs_one_row(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, int s, int k, int row,
+                                            const RowRel& rr, int lane, unsigned& rowctr) {
+  const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
+  const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
+  const unsigned d = dsc[k];
+  if (d == DSC_SKIP) return;  // captured by the step kernel when the agent died
+  const int elems = p.elems[s];
+  float* dst = p.obs[s] + (size_t)row * elems;
+  if (KIND == 1) {
+    if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
+      const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
+      for (int q = lane; q < elems; q += 32) __stcs(dst + q, __ldcg(src + q));  // L2: written by another SM during this launch
+      return;
     }
+    emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
+  } else if (KIND == 2) {
+    if (d == DSC_ZERO) { zero_row(dst, elems, lane); return; }
+    const unsigned x = dsx[k];
+    const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
+    if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+    else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
+  } else {
+    emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
   }
 }
 
-// labels of the newborn rows, the rows their first actions are read from, new_off
-template <int OBS_THREADS>
-__device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env, const int births[2], const int new_base[2], int tid) {
+// Rows of the agents that acted: the warps of the CTA take them one at a time from a shared counter, so a warp that is
+// busy with something else (warp 0: the next env's fetch, the newborn rows) simply takes fewer.  Rows come out in
+// order (species 0 first), so a warp reloads its per-lane gather constants at most once per env.
+template <typename MapT, int KIND>
+__device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
+                                             const int n[2], int* counter, int lane, unsigned& rowctr) {
+  const int total = n[0] + n[1];
+  auto grab = [&]() -> int {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(counter, 1);
+    return __shfl_sync(FULL, k, 0);
+  };
+  int k = grab();
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const int end = s == 0 ? n[0] : total;
+    if (k >= end) continue;
+    const RowRel rr = load_rel(p, s, vb32, lane);
+    const int first = s == 0 ? 0 : n[0], base = s == 0 ? old_base[0] : old_base[1];
+    do {
+      obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, k - first, base + (k - first), rr, lane, rowctr);
+      k = grab();
+    } while (k < end);
+  }
+}
+
+// newborn rows of an env (one warp): descriptors n[s] .. n[s] + births[s] -> rows new_base[s] ..
+template <typename MapT, int KIND>
+__device__ __forceinline__ void obs_new_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int n[2],
+                                             const int births[2], const int new_base[2], int lane, unsigned& rowctr) {
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const int nb = s == 0 ? births[0] : births[1];
+    if (nb <= 0) continue;
+    const int n_s = s == 0 ? n[0] : n[1], base = s == 0 ? new_base[0] : new_base[1];
+    const RowRel rr = load_rel(p, s, vb32, lane);
+    for (int j = 0; j < nb; ++j) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, n_s + j, base + j, rr, lane, rowctr);
+  }
+}
+
+// labels of the newborn rows, the rows their first actions are read from, new_off (one warp)
+__device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env, const int births[2], const int new_base[2], int lane) {
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const size_t sb = (size_t)env * p.cap[s];
-    for (int j = tid; j < births[s]; j += OBS_THREADS) {
+    for (int j = lane; j < births[s]; j += 32) {
       const unsigned long long info = __ldcg(p.nb_info[s] + sb + j);  // L2: written by another SM during this launch
       const int row = new_base[s] + j;
       p.row_env[s][row] = env;
@@ -118,7 +141,7 @@ __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env,
       if (dst != 0xFFFFu) p.ag_prow[s][sb + dst] = row;  // the newborn's first action is read from this row
     }
   }
-  if (tid < 2) p.new_off[tid][env] = births[tid] > 0 ? new_base[tid] : 0;
+  if (lane < 2) p.new_off[lane][env] = births[lane] > 0 ? new_base[lane] : 0;
 }
 
 // KIND: 0 = BASE family, 1 = ECO (own-speed plane), 2 = STAG (cut-off forward view, all-zero rows of ended agents)
@@ -128,17 +151,21 @@ __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env,
 // serialization and fills whatever the step kernel's persistent warps leave free on an SM, above all the step
 // kernel's long tail.  Correctness never depends on the overlap — launched after the step kernel has ended, every
 // queue entry is simply there already.
-// Newborn rows need the births of all envs before this one; if those are not all published yet when the env comes
-// by, its newborn rows are deferred to the end of this CTA's work (the image is fetched again).
+//
+// Inside a CTA: two image buffers; thread 0 is the producer (ticket, queue entry, fences, bulk copy of the NEXT env's
+// image — ~2 us of latency per env), warp 0 also owns the newborn rows (they need the births of all envs before this
+// one: a prefix over L2-resident counters; if those are not all published yet the env's newborn rows are deferred to
+// the end of this CTA's work and the image is fetched again).  The rows of the agents that acted — the bulk — are
+// handed out one at a time from a shared counter, so the other warps absorb whatever warp 0 is busy with and all
+// warps reach the one CTA barrier per env together (with a static split 24 % of the warp time was spent waiting at
+// that barrier for warp 0, profiles/r01_final_summary.md).
 template <typename MapT, int KIND, int OBS_WARPS>
 __global__ void __launch_bounds__(OBS_WARPS * 32, 32 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ int s_env[2];
-  __shared__ int s_nb[3];
-  __shared__ int s_ndefer;
+  __shared__ int s_row[2];  // next row of the env in buffer 0 / 1
   __shared__ int s_defer[OBS_MAX_DEFER];
-  constexpr int OBS_THREADS = OBS_WARPS * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned stride = (unsigned)p.img_stride, img_bytes = (unsigned)p.img_bytes;
   const unsigned img0 = smem_u32(smem_img), bar0 = smem_u32(&s_bar[0]);
@@ -172,13 +199,14 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 32 / OBS_WARPS) ppg_obs_kernel
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
-    s_ndefer = 0;
+    s_row[0] = 0; s_row[1] = 0;
     s_env[0] = fetch(0, true);
   }
   __syncthreads();
   int env = s_env[0];
   unsigned stage = 0, phase = 0;  // bit s of phase: parity the barrier of buffer s completes next
   unsigned rowctr = 0;
+  int n_defer = 0;  // warp 0
 
   while (env < p.B) {
     // next env: its image streams into the other buffer (all reads of that buffer ended before the last barrier)
@@ -193,83 +221,68 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 32 / OBS_WARPS) ppg_obs_kernel
     const int old_base[2] = {ih[IH_OLD_BASE0], ih[IH_OLD_BASE1]};
     const int n[2] = {ih[IH_N0], ih[IH_N1]};
     const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
-    int new_base[2] = {0, 0};
-    bool do_new = false;
 
-    if (births[0] + births[1] > 0) {
-      // first newborn row of this env = old rows of all envs + births of the envs before it
-      if (warp == 0) {
+    if (warp == 0) {
+      if (births[0] + births[1] > 0) {
+        // first newborn row of this env = old rows of all envs + births of the envs before it
         int nb0 = 0, nb1 = 0;
-        const bool ready = prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, false, lane, nb0, nb1);
-        if (lane == 0) {
-          int ok = ready ? 1 : 0;
-          if (!ready) {
-            if (s_ndefer < OBS_MAX_DEFER) s_defer[s_ndefer++] = env;
-            else ok = 2;  // list full: wait here, below (the step kernel never waits for this kernel, so the wait ends)
+        bool ready = prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, false, lane, nb0, nb1);
+        if (!ready) {
+          if (n_defer < OBS_MAX_DEFER) {
+            if (lane == 0) s_defer[n_defer] = env;
+            ++n_defer;
+          } else {
+            // list full: wait here (the step kernel never waits for this kernel, so the wait ends)
+            ready = prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1);
+            if (!ready && lane == 0) atomicOr(p.error, 1u);
           }
-          s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; s_nb[2] = ok;
         }
-      }
-      __syncthreads();
-      if (s_nb[2] == 2) {
-        __syncthreads();
-        if (warp == 0) {
-          int nb0 = 0, nb1 = 0;
-          if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
-            if (lane == 0) atomicOr(p.error, 1u);
-          }
-          if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; s_nb[2] = 1; }
+        if (ready) {
+          const int new_base[2] = {n_old_total[0] + nb0, n_old_total[1] + nb1};
+          obs_newborn_labels(p, env, births, new_base, lane);
+          obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, lane, rowctr);
         }
-        __syncthreads();
+      } else if (lane < 2) {
+        p.new_off[lane][env] = 0;
       }
-      do_new = s_nb[2] != 0;
-      if (do_new) {
-        new_base[0] = s_nb[0]; new_base[1] = s_nb[1];
-        obs_newborn_labels<OBS_THREADS>(p, env, births, new_base, tid);
-      }
-    } else if (tid < 2) {
-      p.new_off[tid][env] = 0;
     }
 
-    obs_rows<MapT, KIND, OBS_WARPS>(p, ibp, vb32, env, old_base, n, births, new_base, true, do_new, warp, lane, rowctr);
+    obs_old_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, &s_row[stage], lane, rowctr);
 
     if (tid == 0) {
       if (nxt < 0) nxt = fetch(stage ^ 1u, true);
       s_env[stage ^ 1u] = nxt;
+      s_row[stage ^ 1u] = 0;  // nobody is using the other buffer's counter between the barriers
     }
     __syncthreads();  // every read of this buffer is done; the next env is known
     env = s_env[stage ^ 1u];
     stage ^= 1u;
   }
 
-  // deferred newborn rows: by now (the completion queue is exhausted) every env has published its births or is about to
-  const int n_defer = s_ndefer;
+  // deferred newborn rows (warp 0): by now (the completion queue is exhausted) every env has published its births or is
+  // about to.  No other warp touches the buffers any more.
+  if (warp != 0) return;
   for (int i = 0; i < n_defer; ++i) {
+    __syncwarp();  // s_defer was written by lane 0; the previous image's reads are done
     env = s_defer[i];
-    if (tid == 0) {
+    if (lane == 0) {
       mbar_expect_tx(bar0 + 8u * stage, img_bytes);
       bulk_load(img0 + stage * stride, p.obs_img + (size_t)env * stride, img_bytes, bar0 + 8u * stage);
     }
-    if (warp == 0) {
-      int nb0 = 0, nb1 = 0;
-      if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
-        if (lane == 0) atomicOr(p.error, 1u);
-      }
-      if (lane == 0) { s_nb[0] = n_old_total[0] + nb0; s_nb[1] = n_old_total[1] + nb1; }
+    int nb0 = 0, nb1 = 0;
+    if (!prefix_before(p.cntB[par], p.sum1[par], p.sum2[par], 2, env, epoch, true, lane, nb0, nb1)) {
+      if (lane == 0) atomicOr(p.error, 1u);
     }
     mbar_wait(bar0 + 8u * stage, (phase >> stage) & 1u);
     phase ^= 1u << stage;
-    __syncthreads();
     const unsigned char* ibp = smem_img + (size_t)stage * stride;
     const unsigned vb32 = img0 + stage * stride - (unsigned)p.so_img;
     const int* ih = reinterpret_cast<const int*>(ibp + (p.so_ihdr - p.so_img));
-    const int old_base[2] = {ih[IH_OLD_BASE0], ih[IH_OLD_BASE1]};
     const int n[2] = {ih[IH_N0], ih[IH_N1]};
     const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
-    const int new_base[2] = {s_nb[0], s_nb[1]};
-    obs_newborn_labels<OBS_THREADS>(p, env, births, new_base, tid);
-    obs_rows<MapT, KIND, OBS_WARPS>(p, ibp, vb32, env, old_base, n, births, new_base, false, true, warp, lane, rowctr);
-    __syncthreads();
+    const int new_base[2] = {n_old_total[0] + nb0, n_old_total[1] + nb1};
+    obs_newborn_labels(p, env, births, new_base, lane);
+    obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, lane, rowctr);
     stage ^= 1u;
   }
 }
