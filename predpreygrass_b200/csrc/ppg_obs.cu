@@ -105,8 +105,10 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
     const RowRel rr = load_rel(p, s, vb32, lane);
     const int first = s == 0 ? 0 : n[0], base = s == 0 ? old_base[0] : old_base[1];
     do {
+      int kn = 0;
+      if (lane == 0) kn = atomicAdd(counter, 1);  // the next row's index arrives while this row is being written
       obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, k - first, base + (k - first), rr, lane, rowctr);
-      k = grab();
+      k = __shfl_sync(FULL, kn, 0);
     } while (k < end);
   }
 }
