@@ -1,16 +1,19 @@
 """predpreygrass_b200 — B200-native batched PredPreyGrass environment step."""
-from .config import BASE_CONFIG, make_config  # noqa: F401
+from .config import BASE_CONFIG, ECO_CONFIG, SEASONAL_CONFIG, STAG_CONFIG, make_config  # noqa: F401
 
-__all__ = ["BASE_CONFIG", "make_config", "BatchedPredPreyGrass", "PredPreyGrass"]
+_LAZY = {
+    "BatchedPredPreyGrass": "batched",
+    "PredPreyGrass": "env", "PredPreyGrassDenseRewards": "env", "PredPreyGrassDenseRewardsAdditive": "env",
+    "PredPreyGrassSparseRewards": "env", "PredPreyGrassSparseRewardsPlusEating": "env",
+    "PredPreyGrassSparseRewardsPlusKickback": "env", "PredPreyGrassSeasonal": "env",
+    "PredPreyGrassEco": "env_evolutionary", "PredPreyGrassStag": "env_evolutionary",
+}
+__all__ = ["BASE_CONFIG", "ECO_CONFIG", "SEASONAL_CONFIG", "STAG_CONFIG", "make_config"] + sorted(_LAZY)
 
 
-def __getattr__(name):
-    if name == "BatchedPredPreyGrass":
-        from .batched import BatchedPredPreyGrass
+def __getattr__(name):  # torch / the CUDA library are loaded only when a class that needs them is asked for
+    if name in _LAZY:
+        import importlib
 
-        return BatchedPredPreyGrass
-    if name == "PredPreyGrass":
-        from .env import PredPreyGrass
-
-        return PredPreyGrass
+        return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
     raise AttributeError(name)

@@ -340,6 +340,18 @@ class PredPreyGrassSparseRewardsPlusKickback(PredPreyGrass):
     reward_variant = "kickback"
 
 
+class PredPreyGrassSparseRewards(PredPreyGrass):
+    """project_reward_shaping/base_environment_sparse_rewards: the same class as BASE (the reference copy differs in its
+    docstring and config import only)"""
+    reward_variant = "sparse"
+
+
+class PredPreyGrassSparseRewardsPlusEating(PredPreyGrass):
+    """project_reward_shaping/base_environment_sparse_rewards_plus_eating: BASE's code with the eating rewards of its own
+    config_env.py (`reward_predator_catch_prey`, `reward_prey_eat_grass`: BASE:322,365 pay them when non-zero)"""
+    reward_variant = "eating"
+
+
 class PredPreyGrassSeasonal(PredPreyGrass):
     """non_evolutionary/base_environment_seasonal: BASE with a square-wave multiplier on the grass regrowth
     (`season_length_steps`, `season_high_multiplier`, `season_low_multiplier`; SEASON:63-67,224-234,268-271 with
