@@ -41,6 +41,7 @@ def parse():
                     help="base: BASELINE configs[1]/[2] (base_environment family); eco: configs[3] (eco_evolutionary, speed trait); "
                          "stag: configs[4] (stag_hunt_forward_view_nature_nurture, team capture)")
     ap.add_argument("--eco-rich", action="store_true", help="eco: reproduction-heavy override (thresholds 8/5, grass regrowth 0.3)")
+    ap.add_argument("--seasonal", action="store_true", help="base: base_environment_seasonal config (square-wave grass regrowth)")
     ap.add_argument("--reward-mode", default="sparse")
     ap.add_argument("--cap", type=int, nargs=2, default=None)
     ap.add_argument("--e2e-steps", type=int, default=30)
@@ -64,7 +65,8 @@ def workload_name(args):
     if args.variant == "eco":
         return (f"eco_evolutionary default config_env{' + reproduction-heavy override' if args.eco_rich else ''}, {args.envs} envs per GPU, "
                 "uniform random actions (25), auto-reset, Philox trait/mutation draws")
-    return f"base_environment default config_env, {args.envs} envs per GPU, uniform random actions, auto-reset, reward={args.reward_mode}"
+    name = "base_environment_seasonal" if getattr(args, "seasonal", False) else "base_environment"
+    return f"{name} default config_env, {args.envs} envs per GPU, uniform random actions, auto-reset, reward={args.reward_mode}"
 
 
 def build_config(args, **kw):
@@ -78,6 +80,10 @@ def build_config(args, **kw):
             d.update(energy_gain_per_step_grass=0.3, prey_creation_energy_threshold=5.0, predator_creation_energy_threshold=8.0,
                      energy_loss_per_step_predator=0.1, n_possible_predators=8000, n_possible_prey=24000)
         return make_config(d, variant=VARIANT_ECO, cap_live=tuple(args.cap), **kw)
+    if getattr(args, "seasonal", False):
+        from predpreygrass_b200.config import SEASONAL_CONFIG
+
+        return make_config(SEASONAL_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), **kw)
     return make_config(BASE_CONFIG, reward_mode=args.reward_mode, cap_live=tuple(args.cap), **kw)
 
 
