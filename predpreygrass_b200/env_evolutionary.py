@@ -360,16 +360,19 @@ class PredPreyGrassEco(_RowDictEnv):
         return {self._name(1, int(i)) for i, d in zip(st["ids"][1], st["dead_prey"]) if d}
 
     def live_speed_metrics(self):
-        """speed distribution of the live population per role (ECO `_build_live_speed_metrics`, ECO:509-539)"""
+        """`_build_live_speed_metrics` (ECO:509-539): speed distribution of the live population, same keys"""
         st = self._read()
         res = {}
         for s, role in enumerate(("predator", "prey")):
-            v = np.asarray(st["speed"][s], np.float64)
-            res[f"{role}_count"] = int(v.size)
+            v = np.asarray(st["speed"][s], np.float64) if self.genome_enabled else np.zeros(0)
             if v.size:
-                res[f"{role}_speed_mean"] = float(v.mean())
-                res[f"{role}_speed_std"] = float(v.std())
-                res[f"{role}_fraction_fast"] = float((v >= self.speed_distance_threshold).mean())
+                p25, p50, p75 = np.percentile(v, [25, 50, 75])
+                vals = (float(v.mean()), float(v.std()), float(p25), float(p50), float(p75),
+                        float((v >= float(self.speed_distance_threshold)).mean()), float(v.size))
+            else:
+                vals = (0.0,) * 7
+            for key, x in zip(("speed_mean", "speed_std", "speed_p25", "speed_p50", "speed_p75", "fraction_fast", "count"), vals):
+                res[f"{role}_{key}"] = x
         return res
 
 

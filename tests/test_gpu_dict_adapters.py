@@ -128,3 +128,28 @@ def test_stag_dict_adapter_replays_reference_episode(name):
             if s == 0:
                 assert face[key(s, i)] == FACING_OPTIONS[int(f)] and trait[key(s, i)] == float(v), (name, t)
     env.close()
+
+
+def test_eco_adapter_time_limit_reports_training_metrics():
+    """reference test_time_limit_truncates_with_final_bootstrap_observations (eco tests :296-329) through the dict API:
+    max_steps = 1 -> everybody truncated, `agents` cleared, `infos["__all__"]["training_metrics"]` carries the speed
+    distribution keys of `_build_live_speed_metrics` (ECO:509-539)"""
+    from predpreygrass_b200.config import ECO_CONFIG
+    from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
+
+    cfg = dict(ECO_CONFIG, max_steps=1, n_initial_active_predators=1, n_initial_active_prey=1, n_possible_predators=8, n_possible_prey=8,
+               initial_num_grass=4, predator_creation_energy_threshold=999.0, prey_creation_energy_threshold=999.0, cap_live=(32, 32))
+    env = PredPreyGrassEco(cfg)
+    obs, _ = env.reset(seed=125)
+    assert set(obs) == {"predator_0", "prey_0"} and env.action_spaces["predator_0"].n == 25
+    stay = next(a for a, mv in env.action_to_move_tuple_agents.items() if mv == (0, 0))
+    obs, rew, term, trunc, infos = env.step({a: stay for a in env.agents})
+    assert set(obs) == {"predator_0", "prey_0"}
+    assert obs["predator_0"].shape == (4, 7, 7) and obs["prey_0"].shape == (4, 9, 9)
+    assert all(trunc[a] and not term[a] for a in obs) and trunc["__all__"] and not term["__all__"]
+    assert env.agents == []
+    m = infos["__all__"]["training_metrics"]
+    for k in ("predator_speed_mean", "prey_speed_mean", "predator_fraction_fast", "prey_speed_p50", "predator_count"):
+        assert k in m
+    assert m["predator_count"] == 1.0 and 0.5 <= m["predator_speed_mean"] <= 2.0
+    env.close()
