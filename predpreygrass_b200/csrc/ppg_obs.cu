@@ -162,7 +162,9 @@ __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env,
 // warps reach the one CTA barrier per env together (with a static split 24 % of the warp time was spent waiting at
 // that barrier for warp 0, profiles/r01_final_summary.md).
 template <typename MapT, int KIND, int OBS_WARPS>
-__global__ void __launch_bounds__(OBS_WARPS * 32, 32 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
+// Register budget: sized for 28 warps per SM (72 registers, no spills) — at 32 (64 registers) the kernel spilled ~100 B
+// per thread and was 3–5 % slower on every config; 24 is as good, 20 and 16 lose (profiles/r01_final_summary.md)
+__global__ void __launch_bounds__(OBS_WARPS * 32, 28 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ int s_env[2];
