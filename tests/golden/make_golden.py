@@ -63,6 +63,15 @@ CASES = [
     ("additive_crowded_s2", "additive", CROWDED, 2, "dict", 200),
     ("kickback_crowded_s1", "kickback", CROWDED, 1, "dict", 200),
     ("kickback_default_s6", "kickback", {}, 6, "dict", 300),
+    # every reward constant non-zero (BASE:288,322,328,341,365,375): step rewards, catch / eat rewards, caught penalty
+    ("base_rewards_s8", "sparse", dict(CROWDED, reward_predator_step=0.125, reward_prey_step=0.25, reward_predator_catch_prey=3.0,
+                                       reward_prey_eat_grass=1.5, penalty_prey_caught=-2.0, reproduction_reward_predator=7.0,
+                                       reproduction_reward_prey=4.0, grid_size=8, initial_num_grass=24), 8, "dict", 200),
+    # other window shapes than the default 7 / 9 (generic row writer on the device), odd grid size
+    ("base_wide_s9", "sparse", dict(grid_size=15, predator_obs_range=9, prey_obs_range=9, initial_num_grass=40,
+                                    n_possible_predators=200, n_possible_prey=300), 9, "shuffle", 200),
+    ("base_narrow_s10", "sparse", dict(grid_size=11, predator_obs_range=3, prey_obs_range=5, initial_num_grass=30,
+                                       n_possible_predators=200, n_possible_prey=300, energy_gain_per_step_grass=0.2), 10, "dict", 200),
     # base_environment_seasonal: square-wave multiplier on the grass regrowth (season_length_steps, high / low multiplier)
     ("seasonal_default_s1", "seasonal", {}, 1, "dict", 300),
     ("seasonal_crowded_s2_shuffle", "seasonal", dict(CROWDED, season_length_steps=7, season_high_multiplier=2.0, season_low_multiplier=0.25),

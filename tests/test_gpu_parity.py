@@ -99,7 +99,7 @@ def test_golden_trajectories_on_gpu(name):
                     o[r] = rank[(s, int(out[f"row_agent{s}"][r]))]
             g.actions[s][: len(a)].copy_(torch.from_numpy(a))
             orders.append(torch.from_numpy(o).cuda())
-        if "shuffle" in name:
+        if str(z["order"]) == "shuffle":
             g.step_ordered(g.actions[0], g.actions[1], orders[0], orders[1])
         else:
             g.step()
