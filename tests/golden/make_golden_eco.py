@@ -62,6 +62,13 @@ CASES = [
     ("eco_nogenome_s1", dict(RICH, genome_enabled=False, include_speed_in_obs=False), 1, "id", 120),
     ("eco_founders_fixed_s7", dict(RICH, founder_genome={"predator": {"speed_mean": 1.6, "speed_std": 0.0},
                                                          "prey": {"speed_mean": 1.2, "speed_std": 0.5}}), 7, "id", 250),
+    # other window shapes (generic row writer on the device), odd grid, 3x3 and 7x7 action tables, other speed bounds /
+    # threshold / jump distances (ECO:551-557,664-683)
+    ("eco_narrow_s8", dict(RICH, grid_size=13, predator_obs_range=3, prey_obs_range=5, action_range=3, initial_num_grass=40), 8, "shuffle", 160),
+    ("eco_jumps_s9", dict(RICH, grid_size=17, predator_obs_range=9, prey_obs_range=7, action_range=7, initial_num_grass=60,
+                          trait_bounds={"speed": (0.25, 3.0)}, speed_distance_threshold=1.2, slow_max_move_distance=2,
+                          fast_max_move_distance=3, founder_genome={"predator": {"speed_mean": 1.3, "speed_std": 0.6},
+                                                                    "prey": {"speed_mean": 1.1, "speed_std": 0.5}}), 9, "id", 160),
 ]
 
 

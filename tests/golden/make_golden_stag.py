@@ -68,6 +68,8 @@ CASES = [
     ("stag_penalty_s9", dict(CROWDED, death_penalty_predator=-2.0, death_penalty_type_1_prey=-3.0, death_penalty_type_2_prey=-1.5,
                              strict_rllib_output=False), 9, "list", 200),
     ("stag_trunc_s2", dict(RICH, max_steps=30), 2, "list", 60),
+    # other window shapes and an odd grid: predators 5x5 (forward shift 2), prey 9x9
+    ("stag_windows_s10", dict(CROWDED, grid_size=11, predator_obs_range=5, prey_obs_range=9, initial_num_grass=30), 10, "shuffle", 200),
     ("stag_tiny_s3", dict(CROWDED, grid_size=5, initial_num_grass=8, n_initial_active_type_1_predator=5, n_initial_active_type_1_prey=3,
                           n_initial_active_type_2_prey=8, predator_obs_range=9, prey_obs_range=7), 3, "shuffle", 150),
 ]
