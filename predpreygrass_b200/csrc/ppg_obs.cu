@@ -91,25 +91,50 @@ __device__ __forceinline__ void obs_one_row(const StepParams& p, const unsigned 
 template <typename MapT, int KIND>
 __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
                                              const int n[2], int* counter, int lane, unsigned& rowctr) {
-  const int total = n[0] + n[1];
+  // Rows are handed out in PAIRS of the same species (rows 2 q, 2 q + 1 of the species): two plain rows go through the
+  // two-row writer, anything else (the odd last row, skipped / zero / copied / cut-off rows) row by row.
+  const int P0 = (n[0] + 1) >> 1, totalP = P0 + ((n[1] + 1) >> 1);
   auto grab = [&]() -> int {
-    int k = 0;
-    if (lane == 0) k = atomicAdd(counter, 1);
-    return __shfl_sync(FULL, k, 0);
+    int q = 0;
+    if (lane == 0) q = atomicAdd(counter, 1);
+    return __shfl_sync(FULL, q, 0);
   };
-  int k = grab();
+  int q = grab();
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
-    const int end = s == 0 ? n[0] : total;
-    if (k >= end) continue;
+    const int endq = s == 0 ? P0 : totalP;
+    if (q >= endq) continue;
     const RowRel rr = load_rel(p, s, vb32, lane);
-    const int first = s == 0 ? 0 : n[0], base = s == 0 ? old_base[0] : old_base[1];
+    const int firstq = s == 0 ? 0 : P0, n_s = s == 0 ? n[0] : n[1], base = s == 0 ? old_base[0] : old_base[1];
+    const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
+    const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
     do {
-      int kn = 0;
-      if (lane == 0) kn = atomicAdd(counter, 1);  // the next row's index arrives while this row is being written
-      obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, k - first, base + (k - first), rr, lane, rowctr);
-      k = __shfl_sync(FULL, kn, 0);
-    } while (k < end);
+      int qn = 0;
+      if (lane == 0) qn = atomicAdd(counter, 1);  // the next pair's index arrives while this one is being written
+      const int ka = 2 * (q - firstq), kb = ka + 1;
+      bool done = false;
+      if (kb < n_s) {
+        const unsigned d0 = dsc[ka], d1 = dsc[kb];
+        bool plain = d0 < DSC_COPY && d1 < DSC_COPY;  // DSC_COPY is the smallest special descriptor
+        float sv0 = 0.f, sv1 = 0.f;
+        if (KIND == 1) { sv0 = __uint_as_float(dsx[ka]); sv1 = __uint_as_float(dsx[kb]); }
+        if (KIND == 2 && plain) {  // STAG: windows cut off by the saturating forward shift take the masked writer
+          const unsigned x0 = dsx[ka], x1 = dsx[kb];
+          const int full = p.R[s] - 1;
+          plain = (int)(x0 & 0xFFu) >= full && (int)((x0 >> 8) & 0xFFu) >= full && (int)(x1 & 0xFFu) >= full && (int)((x1 >> 8) & 0xFFu) >= full;
+        }
+        if (plain) {
+          const int elems = p.elems[s];
+          float* dst0 = p.obs[s] + (size_t)(base + ka) * elems;
+          done = emit_row2<MapT, KIND == 1>(p, vb32, dst0, dst0 + elems, (int)d0, (int)d1, s, rr, lane, sv0, sv1);
+        }
+      }
+      if (!done) {
+        obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, ka, base + ka, rr, lane, rowctr);
+        if (kb < n_s) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, kb, base + kb, rr, lane, rowctr);
+      }
+      q = __shfl_sync(FULL, qn, 0);
+    } while (q < endq);
   }
 }
 
@@ -164,7 +189,7 @@ __device__ __forceinline__ void obs_newborn_labels(const StepParams& p, int env,
 template <typename MapT, int KIND, int OBS_WARPS>
 // Register budget: sized for 28 warps per SM (72 registers, no spills) — at 32 (64 registers) the kernel spilled ~100 B
 // per thread and was 3–5 % slower on every config; 24 is as good, 20 and 16 lose (profiles/r01_final_summary.md)
-__global__ void __launch_bounds__(OBS_WARPS * 32, 28 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ int s_env[2];

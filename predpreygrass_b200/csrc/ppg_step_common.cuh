@@ -310,6 +310,60 @@ __device__ __noinline__ unsigned emit_row_generic(const StepParams& p, unsigned 
   return rowctr;
 }
 
+// TWO rows of the same species at once (direct stores only): all 2N map loads are issued back to back, then all 2N table
+// loads, then the stores — the same two dependent shared-memory latencies as one row, paid once for two rows
+// (short_scoreboard was the observation kernel's top stall, profiles/r01_final_summary.md)
+template <typename MapT, int N, bool VEC, bool SELF>
+__device__ __forceinline__ void emit_row2_t(const StepParams& p, unsigned sb32, float* dst0, float* dst1, int cellp0, int cellp1, int s,
+                                            const RowRel& r, int lane, float selfv0, float selfv1) {
+  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp0 * (int)sizeof(MapT));
+  const unsigned a1 = sb32 + (unsigned)(p.so_map[0] + cellp1 * (int)sizeof(MapT));
+  unsigned idx0[N], idx1[N];
+  float val0[N], val1[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) idx0[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) idx1[j] = lds_map<MapT>(a1 + (unsigned)r.relb[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) val0[j] = lds_f32(r.tbl[j] + 4u * idx0[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) val1[j] = lds_f32(r.tbl[j] + 4u * idx1[j]);
+  if (SELF) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if ((r.self >> j) & 1u) { val0[j] = selfv0; val1[j] = selfv1; }
+  }
+  const int elems = p.elems[s];
+  if (VEC) {
+    float4* d0 = reinterpret_cast<float4*>(dst0) + lane;
+    float4* d1 = reinterpret_cast<float4*>(dst1) + lane;
+#pragma unroll
+    for (int v = 0; v < N / 4; ++v)
+      if (4 * (lane + 32 * v) < elems) {
+        __stcs(d0 + 32 * v, make_float4(val0[4 * v], val0[4 * v + 1], val0[4 * v + 2], val0[4 * v + 3]));
+        __stcs(d1 + 32 * v, make_float4(val1[4 * v], val1[4 * v + 1], val1[4 * v + 2], val1[4 * v + 3]));
+      }
+  } else {
+    float* d0 = dst0 + lane;
+    float* d1 = dst1 + lane;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (lane + 32 * j < elems) { __stcs(d0 + 32 * j, val0[j]); __stcs(d1 + 32 * j, val1[j]); }
+  }
+}
+
+// true if the species' row shape has a two-row writer (else the caller writes the rows one by one)
+template <typename MapT, bool SELF>
+__device__ __forceinline__ bool emit_row2(const StepParams& p, unsigned sb32, float* dst0, float* dst1, int cellp0, int cellp1, int s,
+                                          const RowRel& r, int lane, float selfv0 = 0.f, float selfv1 = 0.f) {
+  switch (p.emit_kind[s]) {
+    case 1: emit_row2_t<MapT, 8, true, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
+    case 2: emit_row2_t<MapT, 12, true, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
+    case 3: emit_row2_t<MapT, 13, false, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
+    default: return false;
+  }
+}
+
 template <typename MapT, bool BULK, bool SELF = false>
 __device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, float* dst, int cellp, int s, const RowRel& r,
                                          unsigned& rowctr, int lane, float selfv = 0.f) {
