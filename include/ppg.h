@@ -273,10 +273,15 @@ void ppg_default_config(ppg_config* cfg);
 /* Loads a replay tape (host pointers), resets the cursors. NULL tape clears it. */
 int ppg_load_tape(ppg_handle h, const ppg_tape* tape);
 
-/* PredPreyGrass.reset(seed=...) (BASE:129-217) for every env with mask[e] != 0 (mask NULL = all).
- * seeds (host, [n_envs], may be NULL) re-key the env's Philox stream (BASE:135,170).
- * Writes the founders' observation rows (PPG_ROW_FOUNDER) for the reset envs; envs not in the mask
- * produce no rows in this call. */
+/* PredPreyGrass.reset(seed=...) (BASE:129-217).
+ * mask == NULL: resets every env now and writes the founders' observation rows (PPG_ROW_FOUNDER): the output of this
+ * call is the reset output of all envs.
+ * mask != NULL (host, [n_envs]): SCHEDULES the reset of every env with mask[e] != 0 and returns without producing an
+ * output; the next ppg_step performs it — for a masked env that call is reset() instead of step() (PPG_ENV_RESET, its
+ * actions are ignored, its rows are the founders' rows), for the others an ordinary step.  This is the lockstep form of
+ * "reset the envs whose episode the caller wants to end early"; an env whose episode ended does the same by itself when
+ * autoreset is on.
+ * seeds (host, [n_envs], may be NULL) re-key the Philox stream of the envs being reset (BASE:135,170). */
 int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cuda_stream);
 
 /* PredPreyGrass.step(action_dict) (BASE:219-473) for all envs in lockstep.
@@ -306,10 +311,20 @@ int ppg_step_host(ppg_handle h, const int32_t* actions_pred, const int32_t* acti
 int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32_t* actions_prey,
                        void* cuda_stream);
 
+/* Random-policy rollout driver (the reference's `random_policy.py` loop: `env.step({a: env.action_spaces[a].sample()})`,
+ * base_environment/random_policy.py:24-40) for SEVERAL handles at once: n_steps times, for every handle in turn,
+ * ppg_random_actions into the handle's own action staging buffers followed by ppg_step, each handle on its own stream
+ * (cuda_streams[g], NULL array = the default stream for all).  Handles on different streams overlap on the device:
+ * the latency-bound step kernel of one group of envs runs under the bandwidth-bound observation kernel of another
+ * (DESIGN.md §3.6).  No host synchronisation; results are exactly those of the same calls made one by one. */
+int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_streams, int32_t n_steps, uint64_t seed);
+
 int ppg_get_buffers(ppg_handle h, ppg_buffers* out);
 
 /* get_state_snapshot()/restore_state_snapshot() (BASE:768-804): the whole SoA slab incl. RNG
- * counters and tape cursors as an opaque host blob.  ppg_snapshot_size gives the byte count. */
+ * counters and tape cursors as an opaque host blob.  ppg_snapshot_size gives the byte count.  The blob's header
+ * records the byte count and a hash of the shape-defining config fields (n_envs, variant, reward mode, grid, slot
+ * capacities, grass patches); ppg_restore refuses (PPG_ERR_INVALID) a blob taken from a handle of another shape. */
 size_t ppg_snapshot_size(ppg_handle h);
 int ppg_snapshot(ppg_handle h, void* host_blob, size_t bytes, void* cuda_stream);
 int ppg_restore(ppg_handle h, const void* host_blob, size_t bytes, void* cuda_stream);

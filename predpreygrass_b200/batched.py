@@ -138,7 +138,9 @@ class BatchedPredPreyGrass:
         _lib.check(rc, self.h)
         if s is not None or m is not None:
             torch.cuda.current_stream(self.device).synchronize()  # host staging arrays must outlive the copy
-        return self.out
+        # a masked reset only SCHEDULES the reset: the masked envs are reset by the next step() (include/ppg.h), whose output
+        # carries their founders' rows — there is no new output to hand out here
+        return None if m is not None else self.out
 
     def step(self, actions_pred=None, actions_prey=None):
         a0 = self.actions[0] if actions_pred is None else actions_pred
@@ -156,6 +158,16 @@ class BatchedPredPreyGrass:
                                      order_prey.data_ptr(), self._stream())
         _lib.check(rc, self.h)
         return self.out
+
+    def n_actions(self, s=0):
+        """size of the movement action space of species s: 9 (BASE:96-106), action_range**2 (ECO:225-232), the type ranges (STAG:178-193)"""
+        from .config import VARIANT_BASE
+
+        if self.cfg.variant == VARIANT_BASE:
+            return 9
+        if self.cfg.variant == VARIANT_ECO:
+            return int(self.cfg.action_range) ** 2
+        return max(int(self.cfg.type_action_range[0]), int(self.cfg.type_action_range[1])) ** 2
 
     def random_actions(self, seed, out_pred=None, out_prey=None):
         a0 = self.actions[0] if out_pred is None else out_pred

@@ -512,3 +512,7 @@ STAG_CONFIG = {
     "num_walls": 0,
     "manual_wall_positions": (),
 }
+
+
+# the other heritable-trait variants of eco_evolutionary (filled below the ECO defaults they derive from)
+TRAIT_CONFIGS = {}

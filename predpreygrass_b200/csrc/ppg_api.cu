@@ -716,6 +716,24 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
   return PPG_OK;
 }
 
+int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_streams, int32_t n_steps, uint64_t seed) {
+  if (!handles || n_handles <= 0 || n_steps < 0) return PPG_ERR_INVALID;
+  for (int g = 0; g < n_handles; ++g) {
+    if (!handles[g]) return PPG_ERR_INVALID;
+    if (handles[g]->launches_step == 0) { handles[g]->err = "ppg_rollout_random before ppg_reset"; return PPG_ERR_STATE; }
+  }
+  for (int k = 0; k < n_steps; ++k)
+    for (int g = 0; g < n_handles; ++g) {
+      ppg_handle h = handles[g];
+      void* st = cuda_streams ? cuda_streams[g] : nullptr;
+      int rc = ppg_random_actions(h, seed, h->d_act[0], h->d_act[1], st);
+      if (rc) return rc;
+      rc = run_step_kernel(h, h->d_act[0], h->d_act[1], nullptr, nullptr, static_cast<cudaStream_t>(st));
+      if (rc) return rc;
+    }
+  return PPG_OK;
+}
+
 int ppg_get_buffers(ppg_handle h, ppg_buffers* out) {
   if (!h || !out) return PPG_ERR_INVALID;
   *out = h->bufs;
@@ -749,9 +767,20 @@ static std::vector<Seg> state_segments(ppg_handle h) {
   return v;
 }
 
+static const size_t SNAP_HEAD = 32;  // calls, magic, total bytes, shape hash
+
+static unsigned long long shape_hash(ppg_handle h) {
+  const StepParams& P = h->P;
+  const long long v[] = {h->B, P.variant, P.reward_mode, P.G, P.cap[0], P.cap[1], P.n_grass, P.n_possible[0], P.n_possible[1]};
+  unsigned long long x = 1469598103934665603ULL;  // FNV-1a
+  for (long long w : v)
+    for (int k = 0; k < 8; ++k) { x ^= (unsigned long long)((w >> (8 * k)) & 0xFF); x *= 1099511628211ULL; }
+  return x;
+}
+
 size_t ppg_snapshot_size(ppg_handle h) {
   if (!h) return 0;
-  size_t t = 16;
+  size_t t = SNAP_HEAD;
   for (const Seg& s : state_segments(h)) t += s.bytes;
   return t;
 }
@@ -761,24 +790,28 @@ int ppg_snapshot(ppg_handle h, void* blob, size_t bytes, void* cuda_stream) {
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CK(cudaSetDevice(h->device));
   char* q = static_cast<char*>(blob);
-  unsigned long long head[2] = {h->calls, 0x50504753ULL};
-  memcpy(q, head, 16);
-  q += 16;
+  unsigned long long head[4] = {h->calls, 0x50504753ULL, (unsigned long long)ppg_snapshot_size(h), shape_hash(h)};
+  memcpy(q, head, SNAP_HEAD);
+  q += SNAP_HEAD;
   for (const Seg& s : state_segments(h)) { CK(cudaMemcpyAsync(q, s.p, s.bytes, cudaMemcpyDeviceToHost, st)); q += s.bytes; }
   CK(cudaStreamSynchronize(st));
   return PPG_OK;
 }
 
 int ppg_restore(ppg_handle h, const void* blob, size_t bytes, void* cuda_stream) {
-  if (!h || !blob || bytes < ppg_snapshot_size(h)) return PPG_ERR_INVALID;
+  if (!h || !blob || bytes < SNAP_HEAD) return PPG_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CK(cudaSetDevice(h->device));
   const char* q = static_cast<const char*>(blob);
-  unsigned long long head[2];
-  memcpy(head, q, 16);
+  unsigned long long head[4];
+  memcpy(head, q, SNAP_HEAD);
   if (head[1] != 0x50504753ULL) { h->err = "ppg_restore: not a snapshot blob"; return PPG_ERR_INVALID; }
+  if (head[2] != (unsigned long long)ppg_snapshot_size(h) || head[3] != shape_hash(h) || bytes < ppg_snapshot_size(h)) {
+    h->err = "ppg_restore: the blob was taken from a handle of another shape (n_envs / variant / grid / cap_live / n_grass)";
+    return PPG_ERR_INVALID;
+  }
   h->calls = head[0];
-  q += 16;
+  q += SNAP_HEAD;
   for (const Seg& s : state_segments(h)) { CK(cudaMemcpyAsync(s.p, q, s.bytes, cudaMemcpyHostToDevice, st)); q += s.bytes; }
   {
     int rc = prepare_offsets(h, st);

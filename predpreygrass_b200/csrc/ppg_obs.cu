@@ -288,6 +288,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
     stage ^= 1u;
   }
 
+  // PDL contract: a grid launched with programmatic stream serialization whose prerequisite executes
+  // griddepcontrol.launch_dependents must itself execute griddepcontrol.wait before it may be considered ordered after that
+  // grid.  The tickets are exhausted, so the step kernel has pushed every env and is in its last instructions (header /
+  // counter / flag stores after the queue push): waiting here costs nothing and makes "this kernel has finished" imply
+  // "the step kernel has finished and its writes are visible" for whatever the stream runs next (the next step kernel,
+  // snapshot copies, host reads of env_flags).  A no-op when the kernel was launched without the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // deferred newborn rows (warp 0): by now (the completion queue is exhausted) every env has published its births or is
   // about to.  No other warp touches the buffers any more.
   if (warp != 0) return;

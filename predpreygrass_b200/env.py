@@ -70,6 +70,25 @@ except Exception:  # noqa: BLE001
 
 _SPECIES = ("predator", "prey")
 
+# include/ppg.h PPG_STATUS_*
+_ST_SLOT_OVERFLOW, _ST_NO_SPAWN_CELL, _ST_TAPE_EXHAUSTED, _ST_BAD_ACTION, _ST_ID_POOL_EMPTY = 0x01, 0x02, 0x04, 0x08, 0x10
+
+
+def raise_on_status(status, variant=0):
+    """The in-kernel conditions the reference raises on (sticky per-env status bits, include/ppg.h) become the
+    reference's exceptions in the dict adapters: a drop-in user must not get a silently diverging trajectory.
+    (PPG_STATUS_TAPE_EXHAUSTED is not an error here: the adapters tape only the reset draws and let the device's
+    Philox stream continue.)"""
+    if status & _ST_BAD_ACTION:
+        raise KeyError("action outside the action space (BASE:502 indexes action_to_move_tuple)")
+    if status & _ST_ID_POOL_EMPTY:
+        # ECO:1104-1111 prints the message and raises SystemExit(msg)
+        raise SystemExit("No available agent IDs left: increase n_possible_predators / n_possible_prey")
+    if status & _ST_NO_SPAWN_CELL:
+        raise RuntimeError("no free cell for a newborn (BASE:766 / ECO:1142-1143)")
+    if status & _ST_SLOT_OVERFLOW:
+        raise RuntimeError("device slot capacity exhausted: a birth the reference allows was suppressed; raise config['cap_live']")
+
 
 def _split(agent):
     kind, idx = agent.rsplit("_", 1)
@@ -153,6 +172,7 @@ class PredPreyGrass(_Base):
             b.load_tape([np.zeros(0, np.int32)])
             b.reset(seeds=np.array([np.random.SeedSequence().generate_state(1, np.uint64)[0]], np.uint64))
         out = b.outputs_numpy()
+        raise_on_status(int(out["env_status"][0]))
         self.current_step = 0
         self._trunc_pending = None
         self._done = False
@@ -189,6 +209,7 @@ class PredPreyGrass(_Base):
             if agent not in self._rows:
                 raise KeyError(agent)  # BASE:246: the reference indexes agent_energies[agent]
             s, row = self._rows[agent]
+            self.action_to_move_tuple[int(action)]  # KeyError on an action outside the space, as BASE:502
             acts[s][row] = int(action)
             order[s][row] = seen[s]
             seen[s] += 1
@@ -199,6 +220,7 @@ class PredPreyGrass(_Base):
         t = [torch.from_numpy(x).to(dev) for x in acts + order]
         b.step_ordered(t[0], t[1], t[2], t[3])
         out = b.outputs_numpy()
+        raise_on_status(int(out["env_status"][0]))
         obs, rew, term, trunc, names = self._dicts(out)
         self.current_step = int(out["env_step"][0])
         flags = int(out["env_flags"][0])

@@ -31,7 +31,7 @@ import numpy as np
 
 from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO, VARIANT_STAG,
                      make_config)
-from .env import Box, Discrete, _Base
+from .env import Box, Discrete, _Base, raise_on_status
 
 try:
     from gymnasium.spaces import Dict as DictSpace
@@ -96,7 +96,8 @@ def reference_reset_tape_stag(seed, config):
     for _ in range(n_pred):
         facing.append(int(rng.integers(8)))
         if g("coop_trait_enabled", True):
-            traits.append(float(rng.normal(g("coop_trait_init_mean", 0.5), g("coop_trait_init_std", 0.1))))
+            # defaults of STAG:140-141 (the std is clamped at 0 there, as in config._fill_stag)
+            traits.append(float(rng.normal(g("coop_trait_init_mean", 0.6), max(0.0, g("coop_trait_init_std", 0.12)))))
     return np.asarray(cells, np.int32), np.asarray(facing, np.int32), np.asarray(traits, np.float64)
 
 
@@ -117,7 +118,7 @@ class _RowDictEnv(_Base):
         self._cfg = make_config(config, variant=self._variant, cap_live=config.get("cap_live"), autoreset=False,
                                 seed=config.get("seed") or 0)
         self._batch = BatchedPredPreyGrass(self._cfg, 1, device=config.get("cuda_device", 0))
-        self.max_steps = config["max_steps"] if self._variant == VARIANT_ECO else config.get("max_steps", 10000)
+        self.max_steps = config["max_steps"] if self._variant == VARIANT_ECO else config.get("max_steps", 0)  # ECO:43, STAG:127
         self.grid_size = self._cfg.grid_size
         self.num_obs_channels = self._cfg.num_obs_channels
         self.predator_obs_range, self.prey_obs_range = self._cfg.obs_range[0], self._cfg.obs_range[1]
@@ -155,7 +156,9 @@ class _RowDictEnv(_Base):
         self.current_step = 0
         self._done = False
         self._state = None
-        return b.outputs_numpy()
+        out = b.outputs_numpy()
+        raise_on_status(int(out["env_status"][0]), self._variant)
+        return out
 
     def _step_device(self, action_dict):
         import torch
@@ -172,7 +175,10 @@ class _RowDictEnv(_Base):
                 self._unknown_actor(agent)
                 continue
             s, row = self._rows[agent]
-            acts[s][row] = self._action(s, action)
+            a = self._action(s, action)
+            if not 0 <= (a & 0xFF) < self._n_moves(agent):
+                raise KeyError(action)  # the reference indexes its action -> move table (ECO:668, STAG:834-841)
+            acts[s][row] = a
             order[s][row] = seen[s]
             seen[s] += 1
         if seen[0] + seen[1] != len(self._rows):
@@ -182,7 +188,11 @@ class _RowDictEnv(_Base):
         b.step_ordered(t[0], t[1], t[2], t[3])
         out = b.outputs_numpy()
         self.current_step = int(out["env_step"][0])
+        raise_on_status(int(out["env_status"][0]), self._variant)
         return out
+
+    def _n_moves(self, agent):
+        raise NotImplementedError
 
     def _unknown_actor(self, agent):
         raise KeyError(agent)
@@ -291,6 +301,9 @@ class PredPreyGrassEco(_RowDictEnv):
     def _name(self, s, i):
         return f"predator_{i}" if s == 0 else f"prey_{i}"
 
+    def _n_moves(self, agent):
+        return self.action_range ** 2
+
     def _read(self):
         if self._state is None:
             self._state = self._batch.read_env_eco(0)
@@ -387,7 +400,7 @@ class PredPreyGrassStag(_RowDictEnv):
     def __init__(self, config=None):
         super().__init__(config)
         c, g = self._cfg, config.get
-        self.strict_rllib_output = bool(g("strict_rllib_output", True))
+        self.strict_rllib_output = bool(g("strict_rllib_output", False))  # STAG:126 (the device flag has the same default)
         self._n1 = (c.n_possible_t[0][0], c.n_possible_t[1][0])
         self.n_possible_type_1_predators, self.n_possible_type_2_predators = c.n_possible_t[0][0], c.n_possible_t[0][1]
         self.n_possible_type_1_prey, self.n_possible_type_2_prey = c.n_possible_t[1][0], c.n_possible_t[1][1]
@@ -412,6 +425,9 @@ class PredPreyGrassStag(_RowDictEnv):
         sp = "predator" if s == 0 else "prey"
         n1 = self._n1[s]
         return f"type_1_{sp}_{i}" if i < n1 else f"type_2_{sp}_{i - n1}"
+
+    def _n_moves(self, agent):
+        return max(1, (self.type_1_act_range if agent.startswith("type_1") else self.type_2_act_range) ** 2)
 
     def _action(self, s, value):
         """`_split_action` (STAG:771-799): predators pass [move, join_hunt] as array / tuple / dict; join defaults to 1"""

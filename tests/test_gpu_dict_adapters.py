@@ -111,7 +111,7 @@ def test_stag_dict_adapter_replays_reference_episode(name):
         # the recording kept the positioned part of `env.agents` (under strict_rllib_output the list also carries the
         # ids that ended this step, STAG:565-573)
         assert [a for a in env.agents if not term.get(a, False)] == agents, (name, t)
-        if cfg.get("strict_rllib_output", True):
+        if cfg.get("strict_rllib_output", False):
             assert sorted(env.agents) == sorted(keys), (name, t)
         c = z["counters"][t]
         assert infos["__all__"]["team_capture_successes"] == c[0] and infos["__all__"]["team_capture_attempts"] == c[8], (name, t)
