@@ -79,8 +79,9 @@ enum {
 #define PPG_STATUS_TAPE_EXHAUSTED 0x04u /* replay tape ran out; Philox stream used instead */
 #define PPG_STATUS_BAD_ACTION 0x08u     /* action outside the action space (reference: KeyError, BASE:502) */
 #define PPG_STATUS_ID_POOL_EMPTY 0x10u  /* ECO: id pool exhausted, birth suppressed (reference: SystemExit, ECO:1104-1111) */
-#define PPG_STATUS_GHOST_CELL 0x20u     /* ECO: a prey that aged out this step was bitten with a finite intake cap; the reference
-                                         * leaves a stale grid value behind (ECO:826-832 after :1060-1090), the device does not */
+#define PPG_STATUS_GHOST_CELL 0x20u     /* ECO: more than 4 stale prey-channel cells at once in one env (a prey that aged out and was
+                                         * bitten under a finite intake cap in the same step leaves its grid value behind, ECO:826-832
+                                         * after :1060-1090; the device carries up to 4 such ghost cells per env, ppg_eco.cu) */
 
 /* error codes */
 #define PPG_OK 0
@@ -370,6 +371,11 @@ int ppg_profile_begin(ppg_handle h);
  * per-env step latency and the kernel's schedule. */
 int ppg_profile_env_cycles(ppg_handle h, uint32_t* cycles, uint32_t* info, uint32_t* start_ns, uint32_t* sm, void* cuda_stream);
 int ppg_profile_end(ppg_handle h, double* ms_step_kernel, double* ms_obs_kernel, int32_t* n_steps);
+
+/* Diagnostic: out[i] = the device's pow(x[i], y[i]) (include/ppg_pow.h: glibc's pow repeated bit for bit — what the
+ * kernels use for `speed ** exponent`, ECO:559-563, and `(1 - p0) ** ratio`, STAG:1137).  Host pointers; synchronises.
+ * tests/test_gpu_pow.py compares it with the host libm on millions of arguments. */
+int ppg_selftest_pow(const double* x, const double* y, double* out, int64_t n, int32_t device);
 
 const char* ppg_last_error(ppg_handle h);
 int ppg_abi_version(void);

@@ -107,34 +107,6 @@ PPG_HD double ppg_log(double x) {
   return (double)e * 0.6931471805599453 + 2.0 * s * p;
 }
 
-/* e^x for x <= 0 (the capture success law, STAG:1137): x = k ln2 + r, |r| <= ln2 / 2, Taylor series to r^13
- * (truncation < 5e-18), scaled by 2^k through the exponent bits.  Basic operations only, like ppg_log. */
-PPG_HD double ppg_exp_neg(double x) {
-  if (!(x > -708.0)) return 0.0;
-  if (x > 0.0) x = 0.0;
-  const int k = (int)(x * 1.4426950408889634 - 0.5);
-  const double r = (x - (double)k * 0.693147180369123816490) - (double)k * 1.90821492927058770002e-10;
-  double p = 1.0 / 6227020800.0;
-  p = p * r + 1.0 / 479001600.0;
-  p = p * r + 1.0 / 39916800.0;
-  p = p * r + 1.0 / 3628800.0;
-  p = p * r + 1.0 / 362880.0;
-  p = p * r + 1.0 / 40320.0;
-  p = p * r + 1.0 / 5040.0;
-  p = p * r + 1.0 / 720.0;
-  p = p * r + 1.0 / 120.0;
-  p = p * r + 1.0 / 24.0;
-  p = p * r + 1.0 / 6.0;
-  p = p * r + 0.5;
-  p = p * r + 1.0;
-  p = p * r + 1.0;
-  return p * PPG_U2D((uint64_t)(1023 + k) << 52);
-}
-
-/* base ** y for 0 < base < 1, y >= 0 — the device's (and, by default, the oracle's) stand-in for CPython's libm pow
- * in `1.0 - (1.0 - p0) ** max(effort_ratio, 0.0)` (STAG:1137); agrees with libm to ~1e-15 relative */
-PPG_HD double ppg_pow_frac(double base, double y) { return ppg_exp_neg(y * ppg_log(base)); }
-
 PPG_HD double ppg_draw_u01(uint64_t seed, uint32_t env, uint32_t episode, uint32_t stream, uint32_t* ctr) {
   const ppg_u32x4 r = ppg_philox4x32(env, episode, (*ctr)++, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ppg_u01(r.v[0], r.v[1]);

@@ -52,7 +52,6 @@ def lib():
         L.ppgo_env_reset_cells.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ppgo_env_agents.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
-        L.ppgo_set_pow_libm.argtypes = [C.c_void_p, C.c_int32]
         L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
@@ -122,8 +121,6 @@ class Oracle:
         t, keep = make_tape(cells_per_env, reals_per_env)
         lib().ppgo_load_tape(self.h, C.byref(t))
 
-    def set_pow_libm(self, on):
-        lib().ppgo_set_pow_libm(self.h, 1 if on else 0)
 
     def env_reset_eco(self, env, cells, founder_speed):
         c = np.ascontiguousarray(cells, np.int32)

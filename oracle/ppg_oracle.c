@@ -855,10 +855,6 @@ int ppgo_env_reset_eco(ppgo_batch* b, int32_t env, const int32_t* cells, const d
   return PPG_OK;
 }
 
-void ppgo_set_pow_libm(ppgo_batch* b, int32_t on) {
-  for (int e = 0; e < b->n_envs; ++e) b->envs[e].pow_libm = on;
-}
-
 int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                       double* speed_prey, uint8_t* dead_prey, int32_t* active_num) {
   if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;

@@ -189,12 +189,11 @@ void eco_env_reset_auto(env_t* e) {
   free(cells); free(sp);
 }
 
-/* speed ** exponent (ECO:559-563).  CPython calls libm pow; the device squares when the exponent is 2 */
+/* speed ** exponent (ECO:559-563): CPython's float power is libm pow(), and so is the oracle's — always.  (The device
+ * repeats glibc's pow bit for bit, include/ppg_pow.h; the checker is never bent toward the kernel.) */
 static double speed_cost_factor(const env_t* e, double speed) {
   if (speed < 0.0) return 1.0; /* no genome */
-  const double ex = e->c->move_speed_cost_exponent;
-  if (!e->pow_libm && ex == 2.0) return speed * speed;
-  return pow(speed, ex);
+  return pow(speed, e->c->move_speed_cost_exponent);
 }
 
 static int sgn(int v) { return (v > 0) - (v < 0); }
@@ -333,7 +332,8 @@ static void handle_predator_engagement(env_t* e, int id) {
     e->energy[1][caught] = rem;
     *GF(e, 1, e->x[1][caught], e->y[1][caught]) = (float)rem;
     e->dead[caught] = 1;
-    if (e->termd[1][caught]) e->status |= PPG_STATUS_GHOST_CELL; /* aged out this step: Step 5 removes it, the grid value stays */
+    /* (if the prey aged out this step, Step 5 removes it and this grid value stays behind: the persistent grid of the
+     * oracle keeps it, the device carries it as a ghost cell — ppg_eco.cu header) */
   } else { /* fully eaten (ECO:846-866) */
     capture_obs(e, 1, caught);
     e->term[j] = 1; e->termd[1][caught] = 1;

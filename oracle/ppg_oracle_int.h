@@ -76,7 +76,6 @@ typedef struct env_t {
   const double* tape_reals;
   int64_t real_pos, real_end;
   uint32_t trait_draws;
-  int pow_libm;       /* 1: speed ** exponent through libm pow like CPython (golden pinning); 0: device semantics */
   /* ---- STAG (ppg_oracle_stag.c) ---- */
   int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
   double* trait;      /* predator_cooperation_trait (STAG:230) */

@@ -255,7 +255,7 @@ static int capture_success(env_t* e, const int* joiners, int nj, double prey_ene
   const double ratio = total / difficulty;
   const double ex = ratio > 0.0 ? ratio : 0.0;
   const double base = 1.0 - c->team_capture_base_success_p0;
-  const double pw = e->pow_libm ? pow(base, ex) : ppg_pow_frac(base, ex); /* CPython `**` = libm pow (golden pinning) */
+  const double pw = pow(base, ex); /* CPython `**` = libm pow (STAG:1137); the device repeats glibc's pow, include/ppg_pow.h */
   const double base_prob = 1.0 - pw;
   double prob = base_prob > c->team_capture_min_success_prob ? base_prob : c->team_capture_min_success_prob;
   if (prob > 1.0) prob = 1.0;

@@ -43,6 +43,11 @@ cudaError_t launch_random_actions_stag(const int32_t* n_rows, const int32_t* re0
 
 using namespace ppg;
 
+// include/ppg_pow.h on the device, argument by argument (ppg_selftest_pow)
+__global__ void ppg_pow_selftest_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = ppg_pow(x[i], y[i]);
+}
+
 struct ppg_handle_s {
   ppg_config cfg;
   int B = 0, device = 0;
@@ -231,7 +236,6 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.action_range = c.action_range; P.n_actions = c.action_range * c.action_range; P.genome_enabled = c.genome_enabled != 0;
     P.speed_in_obs = c.include_speed_in_obs != 0; P.max_age[0] = c.max_agent_age[0]; P.max_age[1] = c.max_agent_age[1];
     P.carcass_age = c.carcass_only_predator_age; P.slow_dist = c.slow_max_move_distance; P.fast_dist = c.fast_max_move_distance;
-    P.pow_square = c.move_speed_cost_exponent == 2.0;
     P.move_cost[0] = c.move_cost_per_cell[0]; P.move_cost[1] = c.move_cost_per_cell[1]; P.move_exp = c.move_speed_cost_exponent;
     P.bite_cap_grass = c.max_energy_gain_per_grass; P.bite_cap_prey = c.max_energy_gain_per_prey;
     for (int s = 0; s < 2; ++s) { P.f_mean[s] = c.founder_speed_mean[s]; P.f_std[s] = c.founder_speed_std[s]; }
@@ -460,7 +464,10 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.done1, n_blk)); CKC(dalloc(h, &P.done2, n_grp)); CKC(dalloc(h, &P.done3, 1));
     CKC(dalloc(h, &P.totals, 8));
   }
-  if (eco) CKC(dalloc(h, &P.ehdr, (size_t)B));
+  if (eco) {
+    CKC(dalloc(h, &P.ehdr, (size_t)B));
+    CKC(dalloc(h, &P.gh_n, (size_t)B)); CKC(dalloc(h, &P.gh_cell, (size_t)B * PPG_MAX_GHOSTS)); CKC(dalloc(h, &P.gh_val, (size_t)B * PPG_MAX_GHOSTS));
+  }
   if (stag) CKC(dalloc(h, &P.shdr, (size_t)B));
   CKC(dalloc(h, &P.gr_pos, (size_t)B * std::max(1, P.n_grass)));
   CKC(dalloc(h, &P.gr_e, (size_t)B * std::max(1, P.n_grass)));
@@ -734,6 +741,23 @@ int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_strea
   return PPG_OK;
 }
 
+int ppg_selftest_pow(const double* x, const double* y, double* out, int64_t n, int32_t device) {
+  if (!x || !y || !out || n <= 0) return PPG_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "ppg_selftest_pow: bad device"; return PPG_ERR_NO_DEVICE; }
+  double *dx = nullptr, *dy = nullptr, *dz = nullptr;
+  const size_t bytes = (size_t)n * sizeof(double);
+  cudaError_t e = cudaMalloc(&dx, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dy, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dz, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { ppg_pow_selftest_kernel<<<148 * 8, 256>>>(dx, dy, dz, (long long)n); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dz, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy); cudaFree(dz);
+  if (e != cudaSuccess) { g_err = std::string("ppg_selftest_pow: ") + cudaGetErrorString(e); return PPG_ERR_CUDA; }
+  return PPG_OK;
+}
+
 int ppg_get_buffers(ppg_handle h, ppg_buffers* out) {
   if (!h || !out) return PPG_ERR_INVALID;
   *out = h->bufs;
@@ -760,7 +784,10 @@ static std::vector<Seg> state_segments(ppg_handle h) {
     }
   }
   if (P.variant == PPG_VARIANT_STAG) v.push_back({P.shdr, sizeof(StagHdr) * (size_t)h->B});
-  if (P.variant == PPG_VARIANT_ECO) v.push_back({P.ehdr, sizeof(EcoHdr) * (size_t)h->B});
+  if (P.variant == PPG_VARIANT_ECO) {
+    v.push_back({P.ehdr, sizeof(EcoHdr) * (size_t)h->B});
+    v.push_back({P.gh_n, (size_t)h->B}); v.push_back({P.gh_cell, (size_t)h->B * PPG_MAX_GHOSTS * 2}); v.push_back({P.gh_val, (size_t)h->B * PPG_MAX_GHOSTS * 4});
+  }
   v.push_back({P.gr_pos, (size_t)h->B * std::max(1, P.n_grass) * 2});
   v.push_back({P.gr_e, (size_t)h->B * std::max(1, P.n_grass) * 8});
   v.push_back({P.counters, (size_t)h->B * PPG_N_STATS * 4});

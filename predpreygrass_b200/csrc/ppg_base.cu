@@ -317,9 +317,11 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
             const bool blocked = ow != 0 && SEL(S.E)[ow - 1] > 0.0;
             const int nx = blocked ? xx : tx, ny = blocked ? yy : ty;
             __syncwarp();
-            own[CELLXY(xx, yy)] = 0;
-            own[CELLXY(nx, ny)] = (MapT)(jj + 1);
-            SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
+            if (lane == 0) {  // one writer: the two map stores may hit the same cell (blocked move) and must keep their order
+              own[CELLXY(xx, yy)] = 0;
+              own[CELLXY(nx, ny)] = (MapT)(jj + 1);
+              SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
+            }
             __syncwarp();
           }
         }
@@ -373,8 +375,10 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           double e = S.E[0][slot];
           if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
             rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, n[0], n[1], rowctr, lane);
-            S.map[0][cell] = 0;  // BASE:293
-            S.flg[0][slot] = F_DIED;
+            if (lane == 0) {
+              S.map[0][cell] = 0;  // BASE:293
+              S.flg[0][slot] = F_DIED;
+            }
             st_starved[0]++;
             __syncwarp();
             continue;
@@ -389,13 +393,17 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
             const int q = best & 0xFFFF;
             e += S.E[1][q];  // BASE:324 (also when the prey's energy is <= 0)
             __syncwarp();
-            S.E[0][slot] = e;
-            S.map[0][cell] = (MapT)(slot + 1);  // BASE:325
-            S.flg[0][slot] |= F_ATE;
+            if (lane == 0) {
+              S.E[0][slot] = e;
+              S.map[0][cell] = (MapT)(slot + 1);  // BASE:325
+              S.flg[0][slot] |= F_ATE;
+            }
             __syncwarp();
             rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, n[0], n[1], rowctr, lane);  // BASE:327
-            S.map[1][cell] = 0;  // BASE:335
-            S.flg[1][q] = F_DIED | F_CAUGHT;
+            if (lane == 0) {
+              S.map[1][cell] = 0;  // BASE:335
+              S.flg[1][q] = F_DIED | F_CAUGHT;
+            }
             st_eaten++;
             __syncwarp();
           }
@@ -440,8 +448,10 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           const double ee = S.E[1][sl];
           if (ee <= 0.0) {  // BASE:284-301
             rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, n[0], n[1], rowctr, lane);
-            S.map[1][cl] = 0;
-            S.flg[1][sl] = F_DIED;
+            if (lane == 0) {
+              S.map[1][cl] = 0;
+              S.flg[1][sl] = F_DIED;
+            }
             st_starved[1]++;
             __syncwarp();
             continue;
@@ -450,10 +460,12 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           if (gg) {
             const double en = ee + S.gE[gg - 1];
             __syncwarp();
-            S.E[1][sl] = en;
-            S.map[1][cl] = (MapT)(sl + 1);
-            S.gE[gg - 1] = 0.0;
-            S.flg[1][sl] |= F_ATE;
+            if (lane == 0) {
+              S.E[1][sl] = en;
+              S.map[1][cl] = (MapT)(sl + 1);
+              S.gE[gg - 1] = 0.0;
+              S.flg[1][sl] |= F_ATE;
+            }
             st_grass++;
             __syncwarp();
           }
@@ -511,19 +523,24 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
             const int child_id = s == 0 ? h.next_idx[0]++ : h.next_idx[1]++;  // BASE:396-397
             const double pe = SEL(S.E)[ps_slot] - p.init_e[s];  // BASE:404
             __syncwarp();
-            SEL(S.id)[cs] = (uint16_t)child_id;
-            SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
-            SEL(S.E)[cs] = p.init_e[s];  // BASE:403
-            SEL(S.flg)[cs] = F_ALIVE | F_NEWBORN;
-            SEL(S.E)[ps_slot] = pe;
-            SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // BASE:405
-            SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // BASE:406
-            SEL(S.flg)[ps_slot] |= F_REPRO;
+            if (lane == 0) {  // one writer for the warp-uniform stores
+              SEL(S.id)[cs] = (uint16_t)child_id;
+              SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
+              SEL(S.E)[cs] = p.init_e[s];  // BASE:403
+              SEL(S.flg)[cs] = F_ALIVE | F_NEWBORN;
+              SEL(S.E)[ps_slot] = pe;
+              SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // BASE:405
+              SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // BASE:406
+              SEL(S.flg)[ps_slot] |= F_REPRO;
+            }
             if (kick) {  // KICK:434-449
-              SEL(S.aux)[cs] = 0;
-              SEL(S.par)[cs] = SEL(S.id)[ps_slot];
-              SEL(S.aux)[ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
               const unsigned gp = SEL(S.par)[ps_slot];
+              __syncwarp();
+              if (lane == 0) {
+                SEL(S.aux)[cs] = 0;
+                SEL(S.par)[cs] = SEL(S.id)[ps_slot];
+                SEL(S.aux)[ps_slot] = 0;  // rewards[agent] = reproduction_reward overwrites earlier kickbacks (BASE:409)
+              }
               __syncwarp();
               if (gp != 0xFFFFu) {
                 int gs = -1;
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
                 if (gs >= 0) {
                   const uint8_t cnt = SEL(S.aux)[gs];
                   __syncwarp();
-                  SEL(S.aux)[gs] = (uint8_t)(cnt + 1);
+                  if (lane == 0) SEL(S.aux)[gs] = (uint8_t)(cnt + 1);
                 }
               }
             }

@@ -17,6 +17,7 @@
 
 #include "../../include/ppg.h"
 #include "../../include/ppg_philox.h"
+#include "../../include/ppg_pow.h"
 
 namespace ppg {
 
@@ -79,6 +80,7 @@ enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_
 #define DSC_ZERO 0xFFFEu  // STAG: ended agents are observed as all-zero rows
 #define DSC_COPY 0xFFFDu  // ECO: the row was captured at birth into born_obs[env][dsx] (episode ended on this step, ECO:417-420)
 #define PPG_BORN_K 4      // at-birth rows kept per env and species; further ones take the (blocking) direct path
+#define PPG_MAX_GHOSTS 4  // ECO: stale prey-channel cells carried per env (ppg_eco.cu header); more raise PPG_STATUS_GHOST_CELL
 
 struct StepParams {
   // ---- config ----
@@ -153,13 +155,15 @@ struct StepParams {
   int init_bytes;
   // ---- ECO (ppg_eco.cu) ----
   int variant, action_range, n_actions, genome_enabled, speed_in_obs, max_age[2], carcass_age, slow_dist, fast_dist;
-  int pow_square;  // movement_speed_cost_exponent == 2: speed * speed
   double move_cost[2], move_exp, bite_cap_grass, bite_cap_prey, f_mean[2], f_std[2], mut_rate, mut_std, sp_lo, sp_hi, sp_thr;
   EcoHdr* ehdr;
   uint16_t* ag_age[2];
   uint16_t* ag_seq[2];
   double* ag_spd[2];
   uint8_t* ag_dead[2];
+  uint8_t* gh_n;       // [B] ghost cells of the env (ppg_eco.cu header)
+  uint16_t* gh_cell;   // [B][PPG_MAX_GHOSTS] packed position x << 8 | y
+  float* gh_val;       // [B][PPG_MAX_GHOSTS] the stale float32 grid value
   const double* tape_reals;
   int so_spd[2], so_age[2], so_seq[2], so_mord[2];
   const unsigned* obs_self;  // [2][32] per-lane bit mask: element j of the lane lies in the agent's own-speed plane (ECO:707-711)

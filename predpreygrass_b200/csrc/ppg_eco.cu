@@ -17,6 +17,14 @@
 // A non-zero cell of the reference's float32 grid always equals float32(current energy) of the agent that
 // wrote it last (every energy change is followed by a grid write: ECO:597,651-655,817,829,913,1154-1155), so
 // the blocked test `grid > 0` (ECO:690) is `owner != 0 && (float)E[owner] > 0`.
+//
+// One exception has no owner: a prey that aged out in this step's ageing loop (grid cell zeroed, ECO:1073) is still in
+// `agent_positions` when the predators engage (removal is Step 5, ECO:332-351); bitten under a finite intake cap it is
+// written back to the grid as a carcass (ECO:826-832) and then removed WITHOUT the grid being zeroed — a stale positive
+// value stays in the prey channel, blocks prey movers and shows up in observations until something overwrites or zeroes
+// that cell.  These GHOST cells are carried per env in HBM (gh_cell / gh_val, at most PPG_MAX_GHOSTS) and loaded as
+// pseudo-slots at the top of the prey list (not alive, no row, energy = the stale value), so the owner-map machinery
+// treats them like the reference's grid does.
 #include <cuda_runtime.h>
 
 #include "ppg_step_common.cuh"
@@ -51,6 +59,9 @@ __device__ __forceinline__ float speed_plane(const StepParams& p, double spd) {
   if (!p.speed_in_obs || spd < 0.0) return 0.f;
   return (float)((spd - p.sp_lo) / (p.sp_hi - p.sp_lo));
 }
+
+// speed ** exponent (ECO:559-563): CPython's float power = glibc pow, repeated bit for bit (include/ppg_pow.h)
+static __device__ __noinline__ double speed_cost_factor(double speed, double exponent) { return ppg_pow(speed, exponent); }
 
 // one tape-or-Philox real draw (uniform lanes)
 __device__ __forceinline__ bool take_real(const StepParams& p, EcoHdr& eh, EnvHdr& h, double& out) {
@@ -115,6 +126,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     unsigned env_flags = 0;
     unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
     bool over = false, trunc = false, done = false, have_new_base = false;
+    int n_gh = 0;  // ghost cells loaded into the pseudo-slots cap[1]-1, cap[1]-2, ...
 
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
@@ -302,6 +314,22 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           }
         }
       __syncwarp();
+      // ghost cells: the stale value is still on the grid unless a prey standing there has just re-written it (ECO:597)
+      n_gh = p.gh_n[env];
+      if (n_gh) {
+        if (lane < n_gh) {
+          const int gs = p.cap[1] - 1 - lane;
+          const unsigned gp = p.gh_cell[(size_t)env * PPG_MAX_GHOSTS + lane];
+          const float gv = p.gh_val[(size_t)env * PPG_MAX_GHOSTS + lane];
+          S.pos[1][gs] = (uint16_t)gp;
+          S.E[1][gs] = (double)gv;
+          S.flg[1][gs] = 0;
+          S.vt[1][1 + gs] = gv;  // outside the range refresh_tables rewrites
+          const int c = CELLP(gp);
+          if (S.map[1][c] == 0) S.map[1][c] = (MapT)(gs + 1);
+        }
+        __syncwarp();
+      }
 
       // age-outs (ECO:602-616,1060-1090), in self.agents order; the grass channel still shows last step's energies
       if (__any_sync(FULL, aged_any)) {
@@ -319,9 +347,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           const int cell = CELLP((unsigned)SEL(S.pos)[slot]);
           rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[s] + (size_t)(SEL(old_base) + slot) * p.elems[s], cell, s, n[0], n[1], rowctr,
                                                    lane, speed_plane(p, SEL(X.spd)[slot]));
-          __syncwarp();
-          SEL(S.map)[cell] = 0;
-          SEL(S.flg)[slot] = F_DIED;
+          if (lane == 0) {
+            SEL(S.map)[cell] = 0;
+            SEL(S.flg)[slot] = F_DIED;
+          }
           if (s == 0) eh.active[0] = max(eh.active[0] - 1, 0); else eh.active[1] = max(eh.active[1] - 1, 0);
           __syncwarp();
         }
@@ -371,7 +400,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int nc = blocked ? oc : tc;
             if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
               const double sp = SEL(X.spd)[j];
-              const double fac = sp < 0.0 ? 1.0 : (p.pow_square ? sp * sp : pow(sp, p.move_exp));
+              const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
               SEL(S.E)[j] = SEL(S.E)[j] - p.move_cost[s] * sqrt((double)d2) * fac;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
             }
@@ -398,14 +427,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int dd = (nx - xx) * (nx - xx) + (ny - yy) * (ny - yy);
             double e = SEL(S.E)[jj];
             if (dd > 0) {
-              const double fac = sp < 0.0 ? 1.0 : (p.pow_square ? sp * sp : pow(sp, p.move_exp));
+              const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
               e = e - p.move_cost[s] * sqrt((double)dd) * fac;
             }
             __syncwarp();
-            SEL(S.E)[jj] = e;
-            own[CELLXY(xx, yy)] = 0;
-            own[CELLXY(nx, ny)] = (MapT)(jj + 1);
-            SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
+            if (lane == 0) {  // one writer: the two map stores may hit the same cell (blocked move) and must keep their order
+              SEL(S.E)[jj] = e;
+              own[CELLXY(xx, yy)] = 0;
+              own[CELLXY(nx, ny)] = (MapT)(jj + 1);
+              SEL(S.pos)[jj] = (uint16_t)((nx << 8) | ny);
+            }
             __syncwarp();
           }
         }
@@ -429,9 +460,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int cell = CELLP((unsigned)SEL(S.pos)[slot]);
             rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[s] + (size_t)(SEL(old_base) + slot) * p.elems[s], cell, s, n[0], n[1],
                                                      rowctr, lane, speed_plane(p, SEL(X.spd)[slot]));
-            __syncwarp();
-            SEL(S.map)[cell] = 0;
-            SEL(S.flg)[slot] = F_DIED;  // also drops F_CARC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
+            if (lane == 0) {
+              SEL(S.map)[cell] = 0;
+              SEL(S.flg)[slot] = F_DIED;  // also drops F_CARC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
+            }
             if (s == 0) { eh.active[0] -= 1; st_starved[0]++; } else { eh.active[1] -= 1; st_starved[1]++; }
             __syncwarp();
           }
@@ -480,10 +512,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const double rem = ge - bite;
             const double en = S.E[1][sl] + bite;
             __syncwarp();
-            S.E[1][sl] = en;
-            S.map[1][cl] = (MapT)(sl + 1);
-            S.gE[gg - 1] = rem > 0.0 ? rem : 0.0;
-            S.flg[1][sl] = (uint8_t)(f | F_ATE);
+            if (lane == 0) {
+              S.E[1][sl] = en;
+              S.map[1][cl] = (MapT)(sl + 1);
+              S.gE[gg - 1] = rem > 0.0 ? rem : 0.0;
+              S.flg[1][sl] = (uint8_t)(f | F_ATE);
+            }
             st_grass++;
             __syncwarp();
           }
@@ -523,22 +557,28 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const double rem = pe - bite;
             const double en = S.E[0][slot] + bite;
             __syncwarp();
-            S.E[0][slot] = en;
-            S.map[0][cell] = (MapT)(slot + 1);  // ECO:817
-            S.flg[0][slot] |= F_ATE;
+            if (lane == 0) {
+              S.E[0][slot] = en;
+              S.map[0][cell] = (MapT)(slot + 1);  // ECO:817
+              S.flg[0][slot] |= F_ATE;
+            }
             if (rem > 0.0) {  // carcass (ECO:826-845)
-              S.E[1][q] = rem;
-              S.map[1][cell] = (MapT)(q + 1);
-              if (qf & F_DIED) h.status |= PPG_STATUS_GHOST_CELL;  // aged out this step: the reference keeps a stale grid value
-              S.flg[1][q] = (uint8_t)(qf | F_CARC);
+              if (lane == 0) {
+                S.E[1][q] = rem;
+                // a prey that aged out this step (F_DIED) is removed in Step 5 without the grid being zeroed: the entry written
+                // here outlives its owner and becomes a ghost cell at write-back (see the header)
+                S.map[1][cell] = (MapT)(q + 1);
+                S.flg[1][q] = (uint8_t)(qf | F_CARC);
+              }
               __syncwarp();
             } else {  // fully eaten (ECO:846-866); its observation is captured now
               __syncwarp();
               rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[1] + (size_t)(old_base[1] + q) * p.elems[1], cell, 1, n[0], n[1], rowctr,
                                                        lane, speed_plane(p, X.spd[1][q]));
-              __syncwarp();
-              S.map[1][cell] = 0;
-              S.flg[1][q] = (uint8_t)((qf & F_ATE) | F_DIED | F_CAUGHT);
+              if (lane == 0) {
+                S.map[1][cell] = 0;
+                S.flg[1][q] = (uint8_t)((qf & F_ATE) | F_DIED | F_CAUGHT);
+              }
               eh.active[1] -= 1;  // also for a prey that already starved or aged out this step (quirk 4)
               st_eaten++;
               __syncwarp();
@@ -567,7 +607,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int ps_slot = b0 + __ffs(m) - 1;
             m &= m - 1;
             if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) { h.status |= PPG_STATUS_ID_POOL_EMPTY; continue; }  // ECO:1104-1111
-            if (SEL(n) + SEL(births) >= p.cap[s]) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
+            if (SEL(n) + SEL(births) >= p.cap[s] - (s == 1 ? n_gh : 0)) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
             // mutate_genome (GENOME:49-59): the draws precede the spawn search (ECO:1119 before :1136)
             double spd = SEL(X.spd)[ps_slot];
             if (p.genome_enabled && p.mut_rate > 0 && p.mut_std > 0) {
@@ -609,17 +649,19 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int child_id = s == 0 ? h.next_idx[0]++ : h.next_idx[1]++;  // smallest never-used id (ECO:260-272)
             const double pe = SEL(S.E)[ps_slot] - p.init_e[s];                // ECO:1150
             __syncwarp();
-            SEL(S.id)[cs] = (uint16_t)child_id;
-            SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
-            SEL(S.E)[cs] = p.init_e[s];
-            SEL(S.flg)[cs] = (uint8_t)(F_ALIVE | F_NEWBORN | (maybe_done ? F_BORNROW : 0));
-            SEL(X.age)[cs] = 0;
-            SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
-            SEL(X.spd)[cs] = p.genome_enabled ? spd : -1.0;
-            SEL(S.E)[ps_slot] = pe;
-            SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // ECO:1154
-            SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // ECO:1155
-            SEL(S.flg)[ps_slot] |= F_REPRO;
+            if (lane == 0) {  // one writer for the warp-uniform stores
+              SEL(S.id)[cs] = (uint16_t)child_id;
+              SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
+              SEL(S.E)[cs] = p.init_e[s];
+              SEL(S.flg)[cs] = (uint8_t)(F_ALIVE | F_NEWBORN | (maybe_done ? F_BORNROW : 0));
+              SEL(X.age)[cs] = 0;
+              SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
+              SEL(X.spd)[cs] = p.genome_enabled ? spd : -1.0;
+              SEL(S.E)[ps_slot] = pe;
+              SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // ECO:1154
+              SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // ECO:1155
+              SEL(S.flg)[ps_slot] |= F_REPRO;
+            }
             eh.next_seq++;
             if (s == 0) eh.active[0] += 1; else eh.active[1] += 1;  // ECO:1157
             __syncwarp();
@@ -780,12 +822,40 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         p.new_cnt[lane][env] = nb;
       }
       if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
+      // ghost cells of the next step: loaded ghosts whose entry nobody overwrote or zeroed, and prey that aged out this
+      // step and were written back as carcasses (their entry outlives them).  Only a finite intake cap can create them.
+      {
+        int kept = 0;
+        if (keep && mode == 2 && (n_gh > 0 || p.bite_cap_prey < HUGE_VAL)) {
+          const size_t gb = (size_t)env * PPG_MAX_GHOSTS;
+          for (int b0 = -32; b0 < n[1]; b0 += 32) {  // first round: the loaded ghosts (pseudo-slots), then the list
+            const int sl = b0 < 0 ? (lane < n_gh ? p.cap[1] - 1 - lane : -1) : (b0 + lane < n[1] ? b0 + lane : -1);
+            bool gh = false;
+            unsigned gp = 0;
+            if (sl >= 0) {
+              const unsigned f = S.flg[1][sl];
+              gp = S.pos[1][sl];
+              gh = (b0 < 0 || ((f & F_DIED) && (f & F_CARC))) && S.map[1][CELLP(gp)] == (MapT)(sl + 1);
+            }
+            const unsigned m = __ballot_sync(FULL, gh);
+            const int at = kept + __popc(m & lt_mask);
+            if (gh && at < PPG_MAX_GHOSTS) {
+              p.gh_cell[gb + at] = (uint16_t)gp;
+              p.gh_val[gb + at] = (float)S.E[1][sl];
+            }
+            kept += __popc(m);
+          }
+          if (kept > PPG_MAX_GHOSTS) { h.status |= PPG_STATUS_GHOST_CELL; kept = PPG_MAX_GHOSTS; }
+        }
+        if (lane == 0 && (kept > 0 || n_gh > 0 || mode == 1)) p.gh_n[env] = (uint8_t)kept;
+      }
       // leave the maps empty for the next env of this warp.  A carcass bitten after it aged out keeps an entry while its
-      // owner is gone, so every loaded slot is un-written, alive or not.
+      // owner is gone, so every loaded slot is un-written, alive or not (and so are the ghost pseudo-slots).
 #pragma unroll
       for (int s = 0; s < 2; ++s)
         #pragma unroll 1
         for (int i = lane; i < n[s] + births[s]; i += 32) S.map[s][CELLP((unsigned)S.pos[s][i])] = 0;
+      if (lane < n_gh) S.map[1][CELLP((unsigned)S.pos[1][p.cap[1] - 1 - lane])] = 0;
       #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) S.map[2][CELLP((unsigned)S.gpos[g])] = 0;
       if (keep) {

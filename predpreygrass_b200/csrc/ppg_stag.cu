@@ -24,6 +24,9 @@ namespace ppg {
 
 #define SEL(a) (s == 0 ? a[0] : a[1])
 
+// (1 - p0) ** ratio of the capture law (STAG:1137): CPython's float power = glibc pow, repeated bit for bit (include/ppg_pow.h)
+static __device__ __noinline__ double capture_pow(double base, double exponent) { return ppg_pow(base, exponent); }
+
 template <typename MapT>
 struct StagSmem {
   MapT* map3;         // rabbits (grid channel 3); EnvSmem::map[1] holds the mammoths (channel 2), map[2] the grass
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
                 }
                 ratio = total / difficulty;
                 const double ex = ratio > 0.0 ? ratio : 0.0;
-                const double base_prob = 1.0 - ppg_pow_frac(1.0 - p.p0, ex);
+                const double base_prob = 1.0 - capture_pow(1.0 - p.p0, ex);  // CPython `**` = glibc pow, bit for bit (include/ppg_pow.h)
                 prob = base_prob > p.min_prob ? base_prob : p.min_prob;
                 if (prob > 1.0) prob = 1.0;
                 const bool force = ratio >= p.force_ratio;

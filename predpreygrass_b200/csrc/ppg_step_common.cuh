@@ -409,6 +409,7 @@ __device__ __noinline__ unsigned emit_row_now(unsigned char* base, const StepPar
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(base);
   const RowRel r = load_rel(p, s, sb32, lane);
   emit_row<MapT, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv);
+  __syncwarp();  // every lane's map / table reads are done before the caller un-writes the dying agent's cell
   return rowctr;
 }
 

@@ -14,7 +14,7 @@ def _caps(cfg, keys):
     return tuple(min(sum(cfg.get(k, 0) for k in ks), lim) for ks, lim in zip(keys, (224, 416)))
 
 
-@pytest.mark.parametrize("name", [n for n in golden_cases(("eco",)) if "ghost" not in n])
+@pytest.mark.parametrize("name", golden_cases(("eco",)))
 def test_eco_dict_adapter_replays_reference_episode(name):
     from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
 

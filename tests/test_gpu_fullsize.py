@@ -1,12 +1,35 @@
-"""Size-independent properties at the BASELINE sizes of the evolutionary configs (`-m gpu`): ECO 16 384 envs
-(configs[3]) and one GPU's 8192-env slice of STAG's 65 536 (configs[4]) — too big for the oracle to follow in seconds,
-so the checks are determinism across handles, sharding invariance (two handles with `env_index_base` = one handle with
-all envs: the multi-GPU contract of DESIGN.md §6), row bookkeeping and the own-cell observation."""
+"""The BASELINE sizes (`-m gpu`): ADD 16 384 envs (configs[2]), ECO 16 384 envs (configs[3]) and one GPU's 8192-env slice
+of STAG's 65 536 (configs[4]).
+
+1. Oracle lockstep AT those sizes: 100 steps with every output array compared bit for bit every 10 steps (and at the
+   end), state of sampled envs included — the oracle does ~1.5e6 agent-steps/s on the box's host cores, i.e. 20-40 s
+   per config.
+2. Size-independent properties: determinism across handles, sharding invariance (two handles with `env_index_base` =
+   one handle with all envs: the multi-GPU contract of DESIGN.md §6), row bookkeeping and the own-cell observation."""
+import os
+
 import pytest
 
 from predpreygrass_b200.config import ECO_CONFIG, STAG_CONFIG, VARIANT_ECO, VARIANT_STAG, make_config
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("which", ["add", "eco", "stag"])
+def test_fullsize_oracle_lockstep(which):
+    from predpreygrass_b200.config import BASE_CONFIG
+    from tests.parity import lockstep_parity
+
+    if which == "add":
+        cfg, B = make_config(BASE_CONFIG, reward_mode="additive", cap_live=(32, 128), seed=41), 16384
+    elif which == "eco":
+        cfg, B = make_config(ECO_CONFIG, variant=VARIANT_ECO, cap_live=(32, 96), seed=42), 16384
+    else:
+        # slot capacities 64 + 192: a few envs fill their prey list within 100 steps — the oracle suppresses the same births
+        # and raises the same status bit, so the comparison covers that path too
+        cfg, B = make_config(STAG_CONFIG, variant=VARIANT_STAG, cap_live=(64, 192), seed=43), 8192
+    st = lockstep_parity(cfg, B, 100, state_envs=(0, B // 2, B - 1), check_every=10, threads=os.cpu_count() or 8)
+    assert st["env_steps"] >= 95 * B and st["births_prey"] > 0
 
 
 def _check_rows(h, cfg, B, own_channel):

@@ -1,9 +1,8 @@
 """ECO (eco_evolutionary env) on the GPU vs the CPU oracle and vs the reference's golden trajectories (`-m gpu`).
 
 Everything goes through the C-ABI.  Bit-exact: ids, row layout, flags, positions, float64 energies, ages, genome speeds,
-dead_prey, the drifting active_num_* counters, float32 observations and rewards.  (The device squares the speed for the
-locomotion cost, CPython calls libm pow — they differ by 1 ulp for ~0.08 % of speeds; none of the golden trajectories
-contains such a speed, see tests/test_oracle_golden_eco.py with PPG_ORACLE_POW=square.)"""
+dead_prey, the drifting active_num_* counters, float32 observations and rewards.  The locomotion cost's
+`speed ** exponent` is glibc's pow on both sides: libm in the oracle (as in CPython), include/ppg_pow.h on the device."""
 import numpy as np
 import pytest
 
@@ -68,12 +67,21 @@ def test_eco_slot_overflow_id_pool_and_idle():
     assert st["births_prey"] > 0
 
 
+def test_eco_ghost_cells():
+    """Prey that age out and are bitten under a finite intake cap in the same step leave a stale value on the reference's
+    grid (ECO:826-832 after :1060-1090, removal ECO:332-351 does not zero it); the device carries it as a ghost cell."""
+    cfg = dict(CROWDED, max_agent_age={"predator": None, "prey": 9}, max_energy_gain_per_prey=0.4, max_steps=80,
+               energy_gain_per_step_grass=0.8, prey_creation_energy_threshold=3.0)
+    st = lockstep_parity(eco(cfg, cap_live=(96, 192), seed=17), 256, 100, state_envs=(0, 255))
+    assert st["eaten_prey"] > 0 and st["status_envs"] == 0
+
+
 def test_eco_4096_envs():
     st = lockstep_parity(eco(ECO_CONFIG, cap_live=(64, 128), seed=21), 4096, 80, state_envs=(0, 4095), check_every=4)
     assert st["status_envs"] == 0
 
 
-@pytest.mark.parametrize("name", [n for n in golden_cases(("eco",)) if "ghost" not in n])
+@pytest.mark.parametrize("name", golden_cases(("eco",)))
 def test_eco_golden_trajectories_on_gpu(name):
     """Golden trajectories of the unmodified reference ECO class replayed on the GPU (one env, tape-driven)."""
     import torch

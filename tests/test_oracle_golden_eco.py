@@ -6,11 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle import Oracle
-import os
-
 from tests.helpers import config_from_golden, golden_cases, id_order_rows, load_golden, sha_f32
-
-POW_LIBM = os.environ.get("PPG_ORACLE_POW", "libm") == "libm"
 
 
 @pytest.mark.parametrize("name", golden_cases(("eco",)))
@@ -18,7 +14,6 @@ def test_eco_oracle_replays_reference(name):
     z, cfg = load_golden(name)
     c = config_from_golden(cfg, autoreset=False)
     o = Oracle(c, 1)
-    o.set_pow_libm(POW_LIBM)  # CPython's `speed ** exponent` is libm pow (ECO:563)
     o.load_tape([z["fallback_cells"]], [z["step_reals"]])
     out = o.env_reset_eco(0, z["init_cells"], z["founder_speed"])
     rows = id_order_rows(out)
@@ -70,5 +65,5 @@ def test_eco_oracle_replays_reference(name):
         g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
         ags, agi = o.env_agents(0)
         assert list(ags) == list(z["ag_s"][g0:g1]) and list(agi) == list(z["ag_id"][g0:g1]), (name, t)
-    assert int(out["env_status"][0]) == (0x20 if "ghost" in name else 0)  # PPG_STATUS_GHOST_CELL
+    assert int(out["env_status"][0]) == 0
     o.close()
