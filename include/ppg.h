@@ -65,6 +65,7 @@ enum {
 #define PPG_ROW_FOUNDER 0x08u    /* row produced by reset(), not by step() (BASE:215) */
 #define PPG_ROW_ATE 0x10u        /* member of agents_just_ate (BASE:319,362) */
 #define PPG_ROW_CARCASS 0x20u    /* ECO: member of dead_prey after the step (bitten, not fully eaten; ECO:826-845) */
+#define PPG_ROW_REPRODUCED 0x40u /* the agent had an offspring this step (BASE:396-409; ECO:1161 `agent_offspring_counts[agent] += 1`) */
 
 /* per-env flag bits (ppg_buffers.env_flags), describe the step that just ran */
 #define PPG_ENV_TERMINATED 0x01u /* terminations["__all__"] (BASE:466) */

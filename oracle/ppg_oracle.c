@@ -110,7 +110,7 @@ static void env_free(env_t* e) {
   }
   free(e->agents); free(e->pending); free(e->grid); free(e->gx); free(e->gy); free(e->ge);
   free(e->obs); free(e->rew); free(e->has_rew); free(e->term); free(e->trunc); free(e->has_obs);
-  free(e->ate); free(e->newborn); free(e->e_before); free(e->bonus);
+  free(e->ate); free(e->repro); free(e->newborn); free(e->e_before); free(e->bonus);
 }
 
 static void ensure_rows(env_t* e, int need) {
@@ -124,6 +124,7 @@ static void ensure_rows(env_t* e, int need) {
   e->trunc = (int8_t*)realloc(e->trunc, n);
   e->has_obs = (int8_t*)realloc(e->has_obs, n);
   e->ate = (uint8_t*)realloc(e->ate, n);
+  e->repro = (uint8_t*)realloc(e->repro, n);
   e->newborn = (uint8_t*)realloc(e->newborn, n);
   e->e_before = (double*)realloc(e->e_before, n * sizeof(double));
   e->bonus = (double*)realloc(e->bonus, n * sizeof(double));
@@ -135,7 +136,7 @@ void eco_ensure_rows(env_t* e, int need) { ensure_rows(e, need); }
 
 static void clear_row(env_t* e, int i) {
   e->rew[i] = 0.0; e->has_rew[i] = 0; e->term[i] = -1; e->trunc[i] = -1; e->has_obs[i] = 0;
-  e->ate[i] = 0; e->newborn[i] = 0; e->e_before[i] = 0.0; e->bonus[i] = 0.0;
+  e->ate[i] = 0; e->repro[i] = 0; e->newborn[i] = 0; e->e_before[i] = 0.0; e->bonus[i] = 0.0;
 }
 
 /* reset() from explicit unique cells in the order predators, prey, grass (BASE:179-217) */
@@ -455,6 +456,7 @@ static int env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id
     *G_AT(e, 1 + s, e->x[s][id], e->y[s][id]) = e->energy[s][id]; /* BASE:406 */
     e->cur_num[s] += 1;
     e->rew[ci] = 0.0; e->has_rew[ci] = 1;               /* BASE:408 */
+    e->repro[i] = 1;
     if (mode == PPG_REWARD_DENSE_ADDITIVE) e->bonus[i] = c->reproduction_reward[s]; /* ADD:419 */
     else if (mode != PPG_REWARD_DENSE) { e->rew[i] = c->reproduction_reward[s]; e->has_rew[i] = 1; } /* BASE:409 */
     if (mode == PPG_REWARD_SPARSE_KICKBACK) {           /* KICK:439-449 */
@@ -657,6 +659,7 @@ static void export_rows(ppgo_batch* b) {
       if (v->newborn[i]) fl |= PPG_ROW_NEWBORN;
       if (v->env_flags & PPG_ENV_RESET) fl |= PPG_ROW_FOUNDER;
       if (v->ate[i]) fl |= PPG_ROW_ATE;
+      if (v->repro[i]) fl |= PPG_ROW_REPRODUCED;
       if (v->row_key && v->carcass[i]) fl |= PPG_ROW_CARCASS;
       b->out.f.flags[s][row] = fl;
       b->prev_row[s][(size_t)e * c->n_possible[s] + id] = row;

@@ -91,7 +91,7 @@ static int take_real(env_t* e, double* out) {
 
 static void clear_row(env_t* e, int i) {
   e->rew[i] = 0.0; e->has_rew[i] = 0; e->term[i] = -1; e->trunc[i] = -1; e->has_obs[i] = 0;
-  e->ate[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0;
+  e->ate[i] = 0; e->repro[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0;
 }
 
 /* reset() (ECO:274-293, 123-223, 1733-1792) from explicit cells and founder speeds */
@@ -394,6 +394,7 @@ static void handle_reproduction(env_t* e, int s, int id) {
   e->active[s] += 1;                                   /* ECO:1157 */
   e->rew[ci] = 0.0; e->has_rew[ci] = 1;                /* ECO:1160 */
   e->rew[i] = c->reproduction_reward[s]; e->has_rew[i] = 1; /* ECO:1161 */
+  e->repro[i] = 1;                                     /* ECO:1168 agent_offspring_counts[agent] += 1 */
   capture_obs(e, s, child);                            /* ECO:1179 */
   e->born_obs[ci] = 1;
   e->term[ci] = 0; e->trunc[ci] = 0;

@@ -43,6 +43,7 @@ typedef struct env_t {
   int8_t* trunc;
   int8_t* has_obs;
   uint8_t* ate;    /* agents_just_ate */
+  uint8_t* repro;  /* had an offspring this step (PPG_ROW_REPRODUCED) */
   uint8_t* newborn;
   double* e_before; /* ADD:256 energy_before */
   double* bonus;    /* ADD:261 reproduction_bonus */

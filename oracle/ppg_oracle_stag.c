@@ -86,7 +86,7 @@ static int take_int(env_t* e, int* out) {
 
 static void clear_row(env_t* e, int i) {
   e->rew[i] = 0.0; e->has_rew[i] = 0; e->term[i] = -1; e->trunc[i] = -1; e->has_obs[i] = 0;
-  e->ate[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0;
+  e->ate[i] = 0; e->repro[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0;
 }
 
 static double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); } /* _clip_trait (STAG:1080-1082): min(max(v, 0), 1) */
@@ -492,6 +492,7 @@ static void handle_reproduction(env_t* e, int s, int id) {
   e->active[s] += 1;
   e->rew[ci] = 0.0; e->has_rew[ci] = 1;
   e->rew[i] = c->reproduction_reward_t[s][t]; e->has_rew[i] = 1; /* STAG:1573,1667: overwrites */
+  e->repro[i] = 1;
   e->term[ci] = 0; e->trunc[ci] = 0;
   e->stats[s == 0 ? PPG_STAT_BIRTHS_PRED : PPG_STAT_BIRTHS_PREY]++;
 }

@@ -23,6 +23,7 @@ ENV_TERMINATED, ENV_TRUNCATED, ENV_RESET, ENV_IDLE = 0x01, 0x02, 0x04, 0x08
 STATUS_SLOT_OVERFLOW, STATUS_NO_SPAWN_CELL, STATUS_TAPE_EXHAUSTED, STATUS_BAD_ACTION = 0x01, 0x02, 0x04, 0x08
 STATUS_ID_POOL_EMPTY, STATUS_GHOST_CELL = 0x10, 0x20
 ROW_CARCASS = 0x20
+ROW_REPRODUCED = 0x40
 N_STATS = 16
 STAT_NAMES = [
     "env_steps", "agent_steps", "episodes", "episode_steps", "births_pred", "births_prey", "starved_pred",

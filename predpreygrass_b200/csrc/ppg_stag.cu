@@ -844,6 +844,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               if (f & F_NEWBORN) rf |= PPG_ROW_NEWBORN;
               if (mode == 1) rf |= PPG_ROW_FOUNDER;
               if (f & F_ATE) rf |= PPG_ROW_ATE;
+              if (f & F_REPRO) rf |= PPG_ROW_REPRODUCED;
               if (!(SPLIT && newborn)) {
                 p.row_env[s][row] = env;
                 p.row_agent[s][row] = SEL(S.id)[slot];
