@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 6
+#define PPG_ABI_VERSION 7
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -80,9 +80,9 @@ enum {
 #define PPG_STATUS_TAPE_EXHAUSTED 0x04u /* replay tape ran out; Philox stream used instead */
 #define PPG_STATUS_BAD_ACTION 0x08u     /* action outside the action space (reference: KeyError, BASE:502) */
 #define PPG_STATUS_ID_POOL_EMPTY 0x10u  /* ECO: id pool exhausted, birth suppressed (reference: SystemExit, ECO:1104-1111) */
-#define PPG_STATUS_GHOST_CELL 0x20u     /* ECO: more than 4 stale prey-channel cells at once in one env (a prey that aged out and was
+#define PPG_STATUS_GHOST_CELL 0x20u     /* ECO: more than 16 stale prey-channel cells at once in one env (a prey that aged out and was
                                          * bitten under a finite intake cap in the same step leaves its grid value behind, ECO:826-832
-                                         * after :1060-1090; the device carries up to 4 such ghost cells per env, ppg_eco.cu) */
+                                         * after :1060-1090; the device carries up to 16 such ghost cells per env, ppg_eco.cu) */
 
 /* error codes */
 #define PPG_OK 0
@@ -133,7 +133,9 @@ typedef struct ppg_config {
   int32_t carcass_only_predator_age; /* "carcass_only_predator_age"["predator"], -1 = None (ECO:65-72,1060-1090) */
   int32_t slow_max_move_distance; /* ECO:110 */
   int32_t fast_max_move_distance; /* ECO:111 */
-  int32_t reserved1[2];
+  int32_t track_episode_sums;     /* 1: keep per-episode totals of distance moved / locomotion energy per species on the device
+                                   * (the inputs of `_build_episode_training_metrics`, ECO:1613-1661; read by ppg_read_episode_eco) */
+  int32_t reserved1;
   double move_cost_per_cell[2];   /* "movement_energy_cost_per_cell_*" (ECO:78-79,565-573) */
   double move_speed_cost_exponent;/* "movement_speed_cost_exponent" (ECO:80,559-563) */
   double max_energy_grass;        /* "max_energy_grass": regrowth cap (ECO:83,618-626) */
@@ -182,7 +184,35 @@ typedef struct ppg_config {
   double season_multiplier[2];
   int32_t season_length_steps;         /* "season_length_steps" (SEASON:64) */
   int32_t reserved2;
+  /* ---- the other heritable-trait variants of eco_evolutionary (variant == PPG_VARIANT_ECO, trait_mode != PPG_TRAIT_SPEED).
+   * MR   = predpreygrass/evolutionary/eco_evolutionary_metabolic_rate/predpreygrass_rllib_env.py
+   * INV  = .../eco_evolutionary_investment/predpreygrass_rllib_env.py
+   * COOP = .../eco_evolutionary_cooperation/predpreygrass_rllib_env.py
+   * CAD  = .../eco_evolutionary_cadence/predpreygrass_rllib_env.py
+   * They share ECO's skeleton (same step order, id allocation, spawn rule, mutation law, output assembly) and re-use
+   * the ECO fields above for what they have in common: the ONE heritable trait lives where the speed does
+   * (founder_speed_mean/std = "<trait>_mean"/"<trait>_std", speed_bounds = "trait_bounds"[<trait>], mutation_rate/std),
+   * energy_loss = "basal_energy_cost_*" (MR, COOP) / "energy_loss_per_step_*" (INV, CAD), initial_energy =
+   * "initial_energy_*" (MR, COOP, CAD) / "initial_energy_*_at_reset" (INV), max_energy_gain_per_prey (MR:64, INV). ---- */
+  int32_t trait_mode;            /* PPG_TRAIT_* */
+  int32_t n_initial_min[2];      /* MR:74-81 "n_initial_active_predators_min" / "_prey_min": founders of an episode ~ U{min..n_initial}
+                                  * (MR:189-192, two `rng.integers` draws per reset, predators first) */
+  int32_t satiation_cooldown;    /* "predator_satiation_cooldown" (MR:63,734-740,756-757; INV), 0 = off */
+  int32_t cooperation_range;     /* "cooperation_range" (COOP:93,556-565): Chebyshev radius of meal sharing */
+  int32_t max_cooldown;          /* "max_cooldown" (CAD:116,556-571): slowest agents move every max_cooldown-th step */
+  double trait_alpha;            /* "metabolic_rate_alpha" (MR:102,751,807): gain = food * rate ** alpha */
+  double repro_max_ratio;        /* "predator_reproduction_max_ratio" (MR:60,843-854), < 0 = None */
+  double metabolic_speed_coeff;  /* "metabolic_speed_coeff" (CAD:79,626-633): decay *= 1 + coeff * speed */
 } ppg_config;
+
+/* ppg_config.trait_mode: which heritable trait the ECO-family handle carries */
+enum {
+  PPG_TRAIT_SPEED = 0,       /* ECO: speed gates the move distance (ECO:551-557) */
+  PPG_TRAIT_METABOLIC = 1,   /* MR: metabolic_rate scales the basal cost linearly and every energy gain by rate ** alpha */
+  PPG_TRAIT_INVESTMENT = 2,  /* INV: offspring_investment_fraction of the parent's energy goes to each child (INV:546-557,890,977) */
+  PPG_TRAIT_COOPERATION = 3, /* COOP: cooperation_rate of every meal is shared with same-species neighbours (COOP:537-589) */
+  PPG_TRAIT_CADENCE = 4      /* CAD: speed sets the move RATE through an accumulator; action mask in the observation */
+};
 
 /* ppg_config.team_capture_success_model (STAG:1141-1148) */
 enum { PPG_CAPTURE_DETERMINISTIC = 0, PPG_CAPTURE_PROBABILISTIC = 1, PPG_CAPTURE_HYBRID = 2 };
@@ -342,6 +372,13 @@ int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, 
  * active_num_predators/prey), in the list order of ppg_read_env.  Any pointer may be NULL. Synchronises. */
 int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                      double* speed_prey, uint8_t* dead_prey, int32_t* active_num);
+
+/* ECO per-episode totals of one env for `_build_episode_training_metrics` (ECO:1613-1661), valid with
+ * ppg_config.track_episode_sums: sums[4] = distance moved by all predators / all prey of the running episode (the sum of
+ * record["distance_traveled"] over the species' agent records, ECO:659), locomotion energy spent likewise
+ * (record["movement_energy_spent"], ECO:660); spawned[2] = agents born so far per species (= the sum of
+ * record["offspring_count"], ECO:1168,1262; the species' record count is founders + spawned).  Synchronises. */
+int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawned);
 
 /* STAG extras of one env (STAG attributes agent_ages, predator_facing as an index into `_predator_facing_options`
  * STAG:197-206, predator_cooperation_trait), in the list order of ppg_read_env, plus the team-capture counters

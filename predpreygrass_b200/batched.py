@@ -286,6 +286,13 @@ class BatchedPredPreyGrass:
         st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]], active_num=act)
         return st
 
+    def read_episode_eco(self, env):
+        """per-episode totals of one ECO env (include/ppg.h ppg_read_episode_eco; needs make_config(track_episode_sums=True)):
+        -> {"distance": (pred, prey), "move_energy": (pred, prey), "spawned": (pred, prey)}"""
+        sums, sp = np.zeros(4, np.float64), np.zeros(2, np.int32)
+        _lib.check(self.L.ppg_read_episode_eco(self.h, env, sums.ctypes.data, sp.ctypes.data), self.h)
+        return {"distance": (float(sums[0]), float(sums[1])), "move_energy": (float(sums[2]), float(sums[3])), "spawned": (int(sp[0]), int(sp[1]))}
+
     def read_env_stag(self, env):
         """read_env (lists in `self.agents` insertion order) plus the STAG attributes agent_ages, predator_facing (index into
         `_predator_facing_options`, STAG:197-206), predator_cooperation_trait and the team-capture counters (STAG:237-254)."""

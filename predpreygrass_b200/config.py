@@ -69,7 +69,8 @@ class PpgConfig(C.Structure):
         ("carcass_only_predator_age", C.c_int32),
         ("slow_max_move_distance", C.c_int32),
         ("fast_max_move_distance", C.c_int32),
-        ("reserved1", C.c_int32 * 2),
+        ("track_episode_sums", C.c_int32),
+        ("reserved1", C.c_int32),
         ("move_cost_per_cell", C.c_double * 2),
         ("move_speed_cost_exponent", C.c_double),
         ("max_energy_grass", C.c_double),
@@ -109,6 +110,15 @@ class PpgConfig(C.Structure):
         ("season_multiplier", C.c_double * 2),
         ("season_length_steps", C.c_int32),
         ("reserved2", C.c_int32),
+        # ---- trait variants of eco_evolutionary ----
+        ("trait_mode", C.c_int32),
+        ("n_initial_min", C.c_int32 * 2),
+        ("satiation_cooldown", C.c_int32),
+        ("cooperation_range", C.c_int32),
+        ("max_cooldown", C.c_int32),
+        ("trait_alpha", C.c_double),
+        ("repro_max_ratio", C.c_double),
+        ("metabolic_speed_coeff", C.c_double),
     ]
 
 
@@ -146,8 +156,12 @@ def _round32(n):
     return max(32, (int(n) + 31) // 32 * 32)
 
 
+TRAITS = {"speed": 0, "metabolic_rate": 1, "offspring_investment_fraction": 2, "cooperation_rate": 3, "cadence": 4}
+TRAIT_SPEED, TRAIT_METABOLIC, TRAIT_INVESTMENT, TRAIT_COOPERATION, TRAIT_CADENCE = 0, 1, 2, 3, 4
+
+
 def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_live=None, autoreset=True, seed=0,
-                env_index_base=0):
+                env_index_base=0, track_episode_sums=False, trait=None):
     """Flatten a reference `config_env` dict (missing keys take the reference's own defaults,
     BASE:22-61) into a PpgConfig."""
     cfg = dict(config or {})
@@ -213,8 +227,18 @@ def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_
             raise ValueError("season_length_steps must be positive (SEASON:232 divides by it)")
         c.season_multiplier[0] = float(g("season_high_multiplier", 1.5))
         c.season_multiplier[1] = float(g("season_low_multiplier", 0.5))
+    c.n_initial_min[0], c.n_initial_min[1] = c.n_initial[0], c.n_initial[1]
+    c.repro_max_ratio = -1.0
+    c.trait_alpha = 1.0
     if variant == VARIANT_ECO:
-        _fill_eco(c, cfg)
+        trait = cfg.get("ppg_trait", "speed") if trait is None else trait
+        if trait not in TRAITS:
+            raise ValueError(f"unknown trait variant {trait!r}")
+        if TRAITS[trait] == TRAIT_SPEED:
+            _fill_eco(c, cfg)
+        else:
+            _fill_trait(c, cfg, trait)
+        c.track_episode_sums = 1 if track_episode_sums else 0
     if variant == VARIANT_STAG:
         _fill_stag(c, cfg, cap_live_given)
     return c
@@ -275,6 +299,84 @@ def _fill_eco(c, cfg):
     lin = cfg.get("lineage_reward_coeff", 0.0)
     if any(float(_role(lin, r, 0.0) or 0.0) != 0.0 for r in ("predator", "prey")):
         raise ValueError("lineage_reward_coeff != 0 is not supported (ECO:943-991 lineage survival rewards)")
+
+
+def _fill_trait(c, cfg, trait):
+    """`_initialize_from_config` of the other trait variants (MR:38-114, INV:38-114, COOP:38-98; mandatory keys are read
+    with `cfg[...]` exactly where the reference does, so a missing one raises KeyError here as well)."""
+    g = cfg.get
+    mode = TRAITS[trait]
+    if mode == TRAIT_CADENCE:
+        raise ValueError("the cadence variant is not built yet")
+    c.trait_mode = mode
+    c.max_steps = cfg["max_steps"]
+    c.n_initial[0] = cfg["n_initial_active_predators"]
+    c.n_initial[1] = cfg["n_initial_active_prey"]
+    # MR:74-81: ~33 % of the maximum unless configured; MR:189-190 clamps to the maximum
+    c.n_initial_min[0] = min(int(g("n_initial_active_predators_min", max(1, c.n_initial[0] // 3))), c.n_initial[0])
+    c.n_initial_min[1] = min(int(g("n_initial_active_prey_min", max(1, c.n_initial[1] // 3))), c.n_initial[1])
+    if c.n_initial_min[0] < 0 or c.n_initial_min[1] < 0:
+        raise ValueError("n_initial_active_*_min must be >= 0")
+    c.n_possible[0], c.n_possible[1] = cfg["n_possible_predators"], cfg["n_possible_prey"]
+    c.grid_size = cfg["grid_size"]
+    c.num_obs_channels = cfg["num_obs_channels"]
+    c.obs_range[0], c.obs_range[1] = cfg["predator_obs_range"], cfg["prey_obs_range"]
+    c.n_grass = cfg["initial_num_grass"]
+    c.initial_energy_grass = cfg["initial_energy_grass"]
+    c.energy_gain_grass = cfg["energy_gain_per_step_grass"]
+    c.max_energy_grass = float(cfg["max_energy_grass"])
+    c.action_range = cfg["action_range"]
+    c.genome_enabled = 1 if g("genome_enabled", True) else 0
+    c.include_speed_in_obs = 0
+    c.max_agent_age[0] = c.max_agent_age[1] = -1   # ages are counted (MR:570) but nothing expires
+    c.carcass_only_predator_age = -1
+    d = (int(c.action_range) - 1) // 2
+    c.slow_max_move_distance = c.fast_max_move_distance = max(d, 0)  # no distance gating: `_get_move` (MR:590-614) has none
+    c.move_cost_per_cell[0] = float(g("movement_energy_cost_per_cell_predator", 0.0))
+    c.move_cost_per_cell[1] = float(g("movement_energy_cost_per_cell_prey", 0.0))
+    c.move_speed_cost_exponent = 1.0
+    c.max_energy_gain_per_grass = float("inf")
+    if mode == TRAIT_INVESTMENT:
+        c.energy_loss[0], c.energy_loss[1] = cfg["energy_loss_per_step_predator"], cfg["energy_loss_per_step_prey"]
+        c.initial_energy[0], c.initial_energy[1] = cfg["initial_energy_predator_at_reset"], cfg["initial_energy_prey_at_reset"]
+    else:
+        c.energy_loss[0], c.energy_loss[1] = cfg["basal_energy_cost_predator"], cfg["basal_energy_cost_prey"]
+        c.initial_energy[0], c.initial_energy[1] = cfg["initial_energy_predator"], cfg["initial_energy_prey"]
+    c.creation_threshold[0] = cfg["predator_creation_energy_threshold"]
+    c.creation_threshold[1] = cfg["prey_creation_energy_threshold"]
+    if mode in (TRAIT_METABOLIC, TRAIT_INVESTMENT):
+        c.satiation_cooldown = int(g("predator_satiation_cooldown", 0))
+        c.max_energy_gain_per_prey = float(g("max_energy_gain_per_prey", float("inf")))
+        if not 0 <= c.satiation_cooldown <= 250:
+            raise ValueError("predator_satiation_cooldown must be in [0, 250]")
+    else:
+        c.satiation_cooldown = 0
+        c.max_energy_gain_per_prey = float("inf")   # COOP:777: the whole prey
+    if mode == TRAIT_METABOLIC:
+        c.trait_alpha = float(g("metabolic_rate_alpha", 0.7))
+        r = g("predator_reproduction_max_ratio", None)
+        c.repro_max_ratio = -1.0 if r is None else float(r)
+        if r is not None and float(r) < 0:
+            raise ValueError("predator_reproduction_max_ratio must be >= 0 or None")
+    if mode == TRAIT_COOPERATION:
+        c.cooperation_range = int(g("cooperation_range", 2))
+    if g("genome_neutral_drift_control", False):
+        raise ValueError("genome_neutral_drift_control (the neutral-drift null model, MR:108-114) is not supported")
+    default_mean = {TRAIT_METABOLIC: 1.0, TRAIT_INVESTMENT: 0.35, TRAIT_COOPERATION: 0.0}[mode]
+    default_bounds = {TRAIT_METABOLIC: (0.5, 2.0), TRAIT_INVESTMENT: (0.10, 0.80), TRAIT_COOPERATION: (0.0, 1.0)}[mode]
+    for s, role in enumerate(("predator", "prey")):
+        f = g("founder_genome", {}).get(role, {})
+        c.founder_speed_mean[s] = float(f.get(f"{trait}_mean", default_mean))
+        c.founder_speed_std[s] = float(f.get(f"{trait}_std", 0.0))
+    m = g("genome_mutation", {})
+    c.mutation_rate, c.mutation_std = float(m.get("rate", 0.0)), float(m.get("std", 0.0))
+    b = g("trait_bounds", {}).get(trait, default_bounds)
+    c.speed_bounds[0], c.speed_bounds[1] = float(b[0]), float(b[1])
+    c.speed_distance_threshold = float("inf")
+    c.reward_predator_catch_prey = c.reward_prey_eat_grass = c.reward_predator_step = c.reward_prey_step = 0.0
+    c.penalty_prey_caught = 0.0
+    c.reproduction_reward[0] = float(_role(cfg["reproduction_reward_predator"], "predator", 0.0))
+    c.reproduction_reward[1] = float(_role(cfg["reproduction_reward_prey"], "prey", 0.0))
 
 
 CAPTURE_MODELS = {"deterministic": 0, "probabilistic": 1, "hybrid": 2}
@@ -515,5 +617,35 @@ STAG_CONFIG = {
 }
 
 
-# the other heritable-trait variants of eco_evolutionary (filled below the ECO defaults they derive from)
-TRAIT_CONFIGS = {}
+# default config_env of the other heritable-trait variants (the reference's config/config_env_eco_evolutionary.py of each)
+_TRAIT_COMMON = {
+    "seed": 41, "max_steps": 1000, "grid_size": 25, "num_obs_channels": 3, "predator_obs_range": 7, "prey_obs_range": 9,
+    "action_range": 3, "reproduction_reward_predator": {"predator": 10.0}, "reproduction_reward_prey": {"prey": 10.0},
+    "movement_energy_cost_per_cell_predator": 0.0, "movement_energy_cost_per_cell_prey": 0.0,
+    "predator_creation_energy_threshold": 12.0, "prey_creation_energy_threshold": 8.0, "genome_enabled": True,
+    "genome_mutation": {"rate": 0.05, "std": 0.04}, "max_energy_grass": 2.0, "n_possible_prey": 1000,
+    "n_initial_active_predators": 6, "n_initial_active_prey": 8, "initial_num_grass": 100, "initial_energy_grass": 2.0,
+    "energy_gain_per_step_grass": 0.04, "debug_mode": False,
+}
+METABOLIC_CONFIG = dict(  # eco_evolutionary_metabolic_rate/config/config_env_eco_evolutionary.py
+    _TRAIT_COMMON, ppg_trait="metabolic_rate", basal_energy_cost_predator=0.15, basal_energy_cost_prey=0.05,
+    predator_reproduction_max_ratio=None, predator_satiation_cooldown=8, max_energy_gain_per_prey=8.0,
+    initial_energy_predator=5.0, initial_energy_prey=3.0, genome_neutral_drift_control=False,
+    founder_genome={"predator": {"metabolic_rate_mean": 1.0, "metabolic_rate_std": 0.10},
+                    "prey": {"metabolic_rate_mean": 1.0, "metabolic_rate_std": 0.10}},
+    trait_bounds={"metabolic_rate": (0.5, 2.0)}, metabolic_rate_alpha=0.4, n_possible_predators=500)
+INVESTMENT_CONFIG = dict(  # eco_evolutionary_investment/config/config_env_eco_evolutionary.py
+    _TRAIT_COMMON, ppg_trait="offspring_investment_fraction", energy_loss_per_step_predator=0.15, energy_loss_per_step_prey=0.05,
+    initial_energy_predator_at_reset=5.0, initial_energy_prey_at_reset=3.0, predator_satiation_cooldown=8,
+    max_energy_gain_per_prey=8.0,
+    founder_genome={"predator": {"offspring_investment_fraction_mean": 0.35, "offspring_investment_fraction_std": 0.08},
+                    "prey": {"offspring_investment_fraction_mean": 0.35, "offspring_investment_fraction_std": 0.08}},
+    trait_bounds={"offspring_investment_fraction": (0.10, 0.80)}, n_possible_predators=200,
+    verbose_engagement=False, verbose_movement=False, verbose_decay=False, verbose_reproduction=False)
+COOPERATION_CONFIG = dict(  # eco_evolutionary_cooperation/config/config_env_eco_evolutionary.py
+    _TRAIT_COMMON, ppg_trait="cooperation_rate", basal_energy_cost_predator=0.15, basal_energy_cost_prey=0.05,
+    initial_energy_predator=5.0, initial_energy_prey=3.0,
+    founder_genome={"predator": {"cooperation_rate_mean": 0.0, "cooperation_rate_std": 0.05},
+                    "prey": {"cooperation_rate_mean": 0.0, "cooperation_rate_std": 0.05}},
+    trait_bounds={"cooperation_rate": (0.0, 1.0)}, cooperation_range=2, n_possible_predators=500)
+TRAIT_CONFIGS = {"metabolic": METABOLIC_CONFIG, "investment": INVESTMENT_CONFIG, "cooperation": COOPERATION_CONFIG}

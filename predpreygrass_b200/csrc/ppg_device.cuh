@@ -80,7 +80,7 @@ enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_
 #define DSC_ZERO 0xFFFEu  // STAG: ended agents are observed as all-zero rows
 #define DSC_COPY 0xFFFDu  // ECO: the row was captured at birth into born_obs[env][dsx] (episode ended on this step, ECO:417-420)
 #define PPG_BORN_K 4      // at-birth rows kept per env and species; further ones take the (blocking) direct path
-#define PPG_MAX_GHOSTS 4  // ECO: stale prey-channel cells carried per env (ppg_eco.cu header); more raise PPG_STATUS_GHOST_CELL
+#define PPG_MAX_GHOSTS 16 // ECO: stale prey-channel cells carried per env (ppg_eco.cu header); more raise PPG_STATUS_GHOST_CELL
 
 struct StepParams {
   // ---- config ----
@@ -161,6 +161,7 @@ struct StepParams {
   uint16_t* ag_seq[2];
   double* ag_spd[2];
   uint8_t* ag_dead[2];
+  double* ep_sums;     // [B][4] optional (ppg_config.track_episode_sums): per-episode distance moved [2], locomotion energy [2]
   uint8_t* gh_n;       // [B] ghost cells of the env (ppg_eco.cu header)
   uint16_t* gh_cell;   // [B][PPG_MAX_GHOSTS] packed position x << 8 | y
   float* gh_val;       // [B][PPG_MAX_GHOSTS] the stale float32 grid value

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     unsigned st_starved[2] = {0, 0}, st_eaten = 0, st_grass = 0, st_fallback = 0;
     bool over = false, trunc = false, done = false, have_new_base = false;
     int n_gh = 0;  // ghost cells loaded into the pseudo-slots cap[1]-1, cap[1]-2, ...
+    double ep_dist[2] = {0.0, 0.0}, ep_cost[2] = {0.0, 0.0};  // this step's distance moved / locomotion energy per species (per lane)
 
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
@@ -401,8 +402,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
               const double sp = SEL(X.spd)[j];
               const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
-              SEL(S.E)[j] = SEL(S.E)[j] - p.move_cost[s] * sqrt((double)d2) * fac;
+              const double dist = sqrt((double)d2), cost = p.move_cost[s] * dist * fac;
+              SEL(S.E)[j] = SEL(S.E)[j] - cost;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
+              if (p.ep_sums) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
             }
             own[oc] = 0;              // ECO:653,657
             own[nc] = (MapT)(j + 1);  // ECO:654,658
@@ -428,7 +431,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             double e = SEL(S.E)[jj];
             if (dd > 0) {
               const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
-              e = e - p.move_cost[s] * sqrt((double)dd) * fac;
+              const double dist = sqrt((double)dd), cost = p.move_cost[s] * dist * fac;
+              e = e - cost;
+              if (p.ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
             }
             __syncwarp();
             if (lane == 0) {  // one writer: the two map stores may hit the same cell (blocked move) and must keep their order
@@ -867,6 +872,20 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         for (int g = lane; g < p.n_grass; g += 32) {
           p.gr_e[gb + g] = S.gE[g];
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
+        }
+      }
+      if (p.ep_sums) {
+        // per-episode totals behind `_build_episode_training_metrics` (ECO:1613-1661): distance moved and locomotion energy of
+        // all agents of a species (record["distance_traveled"], record["movement_energy_spent"], ECO:659-660)
+        double v[4] = {ep_dist[0], ep_dist[1], ep_cost[0], ep_cost[1]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], d);
+        if (lane < 4) {
+          double* dst = p.ep_sums + (size_t)env * 4 + lane;
+          const double add = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
+          *dst = mode == 1 ? 0.0 : *dst + add;
         }
       }
       if (over) h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;

@@ -116,7 +116,7 @@ class _RowDictEnv(_Base):
 
         self.config = config
         self._cfg = make_config(config, variant=self._variant, cap_live=config.get("cap_live"), autoreset=False,
-                                seed=config.get("seed") or 0)
+                                seed=config.get("seed") or 0, track_episode_sums=self._variant == VARIANT_ECO)
         self._batch = BatchedPredPreyGrass(self._cfg, 1, device=config.get("cuda_device", 0))
         self.max_steps = config["max_steps"] if self._variant == VARIANT_ECO else config.get("max_steps", 0)  # ECO:43, STAG:127
         self.grid_size = self._cfg.grid_size
@@ -317,6 +317,12 @@ class PredPreyGrassEco(_RowDictEnv):
         out = self._reset_device(seed, cells, speeds, options)
         obs, *_ = self._dicts(out)
         self.agents = list(obs)
+        # genome speeds of every agent of the episode, founders first (the records `_build_episode_training_metrics` walks)
+        self._episode_speeds = ([], [])
+        if self.genome_enabled:
+            st = self._read()
+            for s in range(2):
+                self._episode_speeds[s].extend(float(v) for v in st["speed"][s])
         return obs, {}
 
     def _dicts(self, out):
@@ -338,6 +344,13 @@ class PredPreyGrassEco(_RowDictEnv):
         out = self._step_device(action_dict)
         obs, rew, term, trunc = self._dicts(out)
         flags = int(out["env_flags"][0])
+        if self.genome_enabled and (int(out["new_cnt0"][0]) or int(out["new_cnt1"][0])):
+            st = self._read()  # newborns join the episode's agent records with their (mutated) genome
+            by_id = [dict(zip(st["ids"][s].tolist(), st["speed"][s].tolist())) for s in range(2)]
+            for s in range(2):
+                r0 = int(out[f"new_off{s}"][0])
+                for r in range(r0, r0 + int(out[f"new_cnt{s}"][0])):
+                    self._episode_speeds[s].append(float(by_id[s][int(out[f"row_agent{s}"][r])]))
         infos = {a: {} for a in rew}
         term["__all__"] = bool(flags & ENV_TERMINATED)   # ECO:392,408 extinction
         trunc["__all__"] = bool(flags & ENV_TRUNCATED)   # ECO:452-486 time limit, same call
@@ -345,7 +358,7 @@ class PredPreyGrassEco(_RowDictEnv):
             self._done = True
             self.agents = []  # ECO:495,500-501
             self._rows = {}
-            infos["__all__"] = {"training_metrics": self.live_speed_metrics()}
+            infos["__all__"] = {"training_metrics": self.episode_training_metrics()}  # ECO:1663-1668, 485
         else:
             # `self.agents` keeps insertion order: survivors, then this step's newborns, predators first (ECO:353-367)
             prev = set(self.agents)
@@ -371,6 +384,33 @@ class PredPreyGrassEco(_RowDictEnv):
     def dead_prey(self):
         st = self._read()
         return {self._name(1, int(i)) for i, d in zip(st["ids"][1], st["dead_prey"]) if d}
+
+    def episode_training_metrics(self):
+        """`_build_episode_training_metrics` (ECO:1613-1661), same keys: over ALL agent records of the episode (alive or
+        not) the speed distribution, and the per-agent means of distance travelled, locomotion energy spent and offspring
+        count.  The totals come from the device (ppg_read_episode_eco); a mean over records is total / record count."""
+        ep = self._batch.read_episode_eco(0)
+        res = {}
+        thr = float(self.speed_distance_threshold)
+        for s, role in enumerate(("predator", "prey")):
+            v = np.asarray(self._episode_speeds[s], np.float64)
+            if v.size:
+                p25, p50, p75 = np.percentile(v, [25, 50, 75])
+                vals = (float(np.mean(v)), float(np.std(v)), float(p25), float(p50), float(p75), float(np.mean(v >= thr)))
+            else:
+                vals = (0.0,) * 6
+            for key, x in zip(("speed_mean", "speed_std", "speed_p25", "speed_p50", "speed_p75", "fraction_fast"), vals):
+                res[f"{role}_{key}"] = x
+            count = int(self._cfg.n_initial[s]) + ep["spawned"][s]
+            if count:
+                res[f"{role}_distance_traveled_mean"] = ep["distance"][s] / count
+                res[f"{role}_movement_energy_spent_mean"] = ep["move_energy"][s] / count
+                res[f"{role}_offspring_count_mean"] = ep["spawned"][s] / count
+                res[f"{role}_agent_count"] = float(count)
+            else:
+                for key in ("distance_traveled_mean", "movement_energy_spent_mean", "offspring_count_mean", "agent_count"):
+                    res[f"{role}_{key}"] = 0.0
+        return res
 
     def live_speed_metrics(self):
         """`_build_live_speed_metrics` (ECO:509-539): speed distribution of the live population, same keys"""

@@ -2,10 +2,13 @@
 episodes recorded from the unmodified reference classes through that same API (`-m gpu`).  reset(seed) uses the
 adapter's own host-side reproduction of the reference's reset draws; the draws after the reset (mutation, spawn
 fallback, capture success) are the reference's recorded ones (`options={"ppg_tape": ...}`)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
-from tests.helpers import golden_cases, load_golden, sha_f32
+from tests.helpers import GOLDEN_DIR, golden_cases, load_golden, sha_f32
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +52,17 @@ def test_eco_dict_adapter_replays_reference_episode(name):
         assert env.current_step == int(z["steps"][t])
         if term["__all__"] or trunc["__all__"]:
             assert env.agents == []
+            # infos["__all__"]["training_metrics"] = `_build_episode_training_metrics` (ECO:1613-1668) of the reference's own run
+            # of this episode (tests/golden/make_golden_eco_metrics.py): same keys in the same order; counts exact, the
+            # float means to 1e-9 (the device keeps per-species totals, the reference averages per-agent sums)
+            want = json.load(open(os.path.join(GOLDEN_DIR, "eco_training_metrics.json")))[name]
+            got = infos["__all__"]["training_metrics"]
+            assert sorted(got) == sorted(want), (name, sorted(set(got) ^ set(want)))
+            for k, v in want.items():
+                if k.endswith("_count") or k.endswith("_fraction_fast") or "_speed_" in k:
+                    assert got[k] == pytest.approx(v, rel=1e-12, abs=0.0), (name, k, got[k], v)
+                else:
+                    assert got[k] == pytest.approx(v, rel=1e-9, abs=1e-12), (name, k, got[k], v)
             break
         g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
         assert env.agents == [key(s, i) for s, i in zip(z["ag_s"][g0:g1], z["ag_id"][g0:g1])], (name, t)
@@ -132,8 +146,8 @@ def test_stag_dict_adapter_replays_reference_episode(name):
 
 def test_eco_adapter_time_limit_reports_training_metrics():
     """reference test_time_limit_truncates_with_final_bootstrap_observations (eco tests :296-329) through the dict API:
-    max_steps = 1 -> everybody truncated, `agents` cleared, `infos["__all__"]["training_metrics"]` carries the speed
-    distribution keys of `_build_live_speed_metrics` (ECO:509-539)"""
+    max_steps = 1 -> everybody truncated, `agents` cleared, `infos["__all__"]["training_metrics"]` carries the keys of
+    `_build_episode_training_metrics` (ECO:1613-1661), the ones `utils/episode_return_callback.py:9-80` reads"""
     from predpreygrass_b200.config import ECO_CONFIG
     from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
 
@@ -149,7 +163,10 @@ def test_eco_adapter_time_limit_reports_training_metrics():
     assert all(trunc[a] and not term[a] for a in obs) and trunc["__all__"] and not term["__all__"]
     assert env.agents == []
     m = infos["__all__"]["training_metrics"]
-    for k in ("predator_speed_mean", "prey_speed_mean", "predator_fraction_fast", "prey_speed_p50", "predator_count"):
-        assert k in m
-    assert m["predator_count"] == 1.0 and 0.5 <= m["predator_speed_mean"] <= 2.0
+    for role in ("predator", "prey"):
+        for k in ("speed_mean", "speed_std", "speed_p25", "speed_p50", "speed_p75", "fraction_fast", "distance_traveled_mean",
+                  "movement_energy_spent_mean", "offspring_count_mean", "agent_count"):
+            assert f"{role}_{k}" in m
+    assert len(m) == 20 and m["predator_agent_count"] == 1.0 and 0.5 <= m["predator_speed_mean"] <= 2.0
+    assert m["prey_distance_traveled_mean"] == 0.0 and m["prey_offspring_count_mean"] == 0.0
     env.close()
