@@ -92,7 +92,7 @@ def workload_name(args):
         name = {"eco": "eco_evolutionary", "cadence": "eco_evolutionary_cadence", "metabolic": "eco_evolutionary_metabolic_rate",
                 "investment": "eco_evolutionary_investment", "cooperation": "eco_evolutionary_cooperation"}[args.variant]
         return (f"{name} default config_env{' + reproduction-heavy override' if args.eco_rich else ''}, {args.envs} envs per GPU, "
-                f"uniform random actions (25), auto-reset, Philox trait/mutation draws, {pre}")
+                f"uniform random actions ({n_actions(args)}), auto-reset, Philox trait/mutation draws, {pre}")
     name = "base_environment_seasonal" if getattr(args, "seasonal", False) else "base_environment"
     return f"{name} default config_env, {args.envs} envs per GPU, uniform random actions, auto-reset, reward={args.reward_mode}, {pre}"
 
@@ -122,7 +122,7 @@ def build_config(args, **kw):
 
 
 def n_actions(args):
-    return 25 if args.variant in ECO_FAMILY else 9
+    return 25 if args.variant in ("eco", "cadence") else 9  # the other trait variants have action_range 3 (MR:203-210)
 
 
 def action_pools(args, n, rng):

@@ -24,6 +24,7 @@
 #define PPG_STREAM_TRAIT 2u     /* founder / offspring trait draws (ECO, STAG) */
 #define PPG_STREAM_CAPTURE 3u   /* STAG capture success draw */
 #define PPG_STREAM_FACING 4u    /* STAG predator facing (founders, newborns) */
+#define PPG_STREAM_FOUNDERS 5u  /* trait variants: number of founders of an episode (MR:189-192) */
 #define PPG_STREAM_ACTION 7u    /* ppg_random_actions */
 
 typedef struct ppg_u32x4 {

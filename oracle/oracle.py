@@ -53,6 +53,7 @@ def lib():
         L.ppgo_env_agents.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
+        L.ppgo_env_reset_trait.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
@@ -126,6 +127,12 @@ class Oracle:
         c = np.ascontiguousarray(cells, np.int32)
         sp = np.ascontiguousarray(founder_speed if len(founder_speed) else [0.0], np.float64)
         assert lib().ppgo_env_reset_eco(self.h, env, c.ctypes.data, sp.ctypes.data) == 0
+        return self.outputs()
+
+    def env_reset_trait(self, env, n_pred, n_prey, cells, founder_trait):
+        c = np.ascontiguousarray(cells, np.int32)
+        sp = np.ascontiguousarray(founder_trait if len(founder_trait) else [0.0], np.float64)
+        assert lib().ppgo_env_reset_trait(self.h, env, int(n_pred), int(n_prey), c.ctypes.data, sp.ctypes.data) == 0
         return self.outputs()
 
     def read_env_eco(self, env):

@@ -858,6 +858,19 @@ int ppgo_env_reset_eco(ppgo_batch* b, int32_t env, const int32_t* cells, const d
   return PPG_OK;
 }
 
+/* trait variants: reset one env with an explicit number of founders (MR:189-192), cells and founder traits */
+int ppgo_env_reset_trait(ppgo_batch* b, int32_t env, int32_t n_pred, int32_t n_prey, const int32_t* cells, const double* founder_trait) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO || b->cfg.trait_mode == PPG_TRAIT_SPEED) return PPG_ERR_INVALID;
+  if (n_pred < 0 || n_pred > b->cfg.n_initial[0] || n_prey < 0 || n_prey > b->cfg.n_initial[1]) return PPG_ERR_INVALID;
+  for (int e = 0; e < b->n_envs; ++e) if (e != env) b->envs[e].n_rows = 0;
+  b->envs[env].episode += 1;
+  b->envs[env].trait_draws = 0;
+  b->envs[env].n_found[0] = n_pred; b->envs[env].n_found[1] = n_prey;
+  eco_env_reset_explicit(&b->envs[env], cells, founder_trait);
+  export_rows(b);
+  return PPG_OK;
+}
+
 int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                       double* speed_prey, uint8_t* dead_prey, int32_t* active_num) {
   if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;

@@ -16,6 +16,14 @@
  *
  * Pinned against golden trajectories recorded from the unmodified reference
  * (tests/golden/make_golden_eco.py -> tests/golden/eco_*.npz, tests/test_oracle_golden_eco.py).
+ *
+ * The same file restates the sibling trait variants, which share ECO's skeleton (ppg_config.trait_mode):
+ *   MR   = predpreygrass/evolutionary/eco_evolutionary_metabolic_rate/predpreygrass_rllib_env.py
+ *   INV  = predpreygrass/evolutionary/eco_evolutionary_investment/predpreygrass_rllib_env.py
+ *   COOP = predpreygrass/evolutionary/eco_evolutionary_cooperation/predpreygrass_rllib_env.py
+ * (random founder counts, trait-scaled decay / gains, satiation cooldown, density cap, offspring investment, meal
+ * sharing; no ageing caps, no carcasses, no speed gating) — each branch cites the variant's lines; pinned by
+ * tests/golden/make_golden_traits.py -> tests/golden/{mr,inv,coop}_*.npz, tests/test_oracle_golden_traits.py.
  */
 #include <math.h>
 #include <stdio.h>
@@ -41,12 +49,14 @@ void eco_env_alloc(env_t* e) {
   }
   e->max_row_elems = e->row_elems[0] > e->row_elems[1] ? e->row_elems[0] : e->row_elems[1];
   e->dead = (uint8_t*)calloc((size_t)c->n_possible[1], 1);
+  e->sat_until = (int32_t*)calloc((size_t)c->n_possible[0], sizeof(int32_t));
+  e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1];
   e->row_key = (int32_t*)malloc(sizeof(int32_t) * (size_t)(c->n_possible[0] + c->n_possible[1]));
 }
 
 void eco_env_free(env_t* e) {
   for (int s = 0; s < 2; ++s) { free(e->age[s]); free(e->speed[s]); free(e->termd[s]); }
-  free(e->gridf); free(e->dead); free(e->row_key);
+  free(e->gridf); free(e->dead); free(e->row_key); free(e->sat_until);
 }
 
 void eco_read_grid(env_t* e, double* out) {
@@ -106,19 +116,22 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
   }
   memset(e->dead, 0, (size_t)c->n_possible[1]); /* ECO:193 */
   e->n_agents = 0;
+  if (c->trait_mode == PPG_TRAIT_SPEED) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; }
+  const int nf[2] = {e->n_found[0], e->n_found[1]}; /* trait variants: drawn per episode (MR:189-192) */
+  memset(e->sat_until, 0, sizeof(int32_t) * (size_t)c->n_possible[0]); /* MR:1141 */
   int k = 0;
   for (int s = 0; s < 2; ++s)
-    for (int i = 0; i < c->n_initial[s]; ++i, ++k) { /* ECO:214-221 + _register_new_agent (ECO:1472-1486) */
+    for (int i = 0; i < nf[s]; ++i, ++k) { /* ECO:214-221 + _register_new_agent (ECO:1472-1486) */
       e->agents[e->n_agents++] = KEY(s, i);
       /* _get_initial_age (ECO:1060-1068): founder predators start at the carcass-only threshold */
       e->age[s][i] = (s == 0 && c->carcass_only_predator_age >= 0) ? c->carcass_only_predator_age : 0;
       e->speed[s][i] = c->genome_enabled ? founder_speed[k] : -1.0;
     }
-  e->next_idx[0] = c->n_initial[0]; /* deque of never-used ids, ascending (ECO:238-258) */
-  e->next_idx[1] = c->n_initial[1];
+  e->next_idx[0] = nf[0]; /* deque of never-used ids, ascending (ECO:238-258; MR:231-243 lowest unused id) */
+  e->next_idx[1] = nf[1];
   k = 0;
   for (int s = 0; s < 2; ++s)
-    for (int i = 0; i < c->n_initial[s]; ++i, ++k) { /* ECO:1764-1782 */
+    for (int i = 0; i < nf[s]; ++i, ++k) { /* ECO:1764-1782 */
       int cx = cells[k] / G, cy = cells[k] % G;
       e->present[s][i] = 1; e->x[s][i] = (int16_t)cx; e->y[s][i] = (int16_t)cy;
       e->energy[s][i] = c->initial_energy[s];
@@ -129,8 +142,8 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
     e->ge[g] = c->initial_energy_grass;
     *GF(e, 2, e->gx[g], e->gy[g]) = (float)c->initial_energy_grass;
   }
-  e->active[0] = c->n_initial[0]; /* ECO:281-282 */
-  e->active[1] = c->n_initial[1];
+  e->active[0] = nf[0]; /* ECO:281-282 */
+  e->active[1] = nf[1];
   e->cur_num[0] = e->active[0]; e->cur_num[1] = e->active[1];
   eco_ensure_rows(e, e->n_agents);
   for (int i = 0; i < e->n_agents; ++i) { /* ECO:292 */
@@ -147,9 +160,24 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
 }
 
 /* lockstep reset: founder speeds then cells, from the tape or the Philox streams */
+/* founders of the next episode (MR:189-192): two `rng.integers(min, max + 1)` draws, predators first — the first two
+ * entries of the episode's cell tape, or the FOUNDERS Philox stream keyed by the episode about to start */
+void eco_founder_counts(env_t* e, int from_tape) {
+  const ppg_config* c = e->c;
+  if (c->trait_mode == PPG_TRAIT_SPEED) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; return; }
+  for (int s = 0; s < 2; ++s) {
+    const int lo = c->n_initial_min[s], hi = c->n_initial[s];
+    int v;
+    if (from_tape && e->tape_cells && e->tape_pos < e->tape_end) v = e->tape_cells[e->tape_pos++];
+    else v = lo + (int)ppg_bounded(ppg_draw_u32(e->seed_key, genv(e), e->episode + 1, PPG_STREAM_FOUNDERS, (uint32_t)s), (uint32_t)(hi - lo + 1));
+    e->n_found[s] = v < lo ? lo : (v > hi ? hi : v);
+  }
+}
+
 void eco_env_reset_auto(env_t* e) {
   const ppg_config* c = e->c;
-  const int n_f = c->n_initial[0] + c->n_initial[1], n_total = n_f + c->n_grass;
+  eco_founder_counts(e, 1);
+  const int n_f = e->n_found[0] + e->n_found[1], n_total = n_f + c->n_grass;
   const int ncell = e->G * e->G;
   int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_total);
   double* sp = (double*)malloc(sizeof(double) * (size_t)(n_f > 0 ? n_f : 1));
@@ -163,7 +191,7 @@ void eco_env_reset_auto(env_t* e) {
     } else {
       if (e->tape_reals) sticky |= PPG_STATUS_TAPE_EXHAUSTED;
       for (int s = 0; s < 2; ++s)
-        for (int i = 0; i < c->n_initial[s]; ++i, ++k) {
+        for (int i = 0; i < e->n_found[s]; ++i, ++k) {
           double v = c->founder_speed_mean[s];
           if (c->founder_speed_std[s] > 0) /* genome.py:30-33 */
             v = c->founder_speed_mean[s] + c->founder_speed_std[s] * ppg_draw_normal(e->seed_key, genv(e), e->episode, PPG_STREAM_TRAIT, &e->trait_draws);
@@ -192,6 +220,7 @@ void eco_env_reset_auto(env_t* e) {
 /* speed ** exponent (ECO:559-563): CPython's float power is libm pow(), and so is the oracle's — always.  (The device
  * repeats glibc's pow bit for bit, include/ppg_pow.h; the checker is never bent toward the kernel.) */
 static double speed_cost_factor(const env_t* e, double speed) {
+  if (e->c->trait_mode != PPG_TRAIT_SPEED) return 1.0; /* MR:531-539: cost_per_cell * distance */
   if (speed < 0.0) return 1.0; /* no genome */
   return pow(speed, e->c->move_speed_cost_exponent);
 }
@@ -278,9 +307,100 @@ static void handle_starvation(env_t* e, int s, int id) {
   e->stats[s == 0 ? PPG_STAT_STARVED_PRED : PPG_STAT_STARVED_PREY]++;
 }
 
+/* metabolic_rate ** alpha (MR:751,807): CPython float power = libm pow; 1.0 without a genome */
+static double gain_factor(const env_t* e, int s, int id) {
+  const double rate = e->speed[s][id] >= 0.0 ? e->speed[s][id] : 1.0;
+  return pow(rate, e->c->trait_alpha);
+}
+
+/* _apply_cooperative_donation (COOP:537-589): a cooperation_rate share of a positive gain goes, in equal parts, to the
+ * live same-species agents within Chebyshev distance cooperation_range; returns what the donor keeps */
+static double coop_donation(env_t* e, int s, int id, double gain) {
+  const ppg_config* c = e->c;
+  if (!c->genome_enabled || gain <= 0.0) return gain;
+  const double rate = e->speed[s][id] >= 0.0 ? e->speed[s][id] : 0.0;
+  if (rate <= 0.0) return gain;
+  const int px = e->x[s][id], py = e->y[s][id], r = c->cooperation_range;
+  int n = 0;
+  for (int q = 0; q < e->next_idx[s]; ++q) { /* predator_positions / prey_positions: insertion order = ascending id */
+    if (q == id || !e->present[s][q] || e->termd[s][q]) continue;
+    const int dx = abs(e->x[s][q] - px), dy = abs(e->y[s][q] - py);
+    if ((dx > dy ? dx : dy) <= r) ++n;
+  }
+  if (n == 0) return gain;
+  const double total = rate * gain, share = total / n;
+  for (int q = 0; q < e->next_idx[s]; ++q) {
+    if (q == id || !e->present[s][q] || e->termd[s][q]) continue;
+    const int dx = abs(e->x[s][q] - px), dy = abs(e->y[s][q] - py);
+    if ((dx > dy ? dx : dy) > r) continue;
+    e->energy[s][q] += share;                                         /* COOP:572 */
+    *GF(e, s, e->x[s][q], e->y[s][q]) = (float)e->energy[s][q];       /* COOP:573 */
+  }
+  return gain - total;
+}
+
+/* _handle_prey_engagement of the trait variants (MR:790-834, INV, COOP:812-851) */
+static void trait_prey_engagement(env_t* e, int id) {
+  const ppg_config* c = e->c;
+  const int i = e->list_index[1][id];
+  if (e->termd[1][id]) return;
+  const int px = e->x[1][id], py = e->y[1][id];
+  int grass = -1;
+  for (int g = 0; g < c->n_grass; ++g)
+    if (e->gx[g] == px && e->gy[g] == py) { grass = g; break; }
+  if (grass < 0) { e->rew[i] = c->reward_prey_step; e->has_rew[i] = 1; return; }
+  e->ate[i] = 1;
+  e->rew[i] = c->reward_prey_eat_grass; e->has_rew[i] = 1;
+  const double ge = e->ge[grass];
+  double gain = ge;
+  if (c->trait_mode == PPG_TRAIT_METABOLIC) gain = ge * gain_factor(e, 1, id);       /* MR:807 */
+  else if (c->trait_mode == PPG_TRAIT_COOPERATION) gain = coop_donation(e, 1, id, ge); /* COOP:828 */
+  e->energy[1][id] += gain;
+  *GF(e, 1, px, py) = (float)e->energy[1][id];
+  e->ge[grass] = 0.0;
+  *GF(e, 2, px, py) = 0.0f;
+  e->stats[PPG_STAT_GRASS_EATEN]++;
+}
+
+/* _handle_predator_engagement of the trait variants (MR:720-788, INV, COOP:756-810): the prey is always consumed */
+static void trait_predator_engagement(env_t* e, int id) {
+  const ppg_config* c = e->c;
+  const int i = e->list_index[0][id];
+  const int px = e->x[0][id], py = e->y[0][id];
+  int caught = -1;
+  for (int q = 0; q < e->next_idx[1]; ++q)
+    if (e->present[1][q] && e->x[1][q] == px && e->y[1][q] == py) { caught = q; break; }
+  if (caught >= 0 && c->satiation_cooldown >= 0 && (c->trait_mode == PPG_TRAIT_METABOLIC || c->trait_mode == PPG_TRAIT_INVESTMENT) &&
+      e->current_step < e->sat_until[id])
+    caught = -1; /* still digesting (MR:734-740) */
+  if (caught < 0) { e->rew[i] = c->reward_predator_step; e->has_rew[i] = 1; return; }
+  const int j = e->list_index[1][caught];
+  e->ate[i] = 1;
+  e->rew[i] = c->reward_predator_catch_prey; e->has_rew[i] = 1;
+  const double pe = e->energy[1][caught];
+  double gain;
+  if (c->trait_mode == PPG_TRAIT_COOPERATION) gain = coop_donation(e, 0, id, pe); /* COOP:777 */
+  else {
+    const double cap = c->max_energy_gain_per_prey;
+    const double bite = pe < cap ? pe : cap; /* min(prey_energy, cap): the first argument wins ties (MR:747) */
+    gain = c->trait_mode == PPG_TRAIT_METABOLIC ? bite * gain_factor(e, 0, id) : bite; /* MR:751, INV:759 */
+  }
+  e->energy[0][id] += gain;
+  *GF(e, 0, px, py) = (float)e->energy[0][id];
+  if (c->satiation_cooldown > 0 && c->trait_mode != PPG_TRAIT_COOPERATION) e->sat_until[id] = e->current_step + c->satiation_cooldown; /* MR:756-757 */
+  capture_obs(e, 1, caught);
+  e->term[j] = 1; e->termd[1][caught] = 1;
+  e->rew[j] = c->penalty_prey_caught; e->has_rew[j] = 1;
+  e->trunc[j] = 0;
+  e->active[1] -= 1;
+  *GF(e, 1, e->x[1][caught], e->y[1][caught]) = 0;
+  e->stats[PPG_STAT_EATEN_PREY]++;
+}
+
 /* _handle_prey_engagement (ECO:885-941) */
 static void handle_prey_engagement(env_t* e, int id) {
   const ppg_config* c = e->c;
+  if (c->trait_mode != PPG_TRAIT_SPEED) { trait_prey_engagement(e, id); return; }
   const int i = e->list_index[1][id];
   if (e->termd[1][id]) return;
   if (e->dead[id]) { e->rew[i] = c->reward_prey_step; e->has_rew[i] = 1; return; }
@@ -307,6 +427,7 @@ static void handle_prey_engagement(env_t* e, int id) {
 /* _handle_predator_engagement (ECO:786-883) */
 static void handle_predator_engagement(env_t* e, int id) {
   const ppg_config* c = e->c;
+  if (c->trait_mode != PPG_TRAIT_SPEED) { trait_predator_engagement(e, id); return; }
   const int i = e->list_index[0][id];
   const int px = e->x[0][id], py = e->y[0][id];
   /* first prey in agent_positions order on the cell (ECO:797-799): prey enter the dict in ascending id
@@ -352,7 +473,11 @@ static void handle_reproduction(env_t* e, int s, int id) {
   const int i = e->list_index[s][id];
   if (s == 1 && e->dead[id]) return;                             /* ECO:1192-1193 */
   if (!(e->energy[s][id] >= c->creation_threshold[s])) return;    /* ECO:1100,1195 */
-  if (e->next_idx[s] >= c->n_possible[s]) { e->status |= PPG_STATUS_ID_POOL_EMPTY; return; } /* SystemExit (ECO:1104-1111) */
+  if (s == 0 && c->trait_mode == PPG_TRAIT_METABOLIC && c->repro_max_ratio >= 0.0 &&
+      (double)e->active[0] >= c->repro_max_ratio * (double)e->active[1])
+    return; /* density-dependent soft cap (MR:843-854) */
+  /* ECO: SystemExit (ECO:1104-1111); the trait variants print a warning and skip the birth (MR:856-864) */
+  if (e->next_idx[s] >= c->n_possible[s]) { e->status |= PPG_STATUS_ID_POOL_EMPTY; return; }
   if (c->cap_live[s] > 0) { /* device slot capacity (not in the reference) */
     int cnt = 0;
     for (int k = 0; k < e->n_rows; ++k) cnt += (KEY_S(e->row_key[k]) == s);
@@ -387,9 +512,15 @@ static void handle_reproduction(env_t* e, int s, int id) {
   e->termd[s][child] = 0;
   if (s == 1) e->dead[child] = 0;
   e->present[s][child] = 1; e->x[s][child] = (int16_t)sx; e->y[s][child] = (int16_t)sy; /* ECO:1145-1146 */
-  e->energy[s][child] = c->initial_energy[s];          /* ECO:1148-1149 */
-  e->energy[s][id] -= c->initial_energy[s];            /* ECO:1150 */
-  *GF(e, s, sx, sy) = (float)c->initial_energy[s];     /* ECO:1154 */
+  double child_e = c->initial_energy[s];               /* ECO:1148-1149 */
+  if (c->trait_mode == PPG_TRAIT_INVESTMENT) {         /* INV:546-557,890,977: parent energy * the PARENT's fraction */
+    const double fraction = e->speed[s][id] >= 0.0 ? e->speed[s][id] : c->founder_speed_mean[s];
+    child_e = e->energy[s][id] * fraction;
+  }
+  if (s == 0) e->sat_until[child] = 0;                 /* MR:1141 */
+  e->energy[s][child] = child_e;
+  e->energy[s][id] -= child_e;                         /* ECO:1150 */
+  *GF(e, s, sx, sy) = (float)child_e;                  /* ECO:1154 */
   *GF(e, s, e->x[s][id], e->y[s][id]) = (float)e->energy[s][id]; /* ECO:1155 */
   e->active[s] += 1;                                   /* ECO:1157 */
   e->rew[ci] = 0.0; e->has_rew[ci] = 1;                /* ECO:1160 */
@@ -426,7 +557,9 @@ int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, c
   /* Step 1: _apply_time_step_update (ECO:582-616), over list(self.agents) */
   for (int i = 0; i < n0; ++i) {
     const int s = KEY_S(e->agents[i]), id = KEY_ID(e->agents[i]);
-    e->energy[s][id] -= c->energy_loss[s];
+    double decay = c->energy_loss[s];
+    if (c->trait_mode == PPG_TRAIT_METABOLIC) decay = c->energy_loss[s] * (e->speed[s][id] >= 0.0 ? e->speed[s][id] : 1.0); /* MR:555-561 */
+    e->energy[s][id] -= decay;
     *GF(e, s, e->x[s][id], e->y[s][id]) = (float)e->energy[s][id];
     if (!(s == 1 && e->dead[id])) e->age[s][id] += 1; /* carcasses do not age (ECO:600-601) */
   }

@@ -77,6 +77,9 @@ typedef struct env_t {
   const double* tape_reals;
   int64_t real_pos, real_end;
   uint32_t trait_draws;
+  /* ---- trait variants of ECO (MR / INV / COOP, ppg_oracle_eco.c) ---- */
+  int n_found[2];     /* founders of the running episode (MR:189-192) */
+  int32_t* sat_until; /* agent_satiation_until by predator id (MR:134,756-757) */
   /* ---- STAG (ppg_oracle_stag.c) ---- */
   int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
   double* trait;      /* predator_cooperation_trait (STAG:230) */
@@ -115,6 +118,7 @@ void eco_env_free(env_t* e);
 void eco_ensure_rows(env_t* e, int need);
 void eco_env_reset_auto(env_t* e);
 void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founder_speed);
+void eco_founder_counts(env_t* e, int from_tape);
 int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, const int32_t* a_val);
 void eco_read_grid(env_t* e, double* out);
 

@@ -158,6 +158,9 @@ def _round32(n):
 
 TRAITS = {"speed": 0, "metabolic_rate": 1, "offspring_investment_fraction": 2, "cooperation_rate": 3, "cadence": 4}
 TRAIT_SPEED, TRAIT_METABOLIC, TRAIT_INVESTMENT, TRAIT_COOPERATION, TRAIT_CADENCE = 0, 1, 2, 3, 4
+# founder mean and bounds each variant's genome.py falls back to (GENOME_FIELD_DEFAULTS / DEFAULT_TRAIT_BOUNDS)
+TRAIT_DEFAULTS = {"metabolic_rate": (1.0, (0.5, 2.0)), "offspring_investment_fraction": (0.35, (0.10, 0.80)),
+                  "cooperation_rate": (0.0, (0.0, 1.0))}
 
 
 def make_config(config=None, *, reward_mode="sparse", variant=VARIANT_BASE, cap_live=None, autoreset=True, seed=0,
@@ -362,8 +365,7 @@ def _fill_trait(c, cfg, trait):
         c.cooperation_range = int(g("cooperation_range", 2))
     if g("genome_neutral_drift_control", False):
         raise ValueError("genome_neutral_drift_control (the neutral-drift null model, MR:108-114) is not supported")
-    default_mean = {TRAIT_METABOLIC: 1.0, TRAIT_INVESTMENT: 0.35, TRAIT_COOPERATION: 0.0}[mode]
-    default_bounds = {TRAIT_METABOLIC: (0.5, 2.0), TRAIT_INVESTMENT: (0.10, 0.80), TRAIT_COOPERATION: (0.0, 1.0)}[mode]
+    default_mean, default_bounds = TRAIT_DEFAULTS[trait]
     for s, role in enumerate(("predator", "prey")):
         f = g("founder_genome", {}).get(role, {})
         c.founder_speed_mean[s] = float(f.get(f"{trait}_mean", default_mean))

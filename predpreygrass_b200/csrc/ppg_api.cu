@@ -15,7 +15,7 @@ namespace ppg {
 cudaError_t launch_step_base(const StepParams& p, int warps_per_cta, int n_cta, size_t smem, cudaStream_t stream);
 cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, bool split, size_t smem, int* blocks_per_sm);
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
-                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s);
+                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, int hdr_founders, cudaStream_t s);
 cudaError_t launch_init_hdr(EnvHdr* hdr, int B, unsigned long long seed, cudaStream_t s);
 cudaError_t launch_relabel_rows(const StepParams& p, const unsigned long long* cntA, const unsigned long long* sum1,
                                 const unsigned long long* sum2, const int32_t* totals4, cudaStream_t s);
@@ -32,6 +32,7 @@ cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm);
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
 cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
+cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s);
 // ppg_stag.cu
 cudaError_t launch_step_stag(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
 cudaError_t step_stag_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm);
@@ -153,6 +154,9 @@ void ppg_default_config(ppg_config* c) {
   c->speed_bounds[0] = 0.5; c->speed_bounds[1] = 2.0;
   c->speed_distance_threshold = 1.5;
   c->season_multiplier[0] = c->season_multiplier[1] = 1.0;  // season_length_steps = 0: no seasons
+  // trait-variant fields: neutral values (trait_mode = PPG_TRAIT_SPEED)
+  c->n_initial_min[0] = c->n_initial[0]; c->n_initial_min[1] = c->n_initial[1];
+  c->trait_alpha = 1.0; c->repro_max_ratio = -1.0;
 }
 
 const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -189,6 +193,16 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
     if (c->cap_live[0] > 32767 || c->cap_live[1] > 32767) { err = "ECO: cap_live must be <= 32767"; return PPG_ERR_INVALID; }
     if (c->slow_max_move_distance < 0 || c->fast_max_move_distance < 0) { err = "max move distance negative"; return PPG_ERR_INVALID; }
     if (!(c->speed_bounds[1] > c->speed_bounds[0])) { err = "speed bounds"; return PPG_ERR_INVALID; }
+    if (c->trait_mode < PPG_TRAIT_SPEED || c->trait_mode > PPG_TRAIT_COOPERATION) { err = "trait_mode: speed, metabolic_rate, offspring_investment_fraction and cooperation_rate are built (cadence is not)"; return PPG_ERR_INVALID; }
+    if (c->trait_mode != PPG_TRAIT_SPEED) {
+      for (int s = 0; s < 2; ++s)
+        if (c->n_initial_min[s] < 0 || c->n_initial_min[s] > c->n_initial[s]) { err = "n_initial_min must lie in [0, n_initial]"; return PPG_ERR_INVALID; }
+      if (c->satiation_cooldown < 0 || c->satiation_cooldown > 250) { err = "satiation_cooldown must be in [0, 250]"; return PPG_ERR_INVALID; }
+      if (c->cooperation_range < 0) { err = "cooperation_range negative"; return PPG_ERR_INVALID; }
+      if (c->include_speed_in_obs || c->max_agent_age[0] >= 0 || c->max_agent_age[1] >= 0 || c->carcass_only_predator_age >= 0) { err = "trait variants have no speed plane, age caps or carcass-only predators"; return PPG_ERR_INVALID; }
+    }
+  } else if (c->trait_mode != 0) { err = "trait_mode belongs to the ECO family"; return PPG_ERR_INVALID; }
+  if (false) {
   }
   for (int s = 0; s < 2; ++s) {
     if (c->obs_range[s] < 1 || (c->obs_range[s] & 1) == 0 || c->obs_range[s] > 255) { err = "obs_range must be odd"; return PPG_ERR_INVALID; }
@@ -241,6 +255,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     for (int s = 0; s < 2; ++s) { P.f_mean[s] = c.founder_speed_mean[s]; P.f_std[s] = c.founder_speed_std[s]; }
     P.mut_rate = c.mutation_rate; P.mut_std = c.mutation_std; P.sp_lo = c.speed_bounds[0]; P.sp_hi = c.speed_bounds[1];
     P.sp_thr = c.speed_distance_threshold;
+    P.trait_mode = c.trait_mode; P.n_init_min[0] = c.n_initial_min[0]; P.n_init_min[1] = c.n_initial_min[1];
+    P.sat_cd = c.satiation_cooldown; P.coop_range = c.cooperation_range; P.trait_alpha = c.trait_alpha; P.repro_ratio = c.repro_max_ratio;
   } else if (stag) {
     P.action_range = std::max(c.type_action_range[0], c.type_action_range[1]); P.n_actions = P.action_range * P.action_range;
     for (int s = 0; s < 2; ++s)
@@ -586,7 +602,7 @@ static int prepare_offsets(ppg_handle h, cudaStream_t st) {
   const unsigned prev_epoch = (unsigned)h->launches_step;
   const int q = (int)(prev_epoch & 1u);
   CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.cntA[q], h->P.sum1[q], h->P.sum2[q],
-                            h->P.totals + 4 * q, prev_epoch, st));
+                            h->P.totals + 4 * q, prev_epoch, h->P.variant == PPG_VARIANT_ECO && h->P.trait_mode != PPG_TRAIT_SPEED, st));
   h->launch_count++;
   return PPG_OK;
 }
@@ -637,6 +653,11 @@ int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cu
   if (mask) { CK(cudaMemcpyAsync(h->d_mask, mask, (size_t)h->B, cudaMemcpyHostToDevice, st)); dmask = h->d_mask; }
   CK(launch_mark_reset(h->P.hdr, h->B, dseeds, dmask, st));
   h->launch_count++;
+  const bool random_founders = h->P.variant == PPG_VARIANT_ECO && h->P.trait_mode != PPG_TRAIT_SPEED;
+  if (random_founders) {  // MR:189-192: the number of founders is drawn per episode; the row allocator needs it before the reset runs
+    CK(launch_eco_founders(h->P, st));
+    h->launch_count++;
+  }
   int rc = prepare_offsets(h, st);
   if (rc) return rc;
   if (mask) return PPG_OK;  // partial reset: performed by the next ppg_step
@@ -644,7 +665,7 @@ int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cu
   if (rc) return rc;
   h->h_n_rows[0] = h->B * h->P.n_init[0]; h->h_n_rows[1] = h->B * h->P.n_init[1];
   h->h_n_rows[2] = h->h_n_rows[3] = 0;
-  h->h_n_rows_valid = true;
+  h->h_n_rows_valid = !random_founders;
   return PPG_OK;
 }
 
@@ -943,7 +964,9 @@ int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawn
   EnvHdr hd;
   CK(cudaMemcpy(&hd, h->P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
   if (sums) CK(cudaMemcpy(sums, h->P.ep_sums + (size_t)env * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (spawned) for (int s = 0; s < 2; ++s) spawned[s] = (int32_t)hd.next_idx[s] - h->P.n_init[s];  // ids are handed out in order and never reused (ECO:260-272)
+  // ids are handed out in order and never reused (ECO:260-272): spawned = ids used - founders of the running episode
+  const bool rf = h->P.trait_mode != PPG_TRAIT_SPEED;
+  if (spawned) for (int s = 0; s < 2; ++s) spawned[s] = (int32_t)hd.next_idx[s] - (rf ? (s == 0 ? (hd.pad[1] & 0xFFFF) : ((hd.pad[1] >> 16) & 0x7FFF)) : h->P.n_init[s]);
   return PPG_OK;
 }
 

@@ -786,13 +786,16 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
 // words, block sums, group sums, totals).  Single CTA; used after ppg_create / ppg_reset /
 // ppg_restore (the step kernel maintains them itself).
 __global__ void ppg_prepare_offsets_kernel(const EnvHdr* __restrict__ hdr, int B, int n_init0, int n_init1, unsigned long long* cntA,
-                                           unsigned long long* sum1, unsigned long long* sum2, int32_t* totals4, unsigned epoch) {
+                                           unsigned long long* sum1, unsigned long long* sum2, int32_t* totals4, unsigned epoch, int hdr_founders) {
   const int t = threadIdx.x, T = blockDim.x;
   const int n_blk = (B + 31) >> 5, n_grp = (B + 1023) >> 10;
   for (int e = t; e < B; e += T) {
     const EnvHdr h = hdr[e];
     const bool rs = h.state & ST_NEEDS_RESET, idle = (h.state & ST_IDLE) && !rs;
-    const int a0 = idle ? 0 : (rs ? n_init0 : h.n_list[0]), a1 = idle ? 0 : (rs ? n_init1 : h.n_list[1]);
+    // founders of a scheduled reset: constants, or (trait variants of ECO) the per-episode draw kept in the header
+    const bool hf = hdr_founders && ((unsigned)h.pad[1] & 0x80000000u);
+    const int f0 = hf ? (h.pad[0] & 0xFFFF) : n_init0, f1 = hf ? ((h.pad[0] >> 16) & 0x7FFF) : n_init1;
+    const int a0 = idle ? 0 : (rs ? f0 : h.n_list[0]), a1 = idle ? 0 : (rs ? f1 : h.n_list[1]);
     cntA[e] = TAG(epoch, (a0 << 16) | a1);
   }
   __syncthreads();
@@ -968,8 +971,8 @@ cudaError_t step_base_occupancy(int warps_per_cta, int map_bytes, bool bulk, boo
 }
 
 cudaError_t launch_prepare_offsets(const EnvHdr* hdr, int B, int n0, int n1, unsigned long long* cntA, unsigned long long* sum1,
-                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, cudaStream_t s) {
-  ppg_prepare_offsets_kernel<<<1, 1024, 0, s>>>(hdr, B, n0, n1, cntA, sum1, sum2, totals4, epoch);
+                                   unsigned long long* sum2, int32_t* totals4, unsigned epoch, int hdr_founders, cudaStream_t s) {
+  ppg_prepare_offsets_kernel<<<1, 1024, 0, s>>>(hdr, B, n0, n1, cntA, sum1, sum2, totals4, epoch, hdr_founders);
   return cudaGetLastError();
 }
 cudaError_t launch_relabel_rows(const StepParams& p, const unsigned long long* cntA, const unsigned long long* sum1,

@@ -161,6 +161,10 @@ struct StepParams {
   uint16_t* ag_seq[2];
   double* ag_spd[2];
   uint8_t* ag_dead[2];
+  // trait variants of ECO (ppg_config.trait_mode): founders ~ U{n_init_min..n_init}, satiation cooldown, meal-sharing radius,
+  // gain exponent, density cap (< 0: none)
+  int trait_mode, n_init_min[2], sat_cd, coop_range;
+  double trait_alpha, repro_ratio;
   double* ep_sums;     // [B][4] optional (ppg_config.track_episode_sums): per-episode distance moved [2], locomotion energy [2]
   uint8_t* gh_n;       // [B] ghost cells of the env (ppg_eco.cu header)
   uint16_t* gh_cell;   // [B][PPG_MAX_GHOSTS] packed position x << 8 | y

@@ -63,6 +63,28 @@ __device__ __forceinline__ float speed_plane(const StepParams& p, double spd) {
 // speed ** exponent (ECO:559-563): CPython's float power = glibc pow, repeated bit for bit (include/ppg_pow.h)
 static __device__ __noinline__ double speed_cost_factor(double speed, double exponent) { return ppg_pow(speed, exponent); }
 
+// trait variants: gain factor metabolic_rate ** alpha (MR:751,807), 1.0 ** alpha = 1 without a genome
+static __device__ __noinline__ double gain_factor(double rate, double alpha) { return ppg_pow(rate >= 0.0 ? rate : 1.0, alpha); }
+
+// Founders of the NEXT episode of a trait-variant env (MR:189-192: two `rng.integers(min, max + 1)` draws, predators
+// first): from the cell tape if it still has entries, else the FOUNDERS Philox stream keyed by the episode about to
+// start.  Drawn when the reset is scheduled (episode end with auto-reset, ppg_reset), because the row allocator must know
+// how many rows the reset will produce before it runs.  Packed pred | prey << 16 into EnvHdr.pad[0]; pad[1] bit 31 = drawn.
+__device__ __forceinline__ void draw_next_founders(const StepParams& p, EnvHdr& h, unsigned genv) {
+  if ((unsigned)h.pad[1] & 0x80000000u) return;  // already drawn for the pending reset
+  int v[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int lo = p.n_init_min[s], hi = p.n_init[s];
+    int x;
+    if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) x = p.tape_cells[h.tape_pos++];
+    else x = lo + (int)ppg_bounded(ppg_draw_u32(h.seed_key, genv, h.episode + 1u, PPG_STREAM_FOUNDERS, (unsigned)s), (unsigned)(hi - lo + 1));
+    v[s] = x < lo ? lo : (x > hi ? hi : x);
+  }
+  h.pad[0] = v[0] | (v[1] << 16);
+  h.pad[1] = (int)((unsigned)h.pad[1] | 0x80000000u);
+}
+
 // one tape-or-Philox real draw (uniform lanes)
 __device__ __forceinline__ bool take_real(const StepParams& p, EcoHdr& eh, EnvHdr& h, double& out) {
   if (p.tape_reals != nullptr) {
@@ -85,6 +107,54 @@ __device__ __forceinline__ unsigned next_in_seq_order(const uint16_t* const seq[
       if ((long long)key > last && pred(s, i)) best = min(best, key);
     }
   return __reduce_min_sync(FULL, best);
+}
+
+// _apply_cooperative_donation (COOP:537-589), warp-cooperative with uniform arguments: a cooperation_rate share of a
+// positive gain goes in equal parts to the live agents of the donor's species within Chebyshev distance
+// cooperation_range; every receiver's cell is re-written (COOP:573: of co-located receivers the later one in
+// `predator_positions` / `prey_positions` order — the higher slot — shows).  Returns what the donor keeps.
+template <typename MapT>
+__device__ __noinline__ double coop_donation(unsigned char* sbase, const StepParams& p, int s, int slot, int n_s, double gain, int lane) {
+  const EnvSmem<MapT> S = carve<MapT>(sbase, p);
+  const EcoSmem<MapT> X = carve_eco<MapT>(sbase, p);
+  const int PP = p.P, PS = p.PS;
+  if (!p.genome_enabled || !(gain > 0.0)) return gain;
+  const double rate = SEL(X.spd)[slot] >= 0.0 ? SEL(X.spd)[slot] : 0.0;
+  if (!(rate > 0.0)) return gain;
+  const unsigned ps = SEL(S.pos)[slot];
+  const int px = ps >> 8, py = ps & 255, r = p.coop_range;
+  int cnt = 0;
+  for (int b0 = 0; b0 < n_s; b0 += 32) {
+    const int i = b0 + lane;
+    bool nb = false;
+    if (i < n_s && i != slot && (SEL(S.flg)[i] & F_ALIVE)) {
+      const unsigned q = SEL(S.pos)[i];
+      nb = max(abs((int)(q >> 8) - px), abs((int)(q & 255u) - py)) <= r;
+    }
+    cnt += __popc(__ballot_sync(FULL, nb));
+  }
+  if (cnt == 0) return gain;
+  const double total = rate * gain, share = total / (double)cnt;
+  for (int b0 = 0; b0 < n_s; b0 += 32) {
+    const int i = b0 + lane;
+    bool nb = false;
+    int cell = 0;
+    if (i < n_s && i != slot && (SEL(S.flg)[i] & F_ALIVE)) {
+      const unsigned q = SEL(S.pos)[i];
+      nb = max(abs((int)(q >> 8) - px), abs((int)(q & 255u) - py)) <= r;
+      cell = CELLP(q);
+    }
+    if (nb) { SEL(S.E)[i] = SEL(S.E)[i] + share; SEL(S.map)[cell] = (MapT)(i + 1); }
+    __syncwarp();
+    bool need = nb && SEL(S.map)[cell] < (unsigned)(i + 1);
+    while (__any_sync(FULL, need)) {
+      if (need) SEL(S.map)[cell] = (MapT)(i + 1);
+      __syncwarp();
+      need = nb && SEL(S.map)[cell] < (unsigned)(i + 1);
+    }
+  }
+  __syncwarp();
+  return gain - total;
 }
 
 template <int W, typename MapT, bool SPLIT>
@@ -133,6 +203,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     const unsigned t_ns0 = globaltimer_lo();
     EnvHdr h = p.hdr[env];
     EcoHdr eh = p.ehdr[env];
+    const int tm = p.trait_mode;  // PPG_TRAIT_*: 0 = ECO (speed)
+    // founders of the episode a reset starts: constant for ECO, drawn per episode by the trait variants (MR:189-192)
+    int nf[2] = {p.n_init[0], p.n_init[1]};
+    if (tm != PPG_TRAIT_SPEED && ((unsigned)h.pad[1] & 0x80000000u)) { nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
       if (lane == 0) atomicOr(p.error, 2u);
     }
@@ -142,7 +216,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     if (mode != 2) {
       // reset / idle envs know their counts up front (founders, no births): publish them before doing any work, so
       // that later envs waiting for their newborn-row prefix never wait for a reset
-      if (mode == 1) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+      if (mode == 1) { next_live[0] = nf[0]; next_live[1] = nf[1]; }
       publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
     }
     const unsigned genv = (unsigned)(env + p.env_base);
@@ -155,7 +229,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       h.status = 0;
       h.state = 0;
       eh.trait_draws = 0;
-      const int n_f = p.n_init[0] + p.n_init[1], n_total = n_f + p.n_grass;
+      const int n_f = nf[0] + nf[1], n_total = n_f + p.n_grass;
+      h.pad[1] = nf[0] | (nf[1] << 16);  // founders of the running episode; clears the "next founders drawn" bit
       // founder genomes first (ECO:216-221 register the founders before the placement draw, ECO:1752)
       if (p.genome_enabled) {
         double* sp0 = X.spd[0];
@@ -165,7 +240,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           for (int k = lane; k < n_f; k += 32) {
             const double v = p.tape_reals[eh.real_pos + k];
             const double c = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
-            if (k < p.n_init[0]) sp0[k] = c; else sp1[k - p.n_init[0]] = c;
+            if (k < nf[0]) sp0[k] = c; else sp1[k - nf[0]] = c;
           }
           eh.real_pos += n_f;
         } else {
@@ -176,12 +251,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 #pragma unroll 1
           for (int s = 0; s < 2; ++s) {
             if (p.f_std[s] > 0) {
-              ctr = draw_normals_batched(SEL(X.spd), p.n_init[s], p.f_mean[s], p.f_std[s], p.sp_lo, p.sp_hi, h.seed_key, genv, h.episode,
+              ctr = draw_normals_batched(SEL(X.spd), SEL(nf), p.f_mean[s], p.f_std[s], p.sp_lo, p.sp_hi, h.seed_key, genv, h.episode,
                                          PPG_STREAM_TRAIT, ctr, lane);
             } else {
               const double v = p.f_mean[s];
               #pragma unroll 1
-              for (int i = lane; i < p.n_init[s]; i += 32) SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
+              for (int i = lane; i < SEL(nf); i += 32) SEL(X.spd)[i] = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
             }
           }
           eh.trait_draws = ctr;
@@ -208,7 +283,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           #pragma unroll 1
-          for (int i = lane; i < p.n_init[s]; i += 32) {
+          for (int i = lane; i < nf[s]; i += 32) {
             const int c = cells[k0 + i];
             const int cx = c / G, cy = c % G;
             S.id[s][i] = (uint16_t)i;
@@ -219,15 +294,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (!p.genome_enabled) X.spd[s][i] = -1.0;
             S.map[s][CELLXY(cx, cy)] = (MapT)(i + 1);
           }
-          k0 += p.n_init[s];
-          n[s] = p.n_init[s];
-          h.next_idx[s] = (unsigned short)p.n_init[s];
+          k0 += nf[s];
+          n[s] = nf[s];
+          h.next_idx[s] = (unsigned short)nf[s];
         }
         __syncwarp();  // `first` aliases the energy arrays: write the energies only after the placement is read
 #pragma unroll
         for (int s = 0; s < 2; ++s)
           #pragma unroll 1
-          for (int i = lane; i < p.n_init[s]; i += 32) S.E[s][i] = p.init_e[s];
+          for (int i = lane; i < nf[s]; i += 32) S.E[s][i] = p.init_e[s];
         #pragma unroll 1
         for (int g = lane; g < p.n_grass; g += 32) {
           const int c = cells[k0 + g];
@@ -238,7 +313,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       }
       __syncwarp();
-      eh.active[0] = p.n_init[0]; eh.active[1] = p.n_init[1];  // ECO:281-282
+      eh.active[0] = nf[0]; eh.active[1] = nf[1];  // ECO:281-282
       eh.next_seq = (unsigned)n_f;
       next_live[0] = n[0]; next_live[1] = n[1];
       env_flags = PPG_ENV_RESET;
@@ -274,13 +349,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           const int prow = p.ag_prow[s][b + i];
           int a = p.actions[s][prow];
           if ((unsigned)a >= (unsigned)p.n_actions) { a = p.n_actions / 2; bad = PPG_STATUS_BAD_ACTION; }
-          const bool carc = p.ag_dead[s][b + i] != 0;
+          const bool carc = tm == PPG_TRAIT_SPEED && p.ag_dead[s][b + i] != 0;  // trait variants: no carcasses (ag_dead[0] = satiation)
           unsigned age = p.ag_age[s][b + i];
           if (!carc) age += 1;  // carcasses do not age (ECO:600-601)
           SEL(S.id)[i] = p.ag_id[s][b + i];
           SEL(S.pos)[i] = p.ag_pos[s][b + i];
-          SEL(S.E)[i] = p.ag_e[s][b + i] - p.loss[s];  // ECO:596
-          SEL(X.spd)[i] = p.ag_spd[s][b + i];
+          const double tr = p.ag_spd[s][b + i];
+          // ECO:596; MR:555-561: the basal cost scales with the metabolic rate (1.0 without a genome)
+          SEL(S.E)[i] = p.ag_e[s][b + i] - (tm == PPG_TRAIT_METABOLIC ? p.loss[s] * (tr >= 0.0 ? tr : 1.0) : p.loss[s]);
+          SEL(X.spd)[i] = tr;
           SEL(X.age)[i] = (uint16_t)age;
           SEL(X.seq)[i] = p.ag_seq[s][b + i];
           SEL(S.act)[i] = (uint8_t)a;
@@ -401,7 +478,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int nc = blocked ? oc : tc;
             if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
               const double sp = SEL(X.spd)[j];
-              const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
+              const double fac = (sp < 0.0 || tm != PPG_TRAIT_SPEED) ? 1.0 : speed_cost_factor(sp, p.move_exp);  // MR:531-539: no speed factor
               const double dist = sqrt((double)d2), cost = p.move_cost[s] * dist * fac;
               SEL(S.E)[j] = SEL(S.E)[j] - cost;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
@@ -430,7 +507,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int dd = (nx - xx) * (nx - xx) + (ny - yy) * (ny - yy);
             double e = SEL(S.E)[jj];
             if (dd > 0) {
-              const double fac = sp < 0.0 ? 1.0 : speed_cost_factor(sp, p.move_exp);
+              const double fac = (sp < 0.0 || tm != PPG_TRAIT_SPEED) ? 1.0 : speed_cost_factor(sp, p.move_exp);
               const double dist = sqrt((double)dd), cost = p.move_cost[s] * dist * fac;
               e = e - cost;
               if (p.ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
@@ -475,8 +552,29 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       }
 
+      // COOP: a meal changes the neighbours' energies (COOP:828), so the prey go one by one in prey_positions order
+      if (tm == PPG_TRAIT_COOPERATION) {
+        for (int sl = 0; sl < n[1]; ++sl) {
+          const unsigned f = S.flg[1][sl];
+          if (!(f & F_ALIVE)) continue;
+          const int cl = CELLP((unsigned)S.pos[1][sl]);
+          const int gg = S.map[2][cl];
+          if (!gg) continue;
+          const double keep_gain = coop_donation<MapT>(sbase, p, 1, sl, n[1], S.gE[gg - 1], lane);
+          const double en = S.E[1][sl] + keep_gain;
+          __syncwarp();
+          if (lane == 0) {
+            S.E[1][sl] = en;
+            S.map[1][cl] = (MapT)(sl + 1);
+            S.gE[gg - 1] = 0.0;
+            S.flg[1][sl] = (uint8_t)(f | F_ATE);
+          }
+          st_grass++;
+          __syncwarp();
+        }
+      }
       // Step 4b: prey eat grass, prey_positions order (ECO:318-323,885-941)
-      for (int b0 = 0; b0 < n[1]; b0 += 32) {
+      for (int b0 = 0; tm != PPG_TRAIT_COOPERATION && b0 < n[1]; b0 += 32) {
         const int slot = b0 + lane;
         int cell = 0, g = 0;
         bool act = false;
@@ -495,7 +593,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const double ge = S.gE[g - 1];
             const double bite = ge < p.bite_cap_grass ? ge : p.bite_cap_grass;  // ECO:909-911
             const double rem = ge - bite;
-            S.E[1][slot] = S.E[1][slot] + bite;
+            // MR:807: gain = grass_energy * metabolic_rate ** alpha
+            S.E[1][slot] = S.E[1][slot] + (tm == PPG_TRAIT_METABOLIC ? bite * gain_factor(X.spd[1][slot], p.trait_alpha) : bite);
             S.map[1][cell] = (MapT)(slot + 1);  // ECO:915
             S.gE[g - 1] = rem > 0.0 ? rem : 0.0;
             S.flg[1][slot] |= F_ATE;
@@ -515,7 +614,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const double ge = S.gE[gg - 1];
             const double bite = ge < p.bite_cap_grass ? ge : p.bite_cap_grass;
             const double rem = ge - bite;
-            const double en = S.E[1][sl] + bite;
+            const double en = S.E[1][sl] + (tm == PPG_TRAIT_METABOLIC ? bite * gain_factor(X.spd[1][sl], p.trait_alpha) : bite);
             __syncwarp();
             if (lane == 0) {
               S.E[1][sl] = en;
@@ -533,6 +632,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       // Step 4c: predators, predator_positions order (ECO:325-330,786-883).  Every prey still in agent_positions counts —
       // also those terminated earlier in this step (removal is Step 5) and carcasses.
       {
+        const bool satiation = tm == PPG_TRAIT_METABOLIC || tm == PPG_TRAIT_INVESTMENT;
+        if (satiation) {  // steps a predator still digests (agent_satiation_until - current_step, MR:734-740); mord is free after the moves
+          #pragma unroll 1
+          for (int i = lane; i < n[0]; i += 32) X.mord[0][i] = p.ag_dead[0][(size_t)env * p.cap[0] + i];
+        }
         #pragma unroll 1
         for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 1;
         __syncwarp();
@@ -557,15 +661,23 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const unsigned qf = S.flg[1][q];
             const bool was_dead = (qf & F_CARC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
             if (!was_dead && p.carcass_age >= 0 && (int)X.age[0][slot] < p.carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
+            if (satiation && X.mord[0][slot] != 0) continue;  // still digesting: does not hunt this step (MR:734-740)
             const double pe = S.E[1][q];
             const double bite = pe < p.bite_cap_prey ? pe : p.bite_cap_prey;  // ECO:812-814
-            const double rem = pe - bite;
-            const double en = S.E[0][slot] + bite;
+            double rem = pe - bite;
+            double en;
+            if (tm == PPG_TRAIT_SPEED) en = S.E[0][slot] + bite;
+            else {  // the trait variants always consume the prey (MR:759-773)
+              rem = 0.0;
+              if (tm == PPG_TRAIT_COOPERATION) en = S.E[0][slot] + coop_donation<MapT>(sbase, p, 0, slot, n[0], pe, lane);  // COOP:777
+              else en = S.E[0][slot] + (tm == PPG_TRAIT_METABOLIC ? bite * gain_factor(X.spd[0][slot], p.trait_alpha) : bite);  // MR:747-751
+            }
             __syncwarp();
             if (lane == 0) {
               S.E[0][slot] = en;
               S.map[0][cell] = (MapT)(slot + 1);  // ECO:817
               S.flg[0][slot] |= F_ATE;
+              if (satiation && p.sat_cd > 0) X.mord[0][slot] = (uint16_t)p.sat_cd;  // MR:756-757
             }
             if (rem > 0.0) {  // carcass (ECO:826-845)
               if (lane == 0) {
@@ -611,6 +723,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           while (m) {
             const int ps_slot = b0 + __ffs(m) - 1;
             m &= m - 1;
+            if (s == 0 && tm == PPG_TRAIT_METABOLIC && p.repro_ratio >= 0.0 && (double)eh.active[0] >= p.repro_ratio * (double)eh.active[1])
+              continue;  // density-dependent soft cap (MR:843-854)
             if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) { h.status |= PPG_STATUS_ID_POOL_EMPTY; continue; }  // ECO:1104-1111
             if (SEL(n) + SEL(births) >= p.cap[s] - (s == 1 ? n_gh : 0)) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
             // mutate_genome (GENOME:49-59): the draws precede the spawn search (ECO:1119 before :1136)
@@ -652,12 +766,17 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int cs = SEL(n) + SEL(births);
             if (s == 0) births[0]++; else births[1]++;
             const int child_id = s == 0 ? h.next_idx[0]++ : h.next_idx[1]++;  // smallest never-used id (ECO:260-272)
-            const double pe = SEL(S.E)[ps_slot] - p.init_e[s];                // ECO:1150
+            double child_e = p.init_e[s];
+            if (tm == PPG_TRAIT_INVESTMENT) {  // INV:546-557,890,977: the PARENT's fraction of the parent's energy
+              const double fr = SEL(X.spd)[ps_slot];
+              child_e = SEL(S.E)[ps_slot] * (fr >= 0.0 ? fr : p.f_mean[s]);
+            }
+            const double pe = SEL(S.E)[ps_slot] - child_e;                    // ECO:1150
             __syncwarp();
             if (lane == 0) {  // one writer for the warp-uniform stores
               SEL(S.id)[cs] = (uint16_t)child_id;
               SEL(S.pos)[cs] = (uint16_t)((sx << 8) | sy);
-              SEL(S.E)[cs] = p.init_e[s];
+              SEL(S.E)[cs] = child_e;
               SEL(S.flg)[cs] = (uint8_t)(F_ALIVE | F_NEWBORN | (maybe_done ? F_BORNROW : 0));
               SEL(X.age)[cs] = 0;
               SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
@@ -702,7 +821,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       over = done || trunc;
       env_flags = (done ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
       if (over) {
-        if (p.autoreset) { next_live[0] = p.n_init[0]; next_live[1] = p.n_init[1]; }
+        if (p.autoreset) {
+          if (tm != PPG_TRAIT_SPEED) { draw_next_founders(p, h, genv); nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
+          next_live[0] = nf[0]; next_live[1] = nf[1];
+        }
       } else {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -798,7 +920,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               p.ag_age[s][sb + dst] = SEL(X.age)[slot];
               p.ag_seq[s][sb + dst] = SEL(X.seq)[slot];
               p.ag_spd[s][sb + dst] = SEL(X.spd)[slot];
-              p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
+              if (tm == PPG_TRAIT_SPEED) p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
+              else {  // predators: steps of digestion left at the next step (MR:734-740,756-757)
+                const unsigned rmn = (mode == 2 && s == 0 && slot < n[0] && (tm == PPG_TRAIT_METABOLIC || tm == PPG_TRAIT_INVESTMENT)) ? X.mord[0][slot] : 0u;
+                p.ag_dead[s][sb + dst] = (uint8_t)(rmn > 0u ? rmn - 1u : 0u);
+              }
             }
             if (s == 0) wpos[0] += __popc(ma); else wpos[1] += __popc(ma);
             if (SPLIT) {
@@ -932,6 +1058,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
   }
 }
 
+// trait variants: founders of the episode a scheduled reset will start (see draw_next_founders), after ppg_reset marked the envs
+__global__ void ppg_eco_founders_kernel(const StepParams p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.B) return;
+  EnvHdr h = p.hdr[e];
+  if (!(h.state & ST_NEEDS_RESET)) return;
+  draw_next_founders(p, h, (unsigned)(e + p.env_base));
+  p.hdr[e] = h;
+}
+
 // reals cursor of the replay tape
 __global__ void ppg_set_tape_reals_kernel(EcoHdr* ehdr, int B, const long long* real_off) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -967,6 +1103,11 @@ static cudaError_t occupancy_eco_t(size_t smem, int* blocks_per_sm) {
 cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
   if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true>(smem, blocks_per_sm);
   return map_bytes == 1 ? occupancy_eco_t<uint8_t, false>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false>(smem, blocks_per_sm);
+}
+
+cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s) {
+  ppg_eco_founders_kernel<<<(p.B + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s) {

@@ -29,8 +29,8 @@ agents that ended this step sorted by id string (STAG:567-568).
 """
 import numpy as np
 
-from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO, VARIANT_STAG,
-                     make_config)
+from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_REPRODUCED, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO,
+                     VARIANT_STAG, make_config)
 from .env import Box, Discrete, _Base, raise_on_status
 
 try:
@@ -107,6 +107,7 @@ class _RowDictEnv(_Base):
 
     _variant = None
     _stay = 0
+    _tolerated_status = 0  # status bits that are not an exception in the reference class mirrored
 
     def __init__(self, config=None):
         super().__init__()
@@ -157,7 +158,7 @@ class _RowDictEnv(_Base):
         self._done = False
         self._state = None
         out = b.outputs_numpy()
-        raise_on_status(int(out["env_status"][0]), self._variant)
+        raise_on_status(int(out["env_status"][0]) & ~self._tolerated_status, self._variant)
         return out
 
     def _step_device(self, action_dict):
@@ -188,7 +189,7 @@ class _RowDictEnv(_Base):
         b.step_ordered(t[0], t[1], t[2], t[3])
         out = b.outputs_numpy()
         self.current_step = int(out["env_step"][0])
-        raise_on_status(int(out["env_status"][0]), self._variant)
+        raise_on_status(int(out["env_status"][0]) & ~self._tolerated_status, self._variant)
         return out
 
     def _n_moves(self, agent):
@@ -427,6 +428,212 @@ class PredPreyGrassEco(_RowDictEnv):
             for key, x in zip(("speed_mean", "speed_std", "speed_p25", "speed_p50", "speed_p75", "fraction_fast", "count"), vals):
                 res[f"{role}_{key}"] = x
         return res
+
+
+# ---------------------------------------------------------------------------------------------- other heritable traits
+def reference_reset_tape_trait(seed, config, trait):
+    """The draws of the trait variants' `reset(seed)` in the tape layout of include/ppg.h (MR:189-200, genome.py
+    `founder_genome`, MR:1469-1473): `rng.integers(min, max + 1)` for the number of predators, then of prey; one
+    `rng.normal(mean, std)` per founder where std > 0 (predators then prey), clipped to the trait bounds; then one
+    `rng.choice(G*G, n, replace=False)` for the cells.  -> (ints = [n_pred, n_prey, cells...], founder trait values)"""
+    from .config import TRAIT_DEFAULTS
+
+    rng = np.random.default_rng(seed)
+    G = config["grid_size"]
+    n_max = (config["n_initial_active_predators"], config["n_initial_active_prey"])
+    n_min = (min(int(config.get("n_initial_active_predators_min", max(1, n_max[0] // 3))), n_max[0]),
+             min(int(config.get("n_initial_active_prey_min", max(1, n_max[1] // 3))), n_max[1]))
+    n = [int(rng.integers(n_min[s], n_max[s] + 1)) for s in range(2)]
+    values = []
+    if config.get("genome_enabled", True):
+        default_mean, default_bounds = TRAIT_DEFAULTS[trait]
+        lo, hi = config.get("trait_bounds", {}).get(trait, default_bounds)
+        for role, k in (("predator", n[0]), ("prey", n[1])):
+            f = config.get("founder_genome", {}).get(role, {})
+            mean, std = f.get(f"{trait}_mean", default_mean), f.get(f"{trait}_std", 0.0)
+            for _ in range(k):
+                v = mean if std <= 0 else float(rng.normal(mean, std))
+                values.append(float(np.clip(v, float(lo), float(hi))))
+    cells = rng.choice(G * G, size=n[0] + n[1] + config["initial_num_grass"], replace=False)
+    return np.concatenate([np.asarray(n, np.int32), np.asarray(cells, np.int32)]), np.asarray(values, np.float64)
+
+
+def _spearman(x, y):
+    """`_spearman_corr` (MR:1362-1368): rank correlation without tie correction"""
+    rx = np.argsort(np.argsort(x)).astype(float)
+    ry = np.argsort(np.argsort(y)).astype(float)
+    rx -= rx.mean()
+    ry -= ry.mean()
+    denom = np.sqrt((rx ** 2).sum() * (ry ** 2).sum())
+    return float(np.dot(rx, ry) / denom) if denom > 0.0 else 0.0
+
+
+class _TraitEnv(PredPreyGrassEco):
+    """Shared dict adapter of the trait variants of eco_evolutionary (MR / INV / COOP): 9 actions, 3-channel windows, a
+    random number of founders per episode, ids never reused, `infos["__all__"]["training_metrics"]` at the episode's end."""
+
+    _trait = None
+    _tolerated_status = 0x10  # PPG_STATUS_ID_POOL_EMPTY: the trait variants print a warning and skip the birth (MR:856-864)
+    _tag = None  # prefix of the reproduction-correlation keys (MR:1370-1392, COOP:1396-1418)
+
+    def __init__(self, config=None):
+        if config is None:
+            raise ValueError("Environment config must be provided explicitly.")
+        config = dict(config, ppg_trait=self._trait)
+        super().__init__(config)
+        self.n_initial_active_predators_min, self.n_initial_active_prey_min = self._cfg.n_initial_min[0], self._cfg.n_initial_min[1]
+        self._records = ({}, {})
+
+    def reset(self, *, seed=None, options=None):
+        _Base.reset(self, seed=seed)
+        if seed is None:
+            seed = self.config["seed"]  # MR:120-121
+        ints, values = reference_reset_tape_trait(seed, self.config, self._trait)
+        out = self._reset_device(seed, ints, values, options)
+        obs, *_ = self._dicts(out)
+        self.agents = list(obs)
+        st = self._read()
+        # one record per agent of the episode (`_iter_all_agent_records`, MR:1397-1404): trait value, offspring, energies
+        self._records = ({}, {})
+        for s in range(2):
+            for i, v in zip(st["ids"][s].tolist(), st["speed"][s].tolist()):
+                self._records[s][i] = self._new_record(v)
+        self.peak_active_predators = self.peak_active_prey = 0  # MR:177-178
+        return obs, {}
+
+    @staticmethod
+    def _new_record(trait_value, initial_energy=0.0):
+        return {"trait": float(trait_value), "offspring": 0, "initial_energy": float(initial_energy), "invested": [], "after": []}
+
+    def step(self, action_dict):
+        out = self._step_device(action_dict)
+        obs, rew, term, trunc = self._dicts(out)
+        flags = int(out["env_flags"][0])
+        if int(out["new_cnt0"][0]) or int(out["new_cnt1"][0]):
+            # births run in predator_positions / prey_positions order (MR:318-331) = the order of the acting rows, and the
+            # newborn rows are in birth order: the k-th parent flagged PPG_ROW_REPRODUCED is the parent of the k-th newborn
+            st = self._read()
+            for s in range(2):
+                e_of = dict(zip(st["ids"][s].tolist(), st["energy"][s].tolist()))
+                t_of = dict(zip(st["ids"][s].tolist(), st["speed"][s].tolist()))
+                parents = [int(out[f"row_agent{s}"][r]) for r in range(int(out[f"old_off{s}"][0]), int(out[f"old_off{s}"][1]))
+                           if int(out[f"flags{s}"][r]) & ROW_REPRODUCED]
+                r0 = int(out[f"new_off{s}"][0])
+                kids = [int(out[f"row_agent{s}"][r]) for r in range(r0, r0 + int(out[f"new_cnt{s}"][0]))]
+                for par, kid in zip(parents, kids):
+                    ce = float(e_of.get(kid, self._cfg.initial_energy[s]))
+                    self._records[s][kid] = self._new_record(t_of.get(kid, -1.0), ce)  # MR:908 offspring_initial_energy
+                    rec = self._records[s][par]
+                    rec["offspring"] += 1
+                    rec["invested"].append(ce)                       # MR:902-903
+                    if par in e_of:
+                        rec["after"].append(float(e_of[par]))        # MR:904-905 (reproduction is the step's last phase)
+        infos = {a: {} for a in rew}
+        term["__all__"] = bool(flags & ENV_TERMINATED)   # MR:354-374 extinction
+        trunc["__all__"] = bool(flags & ENV_TRUNCATED)   # MR:418-461 time limit
+        if flags & (ENV_TERMINATED | ENV_TRUNCATED):
+            self._done = True
+            self.agents = []
+            self._rows = {}
+            infos["__all__"] = {"training_metrics": self.episode_training_metrics()}  # MR:1394-1396, 458
+        else:
+            prev = set(self.agents)
+            self.agents = [a for a in self.agents if a in self._rows] + [a for a in self._rows if a not in prev]
+            n_pred = sum(1 for a in self.agents if "predator" in a)  # MR:466-471
+            self.peak_active_predators = max(self.peak_active_predators, n_pred)
+            self.peak_active_prey = max(self.peak_active_prey, len(self.agents) - n_pred)
+        return obs, rew, term, trunc, infos
+
+    @property
+    def agent_traits(self):
+        """`{agent: getattr(agent_genomes[agent], <trait>)}`"""
+        return self.agent_speeds
+
+    def episode_training_metrics(self):
+        """`_build_episode_training_metrics` of the trait variants (MR:1274-1392): the trait distribution and the per-agent
+        means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the rank correlation
+        between the trait and having reproduced.  Distance and locomotion totals come from the device
+        (ppg_read_episode_eco).  Not emitted: the `*_reproduction_blocked*` / `predator_satiation_blocked_catches` event
+        counters and COOP's donation totals / relatedness proxy."""
+        ep = self._batch.read_episode_eco(0)
+        res, t = {}, self._trait
+        for s, role in enumerate(("predator", "prey")):
+            recs = list(self._records[s].values())
+            v = np.asarray([r["trait"] for r in recs if self.genome_enabled], np.float64)
+            if v.size:
+                p25, p50, p75 = np.percentile(v, [25, 50, 75])
+                vals = (float(np.mean(v)), float(np.std(v)), float(p25), float(p50), float(p75))
+            else:
+                vals = (0.0,) * 5
+            for key, x in zip(("mean", "std", "p25", "p50", "p75"), vals):
+                res[f"{role}_{t}_{key}"] = x
+            if recs:
+                n = len(recs)
+                res[f"{role}_distance_traveled_mean"] = ep["distance"][s] / n
+                res[f"{role}_movement_energy_spent_mean"] = ep["move_energy"][s] / n
+                res[f"{role}_offspring_count_mean"] = float(np.mean([float(r["offspring"]) for r in recs]))
+                res[f"{role}_agent_count"] = float(n)
+                res[f"{role}_offspring_initial_energy_mean"] = float(np.mean([r["initial_energy"] for r in recs]))
+                inv = [sum(r["invested"]) / len(r["invested"]) for r in recs if r["invested"]]
+                aft = [sum(r["after"]) / len(r["after"]) for r in recs if r["after"]]
+                res[f"{role}_reproduction_energy_invested_mean"] = float(np.mean(inv)) if inv else 0.0
+                res[f"{role}_parent_energy_after_reproduction_mean"] = float(np.mean(aft)) if aft else 0.0
+            else:
+                for key in ("distance_traveled_mean", "movement_energy_spent_mean", "offspring_count_mean", "agent_count",
+                            "offspring_initial_energy_mean", "reproduction_energy_invested_mean", "parent_energy_after_reproduction_mean"):
+                    res[f"{role}_{key}"] = 0.0
+        res["predator_spawned_total"] = float(ep["spawned"][0])
+        res["prey_spawned_total"] = float(ep["spawned"][1])
+        res["peak_active_predators"] = float(self.peak_active_predators)
+        res["peak_active_prey"] = float(self.peak_active_prey)
+        res["prey_unique_ids_used"] = float(len(self._records[1]))
+        res["predator_unique_ids_used"] = float(len(self._records[0]))
+        if self._tag and self.genome_enabled:
+            for s, role in ((1, "prey"), (0, "predator")):
+                recs = list(self._records[s].values())
+                if len(recs) < 4:
+                    continue
+                x = np.array([r["trait"] for r in recs])
+                y = np.array([float(r["offspring"] > 0) for r in recs])
+                res[f"{role}_{self._tag}_repro_spearman"] = _spearman(x, y)
+                q25, q50, q75 = np.percentile(x, [25, 50, 75])
+                for k, m in enumerate((x <= q25, (x > q25) & (x <= q50), (x > q50) & (x <= q75), x > q75), 1):
+                    if m.sum() > 0:
+                        res[f"{role}_{self._tag}_repro_rate_q{k}"] = float(y[m].mean())
+        return res
+
+    def live_genome_metrics(self):
+        """`_build_live_genome_metrics` (MR:476-504): trait distribution of the live population, same keys"""
+        st = self._read()
+        res, t = {}, self._trait
+        for s, role in enumerate(("predator", "prey")):
+            v = np.asarray(st["speed"][s], np.float64) if self.genome_enabled else np.zeros(0)
+            if v.size:
+                p25, p50, p75 = np.percentile(v, [25, 50, 75])
+                vals = (float(v.mean()), float(v.std()), float(p25), float(p50), float(p75), float(v.size))
+            else:
+                vals = (0.0,) * 6
+            for key, x in zip((f"{t}_mean", f"{t}_std", f"{t}_p25", f"{t}_p50", f"{t}_p75", "count"), vals):
+                res[f"{role}_{key}"] = x
+        return res
+
+
+class PredPreyGrassMetabolicRate(_TraitEnv):
+    """eco_evolutionary_metabolic_rate `PredPreyGrass(config)`: heritable metabolic rate (basal cost x rate, gains x rate ** alpha)."""
+
+    _trait, _tag = "metabolic_rate", "mr"
+
+
+class PredPreyGrassInvestment(_TraitEnv):
+    """eco_evolutionary_investment `PredPreyGrass(config)`: heritable offspring investment fraction (child energy = parent's x fraction)."""
+
+    _trait, _tag = "offspring_investment_fraction", None
+
+
+class PredPreyGrassCooperation(_TraitEnv):
+    """eco_evolutionary_cooperation `PredPreyGrass(config)`: heritable cooperation rate (a share of every meal goes to neighbours)."""
+
+    _trait, _tag = "cooperation_rate", "coop"
 
 
 # ---------------------------------------------------------------------------------------------- STAG

@@ -32,3 +32,18 @@ def test_adapters_need_a_config_like_the_reference():
     for cls in (PredPreyGrassEco, PredPreyGrassStag):
         with pytest.raises(ValueError):  # ECO:21-22, STAG:21-22
             cls(None)
+
+
+TRAIT_OF = {"mr": "metabolic_rate", "inv": "offspring_investment_fraction", "coop": "cooperation_rate"}
+
+
+@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop")))
+def test_trait_reset_tape_equals_the_reference_reset(name):
+    """founder counts (MR:189-192), founder trait values (genome.py founder_genome) and cells (MR:1473) of the variants"""
+    from predpreygrass_b200.env_evolutionary import reference_reset_tape_trait
+
+    z, cfg = load_golden(name)
+    ints, values = reference_reset_tape_trait(int(z["seed"]), cfg, TRAIT_OF[cfg["variant"]])
+    assert np.array_equal(ints[:2], z["n_found"])
+    assert np.array_equal(ints[2:], z["init_cells"])
+    assert np.array_equal(values, z["founder_trait"])

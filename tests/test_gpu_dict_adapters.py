@@ -170,3 +170,61 @@ def test_eco_adapter_time_limit_reports_training_metrics():
     assert len(m) == 20 and m["predator_agent_count"] == 1.0 and 0.5 <= m["predator_speed_mean"] <= 2.0
     assert m["prey_distance_traveled_mean"] == 0.0 and m["prey_offspring_count_mean"] == 0.0
     env.close()
+
+
+@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop")))
+def test_trait_dict_adapter_replays_reference_episode(name):
+    """PredPreyGrassMetabolicRate / Investment / Cooperation through the reference's dict API: reset(seed) with the adapter's
+    own reproduction of the reset draws (founder counts included), then the recorded episode; at the episode's end the
+    `training_metrics` of the reference's own run (stored in the golden file) for every key the adapter emits."""
+    from predpreygrass_b200 import env_evolutionary as E
+
+    z, cfg = load_golden(name)
+    cls = {"mr": E.PredPreyGrassMetabolicRate, "inv": E.PredPreyGrassInvestment, "coop": E.PredPreyGrassCooperation}[cfg.pop("variant")]
+    cfg["cap_live"] = _caps(cfg, (("n_possible_predators",), ("n_possible_prey",)))
+    env = cls(cfg)
+    names = ("predator", "prey")
+    key = lambda s, i: f"{names[s]}_{i}"  # noqa: E731
+    obs, infos = env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    assert infos == {}
+    assert list(obs) == [key(s, i) for s, i in zip(z["reset_row_s"], z["reset_row_id"])]
+    assert np.array_equal(sha_f32([obs[k] for k in obs]), z["reset_sha"])
+    for a, o in obs.items():
+        assert o.dtype == np.float32 and o.shape == env.observation_spaces[a].shape
+    ended = False
+    for t in range(len(z["steps"])):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {key(s, i): int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        obs, rew, term, trunc, infos = env.step(acts)
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        keys = [key(s, i) for s, i in zip(z["row_s"][r0:r1], z["row_id"][r0:r1])]
+        assert list(obs) == keys and list(rew) == keys, (name, t)
+        assert np.array_equal(np.array([rew[k] for k in keys], np.float32), z["row_rew"][r0:r1].astype(np.float32)), (name, t)
+        assert [int(term[k]) for k in keys] == list(z["row_term"][r0:r1]), (name, t)
+        assert [int(trunc[k]) for k in keys] == list(z["row_trunc"][r0:r1]), (name, t)
+        assert np.array_equal(sha_f32([obs[k] for k in keys]), z["obs_sha"][t]), (name, t)
+        assert term["__all__"] == bool(z["all_term"][t]) and trunc["__all__"] == bool(z["all_trunc"][t]), (name, t)
+        assert env.current_step == int(z["steps"][t])
+        if term["__all__"] or trunc["__all__"]:
+            ended = True
+            assert env.agents == []
+            want = json.loads(str(z["metrics_json"]))
+            got = infos["__all__"]["training_metrics"]
+            assert set(got) <= set(want), (name, sorted(set(got) - set(want)))
+            missing = {k for k in want if k not in got}
+            assert all("blocked" in k or "donated" in k or "received" in k or "relatedness" in k for k in missing), (name, sorted(missing))
+            for k, v in got.items():
+                assert v == pytest.approx(want[k], rel=1e-9, abs=1e-12), (name, k, v, want[k])
+            break
+        g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]
+        assert env.agents == [key(s, i) for s, i in zip(z["ag_s"][g0:g1], z["ag_id"][g0:g1])], (name, t)
+        s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+        want = {key(s, i): ((int(x), int(y)), float(e), int(a), float(v)) for s, i, x, y, e, a, v in
+                zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_x"][s0:s1], z["st_y"][s0:s1], z["st_e"][s0:s1],
+                    z["st_age"][s0:s1], z["st_trait"][s0:s1])}
+        pos, en, age, tr = env.agent_positions, env.agent_energies, env.agent_ages, env.agent_traits
+        assert sorted(pos) == sorted(want), (name, t)
+        assert all((pos[k], en[k], age[k], tr[k]) == want[k] for k in want), (name, t)
+        assert (env.active_num_predators, env.active_num_prey) == tuple(z["active"][t])
+    assert ended or str(z["metrics_json"]) == "null"
+    env.close()
