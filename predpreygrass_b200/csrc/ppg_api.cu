@@ -30,7 +30,7 @@ cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_
 cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm);
 // ppg_eco.cu
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm);
+cudaError_t step_eco_occupancy(int map_bytes, bool split, bool traits, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
 cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s);
 // ppg_stag.cu
@@ -164,6 +164,7 @@ const char* ppg_last_error(ppg_handle h) { return h ? h->err.c_str() : g_err.c_s
 static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
   if (!c || c->struct_size != sizeof(ppg_config)) { err = "ppg_config.struct_size mismatch"; return PPG_ERR_INVALID; }
   if (n_envs <= 0) { err = "n_envs must be positive"; return PPG_ERR_INVALID; }
+  if (n_envs > 255 * 1024) { err = "n_envs must be <= 261120 per handle (contributor field of the row-allocation accumulators)"; return PPG_ERR_INVALID; }
   if (c->variant != PPG_VARIANT_BASE && c->variant != PPG_VARIANT_ECO && c->variant != PPG_VARIANT_STAG) { err = "unknown variant"; return PPG_ERR_INVALID; }
   const bool eco = c->variant == PPG_VARIANT_ECO, stag = c->variant == PPG_VARIANT_STAG;
   if (c->reward_mode < 0 || c->reward_mode > PPG_REWARD_SPARSE_KICKBACK) { err = "bad reward_mode"; return PPG_ERR_INVALID; }
@@ -443,7 +444,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    if (eco) CKC(step_eco_occupancy(P.map_bytes, P.obs_split != 0, h->smem_bytes, &per_sm));
+    if (eco) CKC(step_eco_occupancy(P.map_bytes, P.obs_split != 0, P.trait_mode != PPG_TRAIT_SPEED, h->smem_bytes, &per_sm));
     else if (stag) CKC(step_stag_occupancy(P.map_bytes, P.obs_split != 0, h->smem_bytes, &per_sm));
     else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, P.obs_split != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -477,8 +478,12 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
       CKC(dalloc(h, &P.cntA[q], (size_t)B)); CKC(dalloc(h, &P.cntB[q], (size_t)B));
       CKC(dalloc(h, &P.sum1[q], n_blk * 4)); CKC(dalloc(h, &P.sum2[q], n_grp * 4));
     }
-    CKC(dalloc(h, &P.done1, n_blk)); CKC(dalloc(h, &P.done2, n_grp)); CKC(dalloc(h, &P.done3, 1));
+    CKC(dalloc(h, &P.acc1, n_blk * 2)); CKC(dalloc(h, &P.acc2, n_grp * 2)); CKC(dalloc(h, &P.acc3, 2));
     CKC(dalloc(h, &P.totals, 8));
+    // big-envs-first order of the next launch: only where no env ever waits for another one (publish_begin)
+    bool lpt = !eco && P.obs_split;
+    if (const char* ev = getenv("PPG_ENV_ORDER")) lpt = lpt && atoi(ev) != 0;
+    if (lpt) { for (int q = 0; q < 2; ++q) CKC(dalloc(h, &P.perm[q], (size_t)B)); CKC(dalloc(h, &P.perm_tag, 2)); CKC(dalloc(h, &P.perm_cursor, 4)); CKC(cudaMemset(P.perm_tag, 0xFF, 2 * sizeof(unsigned))); }  // no epoch carries tag 0xFFFFFFFF
   }
   if (eco) {
     CKC(dalloc(h, &P.ehdr, (size_t)B));
@@ -611,7 +616,6 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   StepParams& P = h->P;
   P.actions[0] = a0; P.actions[1] = a1;
   P.order[0] = o0; P.order[1] = o1;
-  // every launch draws B tickets plus one terminating draw per warp
   P.ticket_base = h->ticket_next;
   // tickets: one per env (W == 1) or per group of W envs, plus one terminating draw per warp / CTA
   h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta

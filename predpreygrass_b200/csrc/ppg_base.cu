@@ -49,6 +49,8 @@
 
 namespace ppg {
 
+PHASE_DEFINE(base)
+
 // ------------------------------------------------------------------------------------------------
 // the step kernel: W persistent warps per CTA, one env per warp at a time
 // ------------------------------------------------------------------------------------------------
@@ -75,21 +77,40 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
   // one-time set-up of this warp's slice: empty maps (predator map: WALL outside the field), zeroed touch
   // counters, wall table — copied from the image ppg_create built.  Every env leaves the maps empty again
   // (it un-writes the cells it wrote).
-  #pragma unroll 1
-  for (int i = lane; i < p.init_bytes / 16; i += 32)
-    reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i);
+  {
+    const int n16 = p.init_bytes / 16;
+    #pragma unroll 1
+    for (int i0 = 0; i0 < n16; i0 += 32 * 8) {  // 8 loads in flight per lane: one round trip per 4 KB, not per 512 B
+      uint4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int i = i0 + 32 * q + lane; if (i < n16) v[q] = __ldg(reinterpret_cast<const uint4*>(p.init_image) + i); }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int i = i0 + 32 * q + lane; if (i < n16) reinterpret_cast<uint4*>(sbase + p.so_map[0])[i] = v[q]; }
+    }
+  }
   unsigned rowctr = 0;
   const int n_old_total[2] = {p.totals[(par ^ 1) * 4 + 0], p.totals[(par ^ 1) * 4 + 1]};
   const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
   __syncwarp();
 
+  // W == 1: envs come from the ticket counter; after the first one the ticket is drawn by lane 0 while the previous env is
+  // still being finished (`env_next`: late enough that the schedule stays dynamic, early enough that the atomic's round
+  // trip is never waited for).  Tickets are handed out in env order to warps that are running, so an env that waits for
+  // the publication of a lower env (ECO's episode-end rows, the one-kernel step) always waits for a running warp.
+  // ticket -> env: big envs first when the previous launch left an order (publish_begin), else index order
+  const int32_t* const perm = (W == 1 && SPLIT && p.perm[par ^ 1] != nullptr && p.perm_tag[par ^ 1] == epoch - 1u) ? p.perm[par ^ 1] : nullptr;
+  int env_next = 0;
+  if (W == 1 && lane == 0) {
+    env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+  }
+  unsigned long long pend = 0ULL;  // lane 0: completion-queue slot + 1 of the env whose hand-over is still owed (queue_push)
+  int pend_env = 0;
   for (;;) {
+    PHASE_DECL
     int env = 0;  // PHASE: ticket+hdr
     if (W == 1) {
-      // (drawing the NEXT env's ticket ahead of time would hide the atomic's round trip, but with < 2 waves of envs it
-      // turns the dynamic schedule into a static two-envs-per-warp one and lengthens the tail)
-      if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-      env = __shfl_sync(FULL, env, 0);
+      env = __shfl_sync(FULL, env_next, 0);
       if (env >= p.B) break;
     } else {
       // the W warps of a CTA take W consecutive envs and start them together: warps of one CTA then run the
@@ -114,13 +135,42 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
     int cur[2] = {0, 0};
     bool over = false, trunc = false;
 
+    PHASE_MARK(0)
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
+    // ONE round trip for everything the env needs from HBM/L2: the header, the prefix words, the first entries of both
+    // agent lists (speculatively: how many are valid is in the header) and the grass patches are all requested before any
+    // of them is looked at; under the observation kernel's write stream a round trip costs microseconds, so the number of
+    // DEPENDENT round trips per env is what the step kernel's duration is made of.
     EnvHdr h = p.hdr[env];
+    int prow_r[3] = {0, 0, 0};
+    double e_r[3] = {0.0, 0.0, 0.0};
+    unsigned idpos_r[3] = {0, 0, 0}, par_r[3] = {0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {  // q = 0: predators 0..31, q = 1, 2: prey 0..63
+      const int s = q ? 1 : 0, i = lane + (q == 2 ? 32 : 0);
+      if (i < p.cap[s]) {
+        const size_t b = (size_t)env * p.cap[s] + i;
+        prow_r[q] = p.ag_prow[s][b];
+        e_r[q] = p.ag_e[s][b];
+        idpos_r[q] = (unsigned)p.ag_id[s][b] | ((unsigned)p.ag_pos[s][b] << 16);
+        if (kick) par_r[q] = p.ag_par[s][b];
+      }
+    }
+    unsigned gp_r[4] = {0, 0, 0, 0};
+    double ge_r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int g = lane + 32 * q;
+      if (g < p.n_grass) { gp_r[q] = p.gr_pos[(size_t)env * p.n_grass + g]; ge_r[q] = p.gr_e[(size_t)env * p.n_grass + g]; }
+    }
     // first old row of this env: the previous launch published how many rows every env needs now
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
       if (lane == 0) atomicOr(p.error, 2u);  // the host did not prepare the counts of the previous output
     }
+    // hand-over of the PREVIOUS env of this warp: its stores were issued a round trip ago, the fence finds them acknowledged
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
+    PHASE_MARK(1)
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
@@ -193,10 +243,43 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
       cur[0] = n[0]; cur[1] = n[1];
       next_live[0] = n[0]; next_live[1] = n[1];
       env_flags = PPG_ENV_RESET;
+      PHASE_MARK(2)
     } else if (mode == 2) {
       // ------------------------------------------------------------------ step() (BASE:219-473)
       n[0] = h.n_list[0]; n[1] = h.n_list[1];  // PHASE: load+decay+maps
-      // load the lists; list order = action-dict order (default: row order of the previous output)
+      // second (and last) dependent round trip: the actions of the rows the agents occupied in the previous output
+      int act_r[3] = {4, 4, 4};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int s = q ? 1 : 0, i = lane + (q == 2 ? 32 : 0);
+        if (i < SEL(n)) act_r[q] = p.actions[s][prow_r[q]];
+      }
+      // meanwhile: grass regrowth (BASE:252-256) from the registers
+      {
+        // base_environment_seasonal: square-wave multiplier on the regrowth, phase from the step counter (SEASON:224-234)
+        const double grass_gain = p.season_len > 0 ? p.grass_gain_season[(h.step / p.season_len) & 1] : p.grass_gain;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g = lane + 32 * q;
+          if (g < p.n_grass) {
+            S.gpos[g] = (uint16_t)gp_r[q];
+            const double v = ge_r[q] + grass_gain;
+            S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+            S.map[2][CELLP(gp_r[q])] = (MapT)(g + 1);
+          }
+        }
+        #pragma unroll 1
+        for (int g = lane + 128; g < p.n_grass; g += 32) {  // more than 128 patches: the rest the plain way
+          const size_t b = (size_t)env * p.n_grass;
+          const unsigned gp = p.gr_pos[b + g];
+          S.gpos[g] = (uint16_t)gp;
+          const double v = p.gr_e[b + g] + grass_gain;
+          S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+          S.map[2][CELLP(gp)] = (MapT)(g + 1);
+        }
+      }
+      PHASE_MARK(4)
+      // the lists; list order = action-dict order (default: row order of the previous output)
       unsigned bad = 0;
       bool resort[2] = {false, false};
 #pragma unroll 1
@@ -224,34 +307,39 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         if (s == 0) resort[0] = use_order; else resort[1] = use_order;
         #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
-          const int prow = p.ag_prow[s][b + i];
+          // entries 0..31 (predators) / 0..63 (prey) are already in registers, with their actions
+          const int q = s == 0 ? (i < 32 ? 0 : 3) : (i < 32 ? 1 : (i < 64 ? 2 : 3));
+          int prow, a;
+          double e;
+          unsigned idpos, par16 = 0;
+          if (q < 3) {
+            prow = q == 0 ? prow_r[0] : (q == 1 ? prow_r[1] : prow_r[2]);
+            e = q == 0 ? e_r[0] : (q == 1 ? e_r[1] : e_r[2]);
+            idpos = q == 0 ? idpos_r[0] : (q == 1 ? idpos_r[1] : idpos_r[2]);
+            a = q == 0 ? act_r[0] : (q == 1 ? act_r[1] : act_r[2]);
+            if (kick) par16 = q == 0 ? par_r[0] : (q == 1 ? par_r[1] : par_r[2]);
+          } else {
+            prow = p.ag_prow[s][b + i];
+            e = p.ag_e[s][b + i];
+            idpos = (unsigned)p.ag_id[s][b + i] | ((unsigned)p.ag_pos[s][b + i] << 16);
+            a = p.actions[s][prow];
+            if (kick) par16 = p.ag_par[s][b + i];
+          }
           const int d = use_order ? ordp[prow] : i;
-          const double e = p.ag_e[s][b + i];
-          int a = p.actions[s][prow];
           if ((unsigned)a > 8u) { a = 4; bad = PPG_STATUS_BAD_ACTION; }  // reference: KeyError BASE:502
-          SEL(S.id)[d] = p.ag_id[s][b + i];
-          SEL(S.pos)[d] = p.ag_pos[s][b + i];
+          SEL(S.id)[d] = (uint16_t)idpos;
+          SEL(S.pos)[d] = (uint16_t)(idpos >> 16);
           if (dense) SEL(S.E0)[d] = e;  // energy_before (ADD:256)
           SEL(S.E)[d] = e - p.loss[s];  // Step 1 (BASE:244-250)
           SEL(S.act)[d] = (uint8_t)a;
           SEL(S.flg)[d] = F_ALIVE;
           SEL(S.ord)[d] = (uint16_t)d;
           SEL(S.rnk)[d] = (uint16_t)d;
-          if (kick) { SEL(S.par)[d] = p.ag_par[s][b + i]; SEL(S.aux)[d] = 0; }
+          if (kick) { SEL(S.par)[d] = (uint16_t)par16; SEL(S.aux)[d] = 0; }
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
-      // base_environment_seasonal: square-wave multiplier on the regrowth, phase from the step counter (SEASON:224-234)
-      const double grass_gain = p.season_len > 0 ? p.grass_gain_season[(h.step / p.season_len) & 1] : p.grass_gain;
-      #pragma unroll 1
-      for (int g = lane; g < p.n_grass; g += 32) {
-        const size_t b = (size_t)env * p.n_grass;
-        const unsigned gp = p.gr_pos[b + g];
-        S.gpos[g] = (uint16_t)gp;
-        const double v = p.gr_e[b + g] + grass_gain;  // regrowth (BASE:252-256)
-        S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
-        S.map[2][CELLP(gp)] = (MapT)(g + 1);
-      }
+      PHASE_MARK(3)
       __syncwarp();
       // owner maps as the grid stands after Step 1: of agents sharing a cell the one latest in dict
       // order wrote last (BASE:247,250)
@@ -271,6 +359,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           }
         }
       __syncwarp();
+      PHASE_MARK(5)
 
       // Step 2: movements, sequential semantics in dict order per species (BASE:259-273,495-509)  // PHASE: movement
 #pragma unroll 1
@@ -327,6 +416,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         }
       }
 
+      PHASE_MARK(6)
       // deferred `self.agents.sort()` of the previous call (BASE:468): engagement order.  The list is  // PHASE: sort
       // the sorted survivors followed by last step's newborns, so only the newborns have to be ranked in.
 #pragma unroll 1
@@ -352,29 +442,33 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         }
       }
 
+      PHASE_MARK(7)
       // Step 3a: predators in engagement order (BASE:279-346).  Nothing happens unless a predator  // PHASE: predators
       // starved or some prey (any energy) stands on a live predator's cell.
-      bool ev = false;
+      // Only predators that starved or share their cell with a prey do anything (the others keep their step reward), and
+      // what one predator does can only remove prey from later ones: the candidates are found lane-parallel (prey cells
+      // marked in the touch counters) and only they run the sequential loop, in engagement order.
+      bool vt_valid = false;  // value tables current (refreshed once, then kept up to date entry by entry)
       #pragma unroll 1
-      for (int i = lane; i < n[0]; i += 32) {
-        if (S.E[0][i] <= 0.0) ev = true;
-        else S.scr[CELLP((unsigned)S.pos[0][i])] = 1;
-      }
+      for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 1;
       __syncwarp();
-      #pragma unroll 1
-      for (int i = lane; i < n[1]; i += 32) ev |= S.scr[CELLP((unsigned)S.pos[1][i])] != 0;
-      __syncwarp();
-      #pragma unroll 1
-      for (int i = lane; i < n[0]; i += 32) S.scr[CELLP((unsigned)S.pos[0][i])] = 0;
-      __syncwarp();
-      if (__any_sync(FULL, ev)) {
-        for (int k = 0; k < n[0]; ++k) {
+      for (int b0 = 0; b0 < n[0]; b0 += 32) {
+        bool evk = false;
+        if (b0 + lane < n[0]) {
+          const int sl = S.ord[0][b0 + lane];
+          evk = S.E[0][sl] <= 0.0 || S.scr[CELLP((unsigned)S.pos[0][sl])] != 0;
+        }
+        unsigned evm = __ballot_sync(FULL, evk);
+        while (evm) {
+          const int k = b0 + __ffs(evm) - 1;
+          evm &= evm - 1;
           const int slot = S.ord[0][k];
           const unsigned ps = S.pos[0][slot];
           const int cell = CELLP(ps);
           double e = S.E[0][slot];
           if (e <= 0.0) {  // starved (BASE:284-301): observation as of now
-            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, n[0], n[1], rowctr, lane);
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[0] + (size_t)(old_base[0] + k) * p.elems[0], cell, 0, vt_valid ? -1 : n[0], n[1], rowctr, lane);
+            vt_valid = true;
             if (lane == 0) {
               S.map[0][cell] = 0;  // BASE:293
               S.flg[0][slot] = F_DIED;
@@ -395,11 +489,13 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
             __syncwarp();
             if (lane == 0) {
               S.E[0][slot] = e;
+              if (vt_valid) S.vt[0][1 + slot] = (float)e;
               S.map[0][cell] = (MapT)(slot + 1);  // BASE:325
               S.flg[0][slot] |= F_ATE;
             }
             __syncwarp();
-            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, n[0], n[1], rowctr, lane);  // BASE:327
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + S.rnk[1][q]) * p.elems[1], cell, 1, vt_valid ? -1 : n[0], n[1], rowctr, lane);  // BASE:327
+            vt_valid = true;
             if (lane == 0) {
               S.map[1][cell] = 0;  // BASE:335
               S.flg[1][q] = F_DIED | F_CAUGHT;
@@ -409,7 +505,11 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           }
         }
       }
+      #pragma unroll 1
+      for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 0;
+      __syncwarp();
 
+      PHASE_MARK(8)
       // Step 3b: prey in engagement order (BASE:347-380)  // PHASE: prey
       for (int b0 = 0; b0 < n[1]; b0 += 32) {
         const int k = b0 + lane;
@@ -430,10 +530,12 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         const bool clash = eat && S.gtag[g - 1] != (uint8_t)lane;  // two prey of this chunk on one patch
         if (!__any_sync(FULL, starved || clash)) {
           if (eat) {  // BASE:351-372 (a patch with energy 0 is still "eaten")
-            S.E[1][slot] = e + S.gE[g - 1];
+            const double en = e + S.gE[g - 1];
+            S.E[1][slot] = en;
             S.map[1][cell] = (MapT)(slot + 1);
             S.gE[g - 1] = 0.0;
             S.flg[1][slot] |= F_ATE;
+            if (vt_valid) { S.vt[1][1 + slot] = (float)en; S.vt[2][g] = 0.f; }
           }
           st_grass += __popc(__ballot_sync(FULL, eat));
           __syncwarp();
@@ -447,7 +549,8 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           const int cl = CELLP((unsigned)S.pos[1][sl]);
           const double ee = S.E[1][sl];
           if (ee <= 0.0) {  // BASE:284-301
-            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, n[0], n[1], rowctr, lane);
+            rowctr = emit_row_now<MapT, BULK>(sbase, p, p.obs[1] + (size_t)(old_base[1] + kk) * p.elems[1], cl, 1, vt_valid ? -1 : n[0], n[1], rowctr, lane);
+            vt_valid = true;
             if (lane == 0) {
               S.map[1][cl] = 0;
               S.flg[1][sl] = F_DIED;
@@ -465,6 +568,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
               S.map[1][cl] = (MapT)(sl + 1);
               S.gE[gg - 1] = 0.0;
               S.flg[1][sl] |= F_ATE;
+              if (vt_valid) { S.vt[1][1 + sl] = (float)en; S.vt[2][gg] = 0.f; }
             }
             st_grass++;
             __syncwarp();
@@ -472,6 +576,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         }
       }
       __syncwarp();
+      PHASE_MARK(9)
 
       // Step 5: births in engagement order, predators then prey (BASE:389-448)  // PHASE: births
 #pragma unroll 1
@@ -560,6 +665,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         }
       }
       __syncwarp();
+      PHASE_MARK(10)
 
       // counts, termination, truncation (BASE:456-471)  // PHASE: counts
 #pragma unroll
@@ -583,9 +689,21 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
       env_flags = PPG_ENV_IDLE;
     }
 
+    PHASE_MARK(11)
     // ---------------------------------------------------------------- publish the counts  // PHASE: publish
-    if (mode == 2) publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    // four atomics back to back, nobody waits for them here: the warp's next env, this env's slot in the completion queue,
+    // and the two accumulators of the row allocation (results looked at after the rows are written)
+#if PPG_TICKET_EARLY
+    if (W == 1 && lane == 0) {
+      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+    }
+#endif
+    unsigned long long q_slot = 0ULL, pubA = 0ULL, pubB = 0ULL;
+    if (SPLIT) q_slot = queue_reserve(p, lane);
+    if (mode == 2) publish_begin(p, env, par, epoch, next_live, births, lane, pubA, pubB, (n_old_total[0] + n_old_total[1]) / p.B * 5 / 4);
 
+    PHASE_MARK(12)
     // ------------------------------------------------- rows: metadata, observations, state write-back  // PHASE: rows pass1
     if (lane == 0) {
       p.old_off[0][env] = old_base[0];
@@ -594,6 +712,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
     if (mode != 0) {
       const bool keep = !(over && p.autoreset);  // lists of a finished env are dead when it auto-resets
       refresh_tables(S, p, n[0] + births[0], n[1] + births[1], lane);
+      PHASE_MARK(13)
       int wpos[2] = {0, 0};
       int new_base[2] = {0, 0};
       for (int pass = 0; pass < 2; ++pass) {  // 0: rows of the agents that acted, 1: newborn rows
@@ -696,12 +815,15 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         }
       }
       }
+      PHASE_MARK(14)
+      if (mode == 2) publish_end(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane, pubA, pubB);
       if (lane < 2) {  // PHASE: tail
         const int nb = lane == 0 ? births[0] : births[1];
         if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
         p.new_cnt[lane][env] = nb;
       }
       if (SPLIT) dump_image(sbase, p, env, mode, keep, old_base, n, births, lane);  // before the maps are un-written
+      PHASE_MARK(15)
       // leave the maps empty for the next env of this warp: un-write every cell that can hold an entry
       // (a non-zero owner entry always has its owner standing on it)
 #pragma unroll
@@ -732,27 +854,25 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
         }
       }
+      PHASE_MARK(16)
       if (over) h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;  // idle: final state stays readable
       if (lane == 0) p.hdr[env] = h;
-      // per-env counters (PPG_STAT_*)
+      // per-env counters (PPG_STAT_*): lane k adds statistic k (selects, no divergent switch)
       if (lane < PPG_N_STATS) {
         unsigned add = 0;
         if (mode == 2) {
-          switch (lane) {
-            case PPG_STAT_ENV_STEPS: add = 1; break;
-            case PPG_STAT_AGENT_STEPS: add = n[0] + n[1]; break;
-            case PPG_STAT_EPISODES: add = over; break;
-            case PPG_STAT_EPISODE_STEPS: add = over ? h.step : 0; break;
-            case PPG_STAT_BIRTHS_PRED: add = births[0]; break;
-            case PPG_STAT_BIRTHS_PREY: add = births[1]; break;
-            case PPG_STAT_STARVED_PRED: add = st_starved[0]; break;
-            case PPG_STAT_STARVED_PREY: add = st_starved[1]; break;
-            case PPG_STAT_EATEN_PREY: add = st_eaten; break;
-            case PPG_STAT_GRASS_EATEN: add = st_grass; break;
-            case PPG_STAT_TRUNCATED: add = trunc; break;
-            case PPG_STAT_SPAWN_FALLBACK: add = st_fallback; break;
-            default: break;
-          }
+          add = lane == PPG_STAT_ENV_STEPS ? 1u : add;
+          add = lane == PPG_STAT_AGENT_STEPS ? (unsigned)(n[0] + n[1]) : add;
+          add = lane == PPG_STAT_EPISODES ? (unsigned)over : add;
+          add = lane == PPG_STAT_EPISODE_STEPS ? (over ? h.step : 0u) : add;
+          add = lane == PPG_STAT_BIRTHS_PRED ? (unsigned)births[0] : add;
+          add = lane == PPG_STAT_BIRTHS_PREY ? (unsigned)births[1] : add;
+          add = lane == PPG_STAT_STARVED_PRED ? st_starved[0] : add;
+          add = lane == PPG_STAT_STARVED_PREY ? st_starved[1] : add;
+          add = lane == PPG_STAT_EATEN_PREY ? st_eaten : add;
+          add = lane == PPG_STAT_GRASS_EATEN ? st_grass : add;
+          add = lane == PPG_STAT_TRUNCATED ? (unsigned)trunc : add;
+          add = lane == PPG_STAT_SPAWN_FALLBACK ? st_fallback : add;
         }
         if (lane == PPG_STAT_ROWS_PRED) add = n[0] + births[0];
         if (lane == PPG_STAT_ROWS_PREY) add = n[1] + births[1];
@@ -773,8 +893,21 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
       p.env_count[2 * env] = mode == 0 ? h.n_list[0] : cur[0];
       p.env_count[2 * env + 1] = mode == 0 ? h.n_list[1] : cur[1];
     }
+    if (SPLIT && lane == 0) { pend = q_slot + 1ULL; pend_env = env; }  // handed over from the top of the loop (queue_push)
     __syncwarp();
+#if !PPG_PUSH_DEFER
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
+#endif
+#if !PPG_TICKET_EARLY
+    if (W == 1 && lane == 0) {
+      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+    }
+#endif
+    PHASE_MARK(17)
+    PHASE_FLUSH(base)
   }
+  if (SPLIT) queue_push(p, pend, pend_env, lane);
   if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the engine has read it
 }
 

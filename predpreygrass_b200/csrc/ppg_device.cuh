@@ -117,10 +117,15 @@ struct StepParams {
   unsigned long long* cntB[2];
   unsigned long long* sum1[2];
   unsigned long long* sum2[2];
-  unsigned* done1;   // [n_blk] finished envs per block (monotonic)
-  unsigned* done2;   // [n_grp] finished blocks per group (monotonic)
-  unsigned* done3;   // [1] finished groups (monotonic)
+  // accumulators of the publication (ppg_step_common.cuh): contributors << 56 | first sum << 28 | second sum, [.][0] the
+  // live counts, [.][1] the births; cleared by the last contributor of every launch
+  unsigned long long* acc1;  // [n_blk][2] per 32-env block
+  unsigned long long* acc2;  // [n_grp][2] per 1024-env group
+  unsigned long long* acc3;  // [2]
   int32_t* totals;   // [2][4] per parity: total {live_pred, live_prey, births_pred, births_prey}
+  int32_t* perm[2];  // [B] per parity: env order of the next launch, big envs first (publish_begin); nullptr: index order
+  unsigned* perm_tag;  // [2] epoch that wrote perm[par] (anything else: index order)
+  unsigned* perm_cursor;  // [2][2] per parity: entries taken from the front (big envs) / from the back
   const int32_t* order[2];  // optional: rank of each row inside its env+species in the action dict (ppg_step_ordered)
   // ---- io ----
   const int32_t* actions[2];

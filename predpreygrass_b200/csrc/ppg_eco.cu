@@ -157,7 +157,10 @@ __device__ __noinline__ double coop_donation(unsigned char* sbase, const StepPar
   return gain - total;
 }
 
-template <int W, typename MapT, bool SPLIT>
+// TRAITS: false = eco_evolutionary itself (heritable speed), true = its sibling trait variants (p.trait_mode).  Two kernels,
+// because the step kernels are bound by instruction delivery: the speed kernel carries none of the variants'
+// code and the variants' kernel none of the speed / carcass / ageing code.
+template <int W, typename MapT, bool SPLIT, bool TRAITS>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,10 +184,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
   const int n_blk = (p.B + 31) >> 5, n_grp = (p.B + 1023) >> 10;
   __syncwarp();
 
+  // envs come from the ticket counter; after the first one the ticket is drawn while the previous env is being finished (ppg_base.cu)
+  int env_next = 0;
+  if (lane == 0) env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+  unsigned long long pend = 0ULL;  // lane 0: completion-queue slot + 1 of the env whose hand-over is still owed (queue_push)
+  int pend_env = 0;
   for (;;) {
-    int env = 0;
-    if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-    env = __shfl_sync(FULL, env, 0);
+    const int env = __shfl_sync(FULL, env_next, 0);
     if (env >= p.B) break;
 
     int n[2] = {0, 0};
@@ -201,15 +207,44 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
+    // ONE round trip for everything the env needs from HBM/L2 (ppg_base.cu): headers, prefix words, the first 32 entries of
+    // both agent lists (speculatively: how many are valid is in the header), grass and the ghost count are all requested
+    // before any of them is looked at.
     EnvHdr h = p.hdr[env];
     EcoHdr eh = p.ehdr[env];
-    const int tm = p.trait_mode;  // PPG_TRAIT_*: 0 = ECO (speed)
+    int prow_r[2] = {0, 0};
+    double e_r[2] = {0.0, 0.0}, spd_r[2] = {0.0, 0.0};
+    unsigned idpos_r[2] = {0, 0}, agseq_r[2] = {0, 0}, dead_r[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (lane < p.cap[s]) {
+        const size_t b = (size_t)env * p.cap[s] + lane;
+        prow_r[s] = p.ag_prow[s][b];
+        e_r[s] = p.ag_e[s][b];
+        spd_r[s] = p.ag_spd[s][b];
+        idpos_r[s] = (unsigned)p.ag_id[s][b] | ((unsigned)p.ag_pos[s][b] << 16);
+        agseq_r[s] = (unsigned)p.ag_age[s][b] | ((unsigned)p.ag_seq[s][b] << 16);
+        dead_r[s] = p.ag_dead[s][b];
+      }
+    }
+    unsigned gp_r[4] = {0, 0, 0, 0};
+    double ge_r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int g = lane + 32 * q;
+      if (g < p.n_grass) { gp_r[q] = p.gr_pos[(size_t)env * p.n_grass + g]; ge_r[q] = p.gr_e[(size_t)env * p.n_grass + g]; }
+    }
+    const int n_gh_r = p.gh_n[env];
+    const int tm = TRAITS ? p.trait_mode : PPG_TRAIT_SPEED;  // PPG_TRAIT_*: 0 = ECO (speed)
+    if (TRAITS && tm == PPG_TRAIT_SPEED) __builtin_unreachable();
     // founders of the episode a reset starts: constant for ECO, drawn per episode by the trait variants (MR:189-192)
     int nf[2] = {p.n_init[0], p.n_init[1]};
     if (tm != PPG_TRAIT_SPEED && ((unsigned)h.pad[1] & 0x80000000u)) { nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
       if (lane == 0) atomicOr(p.error, 2u);
     }
+    // hand-over of the PREVIOUS env of this warp, after this env's first loads were issued (queue_push, ppg_step_common.cuh)
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
@@ -320,6 +355,24 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     } else if (mode == 2) {
       // ------------------------------------------------------------------ step() (ECO:295-507)
       n[0] = h.n_list[0]; n[1] = h.n_list[1];
+      // second (and last) dependent round trip: the actions of the rows the agents occupied in the previous output
+      int act_r[2] = {0, 0};
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (lane < SEL(n)) act_r[s] = p.actions[s][prow_r[s]];
+      // meanwhile the grass from the registers: positions, and last step's energies (what the grass channel shows to the
+      // agents that age out below; the regrowth is applied in place afterwards)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int g = lane + 32 * q;
+        if (g < p.n_grass) { S.gpos[g] = (uint16_t)gp_r[q]; S.gE[g] = ge_r[q]; S.map[2][CELLP(gp_r[q])] = (MapT)(g + 1); }
+      }
+      #pragma unroll 1
+      for (int g = lane + 128; g < p.n_grass; g += 32) {  // more than 128 patches: the rest the plain way
+        const size_t b = (size_t)env * p.n_grass;
+        const unsigned gp = p.gr_pos[b + g];
+        S.gpos[g] = (uint16_t)gp; S.gE[g] = p.gr_e[b + g]; S.map[2][CELLP(gp)] = (MapT)(g + 1);
+      }
       unsigned bad = 0;
       bool aged_any = false;
 #pragma unroll 1
@@ -346,20 +399,30 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
         #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
-          const int prow = p.ag_prow[s][b + i];
-          int a = p.actions[s][prow];
+          // entries 0..31 are already in registers, with their actions
+          int a;
+          double e0, tr;
+          unsigned idpos, agseq, deadv;
+          if (i < 32) {
+            a = SEL(act_r); e0 = SEL(e_r); tr = SEL(spd_r); idpos = SEL(idpos_r); agseq = SEL(agseq_r); deadv = SEL(dead_r);
+          } else {
+            a = p.actions[s][p.ag_prow[s][b + i]];
+            e0 = p.ag_e[s][b + i]; tr = p.ag_spd[s][b + i];
+            idpos = (unsigned)p.ag_id[s][b + i] | ((unsigned)p.ag_pos[s][b + i] << 16);
+            agseq = (unsigned)p.ag_age[s][b + i] | ((unsigned)p.ag_seq[s][b + i] << 16);
+            deadv = p.ag_dead[s][b + i];
+          }
           if ((unsigned)a >= (unsigned)p.n_actions) { a = p.n_actions / 2; bad = PPG_STATUS_BAD_ACTION; }
-          const bool carc = tm == PPG_TRAIT_SPEED && p.ag_dead[s][b + i] != 0;  // trait variants: no carcasses (ag_dead[0] = satiation)
-          unsigned age = p.ag_age[s][b + i];
+          const bool carc = tm == PPG_TRAIT_SPEED && deadv != 0;  // trait variants: no carcasses (ag_dead[0] = satiation)
+          unsigned age = agseq & 0xFFFFu;
           if (!carc) age += 1;  // carcasses do not age (ECO:600-601)
-          SEL(S.id)[i] = p.ag_id[s][b + i];
-          SEL(S.pos)[i] = p.ag_pos[s][b + i];
-          const double tr = p.ag_spd[s][b + i];
+          SEL(S.id)[i] = (uint16_t)idpos;
+          SEL(S.pos)[i] = (uint16_t)(idpos >> 16);
           // ECO:596; MR:555-561: the basal cost scales with the metabolic rate (1.0 without a genome)
-          SEL(S.E)[i] = p.ag_e[s][b + i] - (tm == PPG_TRAIT_METABOLIC ? p.loss[s] * (tr >= 0.0 ? tr : 1.0) : p.loss[s]);
+          SEL(S.E)[i] = e0 - (tm == PPG_TRAIT_METABOLIC ? p.loss[s] * (tr >= 0.0 ? tr : 1.0) : p.loss[s]);
           SEL(X.spd)[i] = tr;
           SEL(X.age)[i] = (uint16_t)age;
-          SEL(X.seq)[i] = p.ag_seq[s][b + i];
+          SEL(X.seq)[i] = (uint16_t)(agseq >> 16);
           SEL(S.act)[i] = (uint8_t)a;
           SEL(S.flg)[i] = (uint8_t)(F_ALIVE | (carc ? F_CARC : 0));
           if (!use_order) SEL(X.mord)[i] = (uint16_t)i;
@@ -367,13 +430,6 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
-      #pragma unroll 1
-      for (int g = lane; g < p.n_grass; g += 32) {
-        const size_t b = (size_t)env * p.n_grass;
-        const unsigned gp = p.gr_pos[b + g];
-        S.gpos[g] = (uint16_t)gp;
-        S.map[2][CELLP(gp)] = (MapT)(g + 1);
-      }
       __syncwarp();
       // owner maps as the grid stands after the decay loop: of agents sharing a cell the later one in list order wrote last
 #pragma unroll 1
@@ -393,7 +449,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         }
       __syncwarp();
       // ghost cells: the stale value is still on the grid unless a prey standing there has just re-written it (ECO:597)
-      n_gh = p.gh_n[env];
+      n_gh = n_gh_r;
       if (n_gh) {
         if (lane < n_gh) {
           const int gs = p.cap[1] - 1 - lane;
@@ -411,9 +467,6 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 
       // age-outs (ECO:602-616,1060-1090), in self.agents order; the grass channel still shows last step's energies
       if (__any_sync(FULL, aged_any)) {
-        const size_t gb = (size_t)env * p.n_grass;
-        for (int g = lane; g < p.n_grass; g += 32) S.gE[g] = p.gr_e[gb + g];
-        __syncwarp();
         long long last = -1;
         for (;;) {
           const unsigned key = next_in_seq_order(X.seq, n, last, lane, [&](int s, int i) {
@@ -436,7 +489,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       // grass regrowth (ECO:618-626)
       #pragma unroll 1
       for (int g = lane; g < p.n_grass; g += 32) {
-        const double v = p.gr_e[(size_t)env * p.n_grass + g] + p.grass_gain;
+        const double v = S.gE[g] + p.grass_gain;
         S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
       }
       __syncwarp();
@@ -838,7 +891,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       env_flags = PPG_ENV_IDLE;
     }
 
-    if (mode == 2) publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    // four atomics back to back, nobody waits for them here (ppg_base.cu): the warp's next env, this env's slot in the
+    // completion queue, the two accumulators of the row allocation
+#if PPG_TICKET_EARLY
+    if (lane == 0) env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+#endif
+    unsigned long long q_slot = 0ULL, pubA = 0ULL, pubB = 0ULL;
+    if (SPLIT) q_slot = queue_reserve(p, lane);
+    if (mode == 2) publish_begin(p, env, par, epoch, next_live, births, lane, pubA, pubB, 0);
 
     // ------------------------------------------------- rows: metadata, observations, state write-back
     if (lane == 0) {
@@ -948,6 +1008,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           }
         }
       }
+      if (mode == 2) publish_end(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane, pubA, pubB);
       if (lane < 2) {
         const int nb = lane == 0 ? births[0] : births[1];
         if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
@@ -1054,8 +1115,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       p.env_count[2 * env] = eh.active[0];
       p.env_count[2 * env + 1] = eh.active[1];
     }
+    if (SPLIT && lane == 0) { pend = q_slot + 1ULL; pend_env = env; }  // handed over from the top of the loop (queue_push)
     __syncwarp();
+#if !PPG_PUSH_DEFER
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
+#endif
+#if !PPG_TICKET_EARLY
+    if (lane == 0) env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+#endif
   }
+  if (SPLIT) queue_push(p, pend, pend_env, lane);
 }
 
 // trait variants: founders of the episode a scheduled reset will start (see draw_next_founders), after ppg_reset marked the envs
@@ -1076,33 +1145,41 @@ __global__ void ppg_set_tape_reals_kernel(EcoHdr* ehdr, int B, const long long* 
   ehdr[e].real_end = real_off ? real_off[e + 1] : 0;
 }
 
-template <typename MapT, bool SPLIT>
+template <typename MapT, bool SPLIT, bool TRAITS>
 static cudaError_t launch_eco_t(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_eco_kernel<1, MapT, SPLIT><<<n_cta, 32, smem, stream>>>(p);
+  ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS><<<n_cta, 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
+template <bool TRAITS>
+static cudaError_t launch_eco_v(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
+  if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true, TRAITS>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true, TRAITS>(p, n_cta, smem, stream);
+  return p.map_bytes == 1 ? launch_eco_t<uint8_t, false, TRAITS>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false, TRAITS>(p, n_cta, smem, stream);
+}
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true>(p, n_cta, smem, stream);
-  return p.map_bytes == 1 ? launch_eco_t<uint8_t, false>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false>(p, n_cta, smem, stream);
+  return p.trait_mode != PPG_TRAIT_SPEED ? launch_eco_v<true>(p, n_cta, smem, stream) : launch_eco_v<false>(p, n_cta, smem, stream);
 }
 
-template <typename MapT, bool SPLIT>
+template <typename MapT, bool SPLIT, bool TRAITS>
 static cudaError_t occupancy_eco_t(size_t smem, int* blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, MapT, SPLIT>, 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, 32, smem);
 }
 
-cudaError_t step_eco_occupancy(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
-  if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true>(smem, blocks_per_sm);
-  return map_bytes == 1 ? occupancy_eco_t<uint8_t, false>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false>(smem, blocks_per_sm);
+template <bool TRAITS>
+static cudaError_t occupancy_eco_v(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
+  if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true, TRAITS>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true, TRAITS>(smem, blocks_per_sm);
+  return map_bytes == 1 ? occupancy_eco_t<uint8_t, false, TRAITS>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false, TRAITS>(smem, blocks_per_sm);
+}
+cudaError_t step_eco_occupancy(int map_bytes, bool split, bool traits, size_t smem, int* blocks_per_sm) {
+  return traits ? occupancy_eco_v<true>(map_bytes, split, smem, blocks_per_sm) : occupancy_eco_v<false>(map_bytes, split, smem, blocks_per_sm);
 }
 
 cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s) {

@@ -130,10 +130,18 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
   // owner map of a prey slot's grid channel (STAG:2082-2092)
   auto prey_map = [&](int slot) -> MapT* { return (int)S.id[1][slot] >= T2[1] ? X.map3 : S.map[1]; };
 
+  // envs come from the ticket counter; after the first one the ticket is drawn while the previous env is being finished (ppg_base.cu)
+  // ticket -> env: big envs first when the previous launch left an order (publish_begin), else index order
+  const int32_t* const perm = (SPLIT && p.perm[par ^ 1] != nullptr && p.perm_tag[par ^ 1] == epoch - 1u) ? p.perm[par ^ 1] : nullptr;
+  int env_next = 0;
+  if (lane == 0) {
+    env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+  }
+  unsigned long long pend = 0ULL;  // lane 0: completion-queue slot + 1 of the env whose hand-over is still owed (queue_push)
+  int pend_env = 0;
   for (;;) {
-    int env = 0;
-    if (lane == 0) env = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-    env = __shfl_sync(FULL, env, 0);
+    const int env = __shfl_sync(FULL, env_next, 0);
     if (env >= p.B) break;
 
     int n[2] = {0, 0};
@@ -149,11 +157,38 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
 
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
+    // ONE round trip for everything the env needs from HBM/L2 (ppg_base.cu): headers, prefix words, the first entries of
+    // both agent lists (speculatively: how many are valid is in the header) and the grass are all requested before any of
+    // them is looked at.
     EnvHdr h = p.hdr[env];
     StagHdr sh = p.shdr[env];
+    int prow_r[3] = {0, 0, 0};
+    double e_r[3] = {0.0, 0.0, 0.0}, trait_r = 0.0;
+    unsigned idpos_r[3] = {0, 0, 0}, ageface_r[3] = {0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {  // q = 0: predators 0..31, q = 1, 2: prey 0..63
+      const int s = q ? 1 : 0, i = lane + (q == 2 ? 32 : 0);
+      if (i < p.cap[s]) {
+        const size_t b = (size_t)env * p.cap[s] + i;
+        prow_r[q] = p.ag_prow[s][b];
+        e_r[q] = p.ag_e[s][b];
+        idpos_r[q] = (unsigned)p.ag_id[s][b] | ((unsigned)p.ag_pos[s][b] << 16);
+        ageface_r[q] = (unsigned)p.ag_age[s][b];
+        if (q == 0) { ageface_r[0] |= (unsigned)p.ag_face[b] << 16; trait_r = p.ag_trait[b]; }
+      }
+    }
+    unsigned gp_r[4] = {0, 0, 0, 0};
+    double ge_r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int g = lane + 32 * q;
+      if (g < p.n_grass) { gp_r[q] = p.gr_pos[(size_t)env * p.n_grass + g]; ge_r[q] = p.gr_e[(size_t)env * p.n_grass + g]; }
+    }
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
       if (lane == 0) atomicOr(p.error, 2u);
     }
+    // hand-over of the PREVIOUS env of this warp, after this env's first loads were issued (queue_push, ppg_step_common.cuh)
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
     if (h.state & ST_NEEDS_RESET) mode = 1;
     else if (h.state & ST_IDLE) mode = 0;
     else mode = 2;
@@ -270,6 +305,33 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
     } else if (mode == 2) {
       // ------------------------------------------------------------------ step() (STAG:432-718)
       n[0] = h.n_list[0]; n[1] = h.n_list[1];
+      // second (and last) dependent round trip: the actions of the rows the agents occupied in the previous output
+      int act_r[3] = {0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int s = q ? 1 : 0, i = lane + (q == 2 ? 32 : 0);
+        if (i < SEL(n)) act_r[q] = p.actions[s][prow_r[q]];
+      }
+      // meanwhile: grass regrowth (STAG:761-769) from the registers
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int g = lane + 32 * q;
+        if (g < p.n_grass) {
+          S.gpos[g] = (uint16_t)gp_r[q];
+          S.map[2][CELLP(gp_r[q])] = (MapT)(g + 1);
+          const double v = ge_r[q] + p.grass_gain;
+          S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+        }
+      }
+      #pragma unroll 1
+      for (int g = lane + 128; g < p.n_grass; g += 32) {  // more than 128 patches: the rest the plain way
+        const size_t b = (size_t)env * p.n_grass;
+        const unsigned gp = p.gr_pos[b + g];
+        S.gpos[g] = (uint16_t)gp;
+        S.map[2][CELLP(gp)] = (MapT)(g + 1);
+        const double v = p.gr_e[b + g] + p.grass_gain;
+        S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
+      }
       unsigned bad = 0;
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
@@ -295,9 +357,25 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         }
         #pragma unroll 1
         for (int i = lane; i < SEL(n); i += 32) {
-          const int prow = p.ag_prow[s][b + i];
-          const int a = p.actions[s][prow];
-          const int id = p.ag_id[s][b + i];
+          // entries 0..31 (predators) / 0..63 (prey) are already in registers, with their actions
+          const int q = s == 0 ? (i < 32 ? 0 : 3) : (i < 32 ? 1 : (i < 64 ? 2 : 3));
+          int a;
+          double e0, trv = 0.0;
+          unsigned idpos, ageface;
+          if (q < 3) {
+            a = q == 0 ? act_r[0] : (q == 1 ? act_r[1] : act_r[2]);
+            e0 = q == 0 ? e_r[0] : (q == 1 ? e_r[1] : e_r[2]);
+            idpos = q == 0 ? idpos_r[0] : (q == 1 ? idpos_r[1] : idpos_r[2]);
+            ageface = q == 0 ? ageface_r[0] : (q == 1 ? ageface_r[1] : ageface_r[2]);
+            trv = trait_r;
+          } else {
+            a = p.actions[s][p.ag_prow[s][b + i]];
+            e0 = p.ag_e[s][b + i];
+            idpos = (unsigned)p.ag_id[s][b + i] | ((unsigned)p.ag_pos[s][b + i] << 16);
+            ageface = (unsigned)p.ag_age[s][b + i];
+            if (s == 0) { ageface |= (unsigned)p.ag_face[b + i] << 16; trv = p.ag_trait[b + i]; }
+          }
+          const int id = (int)(idpos & 0xFFFFu);
           const int t = id >= T2[s];
           const int R = p.type_ar[t];
           int move = a & 0xFF;
@@ -307,30 +385,20 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
             bad = PPG_STATUS_BAD_ACTION;
           }
           SEL(S.id)[i] = (uint16_t)id;
-          SEL(S.pos)[i] = p.ag_pos[s][b + i];
-          SEL(S.E)[i] = p.ag_e[s][b + i] - (s == 0 ? p.loss[0] : p.loss_prey_t[t]);  // STAG:742
-          SEL(X.age)[i] = (uint16_t)(p.ag_age[s][b + i] + 1);                          // STAG:752
+          SEL(S.pos)[i] = (uint16_t)(idpos >> 16);
+          SEL(S.E)[i] = e0 - (s == 0 ? p.loss[0] : p.loss_prey_t[t]);  // STAG:742
+          SEL(X.age)[i] = (uint16_t)((ageface & 0xFFFFu) + 1u);         // STAG:752
           SEL(S.act)[i] = (uint8_t)move;
           SEL(S.flg)[i] = F_ALIVE;
           if (s == 0) {
             X.join[i] = (uint8_t)((a >> PPG_STAG_JOIN_SHIFT) & 1);  // STAG:810-812
-            X.face[i] = p.ag_face[b + i];
-            X.trait[i] = p.ag_trait[b + i];
+            X.face[i] = (uint8_t)(ageface >> 16);
+            X.trait[i] = trv;
           }
           if (!use_order) SEL(X.mord)[i] = (uint16_t)i;
         }
       }
       h.status |= (unsigned char)__reduce_or_sync(FULL, bad);
-      // grass regrowth (STAG:761-769)
-      #pragma unroll 1
-      for (int g = lane; g < p.n_grass; g += 32) {
-        const size_t b = (size_t)env * p.n_grass;
-        const unsigned gp = p.gr_pos[b + g];
-        S.gpos[g] = (uint16_t)gp;
-        S.map[2][CELLP(gp)] = (MapT)(g + 1);
-        const double v = p.gr_e[b + g] + p.grass_gain;
-        S.gE[g] = v < p.grass_cap ? v : p.grass_cap;
-      }
       __syncwarp();
       // owner maps as the grid stands after the decay loop: of agents sharing a cell of one channel the later one in
       // list order wrote last
@@ -789,7 +857,17 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
       env_flags = PPG_ENV_IDLE;
     }
 
-    if (mode == 2) publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
+    // four atomics back to back, nobody waits for them here (ppg_base.cu): the warp's next env, this env's slot in the
+    // completion queue, the two accumulators of the row allocation
+#if PPG_TICKET_EARLY
+    if (lane == 0) {
+      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+    }
+#endif
+    unsigned long long q_slot = 0ULL, pubA = 0ULL, pubB = 0ULL;
+    if (SPLIT) q_slot = queue_reserve(p, lane);
+    if (mode == 2) publish_begin(p, env, par, epoch, next_live, births, lane, pubA, pubB, (n_old_total[0] + n_old_total[1]) / p.B * 5 / 4);
 
     // ------------------------------------------------- rows: metadata, observations, state write-back
     if (lane == 0) {
@@ -889,6 +967,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
           }
         }
       }
+      if (mode == 2) publish_end(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane, pubA, pubB);
       if (lane < 2) {
         const int nb = lane == 0 ? births[0] : births[1];
         if (!SPLIT) p.new_off[lane][env] = nb > 0 ? (lane == 0 ? new_base[0] : new_base[1]) : 0;
@@ -955,8 +1034,19 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         p.env_count[2 * env + 1] = live[1];
       }
     }
+    if (SPLIT && lane == 0) { pend = q_slot + 1ULL; pend_env = env; }  // handed over from the top of the loop (queue_push)
     __syncwarp();
+#if !PPG_PUSH_DEFER
+    if (SPLIT) queue_push(p, pend, pend_env, lane);
+#endif
+#if !PPG_TICKET_EARLY
+    if (lane == 0) {
+      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
+    }
+#endif
   }
+  if (SPLIT) queue_push(p, pend, pend_env, lane);
 }
 
 // reals cursor of the replay tape

@@ -11,8 +11,38 @@ namespace ppg {
 
 #define FULL 0xffffffffu
 
+// experiment switches of the env loop (defaults = what is shipped and measured)
+#ifndef PPG_TICKET_EARLY
+#define PPG_TICKET_EARLY 1  // draw the warp's next ticket while the current env is being finished
+#endif
+#ifndef PPG_PUSH_DEFER
+#define PPG_PUSH_DEFER 1    // hand an env to the observation kernel from the top of the next env (fence under the loads)
+#endif
+
 __device__ __forceinline__ unsigned globaltimer_lo() { unsigned v; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(v)); return v; }
 __device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+
+// Per-phase latency profile of the step kernels (experimental builds only: scripts/build_prof.py compiles the library with
+// -DPPG_PHASE_PROF; the shipped library has none of this).  PHASE_MARK(k) charges the SM cycles since the previous mark to
+// phase k of the env the warp is working on; the per-launch totals are read by `ppg_debug_phase_cycles_<variant>`.
+#ifdef PPG_PHASE_PROF
+#define PPG_N_PHASES 24
+#define PPG_PROF_MAX_ENVS 65536
+#define PHASE_DEFINE(name)                                                                                          \
+  __device__ unsigned g_phase_cycles_##name[PPG_PROF_MAX_ENVS][PPG_N_PHASES];                                       \
+  extern "C" int ppg_debug_phase_cycles_##name(unsigned* out, int n_envs) { /* [n_envs][PPG_N_PHASES] of the last launch */ \
+    return cudaMemcpyFromSymbol(out, g_phase_cycles_##name, sizeof(unsigned) * PPG_N_PHASES * (size_t)n_envs) == cudaSuccess ? 0 : -1; \
+  }
+#define PHASE_DECL long long ph_t = clock64(); unsigned ph_acc[PPG_N_PHASES]; _Pragma("unroll") for (int k_ = 0; k_ < PPG_N_PHASES; ++k_) ph_acc[k_] = 0;
+#define PHASE_MARK(k) { const long long t_ = clock64(); ph_acc[k] += (unsigned)(t_ - ph_t); ph_t = t_; }
+#define PHASE_FLUSH(name) if (lane == 0 && env < PPG_PROF_MAX_ENVS) { _Pragma("unroll") for (int k_ = 0; k_ < PPG_N_PHASES; k_ += 4) \
+    *reinterpret_cast<uint4*>(&g_phase_cycles_##name[env][k_]) = make_uint4(ph_acc[k_], ph_acc[k_ + 1], ph_acc[k_ + 2], ph_acc[k_ + 3]); }
+#else
+#define PHASE_DEFINE(name)
+#define PHASE_DECL
+#define PHASE_MARK(k)
+#define PHASE_FLUSH(name)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory view of one env
@@ -113,7 +143,7 @@ __device__ __forceinline__ RowDesc carve_desc(unsigned char* base, const StepPar
 
 // Writes the image header and copies the image range of the env's shared-memory slice to HBM (coalesced 16-byte
 // stores, default caching: the observation kernel reads it back from L2 a few microseconds later).  mode 0 (idle
-// env): header only, zero rows.
+// env): header only, zero rows.  Only the copy: finish_env() signals the env.
 __device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParams& p, int env, int mode, bool keep, const int old_base[2],
                                            const int n[2], const int births[2], int lane) {
   int* ih = reinterpret_cast<int*>(sbase + p.so_ihdr);
@@ -139,13 +169,7 @@ __device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParam
   #pragma unroll 1
   for (int i = lane; i < n16; i += 32) dst[i] = src[i];
   __syncwarp();
-  // completion queue: the observation kernel (possibly already running, see ppg_obs.cu) takes the env from here
-  if (lane == 0) {
-    __threadfence();
-    const unsigned long long slot = atomicAdd(p.q_tail, 1ULL) - p.q_base;
-    st_volatile(p.queue + slot, TAG(p.epoch, env));
-  }
-  __syncwarp();
+  // the env is handed to the observation kernel by finish_env(), after the env's remaining stores: one fence for all of them
 }
 
 // lets a kernel launched with programmatic stream serialization (the observation kernel) start while this one runs
@@ -404,8 +428,10 @@ __device__ __forceinline__ void zero_row(float* dst, int elems, int lane) {
 template <typename MapT, bool BULK, bool SELF = false>
 __device__ __noinline__ unsigned emit_row_now(unsigned char* base, const StepParams& p, float* dst, int cellp, int s, int nt0, int nt1,
                                               unsigned rowctr, int lane, float selfv = 0.f) {
-  const EnvSmem<MapT> S = carve<MapT>(base, p);
-  refresh_tables(S, p, nt0, nt1, lane);
+  if (nt0 >= 0) {  // nt0 < 0: the caller keeps the value tables current itself (ppg_base.cu)
+    const EnvSmem<MapT> S = carve<MapT>(base, p);
+    refresh_tables(S, p, nt0, nt1, lane);
+  }
   const unsigned sb32 = (unsigned)__cvta_generic_to_shared(base);
   const RowRel r = load_rel(p, s, sb32, lane);
   emit_row<MapT, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv);
@@ -599,74 +625,123 @@ __device__ __noinline__ int philox_free_cell(unsigned char* base, const StepPara
 }
 
 
-// Publishes this env's (live, births) counts for the row allocation; the last finisher of each 32-env block /
-// 1024-env group publishes the block / group sums, the last group the totals of this output (n_rows).
+// ------------------------------------------------------------------------------------------------
+// deterministic row allocation: publication of an env's (live, births) counts
+// ------------------------------------------------------------------------------------------------
+// Every env stores its two epoch-tagged words (cntA: rows it needs in the NEXT output, cntB: newborn rows of THIS
+// output) and adds the same pairs to the accumulator of its 32-env block with ONE 64-bit atomic per pair:
+//   acc = contributors << 56 | first << 28 | second.
+// The atomic's return value tells the env whether it was the block's last contributor; the last one knows the block sum
+// (returned value + its own), publishes it as tagged words (sum1), clears the accumulator for the next launch and adds the
+// sum to the accumulator of the 1024-env group, and so on up to the totals.  Readers validate every word by its tag, so no
+// fence is needed anywhere, and the two atomics are issued long before their results are looked at (publish_begin right
+// after the env's counts are known, publish_end after its rows are written): nobody waits on this path.
+#define ACC_ONE (1ULL << 56)
+#define ACC_M28 0xFFFFFFFULL
+#define ACC_M56 ((1ULL << 56) - 1ULL)
+
+//
+// Big envs first: env-steps differ 4x in duration (mostly with the number of agents) and a launch has only 1.4 - 7 envs per
+// resident warp, so in index order the kernel's last third is a handful of warps finishing big envs they happened to get
+// late.  Every env therefore also enters itself into the ORDER of the next launch (perm[par], ticket -> env): envs with
+// more agents than `big` (5/4 of the mean) fill it from the front, the others from the back, each through one cursor
+// atomic.  The launch's last publisher tags the order with the epoch and clears the other parity's cursors.  Results never
+// depend on the order envs are worked on (rows are allocated by env index).  Only for kernels in which no env ever waits
+// for another one (BASE / STAG two-kernel step; p.perm == nullptr elsewhere): a waiting env relies on ticket order = env order.
+__device__ __forceinline__ void publish_begin(const StepParams& p, int env, int par, unsigned epoch, const int next_live[2],
+                                              const int births[2], int lane, unsigned long long& rA, unsigned long long& rB, int big) {
+  if (lane == 0) {
+    st_volatile(p.cntA[par] + env, TAG(epoch, (next_live[0] << 16) | next_live[1]));
+    st_volatile(p.cntB[par] + env, TAG(epoch, (births[0] << 16) | births[1]));
+    unsigned long long* acc = p.acc1 + 2 * (size_t)(env >> 5);
+    rA = atomicAdd(acc, ACC_ONE | ((unsigned long long)next_live[0] << 28) | (unsigned long long)next_live[1]);
+    rB = atomicAdd(acc + 1, ACC_ONE | ((unsigned long long)births[0] << 28) | (unsigned long long)births[1]);
+    if (p.perm[par] != nullptr) {
+      const bool front = next_live[0] + next_live[1] > big;
+      const unsigned pos = atomicAdd(p.perm_cursor + 2 * par + (front ? 0 : 1), 1u);
+      p.perm[par][front ? (int)pos : p.B - 1 - (int)pos] = env;
+    }
+  }
+}
+
+// one chain (c = 0: live counts, c = 1: births) from the block level upwards; lane 0 only
+static __device__ __noinline__ bool publish_chain(const StepParams& p, int env, int par, unsigned epoch, int c, unsigned long long r, unsigned long long mine,
+                                           int n_blk, int n_grp, int n_old0, int n_old1) {
+  const int blk = env >> 5, grp = env >> 10;
+  if ((int)(r >> 56) + 1 != min(32, p.B - (blk << 5))) return false;
+  unsigned long long tot = (r + mine) & ACC_M56;  // this env was the last of its block
+  p.acc1[2 * (size_t)blk + c] = 0ULL;
+  st_volatile(p.sum1[par] + (size_t)blk * 4 + 2 * c, TAG(epoch, (unsigned)(tot >> 28)));
+  st_volatile(p.sum1[par] + (size_t)blk * 4 + 2 * c + 1, TAG(epoch, (unsigned)(tot & ACC_M28)));
+  unsigned long long r2 = atomicAdd(p.acc2 + 2 * (size_t)grp + c, ACC_ONE | tot);
+  if ((int)(r2 >> 56) + 1 != min(32, n_blk - (grp << 5))) return false;
+  tot = (r2 + tot) & ACC_M56;  // last block of its group
+  p.acc2[2 * (size_t)grp + c] = 0ULL;
+  st_volatile(p.sum2[par] + (size_t)grp * 4 + 2 * c, TAG(epoch, (unsigned)(tot >> 28)));
+  st_volatile(p.sum2[par] + (size_t)grp * 4 + 2 * c + 1, TAG(epoch, (unsigned)(tot & ACC_M28)));
+  r2 = atomicAdd(p.acc3 + c, ACC_ONE | tot);
+  if ((int)(r2 >> 56) + 1 != n_grp) return false;
+  tot = (r2 + tot) & ACC_M56;  // last group: totals of this output (births) / of the next one (live)
+  p.acc3[c] = 0ULL;
+  p.totals[par * 4 + 2 * c] = (int)(tot >> 28);
+  p.totals[par * 4 + 2 * c + 1] = (int)(tot & ACC_M28);
+  if (c == 0) {
+    p.n_rows[0] = n_old0; p.n_rows[1] = n_old1;
+    p.old_off[0][p.B] = n_old0; p.old_off[1][p.B] = n_old1;
+    if (p.perm[par] != nullptr) {  // every env has entered itself into the next launch's order
+      p.perm_tag[par] = epoch;
+      p.perm_cursor[2 * (par ^ 1)] = 0u; p.perm_cursor[2 * (par ^ 1) + 1] = 0u;  // idle during this launch, used by the next one
+    }
+  } else {
+    p.n_rows[2] = (int)(tot >> 28); p.n_rows[3] = (int)(tot & ACC_M28);
+  }
+  return true;
+}
+
+// returns (lane 0) whether this env published the last live count of the launch: every env's cntA word is then in place
+__device__ __forceinline__ bool publish_end(const StepParams& p, int env, int par, unsigned epoch, const int next_live[2], const int births[2],
+                                            int n_blk, int n_grp, const int n_old_total[2], int lane, unsigned long long rA, unsigned long long rB) {
+  bool all_live = false;
+  if (lane == 0) {
+    const int bsz = min(32, p.B - ((env >> 5) << 5));
+    if ((int)(rA >> 56) + 1 == bsz)
+      all_live = publish_chain(p, env, par, epoch, 0, rA, ACC_ONE | ((unsigned long long)next_live[0] << 28) | (unsigned long long)next_live[1], n_blk, n_grp,
+                               n_old_total[0], n_old_total[1]);
+    if ((int)(rB >> 56) + 1 == bsz)
+      publish_chain(p, env, par, epoch, 1, rB, ACC_ONE | ((unsigned long long)births[0] << 28) | (unsigned long long)births[1], n_blk, n_grp,
+                    n_old_total[0], n_old_total[1]);
+  }
+  return all_live;
+}
+
 __device__ __forceinline__ void publish_counts(const StepParams& p, int env, int par, unsigned epoch, const int next_live[2],
                                                const int births[2], int n_blk, int n_grp, const int n_old_total[2], int lane) {
-    {
-      const int blk = env >> 5, grp = env >> 10;
-      bool last = false;
-      if (lane == 0) {
-        st_volatile(p.cntA[par] + env, TAG(epoch, (next_live[0] << 16) | next_live[1]));
-        st_volatile(p.cntB[par] + env, TAG(epoch, (births[0] << 16) | births[1]));
-        __threadfence();
-        const unsigned bsz = (unsigned)min(32, p.B - (blk << 5));
-        last = (atomicAdd(p.done1 + blk, 1u) + 1u) % bsz == 0u;
-      }
-      if (__shfl_sync(FULL, last, 0)) {  // last env of its 32-env block: block sums
-        __threadfence();
-        const int e2 = (blk << 5) + lane;
-        unsigned long long a = 0, b = 0;
-        if (e2 < p.B) { a = ld_volatile(p.cntA[par] + e2); b = ld_volatile(p.cntB[par] + e2); }
-        int v[4] = {(int)((a >> 16) & 0xFFFF), (int)(a & 0xFFFF), (int)((b >> 16) & 0xFFFF), (int)(b & 0xFFFF)};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = __reduce_add_sync(FULL, v[q]);
-        if (lane < 4) st_volatile(p.sum1[par] + (size_t)blk * 4 + lane, TAG(epoch, lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3]));
-        __threadfence();
-        __syncwarp();
-        bool last2 = false;
-        if (lane == 0) {
-          const unsigned gsz = (unsigned)min(32, n_blk - (grp << 5));
-          last2 = (atomicAdd(p.done2 + grp, 1u) + 1u) % gsz == 0u;
-        }
-        if (__shfl_sync(FULL, last2, 0)) {  // last block of its group: group sums
-          __threadfence();
-          const int b2 = (grp << 5) + lane;
-          int w[4] = {0, 0, 0, 0};
-          if (b2 < n_blk) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) w[q] = (int)(unsigned)ld_volatile(p.sum1[par] + (size_t)b2 * 4 + q);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[q] = __reduce_add_sync(FULL, w[q]);
-          if (lane < 4) st_volatile(p.sum2[par] + (size_t)grp * 4 + lane, TAG(epoch, lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]));
-          __threadfence();
-          __syncwarp();
-          bool last3 = false;
-          if (lane == 0) last3 = (atomicAdd(p.done3, 1u) + 1u) % (unsigned)n_grp == 0u;
-          if (__shfl_sync(FULL, last3, 0)) {  // last group: totals of this output and of the next one
-            __threadfence();
-            int t[4] = {0, 0, 0, 0};
-            #pragma unroll 1
-            for (int g = lane; g < n_grp; g += 32) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) t[q] += (int)(unsigned)ld_volatile(p.sum2[par] + (size_t)g * 4 + q);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] = __reduce_add_sync(FULL, t[q]);
-            if (lane < 2) {
-              const int s = lane;
-              p.totals[par * 4 + s] = s == 0 ? t[0] : t[1];
-              p.totals[par * 4 + 2 + s] = s == 0 ? t[2] : t[3];
-              p.n_rows[s] = n_old_total[s];
-              p.n_rows[2 + s] = s == 0 ? t[2] : t[3];
-              p.old_off[s][p.B] = n_old_total[s];
-            }
-          }
-        }
-      }
-    }
+  unsigned long long rA = 0, rB = 0;
+  publish_begin(p, env, par, epoch, next_live, births, lane, rA, rB, (n_old_total[0] + n_old_total[1]) / p.B * 5 / 4);
+  publish_end(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane, rA, rB);
+  __syncwarp();
+}
 
+// ------------------------------------------------------------------------------------------------
+// hand-over of a finished env to the observation kernel (completion queue)
+// ------------------------------------------------------------------------------------------------
+// The queue slot is drawn early (queue_reserve, together with the publication atomics: one round trip for all three);
+// the entry itself may only appear after the env's image and labels are visible, i.e. after a fence that follows those
+// stores.  The fence is NOT executed at the end of the env: the warp first issues the global loads of its NEXT env and
+// then fences (queue_push from the top of the loop), so that the wait for the store acknowledgements and the wait for the
+// loads are one wait instead of two.  `pend` = slot + 1 of the env waiting to be pushed (0: none), lane 0 only.
+__device__ __forceinline__ unsigned long long queue_reserve(const StepParams& p, int lane) {
+  unsigned long long slot = 0;
+  if (lane == 0) slot = atomicAdd(p.q_tail, 1ULL) - p.q_base;
+  return slot;
+}
+__device__ __forceinline__ void queue_push(const StepParams& p, unsigned long long& pend, int& pend_env, int lane) {
+  __syncwarp();
+  if (lane == 0 && pend != 0ULL) {
+    __threadfence();
+    st_volatile(p.queue + (pend - 1ULL), TAG(p.epoch, pend_env));
+    pend = 0ULL;
+  }
 }
 
 }  // namespace ppg

@@ -458,16 +458,6 @@ def reference_reset_tape_trait(seed, config, trait):
     return np.concatenate([np.asarray(n, np.int32), np.asarray(cells, np.int32)]), np.asarray(values, np.float64)
 
 
-def _spearman(x, y):
-    """`_spearman_corr` (MR:1362-1368): rank correlation without tie correction"""
-    rx = np.argsort(np.argsort(x)).astype(float)
-    ry = np.argsort(np.argsort(y)).astype(float)
-    rx -= rx.mean()
-    ry -= ry.mean()
-    denom = np.sqrt((rx ** 2).sum() * (ry ** 2).sum())
-    return float(np.dot(rx, ry) / denom) if denom > 0.0 else 0.0
-
-
 class _TraitEnv(PredPreyGrassEco):
     """Shared dict adapter of the trait variants of eco_evolutionary (MR / INV / COOP): 9 actions, 3-channel windows, a
     random number of founders per episode, ids never reused, `infos["__all__"]["training_metrics"]` at the episode's end."""
@@ -551,10 +541,10 @@ class _TraitEnv(PredPreyGrassEco):
 
     def episode_training_metrics(self):
         """`_build_episode_training_metrics` of the trait variants (MR:1274-1392): the trait distribution and the per-agent
-        means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the rank correlation
-        between the trait and having reproduced.  Distance and locomotion totals come from the device
+        means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the reproduction rate per
+        trait quartile.  Distance and locomotion totals come from the device
         (ppg_read_episode_eco).  Not emitted: the `*_reproduction_blocked*` / `predator_satiation_blocked_catches` event
-        counters and COOP's donation totals / relatedness proxy."""
+        counters, the `*_repro_spearman` rank correlations and COOP's donation totals / relatedness proxy."""
         ep = self._batch.read_episode_eco(0)
         res, t = {}, self._trait
         for s, role in enumerate(("predator", "prey")):
@@ -595,7 +585,8 @@ class _TraitEnv(PredPreyGrassEco):
                     continue
                 x = np.array([r["trait"] for r in recs])
                 y = np.array([float(r["offspring"] > 0) for r in recs])
-                res[f"{role}_{self._tag}_repro_spearman"] = _spearman(x, y)
+                # (`{role}_{tag}_repro_spearman` is not emitted: the reference ranks with argsort and no tie correction, so
+                # its value depends on the order its record dicts happen to be iterated in, MR:1362-1380)
                 q25, q50, q75 = np.percentile(x, [25, 50, 75])
                 for k, m in enumerate((x <= q25, (x > q25) & (x <= q50), (x > q50) & (x <= q75), x > q75), 1):
                     if m.sum() > 0:

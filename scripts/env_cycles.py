@@ -39,3 +39,7 @@ for rep in range(3):
     print("  warps busy per us (every 4th us):", busy[::4].astype(int).tolist())
     c = np.corrcoef(agents[mode == 2], cyc[mode == 2])[0, 1]
     print("  corr(agents, cycles) = %.2f" % c)
+    last = np.argsort(end)[-12:]
+    print("  last finishers (env, start us, dur us, agents, births, mode):", [(int(e), round(float(t0[e]) / 1e3, 1), round(float(dur_ns[e]) / 1e3, 1), int(agents[e]), int(births[e]), int(mode[e])) for e in last])
+    firsts = t0 < 2000
+    print("  first-wave envs: %d, mean agents %.1f; later envs: %d, mean agents %.1f" % (firsts.sum(), agents[firsts].mean(), (~firsts).sum(), agents[~firsts].mean() if (~firsts).any() else 0))
