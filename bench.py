@@ -122,7 +122,7 @@ def build_config(args, **kw):
 
 
 def n_actions(args):
-    return 25 if args.variant in ("eco", "cadence") else 9  # the other trait variants have action_range 3 (MR:203-210)
+    return 25 if args.variant == "eco" else 9  # the trait variants have action_range 3 (MR:203-210, CAD config)
 
 
 def action_pools(args, n, rng):

@@ -66,6 +66,7 @@ enum {
 #define PPG_ROW_ATE 0x10u        /* member of agents_just_ate (BASE:319,362) */
 #define PPG_ROW_CARCASS 0x20u    /* ECO: member of dead_prey after the step (bitten, not fully eaten; ECO:826-845) */
 #define PPG_ROW_REPRODUCED 0x40u /* the agent had an offspring this step (BASE:396-409; ECO:1161 `agent_offspring_counts[agent] += 1`) */
+#define PPG_ROW_FROZEN 0x80u     /* CAD: the agent's action mask allows only "stay" in its next step (move accumulator + rate < 1; CAD:577-585,746-753) */
 
 /* per-env flag bits (ppg_buffers.env_flags), describe the step that just ran */
 #define PPG_ENV_TERMINATED 0x01u /* terminations["__all__"] (BASE:466) */
@@ -372,6 +373,10 @@ int ppg_read_env(ppg_handle h, int32_t env, int32_t* n_live, int32_t* ids_pred, 
  * active_num_predators/prey), in the list order of ppg_read_env.  Any pointer may be NULL. Synchronises. */
 int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,
                      double* speed_prey, uint8_t* dead_prey, int32_t* active_num);
+
+/* CAD: `agent_move_accumulator` (CAD:183-186) of the live agents of one env, in the order of ppg_read_env (cadence handles
+ * only; either pointer may be NULL).  Synchronises the device. */
+int ppg_read_env_acc(ppg_handle h, int32_t env, double* acc_pred, double* acc_prey);
 
 /* ECO per-episode totals of one env for `_build_episode_training_metrics` (ECO:1613-1661), valid with
  * ppg_config.track_episode_sums: sums[4] = distance moved by all predators / all prey of the running episode (the sum of

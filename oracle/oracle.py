@@ -54,6 +54,7 @@ def lib():
         L.ppgo_env_reset_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         L.ppgo_env_reset_trait.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ppgo_read_env_acc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
@@ -134,6 +135,13 @@ class Oracle:
         sp = np.ascontiguousarray(founder_trait if len(founder_trait) else [0.0], np.float64)
         assert lib().ppgo_env_reset_trait(self.h, env, int(n_pred), int(n_prey), c.ctypes.data, sp.ctypes.data) == 0
         return self.outputs()
+
+    def read_env_acc(self, env):
+        """CAD agent_move_accumulator of one env, in the list order of read_env"""
+        st = self.read_env(env)
+        acc = [np.zeros(max(1, len(st["ids"][s])), np.float64) for s in range(2)]
+        assert lib().ppgo_read_env_acc(self.h, env, acc[0].ctypes.data, acc[1].ctypes.data) == 0
+        return tuple(a[: len(st["ids"][s])] for s, a in enumerate(acc))
 
     def read_env_eco(self, env):
         st = self.read_env(env)

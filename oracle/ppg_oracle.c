@@ -103,7 +103,7 @@ static void env_alloc(env_t* e, const ppg_config* c, int env_index, int32_t* con
 static void env_free(env_t* e) {
   if (e->c->variant == PPG_VARIANT_ECO) eco_env_free(e);
   if (e->c->variant == PPG_VARIANT_STAG) stag_env_free(e);
-  free(e->carcass); free(e->born_obs);
+  free(e->carcass); free(e->born_obs); free(e->frozen);
   for (int s = 0; s < 2; ++s) {
     free(e->present[s]); free(e->x[s]); free(e->y[s]); free(e->energy[s]); free(e->parent[s]);
     free(e->list_index[s]);
@@ -130,6 +130,7 @@ static void ensure_rows(env_t* e, int need) {
   e->bonus = (double*)realloc(e->bonus, n * sizeof(double));
   e->carcass = (uint8_t*)realloc(e->carcass, n);
   e->born_obs = (uint8_t*)realloc(e->born_obs, n);
+  e->frozen = (uint8_t*)realloc(e->frozen, n);
 }
 
 void eco_ensure_rows(env_t* e, int need) { ensure_rows(e, need); }
@@ -661,6 +662,7 @@ static void export_rows(ppgo_batch* b) {
       if (v->ate[i]) fl |= PPG_ROW_ATE;
       if (v->repro[i]) fl |= PPG_ROW_REPRODUCED;
       if (v->row_key && v->carcass[i]) fl |= PPG_ROW_CARCASS;
+      if (v->row_key && c->trait_mode == PPG_TRAIT_CADENCE && v->frozen[i]) fl |= PPG_ROW_FROZEN;
       b->out.f.flags[s][row] = fl;
       b->prev_row[s][(size_t)e * c->n_possible[s] + id] = row;
     }
@@ -888,6 +890,19 @@ int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* spe
       }
   }
   if (active_num) { active_num[0] = v->active[0]; active_num[1] = v->active[1]; }
+  return PPG_OK;
+}
+
+/* CAD: agent_move_accumulator (CAD:183-186) of one env, in the order of ppgo_read_env_eco */
+int ppgo_read_env_acc(ppgo_batch* b, int32_t env, double* acc_pred, double* acc_prey) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;
+  env_t* v = &b->envs[env];
+  double* out[2] = {acc_pred, acc_prey};
+  for (int s = 0; s < 2; ++s) {
+    int n = 0;
+    for (int id = 0; id < v->next_idx[s]; ++id)
+      if (v->present[s][id]) out[s][n++] = v->acc[s][id];
+  }
   return PPG_OK;
 }
 

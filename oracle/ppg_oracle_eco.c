@@ -24,7 +24,16 @@
  * (random founder counts, trait-scaled decay / gains, satiation cooldown, density cap, offspring investment, meal
  * sharing; no ageing caps, no carcasses, no speed gating) — each branch cites the variant's lines; pinned by
  * tests/golden/make_golden_traits.py -> tests/golden/{mr,inv,coop}_*.npz, tests/test_oracle_golden_traits.py.
+ *   CAD  = predpreygrass/evolutionary/eco_evolutionary_cadence/predpreygrass_rllib_env.py
+ * keeps ECO's step (ageing caps, grass intake cap, speed ** exponent in the move cost) and changes what the speed does: it
+ * sets the RATE at which a per-agent accumulator lets the agent move (CAD:556-585,674-681), scales the basal cost
+ * (CAD:626-633), shows unnormalised in the speed plane (CAD:746) and comes with an action mask (row flag PPG_ROW_FROZEN);
+ * predators catch the nearest prey within Chebyshev distance 1 and eat it whole (CAD:837-880), newborns go to a RANDOM
+ * free neighbour cell (CAD:795) and start with a random accumulator phase (CAD:1327); no carcasses, no lineage rewards.
+ * Pinned by tests/golden/cad_*.npz.
  */
+#define IS_MIC(c) ((c)->trait_mode == PPG_TRAIT_METABOLIC || (c)->trait_mode == PPG_TRAIT_INVESTMENT || (c)->trait_mode == PPG_TRAIT_COOPERATION)
+#define IS_CAD(c) ((c)->trait_mode == PPG_TRAIT_CADENCE)
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -50,12 +59,13 @@ void eco_env_alloc(env_t* e) {
   e->max_row_elems = e->row_elems[0] > e->row_elems[1] ? e->row_elems[0] : e->row_elems[1];
   e->dead = (uint8_t*)calloc((size_t)c->n_possible[1], 1);
   e->sat_until = (int32_t*)calloc((size_t)c->n_possible[0], sizeof(int32_t));
+  for (int s = 0; s < 2; ++s) e->acc[s] = (double*)calloc((size_t)c->n_possible[s], sizeof(double));
   e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1];
   e->row_key = (int32_t*)malloc(sizeof(int32_t) * (size_t)(c->n_possible[0] + c->n_possible[1]));
 }
 
 void eco_env_free(env_t* e) {
-  for (int s = 0; s < 2; ++s) { free(e->age[s]); free(e->speed[s]); free(e->termd[s]); }
+  for (int s = 0; s < 2; ++s) { free(e->age[s]); free(e->speed[s]); free(e->termd[s]); free(e->acc[s]); }
   free(e->gridf); free(e->dead); free(e->row_key); free(e->sat_until);
 }
 
@@ -80,7 +90,8 @@ static void eco_get_observation(env_t* e, int s, int id, double* out) {
     for (int i = xolo; i <= xohi; ++i)
       for (int j = yolo; j <= yohi; ++j) out[(ch * R + i) * R + j] = (double)*GF(e, ch, xlo + (i - xolo), ylo + (j - yolo));
   if (c->include_speed_in_obs && e->speed[s][id] >= 0.0) { /* ECO:707-711 */
-    const double norm = (e->speed[s][id] - c->speed_bounds[0]) / (c->speed_bounds[1] - c->speed_bounds[0]);
+    double norm = (e->speed[s][id] - c->speed_bounds[0]) / (c->speed_bounds[1] - c->speed_bounds[0]);
+    if (IS_CAD(c)) norm = e->speed[s][id]; /* CAD:746: the genome value itself */
     const float v = (float)norm; /* assignment into a float32 array */
     for (int i = 0; i < R * R; ++i) out[CG * R * R + i] = (double)v;
   }
@@ -101,7 +112,16 @@ static int take_real(env_t* e, double* out) {
 
 static void clear_row(env_t* e, int i) {
   e->rew[i] = 0.0; e->has_rew[i] = 0; e->term[i] = -1; e->trunc[i] = -1; e->has_obs[i] = 0;
-  e->ate[i] = 0; e->repro[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0;
+  e->ate[i] = 0; e->repro[i] = 0; e->newborn[i] = 0; e->carcass[i] = 0; e->born_obs[i] = 0; e->frozen[i] = 0;
+}
+
+/* _genome_speed_to_move_rate / _get_agent_move_rate (CAD:556-575): 1/max_cooldown .. 1, linear in the clamped speed */
+static double cad_move_rate(const env_t* e, int s, int id) {
+  const double sp = e->speed[s][id];
+  if (sp < 0.0) return 1.0; /* no genome */
+  const double normalized = sp < 0.0 ? 0.0 : (sp > 1.0 ? 1.0 : sp); /* max(0.0, min(1.0, speed)) */
+  const double min_rate = 1.0 / (double)e->c->max_cooldown;
+  return min_rate + normalized * (1.0 - min_rate);
 }
 
 /* reset() (ECO:274-293, 123-223, 1733-1792) from explicit cells and founder speeds */
@@ -116,7 +136,7 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
   }
   memset(e->dead, 0, (size_t)c->n_possible[1]); /* ECO:193 */
   e->n_agents = 0;
-  if (c->trait_mode == PPG_TRAIT_SPEED) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; }
+  if (!IS_MIC(c)) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; }
   const int nf[2] = {e->n_found[0], e->n_found[1]}; /* trait variants: drawn per episode (MR:189-192) */
   memset(e->sat_until, 0, sizeof(int32_t) * (size_t)c->n_possible[0]); /* MR:1141 */
   int k = 0;
@@ -126,6 +146,8 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
       /* _get_initial_age (ECO:1060-1068): founder predators start at the carcass-only threshold */
       e->age[s][i] = (s == 0 && c->carcass_only_predator_age >= 0) ? c->carcass_only_predator_age : 0;
       e->speed[s][i] = c->genome_enabled ? founder_speed[k] : -1.0;
+      /* CAD:1327: random phase of the move accumulator; after the founders' speeds in `founder_speed` */
+      if (IS_CAD(c)) e->acc[s][i] = founder_speed[(c->genome_enabled ? nf[0] + nf[1] : 0) + k];
     }
   e->next_idx[0] = nf[0]; /* deque of never-used ids, ascending (ECO:238-258; MR:231-243 lowest unused id) */
   e->next_idx[1] = nf[1];
@@ -151,6 +173,7 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
     e->row_key[i] = e->agents[i];
     eco_get_observation(e, KEY_S(e->agents[i]), KEY_ID(e->agents[i]), e->obs + (size_t)i * e->max_row_elems);
     e->has_obs[i] = 1; e->has_rew[i] = 1; e->term[i] = 0; e->trunc[i] = 0;
+    if (IS_CAD(c)) e->frozen[i] = !(e->acc[KEY_S(e->agents[i])][KEY_ID(e->agents[i])] + cad_move_rate(e, KEY_S(e->agents[i]), KEY_ID(e->agents[i])) >= 1.0);
   }
   e->n_rows = e->n_agents;
   e->all_term = e->all_trunc = 0;
@@ -164,7 +187,7 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
  * entries of the episode's cell tape, or the FOUNDERS Philox stream keyed by the episode about to start */
 void eco_founder_counts(env_t* e, int from_tape) {
   const ppg_config* c = e->c;
-  if (c->trait_mode == PPG_TRAIT_SPEED) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; return; }
+  if (!IS_MIC(c)) { e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1]; return; }
   for (int s = 0; s < 2; ++s) {
     const int lo = c->n_initial_min[s], hi = c->n_initial[s];
     int v;
@@ -180,7 +203,7 @@ void eco_env_reset_auto(env_t* e) {
   const int n_f = e->n_found[0] + e->n_found[1], n_total = n_f + c->n_grass;
   const int ncell = e->G * e->G;
   int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_total);
-  double* sp = (double*)malloc(sizeof(double) * (size_t)(n_f > 0 ? n_f : 1));
+  double* sp = (double*)malloc(sizeof(double) * (size_t)(2 * n_f + 1));
   e->episode += 1;
   e->trait_draws = 0;
   uint8_t sticky = 0;
@@ -197,6 +220,15 @@ void eco_env_reset_auto(env_t* e) {
             v = c->founder_speed_mean[s] + c->founder_speed_std[s] * ppg_draw_normal(e->seed_key, genv(e), e->episode, PPG_STREAM_TRAIT, &e->trait_draws);
           sp[k] = clipd(v, c->speed_bounds[0], c->speed_bounds[1]);
         }
+    }
+  }
+  if (IS_CAD(c)) { /* CAD:1327 `rng.uniform(0.0, 1.0)` per founder: from the tape after the speeds, else the trait stream */
+    double* acc = sp + (c->genome_enabled ? n_f : 0);
+    if (e->tape_reals && e->real_pos + n_f <= e->real_end) {
+      for (int k = 0; k < n_f; ++k) acc[k] = e->tape_reals[e->real_pos++];
+    } else {
+      if (e->tape_reals) sticky |= PPG_STATUS_TAPE_EXHAUSTED;
+      for (int k = 0; k < n_f; ++k) acc[k] = ppg_draw_u01(e->seed_key, genv(e), e->episode, PPG_STREAM_TRAIT, &e->trait_draws);
     }
   }
   if (e->tape_cells && e->tape_pos + n_total <= e->tape_end) {
@@ -220,7 +252,7 @@ void eco_env_reset_auto(env_t* e) {
 /* speed ** exponent (ECO:559-563): CPython's float power is libm pow(), and so is the oracle's — always.  (The device
  * repeats glibc's pow bit for bit, include/ppg_pow.h; the checker is never bent toward the kernel.) */
 static double speed_cost_factor(const env_t* e, double speed) {
-  if (e->c->trait_mode != PPG_TRAIT_SPEED) return 1.0; /* MR:531-539: cost_per_cell * distance */
+  if (IS_MIC(e->c)) return 1.0; /* MR:531-539: cost_per_cell * distance */
   if (speed < 0.0) return 1.0; /* no genome */
   return pow(speed, e->c->move_speed_cost_exponent);
 }
@@ -253,10 +285,25 @@ static int occupied_by_agent(env_t* e, int x, int y) { /* `pos in set(self.agent
 static int eco_find_spawn(env_t* e, int px, int py, int* ox, int* oy) {
   static const int dx[4] = {-1, 1, 0, 0}, dy[4] = {0, 0, -1, 1};
   const int G = e->G;
+  int vx[4], vy[4], nv = 0;
   for (int k = 0; k < 4; ++k) {
     int x = px + dx[k], y = py + dy[k];
     if (x < 0 || x >= G || y < 0 || y >= G) continue;
-    if (!occupied_by_agent(e, x, y)) { *ox = x; *oy = y; return 1; }
+    if (!occupied_by_agent(e, x, y)) {
+      if (!IS_CAD(e->c)) { *ox = x; *oy = y; return 1; }
+      vx[nv] = x; vy[nv] = y; ++nv;
+    }
+  }
+  if (nv > 0) { /* CAD:795 `valid_positions[rng.integers(len(valid_positions))]`: the recorded cell, or a Philox index */
+    if (e->tape_cells && e->tape_pos < e->tape_end) {
+      int cell = e->tape_cells[e->tape_pos++];
+      *ox = cell / G; *oy = cell % G;
+      return 1;
+    }
+    if (e->tape_cells) e->status |= PPG_STATUS_TAPE_EXHAUSTED;
+    const uint32_t k = ppg_bounded(ppg_draw_u32(e->seed_key, genv(e), e->episode, PPG_STREAM_SPAWN, e->spawn_draws++), (uint32_t)nv);
+    *ox = vx[k]; *oy = vy[k];
+    return 1;
   }
   e->stats[PPG_STAT_SPAWN_FALLBACK]++;
   if (e->tape_cells && e->tape_pos < e->tape_end) {
@@ -281,6 +328,8 @@ static void capture_obs(env_t* e, int s, int id) { /* self.observations[agent] =
   const int i = e->list_index[s][id];
   eco_get_observation(e, s, id, e->obs + (size_t)i * e->max_row_elems);
   e->has_obs[i] = 1;
+  /* CAD:577-585,746-753 `_agent_will_move_this_step`: the mask looks one increment ahead of the stored accumulator */
+  if (IS_CAD(e->c)) e->frozen[i] = !(e->acc[s][id] + cad_move_rate(e, s, id) >= 1.0);
 }
 
 /* _terminate_agent_due_to_age (ECO:1060-1090) */
@@ -397,10 +446,38 @@ static void trait_predator_engagement(env_t* e, int id) {
   e->stats[PPG_STAT_EATEN_PREY]++;
 }
 
+/* _handle_predator_engagement of the cadence variant (CAD:824-905): the nearest prey within Chebyshev distance 1, the
+ * first one in agent_positions order on ties (prey enter the dict in ascending id), eaten whole */
+static void cad_predator_engagement(env_t* e, int id) {
+  const ppg_config* c = e->c;
+  const int i = e->list_index[0][id];
+  const int px = e->x[0][id], py = e->y[0][id];
+  int caught = -1, best = 0;
+  for (int q = 0; q < e->next_idx[1]; ++q) {
+    if (!e->present[1][q]) continue;
+    const int dx = abs(px - e->x[1][q]), dy = abs(py - e->y[1][q]);
+    const int dist = dx > dy ? dx : dy;
+    if (dist <= 1 && (caught < 0 || dist < best)) { caught = q; best = dist; }
+  }
+  if (caught < 0) { e->rew[i] = c->reward_predator_step; e->has_rew[i] = 1; return; }
+  const int j = e->list_index[1][caught];
+  e->ate[i] = 1;
+  e->rew[i] = c->reward_predator_catch_prey; e->has_rew[i] = 1;
+  e->energy[0][id] += e->energy[1][caught];                       /* CAD:857-861 */
+  *GF(e, 0, px, py) = (float)e->energy[0][id];
+  capture_obs(e, 1, caught);                                      /* CAD:869 */
+  e->term[j] = 1; e->termd[1][caught] = 1;
+  e->rew[j] = c->penalty_prey_caught; e->has_rew[j] = 1;
+  e->trunc[j] = 0;
+  e->active[1] -= 1;
+  *GF(e, 1, e->x[1][caught], e->y[1][caught]) = 0;
+  e->stats[PPG_STAT_EATEN_PREY]++;
+}
+
 /* _handle_prey_engagement (ECO:885-941) */
 static void handle_prey_engagement(env_t* e, int id) {
   const ppg_config* c = e->c;
-  if (c->trait_mode != PPG_TRAIT_SPEED) { trait_prey_engagement(e, id); return; }
+  if (IS_MIC(c)) { trait_prey_engagement(e, id); return; }
   const int i = e->list_index[1][id];
   if (e->termd[1][id]) return;
   if (e->dead[id]) { e->rew[i] = c->reward_prey_step; e->has_rew[i] = 1; return; }
@@ -427,7 +504,8 @@ static void handle_prey_engagement(env_t* e, int id) {
 /* _handle_predator_engagement (ECO:786-883) */
 static void handle_predator_engagement(env_t* e, int id) {
   const ppg_config* c = e->c;
-  if (c->trait_mode != PPG_TRAIT_SPEED) { trait_predator_engagement(e, id); return; }
+  if (IS_MIC(c)) { trait_predator_engagement(e, id); return; }
+  if (IS_CAD(c)) { cad_predator_engagement(e, id); return; }
   const int i = e->list_index[0][id];
   const int px = e->x[0][id], py = e->y[0][id];
   /* first prey in agent_positions order on the cell (ECO:797-799): prey enter the dict in ascending id
@@ -494,6 +572,9 @@ static void handle_reproduction(env_t* e, int s, int id) {
       sp = clipd(sp + d, c->speed_bounds[0], c->speed_bounds[1]);
     }
   }
+  double acc0 = 0.0;
+  if (IS_CAD(c) && !take_real(e, &acc0)) /* CAD:1327: after the genome, before the spawn search */
+    acc0 = ppg_draw_u01(e->seed_key, genv(e), e->episode, PPG_STREAM_TRAIT, &e->trait_draws);
   int sx, sy;
   if (!eco_find_spawn(e, e->x[s][id], e->y[s][id], &sx, &sy)) { /* RuntimeError (ECO:1142-1143) */
     e->status |= PPG_STATUS_NO_SPAWN_CELL;
@@ -518,6 +599,7 @@ static void handle_reproduction(env_t* e, int s, int id) {
     child_e = e->energy[s][id] * fraction;
   }
   if (s == 0) e->sat_until[child] = 0;                 /* MR:1141 */
+  e->acc[s][child] = acc0;
   e->energy[s][child] = child_e;
   e->energy[s][id] -= child_e;                         /* ECO:1150 */
   *GF(e, s, sx, sy) = (float)child_e;                  /* ECO:1154 */
@@ -559,6 +641,8 @@ int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, c
     const int s = KEY_S(e->agents[i]), id = KEY_ID(e->agents[i]);
     double decay = c->energy_loss[s];
     if (c->trait_mode == PPG_TRAIT_METABOLIC) decay = c->energy_loss[s] * (e->speed[s][id] >= 0.0 ? e->speed[s][id] : 1.0); /* MR:555-561 */
+    if (IS_CAD(c) && c->genome_enabled && c->metabolic_speed_coeff > 0.0 && e->speed[s][id] >= 0.0)
+      decay *= 1.0 + c->metabolic_speed_coeff * e->speed[s][id]; /* CAD:626-633 */
     e->energy[s][id] -= decay;
     *GF(e, s, e->x[s][id], e->y[s][id]) = (float)e->energy[s][id];
     if (!(s == 1 && e->dead[id])) e->age[s][id] += 1; /* carcasses do not age (ECO:600-601) */
@@ -580,6 +664,11 @@ int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, c
     int act = a_val[k];
     if (!e->present[s][id] || e->termd[s][id]) continue; /* ECO:633-634 */
     if (s == 1 && e->dead[id]) continue;                  /* ECO:636-637 */
+    if (IS_CAD(c)) { /* cadence gate (CAD:674-681): frozen agents keep their place, the accumulator still advances */
+      const double a = e->acc[s][id] + cad_move_rate(e, s, id);
+      if (a < 1.0) { e->acc[s][id] = a; continue; }
+      e->acc[s][id] = a - 1.0;
+    }
     if (act < 0 || act >= c->action_range * c->action_range) { e->status |= PPG_STATUS_BAD_ACTION; act = (c->action_range * c->action_range) / 2; }
     const int ox = e->x[s][id], oy = e->y[s][id];
     int nx, ny;

@@ -68,6 +68,7 @@ typedef struct env_t {
   int32_t* row_key;   /* ECO: agent of output row i (BASE: row i is self.agents[i]); NULL for BASE */
   uint8_t* carcass;   /* per row: in dead_prey after the step */
   uint8_t* born_obs;  /* per row: observation captured at birth (ECO:1179) is still the one in self.observations */
+  uint8_t* frozen;    /* per row, CAD: the action mask captured with the observation allows only "stay" (CAD:746-753) */
   float* gridf;       /* ECO grid_world_state is float32 [C][G][G] (ECO:222-224) */
   int32_t* age[2];    /* agent_ages (ECO:153) */
   double* speed[2];   /* agent_genomes[..].speed (ECO:177); < 0 = no genome */
@@ -80,6 +81,7 @@ typedef struct env_t {
   /* ---- trait variants of ECO (MR / INV / COOP, ppg_oracle_eco.c) ---- */
   int n_found[2];     /* founders of the running episode (MR:189-192) */
   int32_t* sat_until; /* agent_satiation_until by predator id (MR:134,756-757) */
+  double* acc[2];     /* CAD: agent_move_accumulator by id (CAD:183-186) */
   /* ---- STAG (ppg_oracle_stag.c) ---- */
   int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
   double* trait;      /* predator_cooperation_trait (STAG:230) */

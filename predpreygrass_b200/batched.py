@@ -286,6 +286,13 @@ class BatchedPredPreyGrass:
         st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]], active_num=act)
         return st
 
+    def read_env_acc(self, env):
+        """CAD `agent_move_accumulator` of the live agents of one env, in the order of read_env (include/ppg.h ppg_read_env_acc)"""
+        n = self.read_env(env)["ids"]
+        acc = [np.zeros(max(1, len(n[s])), np.float64) for s in range(2)]
+        _lib.check(self.L.ppg_read_env_acc(self.h, env, acc[0].ctypes.data, acc[1].ctypes.data), self.h)
+        return tuple(a[: len(n[s])] for s, a in enumerate(acc))
+
     def read_episode_eco(self, env):
         """per-episode totals of one ECO env (include/ppg.h ppg_read_episode_eco; needs make_config(track_episode_sums=True)):
         -> {"distance": (pred, prey), "move_energy": (pred, prey), "spawned": (pred, prey)}"""

@@ -24,6 +24,7 @@ STATUS_SLOT_OVERFLOW, STATUS_NO_SPAWN_CELL, STATUS_TAPE_EXHAUSTED, STATUS_BAD_AC
 STATUS_ID_POOL_EMPTY, STATUS_GHOST_CELL = 0x10, 0x20
 ROW_CARCASS = 0x20
 ROW_REPRODUCED = 0x40
+ROW_FROZEN = 0x80  # CAD: the agent's next action mask allows only "stay"
 N_STATS = 16
 STAT_NAMES = [
     "env_steps", "agent_steps", "episodes", "episode_steps", "births_pred", "births_prey", "starved_pred",
@@ -304,13 +305,31 @@ def _fill_eco(c, cfg):
         raise ValueError("lineage_reward_coeff != 0 is not supported (ECO:943-991 lineage survival rewards)")
 
 
+def _fill_cadence(c, cfg):
+    """`_initialize_from_config` of eco_evolutionary_cadence (CAD:44-124): ECO's keys and defaults without the carcass /
+    lineage / distance-gating ones, plus `max_cooldown` and `metabolic_speed_coeff`."""
+    g = cfg.get
+    _fill_eco(c, dict(cfg, lineage_reward_coeff=0.0))
+    c.trait_mode = TRAIT_CADENCE
+    c.carcass_only_predator_age = -1
+    d = (int(c.action_range) - 1) // 2
+    c.slow_max_move_distance = c.fast_max_move_distance = max(d, 0)  # `_get_move` does not clip the move vector (CAD:708-731)
+    c.speed_distance_threshold = float("inf")
+    c.max_energy_gain_per_prey = float("inf")   # CAD:857: the whole prey
+    c.max_cooldown = int(g("max_cooldown", 10))
+    if c.max_cooldown < 1:
+        raise ValueError("max_cooldown must be >= 1")
+    c.metabolic_speed_coeff = float(g("metabolic_speed_coeff", 1.0))
+    c.n_initial_min[0], c.n_initial_min[1] = c.n_initial[0], c.n_initial[1]
+
+
 def _fill_trait(c, cfg, trait):
     """`_initialize_from_config` of the other trait variants (MR:38-114, INV:38-114, COOP:38-98; mandatory keys are read
     with `cfg[...]` exactly where the reference does, so a missing one raises KeyError here as well)."""
     g = cfg.get
     mode = TRAITS[trait]
     if mode == TRAIT_CADENCE:
-        raise ValueError("the cadence variant is not built yet")
+        return _fill_cadence(c, cfg)
     c.trait_mode = mode
     c.max_steps = cfg["max_steps"]
     c.n_initial[0] = cfg["n_initial_active_predators"]
@@ -650,4 +669,20 @@ COOPERATION_CONFIG = dict(  # eco_evolutionary_cooperation/config/config_env_eco
     founder_genome={"predator": {"cooperation_rate_mean": 0.0, "cooperation_rate_std": 0.05},
                     "prey": {"cooperation_rate_mean": 0.0, "cooperation_rate_std": 0.05}},
     trait_bounds={"cooperation_rate": (0.0, 1.0)}, cooperation_range=2, n_possible_predators=500)
-TRAIT_CONFIGS = {"metabolic": METABOLIC_CONFIG, "investment": INVESTMENT_CONFIG, "cooperation": COOPERATION_CONFIG}
+CADENCE_CONFIG = {  # eco_evolutionary_cadence/config/config_env_eco_evolutionary.py
+    "ppg_trait": "cadence", "seed": 41, "max_steps": 1000, "grid_size": 25, "num_obs_channels": 3, "predator_obs_range": 7,
+    "prey_obs_range": 9, "action_range": 3, "reproduction_reward_predator": {"predator": 10.0},
+    "reproduction_reward_prey": {"prey": 10.0}, "max_agent_age": {"predator": None, "prey": 400},
+    "energy_loss_per_step_predator": 0.20, "energy_loss_per_step_prey": 0.05, "movement_energy_cost_per_cell_predator": 0.05,
+    "movement_energy_cost_per_cell_prey": 0.02, "predator_creation_energy_threshold": 12.0, "prey_creation_energy_threshold": 8.0,
+    "initial_energy_predator": 5.0, "initial_energy_prey": 3.0, "genome_enabled": True, "include_speed_in_obs": True,
+    "founder_genome": {"predator": {"speed_mean": 0.75, "speed_std": 0.1}, "prey": {"speed_mean": 0.5, "speed_std": 0.1}},
+    "genome_mutation": {"rate": 0.05, "std": 0.05}, "trait_bounds": {"speed": (0.0, 1.0)}, "max_cooldown": 10,
+    "movement_speed_cost_exponent": 2.0, "metabolic_speed_coeff": 0.3, "max_energy_gain_per_grass": float("inf"),
+    "max_energy_grass": 2.0, "n_possible_predators": 400, "n_possible_prey": 1200, "n_initial_active_predators": 10,
+    "n_initial_active_prey": 10, "initial_num_grass": 100, "initial_energy_grass": 2.0, "energy_gain_per_step_grass": 0.04,
+    "verbose_engagement": False, "verbose_movement": False, "verbose_decay": False, "verbose_reproduction": False,
+    "debug_mode": False, "record_step_data": False,
+}
+TRAIT_CONFIGS = {"metabolic": METABOLIC_CONFIG, "investment": INVESTMENT_CONFIG, "cooperation": COOPERATION_CONFIG,
+                 "cadence": CADENCE_CONFIG}

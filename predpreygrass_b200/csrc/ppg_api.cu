@@ -194,8 +194,12 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
     if (c->cap_live[0] > 32767 || c->cap_live[1] > 32767) { err = "ECO: cap_live must be <= 32767"; return PPG_ERR_INVALID; }
     if (c->slow_max_move_distance < 0 || c->fast_max_move_distance < 0) { err = "max move distance negative"; return PPG_ERR_INVALID; }
     if (!(c->speed_bounds[1] > c->speed_bounds[0])) { err = "speed bounds"; return PPG_ERR_INVALID; }
-    if (c->trait_mode < PPG_TRAIT_SPEED || c->trait_mode > PPG_TRAIT_COOPERATION) { err = "trait_mode: speed, metabolic_rate, offspring_investment_fraction and cooperation_rate are built (cadence is not)"; return PPG_ERR_INVALID; }
-    if (c->trait_mode != PPG_TRAIT_SPEED) {
+    if (c->trait_mode < PPG_TRAIT_SPEED || c->trait_mode > PPG_TRAIT_CADENCE) { err = "trait_mode out of range"; return PPG_ERR_INVALID; }
+    if (c->trait_mode == PPG_TRAIT_CADENCE) {
+      if (c->max_cooldown < 1) { err = "max_cooldown must be >= 1"; return PPG_ERR_INVALID; }
+      if (c->carcass_only_predator_age >= 0) { err = "cadence has no carcass-only predators"; return PPG_ERR_INVALID; }
+      if (c->n_initial_min[0] != c->n_initial[0] || c->n_initial_min[1] != c->n_initial[1]) { err = "cadence: the number of founders is fixed"; return PPG_ERR_INVALID; }
+    } else if (c->trait_mode != PPG_TRAIT_SPEED) {
       for (int s = 0; s < 2; ++s)
         if (c->n_initial_min[s] < 0 || c->n_initial_min[s] > c->n_initial[s]) { err = "n_initial_min must lie in [0, n_initial]"; return PPG_ERR_INVALID; }
       if (c->satiation_cooldown < 0 || c->satiation_cooldown > 250) { err = "satiation_cooldown must be in [0, 250]"; return PPG_ERR_INVALID; }
@@ -258,6 +262,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.sp_thr = c.speed_distance_threshold;
     P.trait_mode = c.trait_mode; P.n_init_min[0] = c.n_initial_min[0]; P.n_init_min[1] = c.n_initial_min[1];
     P.sat_cd = c.satiation_cooldown; P.coop_range = c.cooperation_range; P.trait_alpha = c.trait_alpha; P.repro_ratio = c.repro_max_ratio;
+    P.max_cooldown = c.max_cooldown; P.meta_coeff = c.metabolic_speed_coeff;
   } else if (stag) {
     P.action_range = std::max(c.type_action_range[0], c.type_action_range[1]); P.n_actions = P.action_range * P.action_range;
     for (int s = 0; s < 2; ++s)
@@ -359,6 +364,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     for (int s = 0; s < 2; ++s) {
       P.so_spd[s] = take(8 * (size_t)P.cap[s], 8); P.so_age[s] = take(2 * (size_t)P.cap[s], 2);
       P.so_seq[s] = take(2 * (size_t)P.cap[s], 2); P.so_mord[s] = take(2 * (size_t)P.cap[s], 2);
+      P.so_acc[s] = take(P.trait_mode == PPG_TRAIT_CADENCE ? 8 * (size_t)P.cap[s] : 0, 8);
     }
   }
   if (stag) {
@@ -461,6 +467,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     CKC(dalloc(h, &P.ag_prow[s], n)); CKC(dalloc(h, &P.ag_par[s], c.reward_mode == PPG_REWARD_SPARSE_KICKBACK ? n : 1));
     if (eco) {
       CKC(dalloc(h, &P.ag_age[s], n)); CKC(dalloc(h, &P.ag_seq[s], n)); CKC(dalloc(h, &P.ag_spd[s], n)); CKC(dalloc(h, &P.ag_dead[s], n));
+      if (P.trait_mode == PPG_TRAIT_CADENCE) CKC(dalloc(h, &P.ag_acc[s], n));
     }
     if (stag) {
       CKC(dalloc(h, &P.ag_age[s], n));
@@ -607,7 +614,7 @@ static int prepare_offsets(ppg_handle h, cudaStream_t st) {
   const unsigned prev_epoch = (unsigned)h->launches_step;
   const int q = (int)(prev_epoch & 1u);
   CK(launch_prepare_offsets(h->P.hdr, h->B, h->P.n_init[0], h->P.n_init[1], h->P.cntA[q], h->P.sum1[q], h->P.sum2[q],
-                            h->P.totals + 4 * q, prev_epoch, h->P.variant == PPG_VARIANT_ECO && h->P.trait_mode != PPG_TRAIT_SPEED, st));
+                            h->P.totals + 4 * q, prev_epoch, h->P.variant == PPG_VARIANT_ECO && ppg_random_founders(h->P.trait_mode), st));
   h->launch_count++;
   return PPG_OK;
 }
@@ -657,7 +664,7 @@ int ppg_reset(ppg_handle h, const uint64_t* seeds, const uint8_t* mask, void* cu
   if (mask) { CK(cudaMemcpyAsync(h->d_mask, mask, (size_t)h->B, cudaMemcpyHostToDevice, st)); dmask = h->d_mask; }
   CK(launch_mark_reset(h->P.hdr, h->B, dseeds, dmask, st));
   h->launch_count++;
-  const bool random_founders = h->P.variant == PPG_VARIANT_ECO && h->P.trait_mode != PPG_TRAIT_SPEED;
+  const bool random_founders = h->P.variant == PPG_VARIANT_ECO && ppg_random_founders(h->P.trait_mode);
   if (random_founders) {  // MR:189-192: the number of founders is drawn per episode; the row allocator needs it before the reset runs
     CK(launch_eco_founders(h->P, st));
     h->launch_count++;
@@ -803,6 +810,7 @@ static std::vector<Seg> state_segments(ppg_handle h) {
     if (P.reward_mode == PPG_REWARD_SPARSE_KICKBACK) v.push_back({P.ag_par[s], n * 2});
     if (P.variant == PPG_VARIANT_ECO) {
       v.push_back({P.ag_age[s], n * 2}); v.push_back({P.ag_seq[s], n * 2}); v.push_back({P.ag_spd[s], n * 8}); v.push_back({P.ag_dead[s], n});
+      if (P.trait_mode == PPG_TRAIT_CADENCE) v.push_back({P.ag_acc[s], n * 8});
     }
     if (P.variant == PPG_VARIANT_STAG) {
       v.push_back({P.ag_age[s], n * 2});
@@ -960,6 +968,19 @@ int ppg_read_env_eco(ppg_handle h, int32_t env, int32_t* age_pred, double* speed
   return PPG_OK;
 }
 
+int ppg_read_env_acc(ppg_handle h, int32_t env, double* acc_pred, double* acc_prey) {
+  if (!h || env < 0 || env >= h->B) return PPG_ERR_INVALID;
+  if (h->P.variant != PPG_VARIANT_ECO || h->P.trait_mode != PPG_TRAIT_CADENCE) { h->err = "ppg_read_env_acc: not a cadence handle"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  EnvHdr hd;
+  CK(cudaMemcpy(&hd, h->P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
+  double* out[2] = {acc_pred, acc_prey};
+  for (int s = 0; s < 2; ++s)
+    if (hd.n_list[s] && out[s]) CK(cudaMemcpy(out[s], h->P.ag_acc[s] + (size_t)env * h->P.cap[s], sizeof(double) * hd.n_list[s], cudaMemcpyDeviceToHost));
+  return PPG_OK;
+}
+
 int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawned) {
   if (!h || env < 0 || env >= h->B) return PPG_ERR_INVALID;
   if (h->P.variant != PPG_VARIANT_ECO || !h->P.ep_sums) { h->err = "ppg_read_episode_eco: needs an ECO handle created with track_episode_sums"; return PPG_ERR_STATE; }
@@ -969,7 +990,7 @@ int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawn
   CK(cudaMemcpy(&hd, h->P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
   if (sums) CK(cudaMemcpy(sums, h->P.ep_sums + (size_t)env * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost));
   // ids are handed out in order and never reused (ECO:260-272): spawned = ids used - founders of the running episode
-  const bool rf = h->P.trait_mode != PPG_TRAIT_SPEED;
+  const bool rf = ppg_random_founders(h->P.trait_mode);
   if (spawned) for (int s = 0; s < 2; ++s) spawned[s] = (int32_t)hd.next_idx[s] - (rf ? (s == 0 ? (hd.pad[1] & 0xFFFF) : ((hd.pad[1] >> 16) & 0x7FFF)) : h->P.n_init[s]);
   return PPG_OK;
 }

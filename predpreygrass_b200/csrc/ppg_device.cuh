@@ -82,6 +82,11 @@ enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_
 #define PPG_BORN_K 4      // at-birth rows kept per env and species; further ones take the (blocking) direct path
 #define PPG_MAX_GHOSTS 16 // ECO: stale prey-channel cells carried per env (ppg_eco.cu header); more raise PPG_STATUS_GHOST_CELL
 
+// trait variants whose number of founders is drawn per episode (MR:189-192); cadence and ECO have a fixed number
+__host__ __device__ inline bool ppg_random_founders(int trait_mode) {
+  return trait_mode == PPG_TRAIT_METABOLIC || trait_mode == PPG_TRAIT_INVESTMENT || trait_mode == PPG_TRAIT_COOPERATION;
+}
+
 struct StepParams {
   // ---- config ----
   int B, G, GG, C;
@@ -170,6 +175,10 @@ struct StepParams {
   // gain exponent, density cap (< 0: none)
   int trait_mode, n_init_min[2], sat_cd, coop_range;
   double trait_alpha, repro_ratio;
+  // cadence variant: move accumulators (CAD:183-186), slowest cadence, speed-dependent basal cost
+  int max_cooldown, so_acc[2];
+  double meta_coeff;
+  double* ag_acc[2];
   double* ep_sums;     // [B][4] optional (ppg_config.track_episode_sums): per-episode distance moved [2], locomotion energy [2]
   uint8_t* gh_n;       // [B] ghost cells of the env (ppg_eco.cu header)
   uint16_t* gh_cell;   // [B][PPG_MAX_GHOSTS] packed position x << 8 | y

@@ -39,6 +39,7 @@ struct EcoSmem {
   uint16_t* age[2];
   uint16_t* seq[2];
   uint16_t* mord[2];  // mord[k] = slot of the k-th mover of the species (action-dict order, ECO:632)
+  double* acc[2];     // CAD: move accumulators (cadence handles only)
 };
 
 template <typename MapT>
@@ -50,6 +51,7 @@ __device__ __forceinline__ EcoSmem<MapT> carve_eco(unsigned char* base, const St
     s.age[k] = reinterpret_cast<uint16_t*>(base + p.so_age[k]);
     s.seq[k] = reinterpret_cast<uint16_t*>(base + p.so_seq[k]);
     s.mord[k] = reinterpret_cast<uint16_t*>(base + p.so_mord[k]);
+    s.acc[k] = reinterpret_cast<double*>(base + p.so_acc[k]);
   }
   return s;
 }
@@ -57,7 +59,16 @@ __device__ __forceinline__ EcoSmem<MapT> carve_eco(unsigned char* base, const St
 // own-speed plane value (ECO:707-711): float32((speed - lo) / (hi - lo)); 0 without a genome
 __device__ __forceinline__ float speed_plane(const StepParams& p, double spd) {
   if (!p.speed_in_obs || spd < 0.0) return 0.f;
+  if (p.trait_mode == PPG_TRAIT_CADENCE) return (float)spd;  // CAD:746: the genome value itself
   return (float)((spd - p.sp_lo) / (p.sp_hi - p.sp_lo));
+}
+
+// _genome_speed_to_move_rate / _get_agent_move_rate (CAD:556-575): 1 / max_cooldown .. 1, linear in the clamped speed
+__device__ __forceinline__ double cad_move_rate(const StepParams& p, double spd) {
+  if (spd < 0.0) return 1.0;  // no genome
+  const double nrm = spd > 1.0 ? 1.0 : spd;
+  const double min_rate = 1.0 / (double)p.max_cooldown;
+  return min_rate + nrm * (1.0 - min_rate);
 }
 
 // speed ** exponent (ECO:559-563): CPython's float power = glibc pow, repeated bit for bit (include/ppg_pow.h)
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     if (TRAITS && tm == PPG_TRAIT_SPEED) __builtin_unreachable();
     // founders of the episode a reset starts: constant for ECO, drawn per episode by the trait variants (MR:189-192)
     int nf[2] = {p.n_init[0], p.n_init[1]};
-    if (tm != PPG_TRAIT_SPEED && ((unsigned)h.pad[1] & 0x80000000u)) { nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
+    if (ppg_random_founders(tm) && ((unsigned)h.pad[1] & 0x80000000u)) { nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
     if (!prefix_before(p.cntA[par ^ 1], p.sum1[par ^ 1], p.sum2[par ^ 1], 0, env, epoch - 1u, false, lane, old_base[0], old_base[1])) {
       if (lane == 0) atomicOr(p.error, 2u);
     }
@@ -295,6 +306,25 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             }
           }
           eh.trait_draws = ctr;
+        }
+      }
+      if (tm == PPG_TRAIT_CADENCE) {  // CAD:1327: a random accumulator phase per founder, after the speeds
+        if (p.tape_reals != nullptr && eh.real_pos + n_f <= eh.real_end) {
+          #pragma unroll 1
+          for (int k = lane; k < n_f; k += 32) {
+            const double v = p.tape_reals[eh.real_pos + k];
+            if (k < nf[0]) X.acc[0][k] = v; else X.acc[1][k - nf[0]] = v;
+          }
+          eh.real_pos += n_f;
+        } else {
+          if (p.tape_reals != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+          #pragma unroll 1
+          for (int k = lane; k < n_f; k += 32) {
+            unsigned ctr = eh.trait_draws + (unsigned)k;
+            const double v = ppg_draw_u01(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &ctr);
+            if (k < nf[0]) X.acc[0][k] = v; else X.acc[1][k - nf[0]] = v;
+          }
+          eh.trait_draws += (unsigned)n_f;
         }
       }
       __syncwarp();
@@ -418,8 +448,13 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           if (!carc) age += 1;  // carcasses do not age (ECO:600-601)
           SEL(S.id)[i] = (uint16_t)idpos;
           SEL(S.pos)[i] = (uint16_t)(idpos >> 16);
-          // ECO:596; MR:555-561: the basal cost scales with the metabolic rate (1.0 without a genome)
-          SEL(S.E)[i] = e0 - (tm == PPG_TRAIT_METABOLIC ? p.loss[s] * (tr >= 0.0 ? tr : 1.0) : p.loss[s]);
+          // ECO:596; MR:555-561: the basal cost scales with the metabolic rate (1.0 without a genome); CAD:626-633: with 1 + coeff * speed
+          double decay = tm == PPG_TRAIT_METABOLIC ? p.loss[s] * (tr >= 0.0 ? tr : 1.0) : p.loss[s];
+          if (tm == PPG_TRAIT_CADENCE) {
+            if (p.genome_enabled && p.meta_coeff > 0.0 && tr >= 0.0) decay = decay * (1.0 + p.meta_coeff * tr);
+            SEL(X.acc)[i] = p.ag_acc[s][b + i];
+          }
+          SEL(S.E)[i] = e0 - decay;
           SEL(X.spd)[i] = tr;
           SEL(X.age)[i] = (uint16_t)age;
           SEL(X.seq)[i] = (uint16_t)(agseq >> 16);
@@ -506,6 +541,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             j = SEL(X.mord)[k];
             const unsigned f = SEL(S.flg)[j];
             v = (f & F_ALIVE) && !(f & F_CARC);  // terminated (ECO:633) and dead prey (ECO:636) do not move
+            if (tm == PPG_TRAIT_CADENCE && v) {  // cadence gate (CAD:674-681): frozen agents keep their place, the accumulator still advances
+              const double a = SEL(X.acc)[j] + cad_move_rate(p, SEL(X.spd)[j]);
+              v = a >= 1.0;
+              SEL(X.acc)[j] = v ? a - 1.0 : a;
+            }
           }
           if (v) {
             const unsigned ps = SEL(S.pos)[j];
@@ -531,7 +571,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int nc = blocked ? oc : tc;
             if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
               const double sp = SEL(X.spd)[j];
-              const double fac = (sp < 0.0 || tm != PPG_TRAIT_SPEED) ? 1.0 : speed_cost_factor(sp, p.move_exp);  // MR:531-539: no speed factor
+              const double fac = (sp < 0.0 || ppg_random_founders(tm)) ? 1.0 : speed_cost_factor(sp, p.move_exp);  // MR:531-539 (MR / INV / COOP): no speed factor
               const double dist = sqrt((double)d2), cost = p.move_cost[s] * dist * fac;
               SEL(S.E)[j] = SEL(S.E)[j] - cost;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
@@ -560,7 +600,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int dd = (nx - xx) * (nx - xx) + (ny - yy) * (ny - yy);
             double e = SEL(S.E)[jj];
             if (dd > 0) {
-              const double fac = (sp < 0.0 || tm != PPG_TRAIT_SPEED) ? 1.0 : speed_cost_factor(sp, p.move_exp);
+              const double fac = (sp < 0.0 || ppg_random_founders(tm)) ? 1.0 : speed_cost_factor(sp, p.move_exp);
               const double dist = sqrt((double)dd), cost = p.move_cost[s] * dist * fac;
               e = e - cost;
               if (p.ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
@@ -696,7 +736,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         for (int b0 = 0; b0 < n[0]; b0 += 32) {
           const int k = b0 + lane;
           bool cand = false;
-          if (k < n[0]) cand = (S.flg[0][k] & F_ALIVE) && S.scr[CELLP((unsigned)S.pos[0][k])] != 0;
+          if (k < n[0]) {
+            const int c0 = CELLP((unsigned)S.pos[0][k]);
+            cand = S.scr[c0] != 0;
+            if (tm == PPG_TRAIT_CADENCE)  // catch radius 1 (CAD:837-848): any prey on the 3x3 block (the halo of `scr` is never marked)
+              cand = cand || S.scr[c0 - 1] || S.scr[c0 + 1] || S.scr[c0 - PS] || S.scr[c0 + PS] || S.scr[c0 - PS - 1] || S.scr[c0 - PS + 1] ||
+                     S.scr[c0 + PS - 1] || S.scr[c0 + PS + 1];
+            cand = cand && (S.flg[0][k] & F_ALIVE);
+          }
           unsigned m = __ballot_sync(FULL, cand);
           while (m) {
             const int slot = b0 + __ffs(m) - 1;
@@ -705,12 +752,23 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int cell = CELLP(ps);
             // first prey in agent_positions order on my cell = lowest id = lowest list slot (ECO:797-799)
             unsigned best = 0xFFFFFFFFu;
-            #pragma unroll 1
-            for (int i = lane; i < n[1]; i += 32)
-              if (S.pos[1][i] == ps) best = min(best, (unsigned)i);
+            if (tm == PPG_TRAIT_CADENCE) {  // the nearest prey within Chebyshev distance 1, the first in agent_positions order on ties
+              const int px = (int)(ps >> 8), py = (int)(ps & 255u);
+              #pragma unroll 1
+              for (int i = lane; i < n[1]; i += 32) {
+                const unsigned qp = S.pos[1][i];
+                const int d = max(abs(px - (int)(qp >> 8)), abs(py - (int)(qp & 255u)));
+                if (d <= 1) best = min(best, ((unsigned)d << 16) | (unsigned)i);
+              }
+            } else {
+              #pragma unroll 1
+              for (int i = lane; i < n[1]; i += 32)
+                if (S.pos[1][i] == ps) best = min(best, (unsigned)i);
+            }
             best = __reduce_min_sync(FULL, best);
             if (best == 0xFFFFFFFFu) continue;
-            const int q = (int)best;
+            const int q = (int)(best & 0xFFFFu);
+            const int qcell = CELLP((unsigned)S.pos[1][q]);  // the prey's own cell (= `cell` except for cadence's radius-1 catches)
             const unsigned qf = S.flg[1][q];
             const bool was_dead = (qf & F_CARC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
             if (!was_dead && p.carcass_age >= 0 && (int)X.age[0][slot] < p.carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
@@ -737,16 +795,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                 S.E[1][q] = rem;
                 // a prey that aged out this step (F_DIED) is removed in Step 5 without the grid being zeroed: the entry written
                 // here outlives its owner and becomes a ghost cell at write-back (see the header)
-                S.map[1][cell] = (MapT)(q + 1);
+                S.map[1][qcell] = (MapT)(q + 1);
                 S.flg[1][q] = (uint8_t)(qf | F_CARC);
               }
               __syncwarp();
             } else {  // fully eaten (ECO:846-866); its observation is captured now
               __syncwarp();
-              rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[1] + (size_t)(old_base[1] + q) * p.elems[1], cell, 1, n[0], n[1], rowctr,
+              rowctr = emit_row_now<MapT, false, true>(sbase, p, p.obs[1] + (size_t)(old_base[1] + q) * p.elems[1], qcell, 1, n[0], n[1], rowctr,
                                                        lane, speed_plane(p, X.spd[1][q]));
               if (lane == 0) {
-                S.map[1][cell] = 0;
+                S.map[1][qcell] = 0;
                 S.flg[1][q] = (uint8_t)((qf & F_ATE) | F_DIED | F_CAUGHT);
               }
               eh.active[1] -= 1;  // also for a prey that already starved or aged out this step (quirk 4)
@@ -791,16 +849,37 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                 spd = v < p.sp_lo ? p.sp_lo : (v > p.sp_hi ? p.sp_hi : v);
               }
             }
+            double acc0 = 0.0;
+            if (tm == PPG_TRAIT_CADENCE && !take_real(p, eh, h, acc0))  // CAD:1327: after the genome, before the spawn search
+              acc0 = ppg_draw_u01(h.seed_key, genv, h.episode, PPG_STREAM_TRAIT, &eh.trait_draws);
             const unsigned pp = SEL(S.pos)[ps_slot];
             const int px = pp >> 8, py = pp & 255;
             int nl[2] = {n[0] + births[0], n[1] + births[1]};
             int sx = -1, sy = -1;  // _find_available_spawn_position (ECO:732-764)
+            int vx[4] = {0, 0, 0, 0}, vy[4] = {0, 0, 0, 0}, nv = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int cx = px + (c == 0 ? -1 : (c == 1 ? 1 : 0));
               const int cy = py + (c == 2 ? -1 : (c == 3 ? 1 : 0));
-              if (sx < 0 && cx >= 0 && cx < G && cy >= 0 && cy < G) {
-                if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
+              if ((sx < 0 || tm == PPG_TRAIT_CADENCE) && cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) {
+                  if (sx < 0) { sx = cx; sy = cy; }
+                  if (tm == PPG_TRAIT_CADENCE) {
+                    if (nv == 0) { vx[0] = cx; vy[0] = cy; } else if (nv == 1) { vx[1] = cx; vy[1] = cy; } else if (nv == 2) { vx[2] = cx; vy[2] = cy; } else { vx[3] = cx; vy[3] = cy; }
+                    ++nv;
+                  }
+                }
+              }
+            }
+            if (tm == PPG_TRAIT_CADENCE && nv > 0) {  // CAD:795 `valid_positions[rng.integers(len(valid_positions))]`
+              if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
+                const int c = p.tape_cells[h.tape_pos++];  // the recorded choice
+                sx = c / G; sy = c % G;
+              } else {
+                if (p.tape_cells != nullptr) h.status |= PPG_STATUS_TAPE_EXHAUSTED;
+                const unsigned k = ppg_bounded(ppg_draw_u32(h.seed_key, genv, h.episode, PPG_STREAM_SPAWN, h.spawn_draws++), (unsigned)nv);
+                sx = k == 0 ? vx[0] : (k == 1 ? vx[1] : (k == 2 ? vx[2] : vx[3]));
+                sy = k == 0 ? vy[0] : (k == 1 ? vy[1] : (k == 2 ? vy[2] : vy[3]));
               }
             }
             if (sx < 0) {
@@ -834,6 +913,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               SEL(X.age)[cs] = 0;
               SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
               SEL(X.spd)[cs] = p.genome_enabled ? spd : -1.0;
+              if (tm == PPG_TRAIT_CADENCE) SEL(X.acc)[cs] = acc0;
               SEL(S.E)[ps_slot] = pe;
               SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // ECO:1154
               SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // ECO:1155
@@ -875,7 +955,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       env_flags = (done ? PPG_ENV_TERMINATED : 0) | (trunc ? PPG_ENV_TRUNCATED : 0);
       if (over) {
         if (p.autoreset) {
-          if (tm != PPG_TRAIT_SPEED) { draw_next_founders(p, h, genv); nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
+          if (ppg_random_founders(tm)) { draw_next_founders(p, h, genv); nf[0] = h.pad[0] & 0xFFFF; nf[1] = (h.pad[0] >> 16) & 0x7FFF; }
           next_live[0] = nf[0]; next_live[1] = nf[1];
         }
       } else {
@@ -958,6 +1038,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               if (f & F_ATE) rf |= PPG_ROW_ATE;
               if (f & F_REPRO) rf |= PPG_ROW_REPRODUCED;
               if (alive && (f & F_CARC)) rf |= PPG_ROW_CARCASS;
+              // CAD:577-585,746-753: the action mask of the row looks one increment ahead of the stored accumulator
+              if (tm == PPG_TRAIT_CADENCE && !(SEL(X.acc)[slot] + cad_move_rate(p, SEL(X.spd)[slot]) >= 1.0)) rf |= PPG_ROW_FROZEN;
               if (!(SPLIT && newborn)) {
                 p.row_env[s][row] = env;
                 p.row_agent[s][row] = SEL(S.id)[slot];
@@ -980,6 +1062,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               p.ag_age[s][sb + dst] = SEL(X.age)[slot];
               p.ag_seq[s][sb + dst] = SEL(X.seq)[slot];
               p.ag_spd[s][sb + dst] = SEL(X.spd)[slot];
+              if (tm == PPG_TRAIT_CADENCE) p.ag_acc[s][sb + dst] = SEL(X.acc)[slot];
               if (tm == PPG_TRAIT_SPEED) p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
               else {  // predators: steps of digestion left at the next step (MR:734-740,756-757)
                 const unsigned rmn = (mode == 2 && s == 0 && slot < n[0] && (tm == PPG_TRAIT_METABOLIC || tm == PPG_TRAIT_INVESTMENT)) ? X.mord[0][slot] : 0u;

@@ -29,7 +29,7 @@ agents that ended this step sorted by id string (STAG:567-568).
 """
 import numpy as np
 
-from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_REPRODUCED, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO,
+from .config import (ENV_TERMINATED, ENV_TRUNCATED, ROW_ATE, ROW_FROZEN, ROW_REPRODUCED, ROW_TERMINATED, ROW_TRUNCATED, VARIANT_ECO,
                      VARIANT_STAG, make_config)
 from .env import Box, Discrete, _Base, raise_on_status
 
@@ -625,6 +625,117 @@ class PredPreyGrassCooperation(_TraitEnv):
     """eco_evolutionary_cooperation `PredPreyGrass(config)`: heritable cooperation rate (a share of every meal goes to neighbours)."""
 
     _trait, _tag = "cooperation_rate", "coop"
+
+
+# ---------------------------------------------------------------------------------------------- cadence
+def reference_reset_tape_cadence(seed, config):
+    """The draws of the cadence variant's `reset(seed)` in the tape layout of include/ppg.h: per founder (predators, then prey)
+    `rng.normal(mean, std)` where std > 0 (genome.py founder_genome, clipped to the trait bounds) and then
+    `rng.uniform(0.0, 1.0)` for the move accumulator (CAD:1324-1327); then one `rng.choice(G*G, n, replace=False)` for the cells.
+    -> (cells int32, [speeds..., accumulators...] f64: the device reads all speeds first)"""
+    rng = np.random.default_rng(seed)
+    G = config["grid_size"]
+    n = (config["n_initial_active_predators"], config["n_initial_active_prey"])
+    genome = config.get("genome_enabled", True)
+    lo, hi = config.get("trait_bounds", {}).get("speed", (0.5, 2.0))
+    speeds, accs = [], []
+    for role, k in (("predator", n[0]), ("prey", n[1])):
+        f = config.get("founder_genome", {}).get(role, {})
+        mean, std = f.get("speed_mean", 1.0), f.get("speed_std", 0.0)
+        for _ in range(k):
+            if genome:
+                v = mean if std <= 0 else float(rng.normal(mean, std))
+                speeds.append(float(np.clip(v, float(lo), float(hi))))
+            accs.append(float(rng.uniform(0.0, 1.0)))
+    cells = rng.choice(G * G, size=n[0] + n[1] + config["initial_num_grass"], replace=False)
+    return np.asarray(cells, np.int32), np.asarray(speeds + accs, np.float64)
+
+
+class PredPreyGrassCadence(PredPreyGrassEco):
+    """eco_evolutionary_cadence `PredPreyGrass(config)`: the speed genome sets how OFTEN an agent may move (a per-agent
+    accumulator, CAD:556-585,674-681); observations are dicts {"observations": window, "action_mask": 9 floats} whose mask
+    allows only "stay" on the steps the agent will be frozen (device row flag PPG_ROW_FROZEN)."""
+
+    _tolerated_status = 0
+
+    def __init__(self, config=None):
+        if config is None:
+            raise ValueError("Environment config must be provided explicitly.")
+        config = dict(config, ppg_trait="cadence", lineage_reward_coeff=0.0)
+        super().__init__(config)
+        self.max_cooldown = int(config.get("max_cooldown", 10))
+        n_act = self.action_range ** 2
+        self._stay_action_index = n_act // 2
+        mask_space = Box(low=0.0, high=1.0, shape=(n_act,), dtype=np.float32)
+        C = self.num_obs_channels + (1 if self.include_speed_in_obs else 0)  # CAD:1277-1296: spatial Box(-100, 100) + mask
+        sp = {0: Box(low=-100.0, high=100.0, shape=(C, self.predator_obs_range, self.predator_obs_range), dtype=np.float32),
+              1: Box(low=-100.0, high=100.0, shape=(C, self.prey_obs_range, self.prey_obs_range), dtype=np.float32)}
+        self.observation_spaces = {a: DictSpace({"observations": sp[0 if "predator" in a else 1], "action_mask": mask_space})
+                                   for a in self.possible_agents}
+        self.observation_space = DictSpace(self.observation_spaces)
+        self._all = np.ones(n_act, np.float32)
+        self._stay_only = np.zeros(n_act, np.float32)
+        self._stay_only[self._stay_action_index] = 1.0
+
+    def _mask_dicts(self, out, obs):
+        """window + row flag -> the reference's observation dict (CAD:746-753)"""
+        flags = {self._name(s, int(out[f"row_agent{s}"][r])): int(out[f"flags{s}"][r]) for _, s, r, _ in self._rows_of(out)}
+        return {a: {"observations": o, "action_mask": (self._stay_only if flags[a] & ROW_FROZEN else self._all).copy()} for a, o in obs.items()}
+
+    def reset(self, *, seed=None, options=None):
+        _Base.reset(self, seed=seed)
+        if seed is None:
+            seed = self.config["seed"]
+        cells, reals = reference_reset_tape_cadence(seed, self.config)
+        out = self._reset_device(seed, cells, reals, options)
+        obs, *_ = self._dicts(out)
+        self.agents = list(obs)
+        self._episode_speeds = ([], [])
+        if self.genome_enabled:
+            st = self._read()
+            for s in range(2):
+                self._episode_speeds[s].extend(float(v) for v in st["speed"][s])
+        return self._mask_dicts(out, obs), {}
+
+    def step(self, action_dict):
+        obs, rew, term, trunc, infos = super().step(action_dict)
+        return self._mask_dicts(self._batch.outputs_numpy(), obs), rew, term, trunc, infos
+
+    @property
+    def agent_move_accumulator(self):
+        acc = self._batch.read_env_acc(0)
+        st = self._read()
+        return {self._name(s, int(i)): float(v) for s in range(2) for i, v in zip(st["ids"][s], acc[s])}
+
+    def _move_rate(self, speed):
+        return 1.0 / self.max_cooldown + max(0.0, min(1.0, float(speed))) * (1.0 - 1.0 / self.max_cooldown)  # CAD:556-571
+
+    def _cadence_keys(self, res, role, v):
+        """the cadence keys that replace ECO's `fraction_fast` (CAD:524-542,1471-1485)"""
+        res.pop(f"{role}_fraction_fast", None)
+        if len(v):
+            rates = np.array([self._move_rate(x) for x in v])
+            cd = 1.0 / rates
+            res[f"{role}_fraction_mobile"] = float(np.mean(rates >= 1.0 - 1e-9))
+            res[f"{role}_fraction_fast_cadence"] = float(np.mean(cd <= max(1.0, self.max_cooldown / 2.0)))
+            res[f"{role}_cooldown_mean"] = float(np.mean(cd))
+        else:
+            res[f"{role}_fraction_mobile"] = 0.0
+            res[f"{role}_fraction_fast_cadence"] = 0.0
+            res[f"{role}_cooldown_mean"] = float(self.max_cooldown)
+
+    def episode_training_metrics(self):
+        res = super().episode_training_metrics()
+        for s, role in enumerate(("predator", "prey")):
+            self._cadence_keys(res, role, self._episode_speeds[s])
+        return res
+
+    def live_speed_metrics(self):
+        res = super().live_speed_metrics()
+        st = self._read()
+        for s, role in enumerate(("predator", "prey")):
+            self._cadence_keys(res, role, st["speed"][s] if self.genome_enabled else [])
+        return res
 
 
 # ---------------------------------------------------------------------------------------------- STAG

@@ -3,6 +3,10 @@
   mr_*    predpreygrass/evolutionary/eco_evolutionary_metabolic_rate/predpreygrass_rllib_env.py   (MR)
   inv_*   predpreygrass/evolutionary/eco_evolutionary_investment/predpreygrass_rllib_env.py       (INV)
   coop_*  predpreygrass/evolutionary/eco_evolutionary_cooperation/predpreygrass_rllib_env.py      (COOP)
+  cad_*   predpreygrass/evolutionary/eco_evolutionary_cadence/predpreygrass_rllib_env.py          (CAD; its observations
+          are dicts {"observations", "action_mask"}: the window is recorded like the others', the mask as one "frozen" bit per
+          row after checking that it is all ones or "stay" only; also the founders' move accumulators, the accumulators
+          after every step and, per birth, the extra `rng.uniform` phase draw, CAD:1324-1327)
 
 Runs in the build container only (needs /root/reference); the GPU box never executes this.
 Usage:  python tests/golden/make_golden_traits.py [case ...]
@@ -35,8 +39,9 @@ sys.path.insert(0, REF)
 
 PKG = {"mr": "predpreygrass.evolutionary.eco_evolutionary_metabolic_rate",
        "inv": "predpreygrass.evolutionary.eco_evolutionary_investment",
-       "coop": "predpreygrass.evolutionary.eco_evolutionary_cooperation"}
-TRAIT = {"mr": "metabolic_rate", "inv": "offspring_investment_fraction", "coop": "cooperation_rate"}
+       "coop": "predpreygrass.evolutionary.eco_evolutionary_cooperation",
+       "cad": "predpreygrass.evolutionary.eco_evolutionary_cadence"}
+TRAIT = {"mr": "metabolic_rate", "inv": "offspring_investment_fraction", "coop": "cooperation_rate", "cad": "speed"}
 
 CROWDED = dict(grid_size=9, initial_num_grass=24, n_initial_active_predators=6, n_initial_active_prey=14,
                predator_creation_energy_threshold=6.0, prey_creation_energy_threshold=4.5, energy_gain_per_step_grass=0.3,
@@ -76,6 +81,15 @@ CASES = [
                                              "prey": {"cooperation_rate_mean": 0.5, "cooperation_rate_std": 0.3}}), 3, "id", 200),
     ("coop_trunc_s4", dict(RICH, max_steps=30, founder_genome={"predator": {"cooperation_rate_mean": 0.2, "cooperation_rate_std": 0.1},
                                                                "prey": {"cooperation_rate_mean": 0.2, "cooperation_rate_std": 0.1}}), 4, "id", 60),
+    ("cad_default_s1", {}, 1, "id", 300),
+    ("cad_default_s2_shuffle", {}, 2, "shuffle", 300),
+    ("cad_rich_s3", dict(RICH, energy_loss_per_step_predator=0.1, genome_mutation={"rate": 0.6, "std": 0.15}), 3, "id", 140),
+    ("cad_crowded_s4", dict(CROWDED, energy_loss_per_step_prey=0.02, energy_loss_per_step_predator=0.1, initial_energy_predator=3.0,
+                            initial_energy_prey=2.0, max_cooldown=3, genome_mutation={"rate": 0.5, "std": 0.3}), 4, "shuffle", 200),
+    ("cad_aging_s5", dict(RICH, max_agent_age={"predator": 30, "prey": 12}, max_cooldown=4, metabolic_speed_coeff=0.0,
+                          max_energy_gain_per_grass=1.0), 5, "id", 120),
+    ("cad_nogenome_s6", dict(RICH, genome_enabled=False, include_speed_in_obs=False, energy_loss_per_step_predator=0.1), 6, "id", 120),
+    ("cad_trunc_s7", dict(RICH, max_steps=30), 7, "shuffle", 60),
 ]
 
 
@@ -105,6 +119,11 @@ class RecordingRng:
     def normal(self, *a, **k):
         v = self._rng.normal(*a, **k)
         self._log.append(("n", float(v)))
+        return v
+
+    def uniform(self, *a, **k):
+        v = self._rng.uniform(*a, **k)
+        self._log.append(("f", float(v)))
         return v
 
     def integers(self, *a, **k):
@@ -144,18 +163,33 @@ def record(name, overrides, seed, order, max_calls):
 
     env._find_available_spawn_position = find_wrapped
 
+    cad = fam == "cad"
+    win = (lambda o: o["observations"]) if cad else (lambda o: o)
+
+    def frozen(o):  # CAD:746-753: the mask is all ones, or "stay" only
+        if not cad:
+            return 0
+        m = np.asarray(o["action_mask"])
+        assert m.dtype == np.float32 and m.shape == (n_act_total,)
+        stay_only = np.zeros(n_act_total, np.float32); stay_only[n_act_total // 2] = 1.0
+        assert np.array_equal(m, np.ones(n_act_total, np.float32)) or np.array_equal(m, stay_only), m
+        return int(m.sum() == 1.0)
+
+    n_act_total = env.action_range ** 2
     founders = list(env.agents)
     n_found = [sum(1 for a in founders if split(a)[0] == s) for s in range(2)]
     founder_trait = [float(getattr(env.agent_genomes[a], trait)) for a in founders] if env.genome_enabled else []
+    founder_acc = [float(env.agent_move_accumulator[a]) for a in founders] if cad else []
     init_cells = [int(env.agent_positions[a][0]) * G + int(env.agent_positions[a][1]) for a in founders]
     init_cells += [int(p[0]) * G + int(p[1]) for p in env.grass_positions.values()]
     reset_keys = sorted(split(a) for a in obs)
-    reset_obs = [obs[f"{NAMES[s]}_{i}"] for s, i in reset_keys]
+    reset_obs = [win(obs[f"{NAMES[s]}_{i}"]) for s, i in reset_keys]
+    reset_frozen = [frozen(obs[f"{NAMES[s]}_{i}"]) for s, i in reset_keys]
 
     arng = np.random.default_rng(seed * 7919 + 13)
     n_act = env.action_range ** 2
-    names = ("act_s", "act_id", "act_v", "row_s", "row_id", "row_rew", "row_term", "row_trunc", "st_s", "st_id", "st_x", "st_y",
-             "st_e", "st_age", "st_trait", "ag_s", "ag_id")
+    names = ("act_s", "act_id", "act_v", "row_s", "row_id", "row_rew", "row_term", "row_trunc", "row_frozen", "st_s", "st_id", "st_x", "st_y",
+             "st_e", "st_age", "st_trait", "st_acc", "ag_s", "ag_id")
     rec = {k: [] for k in names}
     offs = {k: [0] for k in ("act", "row", "st", "ag")}
     obs_sha, grid_sha, grass_e, all_term, all_trunc, steps, active = [], [], [], [], [], [], []
@@ -185,8 +219,9 @@ def record(name, overrides, seed, order, max_calls):
             a = f"{NAMES[s]}_{i}"
             rec["row_s"].append(s); rec["row_id"].append(i); rec["row_rew"].append(float(rew[a]))
             rec["row_term"].append(int(bool(term[a]))); rec["row_trunc"].append(int(bool(trunc[a])))
-            assert obs[a].dtype == np.float32
-            row_obs.append(obs[a])
+            assert win(obs[a]).dtype == np.float32
+            row_obs.append(win(obs[a]))
+            rec["row_frozen"].append(frozen(obs[a]))
         offs["row"].append(len(rec["row_s"]))
         obs_sha.append(sha(row_obs, np.float32))
         if calls < 2 or calls % 60 == 0:
@@ -197,6 +232,7 @@ def record(name, overrides, seed, order, max_calls):
             rec["st_e"].append(float(env.agent_energies[a])); rec["st_age"].append(int(env.agent_ages[a]))
             g = env.agent_genomes.get(a)
             rec["st_trait"].append(float(getattr(g, trait)) if g is not None else -1.0)
+            rec["st_acc"].append(float(env.agent_move_accumulator[a]) if cad else 0.0)
         offs["st"].append(len(rec["st_s"]))
         for a in env.agents:
             s, i = split(a)
@@ -213,13 +249,15 @@ def record(name, overrides, seed, order, max_calls):
             metrics = {k: float(v) for k, v in infos["__all__"]["training_metrics"].items()}
         calls += 1
 
-    reals = [v for k, v in log if k in ("u", "n")]
-    assert all(k in ("u", "n") for k, _ in log), "unexpected rng.integers outside the spawn fallback"
+    reals = [v for k, v in log if k in ("u", "n", "f")]
+    assert all(k in ("u", "n", "f") for k, _ in log), "unexpected rng.integers outside the spawn search"
     out = dict(
         cfg_json=np.array(json.dumps(dict(cfg, variant=fam), default=lambda o: None)), seed=np.int64(seed), order=np.array(order),
         n_found=np.array(n_found, np.int32),
         init_cells=np.array(init_cells, np.int32), fallback_cells=np.array(fallback, np.int32),
-        founder_trait=np.array(founder_trait, np.float64), step_reals=np.array(reals, np.float64),
+        founder_trait=np.array(founder_trait, np.float64), founder_acc=np.array(founder_acc, np.float64),
+        step_reals=np.array(reals, np.float64), reset_frozen=np.array(reset_frozen, np.int8),
+        row_frozen=np.array(rec["row_frozen"], np.int8), st_acc=np.array(rec["st_acc"], np.float64),
         reset_row_s=np.array([k[0] for k in reset_keys], np.int8), reset_row_id=np.array([k[1] for k in reset_keys], np.int32),
         reset_sha=sha(reset_obs, np.float32),
         act_off=np.array(offs["act"], np.int64), row_off=np.array(offs["row"], np.int64),

@@ -33,10 +33,10 @@ def config_from_golden(cfg, **kw):
 
         kw.setdefault("cap_live", (cfg["n_possible_predators"], cfg["n_possible_prey"]))
         return make_config(cfg, variant=VARIANT_ECO, **kw)
-    if variant in ("mr", "inv", "coop"):
+    if variant in ("mr", "inv", "coop", "cad"):
         from predpreygrass_b200.config import VARIANT_ECO
 
-        trait = {"mr": "metabolic_rate", "inv": "offspring_investment_fraction", "coop": "cooperation_rate"}[variant]
+        trait = {"mr": "metabolic_rate", "inv": "offspring_investment_fraction", "coop": "cooperation_rate", "cad": "cadence"}[variant]
         kw.setdefault("cap_live", (min(cfg["n_possible_predators"], 224), min(cfg["n_possible_prey"], 416)))
         return make_config(cfg, variant=VARIANT_ECO, trait=trait, **kw)
     if variant == "stag":

@@ -54,6 +54,10 @@ def compare_env_state(gpu, oracle, env, where=""):
             assert np.array_equal(a["speed"][s], b["speed"][s]), (where, env, s)
         assert np.array_equal(a["dead_prey"], b["dead_prey"]), (where, env)
         assert np.array_equal(a["active_num"], b["active_num"]), (where, env)
+        if gpu.cfg.trait_mode == 4:  # cadence: the move accumulators (float64, bit-exact)
+            ga, oa = gpu.read_env_acc(env), oracle.read_env_acc(env)
+            for s in range(2):
+                assert np.array_equal(ga[s], oa[s]), (where, env, s, ga[s], oa[s])
     for s in range(2):
         assert np.array_equal(a["ids"][s], b["ids"][s]), (where, env, s, a["ids"][s], b["ids"][s])
         assert np.array_equal(a["xy"][s], b["xy"][s]), (where, env, s)

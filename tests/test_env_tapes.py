@@ -47,3 +47,14 @@ def test_trait_reset_tape_equals_the_reference_reset(name):
     assert np.array_equal(ints[:2], z["n_found"])
     assert np.array_equal(ints[2:], z["init_cells"])
     assert np.array_equal(values, z["founder_trait"])
+
+
+@pytest.mark.parametrize("name", golden_cases(("cad",)))
+def test_cadence_reset_tape_equals_the_reference_reset(name):
+    """per founder a speed draw then an accumulator phase (CAD:1324-1327), then the cells"""
+    from predpreygrass_b200.env_evolutionary import reference_reset_tape_cadence
+
+    z, cfg = load_golden(name)
+    cells, reals = reference_reset_tape_cadence(int(z["seed"]), cfg)
+    assert np.array_equal(cells, z["init_cells"])
+    assert np.array_equal(reals, np.concatenate([z["founder_trait"], z["founder_acc"]]))

@@ -228,3 +228,59 @@ def test_trait_dict_adapter_replays_reference_episode(name):
         assert (env.active_num_predators, env.active_num_prey) == tuple(z["active"][t])
     assert ended or str(z["metrics_json"]) == "null"
     env.close()
+
+
+@pytest.mark.parametrize("name", golden_cases(("cad",)))
+def test_cadence_dict_adapter_replays_reference_episode(name):
+    """PredPreyGrassCadence through the reference's dict API: observation dicts {"observations", "action_mask"}, the
+    accumulators after every step, the episode's training_metrics."""
+    from predpreygrass_b200.env_evolutionary import PredPreyGrassCadence
+
+    z, cfg = load_golden(name)
+    cfg.pop("variant")
+    cfg["cap_live"] = _caps(cfg, (("n_possible_predators",), ("n_possible_prey",)))
+    env = PredPreyGrassCadence(cfg)
+    names = ("predator", "prey")
+    key = lambda s, i: f"{names[s]}_{i}"  # noqa: E731
+    n_act = cfg["action_range"] ** 2
+
+    def check_masks(obs, keys, frozen):
+        for k, fr in zip(keys, frozen):
+            m = obs[k]["action_mask"]
+            assert m.dtype == np.float32 and m.shape == (n_act,)
+            assert (m.sum() == 1.0 and m[n_act // 2] == 1.0) if fr else bool((m == 1.0).all()), (name, k, m)
+
+    obs, infos = env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    keys = [key(s, i) for s, i in zip(z["reset_row_s"], z["reset_row_id"])]
+    assert list(obs) == keys
+    assert np.array_equal(sha_f32([obs[k]["observations"] for k in obs]), z["reset_sha"])
+    check_masks(obs, keys, z["reset_frozen"])
+    for a, o in obs.items():
+        assert o["observations"].shape == env.observation_spaces[a]["observations"].shape
+    for t in range(len(z["steps"])):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {key(s, i): int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        obs, rew, term, trunc, infos = env.step(acts)
+        r0, r1 = z["row_off"][t], z["row_off"][t + 1]
+        keys = [key(s, i) for s, i in zip(z["row_s"][r0:r1], z["row_id"][r0:r1])]
+        assert list(obs) == keys and list(rew) == keys, (name, t)
+        assert np.array_equal(np.array([rew[k] for k in keys], np.float32), z["row_rew"][r0:r1].astype(np.float32)), (name, t)
+        assert [int(term[k]) for k in keys] == list(z["row_term"][r0:r1]), (name, t)
+        assert [int(trunc[k]) for k in keys] == list(z["row_trunc"][r0:r1]), (name, t)
+        assert np.array_equal(sha_f32([obs[k]["observations"] for k in keys]), z["obs_sha"][t]), (name, t)
+        check_masks(obs, keys, z["row_frozen"][r0:r1])
+        assert term["__all__"] == bool(z["all_term"][t]) and trunc["__all__"] == bool(z["all_trunc"][t]), (name, t)
+        if term["__all__"] or trunc["__all__"]:
+            want = json.loads(str(z["metrics_json"]))
+            got = infos["__all__"]["training_metrics"]
+            assert set(got) <= set(want), (name, sorted(set(got) - set(want)))
+            for k, v in got.items():
+                assert v == pytest.approx(want[k], rel=1e-9, abs=1e-12), (name, k, v, want[k])
+            break
+        s0, s1 = z["st_off"][t], z["st_off"][t + 1]
+        want = {key(s, i): ((int(x), int(y)), float(e), float(a)) for s, i, x, y, e, a in
+                zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_x"][s0:s1], z["st_y"][s0:s1], z["st_e"][s0:s1], z["st_acc"][s0:s1])}
+        pos, en, acc = env.agent_positions, env.agent_energies, env.agent_move_accumulator
+        assert sorted(pos) == sorted(want), (name, t)
+        assert all((pos[k], en[k], acc[k]) == want[k] for k in want), (name, t)
+    env.close()

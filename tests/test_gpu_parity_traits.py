@@ -7,7 +7,8 @@ and rewards, the active_num_* counters.  `metabolic_rate ** alpha` is glibc's po
 import numpy as np
 import pytest
 
-from predpreygrass_b200.config import COOPERATION_CONFIG, INVESTMENT_CONFIG, METABOLIC_CONFIG, VARIANT_ECO, make_config
+from predpreygrass_b200.config import (CADENCE_CONFIG, COOPERATION_CONFIG, INVESTMENT_CONFIG, METABOLIC_CONFIG, VARIANT_ECO,
+                                      make_config)
 from tests.helpers import config_from_golden, golden_cases, id_order_rows, load_golden, sha_f32
 from tests.parity import lockstep_parity
 
@@ -79,13 +80,39 @@ def test_coop_sharing_dominates():
     assert st["eaten_prey"] > 0 and st["grass_eaten"] > 1000
 
 
+def test_cad_default_philox():
+    """default cadence world: move accumulators, speed-scaled basal cost, radius-1 catches, random spawn neighbour, action mask bit"""
+    st = lockstep_parity(trait(CADENCE_CONFIG, cap_live=(64, 160), seed=29), 256, 200, state_envs=(0, 7, 255))
+    assert st["status_envs"] == 0 and st["episodes"] > 256 and st["eaten_prey"] > 0
+
+
+def test_cad_rich_mutation_and_age_caps():
+    cfg = dict(CADENCE_CONFIG, **RICH, energy_loss_per_step_predator=0.1, genome_mutation={"rate": 0.6, "std": 0.15},
+               max_agent_age={"predator": 40, "prey": 25}, max_cooldown=4, max_energy_gain_per_grass=1.0, max_steps=150)
+    st = lockstep_parity(trait(cfg, cap_live=(128, 384), seed=31), 128, 170, state_envs=(0, 64, 127))
+    assert st["births_prey"] > 500 and st["births_pred"] > 0
+
+
+def test_cad_crowded_spawn_choices():
+    cfg = dict(CADENCE_CONFIG, **CROWDED, energy_loss_per_step_prey=0.02, energy_loss_per_step_predator=0.1, initial_energy_predator=3.0,
+               initial_energy_prey=2.0, max_cooldown=3, genome_mutation={"rate": 0.5, "std": 0.3})
+    st = lockstep_parity(trait(cfg, cap_live=(64, 81), seed=37), 256, 120, state_envs=(0, 17, 255))
+    assert st["births_prey"] > 0 and st["episodes"] > 256
+
+
+def test_cad_without_genome():
+    cfg = dict(CADENCE_CONFIG, **RICH, genome_enabled=False, include_speed_in_obs=False, energy_loss_per_step_predator=0.1, max_steps=60)
+    st = lockstep_parity(trait(cfg, cap_live=(128, 384), seed=41), 64, 130, state_envs=(0, 63))
+    assert st["episodes"] > 0
+
+
 def test_traits_2048_envs():
-    for base, seed in ((METABOLIC_CONFIG, 21), (INVESTMENT_CONFIG, 22), (COOPERATION_CONFIG, 23)):
+    for base, seed in ((METABOLIC_CONFIG, 21), (INVESTMENT_CONFIG, 22), (COOPERATION_CONFIG, 23), (CADENCE_CONFIG, 24)):
         st = lockstep_parity(trait(base, cap_live=(64, 160), seed=seed), 2048, 80, state_envs=(0, 2047), check_every=4)
         assert st["status_envs"] == 0
 
 
-@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop")))
+@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop", "cad")))
 def test_trait_golden_trajectories_on_gpu(name):
     """Golden trajectories of the unmodified reference classes replayed on the GPU (one env, tape-driven: founder counts,
     cells, trait values, mutation draws, spawn-fallback cells all from the recording)."""
@@ -97,12 +124,19 @@ def test_trait_golden_trajectories_on_gpu(name):
     c = config_from_golden(cfg, autoreset=False)
     g = BatchedPredPreyGrass(c, 1)
     stay = (cfg["action_range"] ** 2) // 2
-    g.load_tape([np.concatenate([z["n_found"], z["init_cells"], z["fallback_cells"]])],
-                [np.concatenate([z["founder_trait"], z["step_reals"]])])
+    cad = cfg["variant"] == "cad"
+    if cad:  # fixed number of founders; per founder a speed and an accumulator phase; one recorded cell per birth
+        g.load_tape([np.concatenate([z["init_cells"], z["fallback_cells"]])],
+                    [np.concatenate([z["founder_trait"], z["founder_acc"], z["step_reals"]])])
+    else:
+        g.load_tape([np.concatenate([z["n_found"], z["init_cells"], z["fallback_cells"]])],
+                    [np.concatenate([z["founder_trait"], z["step_reals"]])])
     g.reset()
     out = g.outputs_numpy()
     rows = id_order_rows(out)
     assert [s for s, _ in rows] == list(z["reset_row_s"])
+    if cad:
+        assert [int(out[f"flags{s}"][r]) >> 7 for s, r in rows] == list(z["reset_frozen"])
     assert [int(out[f"row_agent{s}"][r]) for s, r in rows] == list(z["reset_row_id"])
     assert np.array_equal(sha_f32([out[f"obs{s}"][r] for s, r in rows]), z["reset_sha"])
     for t in range(len(z["steps"])):
@@ -137,6 +171,8 @@ def test_trait_golden_trajectories_on_gpu(name):
         fl = np.array([out[f"flags{s}"][r] for s, r in rows], np.uint8)
         assert np.array_equal(fl & 1, z["row_term"][r0:r1]), (name, t)
         assert np.array_equal((fl >> 1) & 1, z["row_trunc"][r0:r1]), (name, t)
+        if cad:
+            assert np.array_equal(fl >> 7, z["row_frozen"][r0:r1]), (name, t)
         assert np.array_equal(sha_f32([out[f"obs{s}"][r] for s, r in rows]), z["obs_sha"][t]), (name, t)
         assert bool(out["env_flags"][0] & 1) == bool(z["all_term"][t]), (name, t)
         assert bool(out["env_flags"][0] & 2) == bool(z["all_trunc"][t]), (name, t)
@@ -152,6 +188,8 @@ def test_trait_golden_trajectories_on_gpu(name):
             assert np.array_equal(st["energy"][s], z["st_e"][s0:s1][m]), (name, t, s, st["energy"][s] - z["st_e"][s0:s1][m])
             assert np.array_equal(st["age"][s], z["st_age"][s0:s1][m]), (name, t, s)
             assert np.array_equal(st["speed"][s], z["st_trait"][s0:s1][m]), (name, t, s)
+            if cad:
+                assert np.array_equal(g.read_env_acc(0)[s], z["st_acc"][s0:s1][m]), (name, t, s)
         assert np.array_equal(st["grass_energy"], z["grass_e"][t]), (name, t)
     assert int(out["env_status"][0]) & ~0x04 == 0  # only PPG_STATUS_TAPE_EXHAUSTED may be set (recordings cut before the end)
     g.close()

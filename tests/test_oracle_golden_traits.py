@@ -10,14 +10,18 @@ from oracle.oracle import Oracle
 from tests.helpers import config_from_golden, golden_cases, id_order_rows, load_golden, sha_f32
 
 
-@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop")))
+@pytest.mark.parametrize("name", golden_cases(("mr", "inv", "coop", "cad")))
 def test_trait_oracle_replays_reference(name):
     z, cfg = load_golden(name)
     c = config_from_golden(cfg, autoreset=False)
     o = Oracle(c, 1)
     o.load_tape([z["fallback_cells"]], [z["step_reals"]])
-    out = o.env_reset_trait(0, int(z["n_found"][0]), int(z["n_found"][1]), z["init_cells"], z["founder_trait"])
+    cad = cfg["variant"] == "cad"
+    out = o.env_reset_trait(0, int(z["n_found"][0]), int(z["n_found"][1]), z["init_cells"],
+                            np.concatenate([z["founder_trait"], z["founder_acc"]]) if cad else z["founder_trait"])
     rows = id_order_rows(out)
+    if cad:  # the action mask of the reset observations (CAD:746-753) as the PPG_ROW_FROZEN bit
+        assert [int(out[f"flags{s}"][r]) >> 7 for s, r in rows] == list(z["reset_frozen"])
     assert [s for s, _ in rows] == list(z["reset_row_s"])
     assert [int(out[f"row_agent{s}"][r]) for s, r in rows] == list(z["reset_row_id"])
     assert np.array_equal(sha_f32([out[f"obs{s}"][r] for s, r in rows]), z["reset_sha"])
@@ -35,6 +39,8 @@ def test_trait_oracle_replays_reference(name):
         fl = np.array([out[f"flags{s}"][r] for s, r in rows], np.uint8)
         assert np.array_equal(fl & 1, z["row_term"][r0:r1]), (name, t)
         assert np.array_equal((fl >> 1) & 1, z["row_trunc"][r0:r1]), (name, t)
+        if cad:
+            assert np.array_equal(fl >> 7, z["row_frozen"][r0:r1]), (name, t)
         if t in full:
             for s in range(2):
                 mine = [out[f"obs{s}"][r] for ss, r in rows if ss == s]
@@ -59,6 +65,8 @@ def test_trait_oracle_replays_reference(name):
             assert np.array_equal(st["energy"][s], z["st_e"][s0:s1][m]), (name, t, s, st["energy"][s] - z["st_e"][s0:s1][m])
             assert np.array_equal(st["age"][s], z["st_age"][s0:s1][m]), (name, t, s)
             assert np.array_equal(st["speed"][s], z["st_trait"][s0:s1][m]), (name, t, s)
+            if cad:
+                assert np.array_equal(o.read_env_acc(0)[s], z["st_acc"][s0:s1][m]), (name, t, s)
         assert np.array_equal(st["grass_energy"], z["grass_e"][t]), (name, t)
         assert np.array_equal(sha_f32([o.read_grid(0)]), z["grid_sha"][t]), (name, t)
         g0, g1 = z["ag_off"][t], z["ag_off"][t + 1]

@@ -3,6 +3,7 @@ the batched step and checked on BOTH sides (CPU oracle `-m "not gpu"`, CUDA path
   MR-T   = predpreygrass/evolutionary/eco_evolutionary_metabolic_rate/tests/test_eco_evolutionary_validation.py
   INV-T  = predpreygrass/evolutionary/eco_evolutionary_investment/tests/test_eco_evolutionary_validation.py
   COOP-T = predpreygrass/evolutionary/eco_evolutionary_cooperation/tests/test_eco_evolutionary_validation.py
+  CAD-T  = predpreygrass/evolutionary/eco_evolutionary_cadence/tests/test_eco_evolutionary_validation.py
 
 Same method as tests/test_eco_known_answers.py: the reference tests teleport agents and overwrite energies / genomes,
 then call one private method; here the same worlds are set up through the public inputs only (the replay tape gives
@@ -11,7 +12,8 @@ expected numbers are the reference tests' own formulas, plus the basal decay of 
 import numpy as np
 import pytest
 
-from predpreygrass_b200.config import COOPERATION_CONFIG, INVESTMENT_CONFIG, METABOLIC_CONFIG, VARIANT_ECO, make_config
+from predpreygrass_b200.config import (CADENCE_CONFIG, COOPERATION_CONFIG, INVESTMENT_CONFIG, METABOLIC_CONFIG, VARIANT_ECO,
+                                      make_config)
 from tests.test_eco_known_answers import BACKENDS, TERM, TRUNC, World
 
 STAY = 4            # (0, 0) of the 3x3 action table (MR:203-210)
@@ -50,8 +52,8 @@ class TraitWorld(World):
             from predpreygrass_b200.batched import BatchedPredPreyGrass
 
             self.g = BatchedPredPreyGrass(self.cfg, 1)
-            self.g.load_tape([np.concatenate([np.asarray(founders, np.int32), cells])],
-                             [np.concatenate([traits, np.asarray(reals, np.float64)])])
+            ints = cells if self.cfg.trait_mode == 4 else np.concatenate([np.asarray(founders, np.int32), cells])  # cadence: fixed founder count
+            self.g.load_tape([ints], [np.concatenate([traits, np.asarray(reals, np.float64)])])
             self.g.reset()
             self.out = self.g.outputs_numpy()
 
@@ -274,6 +276,104 @@ def test_prey_share_grass_with_prey_only(backend):
     w.step({(0, 0): STAY, (1, 0): STAY, (1, 1): STAY})
     st = w.state()
     assert st[(1, 0)]["energy"] == 3.0 + 1.0 and st[(1, 1)]["energy"] == 3.0 + 1.0 and st[(0, 0)]["energy"] == 3.0
+    w.close()
+
+
+# ------------------------------------------------------------------------------------------------ cadence
+def cad_world(backend, overrides, speeds, accs, cells=None, founders=(1, 1), reals=()):
+    """founder traits of a cadence world: the speeds, then the accumulator phases (CAD:1327)"""
+    cells = [cell(10, 10), cell(20, 20)] + FAR_GRASS if cells is None else cells
+    return TraitWorld(backend, CADENCE_CONFIG, dict(NO_BIRTHS, max_agent_age={"predator": None, "prey": None}, **overrides), founders, cells,
+                      list(speeds) + list(accs), reals=reals)
+
+
+def acc_of(w):
+    a = w.o.read_env_acc(0) if w.backend == "oracle" else w.g.read_env_acc(0)
+    return float(a[0][0]), float(a[1][0])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_slow_speed_is_frozen_when_accumulator_below_threshold(backend):
+    """CAD-T:404-420 — speed 0.0: move rate 1 / max_cooldown = 0.1; from an empty accumulator the agent stays, the accumulator
+    advances by the rate; the row of the next step carries the "stay only" action mask (0.1 + 0.1 < 1)"""
+    w = cad_world(backend, {}, [0.0, 0.5], [0.0, 0.0])
+    rows = w.step({PRED: MOVE_1_0, PREY: STAY})
+    assert w.state()[PRED]["xy"] == (10, 10)
+    assert acc_of(w)[0] == pytest.approx(0.1)
+    assert rows[PRED][2] & 0x80  # PPG_ROW_FROZEN
+    w.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_fast_speed_moves_every_step(backend):
+    """CAD-T:423-438 — speed 1.0: rate 1.0, the accumulator crosses 1.0 in one step: 0.0 + 1.0 - 1.0 = 0.0, never frozen"""
+    w = cad_world(backend, {}, [1.0, 0.5], [0.0, 0.0])
+    for t in range(3):
+        rows = w.step({PRED: MOVE_1_0, PREY: STAY})
+        assert w.state()[PRED]["xy"] == (11 + t, 10) and acc_of(w)[0] == 0.0
+        assert not rows[PRED][2] & 0x80
+    w.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_accumulator_lets_a_mid_speed_agent_move_on_schedule(backend):
+    """CAD:556-571,674-681 — speed 0.5, max_cooldown 5: rate 0.2 + 0.5 * 0.8 = 0.6; from 0.0 the accumulator reads 0.6 (frozen),
+    then 1.2 -> moves -> 0.2, then 0.8 (frozen), then 1.4 -> moves -> 0.4"""
+    w = cad_world(backend, dict(max_cooldown=5), [0.5, 0.5], [0.0, 0.0])
+    xs, accs = [], []
+    for _ in range(4):
+        w.step({PRED: MOVE_1_0, PREY: STAY})
+        xs.append(w.state()[PRED]["xy"][0]); accs.append(acc_of(w)[0])
+    assert xs == [10, 11, 11, 12]
+    rate = 1.0 / 5 + 0.5 * (1.0 - 1.0 / 5)
+    a, want = 0.0, []
+    for _ in range(4):
+        a = a + rate
+        a = a - 1.0 if a >= 1.0 else a
+        want.append(a)
+    assert accs == want
+    w.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("speed,action,cost", [(1.0, STAY, 0.0), (0.5, MOVE_1_0, 0.05 * 1.0 * (0.5 ** 2))])
+def test_cadence_costs(backend, speed, action, cost):
+    """CAD-T:441-468 stationary at speed 1.0: only the basal 0.2 * (1 + 1.0 * 1.0); CAD-T:471-500 one cell at speed 0.5:
+    basal 0.2 * (1 + 0.5) plus 0.05 * 1 * 0.5 ** 2 (the accumulator is pre-loaded to 1.0 so that the move executes)"""
+    ov = dict(energy_loss_per_step_predator=0.2, movement_energy_cost_per_cell_predator=0.05, movement_speed_cost_exponent=2.0,
+              metabolic_speed_coeff=1.0, initial_energy_predator=10.0)
+    w = cad_world(backend, ov, [speed, 0.5], [1.0, 0.0])
+    w.step({PRED: action, PREY: STAY})
+    assert w.state()[PRED]["energy"] == pytest.approx(10.0 - 0.2 * (1.0 + 1.0 * speed) - cost)
+    w.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_cadence_catch_radius_and_nearest_prey(backend):
+    """CAD:837-848 — the predator catches within Chebyshev distance 1: of a prey on a diagonal neighbour and one on its own
+    cell the nearer one; the prey is eaten whole (CAD:857), the other one lives on"""
+    ov = dict(energy_loss_per_step_predator=0.0, energy_loss_per_step_prey=0.0, metabolic_speed_coeff=0.0, initial_energy_predator=5.0,
+              initial_energy_prey=3.0)
+    cells = [cell(10, 10), cell(11, 11), cell(10, 10), cell(20, 20)] + FAR_GRASS
+    w = cad_world(backend, ov, [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], cells=cells, founders=(1, 3))
+    rows = w.step({PRED: STAY, (1, 0): STAY, (1, 1): STAY, (1, 2): STAY})
+    st = w.state()
+    assert (1, 1) not in st and rows[(1, 1)][2] & TERM      # the prey on the predator's cell (distance 0) goes first
+    assert (1, 0) in st and st[PRED]["energy"] == 5.0 + 3.0
+    rows = w.step({PRED: STAY, (1, 0): STAY, (1, 2): STAY})
+    st = w.state()
+    assert (1, 0) not in st and rows[(1, 0)][2] & TERM      # now the diagonal neighbour
+    assert st[PRED]["energy"] == 5.0 + 3.0 + 3.0 and (1, 2) in st
+    w.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_cadence_speed_plane_is_the_raw_genome_value(backend):
+    """CAD:746 — `spatial[n_ch] = float(genome.speed)`, not normalised by the trait bounds"""
+    w = cad_world(backend, dict(trait_bounds={"speed": (0.0, 2.0)}), [0.75, 0.25], [0.0, 0.0])
+    rows = w.rows()
+    assert rows[PRED][0].shape == (4, 7, 7) and np.all(rows[PRED][0][3] == np.float32(0.75))
+    assert np.all(rows[PREY][0][3] == np.float32(0.25))
     w.close()
 
 
