@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 7
+#define PPG_ABI_VERSION 8
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -204,6 +204,9 @@ typedef struct ppg_config {
   double trait_alpha;            /* "metabolic_rate_alpha" (MR:102,751,807): gain = food * rate ** alpha */
   double repro_max_ratio;        /* "predator_reproduction_max_ratio" (MR:60,843-854), < 0 = None */
   double metabolic_speed_coeff;  /* "metabolic_speed_coeff" (CAD:79,626-633): decay *= 1 + coeff * speed */
+  /* ---- ECO lineage survival rewards (ECO:943-984,1422-1470): every living agent is paid coeff * (change of its number of
+   * living descendants since the last step), on top of its other reward.  0 / 0 (the shipped config): off. ---- */
+  double lineage_reward_coeff[2]; /* "lineage_reward_coeff" per role (ECO:52) */
 } ppg_config;
 
 /* ppg_config.trait_mode: which heritable trait the ECO-family handle carries */

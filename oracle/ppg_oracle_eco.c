@@ -59,13 +59,22 @@ void eco_env_alloc(env_t* e) {
   e->max_row_elems = e->row_elems[0] > e->row_elems[1] ? e->row_elems[0] : e->row_elems[1];
   e->dead = (uint8_t*)calloc((size_t)c->n_possible[1], 1);
   e->sat_until = (int32_t*)calloc((size_t)c->n_possible[0], sizeof(int32_t));
-  for (int s = 0; s < 2; ++s) e->acc[s] = (double*)calloc((size_t)c->n_possible[s], sizeof(double));
+  for (int s = 0; s < 2; ++s) {
+    e->acc[s] = (double*)calloc((size_t)c->n_possible[s], sizeof(double));
+    e->lin_parent[s] = (int32_t*)calloc((size_t)c->n_possible[s], sizeof(int32_t));
+    e->lin_live[s] = (int32_t*)calloc((size_t)c->n_possible[s], sizeof(int32_t));
+    e->lin_prev[s] = (int32_t*)calloc((size_t)c->n_possible[s], sizeof(int32_t));
+    e->lin_alive[s] = (uint8_t*)calloc((size_t)c->n_possible[s], 1);
+  }
   e->n_found[0] = c->n_initial[0]; e->n_found[1] = c->n_initial[1];
   e->row_key = (int32_t*)malloc(sizeof(int32_t) * (size_t)(c->n_possible[0] + c->n_possible[1]));
 }
 
 void eco_env_free(env_t* e) {
-  for (int s = 0; s < 2; ++s) { free(e->age[s]); free(e->speed[s]); free(e->termd[s]); free(e->acc[s]); }
+  for (int s = 0; s < 2; ++s) {
+    free(e->age[s]); free(e->speed[s]); free(e->termd[s]); free(e->acc[s]);
+    free(e->lin_parent[s]); free(e->lin_live[s]); free(e->lin_prev[s]); free(e->lin_alive[s]);
+  }
   free(e->gridf); free(e->dead); free(e->row_key); free(e->sat_until);
 }
 
@@ -98,6 +107,22 @@ static void eco_get_observation(env_t* e, int s, int id, double* out) {
 }
 
 static double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); } /* np.clip */
+
+/* ---- lineage tracking (ECO:1422-1470); parents are of the child's own species ---- */
+#define LINEAGE_ON(c) ((c)->trait_mode == PPG_TRAIT_SPEED && ((c)->lineage_reward_coeff[0] != 0.0 || (c)->lineage_reward_coeff[1] != 0.0))
+/* _set_lineage_alive_flag + _propagate_lineage_delta: a change of the agent's own alive flag moves the live-descendant
+ * count of every ancestor, dead or alive (ECO:1440-1459) */
+static void lineage_set_alive(env_t* e, int s, int id, int alive) {
+  if (!LINEAGE_ON(e->c) || e->lin_alive[s][id] == (uint8_t)alive) return;
+  e->lin_alive[s][id] = (uint8_t)alive;
+  for (int a = e->lin_parent[s][id]; a >= 0; a = e->lin_parent[s][a]) e->lin_live[s][a] += alive ? 1 : -1;
+}
+/* _handle_lineage_birth (ECO:1461-1465) */
+static void lineage_birth(env_t* e, int s, int id, int parent) {
+  if (!LINEAGE_ON(e->c)) return;
+  e->lin_parent[s][id] = parent; e->lin_live[s][id] = 0; e->lin_prev[s][id] = 0; e->lin_alive[s][id] = 0;
+  lineage_set_alive(e, s, id, 1);
+}
 
 static uint32_t genv(const env_t* e) { return (uint32_t)(e->env_index + e->c->env_index_base); }
 
@@ -146,6 +171,7 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
       /* _get_initial_age (ECO:1060-1068): founder predators start at the carcass-only threshold */
       e->age[s][i] = (s == 0 && c->carcass_only_predator_age >= 0) ? c->carcass_only_predator_age : 0;
       e->speed[s][i] = c->genome_enabled ? founder_speed[k] : -1.0;
+      lineage_birth(e, s, i, -1); /* ECO:1525-1526 */
       /* CAD:1327: random phase of the move accumulator; after the founders' speeds in `founder_speed` */
       if (IS_CAD(c)) e->acc[s][i] = founder_speed[(c->genome_enabled ? nf[0] + nf[1] : 0) + k];
     }
@@ -336,6 +362,7 @@ static void capture_obs(env_t* e, int s, int id) { /* self.observations[agent] =
 static void terminate_due_to_age(env_t* e, int s, int id) {
   if (e->termd[s][id] || !e->present[s][id]) return;
   const int i = e->list_index[s][id];
+  lineage_set_alive(e, s, id, 0); /* ECO:1069 */
   if (s == 1) { e->dead[id] = 0; e->active[1] = e->active[1] - 1 > 0 ? e->active[1] - 1 : 0; }
   else e->active[0] = e->active[0] - 1 > 0 ? e->active[0] - 1 : 0;
   capture_obs(e, s, id);
@@ -348,6 +375,7 @@ static void terminate_due_to_age(env_t* e, int s, int id) {
 static void handle_starvation(env_t* e, int s, int id) {
   const int i = e->list_index[s][id];
   if (s == 1) e->dead[id] = 0;
+  lineage_set_alive(e, s, id, 0); /* ECO:770 */
   capture_obs(e, s, id);
   e->rew[i] = 0.0; e->has_rew[i] = 1;
   e->term[i] = 1; e->trunc[i] = 0; e->termd[s][id] = 1;
@@ -527,6 +555,7 @@ static void handle_predator_engagement(env_t* e, int id) {
   e->energy[0][id] += bite;
   *GF(e, 0, px, py) = (float)e->energy[0][id];
   const double rem = pe - bite;
+  if (!was_dead) lineage_set_alive(e, 1, caught, 0); /* the first bite is the prey's death for its lineage (ECO:840-841,848-849) */
   if (rem > 0.0) { /* carcass (ECO:826-845) */
     e->energy[1][caught] = rem;
     *GF(e, 1, e->x[1][caught], e->y[1][caught]) = (float)rem;
@@ -600,6 +629,7 @@ static void handle_reproduction(env_t* e, int s, int id) {
   }
   if (s == 0) e->sat_until[child] = 0;                 /* MR:1141 */
   e->acc[s][child] = acc0;
+  lineage_birth(e, s, child, id);                      /* ECO:1525-1526 (in _register_new_agent) */
   e->energy[s][child] = child_e;
   e->energy[s][id] -= child_e;                         /* ECO:1150 */
   *GF(e, s, sx, sy) = (float)child_e;                  /* ECO:1154 */
@@ -716,6 +746,19 @@ int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, c
         if (s == sp && e->energy[s][id] >= c->creation_threshold[s]) handle_reproduction(e, s, id);
       }
   }
+  /* Step 6.5: _apply_lineage_survival_rewards (ECO:369-370,943-984): every living agent (carcasses and newborns included)
+   * is paid coeff * (change of its live-descendant count since the last step) on top of what it already has */
+  if (LINEAGE_ON(c))
+    for (int i = 0; i < e->n_agents; ++i) {
+      const int s = KEY_S(e->agents[i]), id = KEY_ID(e->agents[i]);
+      const int li = e->list_index[s][id];
+      if (!e->has_rew[li]) { e->rew[li] = 0.0; e->has_rew[li] = 1; } /* rewards.setdefault(agent_id, 0.0) */
+      const int delta = e->lin_live[s][id] - e->lin_prev[s][id];
+      e->lin_prev[s][id] = e->lin_live[s][id];
+      if (delta == 0) continue;
+      const double reward = c->lineage_reward_coeff[s] * (double)delta;
+      if (reward != 0) e->rew[li] = e->rew[li] + reward; /* ECO:965-966 */
+    }
   /* Step 7: outputs (ECO:372-424) */
   const int episode_done = e->active[1] <= 0 || e->active[0] <= 0; /* ECO:392 */
   for (int i = 0; i < e->n_rows; ++i) {

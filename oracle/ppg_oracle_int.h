@@ -82,6 +82,11 @@ typedef struct env_t {
   int n_found[2];     /* founders of the running episode (MR:189-192) */
   int32_t* sat_until; /* agent_satiation_until by predator id (MR:134,756-757) */
   double* acc[2];     /* CAD: agent_move_accumulator by id (CAD:183-186) */
+  /* ECO lineage_tracker by id (ECO:1422-1470): parent (-1: founder), live_descendants, prev_live_descendants, is_alive_descendant */
+  int32_t* lin_parent[2];
+  int32_t* lin_live[2];
+  int32_t* lin_prev[2];
+  uint8_t* lin_alive[2];
   /* ---- STAG (ppg_oracle_stag.c) ---- */
   int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
   double* trait;      /* predator_cooperation_trait (STAG:230) */

@@ -120,6 +120,7 @@ class PpgConfig(C.Structure):
         ("trait_alpha", C.c_double),
         ("repro_max_ratio", C.c_double),
         ("metabolic_speed_coeff", C.c_double),
+        ("lineage_reward_coeff", C.c_double * 2),
     ]
 
 
@@ -300,9 +301,9 @@ def _fill_eco(c, cfg):
     c.penalty_prey_caught = 0.0
     c.reproduction_reward[0] = float(_role(cfg["reproduction_reward_predator"], "predator", 0.0))
     c.reproduction_reward[1] = float(_role(cfg["reproduction_reward_prey"], "prey", 0.0))
-    lin = cfg.get("lineage_reward_coeff", 0.0)
-    if any(float(_role(lin, r, 0.0) or 0.0) != 0.0 for r in ("predator", "prey")):
-        raise ValueError("lineage_reward_coeff != 0 is not supported (ECO:943-991 lineage survival rewards)")
+    lin = cfg["lineage_reward_coeff"]  # ECO:52 (mandatory key)
+    for s, role in enumerate(("predator", "prey")):
+        c.lineage_reward_coeff[s] = float(_role(lin, role, 0.0) or 0.0)  # `_get_role_specific` (ECO:1723-1731)
 
 
 def _fill_cadence(c, cfg):

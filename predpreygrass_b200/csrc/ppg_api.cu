@@ -30,7 +30,7 @@ cudaError_t launch_obs(const StepParams& p, int n_cta, bool overlap, cudaStream_
 cudaError_t obs_occupancy(const StepParams& p, int* blocks_per_sm);
 // ppg_eco.cu
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream);
-cudaError_t step_eco_occupancy(int map_bytes, bool split, bool traits, size_t smem, int* blocks_per_sm);
+cudaError_t step_eco_occupancy(int map_bytes, bool split, int kind, size_t smem, int* blocks_per_sm);
 cudaError_t launch_set_tape_reals(EcoHdr* ehdr, int B, const long long* real_off, cudaStream_t s);
 cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s);
 // ppg_stag.cu
@@ -195,6 +195,8 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
     if (c->slow_max_move_distance < 0 || c->fast_max_move_distance < 0) { err = "max move distance negative"; return PPG_ERR_INVALID; }
     if (!(c->speed_bounds[1] > c->speed_bounds[0])) { err = "speed bounds"; return PPG_ERR_INVALID; }
     if (c->trait_mode < PPG_TRAIT_SPEED || c->trait_mode > PPG_TRAIT_CADENCE) { err = "trait_mode out of range"; return PPG_ERR_INVALID; }
+    if (c->trait_mode != PPG_TRAIT_SPEED && (c->lineage_reward_coeff[0] != 0.0 || c->lineage_reward_coeff[1] != 0.0)) { err = "lineage rewards belong to eco_evolutionary (trait_mode speed)"; return PPG_ERR_INVALID; }
+    if ((c->lineage_reward_coeff[0] != 0.0 || c->lineage_reward_coeff[1] != 0.0) && (c->cap_live[0] > 32767 || c->n_possible[0] > 65534 || c->n_possible[1] > 65534)) { err = "lineage rewards: n_possible must be <= 65534"; return PPG_ERR_INVALID; }
     if (c->trait_mode == PPG_TRAIT_CADENCE) {
       if (c->max_cooldown < 1) { err = "max_cooldown must be >= 1"; return PPG_ERR_INVALID; }
       if (c->carcass_only_predator_age >= 0) { err = "cadence has no carcass-only predators"; return PPG_ERR_INVALID; }
@@ -263,6 +265,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     P.trait_mode = c.trait_mode; P.n_init_min[0] = c.n_initial_min[0]; P.n_init_min[1] = c.n_initial_min[1];
     P.sat_cd = c.satiation_cooldown; P.coop_range = c.cooperation_range; P.trait_alpha = c.trait_alpha; P.repro_ratio = c.repro_max_ratio;
     P.max_cooldown = c.max_cooldown; P.meta_coeff = c.metabolic_speed_coeff;
+    P.lin_coeff[0] = c.lineage_reward_coeff[0]; P.lin_coeff[1] = c.lineage_reward_coeff[1];
+    P.lin_on = c.trait_mode == PPG_TRAIT_SPEED && (P.lin_coeff[0] != 0.0 || P.lin_coeff[1] != 0.0);
   } else if (stag) {
     P.action_range = std::max(c.type_action_range[0], c.type_action_range[1]); P.n_actions = P.action_range * P.action_range;
     for (int s = 0; s < 2; ++s)
@@ -450,7 +454,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   {
     // persistent warps: as many CTAs as fit on the device, never more than there are envs
     int per_sm = 0, n_sm = 0;
-    if (eco) CKC(step_eco_occupancy(P.map_bytes, P.obs_split != 0, P.trait_mode != PPG_TRAIT_SPEED, h->smem_bytes, &per_sm));
+    if (eco) CKC(step_eco_occupancy(P.map_bytes, P.obs_split != 0, P.trait_mode != PPG_TRAIT_SPEED ? 1 : (P.lin_on ? 2 : 0), h->smem_bytes, &per_sm));
     else if (stag) CKC(step_stag_occupancy(P.map_bytes, P.obs_split != 0, h->smem_bytes, &per_sm));
     else CKC(step_base_occupancy(W, P.map_bytes, P.obs_bulk != 0, P.obs_split != 0, h->smem_bytes, &per_sm));
     CKC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -468,6 +472,10 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     if (eco) {
       CKC(dalloc(h, &P.ag_age[s], n)); CKC(dalloc(h, &P.ag_seq[s], n)); CKC(dalloc(h, &P.ag_spd[s], n)); CKC(dalloc(h, &P.ag_dead[s], n));
       if (P.trait_mode == PPG_TRAIT_CADENCE) CKC(dalloc(h, &P.ag_acc[s], n));
+      if (P.lin_on) {
+        const size_t m = (size_t)B * P.n_possible[s];
+        CKC(dalloc(h, &P.lin_parent[s], m)); CKC(dalloc(h, &P.lin_live[s], m)); CKC(dalloc(h, &P.lin_prev[s], m)); CKC(dalloc(h, &P.lin_alive[s], m));
+      }
     }
     if (stag) {
       CKC(dalloc(h, &P.ag_age[s], n));
@@ -811,6 +819,10 @@ static std::vector<Seg> state_segments(ppg_handle h) {
     if (P.variant == PPG_VARIANT_ECO) {
       v.push_back({P.ag_age[s], n * 2}); v.push_back({P.ag_seq[s], n * 2}); v.push_back({P.ag_spd[s], n * 8}); v.push_back({P.ag_dead[s], n});
       if (P.trait_mode == PPG_TRAIT_CADENCE) v.push_back({P.ag_acc[s], n * 8});
+      if (P.lin_on) {
+        const size_t m = (size_t)h->B * P.n_possible[s];
+        v.push_back({P.lin_parent[s], m * 2}); v.push_back({P.lin_live[s], m * 2}); v.push_back({P.lin_prev[s], m * 2}); v.push_back({P.lin_alive[s], m});
+      }
     }
     if (P.variant == PPG_VARIANT_STAG) {
       v.push_back({P.ag_age[s], n * 2});

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
       publish_counts(p, env, par, epoch, next_live, births, n_blk, n_grp, n_old_total, lane);
     }
 
-    if (mode == 1) {  // PHASE: reset
+    if (PPG_UNLIKELY(mode == 1)) {  // PHASE: reset
       // ------------------------------------------------------------------ reset() (BASE:129-217)
       h.episode += 1;
       h.step = 0;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
         const size_t b = (size_t)env * p.cap[s];
         const int32_t* ordp = p.order[s];
         bool use_order = ordp != nullptr;
-        if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to row order
+        if (PPG_UNLIKELY(use_order)) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to row order
           bool ok = true;
           #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
           }
         }
       }
+      __syncwarp();  // every lane's candidate reads of the marks are done
       #pragma unroll 1
       for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 0;
       __syncwarp();
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
                 if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
               }
             }
-            if (sx < 0) {
+            if (PPG_UNLIKELY(sx < 0)) {
               st_fallback++;
               if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
                 const int c = p.tape_cells[h.tape_pos++];  // recorded np.random.randint choice (BASE:764)

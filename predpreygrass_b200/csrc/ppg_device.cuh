@@ -175,6 +175,14 @@ struct StepParams {
   // gain exponent, density cap (< 0: none)
   int trait_mode, n_init_min[2], sat_cd, coop_range;
   double trait_alpha, repro_ratio;
+  // ECO lineage survival rewards (ECO:943-984,1422-1470), by agent id: parent id (0xFFFF: founder), live descendants,
+  // their count at the previous step, own alive flag; lin_on = any coefficient non-zero
+  int lin_on;
+  double lin_coeff[2];
+  uint16_t* lin_parent[2];  // [B][n_possible[s]]
+  int16_t* lin_live[2];
+  int16_t* lin_prev[2];
+  uint8_t* lin_alive[2];
   // cadence variant: move accumulators (CAD:183-186), slowest cadence, speed-dependent basal cost
   int max_cooldown, so_acc[2];
   double meta_coeff;

@@ -96,6 +96,23 @@ __device__ __forceinline__ void draw_next_founders(const StepParams& p, EnvHdr& 
   h.pad[1] = (int)((unsigned)h.pad[1] | 0x80000000u);
 }
 
+// ---- lineage tracking (ECO:1422-1470), global arrays indexed by agent id; called by lane 0 only ----
+// _set_lineage_alive_flag + _propagate_lineage_delta: a change of the agent's own alive flag moves the live-descendant
+// count of every ancestor, dead or alive
+static __device__ __noinline__ void lineage_set_alive(const StepParams& p, int env, int s, int id, int alive) {
+  const size_t b = (size_t)env * p.n_possible[s];
+  if (p.lin_alive[s][b + id] == (uint8_t)alive) return;
+  p.lin_alive[s][b + id] = (uint8_t)alive;
+  for (unsigned a = p.lin_parent[s][b + id]; a != 0xFFFFu; a = p.lin_parent[s][b + a])
+    p.lin_live[s][b + a] = (int16_t)(p.lin_live[s][b + a] + (alive ? 1 : -1));
+}
+// _handle_lineage_birth (ECO:1461-1465)
+static __device__ __noinline__ void lineage_birth(const StepParams& p, int env, int s, int id, unsigned parent) {
+  const size_t b = (size_t)env * p.n_possible[s];
+  p.lin_parent[s][b + id] = (uint16_t)parent; p.lin_live[s][b + id] = 0; p.lin_prev[s][b + id] = 0; p.lin_alive[s][b + id] = 0;
+  lineage_set_alive(p, env, s, id, 1);
+}
+
 // one tape-or-Philox real draw (uniform lanes)
 __device__ __forceinline__ bool take_real(const StepParams& p, EcoHdr& eh, EnvHdr& h, double& out) {
   if (p.tape_reals != nullptr) {
@@ -171,8 +188,11 @@ __device__ __noinline__ double coop_donation(unsigned char* sbase, const StepPar
 // TRAITS: false = eco_evolutionary itself (heritable speed), true = its sibling trait variants (p.trait_mode).  Two kernels,
 // because the step kernels are bound by instruction delivery: the speed kernel carries none of the variants'
 // code and the variants' kernel none of the speed / carcass / ageing code.
-template <int W, typename MapT, bool SPLIT, bool TRAITS>
+// KIND 2 = eco_evolutionary with lineage survival rewards (lineage_reward_coeff != 0; the shipped config has 0): a third
+// kernel for the same reason.
+template <int W, typename MapT, bool SPLIT, int KIND>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __grid_constant__ StepParams p) {
+  constexpr bool TRAITS = KIND == 1, LIN = KIND == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     }
     const unsigned genv = (unsigned)(env + p.env_base);
 
-    if (mode == 1) {
+    if (PPG_UNLIKELY(mode == 1)) {
       // ------------------------------------------------------------------ reset() (ECO:274-293,123-223,1733-1792)
       h.episode += 1;
       h.step = 0;
@@ -379,6 +399,16 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       }
       __syncwarp();
       eh.active[0] = nf[0]; eh.active[1] = nf[1];  // ECO:281-282
+      if (LIN) {  // lineage_tracker = {} and one entry per founder: no parent, alive (ECO:171,1525-1526)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const size_t b = (size_t)env * p.n_possible[s];
+          #pragma unroll 1
+          for (int i = lane; i < p.n_possible[s]; i += 32) {
+            p.lin_parent[s][b + i] = 0xFFFFu; p.lin_live[s][b + i] = 0; p.lin_prev[s][b + i] = 0; p.lin_alive[s][b + i] = i < nf[s] ? 1 : 0;
+          }
+        }
+      }
       eh.next_seq = (unsigned)n_f;
       next_live[0] = n[0]; next_live[1] = n[1];
       env_flags = PPG_ENV_RESET;
@@ -410,7 +440,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         const size_t b = (size_t)env * p.cap[s];
         const int32_t* ordp = p.order[s];
         bool use_order = ordp != nullptr;
-        if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
+        if (PPG_UNLIKELY(use_order)) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
           bool ok = true;
           #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {
@@ -485,7 +515,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       __syncwarp();
       // ghost cells: the stale value is still on the grid unless a prey standing there has just re-written it (ECO:597)
       n_gh = n_gh_r;
-      if (n_gh) {
+      if (PPG_UNLIKELY(n_gh)) {
         if (lane < n_gh) {
           const int gs = p.cap[1] - 1 - lane;
           const unsigned gp = p.gh_cell[(size_t)env * PPG_MAX_GHOSTS + lane];
@@ -501,7 +531,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       }
 
       // age-outs (ECO:602-616,1060-1090), in self.agents order; the grass channel still shows last step's energies
-      if (__any_sync(FULL, aged_any)) {
+      if (PPG_UNLIKELY(__any_sync(FULL, aged_any))) {
         long long last = -1;
         for (;;) {
           const unsigned key = next_in_seq_order(X.seq, n, last, lane, [&](int s, int i) {
@@ -516,6 +546,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           if (lane == 0) {
             SEL(S.map)[cell] = 0;
             SEL(S.flg)[slot] = F_DIED;
+            if (LIN) lineage_set_alive(p, env, s, SEL(S.id)[slot], 0);  // ECO:1069
           }
           if (s == 0) eh.active[0] = max(eh.active[0] - 1, 0); else eh.active[1] = max(eh.active[1] - 1, 0);
           __syncwarp();
@@ -638,6 +669,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (lane == 0) {
               SEL(S.map)[cell] = 0;
               SEL(S.flg)[slot] = F_DIED;  // also drops F_CARC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
+              if (LIN) lineage_set_alive(p, env, s, SEL(S.id)[slot], 0);  // ECO:770
             }
             if (s == 0) { eh.active[0] -= 1; st_starved[0]++; } else { eh.active[1] -= 1; st_starved[1]++; }
             __syncwarp();
@@ -785,6 +817,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             }
             __syncwarp();
             if (lane == 0) {
+              if (LIN && !was_dead) lineage_set_alive(p, env, 1, S.id[1][q], 0);  // the first bite is the prey's death for its lineage (ECO:840-841,848-849)
               S.E[0][slot] = en;
               S.map[0][cell] = (MapT)(slot + 1);  // ECO:817
               S.flg[0][slot] |= F_ATE;
@@ -813,6 +846,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             }
           }
         }
+        __syncwarp();  // every lane's candidate reads of the marks are done (racecheck: read / write on `scr`)
         #pragma unroll 1
         for (int i = lane; i < n[1]; i += 32) S.scr[CELLP((unsigned)S.pos[1][i])] = 0;
         __syncwarp();
@@ -882,7 +916,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                 sy = k == 0 ? vy[0] : (k == 1 ? vy[1] : (k == 2 ? vy[2] : vy[3]));
               }
             }
-            if (sx < 0) {
+            if (PPG_UNLIKELY(sx < 0)) {
               st_fallback++;
               if (p.tape_cells != nullptr && h.tape_pos < h.tape_end) {
                 const int c = p.tape_cells[h.tape_pos++];
@@ -914,6 +948,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               SEL(X.seq)[cs] = (uint16_t)eh.next_seq;
               SEL(X.spd)[cs] = p.genome_enabled ? spd : -1.0;
               if (tm == PPG_TRAIT_CADENCE) SEL(X.acc)[cs] = acc0;
+              if (LIN) lineage_birth(p, env, s, child_id, SEL(S.id)[ps_slot]);  // ECO:1525-1526
               SEL(S.E)[ps_slot] = pe;
               SEL(S.map)[CELLXY(sx, sy)] = (MapT)(cs + 1);       // ECO:1154
               SEL(S.map)[CELLXY(px, py)] = (MapT)(ps_slot + 1);  // ECO:1155
@@ -1028,6 +1063,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                 else {
                   rew = s == 0 ? ((f & F_ATE) ? p.r_catch : p.r_pstep) : ((f & F_ATE) ? p.r_eat : p.r_qstep);
                   if (f & F_REPRO) rew = p.r_repro[s];  // ECO:1161 overwrites
+                  if (LIN) {  // Step 6.5 (ECO:943-984): coeff * change of the live-descendant count, for the living
+                    const size_t li = (size_t)env * p.n_possible[s] + SEL(S.id)[slot];
+                    const int cur_d = __ldcg(p.lin_live[s] + li), delta = cur_d - __ldcg(p.lin_prev[s] + li);  // written by lane 0 earlier in this step: read at L2
+                    if (delta != 0) { p.lin_prev[s][li] = (int16_t)cur_d; rew = rew + p.lin_coeff[s] * (double)delta; }
+                  }
                 }
               }
               unsigned rf = 0;
@@ -1228,41 +1268,43 @@ __global__ void ppg_set_tape_reals_kernel(EcoHdr* ehdr, int B, const long long* 
   ehdr[e].real_end = real_off ? real_off[e + 1] : 0;
 }
 
-template <typename MapT, bool SPLIT, bool TRAITS>
+template <typename MapT, bool SPLIT, int KIND>
 static cudaError_t launch_eco_t(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS><<<n_cta, 32, smem, stream>>>(p);
+  ppg_step_eco_kernel<1, MapT, SPLIT, KIND><<<n_cta, 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <bool TRAITS>
+template <int KIND>
 static cudaError_t launch_eco_v(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true, TRAITS>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true, TRAITS>(p, n_cta, smem, stream);
-  return p.map_bytes == 1 ? launch_eco_t<uint8_t, false, TRAITS>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false, TRAITS>(p, n_cta, smem, stream);
+  if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true, KIND>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true, KIND>(p, n_cta, smem, stream);
+  return p.map_bytes == 1 ? launch_eco_t<uint8_t, false, KIND>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false, KIND>(p, n_cta, smem, stream);
 }
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
-  return p.trait_mode != PPG_TRAIT_SPEED ? launch_eco_v<true>(p, n_cta, smem, stream) : launch_eco_v<false>(p, n_cta, smem, stream);
+  if (p.trait_mode != PPG_TRAIT_SPEED) return launch_eco_v<1>(p, n_cta, smem, stream);
+  return p.lin_on ? launch_eco_v<2>(p, n_cta, smem, stream) : launch_eco_v<0>(p, n_cta, smem, stream);
 }
 
-template <typename MapT, bool SPLIT, bool TRAITS>
+template <typename MapT, bool SPLIT, int KIND>
 static cudaError_t occupancy_eco_t(size_t smem, int* blocks_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ppg_step_eco_kernel<1, MapT, SPLIT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, MapT, SPLIT, TRAITS>, 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ppg_step_eco_kernel<1, MapT, SPLIT, KIND>, 32, smem);
 }
 
-template <bool TRAITS>
+template <int KIND>
 static cudaError_t occupancy_eco_v(int map_bytes, bool split, size_t smem, int* blocks_per_sm) {
-  if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true, TRAITS>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true, TRAITS>(smem, blocks_per_sm);
-  return map_bytes == 1 ? occupancy_eco_t<uint8_t, false, TRAITS>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false, TRAITS>(smem, blocks_per_sm);
+  if (split) return map_bytes == 1 ? occupancy_eco_t<uint8_t, true, KIND>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, true, KIND>(smem, blocks_per_sm);
+  return map_bytes == 1 ? occupancy_eco_t<uint8_t, false, KIND>(smem, blocks_per_sm) : occupancy_eco_t<uint16_t, false, KIND>(smem, blocks_per_sm);
 }
-cudaError_t step_eco_occupancy(int map_bytes, bool split, bool traits, size_t smem, int* blocks_per_sm) {
-  return traits ? occupancy_eco_v<true>(map_bytes, split, smem, blocks_per_sm) : occupancy_eco_v<false>(map_bytes, split, smem, blocks_per_sm);
+cudaError_t step_eco_occupancy(int map_bytes, bool split, int kind, size_t smem, int* blocks_per_sm) {
+  if (kind == 1) return occupancy_eco_v<1>(map_bytes, split, smem, blocks_per_sm);
+  return kind == 2 ? occupancy_eco_v<2>(map_bytes, split, smem, blocks_per_sm) : occupancy_eco_v<0>(map_bytes, split, smem, blocks_per_sm);
 }
 
 cudaError_t launch_eco_founders(const StepParams& p, cudaStream_t s) {

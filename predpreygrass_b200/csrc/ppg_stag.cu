@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
     }
     const unsigned genv = (unsigned)(env + p.env_base);
 
-    if (mode == 1) {
+    if (PPG_UNLIKELY(mode == 1)) {
       // ------------------------------------------------------------------ reset() (STAG:414-430,268-412,2095-2193)
       h.episode += 1;
       h.step = 0;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         const size_t b = (size_t)env * p.cap[s];
         const int32_t* ordp = p.order[s];
         bool use_order = ordp != nullptr;
-        if (use_order) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
+        if (PPG_UNLIKELY(use_order)) {  // must be a permutation of [0, n) (ppg_step_ordered); else fall back to list order
           bool ok = true;
           #pragma unroll 1
           for (int i = lane; i < SEL(n); i += 32) {

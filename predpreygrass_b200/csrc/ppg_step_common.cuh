@@ -10,6 +10,9 @@
 namespace ppg {
 
 #define FULL 0xffffffffu
+// rarely taken branches (reset, replay tapes, explicit action order, fall-backs): kept out of the fall-through path, the step
+// kernels are bound by instruction delivery
+#define PPG_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 // experiment switches of the env loop (defaults = what is shipped and measured)
 #ifndef PPG_TICKET_EARLY

@@ -64,6 +64,11 @@ CASES = [
                                                          "prey": {"speed_mean": 1.2, "speed_std": 0.5}}), 7, "id", 250),
     # other window shapes (generic row writer on the device), odd grid, 3x3 and 7x7 action tables, other speed bounds /
     # threshold / jump distances (ECO:551-557,664-683)
+    # lineage survival rewards (ECO:943-984): non-zero coefficients; births, deaths, carcasses, age-outs all move the counts
+    ("eco_lineage_s1", dict(RICH, lineage_reward_coeff={"predator": 0.5, "prey": 0.25}), 1, "id", 160),
+    ("eco_lineage_s2_shuffle", dict(CROWDED, grid_size=10, lineage_reward_coeff={"predator": 1.0, "prey": -0.125}, max_energy_gain_per_prey=0.8,
+                                    genome_mutation={"rate": 0.5, "std": 0.4}), 2, "shuffle", 200),
+    ("eco_lineage_age_s3", dict(CROWDED, grid_size=10, max_agent_age={"predator": 25, "prey": 12}, lineage_reward_coeff=0.75), 3, "id", 200),
     ("eco_narrow_s8", dict(RICH, grid_size=13, predator_obs_range=3, prey_obs_range=5, action_range=3, initial_num_grass=40), 8, "shuffle", 160),
     ("eco_jumps_s9", dict(RICH, grid_size=17, predator_obs_range=9, prey_obs_range=7, action_range=7, initial_num_grass=60,
                           trait_bounds={"speed": (0.25, 3.0)}, speed_distance_threshold=1.2, slow_max_move_distance=2,

@@ -13,9 +13,10 @@ def test_stag_walls_and_line_of_sight_are_rejected():
     assert make_config(STAG_CONFIG, variant=VARIANT_STAG).grid_size == 30  # the BASELINE config itself is fine
 
 
-def test_eco_lineage_rewards_are_rejected():
-    with pytest.raises(ValueError):
-        make_config(dict(ECO_CONFIG, lineage_reward_coeff={"predator": 0.5, "prey": 0.0}), variant=VARIANT_ECO)
+def test_eco_lineage_coefficients_are_read_per_role():
+    c = make_config(dict(ECO_CONFIG, lineage_reward_coeff={"predator": 0.5, "prey": 0.0}), variant=VARIANT_ECO)
+    assert list(c.lineage_reward_coeff) == [0.5, 0.0]
+    assert list(make_config(dict(ECO_CONFIG, lineage_reward_coeff=0.25), variant=VARIANT_ECO).lineage_reward_coeff) == [0.25, 0.25]
     assert make_config(ECO_CONFIG, variant=VARIANT_ECO).action_range == 5
 
 

@@ -76,6 +76,17 @@ def test_eco_ghost_cells():
     assert st["eaten_prey"] > 0  # (status words are compared env by env inside lockstep_parity: a ghost overflow would differ)
 
 
+def test_eco_lineage_survival_rewards():
+    """non-zero lineage_reward_coeff (ECO:943-984): ancestors are paid for births and charged for deaths of their descendants
+    (carcass bites and age-outs included); the per-id lineage tables live in HBM"""
+    cfg = dict(CROWDED, grid_size=10, lineage_reward_coeff={"predator": 0.5, "prey": -0.25}, max_agent_age={"predator": 25, "prey": 12},
+               max_energy_gain_per_prey=0.8)
+    st = lockstep_parity(eco(cfg, cap_live=(96, 192), seed=23), 256, 120, state_envs=(0, 255))
+    assert st["births_prey"] > 1000 and st["eaten_prey"] > 0
+    st = lockstep_parity(eco(dict(RICH, lineage_reward_coeff=0.75), cap_live=(128, 320), seed=29), 128, 150, state_envs=(0, 127))
+    assert st["births_prey"] > 1000
+
+
 def test_eco_4096_envs():
     st = lockstep_parity(eco(ECO_CONFIG, cap_live=(64, 128), seed=21), 4096, 80, state_envs=(0, 4095), check_every=4)
     assert st["status_envs"] == 0
