@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 8
+#define PPG_ABI_VERSION 9
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -207,6 +207,17 @@ typedef struct ppg_config {
   /* ---- ECO lineage survival rewards (ECO:943-984,1422-1470): every living agent is paid coeff * (change of its number of
    * living descendants since the last step), on top of its other reward.  0 / 0 (the shipped config): off. ---- */
   double lineage_reward_coeff[2]; /* "lineage_reward_coeff" per role (ECO:52) */
+  /* ---- STAG walls and line of sight (STAG:112-124,172-175,860-925,977-994,1026-1037,2107-2160).  Walls are static cells of
+   * channel 0: nobody moves or is born onto them and the reset placement avoids them.  respect_los_for_movement: a move
+   * that is neither blocked by a wall nor by an occupied cell is cancelled if it cuts a wall corner diagonally or if a wall
+   * lies strictly between its end points (integer Bresenham, STAG:892-925).  include_visibility_channel appends one
+   * observation channel holding the reference's line-of-sight mask — all ones: the reference computes its masks once in
+   * __init__, before any wall exists (STAG:408-412), which also makes mask_observation_with_visibility a no-op. ---- */
+  const int32_t* wall_cells;            /* [n_walls] cells x * grid_size + y ("manual_wall_positions", in bounds, distinct); copied by ppg_create */
+  int32_t n_walls;
+  int32_t respect_los_for_movement;     /* STAG:123 */
+  int32_t include_visibility_channel;   /* STAG:122 */
+  int32_t reserved3;
 } ppg_config;
 
 /* ppg_config.trait_mode: which heritable trait the ECO-family handle carries */

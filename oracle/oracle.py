@@ -103,7 +103,8 @@ class Oracle:
         if not self.h:
             raise ValueError("ppgo_create rejected the config")
         lib().ppgo_set_threads(self.h, threads)
-        self.C = cfg.num_obs_channels + (1 if cfg.variant == 1 and cfg.include_speed_in_obs else 0)
+        self.C = (cfg.num_obs_channels + (1 if cfg.variant == 1 and cfg.include_speed_in_obs else 0)
+                  + (1 if cfg.variant == 2 and cfg.include_visibility_channel else 0))
         self.grid_C = cfg.num_obs_channels
         self.R = (cfg.obs_range[0], cfg.obs_range[1])
         self._keep = None

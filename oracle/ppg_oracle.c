@@ -529,6 +529,11 @@ ppgo_batch* ppgo_create(const ppg_config* cfg, int32_t n_envs) {
   if (cfg->n_initial[0] + cfg->n_initial[1] + cfg->n_grass > cfg->grid_size * cfg->grid_size) return NULL; /* BASE:167 */
   ppgo_batch* b = (ppgo_batch*)calloc(1, sizeof *b);
   b->cfg = *cfg;
+  if (cfg->n_walls > 0 && cfg->wall_cells) { /* the caller's wall list is copied (include/ppg.h) */
+    int32_t* w = (int32_t*)malloc(sizeof(int32_t) * (size_t)cfg->n_walls);
+    memcpy(w, cfg->wall_cells, sizeof(int32_t) * (size_t)cfg->n_walls);
+    b->cfg.wall_cells = w;
+  } else { b->cfg.wall_cells = NULL; b->cfg.n_walls = 0; }
   b->n_envs = n_envs;
   b->n_threads = 1;
   for (int s = 0; s < 2; ++s) b->lexrank[s] = build_lexrank(cfg->n_possible[s]);
@@ -573,6 +578,7 @@ void ppgo_destroy(ppgo_batch* b) {
   }
   free(b->out.f.env_flags); free(b->out.f.env_status); free(b->out.f.env_step); free(b->out.f.env_count);
   free(b->tape_cells); free(b->tape_off); free(b->tape_reals); free(b->tape_real_off);
+  free((void*)b->cfg.wall_cells);
   free(b);
 }
 

@@ -44,7 +44,9 @@
 
 static inline float* GF(env_t* e, int ch, int x, int y) { return &e->gridf[((size_t)ch * e->G + x) * e->G + y]; }
 static inline int clipi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-static inline int n_row_channels(const ppg_config* c) { return c->num_obs_channels + (c->include_speed_in_obs ? 1 : 0); }
+static inline int n_row_channels(const ppg_config* c) { /* + ECO's own-speed plane (ECO:1396-1406) / STAG's visibility channel (STAG:1788) */
+  return c->num_obs_channels + (c->include_speed_in_obs ? 1 : 0) + ((c->variant == PPG_VARIANT_STAG && c->include_visibility_channel) ? 1 : 0);
+}
 
 void eco_env_alloc(env_t* e) {
   const ppg_config* c = e->c;

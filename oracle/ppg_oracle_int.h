@@ -88,6 +88,7 @@ typedef struct env_t {
   int32_t* lin_prev[2];
   uint8_t* lin_alive[2];
   /* ---- STAG (ppg_oracle_stag.c) ---- */
+  uint8_t* wallmap;   /* [G*G] 1 at wall cells (STAG:2107-2127) */
   int8_t* facing;     /* predator_facing as an index into _predator_facing_options (STAG:197-206) */
   double* trait;      /* predator_cooperation_trait (STAG:230) */
   uint8_t* join;      /* predator_join_intent of the running step: 0 / 1, 2 = no entry (defaults to True, STAG:1163) */

@@ -38,11 +38,13 @@ void stag_env_alloc(env_t* e) {
   e->facing = (int8_t*)calloc((size_t)c->n_possible[0] + 1, 1);
   e->trait = (double*)calloc((size_t)c->n_possible[0] + 1, sizeof(double));
   e->join = (uint8_t*)calloc((size_t)c->n_possible[0] + 1, 1);
+  e->wallmap = (uint8_t*)calloc((size_t)e->G * e->G, 1); /* _create_wall_positions (STAG:2107-2127): static per config */
+  for (int k = 0; k < c->n_walls; ++k) e->wallmap[c->wall_cells[k]] = 1;
 }
 
 void stag_env_free(env_t* e) {
   eco_env_free(e);
-  free(e->facing); free(e->trait); free(e->join);
+  free(e->facing); free(e->trait); free(e->join); free(e->wallmap);
 }
 
 /* _predator_facing_options (STAG:197-206) */
@@ -67,6 +69,38 @@ static void stag_get_observation(env_t* e, int s, int id, double* out) {
   for (int ch = 0; ch < CG; ++ch)
     for (int i = xolo; i <= xohi; ++i)
       for (int j = yolo; j <= yohi; ++j) out[(ch * R + i) * R + j] = (double)*GF(e, ch, xlo + (i - xolo), ylo + (j - yolo));
+  /* the line-of-sight masks are computed once in __init__, when wall_positions is still empty (STAG:175,408-412): all
+   * ones, so masking the dynamic channels changes nothing (STAG:989-992) and the visibility channel is a plane of ones
+   * over the WHOLE window, clipped or not (STAG:993-994) */
+  if (c->include_visibility_channel)
+    for (int i = 0; i < R * R; ++i) out[CG * R * R + i] = 1.0;
+}
+
+static int is_wall(const env_t* e, int x, int y) { return e->wallmap[x * e->G + y]; }
+
+/* _line_of_sight_clear (STAG:892-925): integer Bresenham walk from start to end, no wall strictly between */
+static int los_clear(const env_t* e, int x0, int y0, int x1, int y1) {
+  const int dx = abs(x1 - x0), dy = abs(y1 - y0);
+  int x = x0, y = y0;
+  const int sx = x1 > x0 ? 1 : -1, sy = y1 > y0 ? 1 : -1;
+  if (dx >= dy) {
+    double err = dx / 2.0;
+    while (x != x1) {
+      if (!(x == x0 && y == y0) && !(x == x1 && y == y1) && is_wall(e, x, y)) return 0;
+      err -= dy;
+      if (err < 0) { y += sy; err += dx; }
+      x += sx;
+    }
+  } else {
+    double err = dy / 2.0;
+    while (y != y1) {
+      if (!(x == x0 && y == y0) && !(x == x1 && y == y1) && is_wall(e, x, y)) return 0;
+      err -= dx;
+      if (err < 0) { x += sx; err += dy; }
+      y += sy;
+    }
+  }
+  return 1;
 }
 
 static int take_real(env_t* e, double* out) {
@@ -109,6 +143,8 @@ void stag_env_reset_explicit(env_t* e, const int32_t* cells, const int32_t* faci
       for (int i = 0; i < c->n_initial_t[s][t]; ++i) e->agents[e->n_agents++] = KEY(s, (t ? c->n_possible_t[s][0] : 0) + i);
       e->next_idx_t[s][t] = c->n_initial_t[s][t]; /* pools hold the never-used ids in ascending order (STAG:2259-2291) */
     }
+  for (int cell = 0; cell < G * G; ++cell) /* _place_walls (STAG:2152-2159) */
+    if (e->wallmap[cell]) *GF(e, 0, cell / G, cell % G) = 1.0f;
   int k = 0, kp = 0;
   for (int i = 0; i < e->n_agents; ++i, ++k) { /* _place_predators / _place_prey (STAG:2162-2183) */
     const int s = KEY_S(e->agents[i]), id = KEY_ID(e->agents[i]);
@@ -167,7 +203,7 @@ void stag_env_reset_auto(env_t* e) {
     int n = 0;
     for (uint32_t idx = 0; n < n_total; ++idx) { /* same law as rng.choice(replace=False) (STAG:2140) */
       uint32_t cell = ppg_bounded(ppg_draw_u32(e->seed_key, genv(e), e->episode, PPG_STREAM_PLACEMENT, idx), (uint32_t)ncell);
-      if (!taken[cell]) { taken[cell] = 1; cells[n++] = (int32_t)cell; }
+      if (!taken[cell] && !e->wallmap[cell]) { taken[cell] = 1; cells[n++] = (int32_t)cell; } /* free_non_wall_indices (STAG:2138) */
     }
     free(taken);
     for (int k = 0; k < n_pred; ++k) /* _random_predator_facing (STAG:939-942) */
@@ -414,17 +450,17 @@ static int stag_find_spawn(env_t* e, int px, int py, int* ox, int* oy) {
   for (int k = 0; k < 4; ++k) {
     const int x = px + dx[k], y = py + dy[k];
     if (x < 0 || x >= G || y < 0 || y >= G) continue;
-    if (!occupied_by_agent(e, x, y)) { *ox = x; *oy = y; return 1; }
+    if (!occupied_by_agent(e, x, y) && !is_wall(e, x, y)) { *ox = x; *oy = y; return 1; } /* STAG:1026-1027 */
   }
   int n_free = 0;
-  for (int cell = 0; cell < G * G; ++cell) n_free += !occupied_by_agent(e, cell / G, cell % G);
+  for (int cell = 0; cell < G * G; ++cell) n_free += !occupied_by_agent(e, cell / G, cell % G) && !e->wallmap[cell];
   if (n_free == 0) return 0; /* no draw (STAG:1041-1044) */
   e->stats[PPG_STAT_SPAWN_FALLBACK]++;
   int cell;
   if (take_int(e, &cell)) { *ox = cell / G; *oy = cell % G; return 1; }
   uint32_t k = ppg_bounded(ppg_draw_u32(e->seed_key, genv(e), e->episode, PPG_STREAM_SPAWN, e->spawn_draws++), (uint32_t)n_free);
   for (cell = 0; cell < G * G; ++cell) /* sorted(all_positions - occupied)[k] (STAG:1039-1042) */
-    if (!occupied_by_agent(e, cell / G, cell % G)) {
+    if (!occupied_by_agent(e, cell / G, cell % G) && !e->wallmap[cell]) { /* STAG:1033-1039 */
       if (k == 0) { *ox = cell / G; *oy = cell % G; return 1; }
       --k;
     }
@@ -556,10 +592,18 @@ int stag_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, 
     }
     const int ox = e->x[s][id], oy = e->y[s][id];
     int nx = clipi(ox + dx, 0, e->G - 1), ny = clipi(oy + dy, 0, e->G - 1);
-    if (s == 0) { /* STAG:865-868 */
+    if (is_wall(e, nx, ny)) { nx = ox; ny = oy; } /* STAG:861-864 */
+    else if (s == 0) { /* STAG:865-868: the `elif "predator" in agent` arm ends the chain: predators never reach the LOS test */
       if (*GF(e, CH_PRED, nx, ny) > 0) { nx = ox; ny = oy; }
     } else if (*GF(e, CH_PREY1, nx, ny) > 0 || *GF(e, CH_PREY2, nx, ny) > 0) { /* STAG:869-874 */
       nx = ox; ny = oy;
+    } else {
+      if (c->respect_los_for_movement && (nx != ox || ny != oy)) { /* STAG:875-889 (prey only, see above) */
+        const int mx = nx - ox, my = ny - oy;
+        if (abs(mx) == 1 && abs(my) == 1) { /* no corner cutting */
+          if (is_wall(e, ox + mx, oy) || is_wall(e, ox, oy + my)) { nx = ox; ny = oy; }
+        } else if (!los_clear(e, ox, oy, nx, ny)) { nx = ox; ny = oy; }
+      }
     }
     const int ch = channel_of(c, s, id);
     *GF(e, ch, ox, oy) = 0;                         /* STAG:819,824 */

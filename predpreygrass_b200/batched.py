@@ -71,7 +71,8 @@ class BatchedPredPreyGrass:
         b = PpgBuffers()
         _lib.check(self.L.ppg_get_buffers(self.h, C.byref(b)), self.h)
         # row channels: the grid channels, plus ECO's own-speed plane (ECO:707-711)
-        self.C = cfg.num_obs_channels + (1 if cfg.variant == VARIANT_ECO and cfg.include_speed_in_obs else 0)
+        self.C = (cfg.num_obs_channels + (1 if cfg.variant == VARIANT_ECO and cfg.include_speed_in_obs else 0)
+                  + (1 if cfg.variant == 2 and cfg.include_visibility_channel else 0))  # STAG:1788
         self.R = (cfg.obs_range[0], cfg.obs_range[1])
         self.row_capacity = (int(b.row_capacity[0]), int(b.row_capacity[1]))
         d, B = self.device, self.n_envs

@@ -6,6 +6,8 @@ flattened once into the C struct the kernels read.
 """
 import ctypes as C
 
+import numpy as np
+
 VARIANT_BASE, VARIANT_ECO, VARIANT_STAG = 0, 1, 2
 REWARD_SPARSE, REWARD_DENSE, REWARD_DENSE_ADDITIVE, REWARD_SPARSE_KICKBACK = 0, 1, 2, 3
 
@@ -121,6 +123,11 @@ class PpgConfig(C.Structure):
         ("repro_max_ratio", C.c_double),
         ("metabolic_speed_coeff", C.c_double),
         ("lineage_reward_coeff", C.c_double * 2),
+        ("wall_cells", C.c_void_p),
+        ("n_walls", C.c_int32),
+        ("respect_los_for_movement", C.c_int32),
+        ("include_visibility_channel", C.c_int32),
+        ("reserved3", C.c_int32),
     ]
 
 
@@ -416,12 +423,20 @@ def _by_type(value, kind, default, fallback_key="type_1"):
 def _fill_stag(c, cfg, cap_live_given):
     """STAG `__init__` (STAG:19-266) — same keys, same defaults, same clamps."""
     g = cfg.get
-    if g("manual_wall_positions") or g("num_walls", 0) and g("wall_placement_mode", "manual") != "manual":
-        raise ValueError("walls are not supported (STAG:2107-2127); the BASELINE stag_hunt config has none")
-    for k in ("mask_observation_with_visibility", "include_visibility_channel", "respect_los_for_movement"):
-        if g(k, False):
-            raise ValueError(f"{k} is not supported (line-of-sight masks, STAG:892-925,983-994)")
     c.grid_size = g("grid_size", 0)
+    # `_create_wall_positions` (STAG:2107-2127): the in-bounds manual positions, duplicates dropped; `num_walls` and
+    # `wall_placement_mode` are read by the reference (STAG:172-173) but never used
+    walls = []
+    for x, y in (g("manual_wall_positions") or []):
+        if 0 <= x < c.grid_size and 0 <= y < c.grid_size and int(x) * c.grid_size + int(y) not in walls:
+            walls.append(int(x) * c.grid_size + int(y))
+    c._walls = np.asarray(sorted(walls), np.int32)  # kept alive with the config object
+    c.n_walls = len(walls)
+    c.wall_cells = c._walls.ctypes.data if walls else None
+    c.respect_los_for_movement = 1 if g("respect_los_for_movement", False) else 0
+    c.include_visibility_channel = 1 if g("include_visibility_channel", False) else 0
+    # mask_observation_with_visibility multiplies by the reference's masks, which are all ones (computed before any wall
+    # exists, STAG:408-412): accepted, no effect
     c.max_steps = g("max_steps", 0)
     c.num_obs_channels = max(int(g("num_obs_channels", 0)), 5)  # STAG:118-119
     c.obs_range[0], c.obs_range[1] = g("predator_obs_range", 0), g("prey_obs_range", 0)

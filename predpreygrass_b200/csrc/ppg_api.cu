@@ -53,6 +53,7 @@ struct ppg_handle_s {
   ppg_config cfg;
   int B = 0, device = 0;
   StepParams P;
+  std::vector<int32_t> walls;  // copy of ppg_config.wall_cells
   int warps_per_cta = 4, n_cta = 0;
   size_t smem_bytes = 0;
   unsigned long long launches_step = 0;  // step-kernel launches so far (epoch)
@@ -209,6 +210,16 @@ static int validate(const ppg_config* c, int32_t n_envs, std::string& err) {
       if (c->include_speed_in_obs || c->max_agent_age[0] >= 0 || c->max_agent_age[1] >= 0 || c->carcass_only_predator_age >= 0) { err = "trait variants have no speed plane, age caps or carcass-only predators"; return PPG_ERR_INVALID; }
     }
   } else if (c->trait_mode != 0) { err = "trait_mode belongs to the ECO family"; return PPG_ERR_INVALID; }
+  if (c->n_walls != 0 || c->respect_los_for_movement || c->include_visibility_channel) {
+    if (!stag) { err = "walls / line of sight belong to the STAG variant"; return PPG_ERR_INVALID; }
+    if (c->n_walls < 0 || (c->n_walls > 0 && !c->wall_cells)) { err = "wall_cells missing"; return PPG_ERR_INVALID; }
+    for (int k = 0; k < c->n_walls; ++k)
+      if (c->wall_cells[k] < 0 || c->wall_cells[k] >= c->grid_size * c->grid_size) { err = "wall cell out of the grid"; return PPG_ERR_INVALID; }
+    if (c->n_walls + c->n_initial[0] + c->n_initial[1] + c->n_grass > c->grid_size * c->grid_size) { err = "walls leave too few cells for the reset placement"; return PPG_ERR_INVALID; }
+    // the reference's visibility channel is a constant plane of ones (its masks are computed before any wall exists,
+    // STAG:408-412); the dict adapter appends it on the host, the batched row layout does not carry it
+    if (c->include_visibility_channel) { err = "include_visibility_channel: a constant plane of ones in the reference; appended by the dict adapter (PredPreyGrassStag), not part of the batched rows"; return PPG_ERR_INVALID; }
+  }
   if (false) {
   }
   for (int s = 0; s < 2; ++s) {
@@ -236,6 +247,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   if (device < 0 || device >= ndev) { g_err = "bad device index"; return PPG_ERR_INVALID; }
   ppg_handle h = new ppg_handle_s();
   h->cfg = *cfg;
+  h->walls.assign(cfg->wall_cells, cfg->wall_cells + (cfg->wall_cells ? cfg->n_walls : 0));  // the caller's list is copied
+  h->cfg.wall_cells = h->walls.empty() ? nullptr : h->walls.data();
   h->B = n_envs;
   h->device = device;
   auto fail = [&](int code) { g_err = h->err; ppg_destroy(h); return code; };
@@ -278,6 +291,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
     for (int k = 0; k < 3; ++k) P.death_pen[k] = c.death_penalty[k];
     P.equal_split = c.team_capture_equal_split != 0; P.coop_enabled = c.coop_trait_enabled != 0; P.capture_model = c.team_capture_success_model;
     P.strict_out = c.strict_rllib_output != 0;
+    P.n_walls = (int)h->walls.size(); P.los_move = c.respect_los_for_movement != 0;
     P.cap_margin = c.team_capture_margin; P.join_cost = c.team_capture_join_cost; P.scav_frac = c.team_capture_scavenger_fraction;
     P.nature_w = c.team_capture_nature_weight; P.p0 = c.team_capture_base_success_p0; P.force_ratio = c.team_capture_force_success_ratio;
     P.min_prob = c.team_capture_min_success_prob; P.trait_mean = c.coop_trait_init_mean; P.trait_std = c.coop_trait_init_std;
@@ -393,6 +407,18 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
         }
       }
       if (!eco && !stag) reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
+      if (stag && !h->walls.empty()) {  // STAG walls (STAG:2152-2159): static WALL entries of the predator map, shown by channel 0
+        for (int w : h->walls) {
+          const int i = P.P + (w / G + P.P) * P.PS + w % G;
+          if (P.map_bytes == 1) img[(size_t)i] = (unsigned char)P.wall_idx;
+          else reinterpret_cast<uint16_t*>(img.data())[i] = (uint16_t)P.wall_idx;
+        }
+        reinterpret_cast<float*>(img.data() + (P.so_wt - P.so_map[0]))[P.wall_idx] = 1.0f;
+        int32_t* d_w = nullptr;
+        CKC(dalloc(h, &d_w, h->walls.size()));
+        CKC(cudaMemcpy(d_w, h->walls.data(), h->walls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        P.wall_cells = d_w;
+      }
       unsigned char* d_img = nullptr;
       CKC(dalloc(h, &d_img, img.size()));
       CKC(cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice));

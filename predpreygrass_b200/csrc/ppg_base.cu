@@ -376,8 +376,8 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
             const int ax = (a * 11) >> 5;  // a / 3 for 0 <= a <= 8
             nx0 = min(max(x + ax - 1, 0), G - 1); ny0 = min(max(y + (a - 3 * ax) - 1, 0), G - 1);
             oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
-            atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
-            if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+            red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
+            if (tc != oc) red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
           }
           __syncwarp();
           const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);

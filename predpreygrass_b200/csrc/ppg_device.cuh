@@ -175,6 +175,9 @@ struct StepParams {
   // gain exponent, density cap (< 0: none)
   int trait_mode, n_init_min[2], sat_cd, coop_range;
   double trait_alpha, repro_ratio;
+  // STAG walls (static cells of channel 0, STAG:2107-2160) and line-of-sight test of prey moves (STAG:875-925)
+  const int32_t* wall_cells;  // [n_walls] x * G + y
+  int n_walls, los_move;
   // ECO lineage survival rewards (ECO:943-984,1422-1470), by agent id: parent id (0xFFFF: founder), live descendants,
   // their count at the previous step, own alive flag; lin_on = any coefficient non-zero
   int lin_on;

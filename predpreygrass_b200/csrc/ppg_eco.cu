@@ -589,8 +589,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             nx0 = min(max(x + dx, 0), G - 1); ny0 = min(max(y + dy, 0), G - 1);
             d2 = (nx0 - x) * (nx0 - x) + (ny0 - y) * (ny0 - y);
             oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
-            atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
-            if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+            red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
+            if (tc != oc) red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
           }
           __syncwarp();
           const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);

@@ -96,7 +96,7 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
   const int P0 = (n[0] + 1) >> 1, totalP = P0 + ((n[1] + 1) >> 1);
   auto grab = [&]() -> int {
     int q = 0;
-    if (lane == 0) q = atomicAdd(counter, 1);
+    if (lane == 0) q = atom_shared_add(counter, 1);
     return __shfl_sync(FULL, q, 0);
   };
   int q = grab();
@@ -110,7 +110,7 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
     const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
     do {
       int qn = 0;
-      if (lane == 0) qn = atomicAdd(counter, 1);  // the next pair's index arrives while this one is being written
+      if (lane == 0) qn = atom_shared_add(counter, 1);  // the next pair's index arrives while this one is being written
       const int ka = 2 * (q - firstq), kb = ka + 1;
       bool done = false;
       if (kb < n_s) {

@@ -103,6 +103,58 @@ __device__ __forceinline__ int stag_view(const StepParams& p, int s, unsigned ps
   return CELLXY(x, y);
 }
 
+template <typename MapT>
+__device__ bool los_blocked(const MapT* wm, MapT WALL, int PS, int oc, int tc);
+
+// `_get_move`'s block tests (STAG:860-890) for a move from padded cell `oc` to `tc`: a wall cell (static WALL entry of the
+// predator map) blocks everybody; predators are blocked by a predator with energy > 0 — and the reference's `elif` chain
+// ends there for them; prey by a prey of either type, else (respect_los_for_movement) by a wall corner cut diagonally or a
+// wall strictly between the end points of the integer Bresenham walk (STAG:892-925).
+template <typename MapT>
+__device__ __forceinline__ bool move_blocked(const MapT* wm, const MapT* map1, const MapT* map3, const double* E0, const double* E1,
+                                             const StepParams& p, int s, int oc, int tc) {
+  const MapT WALL = (MapT)p.wall_idx;
+  const unsigned ow = wm[tc];
+  if (p.n_walls && ow == WALL) return true;
+  if (s == 0) return ow != 0 && (float)E0[ow - 1] > 0.f;
+  const unsigned o1 = map1[tc], o3 = map3[tc];
+  if ((o1 != 0 && (float)E1[o1 - 1] > 0.f) || (o3 != 0 && (float)E1[o3 - 1] > 0.f)) return true;
+  if (!p.los_move || !p.n_walls || tc == oc) return false;
+  return los_blocked<MapT>(wm, WALL, p.PS, oc, tc);
+}
+
+// corner cutting and the Bresenham walk of `_line_of_sight_clear` (STAG:875-925) on the padded predator map
+template <typename MapT>
+__device__ __noinline__ bool los_blocked(const MapT* wm, MapT WALL, int PS, int oc, int tc) {
+  // padded index -> (row, column) differences: rows are PS apart, |dy| < PS / 2
+  int dxy = tc - oc, mx = 0;
+  while (dxy > PS / 2) { dxy -= PS; ++mx; }
+  while (dxy < -(PS / 2)) { dxy += PS; --mx; }
+  const int my = dxy;
+  const int adx = abs(mx), ady = abs(my);
+  if (adx == 1 && ady == 1) return wm[oc + mx * PS] == WALL || wm[oc + my] == WALL;  // no corner cutting
+  const int sx = mx > 0 ? 1 : -1, sy = my > 0 ? 1 : -1;
+  int c = oc;
+  if (adx >= ady) {
+    double err = adx / 2.0;
+    for (int i = 0; i < adx; ++i) {
+      if (c != oc && c != tc && wm[c] == WALL) return true;
+      err -= ady;
+      if (err < 0) { c += sy; err += adx; }
+      c += sx * PS;
+    }
+  } else {
+    double err = ady / 2.0;
+    for (int i = 0; i < ady; ++i) {
+      if (c != oc && c != tc && wm[c] == WALL) return true;
+      err -= adx;
+      if (err < 0) { c += sx * PS; err += ady; }
+      c += sy;
+    }
+  }
+  return false;
+}
+
 template <int W, typename MapT, bool SPLIT>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -228,7 +280,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
         }
       }
       if (!from_tape) {
-        philox_placement(cells, first, n_total, GG, genv, h.episode, h.seed_key, lane);
+        philox_placement(cells, first, n_total, GG, genv, h.episode, h.seed_key, lane, p.wall_cells, p.n_walls);
         #pragma unroll 1
         for (int i = lane; i < n_pred; i += 32)  // _random_predator_facing (STAG:939-942)
           X.face[i] = (uint8_t)ppg_bounded(ppg_draw_u32(h.seed_key, genv, h.episode, PPG_STREAM_FACING, (unsigned)i), 8u);
@@ -451,22 +503,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
             }
             nx0 = min(max(x + dx, 0), G - 1); ny0 = min(max(y + dy, 0), G - 1);
             oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
-            atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
-            if (tc != oc) atomicAdd(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+            red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
+            if (tc != oc) red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
           }
           __syncwarp();
           const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);
           __syncwarp();
           if (v) { S.scr[oc] = 0; S.scr[tc] = 0; }
           if (v && !dirty) {
-            bool blocked;
-            if (s == 0) {  // STAG:865-868
-              const unsigned ow = S.map[0][tc];
-              blocked = ow != 0 && (float)S.E[0][ow - 1] > 0.f;
-            } else {       // either prey channel (STAG:869-874)
-              const unsigned o1 = S.map[1][tc], o3 = X.map3[tc];
-              blocked = (o1 != 0 && (float)S.E[1][o1 - 1] > 0.f) || (o3 != 0 && (float)S.E[1][o3 - 1] > 0.f);
-            }
+            const bool blocked = move_blocked<MapT>(S.map[0], S.map[1], X.map3, S.E[0], S.E[1], p, s, oc, tc);
             const int nc = blocked ? oc : tc;
             if (!blocked) SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
             own[oc] = 0;              // STAG:819,824
@@ -480,14 +525,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
             const int jj = __shfl_sync(FULL, j, l);
             const int tcl = __shfl_sync(FULL, tc, l), ocl = __shfl_sync(FULL, oc, l);
             const int nxl = __shfl_sync(FULL, nx0, l), nyl = __shfl_sync(FULL, ny0, l);
-            bool blocked;
-            if (s == 0) {
-              const unsigned ow = S.map[0][tcl];
-              blocked = ow != 0 && (float)S.E[0][ow - 1] > 0.f;
-            } else {
-              const unsigned o1 = S.map[1][tcl], o3 = X.map3[tcl];
-              blocked = (o1 != 0 && (float)S.E[1][o1 - 1] > 0.f) || (o3 != 0 && (float)S.E[1][o3 - 1] > 0.f);
-            }
+            const bool blocked = move_blocked<MapT>(S.map[0], S.map[1], X.map3, S.E[0], S.E[1], p, s, ocl, tcl);
             MapT* ownl = s == 0 ? S.map[0] : prey_map(jj);
             __syncwarp();
             if (lane == 0) {
@@ -789,7 +827,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
               const int cx = px + (c == 0 ? -1 : (c == 1 ? 1 : 0));
               const int cy = py + (c == 2 ? -1 : (c == 3 ? 1 : 0));
               if (sx < 0 && cx >= 0 && cx < G && cy >= 0 && cy < G) {
-                if (!any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }
+                if (!(p.n_walls && S.map[0][CELLXY(cx, cy)] == (MapT)p.wall_idx) && !any_agent_at(S, nl, (unsigned)((cx << 8) | cy), lane)) { sx = cx; sy = cy; }  // STAG:1026-1027
               }
             }
             if (sx < 0) {

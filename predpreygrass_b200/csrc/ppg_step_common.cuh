@@ -22,6 +22,17 @@ namespace ppg {
 #define PPG_PUSH_DEFER 1    // hand an env to the observation kernel from the top of the next env (fence under the loads)
 #endif
 
+// shared-memory atomics by 32-bit shared address: one ATOMS / RED instruction instead of the generic-pointer atomicAdd's
+// address-space dispatch (~15 instructions per call in the SASS of the previous build)
+__device__ __forceinline__ void red_shared_add(const void* smem_ptr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(smem_ptr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_shared_add(const void* smem_ptr, int v) {
+  int old;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(smem_ptr)), "r"(v) : "memory");
+  return old;
+}
+
 __device__ __forceinline__ unsigned globaltimer_lo() { unsigned v; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(v)); return v; }
 __device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 
@@ -529,10 +540,15 @@ static __device__ __noinline__ unsigned draw_normals_batched(double* out, int co
 }
 
 // reset(): n_total unique cells in draw order (law of BASE:156-177) from the env's Philox placement stream
+// `first[cell]` = 1 + index of the first draw that hit the cell; wall cells (STAG:2138 `free_non_wall_indices`) are
+// pre-claimed with 0, which no draw equals: a draw that hits a wall is skipped like a duplicate.
 static __device__ __noinline__ void philox_placement(int* cells, unsigned* first, int n_total, int GG, unsigned env, unsigned episode,
-                                              unsigned long long seed_key, int lane) {
+                                              unsigned long long seed_key, int lane, const int32_t* walls = nullptr, int n_walls = 0) {
   #pragma unroll 1
   for (int i = lane; i < GG; i += 32) first[i] = 0xFFFFFFFFu;
+  __syncwarp();
+  #pragma unroll 1
+  for (int i = lane; i < n_walls; i += 32) first[walls[i]] = 0u;
   __syncwarp();
   int accepted = 0;
   for (unsigned batch = 0; accepted < n_total; ++batch) {
@@ -542,13 +558,13 @@ static __device__ __noinline__ void philox_placement(int* cells, unsigned* first
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       cell[k] = ppg_bounded(r.v[k], (unsigned)GG);
-      atomicMin(&first[cell[k]], idx0 + k);
+      atomicMin(&first[cell[k]], idx0 + k + 1u);
     }
     __syncwarp();
     int mine = 0;
     bool ok[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k; mine += ok[k]; }
+    for (int k = 0; k < 4; ++k) { ok[k] = first[cell[k]] == idx0 + k + 1u; mine += ok[k]; }
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
@@ -571,6 +587,9 @@ __device__ __forceinline__ void mark_agents(const EnvSmem<MapT>& S, const StepPa
     #pragma unroll 1
     for (int i = lane; i < nl[s2]; i += 32)
       if (S.flg[s2][i] & F_ALIVE) S.scr[CELLP((unsigned)S.pos[s2][i])] = v;
+  const int G = p.G;
+  #pragma unroll 1
+  for (int i = lane; i < p.n_walls; i += 32) S.scr[CELLXY(p.wall_cells[i] / G, p.wall_cells[i] % G)] = v;  // walls are never free (STAG:1033-1037)
   __syncwarp();
 }
 

@@ -91,7 +91,9 @@ def reference_reset_tape_stag(seed, config):
     G = config["grid_size"]
     n_pred = g("n_initial_active_type_1_predator", 0) + g("n_initial_active_type_2_predator", 0)
     n_prey = g("n_initial_active_type_1_prey", 0) + g("n_initial_active_type_2_prey", 0)
-    cells = rng.choice(list(range(G * G)), size=n_pred + n_prey + g("initial_num_grass", 0), replace=False)
+    walls = {(int(x), int(y)) for x, y in (g("manual_wall_positions") or []) if 0 <= x < G and 0 <= y < G}  # STAG:2107-2127
+    free = [i for i in range(G * G) if (i // G, i % G) not in walls]  # STAG:2138
+    cells = rng.choice(free, size=n_pred + n_prey + g("initial_num_grass", 0), replace=False)
     facing, traits = [], []
     for _ in range(n_pred):
         facing.append(int(rng.integers(8)))
@@ -116,6 +118,11 @@ class _RowDictEnv(_Base):
         from .batched import BatchedPredPreyGrass  # needs the CUDA extension; fails loudly without it
 
         self.config = config
+        # STAG's visibility channel is a constant plane of ones in the reference (its line-of-sight masks are computed before
+        # any wall exists, STAG:408-412): the device rows do not carry it, `_vis` appends it to the dict observations
+        self._vis_plane = bool(self._variant == VARIANT_STAG and config.get("include_visibility_channel", False))
+        if self._vis_plane:
+            config = dict(config, include_visibility_channel=False)
         self._cfg = make_config(config, variant=self._variant, cap_live=config.get("cap_live"), autoreset=False,
                                 seed=config.get("seed") or 0, track_episode_sums=self._variant == VARIANT_ECO)
         self._batch = BatchedPredPreyGrass(self._cfg, 1, device=config.get("cuda_device", 0))
@@ -759,7 +766,7 @@ class PredPreyGrassStag(_RowDictEnv):
                                 [f"type_2_predator_{i}" for i in range(c.n_possible_t[0][1])] +
                                 [f"type_1_prey_{i}" for i in range(c.n_possible_t[1][0])] +
                                 [f"type_2_prey_{i}" for i in range(c.n_possible_t[1][1])])  # STAG:1768-1782
-        C = self.num_obs_channels
+        C = self.num_obs_channels + (1 if self._vis_plane else 0)  # STAG:1788
         pred_space = Box(low=0, high=100.0, shape=(C, self.predator_obs_range, self.predator_obs_range), dtype=np.float32)
         prey_space = Box(low=0, high=100.0, shape=(C, self.prey_obs_range, self.prey_obs_range), dtype=np.float32)
         self.observation_spaces = {a: pred_space if "predator" in a else prey_space for a in self.possible_agents}
@@ -769,6 +776,13 @@ class PredPreyGrassStag(_RowDictEnv):
         self.observation_space = DictSpace(self.observation_spaces)
         self.action_space = DictSpace(self.action_spaces)
         self.predator_join_intent = {}
+
+    def _vis(self, window, value):
+        """include_visibility_channel (STAG:993-994): one more channel holding the reference's line-of-sight mask, which is
+        all ones (see __init__); mask_observation_with_visibility multiplies by the same ones"""
+        if not self._vis_plane:
+            return window
+        return np.concatenate([window, np.full((1,) + window.shape[1:], value, np.float32)])
 
     def _name(self, s, i):
         sp = "predator" if s == 0 else "prey"
@@ -812,7 +826,7 @@ class PredPreyGrassStag(_RowDictEnv):
         obs = {}
         self._rows = {}
         for name, s, r, f in self._rows_of(out):  # founders: type_1/type_2 predators, type_1/type_2 prey (STAG:340-380)
-            obs[name] = out[f"obs{s}"][r]
+            obs[name] = self._vis(out[f"obs{s}"][r], 1.0)
             self._rows[name] = (s, r)
         self.agents = list(obs)
         return obs, {}
@@ -836,7 +850,7 @@ class PredPreyGrassStag(_RowDictEnv):
         self.agents_just_ate = set()
         for a in live + gone:
             s, r, f = rows[a]
-            obs[a] = out[f"obs{s}"][r]
+            obs[a] = self._vis(out[f"obs{s}"][r], 0.0 if f & ROW_TERMINATED else 1.0)  # ended agents: all-zero rows (STAG:596-612)
             rew[a] = float(out[f"reward{s}"][r])
             term[a] = bool(f & ROW_TERMINATED)
             trunc[a] = bool(f & ROW_TRUNCATED)

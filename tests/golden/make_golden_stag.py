@@ -69,6 +69,15 @@ CASES = [
                              strict_rllib_output=False), 9, "list", 200),
     ("stag_trunc_s2", dict(RICH, max_steps=30), 2, "list", 60),
     # other window shapes and an odd grid: predators 5x5 (forward shift 2), prey 9x9
+    # walls and line of sight (STAG:860-925,977-994,1026-1037,2107-2160)
+    ("stag_walls_s1", dict(CROWDED, grid_size=10, manual_wall_positions=[(2, 2), (2, 3), (2, 4), (5, 5), (5, 6), (6, 5), (8, 1), (0, 9), (12, 3)]),
+     1, "list", 200),
+    ("stag_walls_los_s2_shuffle", dict(CROWDED, grid_size=10, type_2_action_range=5, respect_los_for_movement=True,
+                                       include_visibility_channel=True, mask_observation_with_visibility=True,
+                                       manual_wall_positions=[(3, y) for y in range(2, 8)] + [(6, 1), (6, 2), (7, 7), (8, 7), (1, 8)]),
+     2, "shuffle", 200),
+    ("stag_walls_vis_s3", dict(RICH, include_visibility_channel=True, respect_los_for_movement=True, type_2_action_range=5,
+                               manual_wall_positions=[(x, 15) for x in range(5, 25)] + [(10, y) for y in range(3, 12)]), 3, "list", 120),
     ("stag_windows_s10", dict(CROWDED, grid_size=11, predator_obs_range=5, prey_obs_range=9, initial_num_grass=30), 10, "shuffle", 200),
     ("stag_tiny_s3", dict(CROWDED, grid_size=5, initial_num_grass=8, n_initial_active_type_1_predator=5, n_initial_active_type_1_prey=3,
                           n_initial_active_type_2_prey=8, predator_obs_range=9, prey_obs_range=7), 3, "shuffle", 150),
@@ -136,7 +145,7 @@ def record(name, overrides, seed, order, max_calls):
     obs, _ = env.reset(seed=seed)
     twin = np.random.default_rng(seed)
     n_all = len(env.agents) + len(env.grass_agents)
-    twin_cells = twin.choice([i for i in range(G * G)], size=n_all, replace=False)
+    twin_cells = twin.choice([i for i in range(G * G) if (i // G, i % G) not in env.wall_positions], size=n_all, replace=False)  # STAG:2138-2140
     founders = list(env.agents)
     pred_founders = [a for a in founders if "predator" in a]
     founder_facing, founder_trait_raw = [], []

@@ -4,13 +4,13 @@ import pytest
 from predpreygrass_b200.config import ECO_CONFIG, STAG_CONFIG, VARIANT_ECO, VARIANT_STAG, make_config
 
 
-def test_stag_walls_and_line_of_sight_are_rejected():
-    with pytest.raises(ValueError):
-        make_config(dict(STAG_CONFIG, manual_wall_positions=[(3, 3)]), variant=VARIANT_STAG)
-    for k in ("mask_observation_with_visibility", "include_visibility_channel", "respect_los_for_movement"):
-        with pytest.raises(ValueError):
-            make_config(dict(STAG_CONFIG, **{k: True}), variant=VARIANT_STAG)
-    assert make_config(STAG_CONFIG, variant=VARIANT_STAG).grid_size == 30  # the BASELINE config itself is fine
+def test_stag_walls_and_line_of_sight_keys_are_read():
+    c = make_config(dict(STAG_CONFIG, manual_wall_positions=[(3, 3), (3, 3), (40, 1), (0, 29)], respect_los_for_movement=True,
+                         include_visibility_channel=True, mask_observation_with_visibility=True), variant=VARIANT_STAG)
+    assert c.n_walls == 2 and list(c._walls) == [29, 93]  # duplicates and out-of-bounds cells dropped (STAG:2112-2122)
+    assert c.respect_los_for_movement == 1 and c.include_visibility_channel == 1
+    c = make_config(STAG_CONFIG, variant=VARIANT_STAG)
+    assert c.grid_size == 30 and c.n_walls == 0 and c.include_visibility_channel == 0
 
 
 def test_eco_lineage_coefficients_are_read_per_role():

@@ -67,6 +67,18 @@ def test_stag_slot_overflow_id_pool_and_idle():
     assert st["births_prey"] > 0
 
 
+def test_stag_walls_and_line_of_sight():
+    """manual walls (channel 0, blocked moves, spawn and placement exclusion, STAG:860-864,1026-1037,2107-2160) and the
+    line-of-sight test of prey moves with a 5x5 action range (STAG:875-925), Philox placement around the walls"""
+    walls = [(3, y) for y in range(2, 8)] + [(6, 1), (6, 2), (7, 7), (8, 7), (1, 8), (9, 9)]
+    cfg = dict(CROWDED, grid_size=10, manual_wall_positions=walls, respect_los_for_movement=True, type_2_action_range=5)
+    st = lockstep_parity(stag(cfg, cap_live=(96, 224), seed=31), 256, 120, state_envs=(0, 100, 255))
+    assert st["births_prey"] > 0 and st["episodes"] > 0
+    cfg = dict(STAG_CONFIG, manual_wall_positions=[(x, 15) for x in range(5, 25)] + [(10, y) for y in range(3, 12)], respect_los_for_movement=True)
+    st = lockstep_parity(stag(cfg, cap_live=(64, 192), seed=37), 128, 100, state_envs=(0, 127))
+    assert st["status_envs"] == 0
+
+
 def test_stag_4096_envs():
     st = lockstep_parity(stag(STAG_CONFIG, cap_live=(64, 160), seed=21), 4096, 80, state_envs=(0, 4095), check_every=4)
     print(st)
@@ -89,17 +101,24 @@ def test_stag_golden_trajectories_on_gpu(name):
     from predpreygrass_b200.batched import BatchedPredPreyGrass
 
     z, cfg = load_golden(name)
-    c = config_from_golden(cfg, autoreset=False)
+    # the visibility channel is a constant plane of ones in the reference (STAG:408-412,993-994) and not part of the device
+    # rows (include/ppg.h): the device runs without it and the plane is appended here, as PredPreyGrassStag does
+    vis = bool(cfg.get("include_visibility_channel"))
+    c = config_from_golden(dict(cfg, include_visibility_channel=False), autoreset=False)
     c.cap_live[0] = min(c.cap_live[0], 224)
     c.cap_live[1] = min(c.cap_live[1], 416)
     g = BatchedPredPreyGrass(c, 1)
+
+    def with_vis(o, flags=0):
+        return np.concatenate([o, np.full((1,) + o.shape[1:], 0.0 if flags & 1 else 1.0, np.float32)]) if vis else o
+
     reals = np.concatenate([z["founder_trait_raw"] if c.coop_trait_enabled else np.zeros(0), z["step_reals"]])
     g.load_tape([np.concatenate([z["init_cells"], z["founder_facing"], z["step_ints"]])], [reals])
     g.reset()
     out = g.outputs_numpy()
     keys = list(zip(z["reset_row_s"].tolist(), z["reset_row_id"].tolist()))
     rows = ref_order_rows(out, keys)
-    assert np.array_equal(sha_f32([out[f"obs{s}"][r] for s, r in rows]), z["reset_sha"])
+    assert np.array_equal(sha_f32([with_vis(out[f"obs{s}"][r]) for s, r in rows]), z["reset_sha"])
     T = len(z["steps"])
     full = set(int(t) for t in z["full_obs_steps"])
     for t in range(T):
@@ -143,12 +162,13 @@ def test_stag_golden_trajectories_on_gpu(name):
         assert np.array_equal((fl >> 1) & 1, z["row_trunc"][r0:r1]), (name, t)
         if t in full:
             for s in range(2):
-                mine = [out[f"obs{s}"][r] for ss, r in rows if ss == s]
+                mine = [with_vis(out[f"obs{s}"][r], out[f"flags{s}"][r]) for ss, r in rows if ss == s]
                 ref = z[f"full_obs_{t}_{s}"]
                 assert len(mine) == len(ref), (name, t, s)
                 for k in range(len(mine)):
                     assert np.array_equal(mine[k], ref[k]), (name, t, s, k, np.argwhere(mine[k] != ref[k])[:4])
-        ordered = [out[f"obs{s}"][r] for s, r in rows if s == 0] + [out[f"obs{s}"][r] for s, r in rows if s == 1]
+        ordered = ([with_vis(out[f"obs{s}"][r], out[f"flags{s}"][r]) for s, r in rows if s == 0] +
+                   [with_vis(out[f"obs{s}"][r], out[f"flags{s}"][r]) for s, r in rows if s == 1])
         assert np.array_equal(sha_f32(ordered), z["obs_sha"][t]), (name, t)
         assert bool(out["env_flags"][0] & 1) == bool(z["all_term"][t]), (name, t)
         assert bool(out["env_flags"][0] & 2) == bool(z["all_trunc"][t]), (name, t)
