@@ -658,8 +658,12 @@ static int run_step_kernel(ppg_handle h, const int32_t* a0, const int32_t* a1, c
   P.actions[0] = a0; P.actions[1] = a1;
   P.order[0] = o0; P.order[1] = o1;
   P.ticket_base = h->ticket_next;
-  // tickets: one per env (W == 1) or per group of W envs, plus one terminating draw per warp / CTA
-  h->ticket_next += h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
+  // tickets: one per env (W == 1) or per group of W envs, plus one terminating draw per warp / CTA.  static_first: a
+  // warp's first ticket is its CTA index and every env it works on draws the warp's next one: exactly B draws.
+  P.static_first = (h->warps_per_cta == 1 && P.obs_split && P.variant != PPG_VARIANT_ECO) ? 1 : 0;
+  if (const char* ev = getenv("PPG_STATIC_FIRST")) P.static_first = P.static_first && atoi(ev) != 0;
+  h->ticket_next += P.static_first ? (unsigned long long)h->B
+                    : h->warps_per_cta == 1 ? (unsigned long long)h->B + (unsigned long long)h->n_cta
                                           : (unsigned long long)((h->B + h->warps_per_cta - 1) / h->warps_per_cta) + (unsigned long long)h->n_cta;
   P.epoch = (unsigned)(h->launches_step + 1);
   P.q_base = h->q_next;

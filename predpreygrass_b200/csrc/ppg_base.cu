@@ -50,6 +50,7 @@
 namespace ppg {
 
 PHASE_DEFINE(base)
+SPAN_DEFINE(base)
 
 // ------------------------------------------------------------------------------------------------
 // the step kernel: W persistent warps per CTA, one env per warp at a time
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SPAN_MARK(base, 0)
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
@@ -99,13 +101,17 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
   // the publication of a lower env (ECO's episode-end rows, the one-kernel step) always waits for a running warp.
   // ticket -> env: big envs first when the previous launch left an order (publish_begin), else index order
   const int32_t* const perm = (W == 1 && SPLIT && p.perm[par ^ 1] != nullptr && p.perm_tag[par ^ 1] == epoch - 1u) ? p.perm[par ^ 1] : nullptr;
+  // static_first: the first ticket of a warp is its CTA index — 2960 atomics on one address at kernel start cost the last
+  // warp ~7 us; the counter then hands out the tickets from min(grid, B) on
+  const int t_first = p.static_first ? min((int)gridDim.x, p.B) : 0;
   int env_next = 0;
   if (W == 1 && lane == 0) {
-    env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    env_next = p.static_first ? min((int)blockIdx.x, p.B) : (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
     if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
   }
   unsigned long long pend = 0ULL;  // lane 0: completion-queue slot + 1 of the env whose hand-over is still owed (queue_push)
   int pend_env = 0;
+  SPAN_MARK(base, 1)
   for (;;) {
     PHASE_DECL
     int env = 0;  // PHASE: ticket+hdr
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
     // and the two accumulators of the row allocation (results looked at after the rows are written)
 #if PPG_TICKET_EARLY
     if (W == 1 && lane == 0) {
-      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      env_next = t_first + (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
       if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
     }
 #endif
@@ -901,7 +907,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
 #endif
 #if !PPG_TICKET_EARLY
     if (W == 1 && lane == 0) {
-      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      env_next = t_first + (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
       if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
     }
 #endif
@@ -910,6 +916,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
   }
   if (SPLIT) queue_push(p, pend, pend_env, lane);
   if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the engine has read it
+  SPAN_MARK(base, 2)
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -112,6 +112,8 @@ struct StepParams {
   // ---- dynamic env scheduling + deterministic row allocation (hierarchical counts, see ppg_base.cu) ----
   unsigned long long* ticket;      // env ticket counter (monotonic over launches)
   unsigned long long ticket_base;  // value of *ticket at launch
+  int static_first;                // 1: a warp's first env is ticket blockIdx.x (no atomic), the counter hands out tickets >= min(grid, B);
+                                   // only where no env ever waits for another one (BASE / STAG two-kernel step)
   unsigned epoch;                  // launch number (1-based); tags every published word
   unsigned* error;                 // device error word (bit0: prefix wait wedged)
   // published per env / per 32-env block / per 1024-env group, ping-pong by epoch parity:

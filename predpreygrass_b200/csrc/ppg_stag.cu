@@ -185,9 +185,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
   // envs come from the ticket counter; after the first one the ticket is drawn while the previous env is being finished (ppg_base.cu)
   // ticket -> env: big envs first when the previous launch left an order (publish_begin), else index order
   const int32_t* const perm = (SPLIT && p.perm[par ^ 1] != nullptr && p.perm_tag[par ^ 1] == epoch - 1u) ? p.perm[par ^ 1] : nullptr;
+  const int t_first = p.static_first ? min((int)gridDim.x, p.B) : 0;  // first ticket of a warp = its CTA index (ppg_base.cu)
   int env_next = 0;
   if (lane == 0) {
-    env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    env_next = p.static_first ? min((int)blockIdx.x, p.B) : (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
     if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
   }
   unsigned long long pend = 0ULL;  // lane 0: completion-queue slot + 1 of the env whose hand-over is still owed (queue_push)
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
     // completion queue, the two accumulators of the row allocation
 #if PPG_TICKET_EARLY
     if (lane == 0) {
-      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      env_next = t_first + (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
       if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
     }
 #endif
@@ -1079,7 +1080,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __g
 #endif
 #if !PPG_TICKET_EARLY
     if (lane == 0) {
-      env_next = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+      env_next = t_first + (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
       if (perm != nullptr && env_next < p.B) env_next = perm[env_next];
     }
 #endif

@@ -47,12 +47,19 @@ __device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %
   extern "C" int ppg_debug_phase_cycles_##name(unsigned* out, int n_envs) { /* [n_envs][PPG_N_PHASES] of the last launch */ \
     return cudaMemcpyFromSymbol(out, g_phase_cycles_##name, sizeof(unsigned) * PPG_N_PHASES * (size_t)n_envs) == cudaSuccess ? 0 : -1; \
   }
+// kernel span per CTA: globaltimer (ns, low 32 bits) at kernel entry, at the first env's start and at exit
+#define SPAN_DEFINE(name)                                                                                           \
+  __device__ unsigned g_span_##name[3][8192];                                                                       \
+  extern "C" int ppg_debug_span_##name(unsigned* out) { return cudaMemcpyFromSymbol(out, g_span_##name, sizeof(unsigned) * 3 * 8192) == cudaSuccess ? 0 : -1; }
+#define SPAN_MARK(name, k) if (lane == 0 && blockIdx.x < 8192) g_span_##name[k][blockIdx.x] = globaltimer_lo();
 #define PHASE_DECL long long ph_t = clock64(); unsigned ph_acc[PPG_N_PHASES]; _Pragma("unroll") for (int k_ = 0; k_ < PPG_N_PHASES; ++k_) ph_acc[k_] = 0;
 #define PHASE_MARK(k) { const long long t_ = clock64(); ph_acc[k] += (unsigned)(t_ - ph_t); ph_t = t_; }
 #define PHASE_FLUSH(name) if (lane == 0 && env < PPG_PROF_MAX_ENVS) { _Pragma("unroll") for (int k_ = 0; k_ < PPG_N_PHASES; k_ += 4) \
     *reinterpret_cast<uint4*>(&g_phase_cycles_##name[env][k_]) = make_uint4(ph_acc[k_], ph_acc[k_ + 1], ph_acc[k_ + 2], ph_acc[k_ + 3]); }
 #else
 #define PHASE_DEFINE(name)
+#define SPAN_DEFINE(name)
+#define SPAN_MARK(name, k)
 #define PHASE_DECL
 #define PHASE_MARK(k)
 #define PHASE_FLUSH(name)
