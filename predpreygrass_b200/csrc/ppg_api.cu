@@ -329,7 +329,8 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   for (int s = 0; s < 2; ++s) {
     P.obs_vec[s] = P.elems[s] % 4 == 0;
     P.nj[s] = P.obs_vec[s] ? 4 * ((P.elems[s] / 4 + 31) / 32) : (P.elems[s] + 31) / 32;
-    P.emit_kind[s] = (P.obs_vec[s] && P.nj[s] == 8) ? 1 : (P.obs_vec[s] && P.nj[s] == 12) ? 2 : (!P.obs_vec[s] && P.nj[s] == 13) ? 3 : 0;
+    P.emit_kind[s] = (P.obs_vec[s] && P.nj[s] == 8) ? 1 : (P.obs_vec[s] && P.nj[s] == 12) ? 2 : (!P.obs_vec[s] && P.nj[s] == 13) ? 3
+                     : (!P.obs_vec[s] && P.nj[s] == 5) ? 4 : (!P.obs_vec[s] && P.nj[s] == 8) ? 5 : 0;
   }
   if (P.nj[0] > PPG_MAX_NJ || P.nj[1] > PPG_MAX_NJ) { h->err = "observation row too large for this build"; return fail(PPG_ERR_INVALID); }
 

@@ -161,7 +161,7 @@ struct StepParams {
   int nj[2];            // per-lane elements of a row per species (see obs_vec)
   int obs_vec[2];       // 1: lane owns float4 groups (row length % 4 == 0, nj = 4 * ceil(elems / 128)); 0: lane owns
                         //    elements lane + 32 j (nj = ceil(elems / 32))
-  int emit_kind[2];     // specialised row writer: 1 = (4,7,7), 2 = (4,9,9), 3 = (5,9,9), 0 = generic
+  int emit_kind[2];     // specialised row writer: 1 = (4,7,7), 2 = (4,9,9), 3 = (5,9,9), 4 = (3,7,7), 5 = (3,9,9), 0 = generic
   int obs_bulk;         // 1: rows leave through shared-memory staging + cp.async.bulk; 0: direct streaming stores
   const void* init_image;  // [init_bytes] initial contents of the maps / touch counters / wall table of a warp's slice
   int init_bytes;

@@ -405,6 +405,8 @@ __device__ __forceinline__ bool emit_row2(const StepParams& p, unsigned sb32, fl
     case 1: emit_row2_t<MapT, 8, true, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
     case 2: emit_row2_t<MapT, 12, true, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
     case 3: emit_row2_t<MapT, 13, false, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
+    case 4: emit_row2_t<MapT, 5, false, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
+    case 5: emit_row2_t<MapT, 8, false, SELF>(p, sb32, dst0, dst1, cellp0, cellp1, s, r, lane, selfv0, selfv1); return true;
     default: return false;
   }
 }
@@ -416,6 +418,8 @@ __device__ __forceinline__ void emit_row(const StepParams& p, unsigned sb32, flo
     case 1: emit_row_t<MapT, 8, true, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;    // (4,7,7): 49 float4
     case 2: emit_row_t<MapT, 12, true, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;   // (4,9,9): 81 float4
     case 3: emit_row_t<MapT, 13, false, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;  // (5,9,9): 405 floats
+    case 4: emit_row_t<MapT, 5, false, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;   // (3,7,7): 147 floats (trait variants without a trait plane)
+    case 5: emit_row_t<MapT, 8, false, BULK, SELF>(p, sb32, dst, cellp, s, r, rowctr, lane, selfv); break;   // (3,9,9): 243 floats
     default: rowctr = emit_row_generic<MapT, BULK>(p, sb32, dst, cellp, s, rowctr, lane, SELF ? r.self : 0u, selfv);
   }
 }

@@ -165,8 +165,11 @@ class PredPreyGrass(_Base):
         super().reset(seed=seed)
         b = self._batch
         n_total = self.n_initial_active_predator + self.n_initial_active_prey + self.initial_num_grass
+        # options={"ppg_tape": cells}: recorded spawn-fallback cells (BASE:760-764 draws them from the GLOBAL numpy generator,
+        # which no seed of this class reaches) replayed after the reset cells; without it the device's Philox stream decides
+        extra = np.asarray((options or {}).get("ppg_tape", ()), np.int32).reshape(-1)
         if seed is not None:
-            b.load_tape([reference_initial_cells(seed, self.grid_size, n_total)])
+            b.load_tape([np.concatenate([reference_initial_cells(seed, self.grid_size, n_total), extra])])
             b.reset(seeds=np.array([np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)], np.uint64))
         else:
             b.load_tape([np.zeros(0, np.int32)])

@@ -218,7 +218,9 @@ def test_full_size_properties_16384_envs():
 
 
 @pytest.mark.parametrize("name", ["base_default_s1", "base_default_s7_shuffle", "base_trunc_s2", "additive_default_s1", "kickback_default_s6",
-                                  "seasonal_default_s1", "seasonal_trunc_s3", "seasonal_default_s5"])
+                                  "seasonal_default_s1", "seasonal_trunc_s3", "seasonal_default_s5",
+                                  "base_crowded_s1", "base_crowded_s2_shuffle", "additive_crowded_s2", "kickback_crowded_s1", "base_rewards_s8",
+                                  "dense_crowded_s3", "seasonal_crowded_s2_shuffle"])
 def test_dict_adapter_replays_reference_episode(name):
     """`PredPreyGrass` (the MultiAgentEnv-shaped adapter) against an episode recorded from the reference
     through the same dict API: reset(seed) placement, observation-dict key order, rewards,
@@ -226,12 +228,11 @@ def test_dict_adapter_replays_reference_episode(name):
     from predpreygrass_b200.env import PredPreyGrass
 
     z, cfg = load_golden(name)
-    if len(z["fallback_cells"]):
-        pytest.skip("episode uses the global-numpy spawn fallback draw (BASE:764), which the device replaces by Philox")
     variant = cfg.pop("variant")
     cfg = dict(cfg, reward_variant=variant, cap_live=(min(cfg["n_possible_predators"], 320), min(cfg["n_possible_prey"], 320)))
     env = PredPreyGrass(cfg)
-    obs, infos = env.reset(seed=int(z["seed"]))
+    # spawn-fallback cells (BASE:764, global numpy generator) are the reference's recorded ones
+    obs, infos = env.reset(seed=int(z["seed"]), options={"ppg_tape": z["fallback_cells"]})
     assert infos == {}
     G = env.grid_size
     names = ("predator", "prey")
