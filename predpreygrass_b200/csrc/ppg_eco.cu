@@ -57,7 +57,14 @@ __device__ __forceinline__ EcoSmem<MapT> carve_eco(unsigned char* base, const St
 }
 
 // own-speed plane value (ECO:707-711): float32((speed - lo) / (hi - lo)); 0 without a genome
+#ifndef PPG_EXP_PLANE_NOINLINE
+#define PPG_EXP_PLANE_NOINLINE 0
+#endif
+#if PPG_EXP_PLANE_NOINLINE
+static __device__ __noinline__ float speed_plane(const StepParams& p, double spd) {
+#else
 __device__ __forceinline__ float speed_plane(const StepParams& p, double spd) {
+#endif
   if (!p.speed_in_obs || spd < 0.0) return 0.f;
   if (p.trait_mode == PPG_TRAIT_CADENCE) return (float)spd;  // CAD:746: the genome value itself
   return (float)((spd - p.sp_lo) / (p.sp_hi - p.sp_lo));
@@ -72,7 +79,11 @@ __device__ __forceinline__ double cad_move_rate(const StepParams& p, double spd)
 }
 
 // speed ** exponent (ECO:559-563): CPython's float power = glibc pow, repeated bit for bit (include/ppg_pow.h)
+#if defined(PPG_EXP_FASTPOW) && PPG_EXP_FASTPOW  // experiment only (NOT bit-exact): what the exact pow costs the kernel
+static __device__ __forceinline__ double speed_cost_factor(double speed, double exponent) { return speed * speed; }
+#else
 static __device__ __noinline__ double speed_cost_factor(double speed, double exponent) { return ppg_pow(speed, exponent); }
+#endif
 
 // trait variants: gain factor metabolic_rate ** alpha (MR:751,807), 1.0 ** alpha = 1 without a genome
 static __device__ __noinline__ double gain_factor(double rate, double alpha) { return ppg_pow(rate >= 0.0 ? rate : 1.0, alpha); }
@@ -568,6 +579,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           const int k = b0 + lane;
           int j = 0, oc = 0, tc = 0, nx0 = 0, ny0 = 0, d2 = 0;
           bool v = false;
+          double fac_l = 1.0, dist_l = 0.0;  // speed ** exponent and step length of this lane's agent: ONE lane-parallel pow / sqrt per batch, also for the replay below
           if (k < SEL(n)) {
             j = SEL(X.mord)[k];
             const unsigned f = SEL(S.flg)[j];
@@ -591,6 +603,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             oc = CELLXY(x, y); tc = CELLXY(nx0, ny0);
             red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (oc >> 2), 1u << ((oc & 3) * 8));
             if (tc != oc) red_shared_add(reinterpret_cast<unsigned*>(S.scr) + (tc >> 2), 1u << ((tc & 3) * 8));
+            // _get_movement_energy_cost's speed factor (ECO:559-563; MR:531-539 (MR / INV / COOP): no speed factor), needed only by
+            // an agent that can leave its cell
+            if (tc != oc) {
+              dist_l = sqrt((double)d2);
+              if (sp >= 0.0 && !ppg_random_founders(tm)) fac_l = speed_cost_factor(sp, p.move_exp);
+            }
           }
           __syncwarp();
           const bool dirty = v && (S.scr[oc] > 1 || S.scr[tc] > 1);
@@ -601,9 +619,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const bool blocked = ow != 0 && (float)SEL(S.E)[ow - 1] > 0.f;  // float32 grid > 0 (ECO:690)
             const int nc = blocked ? oc : tc;
             if (!blocked && d2 > 0) {  // _get_movement_energy_cost (ECO:565-573)
-              const double sp = SEL(X.spd)[j];
-              const double fac = (sp < 0.0 || ppg_random_founders(tm)) ? 1.0 : speed_cost_factor(sp, p.move_exp);  // MR:531-539 (MR / INV / COOP): no speed factor
-              const double dist = sqrt((double)d2), cost = p.move_cost[s] * dist * fac;
+              const double dist = dist_l, cost = p.move_cost[s] * dist * fac_l;
               SEL(S.E)[j] = SEL(S.E)[j] - cost;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
               if (p.ep_sums) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
@@ -617,6 +633,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int l = __ffs(dm) - 1;
             dm &= dm - 1;
             const int jj = __shfl_sync(FULL, j, l);
+            const double fac = __shfl_sync(FULL, fac_l, l), dist = __shfl_sync(FULL, dist_l, l);  // dd is 0 or the agent's own d2 (its cell has not changed yet)
             const unsigned ps = SEL(S.pos)[jj];
             const int a = SEL(S.act)[jj];
             const int xx = ps >> 8, yy = ps & 255;
@@ -631,8 +648,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int dd = (nx - xx) * (nx - xx) + (ny - yy) * (ny - yy);
             double e = SEL(S.E)[jj];
             if (dd > 0) {
-              const double fac = (sp < 0.0 || ppg_random_founders(tm)) ? 1.0 : speed_cost_factor(sp, p.move_exp);
-              const double dist = sqrt((double)dd), cost = p.move_cost[s] * dist * fac;
+              const double cost = p.move_cost[s] * dist * fac;
               e = e - cost;
               if (p.ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
             }
@@ -776,10 +792,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                      S.scr[c0 + PS - 1] || S.scr[c0 + PS + 1];
             cand = cand && (S.flg[0][k] & F_ALIVE);
           }
+          // MR:747-751 gain factor metabolic_rate ** alpha of the candidates: one lane-parallel pow, not one per catch in the ordered loop
+          double gf_l = 1.0;
+          if (tm == PPG_TRAIT_METABOLIC && cand) gf_l = gain_factor(X.spd[0][k], p.trait_alpha);
           unsigned m = __ballot_sync(FULL, cand);
           while (m) {
             const int slot = b0 + __ffs(m) - 1;
             m &= m - 1;
+            const double gf = tm == PPG_TRAIT_METABOLIC ? __shfl_sync(FULL, gf_l, slot - b0) : 1.0;
             const unsigned ps = S.pos[0][slot];
             const int cell = CELLP(ps);
             // first prey in agent_positions order on my cell = lowest id = lowest list slot (ECO:797-799)
@@ -813,7 +833,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             else {  // the trait variants always consume the prey (MR:759-773)
               rem = 0.0;
               if (tm == PPG_TRAIT_COOPERATION) en = S.E[0][slot] + coop_donation<MapT>(sbase, p, 0, slot, n[0], pe, lane);  // COOP:777
-              else en = S.E[0][slot] + (tm == PPG_TRAIT_METABOLIC ? bite * gain_factor(X.spd[0][slot], p.trait_alpha) : bite);  // MR:747-751
+              else en = S.E[0][slot] + (tm == PPG_TRAIT_METABOLIC ? bite * gf : bite);  // MR:747-751
             }
             __syncwarp();
             if (lane == 0) {
