@@ -200,10 +200,19 @@ __device__ __noinline__ double coop_donation(unsigned char* sbase, const StepPar
 // because the step kernels are bound by instruction delivery: the speed kernel carries none of the variants'
 // code and the variants' kernel none of the speed / carcass / ageing code.
 // KIND 2 = eco_evolutionary with lineage survival rewards (lineage_reward_coeff != 0; the shipped config has 0): a third
-// kernel for the same reason.
+// kernel for the same reason.  KIND 10 + PPG_TRAIT_x = the kernel of ONE trait variant (trait_mode a compile-time constant:
+// none of the other variants' code), used by the two-kernel step; KIND 1 keeps trait_mode a runtime value (one-kernel fallback).
 template <int W, typename MapT, bool SPLIT, int KIND>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __grid_constant__ StepParams p) {
-  constexpr bool TRAITS = KIND == 1, LIN = KIND == 2;
+  constexpr bool TRAITS = KIND == 1 || KIND >= 10, LIN = KIND == 2;
+  // KIND 3 = eco_evolutionary WITHOUT the carcass machinery: max_energy_gain_per_prey = inf (every catch eats the whole prey:
+  // no dead_prey, no ghost cells), no carcass_only_predator_age, no per-episode sums — the shipped config (BASELINE configs[3]).
+  // The kernel is bound by instruction delivery: what the config cannot reach is not compiled in.
+  constexpr bool LEAN = KIND == 3;
+  constexpr unsigned FC = LEAN ? 0u : (unsigned)F_CARC;
+  const int carcass_age = LEAN ? -1 : p.carcass_age;
+  const double bite_cap_prey = LEAN ? HUGE_VAL : p.bite_cap_prey;
+  double* const ep_sums = LEAN ? nullptr : p.ep_sums;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
@@ -276,8 +285,8 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       const int g = lane + 32 * q;
       if (g < p.n_grass) { gp_r[q] = p.gr_pos[(size_t)env * p.n_grass + g]; ge_r[q] = p.gr_e[(size_t)env * p.n_grass + g]; }
     }
-    const int n_gh_r = p.gh_n[env];
-    const int tm = TRAITS ? p.trait_mode : PPG_TRAIT_SPEED;  // PPG_TRAIT_*: 0 = ECO (speed)
+    const int n_gh_r = LEAN ? 0 : p.gh_n[env];
+    const int tm = KIND >= 10 ? KIND - 10 : TRAITS ? p.trait_mode : PPG_TRAIT_SPEED;  // PPG_TRAIT_*: 0 = ECO (speed)
     if (TRAITS && tm == PPG_TRAIT_SPEED) __builtin_unreachable();
     // founders of the episode a reset starts: constant for ECO, drawn per episode by the trait variants (MR:189-192)
     int nf[2] = {p.n_init[0], p.n_init[1]};
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             S.id[s][i] = (uint16_t)i;
             S.pos[s][i] = (uint16_t)((cx << 8) | cy);
             S.flg[s][i] = F_ALIVE;
-            X.age[s][i] = (uint16_t)((s == 0 && p.carcass_age >= 0) ? p.carcass_age : 0);  // ECO:1060-1068
+            X.age[s][i] = (uint16_t)((s == 0 && carcass_age >= 0) ? carcass_age : 0);  // ECO:1060-1068
             X.seq[s][i] = (uint16_t)(k0 + i);
             if (!p.genome_enabled) X.spd[s][i] = -1.0;
             S.map[s][CELLXY(cx, cy)] = (MapT)(i + 1);
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           SEL(X.age)[i] = (uint16_t)age;
           SEL(X.seq)[i] = (uint16_t)(agseq >> 16);
           SEL(S.act)[i] = (uint8_t)a;
-          SEL(S.flg)[i] = (uint8_t)(F_ALIVE | (carc ? F_CARC : 0));
+          SEL(S.flg)[i] = (uint8_t)(F_ALIVE | (carc ? FC : 0));
           if (!use_order) SEL(X.mord)[i] = (uint16_t)i;
           if (!carc && p.max_age[s] >= 0 && (int)age >= p.max_age[s]) aged_any = true;  // ECO:1052-1058
         }
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         long long last = -1;
         for (;;) {
           const unsigned key = next_in_seq_order(X.seq, n, last, lane, [&](int s, int i) {
-            return !(S.flg[s][i] & F_CARC) && p.max_age[s] >= 0 && (int)X.age[s][i] >= p.max_age[s];
+            return !(S.flg[s][i] & FC) && p.max_age[s] >= 0 && (int)X.age[s][i] >= p.max_age[s];
           });
           if (key == 0xFFFFFFFFu) break;
           last = (long long)key;
@@ -583,7 +592,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           if (k < SEL(n)) {
             j = SEL(X.mord)[k];
             const unsigned f = SEL(S.flg)[j];
-            v = (f & F_ALIVE) && !(f & F_CARC);  // terminated (ECO:633) and dead prey (ECO:636) do not move
+            v = (f & F_ALIVE) && !(f & FC);  // terminated (ECO:633) and dead prey (ECO:636) do not move
             if (tm == PPG_TRAIT_CADENCE && v) {  // cadence gate (CAD:674-681): frozen agents keep their place, the accumulator still advances
               const double a = SEL(X.acc)[j] + cad_move_rate(p, SEL(X.spd)[j]);
               v = a >= 1.0;
@@ -622,7 +631,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               const double dist = dist_l, cost = p.move_cost[s] * dist * fac_l;
               SEL(S.E)[j] = SEL(S.E)[j] - cost;
               SEL(S.pos)[j] = (uint16_t)((nx0 << 8) | ny0);
-              if (p.ep_sums) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
+              if (ep_sums) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
             }
             own[oc] = 0;              // ECO:653,657
             own[nc] = (MapT)(j + 1);  // ECO:654,658
@@ -650,7 +659,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (dd > 0) {
               const double cost = p.move_cost[s] * dist * fac;
               e = e - cost;
-              if (p.ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
+              if (ep_sums && lane == 0) { if (s == 0) { ep_dist[0] += dist; ep_cost[0] += cost; } else { ep_dist[1] += dist; ep_cost[1] += cost; } }
             }
             __syncwarp();
             if (lane == 0) {  // one writer: the two map stores may hit the same cell (blocked move) and must keep their order
@@ -684,7 +693,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                                                      rowctr, lane, speed_plane(p, SEL(X.spd)[slot]));
             if (lane == 0) {
               SEL(S.map)[cell] = 0;
-              SEL(S.flg)[slot] = F_DIED;  // also drops F_CARC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
+              SEL(S.flg)[slot] = F_DIED;  // also drops FC (dead_prey.discard, ECO:768-769) and F_CAUGHT (reward 0, ECO:772)
               if (LIN) lineage_set_alive(p, env, s, SEL(S.id)[slot], 0);  // ECO:770
             }
             if (s == 0) { eh.active[0] -= 1; st_starved[0]++; } else { eh.active[1] -= 1; st_starved[1]++; }
@@ -721,7 +730,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         bool act = false;
         if (slot < n[1]) {
           const unsigned f = S.flg[1][slot];
-          act = (f & F_ALIVE) && !(f & F_CARC);
+          act = (f & F_ALIVE) && !(f & FC);
           cell = CELLP((unsigned)S.pos[1][slot]);
           g = S.map[2][cell];
         }
@@ -748,7 +757,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
         const int kend = min(b0 + 32, n[1]);
         for (int sl = b0; sl < kend; ++sl) {  // two prey of this chunk share a patch: exact order
           const unsigned f = S.flg[1][sl];
-          if (!(f & F_ALIVE) || (f & F_CARC)) continue;
+          if (!(f & F_ALIVE) || (f & FC)) continue;
           const int cl = CELLP((unsigned)S.pos[1][sl]);
           const int gg = S.map[2][cl];
           if (gg) {
@@ -822,12 +831,12 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const int q = (int)(best & 0xFFFFu);
             const int qcell = CELLP((unsigned)S.pos[1][q]);  // the prey's own cell (= `cell` except for cadence's radius-1 catches)
             const unsigned qf = S.flg[1][q];
-            const bool was_dead = (qf & F_CARC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
-            if (!was_dead && p.carcass_age >= 0 && (int)X.age[0][slot] < p.carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
+            const bool was_dead = (qf & FC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
+            if (!was_dead && carcass_age >= 0 && (int)X.age[0][slot] < carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
             if (satiation && X.mord[0][slot] != 0) continue;  // still digesting: does not hunt this step (MR:734-740)
             const double pe = S.E[1][q];
-            const double bite = pe < p.bite_cap_prey ? pe : p.bite_cap_prey;  // ECO:812-814
-            double rem = pe - bite;
+            const double bite = LEAN ? pe : (pe < bite_cap_prey ? pe : bite_cap_prey);  // ECO:812-814
+            double rem = LEAN ? 0.0 : pe - bite;
             double en;
             if (tm == PPG_TRAIT_SPEED) en = S.E[0][slot] + bite;
             else {  // the trait variants always consume the prey (MR:759-773)
@@ -849,7 +858,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
                 // a prey that aged out this step (F_DIED) is removed in Step 5 without the grid being zeroed: the entry written
                 // here outlives its owner and becomes a ghost cell at write-back (see the header)
                 S.map[1][qcell] = (MapT)(q + 1);
-                S.flg[1][q] = (uint8_t)(qf | F_CARC);
+                S.flg[1][q] = (uint8_t)(qf | FC);
               }
               __syncwarp();
             } else {  // fully eaten (ECO:846-866); its observation is captured now
@@ -882,7 +891,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           bool elig = false;
           if (k < SEL(n)) {
             const unsigned f = SEL(S.flg)[k];
-            elig = (f & F_ALIVE) && !(f & F_CARC) && SEL(S.E)[k] >= p.thr[s];
+            elig = (f & F_ALIVE) && !(f & FC) && SEL(S.E)[k] >= p.thr[s];
           }
           unsigned m = __ballot_sync(FULL, elig);
           while (m) {
@@ -1097,7 +1106,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               if (mode == 1) rf |= PPG_ROW_FOUNDER;
               if (f & F_ATE) rf |= PPG_ROW_ATE;
               if (f & F_REPRO) rf |= PPG_ROW_REPRODUCED;
-              if (alive && (f & F_CARC)) rf |= PPG_ROW_CARCASS;
+              if (alive && (f & FC)) rf |= PPG_ROW_CARCASS;
               // CAD:577-585,746-753: the action mask of the row looks one increment ahead of the stored accumulator
               if (tm == PPG_TRAIT_CADENCE && !(SEL(X.acc)[slot] + cad_move_rate(p, SEL(X.spd)[slot]) >= 1.0)) rf |= PPG_ROW_FROZEN;
               if (!(SPLIT && newborn)) {
@@ -1123,7 +1132,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
               p.ag_seq[s][sb + dst] = SEL(X.seq)[slot];
               p.ag_spd[s][sb + dst] = SEL(X.spd)[slot];
               if (tm == PPG_TRAIT_CADENCE) p.ag_acc[s][sb + dst] = SEL(X.acc)[slot];
-              if (tm == PPG_TRAIT_SPEED) p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & F_CARC) ? 1 : 0;
+              if (tm == PPG_TRAIT_SPEED) p.ag_dead[s][sb + dst] = (SEL(S.flg)[slot] & FC) ? 1 : 0;
               else {  // predators: steps of digestion left at the next step (MR:734-740,756-757)
                 const unsigned rmn = (mode == 2 && s == 0 && slot < n[0] && (tm == PPG_TRAIT_METABOLIC || tm == PPG_TRAIT_INVESTMENT)) ? X.mord[0][slot] : 0u;
                 p.ag_dead[s][sb + dst] = (uint8_t)(rmn > 0u ? rmn - 1u : 0u);
@@ -1162,7 +1171,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
       // step and were written back as carcasses (their entry outlives them).  Only a finite intake cap can create them.
       {
         int kept = 0;
-        if (keep && mode == 2 && (n_gh > 0 || p.bite_cap_prey < HUGE_VAL)) {
+        if (keep && mode == 2 && (n_gh > 0 || bite_cap_prey < HUGE_VAL)) {
           const size_t gb = (size_t)env * PPG_MAX_GHOSTS;
           for (int b0 = -32; b0 < n[1]; b0 += 32) {  // first round: the loaded ghosts (pseudo-slots), then the list
             const int sl = b0 < 0 ? (lane < n_gh ? p.cap[1] - 1 - lane : -1) : (b0 + lane < n[1] ? b0 + lane : -1);
@@ -1171,7 +1180,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (sl >= 0) {
               const unsigned f = S.flg[1][sl];
               gp = S.pos[1][sl];
-              gh = (b0 < 0 || ((f & F_DIED) && (f & F_CARC))) && S.map[1][CELLP(gp)] == (MapT)(sl + 1);
+              gh = (b0 < 0 || ((f & F_DIED) && (f & FC))) && S.map[1][CELLP(gp)] == (MapT)(sl + 1);
             }
             const unsigned m = __ballot_sync(FULL, gh);
             const int at = kept + __popc(m & lt_mask);
@@ -1204,7 +1213,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           if (mode == 1) p.gr_pos[gb + g] = S.gpos[g];
         }
       }
-      if (p.ep_sums) {
+      if (ep_sums) {
         // per-episode totals behind `_build_episode_training_metrics` (ECO:1613-1661): distance moved and locomotion energy of
         // all agents of a species (record["distance_traveled"], record["movement_energy_spent"], ECO:659-660)
         double v[4] = {ep_dist[0], ep_dist[1], ep_cost[0], ep_cost[1]};
@@ -1213,7 +1222,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], d);
         if (lane < 4) {
-          double* dst = p.ep_sums + (size_t)env * 4 + lane;
+          double* dst = ep_sums + (size_t)env * 4 + lane;
           const double add = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
           *dst = mode == 1 ? 0.0 : *dst + add;
         }
@@ -1305,9 +1314,26 @@ static cudaError_t launch_eco_v(const StepParams& p, int n_cta, size_t smem, cud
   if (p.obs_split) return p.map_bytes == 1 ? launch_eco_t<uint8_t, true, KIND>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true, KIND>(p, n_cta, smem, stream);
   return p.map_bytes == 1 ? launch_eco_t<uint8_t, false, KIND>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, false, KIND>(p, n_cta, smem, stream);
 }
+template <int KIND>
+static cudaError_t launch_eco_split(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
+  return p.map_bytes == 1 ? launch_eco_t<uint8_t, true, KIND>(p, n_cta, smem, stream) : launch_eco_t<uint16_t, true, KIND>(p, n_cta, smem, stream);
+}
 cudaError_t launch_step_eco(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
+  if (p.trait_mode != PPG_TRAIT_SPEED && p.obs_split) {
+    switch (p.trait_mode) {
+      case PPG_TRAIT_METABOLIC: return launch_eco_split<10 + PPG_TRAIT_METABOLIC>(p, n_cta, smem, stream);
+      case PPG_TRAIT_INVESTMENT: return launch_eco_split<10 + PPG_TRAIT_INVESTMENT>(p, n_cta, smem, stream);
+      case PPG_TRAIT_COOPERATION: return launch_eco_split<10 + PPG_TRAIT_COOPERATION>(p, n_cta, smem, stream);
+      case PPG_TRAIT_CADENCE: return launch_eco_split<10 + PPG_TRAIT_CADENCE>(p, n_cta, smem, stream);
+      default: break;
+    }
+  }
   if (p.trait_mode != PPG_TRAIT_SPEED) return launch_eco_v<1>(p, n_cta, smem, stream);
-  return p.lin_on ? launch_eco_v<2>(p, n_cta, smem, stream) : launch_eco_v<0>(p, n_cta, smem, stream);
+  if (p.lin_on) return launch_eco_v<2>(p, n_cta, smem, stream);
+  // the shipped config reaches none of the carcass / ghost-cell / juvenile / episode-sum code: the kernel without it (KIND 3)
+  const bool lean = p.obs_split && p.trait_mode == PPG_TRAIT_SPEED && !(p.bite_cap_prey < HUGE_VAL) && p.carcass_age < 0 && p.ep_sums == nullptr;
+  if (const char* ev = getenv("PPG_ECO_LEAN")) { if (atoi(ev) == 0) return launch_eco_v<0>(p, n_cta, smem, stream); }
+  return lean ? launch_eco_split<3>(p, n_cta, smem, stream) : launch_eco_v<0>(p, n_cta, smem, stream);
 }
 
 template <typename MapT, bool SPLIT, int KIND>
