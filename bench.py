@@ -78,8 +78,12 @@ def parse(argv=None):
         # a full list would suppress births the reference allows); measured maxima: BASE 26 / 83, ECO 13 / 65,
         # ECO reproduction-heavy 222 / 416+, STAG 127 / 416+ (scripts/status_diag.py)
         args.cap = DEFAULT_CAPS["eco_rich" if (args.variant == "eco" and args.eco_rich) else args.variant]
+    args.groups_explicit = args.groups is not None or "PPG_BENCH_GROUPS" in os.environ
     if args.groups is None:
-        args.groups = int(os.environ.get("PPG_BENCH_GROUPS", "1"))
+        # measured (profiles/r02_summary.md): two groups win where each group still fills the GPU's 2960 step-kernel warps
+        # (16384-env configs of the base / eco families: +8..12 %), lose at 4096 envs (-20 %) and for STAG (-3 %)
+        auto = 2 if (args.variant != "stag" and args.envs >= 8192 and args.envs % 2 == 0) else 1
+        args.groups = int(os.environ.get("PPG_BENCH_GROUPS", auto))
     return args
 
 
@@ -420,7 +424,7 @@ def main():
         for name, extra in (("configs[2] dense_rewards_additive 16384 envs", ["--reward-mode", "additive", "--envs", "16384"]),
                             ("configs[3] eco_evolutionary 16384 envs", ["--variant", "eco", "--envs", "16384"]),
                             ("configs[4] stag_hunt 8192 envs per GPU", ["--variant", "stag", "--envs", "8192"])):
-            a2 = parse(extra + ["--preroll", str(args.preroll), "--no-e2e", "--no-cpu"] + (["--groups", str(args.groups)] if args.groups else []))
+            a2 = parse(extra + ["--preroll", str(args.preroll), "--no-e2e", "--no-cpu"] + (["--groups", str(args.groups)] if args.groups_explicit else []))
             try:
                 r2 = measure(a2, rank, local_rank, world, 50, 5, full=False)
                 others[name] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"], "envs_per_gpu": a2.envs,

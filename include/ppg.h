@@ -366,6 +366,14 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
  * (DESIGN.md §3.6).  No host synchronisation; results are exactly those of the same calls made one by one. */
 int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_streams, int32_t n_steps, uint64_t seed);
 
+/* Launch chain of a step (process-wide switch, returns the previous setting).  on (default, or PPG_PDL_CHAIN=1): the action
+ * kernel and the step kernel are launched with programmatic stream serialization behind the observation kernel of the step
+ * before, i.e. their CTAs become resident in the slots that kernel's tail leaves free and wait there (griddepcontrol.wait)
+ * until it has completed — results are identical, the launch ramp is hidden.  off: plain stream order; the right choice when
+ * several handles are stepped on their own streams (ppg_rollout_random with n_handles > 1 does it itself), because a parked
+ * grid holds SM slots the other streams could use.  No counterpart in the reference (there is no device). */
+int ppg_set_pdl_chain(int32_t on);
+
 int ppg_get_buffers(ppg_handle h, ppg_buffers* out);
 
 /* get_state_snapshot()/restore_state_snapshot() (BASE:768-804): the whole SoA slab incl. RNG

@@ -16,7 +16,7 @@ SYMBOLS = [
     "ppg_abi_version", "ppg_default_config", "ppg_create", "ppg_destroy", "ppg_load_tape", "ppg_reset", "ppg_step",
     "ppg_step_ordered", "ppg_step_host", "ppg_random_actions", "ppg_get_buffers", "ppg_snapshot_size", "ppg_snapshot", "ppg_restore",
     "ppg_read_env", "ppg_read_env_eco", "ppg_read_env_stag", "ppg_stats", "ppg_stats_device", "ppg_stats_clear", "ppg_launch_count", "ppg_last_error",
-    "ppg_profile_begin", "ppg_profile_end", "ppg_profile_env_cycles", "ppg_rollout_random", "ppg_selftest_pow", "ppg_read_episode_eco", "ppg_read_env_acc",
+    "ppg_profile_begin", "ppg_profile_end", "ppg_profile_env_cycles", "ppg_rollout_random", "ppg_selftest_pow", "ppg_read_episode_eco", "ppg_read_env_acc", "ppg_set_pdl_chain",
 ]
 
 _lib = None
@@ -54,6 +54,7 @@ def load():
     L.ppg_get_buffers.argtypes = [vp, C.POINTER(PpgBuffers)]
     L.ppg_selftest_pow.argtypes = [vp, vp, vp, C.c_int64, i32]
     L.ppg_rollout_random.argtypes = [C.POINTER(vp), i32, C.POINTER(vp), i32, u64]
+    L.ppg_set_pdl_chain.argtypes = [i32]
     L.ppg_snapshot_size.argtypes = [vp]
     L.ppg_snapshot_size.restype = C.c_size_t
     L.ppg_snapshot.argtypes = [vp, vp, C.c_size_t, vp]

@@ -42,6 +42,8 @@ cudaError_t launch_random_actions_stag(const int32_t* n_rows, const int32_t* re0
                                        int t2_prey, int ar0, int ar1, int blocks, cudaStream_t s);
 }  // namespace ppg
 
+namespace ppg { int g_pdl_chain = -1; }
+
 using namespace ppg;
 
 // include/ppg_pow.h on the device, argument by argument (ppg_selftest_pow)
@@ -795,8 +797,17 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
   return PPG_OK;
 }
 
+int ppg_set_pdl_chain(int32_t on) {
+  const int before = pdl_chain_enabled() ? 1 : 0;
+  g_pdl_chain = on ? 1 : 0;
+  return before;
+}
+
 int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_streams, int32_t n_steps, uint64_t seed) {
   if (!handles || n_handles <= 0 || n_steps < 0) return PPG_ERR_INVALID;
+  // several handles on their own streams: a step kernel parked in griddepcontrol.wait would hold the slots the other
+  // group's kernels are meant to fill, so the launch chain is plain stream order here
+  struct ChainOff { int before; bool off; ChainOff(bool o) : before(pdl_chain_enabled()), off(o) { if (off) g_pdl_chain = 0; } ~ChainOff() { if (off) g_pdl_chain = before; } } chain_off(n_handles > 1);
   for (int g = 0; g < n_handles; ++g) {
     if (!handles[g]) return PPG_ERR_INVALID;
     if (handles[g]->launches_step == 0) { handles[g]->err = "ppg_rollout_random before ppg_reset"; return PPG_ERR_STATE; }

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(W * 32, PPG_MIN_CTAS / W) ppg_step_base_kernel
   __shared__ int s_env0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SPAN_MARK(base, 0)
+  wait_for_stream_predecessor();  // PDL chain: this grid may have become resident under the tail of the kernel before it
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
@@ -1030,6 +1031,8 @@ __global__ void ppg_random_actions_kernel(const int32_t* __restrict__ n_rows, co
                                           const int32_t* __restrict__ row_agent0, const int32_t* __restrict__ row_env1,
                                           const int32_t* __restrict__ row_agent1, int32_t* act0, int32_t* act1,
                                           unsigned long long seed, unsigned call, unsigned n_actions, unsigned env_base) {
+  allow_dependent_launch();       // PDL chain: the step kernel behind this one may become resident now ...
+  wait_for_stream_predecessor();  // ... and this one waits for the observation kernel (row labels, row counts) before it reads
   const int n0 = n_rows[0] + n_rows[2], n1 = n_rows[1] + n_rows[3];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const int s = i >= n0;
@@ -1070,8 +1073,7 @@ static cudaError_t launch_w(const StepParams& p, int n_cta, size_t smem, cudaStr
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_base_kernel<W, MapT, BULK, SPLIT><<<n_cta, W * 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  return pdl_launch(ppg_step_base_kernel<W, MapT, BULK, SPLIT>, dim3((unsigned)n_cta), dim3(W * 32), smem, stream, p);
 }
 
 template <int W, typename MapT, bool BULK, bool SPLIT>
@@ -1136,8 +1138,7 @@ cudaError_t launch_set_tape(EnvHdr* hdr, int B, const long long* cell_off, cudaS
 cudaError_t launch_random_actions(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1,
                                   const int32_t* ra1, int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call,
                                   unsigned n_actions, unsigned env_base, int blocks, cudaStream_t s) {
-  ppg_random_actions_kernel<<<blocks, 256, 0, s>>>(n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, n_actions, env_base);
-  return cudaGetLastError();
+  return pdl_launch(ppg_random_actions_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, n_actions, env_base);
 }
 cudaError_t launch_stats(const uint32_t* counters, const EnvHdr* hdr, int B, unsigned long long* out, cudaStream_t s) {
   ppg_stats_kernel<<<148, 256, 0, s>>>(counters, hdr, B, out);

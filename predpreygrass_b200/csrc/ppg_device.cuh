@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include "../../include/ppg.h"
 #include "../../include/ppg_philox.h"
 #include "../../include/ppg_pow.h"
@@ -231,5 +234,29 @@ struct StepParams {
   const int2* obs_rel;  // [2][PPG_MAX_NJ][32]: x = byte offset of the map entry relative to the agent's own entry in map 0..2
                         //                       (so_map[m] + rel * map_bytes), y = byte offset of the value table; x = INT_MAX: no element
 };
+
+// Launch with programmatic stream serialization (PDL): the grid's CTAs may be scheduled as soon as every CTA of the kernel
+// before it in the stream has executed griddepcontrol.launch_dependents (or exited), which hides the launch ramp of the 2960
+// one-warp CTAs of a step kernel behind the tail of the observation kernel.  The kernel MUST execute griddepcontrol.wait before
+// it reads or writes anything the predecessor touches.  PPG_PDL_CHAIN=0 / ppg_set_pdl_chain(0) turn the chain off (plain stream
+// order): a grid waiting in griddepcontrol.wait holds its SM slots, which only hurts when OTHER streams have work for them
+// (env groups on their own streams).
+#ifdef __CUDACC__
+extern int g_pdl_chain;  // ppg_api.cu: -1 = not read yet, 0 = off, 1 = on (ppg_set_pdl_chain)
+inline bool pdl_chain_enabled() {
+  if (g_pdl_chain < 0) { const char* ev = getenv("PPG_PDL_CHAIN"); g_pdl_chain = ev ? (atoi(ev) != 0) : 1; }
+  return g_pdl_chain != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_chain_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 }  // namespace ppg

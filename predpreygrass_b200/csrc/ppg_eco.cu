@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
   double* const ep_sums = LEAN ? nullptr : p.ep_sums;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wait_for_stream_predecessor();  // PDL chain: this grid may have become resident under the tail of the kernel before it
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
@@ -1305,8 +1306,7 @@ static cudaError_t launch_eco_t(const StepParams& p, int n_cta, size_t smem, cud
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_eco_kernel<1, MapT, SPLIT, KIND><<<n_cta, 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  return pdl_launch(ppg_step_eco_kernel<1, MapT, SPLIT, KIND>, dim3((unsigned)n_cta), dim3(32), smem, stream, p);
 }
 
 template <int KIND>

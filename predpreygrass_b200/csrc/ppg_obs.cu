@@ -85,33 +85,69 @@ __device__ __forceinline__ void obs_one_row(const StepParams& p, const unsigned 
   }
 }
 
-// Rows of the agents that acted: the warps of the CTA take them one at a time from a shared counter, so a warp that is
-// busy with something else (warp 0: the next env's fetch, the newborn rows) simply takes fewer.  Rows come out in
-// order (species 0 first), so a warp reloads its per-lane gather constants at most once per env.
+// The per-lane gather constants of ONE species are kept by a warp ACROSS envs: loading them from global memory cost ~60
+// instructions and a global round trip per species and env (13 % of the kernel's instructions when every warp reloaded both
+// species for every env, profiles/r02_summary.md).  The CTA holds both species' tables in shared memory (6.6 KB, loaded
+// once); a warp reloads from there only when it changes species and re-bases the table addresses when the image buffer
+// alternates (nj integer adds).
+struct RelCache {
+  RowRel rr;
+  int s;          // species the constants belong to (-1: none)
+  unsigned base;  // virtual image base the table addresses were built for
+};
+struct RelSmem {
+  int2 rel[2][PPG_MAX_NJ][32];
+  unsigned self[2][32];
+};
+__device__ __forceinline__ void ensure_rel(const StepParams& p, const RelSmem& t, RelCache& c, int s, unsigned vb32, int lane) {
+  if (c.s != s) {
+    const int nj = p.nj[s];
+    c.rr.self = t.self[s][lane];
+#pragma unroll
+    for (int j = 0; j < PPG_MAX_NJ; ++j) {
+      c.rr.relb[j] = 0; c.rr.tbl[j] = 0;
+      if (j < nj) {
+        const int2 v = t.rel[s][j][lane];
+        c.rr.relb[j] = v.x; c.rr.tbl[j] = vb32 + (unsigned)v.y;
+      }
+    }
+    c.s = s;
+  } else if (c.base != vb32) {
+    const unsigned d = vb32 - c.base;
+#pragma unroll
+    for (int j = 0; j < PPG_MAX_NJ; ++j) c.rr.tbl[j] += d;
+  }
+  c.base = vb32;
+}
+
+// Rows of the agents that acted: the warps of the CTA take them in pairs from one shared counter PER SPECIES, so a warp
+// that is busy with something else (warp 0: the next env's fetch, the newborn rows) simply takes fewer.  A warp starts
+// with the species whose constants it holds and moves to the other one when nothing is left there.
 template <typename MapT, int KIND>
 __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int old_base[2],
-                                             const int n[2], int* counter, int lane, unsigned& rowctr) {
+                                             const int n[2], int* counter, const RelSmem& rt, RelCache& rc, int lane, unsigned& rowctr) {
   // Rows are handed out in PAIRS of the same species (rows 2 q, 2 q + 1 of the species): two plain rows go through the
   // two-row writer, anything else (the odd last row, skipped / zero / copied / cut-off rows) row by row.
-  const int P0 = (n[0] + 1) >> 1, totalP = P0 + ((n[1] + 1) >> 1);
-  auto grab = [&]() -> int {
-    int q = 0;
-    if (lane == 0) q = atom_shared_add(counter, 1);
-    return __shfl_sync(FULL, q, 0);
-  };
-  int q = grab();
 #pragma unroll 1
-  for (int s = 0; s < 2; ++s) {
-    const int endq = s == 0 ? P0 : totalP;
+  const int first = rc.s;
+  for (int it = 0; it < 2; ++it) {
+    const int s = it == 0 ? first : first ^ 1;
+    const int n_s = s == 0 ? n[0] : n[1], base = s == 0 ? old_base[0] : old_base[1];
+    const int endq = (n_s + 1) >> 1;
+    int* ctr = counter + s;
+    if (*reinterpret_cast<volatile int*>(ctr) >= endq) continue;  // nothing left of this species
+    int q = 0;
+    if (lane == 0) q = atom_shared_add(ctr, 1);
+    q = __shfl_sync(FULL, q, 0);
     if (q >= endq) continue;
-    const RowRel rr = load_rel(p, s, vb32, lane);
-    const int firstq = s == 0 ? 0 : P0, n_s = s == 0 ? n[0] : n[1], base = s == 0 ? old_base[0] : old_base[1];
+    ensure_rel(p, rt, rc, s, vb32, lane);
+    const RowRel& rr = rc.rr;
     const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
     const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
     do {
       int qn = 0;
-      if (lane == 0) qn = atom_shared_add(counter, 1);  // the next pair's index arrives while this one is being written
-      const int ka = 2 * (q - firstq), kb = ka + 1;
+      if (lane == 0) qn = atom_shared_add(ctr, 1);  // the next pair's index arrives while this one is being written
+      const int ka = 2 * q, kb = ka + 1;
       bool done = false;
       if (kb < n_s) {
         const unsigned d0 = dsc[ka], d1 = dsc[kb];
@@ -141,14 +177,14 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
 // newborn rows of an env (one warp): descriptors n[s] .. n[s] + births[s] -> rows new_base[s] ..
 template <typename MapT, int KIND>
 __device__ __forceinline__ void obs_new_rows(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, const int n[2],
-                                             const int births[2], const int new_base[2], int lane, unsigned& rowctr) {
+                                             const int births[2], const int new_base[2], const RelSmem& rt, RelCache& rc, int lane, unsigned& rowctr) {
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
     const int nb = s == 0 ? births[0] : births[1];
     if (nb <= 0) continue;
     const int n_s = s == 0 ? n[0] : n[1], base = s == 0 ? new_base[0] : new_base[1];
-    const RowRel rr = load_rel(p, s, vb32, lane);
-    for (int j = 0; j < nb; ++j) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, n_s + j, base + j, rr, lane, rowctr);
+    ensure_rel(p, rt, rc, s, vb32, lane);
+    for (int j = 0; j < nb; ++j) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, n_s + j, base + j, rc.rr, lane, rowctr);
   }
 }
 
@@ -193,9 +229,14 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
   extern __shared__ __align__(128) unsigned char smem_img[];  // 2 image buffers
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ int s_env[2];
-  __shared__ int s_row[2];  // next row of the env in buffer 0 / 1
+  __shared__ int s_row[2][2];  // next pair of the env in buffer 0 / 1, per species
   __shared__ int s_defer[OBS_MAX_DEFER];
+  __shared__ RelSmem s_rel;  // both species' per-lane gather constants
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // PDL chain: whatever follows in the stream with programmatic serialization (the action kernel of the next step, then its
+  // step kernel) may become resident in the slots this grid leaves free; it blocks in griddepcontrol.wait until this grid
+  // has completed.  All CTAs of this grid are resident (or done) before that can happen, so nothing can starve it.
+  allow_dependent_launch();
   const unsigned stride = (unsigned)p.img_stride, img_bytes = (unsigned)p.img_bytes;
   const unsigned img0 = smem_u32(smem_img), bar0 = smem_u32(&s_bar[0]);
   const unsigned epoch = p.epoch;
@@ -223,12 +264,17 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
     return e;
   };
 
+  {
+    int2* flat = &s_rel.rel[0][0][0];
+    for (int i = tid; i < 2 * PPG_MAX_NJ * 32; i += OBS_WARPS * 32) flat[i] = __ldg(p.obs_rel + i);
+    if (tid < 64) (&s_rel.self[0][0])[tid] = p.obs_self ? __ldg(p.obs_self + tid) : 0u;
+  }
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
-    s_row[0] = 0; s_row[1] = 0;
+    s_row[0][0] = 0; s_row[0][1] = 0; s_row[1][0] = 0; s_row[1][1] = 0;
     s_env[0] = fetch(0, true);
   }
   __syncthreads();
@@ -236,6 +282,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
   unsigned stage = 0, phase = 0;  // bit s of phase: parity the barrier of buffer s completes next
   unsigned rowctr = 0;
   int n_defer = 0;  // warp 0
+  RelCache rc;
+  rc.s = -1; rc.base = 0u;
+  ensure_rel(p, s_rel, rc, warp == 0 ? 0 : 1, img0 - (unsigned)p.so_img, lane);  // warp 0 starts with species 0, the others with species 1
 
   while (env < p.B) {
     // next env: its image streams into the other buffer (all reads of that buffer ended before the last barrier)
@@ -269,19 +318,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
         if (ready) {
           const int new_base[2] = {n_old_total[0] + nb0, n_old_total[1] + nb1};
           obs_newborn_labels(p, env, births, new_base, lane);
-          obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, lane, rowctr);
+          obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, s_rel, rc, lane, rowctr);
         }
       } else if (lane < 2) {
         p.new_off[lane][env] = 0;
       }
     }
 
-    obs_old_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, &s_row[stage], lane, rowctr);
+    obs_old_rows<MapT, KIND>(p, ibp, vb32, env, old_base, n, &s_row[stage][0], s_rel, rc, lane, rowctr);
 
     if (tid == 0) {
       if (nxt < 0) nxt = fetch(stage ^ 1u, true);
       s_env[stage ^ 1u] = nxt;
-      s_row[stage ^ 1u] = 0;  // nobody is using the other buffer's counter between the barriers
+      s_row[stage ^ 1u][0] = 0; s_row[stage ^ 1u][1] = 0;  // nobody is using the other buffer's counters between the barriers
     }
     __syncthreads();  // every read of this buffer is done; the next env is known
     env = s_env[stage ^ 1u];
@@ -318,7 +367,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
     const int births[2] = {ih[IH_BIRTHS0], ih[IH_BIRTHS1]};
     const int new_base[2] = {n_old_total[0] + nb0, n_old_total[1] + nb1};
     obs_newborn_labels(p, env, births, new_base, lane);
-    obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, lane, rowctr);
+    obs_new_rows<MapT, KIND>(p, ibp, vb32, env, n, births, new_base, s_rel, rc, lane, rowctr);
     stage ^= 1u;
   }
 }

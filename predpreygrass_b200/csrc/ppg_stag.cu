@@ -159,6 +159,7 @@ template <int W, typename MapT, bool SPLIT>
 __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_stag_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wait_for_stream_predecessor();  // PDL chain: this grid may have become resident under the tail of the kernel before it
   if (SPLIT) allow_dependent_launch();  // the observation kernel may start filling the SMs' free slots right away
   unsigned char* const sbase = smem_raw + (size_t)warp * p.smem_per_env;
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
@@ -1103,6 +1104,8 @@ __global__ void ppg_random_actions_stag_kernel(const int32_t* __restrict__ n_row
                                                const int32_t* __restrict__ row_agent1, int32_t* act0, int32_t* act1,
                                                unsigned long long seed, unsigned call, unsigned env_base, int t2_pred, int t2_prey,
                                                int ar0, int ar1) {
+  allow_dependent_launch();       // PDL chain (see ppg_random_actions_kernel)
+  wait_for_stream_predecessor();
   const int n0 = n_rows[0] + n_rows[2], n1 = n_rows[1] + n_rows[3];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const int s = i >= n0;
@@ -1125,8 +1128,7 @@ static cudaError_t launch_stag_t(const StepParams& p, int n_cta, size_t smem, cu
     if (e != cudaSuccess) return e;
     attr_bytes = smem;
   }
-  ppg_step_stag_kernel<1, MapT, SPLIT><<<n_cta, 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  return pdl_launch(ppg_step_stag_kernel<1, MapT, SPLIT>, dim3((unsigned)n_cta), dim3(32), smem, stream, p);
 }
 
 cudaError_t launch_step_stag(const StepParams& p, int n_cta, size_t smem, cudaStream_t stream) {
@@ -1154,8 +1156,8 @@ cudaError_t launch_set_tape_reals_stag(StagHdr* shdr, int B, const long long* re
 cudaError_t launch_random_actions_stag(const int32_t* n_rows, const int32_t* re0, const int32_t* ra0, const int32_t* re1, const int32_t* ra1,
                                        int32_t* a0, int32_t* a1, unsigned long long seed, unsigned call, unsigned env_base, int t2_pred,
                                        int t2_prey, int ar0, int ar1, int blocks, cudaStream_t s) {
-  ppg_random_actions_stag_kernel<<<blocks, 256, 0, s>>>(n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, env_base, t2_pred, t2_prey, ar0, ar1);
-  return cudaGetLastError();
+  return pdl_launch(ppg_random_actions_stag_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n_rows, re0, ra0, re1, ra1, a0, a1, seed, call, env_base, t2_pred,
+                    t2_prey, ar0, ar1);
 }
 
 }  // namespace ppg

@@ -195,6 +195,11 @@ __device__ __forceinline__ void dump_image(unsigned char* sbase, const StepParam
 
 // lets a kernel launched with programmatic stream serialization (the observation kernel) start while this one runs
 __device__ __forceinline__ void allow_dependent_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// A kernel launched with programmatic stream serialization (pdl_launch below) may become resident while the kernel before it
+// in the stream is still running; this is where it waits for that kernel to have completed and flushed its writes.  A no-op
+// for a kernel launched without the attribute.  Every step / action kernel executes it before touching global memory.
+__device__ __forceinline__ void wait_for_stream_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 
 // ------------------------------------------------------------------------------------------------
 // observation rows

@@ -35,6 +35,8 @@ class PipelinedPredPreyGrass:
         self.C, self.R = self.envs[0].C, self.envs[0].R
         # one stream per group; a single group stays on the caller's current stream
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.groups)] if self.groups > 1 else [None]
+        if self.groups > 1:
+            self.envs[0].L.ppg_set_pdl_chain(0)  # parked step kernels would hold the slots the other groups' kernels are meant to fill
         self._ev = [torch.cuda.Event() for _ in range(self.groups)]
 
     # ------------------------------------------------------------------ plumbing
