@@ -282,6 +282,7 @@ class PredPreyGrassEco(_RowDictEnv):
     """eco_evolutionary `PredPreyGrass(config)`: heritable speed trait, 25 actions, move cost, ageing, carcasses."""
 
     _variant = VARIANT_ECO
+    _events_supported = True  # per_step_agent_data / agent_event_log (event_log.py) follow eco_evolutionary's energy rules
 
     def __init__(self, config=None):
         super().__init__(config)
@@ -305,9 +306,55 @@ class PredPreyGrassEco(_RowDictEnv):
         self.action_space = DictSpace(self.action_spaces)
         d = (self.action_range - 1) // 2  # ECO:225-232
         self.action_to_move_tuple_agents = {i: (i // self.action_range - d, i % self.action_range - d) for i in range(self.action_range ** 2)}
+        # the exporters of the evaluation scripts (ECO:426-446, 1575-1597); "record_agent_events": False switches them off
+        # (they cost one read-back of the env's agent lists per step)
+        self._events = None
+        if self._events_supported and config.get("record_agent_events", True):
+            from .event_log import EcoEventRecorder
+
+            self._events = EcoEventRecorder(config, self.action_to_move_tuple_agents, self.grid_size, self.speed_distance_threshold)
 
     def _name(self, s, i):
         return f"predator_{i}" if s == 0 else f"prey_{i}"
+
+    def _event_state(self):
+        """{agent: (position, energy, age, genome speed or None, member of dead_prey)} and {cell: (grass id, energy)} of the env"""
+        st = self._read()
+        state = {}
+        for s in range(2):
+            for k, i in enumerate(st["ids"][s]):
+                state[self._name(s, int(i))] = ((int(st["xy"][s][k][0]), int(st["xy"][s][k][1])), float(st["energy"][s][k]), int(st["age"][s][k]),
+                                                float(st["speed"][s][k]) if self.genome_enabled else None,
+                                                bool(st["dead_prey"][k]) if s == 1 else False)
+        grass = {(int(x), int(y)): (f"grass_{k}", float(e)) for k, ((x, y), e) in enumerate(zip(st["grass_xy"], st["grass_energy"]))}
+        return state, grass
+
+    # the reference's attributes (ECO:161-170), read by evaluate_ppo_from_checkpoint_*.py and the renderer's tooltips
+    @property
+    def per_step_agent_data(self):
+        return self._events.per_step_agent_data if self._events else []
+
+    @property
+    def agent_event_log(self):
+        return self._events.agent_event_log if self._events else {}
+
+    @property
+    def agent_parents(self):
+        return self._events.agent_parents if self._events else {}
+
+    @property
+    def agent_offspring_counts(self):
+        return self._events.agent_offspring_counts if self._events else {}
+
+    @property
+    def agent_live_offspring_ids(self):
+        return self._events.agent_live_offspring_ids if self._events else {}
+
+    def export_agent_event_log(self, path):
+        """ECO:1575-1597"""
+        if self._events is None:
+            raise RuntimeError("agent events are not recorded (record_agent_events=False, or a trait variant)")
+        self._events.export(path)
 
     def _n_moves(self, agent):
         return self.action_range ** 2
@@ -331,6 +378,9 @@ class PredPreyGrassEco(_RowDictEnv):
             st = self._read()
             for s in range(2):
                 self._episode_speeds[s].extend(float(v) for v in st["speed"][s])
+        if self._events is not None:
+            state, grass = self._event_state()
+            self._events.reset(state, self.agents, grass)
         return obs, {}
 
     def _dicts(self, out):
@@ -349,9 +399,16 @@ class PredPreyGrassEco(_RowDictEnv):
         return obs, rew, term, trunc
 
     def step(self, action_dict):
+        t = self.current_step
         out = self._step_device(action_dict)
         obs, rew, term, trunc = self._dicts(out)
         flags = int(out["env_flags"][0])
+        if self._events is not None:
+            rows = self._rows_of(out)
+            n_old = sum(int(out[f"old_off{s}"][1]) - int(out[f"old_off{s}"][0]) for s in range(2))
+            newborn = sorted((name for name, s, r, f in rows[n_old:]), key=lambda a: ("prey" in a, int(a.rsplit("_", 1)[1])))
+            state, grass = self._event_state()
+            self._events.step(t, action_dict, {name: f for name, s, r, f in rows}, state, newborn, grass, bool(flags & ENV_TRUNCATED))
         if self.genome_enabled and (int(out["new_cnt0"][0]) or int(out["new_cnt1"][0])):
             st = self._read()  # newborns join the episode's agent records with their (mutated) genome
             by_id = [dict(zip(st["ids"][s].tolist(), st["speed"][s].tolist())) for s in range(2)]
@@ -470,6 +527,7 @@ class _TraitEnv(PredPreyGrassEco):
     random number of founders per episode, ids never reused, `infos["__all__"]["training_metrics"]` at the episode's end."""
 
     _trait = None
+    _events_supported = False  # the trait variants' energy rules differ (rates, investment, meal sharing): no event recorder
     _tolerated_status = 0x10  # PPG_STATUS_ID_POOL_EMPTY: the trait variants print a warning and skip the birth (MR:856-864)
     _tag = None  # prefix of the reproduction-correlation keys (MR:1370-1392, COOP:1396-1418)
 
@@ -664,6 +722,7 @@ class PredPreyGrassCadence(PredPreyGrassEco):
     allows only "stay" on the steps the agent will be frozen (device row flag PPG_ROW_FROZEN)."""
 
     _tolerated_status = 0
+    _events_supported = False
 
     def __init__(self, config=None):
         if config is None:

@@ -1,0 +1,330 @@
+"""Host-side exporters of eco_evolutionary: `per_step_agent_data` (ECO:426-446) and `agent_event_log` (ECO:1488-1500) rebuilt
+from what the device hands back every step.
+
+The reference fills both inside `step()` while it walks its dicts.  The device step keeps none of this (it is analytics of
+the evaluation scripts and the renderer's tooltips), but everything in it follows from the state before the step,
+the state after it and the row flags, because the energy bookkeeping of ECO is a fixed chain per agent:
+
+    E0 --(-basal loss, ECO:597-599)--> E1 --(-move cost, ECO:644-647)--> E2 --(+bite, ECO:812-818 / 903-908)--> E3
+       --(-offspring energy, ECO:1147-1151 / 1243-1247)--> E4
+
+Each link is the reference's own float64 expression evaluated on the host with the same operands, so the deltas come out
+bit-identical; the chain's end is compared with the energy the device reports and a mismatch is counted in
+`inexact_chains` (0 on every recording of tests/golden/eco_events_*.json.gz).  The only thing the device does not report is
+where an agent that died this step stood when it died; a fully eaten prey is therefore matched to its predator through the
+two cells it can have ended on (its move target, or its old cell if the move was blocked), and the match is confirmed by
+the predator's energy.
+
+Not mirrored: `agent_stats_live/completed` (the per-agent totals behind `training_metrics` are device counters,
+`ppg_read_episode_eco`), lineage `reward_events` (the event log is built for `lineage_reward_coeff = 0`).
+"""
+import json
+
+import numpy as np
+
+ROW_TERMINATED, ROW_TRUNCATED, ROW_ATE, ROW_CARCASS, ROW_REPRODUCED = 0x01, 0x02, 0x10, 0x20, 0x40
+
+
+def _role(value, agent):
+    """`_get_role_specific` (ECO:1723-1730): scalars, or dicts keyed by an agent-id prefix"""
+    if isinstance(value, dict):
+        for k in value:
+            if agent.startswith(k):
+                return value[k]
+        raise KeyError(f"Type-specific key '{agent}' not found")
+    return value
+
+
+class EcoEventRecorder:
+    def __init__(self, config, action_to_move, grid_size, speed_distance_threshold):
+        g = config.get
+        self.cfg = config
+        self.loss = (g("energy_loss_per_step_predator"), g("energy_loss_per_step_prey"))
+        self.move_cost = (float(g("movement_energy_cost_per_cell_predator", 0.0)), float(g("movement_energy_cost_per_cell_prey", 0.0)))
+        self.exponent = float(g("movement_speed_cost_exponent", 2.0))  # ECO:81
+        self.grass_gain, self.grass_max = g("energy_gain_per_step_grass"), g("max_energy_grass")
+        self.cap_prey = float(g("max_energy_gain_per_prey", float("inf")))
+        self.cap_grass = float(g("max_energy_gain_per_grass", float("inf")))
+        self.init_e = (float(g("initial_energy_predator")), float(g("initial_energy_prey")))
+        self.max_age = g("max_agent_age", None)
+        self.carcass_age = g("carcass_only_predator_age", None)
+        self.moves, self.G, self.thr = action_to_move, int(grid_size), float(speed_distance_threshold)
+        self.jump_low, self.jump_high = int(g("slow_max_move_distance", 1)), int(g("fast_max_move_distance", 2))  # ECO:551-557
+        self.reset({}, [], {})
+
+    # ---------------------------------------------------------------- helpers (each one the reference's own expression)
+    def _limit(self, caps, agent):
+        if caps is None:
+            return None
+        if isinstance(caps, dict):
+            for prefix, limit in caps.items():
+                if agent.startswith(prefix):
+                    return limit
+            return None
+        return caps
+
+    def _cost(self, agent, s, old, new, speed):
+        """`_get_movement_energy_cost` (ECO:565-573)"""
+        distance = float(np.linalg.norm(np.array(new) - np.array(old)))
+        if distance <= 0:
+            return 0.0
+        factor = 1.0 if speed is None else float(speed) ** self.exponent  # ECO:559-563
+        return self.move_cost[s] * distance * factor
+
+    def _target(self, pos, action, speed):
+        """`_get_move` without the occupancy test (ECO:664-686): the cell the agent moves to unless it is blocked"""
+        mv = self.moves[int(action)]
+        max_d = self.jump_low if (speed is None or float(speed) < self.thr) else self.jump_high
+        if max(abs(mv[0]), abs(mv[1])) > max_d:
+            mv = (int(np.sign(mv[0])) * max_d, int(np.sign(mv[1])) * max_d)
+        return (min(max(pos[0] + mv[0], 0), self.G - 1), min(max(pos[1] + mv[1], 0), self.G - 1))
+
+    # ---------------------------------------------------------------- episode start
+    def reset(self, state, agents, grass):
+        """state: {agent: (pos, energy, age, speed or None, dead)}; grass: {cell: (name, energy)}"""
+        self.per_step_agent_data = []
+        self.agent_event_log = {}
+        self.agent_parents, self.agent_offspring_counts, self.agent_live_offspring_ids = {}, {}, {}
+        self.cumulative_reward = {}
+        self.lineage = {}  # agent -> [parent, live descendants, live descendants at the last reward pass, counted as alive]
+        self.first_bite_step = {}
+        self.inexact_chains = 0
+        self.closed = set()  # agents whose record is finalized (no longer in `agent_stats_live`)
+        self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+        for a in agents:
+            self._register(a, None, 0, state[a][3])
+
+    def _register(self, agent, parent, t, speed):
+        self.agent_parents[agent] = parent
+        self.agent_offspring_counts[agent] = 0
+        self.agent_live_offspring_ids[agent] = []
+        self.cumulative_reward[agent] = 0.0
+        self.lineage[agent] = [parent, 0, 0, False]
+        self._lineage_alive(agent, True)  # `_handle_lineage_birth` (ECO:1462-1466)
+        self.agent_event_log[agent] = {
+            "agent_id": agent, "birth_step": t, "death_step": None, "parent_id": parent, "death_cause": None,
+            "eating_events": [], "reproduction_events": [], "reward_events": [], "diet_events": [], "lifecycle_events": [],
+            "genome": None if speed is None else {"speed": float(speed)},
+        }
+
+    def _lineage_alive(self, agent, alive):
+        """`_set_lineage_alive_flag` + `_propagate_lineage_delta` (ECO:1440-1460): every ancestor, dead or alive, counts the
+        agent among its live descendants while the flag is set"""
+        rec = self.lineage[agent]
+        if rec[3] == alive:
+            return
+        rec[3] = alive
+        cur = rec[0]
+        while cur is not None and cur in self.lineage:
+            self.lineage[cur][1] += 1 if alive else -1
+            cur = self.lineage[cur][0]
+
+    def _finalize(self, agent, cause, step):
+        """the event-log part of `_finalize_agent_record` (ECO:1532-1573); every death path of the reference calls
+        `_handle_lineage_death` first (ECO:764, 1072; a bitten prey at its first bite, ECO:840, 846)"""
+        self._lineage_alive(agent, False)
+        self.closed.add(agent)
+        evt = self.agent_event_log[agent]
+        evt["death_step"] = self.first_bite_step.get(agent, step)
+        evt["death_cause"] = cause
+        self.agent_live_offspring_ids.pop(agent, None)
+
+    # ---------------------------------------------------------------- one step
+    def step(self, t, action_dict, rows, state, newborn, grass, time_limit):
+        """t: `current_step` during the step; rows: {agent: flags} of every row of the step; state / grass: after the step;
+        newborn: this step's newborns in birth order, predators first (the tail of the reference's `self.agents`)"""
+        cfg, prev = self.cfg, self.prev
+        agents = [a for a in self.prev_agents if a in state] + list(newborn)  # ECO:353-367
+        is_pred = lambda a: "predator" in a  # noqa: E731
+        E, deltas, age = {}, {}, {}
+        gone = set()  # terminated so far in this step
+        # Step 1 (ECO:582-614): basal loss, ageing, age cap
+        for a in self.prev_agents:
+            s = 0 if is_pred(a) else 1
+            pos, e0, ag, spd, dead = prev[a]
+            E[a] = e0 - self.loss[s]
+            deltas[a] = {"decay": -self.loss[s], "move": 0.0, "eat": 0.0, "repro": 0.0}
+            age[a] = ag
+            if not (s == 1 and dead):
+                age[a] = ag + 1
+        for a in self.prev_agents:
+            s = 0 if is_pred(a) else 1
+            limit = self._limit(self.max_age, a)
+            if not (s == 1 and prev[a][4]) and isinstance(limit, (int, float)) and limit >= 0 and age[a] >= limit:
+                self.agent_event_log[a]["lifecycle_events"].append({"t": int(t), "event": "max_age_reached", "age": int(age[a])})
+                self._finalize(a, "max_age", t)
+                gone.add(a)
+        # Step 2 (ECO:616-624): grass regrowth
+        g_now = {cell: (name, min(e + self.grass_gain, self.grass_max)) for cell, (name, e) in self.prev_grass.items()}
+        # Step 3 (ECO:626-662): moves.  Survivors: old and new cell are known.  Agents that die in this step: the cells they
+        # can have died on are kept as candidates (cell, energy) — the move target, or the old cell if the move was blocked;
+        # terminated agents (age cap) and carcasses do not move.
+        cand = {}
+        for a, action in action_dict.items():
+            if a not in prev or a in gone or (not is_pred(a) and prev[a][4]):
+                continue
+            s = 0 if is_pred(a) else 1
+            old, spd = prev[a][0], prev[a][3]
+            if a in state:
+                cost = self._cost(a, s, old, state[a][0], spd)
+                E[a] -= cost
+                deltas[a]["move"] -= cost
+            else:
+                tgt = self._target(old, action, spd)
+                cand[a] = [(tgt, E[a] - self._cost(a, s, old, tgt, spd))] + ([(old, E[a])] if tgt != old else [])
+        # Step 4a (ECO:314-319): starvation.  Predators that are gone and not aged out starved.  A prey that is gone stays
+        # on the grid until Step 5, so a predator can still bite it (ECO:789-791 looks at `agent_positions`), whatever it
+        # died of: every prey that is gone keeps its candidates for Step 4c.
+        dead_prey = {}
+        for a in self.prev_agents:
+            if a in state:
+                continue
+            if a not in cand:  # aged out in Step 1 or a carcass: it did not move
+                cand[a] = [(prev[a][0], E[a])]
+            if is_pred(a):
+                if a not in gone:
+                    self._finalize(a, "starved", t)
+                    gone.add(a)
+            else:
+                dead_prey[a] = [{"cell": c, "e": e, "grass": None} for c, e in cand[a]]
+        # Step 4b (ECO:886-939): prey eat grass (not the carcasses, not the terminated ones)
+        for a in self.prev_agents:
+            if is_pred(a) or a in gone:
+                continue
+            if prev[a][4]:
+                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+                continue
+            f = rows.get(a, 0)
+            if a in state and f & ROW_ATE and state[a][0] in g_now:
+                name, ge = g_now[state[a][0]]
+                bite = min(float(ge), self.cap_grass)
+                E[a] += bite
+                deltas[a]["eat"] = bite
+                self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
+                self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": name, "alive_before_bite": True,
+                                                                 "bite_size": float(bite), "energy_after": float(E[a])})
+            elif a in dead_prey and f & ROW_ATE:
+                # ate grass, then was eaten in the same step: on a candidate cell with a patch (and energy left: a starved
+                # prey is terminated before it can eat) the bite raises that candidate's energy
+                for c in dead_prey[a]:
+                    if c["e"] > 0 and c["cell"] in g_now:
+                        name, ge = g_now[c["cell"]]
+                        bite = min(float(ge), self.cap_grass)
+                        c["e"] += bite
+                        c["grass"] = (name, bite)
+            elif a in state:
+                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+        # Step 4c (ECO:775-884): predators
+        prey_at = {state[a][0]: a for a in state if not is_pred(a) and a in prev}
+        eaten = {}
+        for a in self.prev_agents:
+            if not is_pred(a) or a in gone or a not in state:
+                continue
+            f = rows.get(a, 0)
+            pos = state[a][0]
+            gone_here = [(q, c) for q, cs in dead_prey.items() if q not in eaten for c in cs if c["cell"] == pos]
+            if not f & ROW_ATE:
+                q = prey_at.get(pos)
+                was_dead = prev[q][4] if q is not None else False
+                if q is None and gone_here:
+                    q, c = gone_here[0]
+                    was_dead = prev[q][4] and c["e"] > 0  # a carcass that starved left `dead_prey` when it did (ECO:761-763)
+                limit = self._limit(self.carcass_age, a)
+                if q is not None and not was_dead and isinstance(limit, (int, float)) and limit >= 0 and age[a] < limit:
+                    self.agent_event_log[a]["diet_events"].append({"t": int(t), "event": "carcass_only_block", "prey_id": q, "age": int(age[a])})  # ECO:1035-1059
+                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
+                continue
+            # which prey: a bitten one that is still there (carcass), else a prey that is gone and can have stood here
+            q = prey_at.get(pos)
+            if q is not None and state[q][4]:
+                was_dead = prev[q][4]
+                pe = E[q]
+                bite = min(float(pe), self.cap_prey)
+                E[q] = pe - bite
+                if q not in self.first_bite_step:
+                    self.first_bite_step[q] = int(t)  # ECO:836-838: the first bite freezes death_step
+                self._lineage_alive(q, False)  # ECO:839-840
+            else:
+                if not gone_here:
+                    self.inexact_chains += 1
+                    continue
+                want = state[a][1] + (self.init_e[0] if f & ROW_REPRODUCED else 0.0)  # only used to choose between candidates
+                q, c = min(gone_here, key=lambda o: abs((E[a] + min(float(o[1]["e"]), self.cap_prey)) - want))
+                was_dead = prev[q][4] and c["e"] > 0  # a carcass that starved left `dead_prey` when it did (ECO:761-763)
+                bite = min(float(c["e"]), self.cap_prey)
+                eaten[q] = c
+            E[a] += bite
+            deltas[a]["eat"] = bite
+            self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
+            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "alive_before_bite": not was_dead,
+                                                             "bite_size": float(bite), "energy_after": float(E[a])})
+        for q, cs in dead_prey.items():
+            c = eaten.get(q)
+            if c is not None and c["grass"] is not None:  # its last meal (ECO:926-937)
+                self.agent_event_log[q]["eating_events"].append({"t": int(t), "id_eaten": c["grass"][0], "alive_before_bite": True,
+                                                                 "bite_size": float(c["grass"][1]), "energy_after": float(c["e"])})
+            if q in gone:  # aged out: the cause stays (its record was closed in Step 1)
+                continue
+            if c is not None and c["e"] > 0:
+                self._finalize(q, "eaten", t)
+            else:
+                if c is None and all(x["e"] > 0 for x in cs):
+                    self.inexact_chains += 1  # gone, but it can neither have starved nor did a predator take it
+                self._finalize(q, "starved", t)
+            gone.add(q)
+        # Step 6 (ECO:1092-1270): births, predators first; the k-th newborn row of a species belongs to the k-th parent
+        new_agents = list(newborn)
+        for s, role in enumerate(("predator", "prey")):
+            parents = [a for a in self.prev_agents if (is_pred(a) == (s == 0)) and a in state and rows.get(a, 0) & ROW_REPRODUCED]
+            children = [a for a in new_agents if is_pred(a) == (s == 0)]
+            if len(parents) != len(children):
+                self.inexact_chains += 1
+            for par, child in zip(parents, children):
+                self._register(child, par, int(t), state[child][3])
+                self.agent_live_offspring_ids[par].append(child)
+                self.agent_offspring_counts[par] += 1
+                self.agent_event_log[par]["reproduction_events"].append({"t": int(t), "child_id": child})
+                E[par] -= self.init_e[s]
+                deltas[par]["repro"] = -self.init_e[s]
+                r = _role(cfg.get(f"reproduction_reward_{role}", 0.0), par)
+                self.cumulative_reward[par] += r
+                self.agent_event_log[par]["reward_events"].append({"t": int(t), "reproduction_reward": float(r), "lineage_reward": 0.0,
+                                                                   "cumulative_reward": float(self.cumulative_reward[par])})
+                deltas[child] = {"decay": 0.0, "move": 0.0, "eat": 0.0, "repro": 0.0}
+        # Step 6.5 (ECO:943-984): lineage survival rewards of the agents whose record is still open; an event is logged for
+        # every change of the live-descendant count, also when the coefficient (and with it the reward) is zero
+        for a, rec in self.lineage.items():
+            if a in self.closed:
+                continue
+            delta = rec[1] - rec[2]
+            rec[2] = rec[1]
+            if delta == 0:
+                continue
+            reward = _role(cfg.get("lineage_reward_coeff", 0.0), a) * float(delta)
+            if reward != 0:
+                self.cumulative_reward[a] += reward
+            self.agent_event_log[a]["reward_events"].append({"t": int(t), "reproduction_reward": 0.0, "lineage_reward": float(reward),
+                                                             "cumulative_reward": float(self.cumulative_reward[a])})
+        # the chain's end is the device's energy
+        for a in self.prev_agents:
+            if a in state and E[a] != state[a][1]:
+                self.inexact_chains += 1
+        # per_step_agent_data (ECO:426-446); `offspring_ids` is the live list object itself, as in the reference
+        step_data = {}
+        for a in agents:
+            pos, e, ag, spd, dead = state[a]
+            d = deltas[a]
+            step_data[a] = {"position": pos, "energy": e, "energy_decay": d["decay"], "energy_movement": d["move"],
+                            "energy_eating": d["eat"], "energy_reproduction": d["repro"], "age": ag,
+                            "offspring_count": self.agent_offspring_counts[a],
+                            "offspring_ids": self.agent_live_offspring_ids.get(a, []), "parent": self.agent_parents.get(a)}
+        self.per_step_agent_data.append(step_data)
+        if time_limit:  # ECO:478-479: every record still open is closed with the step counter already advanced
+            for a in agents:
+                self._finalize(a, "time_limit", int(t) + 1)
+        self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+
+    def export(self, path):
+        """`export_agent_event_log` (ECO:1575-1597)"""
+        with open(path, "w", encoding="utf-8") as f:
+            json.dump(self.agent_event_log, f, indent=2)

@@ -1,0 +1,68 @@
+"""`per_step_agent_data` (ECO:426-446) and `agent_event_log` (ECO:1488-1500, ...) of the ECO dict adapter against recordings
+of the unmodified reference class (tests/golden/eco_events_*.json.gz, made by tests/golden/make_golden_eco_events.py).
+
+The adapter's host logic is the same on both backends: the CPU test drives it over the C oracle (tests/oracle_batch.py), the
+GPU test over the CUDA library.  Everything is compared for equality — positions, float64 energies, the four energy
+deltas, ages, parents, offspring lists, every event with its step, ids, bite size and energy."""
+import glob
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN_DIR, load_golden
+
+CASES = sorted(os.path.basename(p)[len("eco_events_"):-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "eco_events_*.json.gz")))
+
+
+def _plain(obj):
+    if isinstance(obj, dict):
+        return {str(k): _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    return obj
+
+
+def _replay(case):
+    from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
+
+    z, cfg = load_golden("eco_" + case)
+    cfg.pop("variant")
+    cfg["cap_live"] = (min(cfg["n_possible_predators"], 250), min(cfg["n_possible_prey"], 250))
+    want = json.loads(gzip.open(os.path.join(GOLDEN_DIR, f"eco_events_{case}.json.gz")).read())
+    env = PredPreyGrassEco(cfg)
+    env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    names = ("predator", "prey")
+    for t in range(want["steps"]):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {f"{names[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        env.step(acts)
+    got_steps, got_log = _plain(env.per_step_agent_data), _plain(env.agent_event_log)
+    assert env._events.inexact_chains == 0
+    assert len(got_steps) == len(want["per_step_agent_data"]) == want["steps"]
+    for t, (g, w) in enumerate(zip(got_steps, want["per_step_agent_data"])):
+        assert sorted(g) == sorted(w), (case, t)  # the recording is a JSON object with sorted keys: the order is not in it
+        for a in w:
+            assert g[a] == w[a], (case, t, a, g[a], w[a])
+    assert sorted(got_log) == sorted(want["agent_event_log"]), case
+    for a, w in want["agent_event_log"].items():
+        for k in w:
+            assert got_log[a][k] == w[k], (case, a, k, got_log[a][k], w[k])
+    env.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_event_log_host_logic_over_the_oracle(case, monkeypatch):
+    import predpreygrass_b200.batched as batched
+    from tests.oracle_batch import OracleBatch
+
+    monkeypatch.setattr(batched, "BatchedPredPreyGrass", OracleBatch)
+    _replay(case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_event_log_on_the_device(case):
+    _replay(case)
