@@ -57,34 +57,6 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void* gsrc, unsig
 
 #define OBS_MAX_DEFER 256
 
-// one observation row of an env from its image in shared memory: descriptor k of species s -> global row `row`
-template <typename MapT, int KIND>
-__device__ __forceinline__ void obs_one_row(const StepParams& p, const unsigned char* ibp, unsigned vb32, int env, int s, int k, int row,
-                                            const RowRel& rr, int lane, unsigned& rowctr) {
-  const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
-  const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
-  const unsigned d = dsc[k];
-  if (d == DSC_SKIP) return;  // captured by the step kernel when the agent died
-  const int elems = p.elems[s];
-  float* dst = p.obs[s] + (size_t)row * elems;
-  if (KIND == 1) {
-    if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
-      const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
-      for (int q = lane; q < elems; q += 32) __stcs(dst + q, __ldcg(src + q));  // L2: written by another SM during this launch
-      return;
-    }
-    emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
-  } else if (KIND == 2) {
-    if (d == DSC_ZERO) { zero_row(dst, elems, lane); return; }
-    const unsigned x = dsx[k];
-    const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
-    if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-    else emit_row_masked<MapT>(p, vb32, dst, (int)d, s, ih2, jh2, lane);
-  } else {
-    emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
-  }
-}
-
 // The per-lane gather constants of ONE species are kept by a warp ACROSS envs: loading them from global memory cost ~60
 // instructions and a global round trip per species and env (13 % of the kernel's instructions when every warp reloaded both
 // species for every env, profiles/r02_summary.md).  The CTA holds both species' tables in shared memory (6.6 KB, loaded
@@ -98,7 +70,52 @@ struct RelCache {
 struct RelSmem {
   int2 rel[2][PPG_MAX_NJ][32];
   unsigned self[2][32];
+  unsigned short ij[2][PPG_MAX_NJ][32];  // window row | window column << 8 of the element (STAG: cut-off windows)
 };
+
+// STAG: a row whose window is cut off (saturated forward view, STAG:944-1008): element (c, i, j) is zero unless i <= ihi and
+// j <= jhi.  Straight-line like emit_row_t, the gather constants from the warp's registers, the element's window
+// coordinates from shared memory (the generic emit_row_masked reads its constants from global memory element by element).
+template <typename MapT, int N, bool VEC>
+__device__ __forceinline__ void emit_row_cut_t(const StepParams& p, const RelSmem& t, unsigned sb32, float* dst, int cellp, int s,
+                                               const RowRel& r, int ihi, int jhi, int lane) {
+  const unsigned a0 = sb32 + (unsigned)(p.so_map[0] + cellp * (int)sizeof(MapT));
+  unsigned idx[N];
+  float val[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) idx[j] = lds_map<MapT>(a0 + (unsigned)r.relb[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) val[j] = lds_f32(r.tbl[j] + 4u * idx[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const unsigned m = t.ij[s][j][lane];
+    if ((int)(m & 0xFFu) > ihi || (int)(m >> 8) > jhi) val[j] = 0.f;
+  }
+  const int elems = p.elems[s];
+  if (VEC) {
+    float4* d = reinterpret_cast<float4*>(dst) + lane;
+#pragma unroll
+    for (int v = 0; v < N / 4; ++v)
+      if (4 * (lane + 32 * v) < elems) __stcs(d + 32 * v, make_float4(val[4 * v], val[4 * v + 1], val[4 * v + 2], val[4 * v + 3]));
+  } else {
+    float* d = dst + lane;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (lane + 32 * j < elems) __stcs(d + 32 * j, val[j]);
+  }
+}
+template <typename MapT>
+__device__ __forceinline__ void emit_row_cut(const StepParams& p, const RelSmem& t, unsigned sb32, float* dst, int cellp, int s,
+                                             const RowRel& r, int ihi, int jhi, int lane) {
+  switch (p.emit_kind[s]) {
+    case 1: emit_row_cut_t<MapT, 8, true>(p, t, sb32, dst, cellp, s, r, ihi, jhi, lane); break;
+    case 2: emit_row_cut_t<MapT, 12, true>(p, t, sb32, dst, cellp, s, r, ihi, jhi, lane); break;
+    case 3: emit_row_cut_t<MapT, 13, false>(p, t, sb32, dst, cellp, s, r, ihi, jhi, lane); break;
+    case 4: emit_row_cut_t<MapT, 5, false>(p, t, sb32, dst, cellp, s, r, ihi, jhi, lane); break;
+    case 5: emit_row_cut_t<MapT, 8, false>(p, t, sb32, dst, cellp, s, r, ihi, jhi, lane); break;
+    default: emit_row_masked<MapT>(p, sb32, dst, cellp, s, ihi, jhi, lane);
+  }
+}
 __device__ __forceinline__ void ensure_rel(const StepParams& p, const RelSmem& t, RelCache& c, int s, unsigned vb32, int lane) {
   if (c.s != s) {
     const int nj = p.nj[s];
@@ -118,6 +135,34 @@ __device__ __forceinline__ void ensure_rel(const StepParams& p, const RelSmem& t
     for (int j = 0; j < PPG_MAX_NJ; ++j) c.rr.tbl[j] += d;
   }
   c.base = vb32;
+}
+
+// one observation row of an env from its image in shared memory: descriptor k of species s -> global row `row`
+template <typename MapT, int KIND>
+__device__ __forceinline__ void obs_one_row(const StepParams& p, const RelSmem& rt, const unsigned char* ibp, unsigned vb32, int env, int s, int k,
+                                            int row, const RowRel& rr, int lane, unsigned& rowctr) {
+  const uint16_t* dsc = reinterpret_cast<const uint16_t*>(ibp + (p.so_dsc[s] - p.so_img));
+  const unsigned* dsx = reinterpret_cast<const unsigned*>(ibp + (p.so_dsx[s] - p.so_img));
+  const unsigned d = dsc[k];
+  if (d == DSC_SKIP) return;  // captured by the step kernel when the agent died
+  const int elems = p.elems[s];
+  float* dst = p.obs[s] + (size_t)row * elems;
+  if (KIND == 1) {
+    if (d == DSC_COPY) {  // captured at birth by the step kernel (the episode ended on this step)
+      const float* src = p.born_obs[s] + ((size_t)env * PPG_BORN_K + dsx[k]) * elems;
+      for (int q = lane; q < elems; q += 32) __stcs(dst + q, __ldcg(src + q));  // L2: written by another SM during this launch
+      return;
+    }
+    emit_row<MapT, false, true>(p, vb32, dst, (int)d, s, rr, rowctr, lane, __uint_as_float(dsx[k]));
+  } else if (KIND == 2) {
+    if (d == DSC_ZERO) { zero_row(dst, elems, lane); return; }
+    const unsigned x = dsx[k];
+    const int ih2 = (int)(x & 0xFFu), jh2 = (int)((x >> 8) & 0xFFu);
+    if (ih2 >= p.R[s] - 1 && jh2 >= p.R[s] - 1) emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+    else emit_row_cut<MapT>(p, rt, vb32, dst, (int)d, s, rr, ih2, jh2, lane);
+  } else {
+    emit_row<MapT, false, false>(p, vb32, dst, (int)d, s, rr, rowctr, lane);
+  }
 }
 
 // Rows of the agents that acted: the warps of the CTA take them in pairs from one shared counter PER SPECIES, so a warp
@@ -166,8 +211,8 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
         }
       }
       if (!done) {
-        obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, ka, base + ka, rr, lane, rowctr);
-        if (kb < n_s) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, kb, base + kb, rr, lane, rowctr);
+        obs_one_row<MapT, KIND>(p, rt, ibp, vb32, env, s, ka, base + ka, rr, lane, rowctr);
+        if (kb < n_s) obs_one_row<MapT, KIND>(p, rt, ibp, vb32, env, s, kb, base + kb, rr, lane, rowctr);
       }
       q = __shfl_sync(FULL, qn, 0);
     } while (q < endq);
@@ -184,7 +229,7 @@ __device__ __forceinline__ void obs_new_rows(const StepParams& p, const unsigned
     if (nb <= 0) continue;
     const int n_s = s == 0 ? n[0] : n[1], base = s == 0 ? new_base[0] : new_base[1];
     ensure_rel(p, rt, rc, s, vb32, lane);
-    for (int j = 0; j < nb; ++j) obs_one_row<MapT, KIND>(p, ibp, vb32, env, s, n_s + j, base + j, rc.rr, lane, rowctr);
+    for (int j = 0; j < nb; ++j) obs_one_row<MapT, KIND>(p, rt, ibp, vb32, env, s, n_s + j, base + j, rc.rr, lane, rowctr);
   }
 }
 
@@ -264,11 +309,16 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
     return e;
   };
 
-  {
-    int2* flat = &s_rel.rel[0][0][0];
-    for (int i = tid; i < 2 * PPG_MAX_NJ * 32; i += OBS_WARPS * 32) flat[i] = __ldg(p.obs_rel + i);
-    if (tid < 64) (&s_rel.self[0][0])[tid] = p.obs_self ? __ldg(p.obs_self + tid) : 0u;
+  // both species' gather constants -> shared memory; the loads are in flight while thread 0 draws the first ticket and starts
+  // the first image copy (they were 6 % of the kernel's stall samples when issued and awaited before that)
+  constexpr int REL_N = 2 * PPG_MAX_NJ * 32, REL_IT = (REL_N + OBS_WARPS * 32 - 1) / (OBS_WARPS * 32);
+  int2 rel_tmp[REL_IT];
+#pragma unroll
+  for (int k = 0; k < REL_IT; ++k) {
+    const int i = tid + k * OBS_WARPS * 32;
+    rel_tmp[k] = i < REL_N ? __ldg(p.obs_rel + i) : make_int2(0, 0);
   }
+  const unsigned self_tmp = (tid < 64 && p.obs_self) ? __ldg(p.obs_self + tid) : 0u;
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -276,6 +326,23 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 24 / OBS_WARPS) ppg_obs_kernel
     fence_async_smem();
     s_row[0][0] = 0; s_row[0][1] = 0; s_row[1][0] = 0; s_row[1][1] = 0;
     s_env[0] = fetch(0, true);
+  }
+  {
+    int2* flat = &s_rel.rel[0][0][0];
+    unsigned short* ijf = &s_rel.ij[0][0][0];
+#pragma unroll
+    for (int k = 0; k < REL_IT; ++k) {
+      const int i = tid + k * OBS_WARPS * 32;
+      if (i < REL_N) {
+        flat[i] = rel_tmp[k];
+        if (KIND == 2) {  // only STAG has cut-off windows
+          const int s = i / (PPG_MAX_NJ * 32), j = (i / 32) % PPG_MAX_NJ, l = i & 31;
+          const int R = p.R[s], q = p.obs_vec[s] ? 4 * (l + 32 * (j >> 2)) + (j & 3) : l + 32 * j, r = q % (R * R);
+          ijf[i] = (unsigned short)((r / R) | ((r % R) << 8));
+        }
+      }
+    }
+    if (tid < 64) (&s_rel.self[0][0])[tid] = self_tmp;
   }
   __syncthreads();
   int env = s_env[0];
