@@ -19,6 +19,8 @@ elif which == "add":
 elif which == "eco":
     cfg = make_config(dict(ECO_CONFIG, max_steps=25, energy_gain_per_step_grass=0.3, prey_creation_energy_threshold=5.0,
                            predator_creation_energy_threshold=8.0, max_energy_gain_per_prey=2.0), variant=VARIANT_ECO, cap_live=(64, 128), seed=3)
+elif which == "eco_lean":  # the shipped config: the step kernel without the carcass / ghost-cell / juvenile code (ppg_eco.cu KIND 3)
+    cfg = make_config(dict(ECO_CONFIG, max_steps=25), variant=VARIANT_ECO, cap_live=(64, 128), seed=3)
 elif which in ("metabolic", "investment", "cooperation", "cadence"):
     from predpreygrass_b200.config import TRAIT_CONFIGS  # noqa: E402
 
