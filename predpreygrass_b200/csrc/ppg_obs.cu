@@ -173,8 +173,8 @@ __device__ __forceinline__ void obs_old_rows(const StepParams& p, const unsigned
                                              const int n[2], int* counter, const RelSmem& rt, RelCache& rc, int lane, unsigned& rowctr) {
   // Rows are handed out in PAIRS of the same species (rows 2 q, 2 q + 1 of the species): two plain rows go through the
   // two-row writer, anything else (the odd last row, skipped / zero / copied / cut-off rows) row by row.
-#pragma unroll 1
   const int first = rc.s;
+#pragma unroll 1
   for (int it = 0; it < 2; ++it) {
     const int s = it == 0 ? first : first ^ 1;
     const int n_s = s == 0 ? n[0] : n[1], base = s == 0 ? old_base[0] : old_base[1];
