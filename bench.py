@@ -411,6 +411,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound = 0
+    if world > 1 and os.environ.get("PPG_BENCH_BIND", "1") != "0":
+        from predpreygrass_b200.sharding import bind_to_gpu_locality
+
+        bound = bind_to_gpu_locality(local_rank)  # pinned e2e buffers on the GPU's own NUMA node
+        print(f"[bench] rank {rank}: bound to {bound} cores next to GPU {local_rank}", file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), args.steps
@@ -449,7 +455,7 @@ def main():
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": cfgb, "groups": args.groups, "l2_note": res["l2_note"],
+            "config": cfgb, "groups": args.groups, "host_cores_bound": bound, "l2_note": res["l2_note"],
             "env_steps_per_s": res["env_steps_per_s"],
             "mean_live_agents_per_env": res["mean_live_agents_per_env"],
             "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": res.get("e2e"), "e2e_device_policy": res.get("e2e_device_policy"),

@@ -23,6 +23,31 @@ def global_env_index(local_env, rank, n_envs_total, world_size):
     return shard_range(n_envs_total, rank, world_size)[0] + local_env
 
 
+def bind_to_gpu_locality(device_index):
+    """Pin the calling process to the CPU cores next to GPU `device_index` (NVML's ideal affinity), so that pinned host buffers
+    allocated afterwards are first-touched on the GPU's own NUMA node and the rank's device->host copies do not cross sockets
+    (one process per GPU on an 8-GPU box).  Returns the number of cores bound to, or 0 if NVML is not available — then
+    nothing changes."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cores &= set(os.sched_getaffinity(0))
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:  # noqa: BLE001 — locality is an optimisation, never a requirement
+        return 0
+
+
 def allreduce_stats(stats, group=None):
     """Sum the PPG_N_STATS vector over all ranks in place (int64 tensor on the rank's device; with the
     nccl backend this is `BatchedPredPreyGrass.stats_device()` as is).  Returns a name -> int dict."""
