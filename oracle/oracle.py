@@ -55,6 +55,7 @@ def lib():
         L.ppgo_read_env_eco.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         L.ppgo_env_reset_trait.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_acc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ppgo_read_episode_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
@@ -156,6 +157,12 @@ class Oracle:
         st.update(age=(age[0][: n[0]], age[1][: n[1]]), speed=(sp[0][: n[0]], sp[1][: n[1]]), dead_prey=dead[: n[1]],
                   active_num=act)
         return st
+
+    def read_episode_eco(self, env):
+        """per-episode totals of one ECO env (the dict of BatchedPredPreyGrass.read_episode_eco)"""
+        sums, sp = np.zeros(4, np.float64), np.zeros(2, np.int32)
+        assert lib().ppgo_read_episode_eco(self.h, env, sums.ctypes.data, sp.ctypes.data) == 0
+        return {"distance": (float(sums[0]), float(sums[1])), "move_energy": (float(sums[2]), float(sums[3])), "spawned": (int(sp[0]), int(sp[1]))}
 
     def env_reset_stag(self, env, cells, facing, trait_raw):
         c = np.ascontiguousarray(cells, np.int32)

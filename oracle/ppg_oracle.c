@@ -899,6 +899,15 @@ int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* spe
   return PPG_OK;
 }
 
+/* per-episode totals of one ECO env, the layout of ppg_read_episode_eco (include/ppg.h; ECO:1613-1661) */
+int ppgo_read_episode_eco(ppgo_batch* b, int32_t env, double* sums, int32_t* spawned) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;
+  const env_t* v = &b->envs[env];
+  if (sums) for (int k = 0; k < 4; ++k) sums[k] = v->ep_sums[k];
+  if (spawned) { spawned[0] = v->ep_spawned[0]; spawned[1] = v->ep_spawned[1]; }
+  return PPG_OK;
+}
+
 /* CAD: agent_move_accumulator (CAD:183-186) of one env, in the order of ppgo_read_env_eco */
 int ppgo_read_env_acc(ppgo_batch* b, int32_t env, double* acc_pred, double* acc_prey) {
   if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;

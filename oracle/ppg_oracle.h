@@ -69,6 +69,9 @@ int ppgo_env_reset_eco(ppgo_batch* b, int32_t env, const int32_t* cells, const d
 /* trait variants (MR / INV / COOP): reset one env with an explicit founder count per species, cells and founder traits */
 int ppgo_env_reset_trait(ppgo_batch* b, int32_t env, int32_t n_pred, int32_t n_prey, const int32_t* cells, const double* founder_trait);
 /* CAD: the move accumulators of one env, in the order of ppgo_read_env_eco */
+/* per-episode totals of one ECO env in the layout of ppg_read_episode_eco (include/ppg.h): sums[4] = distance pred / prey, locomotion
+ * energy pred / prey; spawned[2] = births so far (ECO:1613-1661) */
+int ppgo_read_episode_eco(ppgo_batch* b, int32_t env, double* sums, int32_t* spawned);
 int ppgo_read_env_acc(ppgo_batch* b, int32_t env, double* acc_pred, double* acc_prey);
 /* agent_ages / genome speeds / dead_prey / active_num_* of one env, in the list order of ppgo_read_env */
 int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,

@@ -208,6 +208,8 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
   e->env_flags = PPG_ENV_RESET;
   e->needs_reset = 0; e->idle = 0; e->status = 0;
   e->spawn_draws = 0;
+  for (int k = 0; k < 4; ++k) e->ep_sums[k] = 0.0;
+  e->ep_spawned[0] = e->ep_spawned[1] = 0;
 }
 
 /* lockstep reset: founder speeds then cells, from the tape or the Philox streams */
@@ -637,6 +639,7 @@ static void handle_reproduction(env_t* e, int s, int id) {
   *GF(e, s, sx, sy) = (float)child_e;                  /* ECO:1154 */
   *GF(e, s, e->x[s][id], e->y[s][id]) = (float)e->energy[s][id]; /* ECO:1155 */
   e->active[s] += 1;                                   /* ECO:1157 */
+  e->ep_spawned[s] += 1;                               /* ECO:1168 offspring_count of the parent's record */
   e->rew[ci] = 0.0; e->has_rew[ci] = 1;                /* ECO:1160 */
   e->rew[i] = c->reproduction_reward[s]; e->has_rew[i] = 1; /* ECO:1161 */
   e->repro[i] = 1;                                     /* ECO:1168 agent_offspring_counts[agent] += 1 */
@@ -711,6 +714,7 @@ int eco_env_step(env_t* e, int n_act, const int32_t* a_s, const int32_t* a_id, c
     double cost = 0.0;
     if (dist > 0) cost = c->move_cost_per_cell[s] * dist * speed_cost_factor(e, e->speed[s][id]);
     e->energy[s][id] -= cost;
+    e->ep_sums[s] += dist; e->ep_sums[2 + s] += cost; /* ECO:659-660 */
     *GF(e, s, ox, oy) = 0;
     *GF(e, s, nx, ny) = (float)e->energy[s][id];
     e->x[s][id] = (int16_t)nx; e->y[s][id] = (int16_t)ny;

@@ -82,6 +82,10 @@ typedef struct env_t {
   int n_found[2];     /* founders of the running episode (MR:189-192) */
   int32_t* sat_until; /* agent_satiation_until by predator id (MR:134,756-757) */
   double* acc[2];     /* CAD: agent_move_accumulator by id (CAD:183-186) */
+  /* per-episode totals behind _build_episode_training_metrics (ECO:1613-1661): distance moved and locomotion energy of all
+   * agents of a species (the sums of record["distance_traveled"] / record["movement_energy_spent"], ECO:659-660), births */
+  double ep_sums[4];
+  int32_t ep_spawned[2];
   /* ECO lineage_tracker by id (ECO:1422-1470): parent (-1: founder), live_descendants, prev_live_descendants, is_alive_descendant */
   int32_t* lin_parent[2];
   int32_t* lin_live[2];

@@ -24,7 +24,13 @@ class OracleBatch:
         self.o.reset(seeds, mask)
 
     def outputs_numpy(self):
-        return self.o.outputs()
+        out = self.o.outputs()
+        # The oracle's literal single-env interface follows BASE's own protocol (the step after max_steps real steps is the
+        # truncation call, BASE:228-238); the batch interface of include/ppg.h flags the env on the max_steps-th step
+        # itself (PPG_ENV_TRUNCATED) and the adapter plays the extra call.  Bridge the two for the BASE family.
+        if self.cfg.variant == 0 and self.cfg.max_steps > 0 and int(out["env_step"][0]) >= self.cfg.max_steps and not out["env_flags"][0] & 1:
+            out["env_flags"][0] |= 2
+        return out
 
     def step_ordered(self, a0, a1, ord0, ord1):
         out = self.o.outputs()
@@ -43,4 +49,13 @@ class OracleBatch:
         return self.o.read_env_eco(env)
 
     def read_episode_eco(self, env):
-        return {"distance": (0.0, 0.0), "move_energy": (0.0, 0.0), "spawned": (0, 0)}
+        return self.o.read_episode_eco(env)
+
+    def read_env(self, env):
+        return self.o.read_env(env)
+
+    def read_env_stag(self, env):
+        return self.o.read_env_stag(env)
+
+    def read_env_acc(self, env):
+        return self.o.read_env_acc(env)
