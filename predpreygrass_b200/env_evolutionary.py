@@ -350,6 +350,24 @@ class PredPreyGrassEco(_RowDictEnv):
     def agent_live_offspring_ids(self):
         return self._events.agent_live_offspring_ids if self._events else {}
 
+    def get_state_snapshot(self):
+        """ECO:1277-1330: the snapshot carries the exporters' state as well"""
+        import copy
+
+        snap = super().get_state_snapshot()
+        snap["events"] = copy.deepcopy(self._events)
+        snap["episode_speeds"] = copy.deepcopy(getattr(self, "_episode_speeds", None))
+        return snap
+
+    def restore_state_snapshot(self, snapshot):
+        import copy
+
+        super().restore_state_snapshot(snapshot)
+        if "events" in snapshot:
+            self._events = copy.deepcopy(snapshot["events"])
+        if snapshot.get("episode_speeds") is not None:
+            self._episode_speeds = copy.deepcopy(snapshot["episode_speeds"])
+
     def export_agent_event_log(self, path):
         """ECO:1575-1597"""
         if self._events is None:

@@ -66,3 +66,36 @@ def test_event_log_host_logic_over_the_oracle(case, monkeypatch):
 @pytest.mark.parametrize("case", CASES)
 def test_event_log_on_the_device(case):
     _replay(case)
+
+
+@pytest.mark.gpu
+def test_snapshot_restore_carries_the_exporters():
+    """get_state_snapshot / restore_state_snapshot (ECO:1277-1376) of the dict adapter: the steps after a restore reproduce the
+    steps after the snapshot, exporters included"""
+    from predpreygrass_b200.env_evolutionary import PredPreyGrassEco
+
+    z, cfg = load_golden("eco_default_s1")
+    cfg.pop("variant")
+    cfg["cap_live"] = (min(cfg["n_possible_predators"], 250), min(cfg["n_possible_prey"], 250))
+    env = PredPreyGrassEco(cfg)
+    env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    names = ("predator", "prey")
+
+    def acts(t):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        return {f"{names[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+
+    for t in range(20):
+        env.step(acts(t))
+    snap = env.get_state_snapshot()
+    first = [env.step(acts(t)) for t in range(20, 30)]
+    data1, log1 = _plain(env.per_step_agent_data), _plain(env.agent_event_log)
+    env.restore_state_snapshot(snap)
+    assert len(env.per_step_agent_data) == 20
+    second = [env.step(acts(t)) for t in range(20, 30)]
+    for (o1, r1, t1, u1, _), (o2, r2, t2, u2, _) in zip(first, second):
+        assert list(o1) == list(o2) and r1 == r2 and t1 == t2 and u1 == u2
+        assert all(np.array_equal(o1[k], o2[k]) for k in o1)
+    assert _plain(env.per_step_agent_data) == data1 and _plain(env.agent_event_log) == log1
+    assert env._events.inexact_chains == 0
+    env.close()
