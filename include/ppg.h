@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 9
+#define PPG_ABI_VERSION 10
 
 /* species index used throughout */
 #define PPG_PREDATOR 0
@@ -406,6 +406,15 @@ int ppg_read_env_acc(ppg_handle h, int32_t env, double* acc_pred, double* acc_pr
  * (record["movement_energy_spent"], ECO:660); spawned[2] = agents born so far per species (= the sum of
  * record["offspring_count"], ECO:1168,1262; the species' record count is founders + spawned).  Synchronises. */
 int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawned);
+
+/* Trait variants (MR / INV / COOP), valid with ppg_config.track_episode_sums: the event counters of the running episode that
+ * `_build_episode_training_metrics` reports — events[6] = {reproduction_blocked_due_to_capacity_predator, _prey (id pool
+ * exhausted: MR:857,943 -> "predator_reproduction_blocked", "prey_reproduction_blocked", MR:1347-1348),
+ * reproduction_blocked_due_to_density_predator (MR:852 -> "predator_reproduction_blocked_density", MR:1349),
+ * satiation_blocked_catches_predator (MR:739 -> "predator_satiation_blocked_catches", MR:1350),
+ * total_energy_donated["predator"], ["prey"] (= total_energy_received; COOP:585-586 -> "*_energy_donated_total",
+ * "*_energy_received_total", COOP:1365-1368), accumulated in the reference's order}.  Synchronises. */
+int ppg_read_episode_events_eco(ppg_handle h, int32_t env, double* events);
 
 /* STAG extras of one env (STAG attributes agent_ages, predator_facing as an index into `_predator_facing_options`
  * STAG:197-206, predator_cooperation_trait), in the list order of ppg_read_env, plus the team-capture counters

@@ -56,6 +56,7 @@ def lib():
         L.ppgo_env_reset_trait.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_acc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ppgo_read_episode_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ppgo_read_episode_events_eco.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ppgo_env_reset_stag.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ppgo_read_env_stag.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         _lib = L
@@ -163,6 +164,13 @@ class Oracle:
         sums, sp = np.zeros(4, np.float64), np.zeros(2, np.int32)
         assert lib().ppgo_read_episode_eco(self.h, env, sums.ctypes.data, sp.ctypes.data) == 0
         return {"distance": (float(sums[0]), float(sums[1])), "move_energy": (float(sums[2]), float(sums[3])), "spawned": (int(sp[0]), int(sp[1]))}
+
+    def read_episode_events_eco(self, env):
+        """event counters of one trait-variant env (the dict of BatchedPredPreyGrass.read_episode_events_eco)"""
+        ev = np.zeros(6, np.float64)
+        assert lib().ppgo_read_episode_events_eco(self.h, env, ev.ctypes.data) == 0
+        return {"blocked_capacity": (int(ev[0]), int(ev[1])), "blocked_density": int(ev[2]), "satiation_blocked": int(ev[3]),
+                "donated": (float(ev[4]), float(ev[5]))}
 
     def env_reset_stag(self, env, cells, facing, trait_raw):
         c = np.ascontiguousarray(cells, np.int32)

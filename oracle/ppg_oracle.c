@@ -908,6 +908,13 @@ int ppgo_read_episode_eco(ppgo_batch* b, int32_t env, double* sums, int32_t* spa
   return PPG_OK;
 }
 
+/* the trait variants' event counters of one env, the layout of ppg_read_episode_events_eco (include/ppg.h; MR:1347-1350, COOP:1365-1368) */
+int ppgo_read_episode_events_eco(ppgo_batch* b, int32_t env, double* events) {
+  if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO || !events) return PPG_ERR_INVALID;
+  for (int k = 0; k < 6; ++k) events[k] = b->envs[env].ep_events[k];
+  return PPG_OK;
+}
+
 /* CAD: agent_move_accumulator (CAD:183-186) of one env, in the order of ppgo_read_env_eco */
 int ppgo_read_env_acc(ppgo_batch* b, int32_t env, double* acc_pred, double* acc_prey) {
   if (env < 0 || env >= b->n_envs || b->cfg.variant != PPG_VARIANT_ECO) return PPG_ERR_INVALID;

@@ -72,6 +72,8 @@ int ppgo_env_reset_trait(ppgo_batch* b, int32_t env, int32_t n_pred, int32_t n_p
 /* per-episode totals of one ECO env in the layout of ppg_read_episode_eco (include/ppg.h): sums[4] = distance pred / prey, locomotion
  * energy pred / prey; spawned[2] = births so far (ECO:1613-1661) */
 int ppgo_read_episode_eco(ppgo_batch* b, int32_t env, double* sums, int32_t* spawned);
+/* the trait variants' event counters in the layout of ppg_read_episode_events_eco (include/ppg.h): events[6] */
+int ppgo_read_episode_events_eco(ppgo_batch* b, int32_t env, double* events);
 int ppgo_read_env_acc(ppgo_batch* b, int32_t env, double* acc_pred, double* acc_prey);
 /* agent_ages / genome speeds / dead_prey / active_num_* of one env, in the list order of ppgo_read_env */
 int ppgo_read_env_eco(ppgo_batch* b, int32_t env, int32_t* age_pred, double* speed_pred, int32_t* age_prey,

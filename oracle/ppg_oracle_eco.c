@@ -209,6 +209,7 @@ void eco_env_reset_explicit(env_t* e, const int32_t* cells, const double* founde
   e->needs_reset = 0; e->idle = 0; e->status = 0;
   e->spawn_draws = 0;
   for (int k = 0; k < 4; ++k) e->ep_sums[k] = 0.0;
+  for (int k = 0; k < 6; ++k) e->ep_events[k] = 0.0;
   e->ep_spawned[0] = e->ep_spawned[1] = 0;
 }
 
@@ -410,6 +411,7 @@ static double coop_donation(env_t* e, int s, int id, double gain) {
   }
   if (n == 0) return gain;
   const double total = rate * gain, share = total / n;
+  e->ep_events[4 + s] += total;                                       /* COOP:585-586 */
   for (int q = 0; q < e->next_idx[s]; ++q) {
     if (q == id || !e->present[s][q] || e->termd[s][q]) continue;
     const int dx = abs(e->x[s][q] - px), dy = abs(e->y[s][q] - py);
@@ -452,8 +454,10 @@ static void trait_predator_engagement(env_t* e, int id) {
   for (int q = 0; q < e->next_idx[1]; ++q)
     if (e->present[1][q] && e->x[1][q] == px && e->y[1][q] == py) { caught = q; break; }
   if (caught >= 0 && c->satiation_cooldown >= 0 && (c->trait_mode == PPG_TRAIT_METABOLIC || c->trait_mode == PPG_TRAIT_INVESTMENT) &&
-      e->current_step < e->sat_until[id])
+      e->current_step < e->sat_until[id]) {
+    e->ep_events[3] += 1.0; /* satiation_blocked_catches_predator (MR:739) */
     caught = -1; /* still digesting (MR:734-740) */
+  }
   if (caught < 0) { e->rew[i] = c->reward_predator_step; e->has_rew[i] = 1; return; }
   const int j = e->list_index[1][caught];
   e->ate[i] = 1;
@@ -585,10 +589,16 @@ static void handle_reproduction(env_t* e, int s, int id) {
   if (s == 1 && e->dead[id]) return;                             /* ECO:1192-1193 */
   if (!(e->energy[s][id] >= c->creation_threshold[s])) return;    /* ECO:1100,1195 */
   if (s == 0 && c->trait_mode == PPG_TRAIT_METABOLIC && c->repro_max_ratio >= 0.0 &&
-      (double)e->active[0] >= c->repro_max_ratio * (double)e->active[1])
+      (double)e->active[0] >= c->repro_max_ratio * (double)e->active[1]) {
+    e->ep_events[2] += 1.0; /* reproduction_blocked_due_to_density_predator (MR:852) */
     return; /* density-dependent soft cap (MR:843-854) */
+  }
   /* ECO: SystemExit (ECO:1104-1111); the trait variants print a warning and skip the birth (MR:856-864) */
-  if (e->next_idx[s] >= c->n_possible[s]) { e->status |= PPG_STATUS_ID_POOL_EMPTY; return; }
+  if (e->next_idx[s] >= c->n_possible[s]) {
+    e->status |= PPG_STATUS_ID_POOL_EMPTY;
+    if (c->trait_mode != PPG_TRAIT_SPEED) e->ep_events[s] += 1.0; /* reproduction_blocked_due_to_capacity_* (MR:857,943) */
+    return;
+  }
   if (c->cap_live[s] > 0) { /* device slot capacity (not in the reference) */
     int cnt = 0;
     for (int k = 0; k < e->n_rows; ++k) cnt += (KEY_S(e->row_key[k]) == s);

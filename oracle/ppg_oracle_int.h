@@ -85,6 +85,9 @@ typedef struct env_t {
   /* per-episode totals behind _build_episode_training_metrics (ECO:1613-1661): distance moved and locomotion energy of all
    * agents of a species (the sums of record["distance_traveled"] / record["movement_energy_spent"], ECO:659-660), births */
   double ep_sums[4];
+  /* trait variants' event counters in the layout of ppg_read_episode_events_eco (include/ppg.h): births blocked by the id pool
+   * [2] (MR:857,943), by the density cap (MR:852), catches blocked by satiation (MR:739), energy donated [2] (COOP:585-586) */
+  double ep_events[6];
   int32_t ep_spawned[2];
   /* ECO lineage_tracker by id (ECO:1422-1470): parent (-1: founder), live_descendants, prev_live_descendants, is_alive_descendant */
   int32_t* lin_parent[2];

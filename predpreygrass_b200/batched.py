@@ -301,6 +301,14 @@ class BatchedPredPreyGrass:
         _lib.check(self.L.ppg_read_episode_eco(self.h, env, sums.ctypes.data, sp.ctypes.data), self.h)
         return {"distance": (float(sums[0]), float(sums[1])), "move_energy": (float(sums[2]), float(sums[3])), "spawned": (int(sp[0]), int(sp[1]))}
 
+    def read_episode_events_eco(self, env):
+        """event counters of the running episode of one trait-variant env (include/ppg.h ppg_read_episode_events_eco):
+        -> {"blocked_capacity": (pred, prey), "blocked_density": n, "satiation_blocked": n, "donated": (pred, prey)}"""
+        ev = np.zeros(6, np.float64)
+        _lib.check(self.L.ppg_read_episode_events_eco(self.h, env, ev.ctypes.data), self.h)
+        return {"blocked_capacity": (int(ev[0]), int(ev[1])), "blocked_density": int(ev[2]), "satiation_blocked": int(ev[3]),
+                "donated": (float(ev[4]), float(ev[5]))}
+
     def read_env_stag(self, env):
         """read_env (lists in `self.agents` insertion order) plus the STAG attributes agent_ages, predator_facing (index into
         `_predator_facing_options`, STAG:197-206), predator_cooperation_trait and the team-capture counters (STAG:237-254)."""

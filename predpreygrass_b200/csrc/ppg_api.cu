@@ -531,7 +531,7 @@ int ppg_create(const ppg_config* cfg, int32_t n_envs, int32_t device, ppg_handle
   }
   if (eco) {
     CKC(dalloc(h, &P.ehdr, (size_t)B));
-    if (c.track_episode_sums) CKC(dalloc(h, &P.ep_sums, (size_t)B * 4));
+    if (c.track_episode_sums) CKC(dalloc(h, &P.ep_sums, (size_t)B * PPG_EP_STRIDE));
     CKC(dalloc(h, &P.gh_n, (size_t)B)); CKC(dalloc(h, &P.gh_cell, (size_t)B * PPG_MAX_GHOSTS)); CKC(dalloc(h, &P.gh_val, (size_t)B * PPG_MAX_GHOSTS));
   }
   if (stag) CKC(dalloc(h, &P.shdr, (size_t)B));
@@ -874,7 +874,7 @@ static std::vector<Seg> state_segments(ppg_handle h) {
   if (P.variant == PPG_VARIANT_STAG) v.push_back({P.shdr, sizeof(StagHdr) * (size_t)h->B});
   if (P.variant == PPG_VARIANT_ECO) {
     v.push_back({P.ehdr, sizeof(EcoHdr) * (size_t)h->B});
-    if (P.ep_sums) v.push_back({P.ep_sums, (size_t)h->B * 4 * 8});
+    if (P.ep_sums) v.push_back({P.ep_sums, (size_t)h->B * PPG_EP_STRIDE * 8});
     v.push_back({P.gh_n, (size_t)h->B}); v.push_back({P.gh_cell, (size_t)h->B * PPG_MAX_GHOSTS * 2}); v.push_back({P.gh_val, (size_t)h->B * PPG_MAX_GHOSTS * 4});
   }
   v.push_back({P.gr_pos, (size_t)h->B * std::max(1, P.n_grass) * 2});
@@ -1042,10 +1042,19 @@ int ppg_read_episode_eco(ppg_handle h, int32_t env, double* sums, int32_t* spawn
   CK(cudaDeviceSynchronize());
   EnvHdr hd;
   CK(cudaMemcpy(&hd, h->P.hdr + env, sizeof hd, cudaMemcpyDeviceToHost));
-  if (sums) CK(cudaMemcpy(sums, h->P.ep_sums + (size_t)env * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sums) CK(cudaMemcpy(sums, h->P.ep_sums + (size_t)env * PPG_EP_STRIDE, 4 * sizeof(double), cudaMemcpyDeviceToHost));
   // ids are handed out in order and never reused (ECO:260-272): spawned = ids used - founders of the running episode
   const bool rf = ppg_random_founders(h->P.trait_mode);
   if (spawned) for (int s = 0; s < 2; ++s) spawned[s] = (int32_t)hd.next_idx[s] - (rf ? (s == 0 ? (hd.pad[1] & 0xFFFF) : ((hd.pad[1] >> 16) & 0x7FFF)) : h->P.n_init[s]);
+  return PPG_OK;
+}
+
+int ppg_read_episode_events_eco(ppg_handle h, int32_t env, double* events) {
+  if (!h || env < 0 || env >= h->B || !events) return PPG_ERR_INVALID;
+  if (h->P.variant != PPG_VARIANT_ECO || !h->P.ep_sums) { h->err = "ppg_read_episode_events_eco: needs an ECO handle created with track_episode_sums"; return PPG_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(events, h->P.ep_sums + (size_t)env * PPG_EP_STRIDE + PPG_EP_BLOCKED_CAPACITY, 6 * sizeof(double), cudaMemcpyDeviceToHost));
   return PPG_OK;
 }
 

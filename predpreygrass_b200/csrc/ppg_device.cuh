@@ -82,6 +82,11 @@ enum { IH_OLD_BASE0 = 0, IH_OLD_BASE1, IH_N0, IH_N1, IH_BIRTHS0, IH_BIRTHS1, IH_
 #define DSC_SKIP 0xFFFFu  // the row was written by the step kernel (captured at the moment of death / birth)
 #define DSC_ZERO 0xFFFEu  // STAG: ended agents are observed as all-zero rows
 #define DSC_COPY 0xFFFDu  // ECO: the row was captured at birth into born_obs[env][dsx] (episode ended on this step, ECO:417-420)
+#define PPG_EP_STRIDE 12            // doubles per env in StepParams::ep_sums
+#define PPG_EP_BLOCKED_CAPACITY 4   // [2] births skipped because the id pool was exhausted (MR:857,943)
+#define PPG_EP_BLOCKED_DENSITY 6    // predator births skipped by the density cap (MR:852)
+#define PPG_EP_SATIATION_BLOCKED 7  // catches skipped while digesting (MR:739)
+#define PPG_EP_DONATED 8            // [2] energy donated = received per species (COOP:585-586)
 #define PPG_BORN_K 4      // at-birth rows kept per env and species; further ones take the (blocking) direct path
 #define PPG_MAX_GHOSTS 16 // ECO: stale prey-channel cells carried per env (ppg_eco.cu header); more raise PPG_STATUS_GHOST_CELL
 
@@ -195,7 +200,8 @@ struct StepParams {
   int max_cooldown, so_acc[2];
   double meta_coeff;
   double* ag_acc[2];
-  double* ep_sums;     // [B][4] optional (ppg_config.track_episode_sums): per-episode distance moved [2], locomotion energy [2]
+  double* ep_sums;     // [B][PPG_EP_STRIDE] optional (ppg_config.track_episode_sums): per-episode distance moved [2], locomotion energy [2],
+                       // then the trait variants' event counters at PPG_EP_BLOCKED_CAPACITY ... (ppg_read_episode_events_eco)
   uint8_t* gh_n;       // [B] ghost cells of the env (ppg_eco.cu header)
   uint16_t* gh_cell;   // [B][PPG_MAX_GHOSTS] packed position x << 8 | y
   float* gh_val;       // [B][PPG_MAX_GHOSTS] the stale float32 grid value

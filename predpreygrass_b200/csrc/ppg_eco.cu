@@ -153,7 +153,7 @@ __device__ __forceinline__ unsigned next_in_seq_order(const uint16_t* const seq[
 // cooperation_range; every receiver's cell is re-written (COOP:573: of co-located receivers the later one in
 // `predator_positions` / `prey_positions` order — the higher slot — shows).  Returns what the donor keeps.
 template <typename MapT>
-__device__ __noinline__ double coop_donation(unsigned char* sbase, const StepParams& p, int s, int slot, int n_s, double gain, int lane) {
+__device__ __noinline__ double coop_donation(unsigned char* sbase, const StepParams& p, int s, int slot, int n_s, double gain, int lane, double* donated) {
   const EnvSmem<MapT> S = carve<MapT>(sbase, p);
   const EcoSmem<MapT> X = carve_eco<MapT>(sbase, p);
   const int PP = p.P, PS = p.PS;
@@ -174,6 +174,7 @@ __device__ __noinline__ double coop_donation(unsigned char* sbase, const StepPar
   }
   if (cnt == 0) return gain;
   const double total = rate * gain, share = total / (double)cnt;
+  if (donated != nullptr && lane == 0) *donated += total;  // total_energy_donated / total_energy_received (COOP:585-586), in call order
   for (int b0 = 0; b0 < n_s; b0 += 32) {
     const int i = b0 + lane;
     bool nb = false;
@@ -256,6 +257,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
     bool over = false, trunc = false, done = false, have_new_base = false;
     int n_gh = 0;  // ghost cells loaded into the pseudo-slots cap[1]-1, cap[1]-2, ...
     double ep_dist[2] = {0.0, 0.0}, ep_cost[2] = {0.0, 0.0};  // this step's distance moved / locomotion energy per species (per lane)
+    // trait variants: the episode's event counters behind `training_metrics` (births blocked by the id pool / the density cap,
+    // catches blocked by satiation, energy donated; MR:1347-1350, COOP:1365-1368) are bumped in place by lane 0 — rare events
+    double* const ep_ev = (TRAITS && ep_sums != nullptr) ? ep_sums + (size_t)env * PPG_EP_STRIDE : nullptr;
 
     const long long t_env0 = clock64();
     const unsigned t_ns0 = globaltimer_lo();
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           const int cl = CELLP((unsigned)S.pos[1][sl]);
           const int gg = S.map[2][cl];
           if (!gg) continue;
-          const double keep_gain = coop_donation<MapT>(sbase, p, 1, sl, n[1], S.gE[gg - 1], lane);
+          const double keep_gain = coop_donation<MapT>(sbase, p, 1, sl, n[1], S.gE[gg - 1], lane, ep_ev ? ep_ev + PPG_EP_DONATED + 1 : nullptr);
           const double en = S.E[1][sl] + keep_gain;
           __syncwarp();
           if (lane == 0) {
@@ -834,7 +838,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             const unsigned qf = S.flg[1][q];
             const bool was_dead = (qf & FC) != 0 || ((qf & F_DIED) && (qf & F_CAUGHT));  // dead_prey membership
             if (!was_dead && carcass_age >= 0 && (int)X.age[0][slot] < carcass_age) continue;  // juvenile: carcasses only (ECO:802-804)
-            if (satiation && X.mord[0][slot] != 0) continue;  // still digesting: does not hunt this step (MR:734-740)
+            if (satiation && X.mord[0][slot] != 0) {  // still digesting: does not hunt this step (MR:734-740)
+              if (ep_ev && lane == 0) ep_ev[PPG_EP_SATIATION_BLOCKED] += 1.0;  // satiation_blocked_catches_predator (MR:739)
+              continue;
+            }
             const double pe = S.E[1][q];
             const double bite = LEAN ? pe : (pe < bite_cap_prey ? pe : bite_cap_prey);  // ECO:812-814
             double rem = LEAN ? 0.0 : pe - bite;
@@ -842,7 +849,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
             if (tm == PPG_TRAIT_SPEED) en = S.E[0][slot] + bite;
             else {  // the trait variants always consume the prey (MR:759-773)
               rem = 0.0;
-              if (tm == PPG_TRAIT_COOPERATION) en = S.E[0][slot] + coop_donation<MapT>(sbase, p, 0, slot, n[0], pe, lane);  // COOP:777
+              if (tm == PPG_TRAIT_COOPERATION) en = S.E[0][slot] + coop_donation<MapT>(sbase, p, 0, slot, n[0], pe, lane, ep_ev ? ep_ev + PPG_EP_DONATED : nullptr);  // COOP:777
               else en = S.E[0][slot] + (tm == PPG_TRAIT_METABOLIC ? bite * gf : bite);  // MR:747-751
             }
             __syncwarp();
@@ -898,9 +905,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
           while (m) {
             const int ps_slot = b0 + __ffs(m) - 1;
             m &= m - 1;
-            if (s == 0 && tm == PPG_TRAIT_METABOLIC && p.repro_ratio >= 0.0 && (double)eh.active[0] >= p.repro_ratio * (double)eh.active[1])
+            if (s == 0 && tm == PPG_TRAIT_METABOLIC && p.repro_ratio >= 0.0 && (double)eh.active[0] >= p.repro_ratio * (double)eh.active[1]) {
+              if (ep_ev && lane == 0) ep_ev[PPG_EP_BLOCKED_DENSITY] += 1.0;  // reproduction_blocked_due_to_density_predator (MR:852)
               continue;  // density-dependent soft cap (MR:843-854)
-            if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) { h.status |= PPG_STATUS_ID_POOL_EMPTY; continue; }  // ECO:1104-1111
+            }
+            if ((s == 0 ? h.next_idx[0] : h.next_idx[1]) >= p.n_possible[s]) {  // ECO:1104-1111
+              h.status |= PPG_STATUS_ID_POOL_EMPTY;
+              if (ep_ev && lane == 0) ep_ev[PPG_EP_BLOCKED_CAPACITY + s] += 1.0;  // reproduction_blocked_due_to_capacity_* (MR:857,943)
+              continue;
+            }
             if (SEL(n) + SEL(births) >= p.cap[s] - (s == 1 ? n_gh : 0)) { h.status |= PPG_STATUS_SLOT_OVERFLOW; continue; }
             // mutate_genome (GENOME:49-59): the draws precede the spawn search (ECO:1119 before :1136)
             double spd = SEL(X.spd)[ps_slot];
@@ -1223,10 +1236,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) ppg_step_eco_kernel(const __gr
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], d);
         if (lane < 4) {
-          double* dst = ep_sums + (size_t)env * 4 + lane;
+          double* dst = ep_sums + (size_t)env * PPG_EP_STRIDE + lane;
           const double add = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
           *dst = mode == 1 ? 0.0 : *dst + add;
-        }
+        } else if (lane < PPG_EP_STRIDE && mode == 1) ep_sums[(size_t)env * PPG_EP_STRIDE + lane] = 0.0;  // the event counters start with the episode
+
       }
       if (over) h.state = p.autoreset ? ST_NEEDS_RESET : ST_IDLE;
       if (lane == 0) { p.hdr[env] = h; p.ehdr[env] = eh; }

@@ -625,10 +625,12 @@ class _TraitEnv(PredPreyGrassEco):
     def episode_training_metrics(self):
         """`_build_episode_training_metrics` of the trait variants (MR:1274-1392): the trait distribution and the per-agent
         means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the reproduction rate per
-        trait quartile.  Distance and locomotion totals come from the device
-        (ppg_read_episode_eco).  Not emitted: the `*_reproduction_blocked*` / `predator_satiation_blocked_catches` event
-        counters, the `*_repro_spearman` rank correlations and COOP's donation totals / relatedness proxy."""
+        trait quartile.  Distance and locomotion totals and the event counters (births blocked by the id pool or the density
+        cap, catches blocked by satiation, COOP's donated energy) come from the device (ppg_read_episode_eco,
+        ppg_read_episode_events_eco).  Not emitted: the `*_repro_spearman` rank correlations and COOP's
+        `*_local_relatedness_proxy` (INTEGRATION.md)."""
         ep = self._batch.read_episode_eco(0)
+        ev = self._batch.read_episode_events_eco(0)
         res, t = {}, self._trait
         for s, role in enumerate(("predator", "prey")):
             recs = list(self._records[s].values())
@@ -651,10 +653,24 @@ class _TraitEnv(PredPreyGrassEco):
                 aft = [sum(r["after"]) / len(r["after"]) for r in recs if r["after"]]
                 res[f"{role}_reproduction_energy_invested_mean"] = float(np.mean(inv)) if inv else 0.0
                 res[f"{role}_parent_energy_after_reproduction_mean"] = float(np.mean(aft)) if aft else 0.0
+                if t == "cooperation_rate":  # COOP:1349-1354: every donated unit is received by the same species (COOP:585-586)
+                    res[f"{role}_energy_donated_mean"] = ev["donated"][s] / n
+                    res[f"{role}_energy_received_mean"] = ev["donated"][s] / n
             else:
                 for key in ("distance_traveled_mean", "movement_energy_spent_mean", "offspring_count_mean", "agent_count",
                             "offspring_initial_energy_mean", "reproduction_energy_invested_mean", "parent_energy_after_reproduction_mean"):
                     res[f"{role}_{key}"] = 0.0
+                if t == "cooperation_rate":
+                    res[f"{role}_energy_donated_mean"] = res[f"{role}_energy_received_mean"] = 0.0
+        if t == "cooperation_rate":  # COOP:1365-1368
+            for s, role in enumerate(("predator", "prey")):
+                res[f"{role}_energy_donated_total"] = res[f"{role}_energy_received_total"] = ev["donated"][s]
+        res["predator_reproduction_blocked"] = float(ev["blocked_capacity"][0])  # MR:1347-1350
+        res["prey_reproduction_blocked"] = float(ev["blocked_capacity"][1])
+        if t == "metabolic_rate":
+            res["predator_reproduction_blocked_density"] = float(ev["blocked_density"])
+        if t in ("metabolic_rate", "offspring_investment_fraction"):
+            res["predator_satiation_blocked_catches"] = float(ev["satiation_blocked"])
         res["predator_spawned_total"] = float(ep["spawned"][0])
         res["prey_spawned_total"] = float(ep["spawned"][1])
         res["peak_active_predators"] = float(self.peak_active_predators)

@@ -51,6 +51,9 @@ class OracleBatch:
     def read_episode_eco(self, env):
         return self.o.read_episode_eco(env)
 
+    def read_episode_events_eco(self, env):
+        return self.o.read_episode_events_eco(env)
+
     def read_env(self, env):
         return self.o.read_env(env)
 

@@ -54,6 +54,11 @@ def compare_env_state(gpu, oracle, env, where=""):
             assert np.array_equal(a["speed"][s], b["speed"][s]), (where, env, s)
         assert np.array_equal(a["dead_prey"], b["dead_prey"]), (where, env)
         assert np.array_equal(a["active_num"], b["active_num"]), (where, env)
+        if gpu.cfg.track_episode_sums:  # per-episode totals and the trait variants' event counters (float64, accumulated in order)
+            assert gpu.read_episode_eco(env) == oracle.read_episode_eco(env), (where, env, gpu.read_episode_eco(env), oracle.read_episode_eco(env))
+            if gpu.cfg.trait_mode != 0:
+                ge, oe = gpu.read_episode_events_eco(env), oracle.read_episode_events_eco(env)
+                assert ge == oe, (where, env, ge, oe)
         if gpu.cfg.trait_mode == 4:  # cadence: the move accumulators (float64, bit-exact)
             ga, oa = gpu.read_env_acc(env), oracle.read_env_acc(env)
             for s in range(2):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(_lib.SYMBOLS) == declared
-    assert _lib.load().ppg_abi_version() == 9
+    assert _lib.load().ppg_abi_version() == 10
 
 
 def test_struct_layout_matches_header():

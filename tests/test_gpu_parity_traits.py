@@ -106,6 +106,24 @@ def test_cad_without_genome():
     assert st["episodes"] > 0
 
 
+@pytest.mark.parametrize("base", ["mr", "inv", "coop"])
+def test_trait_episode_event_counters(base):
+    """the counters behind `training_metrics` (births blocked by an exhausted id pool / the density cap, catches blocked by
+    satiation, COOP's donated energy; MR:1347-1350, COOP:1365-1368) against the oracle, every step, on worlds that hit them:
+    tiny id pools, a tight density cap, a long satiation cooldown, generous sharing"""
+    cfg = dict({"mr": METABOLIC_CONFIG, "inv": INVESTMENT_CONFIG, "coop": COOPERATION_CONFIG}[base], **RICH,
+               n_possible_predators=24, n_possible_prey=60, genome_mutation={"rate": 1.0, "std": 0.3}, max_steps=120)
+    if base == "mr":
+        cfg.update(predator_reproduction_max_ratio=0.3, predator_satiation_cooldown=6)
+    if base == "inv":
+        cfg.update(predator_satiation_cooldown=6)
+    if base == "coop":
+        cfg.update(cooperation_range=3)
+    envs = tuple(range(0, 64, 7))
+    st = lockstep_parity(trait(cfg, cap_live=(32, 64), seed=43, track_episode_sums=True), 64, 140, state_envs=envs)
+    assert st["births_prey"] > 0 and st["status_or"] & 0x10  # PPG_STATUS_ID_POOL_EMPTY: some births were blocked by capacity
+
+
 def test_traits_2048_envs():
     for base, seed in ((METABOLIC_CONFIG, 21), (INVESTMENT_CONFIG, 22), (COOPERATION_CONFIG, 23), (CADENCE_CONFIG, 24)):
         st = lockstep_parity(trait(base, cap_live=(64, 160), seed=seed), 2048, 80, state_envs=(0, 2047), check_every=4)
