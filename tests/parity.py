@@ -55,7 +55,10 @@ def compare_env_state(gpu, oracle, env, where=""):
         assert np.array_equal(a["dead_prey"], b["dead_prey"]), (where, env)
         assert np.array_equal(a["active_num"], b["active_num"]), (where, env)
         if gpu.cfg.track_episode_sums:  # per-episode totals and the trait variants' event counters (float64, accumulated in order)
-            assert gpu.read_episode_eco(env) == oracle.read_episode_eco(env), (where, env, gpu.read_episode_eco(env), oracle.read_episode_eco(env))
+            a_ep, b_ep = gpu.read_episode_eco(env), oracle.read_episode_eco(env)
+            assert a_ep["spawned"] == b_ep["spawned"], (where, env, a_ep, b_ep)
+            for k in ("distance", "move_energy"):  # the device adds per-lane partial sums: equal to the last few ulps
+                assert np.allclose(a_ep[k], b_ep[k], rtol=1e-12, atol=0.0), (where, env, k, a_ep, b_ep)
             if gpu.cfg.trait_mode != 0:
                 ge, oe = gpu.read_episode_events_eco(env), oracle.read_episode_events_eco(env)
                 assert ge == oe, (where, env, ge, oe)
