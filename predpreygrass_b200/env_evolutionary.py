@@ -556,6 +556,11 @@ class _TraitEnv(PredPreyGrassEco):
         super().__init__(config)
         self.n_initial_active_predators_min, self.n_initial_active_prey_min = self._cfg.n_initial_min[0], self._cfg.n_initial_min[1]
         self._records = ({}, {})
+        # per_step_agent_data / agent_event_log (MR:391-411, 1153-1165) for the variants whose energy chain the recorder follows
+        if self._trait in ("metabolic_rate", "offspring_investment_fraction") and config.get("record_agent_events", True):
+            from .event_log import TraitEventRecorder
+
+            self._events = TraitEventRecorder(config, self.action_to_move_tuple_agents, self.grid_size, self._trait)
 
     def reset(self, *, seed=None, options=None):
         _Base.reset(self, seed=seed)
@@ -572,6 +577,9 @@ class _TraitEnv(PredPreyGrassEco):
             for i, v in zip(st["ids"][s].tolist(), st["speed"][s].tolist()):
                 self._records[s][i] = self._new_record(v)
         self.peak_active_predators = self.peak_active_prey = 0  # MR:177-178
+        if self._events is not None:
+            state, grass = self._event_state()
+            self._events.reset(state, self.agents, grass)
         return obs, {}
 
     @staticmethod
@@ -579,9 +587,16 @@ class _TraitEnv(PredPreyGrassEco):
         return {"trait": float(trait_value), "offspring": 0, "initial_energy": float(initial_energy), "invested": [], "after": []}
 
     def step(self, action_dict):
+        t = self.current_step
         out = self._step_device(action_dict)
         obs, rew, term, trunc = self._dicts(out)
         flags = int(out["env_flags"][0])
+        if self._events is not None:
+            rows = self._rows_of(out)
+            n_old = sum(int(out[f"old_off{s}"][1]) - int(out[f"old_off{s}"][0]) for s in range(2))
+            newborn = sorted((name for name, s, r, f in rows[n_old:]), key=lambda a: ("prey" in a, int(a.rsplit("_", 1)[1])))
+            state, grass = self._event_state()
+            self._events.step(t, action_dict, {name: f for name, s, r, f in rows}, state, newborn, grass, bool(flags & ENV_TRUNCATED))
         if int(out["new_cnt0"][0]) or int(out["new_cnt1"][0]):
             # births run in predator_positions / prey_positions order (MR:318-331) = the order of the acting rows, and the
             # newborn rows are in birth order: the k-th parent flagged PPG_ROW_REPRODUCED is the parent of the k-th newborn
@@ -627,8 +642,8 @@ class _TraitEnv(PredPreyGrassEco):
         means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the reproduction rate per
         trait quartile.  Distance and locomotion totals and the event counters (births blocked by the id pool or the density
         cap, catches blocked by satiation, COOP's donated energy) come from the device (ppg_read_episode_eco,
-        ppg_read_episode_events_eco).  Not emitted: the `*_repro_spearman` rank correlations and COOP's
-        `*_local_relatedness_proxy` (INTEGRATION.md)."""
+        ppg_read_episode_events_eco); `*_mr_repro_spearman` needs the event recorder (the order of the agent records).  Not
+        emitted: COOP's `*_coop_repro_spearman` and `*_local_relatedness_proxy` (INTEGRATION.md)."""
         ep = self._batch.read_episode_eco(0)
         ev = self._batch.read_episode_events_eco(0)
         res, t = {}, self._trait
@@ -682,10 +697,20 @@ class _TraitEnv(PredPreyGrassEco):
                 recs = list(self._records[s].values())
                 if len(recs) < 4:
                     continue
+                if self._events is not None:
+                    # `{role}_{tag}_repro_spearman` (MR:1358-1382): the reference ranks with argsort and no tie correction, so the
+                    # value depends on the order its record dicts are iterated in — live records, then the completed ones in
+                    # the order they were closed, which the event recorder keeps
+                    ids = [int(a.rsplit("_", 1)[1]) for a in self._events.record_order() if a.startswith(role)]
+                    recs = [self._records[s][i] for i in ids]
                 x = np.array([r["trait"] for r in recs])
                 y = np.array([float(r["offspring"] > 0) for r in recs])
-                # (`{role}_{tag}_repro_spearman` is not emitted: the reference ranks with argsort and no tie correction, so
-                # its value depends on the order its record dicts happen to be iterated in, MR:1362-1380)
+                if self._events is not None:
+                    rx, ry = np.argsort(np.argsort(x)).astype(float), np.argsort(np.argsort(y)).astype(float)
+                    rx -= rx.mean()
+                    ry -= ry.mean()
+                    denom = np.sqrt((rx ** 2).sum() * (ry ** 2).sum())
+                    res[f"{role}_{self._tag}_repro_spearman"] = float(np.dot(rx, ry) / denom) if denom > 0.0 else 0.0
                 q25, q50, q75 = np.percentile(x, [25, 50, 75])
                 for k, m in enumerate((x <= q25, (x > q25) & (x <= q50), (x > q50) & (x <= q75), x > q75), 1):
                     if m.sum() > 0:

@@ -328,3 +328,254 @@ class EcoEventRecorder:
         """`export_agent_event_log` (ECO:1575-1597)"""
         with open(path, "w", encoding="utf-8") as f:
             json.dump(self.agent_event_log, f, indent=2)
+
+
+class TraitEventRecorder:
+    """The same exporters for the trait variants metabolic_rate / investment (MR:391-411, 1153-1165): their step has no
+    carcasses, no age caps and no lineage rewards, and a fixed chain per agent
+
+        E0 --(-basal cost [x rate], MR:555-563)--> E1 --(-move cost, MR:516-523)--> E2 --(+gain [x rate ** alpha], MR:747-751,
+           805-807)--> E3 --(-offspring energy [parent energy x fraction], MR:897-899 / INV:546-557)--> E4
+
+    evaluated with the reference's own float64 expressions.  Besides the two exporters the recorder keeps the order in which
+    the reference iterates its agent records (`_iter_all_agent_records`, MR:1400-1404: live records in registration order,
+    then the completed ones in the order they were finalized) — the `*_repro_spearman` metrics rank with argsort and no tie
+    correction, so they depend on it (MR:1358-1382)."""
+
+    def __init__(self, config, action_to_move, grid_size, trait):
+        g = config.get
+        self.cfg, self.trait = config, trait
+        mr, inv = trait == "metabolic_rate", trait == "offspring_investment_fraction"
+        if inv:
+            self.loss = (g("energy_loss_per_step_predator"), g("energy_loss_per_step_prey"))  # INV:54-55
+        else:
+            self.loss = (g("basal_energy_cost_predator"), g("basal_energy_cost_prey"))  # MR:50-51
+        self.scale_loss = mr
+        self.alpha = float(g("metabolic_rate_alpha", 0.7)) if mr else None  # MR:102
+        self.move_cost = (float(g("movement_energy_cost_per_cell_predator", 0.0)), float(g("movement_energy_cost_per_cell_prey", 0.0)))
+        self.grass_gain, self.grass_max = g("energy_gain_per_step_grass"), g("max_energy_grass")
+        self.cap_prey = float(g("max_energy_gain_per_prey", float("inf")))  # MR:64
+        self.init_e = None if inv else (g("initial_energy_predator"), g("initial_energy_prey"))
+        self.moves, self.G = action_to_move, int(grid_size)
+        self.reset({}, [], {})
+
+    def _cost(self, s, old, new):
+        """`_get_movement_energy_cost` (MR:516-523)"""
+        distance = float(np.linalg.norm(np.array(new) - np.array(old)))
+        if distance <= 0:
+            return 0.0
+        return self.move_cost[s] * distance
+
+    def _target(self, pos, action):
+        """`_get_move` without the occupancy test (MR:617-630)"""
+        mv = self.moves[int(action)]
+        return (min(max(pos[0] + mv[0], 0), self.G - 1), min(max(pos[1] + mv[1], 0), self.G - 1))
+
+    def _gain(self, food, rate):
+        """MR:751 / 807: food x rate ** alpha; INV:759 / 812: the food itself"""
+        if self.alpha is None:
+            return food
+        return food * ((float(rate) if rate is not None else 1.0) ** self.alpha)
+
+    def reset(self, state, agents, grass):
+        """state: {agent: (pos, energy, age, trait value or None, _)}; grass: {cell: (name, energy)}"""
+        self.per_step_agent_data = []
+        self.agent_event_log = {}
+        self.agent_parents, self.agent_offspring_counts, self.agent_live_offspring_ids = {}, {}, {}
+        self.cumulative_reward = {}
+        self.live_order, self.completed_order = [], []  # `agent_stats_live` / `agent_stats_completed` key order
+        self.inexact_chains = 0
+        self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+        for a in agents:
+            self._register(a, None, 0, state[a][3])
+
+    def _register(self, agent, parent, t, value):
+        self.agent_parents[agent] = parent
+        self.agent_offspring_counts[agent] = 0
+        self.agent_live_offspring_ids[agent] = []
+        self.cumulative_reward[agent] = 0.0
+        self.live_order.append(agent)
+        self.agent_event_log[agent] = {
+            "agent_id": agent, "birth_step": t, "death_step": None, "parent_id": parent, "death_cause": None,
+            "eating_events": [], "reproduction_events": [], "reward_events": [], "diet_events": [], "lifecycle_events": [],
+            "genome": None if value is None else {self.trait: float(value)},
+        }
+
+    def _finalize(self, agent, cause, step):
+        """the event-log part of `_finalize_agent_record` (MR:1197-1234): a no-op for a record that is already closed"""
+        if agent not in self.live_order:
+            return
+        self.live_order.remove(agent)
+        self.completed_order.append(agent)
+        evt = self.agent_event_log[agent]
+        evt["death_step"] = step
+        evt["death_cause"] = cause
+        self.agent_live_offspring_ids.pop(agent, None)
+
+    def record_order(self):
+        return list(self.live_order) + list(self.completed_order)
+
+    def step(self, t, action_dict, rows, state, newborn, grass, time_limit):
+        cfg, prev = self.cfg, self.prev
+        agents = [a for a in self.prev_agents if a in state] + list(newborn)
+        is_pred = lambda a: "predator" in a  # noqa: E731
+        E, deltas = {}, {}
+        # Step 1 (MR:546-574): basal cost, ageing
+        for a in self.prev_agents:
+            s = 0 if is_pred(a) else 1
+            rate = prev[a][3]
+            decay = self.loss[s] * (float(rate) if rate is not None else 1.0) if self.scale_loss else self.loss[s]
+            E[a] = prev[a][1] - decay
+            deltas[a] = {"decay": -decay, "move": 0.0, "eat": 0.0, "repro": 0.0}
+        # Step 2 (MR:576-584)
+        g_now = {cell: (name, min(e + self.grass_gain, self.grass_max)) for cell, (name, e) in self.prev_grass.items()}
+        # Step 3 (MR:586-615): survivors moved from their old to their new cell; for an agent that dies in this step the cells it
+        # can have died on are kept as candidates (cell, energy): the move target, or the old cell if the move was blocked
+        cand = {}
+        for a, action in action_dict.items():
+            if a not in prev:
+                continue
+            s = 0 if is_pred(a) else 1
+            old = prev[a][0]
+            if a in state:
+                cost = self._cost(s, old, state[a][0])
+                E[a] -= cost
+                deltas[a]["move"] -= cost
+            else:
+                tgt = self._target(old, action)
+                cand[a] = [(tgt, E[a] - self._cost(s, old, tgt))] + ([(old, E[a])] if tgt != old else [])
+        gone_prey = {}
+        for a in self.prev_agents:
+            if a in state:
+                continue
+            if a not in cand:
+                cand[a] = [(prev[a][0], E[a])]
+            if not is_pred(a):
+                gone_prey[a] = [{"cell": c, "e": e, "grass": None} for c, e in cand[a]]
+        # Step 4b (MR:790-834): prey that are still alive eat (a starved prey is terminated before: MR:277-280)
+        for a in self.prev_agents:
+            if is_pred(a):
+                continue
+            f = rows.get(a, 0)
+            if a in state:
+                if f & ROW_ATE and state[a][0] in g_now:
+                    name, ge = g_now[state[a][0]]
+                    gain = self._gain(float(ge), prev[a][3])
+                    E[a] += gain
+                    deltas[a]["eat"] = gain
+                    self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
+                    self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": name, "energy_after": float(E[a])})
+                else:
+                    self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+            elif f & ROW_ATE:  # ate, then was caught in the same step: on a candidate cell with a patch the bite raises that candidate
+                for c in gone_prey[a]:
+                    if c["e"] > 0 and c["cell"] in g_now:
+                        name, ge = g_now[c["cell"]]
+                        c["e"] += self._gain(float(ge), prev[a][3])
+                        c["grass"] = (name, c["e"])
+        # Step 4c (MR:720-788): predators, in predator_positions order.  The prey a predator caught is gone after the step; it is
+        # matched through its candidate cells and confirmed by the predator's energy.  A prey stays in `agent_positions`
+        # until Step 5, so a second predator on the cell catches the same prey again.
+        eaten = {}  # prey -> its candidate, in the order of the first catch
+        for a in self.prev_agents:
+            if not is_pred(a) or a not in state:
+                continue
+            f = rows.get(a, 0)
+            if not f & ROW_ATE:
+                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
+                continue
+            pos = state[a][0]
+            here = [(q, c) for q, cs in gone_prey.items() for c in cs if c["cell"] == pos and (q not in eaten or eaten[q] is c)]
+            if not here:
+                self.inexact_chains += 1
+                continue
+            child = self._child_energy_hint(a, rows, state, newborn)
+            want = state[a][1] + child
+            q, c = min(here, key=lambda o: abs((E[a] + self._gain(min(float(o[1]["e"]), self.cap_prey), prev[a][3])) - want))
+            eaten.setdefault(q, c)
+            gain = self._gain(min(float(c["e"]), self.cap_prey), prev[a][3])
+            E[a] += gain
+            deltas[a]["eat"] = gain
+            self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
+            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "energy_after": float(E[a])})
+        # the records close in the reference's order: starvation (Step 4a, `agent_energies` order), then the catches (Step 4c)
+        for a in self.prev_agents:
+            if a in state:
+                continue
+            if is_pred(a):
+                self._finalize(a, "starved", t)
+                continue
+            c = eaten.get(a)
+            if c is not None and c["e"] > 0:
+                continue  # caught alive: closed below, in the predators' order (a starved prey is closed here, the catch changes nothing)
+            if c is None and all(x["e"] > 0 for x in gone_prey[a]):
+                self.inexact_chains += 1  # gone, but it can neither have starved nor did a predator take it
+            self._finalize(a, "starved", t)
+        for q, c in eaten.items():
+            if c["grass"] is not None:  # its last meal (MR:825-833)
+                self.agent_event_log[q]["eating_events"].append({"t": int(t), "id_eaten": c["grass"][0], "energy_after": float(c["grass"][1])})
+            self._finalize(q, "eaten", t)
+        # Step 6 (MR:836-1010): births, predators first; the k-th newborn row of a species belongs to the k-th parent
+        new_agents = list(newborn)
+        for s, role in enumerate(("predator", "prey")):
+            parents = [a for a in self.prev_agents if (is_pred(a) == (s == 0)) and a in state and rows.get(a, 0) & ROW_REPRODUCED]
+            children = [a for a in new_agents if is_pred(a) == (s == 0)]
+            if len(parents) != len(children):
+                self.inexact_chains += 1
+            for par, child in zip(parents, children):
+                self._register(child, par, int(t), state[child][3])
+                self.agent_live_offspring_ids[par].append(child)
+                self.agent_offspring_counts[par] += 1
+                self.agent_event_log[par]["reproduction_events"].append({"t": int(t), "child_id": child})
+                ce = self._offspring_energy(par, s, E[par], prev[par][3])
+                if ce != state[child][1]:
+                    self.inexact_chains += 1
+                E[par] -= ce
+                deltas[par]["repro"] = -ce
+                r = _role(cfg.get(f"reproduction_reward_{role}", 0.0), par)
+                self.cumulative_reward[par] += r
+                self.agent_event_log[par]["reward_events"].append({"t": int(t), "reproduction_reward": float(r),
+                                                                   "cumulative_reward": float(self.cumulative_reward[par])})
+                deltas[child] = {"decay": 0.0, "move": 0.0, "eat": 0.0, "repro": 0.0}
+        for a in self.prev_agents:
+            if a in state and E[a] != state[a][1]:
+                self.inexact_chains += 1
+        step_data = {}
+        for a in agents:
+            pos, e, ag, _, _ = state[a]
+            d = deltas[a]
+            step_data[a] = {"position": pos, "energy": e, "energy_decay": d["decay"], "energy_movement": d["move"],
+                            "energy_eating": d["eat"], "energy_reproduction": d["repro"], "age": ag,
+                            "offspring_count": self.agent_offspring_counts[a],
+                            "offspring_ids": self.agent_live_offspring_ids.get(a, []), "parent": self.agent_parents.get(a)}
+        self.per_step_agent_data.append(step_data)
+        if time_limit:  # MR:453-454: every record still open is closed with the step counter already advanced
+            for a in list(self.live_order):
+                self._finalize(a, "time_limit", int(t) + 1)
+        self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+
+    def _offspring_energy(self, parent, s, parent_energy, value):
+        """MR:897 / 984: the configured initial energy; INV:546-557: the parent's energy x its investment fraction"""
+        if self.init_e is not None:
+            return self.init_e[s]
+        if value is not None:
+            fraction = float(value)
+        else:
+            role = "predator" if s == 0 else "prey"
+            fraction = float(self.cfg.get("founder_genome", {}).get(role, {}).get("offspring_investment_fraction_mean", 0.35))
+        return float(parent_energy) * fraction
+
+    def _child_energy_hint(self, a, rows, state, newborn):
+        """what a parent paid for this step's child (only used to choose between candidate prey)"""
+        if not rows.get(a, 0) & ROW_REPRODUCED:
+            return 0.0
+        if self.init_e is not None:
+            return self.init_e[0]
+        parents = [p for p in self.prev_agents if "predator" in p and p in state and rows.get(p, 0) & ROW_REPRODUCED]
+        kids = [k for k in newborn if "predator" in k]
+        k = parents.index(a)
+        return state[kids[k]][1] if k < len(kids) else 0.0
+
+    def export(self, path):
+        with open(path, "w", encoding="utf-8") as f:
+            json.dump(self.agent_event_log, f, indent=2)

@@ -99,3 +99,58 @@ def test_snapshot_restore_carries_the_exporters():
     assert _plain(env.per_step_agent_data) == data1 and _plain(env.agent_event_log) == log1
     assert env._events.inexact_chains == 0
     env.close()
+
+
+TRAIT_CASES = sorted(os.path.basename(p)[len("trait_events_"):-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "trait_events_*.json.gz")))
+TRAIT_CASES = [c for c in TRAIT_CASES if not c.startswith("coop")]
+
+
+def _replay_trait(case):
+    """the exporters of PredPreyGrassMetabolicRate / Investment against recordings of the unmodified reference classes
+    (tests/golden/trait_events_*.json.gz, made by tests/golden/make_golden_trait_events.py), and the order of the agent records"""
+    from predpreygrass_b200 import env_evolutionary as E
+
+    z, cfg = load_golden(case)
+    cls = {"mr": E.PredPreyGrassMetabolicRate, "inv": E.PredPreyGrassInvestment, "coop": E.PredPreyGrassCooperation}[cfg.pop("variant")]
+    cfg["cap_live"] = (min(cfg["n_possible_predators"], 250), min(cfg["n_possible_prey"], 450))
+    want = json.loads(gzip.open(os.path.join(GOLDEN_DIR, f"trait_events_{case}.json.gz")).read())
+    env = cls(cfg)
+    env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    names = ("predator", "prey")
+    infos = {}
+    for t in range(want["steps"]):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        acts = {f"{names[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
+        *_, infos = env.step(acts)
+    got_steps, got_log = _plain(env.per_step_agent_data), _plain(env.agent_event_log)
+    assert env._events.inexact_chains == 0
+    assert len(got_steps) == len(want["per_step_agent_data"]) == want["steps"]
+    for t, (g, w) in enumerate(zip(got_steps, want["per_step_agent_data"])):
+        assert sorted(g) == sorted(w), (case, t)
+        for a in w:
+            assert g[a] == w[a], (case, t, a, g[a], w[a])
+    assert sorted(got_log) == sorted(want["agent_event_log"]), case
+    for a, w in want["agent_event_log"].items():
+        for k in w:
+            assert got_log[a][k] == w[k], (case, a, k, got_log[a][k], w[k])
+    assert env._events.record_order() == want["record_order"], case
+    if want["ended"]:
+        got = infos["__all__"]["training_metrics"]
+        for k, v in want["spearman"].items():
+            assert got[k] == v, (case, k, got[k], v)
+    env.close()
+
+
+@pytest.mark.parametrize("case", TRAIT_CASES)
+def test_trait_event_log_host_logic_over_the_oracle(case, monkeypatch):
+    import predpreygrass_b200.batched as batched
+    from tests.oracle_batch import OracleBatch
+
+    monkeypatch.setattr(batched, "BatchedPredPreyGrass", OracleBatch)
+    _replay_trait(case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TRAIT_CASES)
+def test_trait_event_log_on_the_device(case):
+    _replay_trait(case)
