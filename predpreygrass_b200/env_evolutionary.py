@@ -557,7 +557,7 @@ class _TraitEnv(PredPreyGrassEco):
         self.n_initial_active_predators_min, self.n_initial_active_prey_min = self._cfg.n_initial_min[0], self._cfg.n_initial_min[1]
         self._records = ({}, {})
         # per_step_agent_data / agent_event_log (MR:391-411, 1153-1165) for the variants whose energy chain the recorder follows
-        if self._trait in ("metabolic_rate", "offspring_investment_fraction") and config.get("record_agent_events", True):
+        if config.get("record_agent_events", True):
             from .event_log import TraitEventRecorder
 
             self._events = TraitEventRecorder(config, self.action_to_move_tuple_agents, self.grid_size, self._trait)
@@ -642,8 +642,8 @@ class _TraitEnv(PredPreyGrassEco):
         means over ALL agent records of the episode, spawn / peak / id counters and (MR, COOP) the reproduction rate per
         trait quartile.  Distance and locomotion totals and the event counters (births blocked by the id pool or the density
         cap, catches blocked by satiation, COOP's donated energy) come from the device (ppg_read_episode_eco,
-        ppg_read_episode_events_eco); `*_mr_repro_spearman` needs the event recorder (the order of the agent records).  Not
-        emitted: COOP's `*_coop_repro_spearman` and `*_local_relatedness_proxy` (INTEGRATION.md)."""
+        ppg_read_episode_events_eco); the `*_repro_spearman` rank correlations and COOP's `*_local_relatedness_proxy` come from
+        the event recorder (the order of the agent records, the parents) and are left out with `record_agent_events: False`."""
         ep = self._batch.read_episode_eco(0)
         ev = self._batch.read_episode_events_eco(0)
         res, t = {}, self._trait
@@ -680,6 +680,9 @@ class _TraitEnv(PredPreyGrassEco):
         if t == "cooperation_rate":  # COOP:1365-1368
             for s, role in enumerate(("predator", "prey")):
                 res[f"{role}_energy_donated_total"] = res[f"{role}_energy_received_total"] = ev["donated"][s]
+                if self._events is not None:  # kinship needs the parents, which the event recorder keeps (COOP:529-535, 1369-1371)
+                    donated = self._events.energy_donated[s]
+                    res[f"{role}_local_relatedness_proxy"] = float(self._events.kin_donation[s] / donated) if donated > 0.0 else 0.0
         res["predator_reproduction_blocked"] = float(ev["blocked_capacity"][0])  # MR:1347-1350
         res["prey_reproduction_blocked"] = float(ev["blocked_capacity"][1])
         if t == "metabolic_rate":

@@ -356,6 +356,11 @@ class TraitEventRecorder:
         self.grass_gain, self.grass_max = g("energy_gain_per_step_grass"), g("max_energy_grass")
         self.cap_prey = float(g("max_energy_gain_per_prey", float("inf")))  # MR:64
         self.init_e = None if inv else (g("initial_energy_predator"), g("initial_energy_prey"))
+        self.coop = trait == "cooperation_rate"
+        if self.coop:
+            self.cap_prey = float("inf")  # COOP:776-777: the whole prey
+        self.coop_range = int(g("cooperation_range", 2))  # COOP:93
+        self.sat_cd = -1 if self.coop else int(g("predator_satiation_cooldown", 0))  # MR:62
         self.moves, self.G = action_to_move, int(grid_size)
         self.reset({}, [], {})
 
@@ -384,6 +389,8 @@ class TraitEventRecorder:
         self.agent_parents, self.agent_offspring_counts, self.agent_live_offspring_ids = {}, {}, {}
         self.cumulative_reward = {}
         self.live_order, self.completed_order = [], []  # `agent_stats_live` / `agent_stats_completed` key order
+        self.sat_until = {}  # agent_satiation_until (MR:134)
+        self.energy_donated, self.kin_donation = [0.0, 0.0], [0.0, 0.0]  # total_energy_donated / total_kin_donation (COOP:159-162)
         self.inexact_chains = 0
         self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
         for a in agents:
@@ -415,11 +422,39 @@ class TraitEventRecorder:
     def record_order(self):
         return list(self.live_order) + list(self.completed_order)
 
+    def _donate(self, a, s, gain, order, pos, E, termd):
+        """`_apply_cooperative_donation` (COOP:537-589): a cooperation_rate share of a positive gain goes, in equal parts, to the
+        live same-species agents within Chebyshev distance cooperation_range; returns what the donor keeps"""
+        if not self.coop or self.prev[a][3] is None or gain <= 0.0:
+            return gain
+        rate = float(self.prev[a][3])
+        if rate <= 0.0:
+            return gain
+        p = pos[a]
+        nbrs = [o for o in order[s] if o != a and o not in termd and max(abs(pos[o][0] - p[0]), abs(pos[o][1] - p[1])) <= self.coop_range]
+        if not nbrs:
+            return gain
+        total = rate * gain
+        share = total / len(nbrs)
+        kin = 0.0
+        for o in nbrs:
+            E[o] += share
+            pa, pb = self.agent_parents.get(a), self.agent_parents.get(o)
+            if o == pa or a == pb or (pa is not None and pa == pb):  # `_is_kin` (COOP:529-535)
+                kin += share
+        self.energy_donated[s] += total
+        self.kin_donation[s] += kin
+        return gain - total
+
     def step(self, t, action_dict, rows, state, newborn, grass, time_limit):
+        """The reference's own step replayed on the host (positions, energies, who eats whom), checked against what the device
+        reports: the survivors' cells and energies, the PPG_ROW_ATE / PPG_ROW_REPRODUCED flags and who is gone."""
         cfg, prev = self.cfg, self.prev
         agents = [a for a in self.prev_agents if a in state] + list(newborn)
         is_pred = lambda a: "predator" in a  # noqa: E731
-        E, deltas = {}, {}
+        order = ([a for a in self.prev_agents if is_pred(a)], [a for a in self.prev_agents if not is_pred(a)])  # *_positions order
+        E, deltas, pos = {}, {}, {}
+        cell = ({}, {})  # grid_world_state layers 0 / 1 (float32): what `_get_move` tests (MR:636)
         # Step 1 (MR:546-574): basal cost, ageing
         for a in self.prev_agents:
             s = 0 if is_pred(a) else 1
@@ -427,98 +462,80 @@ class TraitEventRecorder:
             decay = self.loss[s] * (float(rate) if rate is not None else 1.0) if self.scale_loss else self.loss[s]
             E[a] = prev[a][1] - decay
             deltas[a] = {"decay": -decay, "move": 0.0, "eat": 0.0, "repro": 0.0}
+            pos[a] = prev[a][0]
+            cell[s][pos[a]] = np.float32(E[a])
         # Step 2 (MR:576-584)
-        g_now = {cell: (name, min(e + self.grass_gain, self.grass_max)) for cell, (name, e) in self.prev_grass.items()}
-        # Step 3 (MR:586-615): survivors moved from their old to their new cell; for an agent that dies in this step the cells it
-        # can have died on are kept as candidates (cell, energy): the move target, or the old cell if the move was blocked
-        cand = {}
+        g_now = {c: [name, min(e + self.grass_gain, self.grass_max)] for c, (name, e) in self.prev_grass.items()}
+        # Step 3 (MR:586-615): moves in the order of the action dict; a target whose own-species layer reads > 0 blocks
         for a, action in action_dict.items():
             if a not in prev:
                 continue
             s = 0 if is_pred(a) else 1
-            old = prev[a][0]
-            if a in state:
-                cost = self._cost(s, old, state[a][0])
-                E[a] -= cost
-                deltas[a]["move"] -= cost
-            else:
-                tgt = self._target(old, action)
-                cand[a] = [(tgt, E[a] - self._cost(s, old, tgt))] + ([(old, E[a])] if tgt != old else [])
-        gone_prey = {}
+            old = pos[a]
+            new = self._target(old, action)
+            if cell[s].get(new, 0.0) > 0:
+                new = old
+            cost = self._cost(s, old, new)
+            E[a] -= cost
+            deltas[a]["move"] -= cost
+            cell[s][old] = np.float32(0.0)
+            cell[s][new] = np.float32(E[a])
+            pos[a] = new
+        # Step 4a (MR:274-280): starvation, `agent_energies` order
+        termd = set()
         for a in self.prev_agents:
-            if a in state:
+            if E[a] <= 0:
+                termd.add(a)
+                self._finalize(a, "starved", t)
+        # Step 4b (MR:790-834): prey that are still alive eat the patch they stand on
+        for a in order[1]:
+            if a in termd:
                 continue
-            if a not in cand:
-                cand[a] = [(prev[a][0], E[a])]
-            if not is_pred(a):
-                gone_prey[a] = [{"cell": c, "e": e, "grass": None} for c, e in cand[a]]
-        # Step 4b (MR:790-834): prey that are still alive eat (a starved prey is terminated before: MR:277-280)
-        for a in self.prev_agents:
-            if is_pred(a):
+            g = g_now.get(pos[a])
+            if g is None:
+                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
                 continue
-            f = rows.get(a, 0)
-            if a in state:
-                if f & ROW_ATE and state[a][0] in g_now:
-                    name, ge = g_now[state[a][0]]
-                    gain = self._gain(float(ge), prev[a][3])
-                    E[a] += gain
-                    deltas[a]["eat"] = gain
-                    self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
-                    self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": name, "energy_after": float(E[a])})
-                else:
-                    self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
-            elif f & ROW_ATE:  # ate, then was caught in the same step: on a candidate cell with a patch the bite raises that candidate
-                for c in gone_prey[a]:
-                    if c["e"] > 0 and c["cell"] in g_now:
-                        name, ge = g_now[c["cell"]]
-                        c["e"] += self._gain(float(ge), prev[a][3])
-                        c["grass"] = (name, c["e"])
-        # Step 4c (MR:720-788): predators, in predator_positions order.  The prey a predator caught is gone after the step; it is
-        # matched through its candidate cells and confirmed by the predator's energy.  A prey stays in `agent_positions`
-        # until Step 5, so a second predator on the cell catches the same prey again.
-        eaten = {}  # prey -> its candidate, in the order of the first catch
-        for a in self.prev_agents:
-            if not is_pred(a) or a not in state:
-                continue
-            f = rows.get(a, 0)
-            if not f & ROW_ATE:
-                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
-                continue
-            pos = state[a][0]
-            here = [(q, c) for q, cs in gone_prey.items() for c in cs if c["cell"] == pos and (q not in eaten or eaten[q] is c)]
-            if not here:
-                self.inexact_chains += 1
-                continue
-            child = self._child_energy_hint(a, rows, state, newborn)
-            want = state[a][1] + child
-            q, c = min(here, key=lambda o: abs((E[a] + self._gain(min(float(o[1]["e"]), self.cap_prey), prev[a][3])) - want))
-            eaten.setdefault(q, c)
-            gain = self._gain(min(float(c["e"]), self.cap_prey), prev[a][3])
+            gain = self._donate(a, 1, float(g[1]), order, pos, E, termd) if self.coop else self._gain(float(g[1]), prev[a][3])
             E[a] += gain
             deltas[a]["eat"] = gain
+            g[1] = 0.0
+            self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
+            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": g[0], "energy_after": float(E[a])})
+            if not rows.get(a, 0) & ROW_ATE:
+                self.inexact_chains += 1
+        # Step 4c (MR:720-788): predators, predator_positions order.  The first prey of `agent_positions` on the cell is caught —
+        # a prey stays there until Step 5, also one that starved or was caught before in this step
+        for a in order[0]:
+            if a in termd:
+                continue
+            q = next((o for o in order[1] if pos[o] == pos[a]), None)
+            if q is not None and self.sat_cd >= 0 and t < self.sat_until.get(a, 0):
+                q = None  # still digesting (MR:734-740)
+            if q is None:
+                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
+                if rows.get(a, 0) & ROW_ATE:
+                    self.inexact_chains += 1
+                continue
+            pe = float(E[q])
+            gain = self._donate(a, 0, pe, order, pos, E, termd) if self.coop else self._gain(min(pe, self.cap_prey), prev[a][3])
+            E[a] += gain
+            deltas[a]["eat"] = gain
+            if self.sat_cd > 0:
+                self.sat_until[a] = int(t) + self.sat_cd  # MR:756-757
             self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
-            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "energy_after": float(E[a])})
-        # the records close in the reference's order: starvation (Step 4a, `agent_energies` order), then the catches (Step 4c)
-        for a in self.prev_agents:
-            if a in state:
-                continue
-            if is_pred(a):
-                self._finalize(a, "starved", t)
-                continue
-            c = eaten.get(a)
-            if c is not None and c["e"] > 0:
-                continue  # caught alive: closed below, in the predators' order (a starved prey is closed here, the catch changes nothing)
-            if c is None and all(x["e"] > 0 for x in gone_prey[a]):
-                self.inexact_chains += 1  # gone, but it can neither have starved nor did a predator take it
-            self._finalize(a, "starved", t)
-        for q, c in eaten.items():
-            if c["grass"] is not None:  # its last meal (MR:825-833)
-                self.agent_event_log[q]["eating_events"].append({"t": int(t), "id_eaten": c["grass"][0], "energy_after": float(c["grass"][1])})
+            termd.add(q)
             self._finalize(q, "eaten", t)
+            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "energy_after": float(E[a])})
+            if not rows.get(a, 0) & ROW_ATE:
+                self.inexact_chains += 1
+        # what the device reports: who is gone, where the survivors stand
+        for a in self.prev_agents:
+            if (a in termd) != (a not in state) or (a in state and pos[a] != state[a][0]):
+                self.inexact_chains += 1
         # Step 6 (MR:836-1010): births, predators first; the k-th newborn row of a species belongs to the k-th parent
         new_agents = list(newborn)
         for s, role in enumerate(("predator", "prey")):
-            parents = [a for a in self.prev_agents if (is_pred(a) == (s == 0)) and a in state and rows.get(a, 0) & ROW_REPRODUCED]
+            parents = [a for a in order[s] if a in state and rows.get(a, 0) & ROW_REPRODUCED]
             children = [a for a in new_agents if is_pred(a) == (s == 0)]
             if len(parents) != len(children):
                 self.inexact_chains += 1
@@ -542,9 +559,9 @@ class TraitEventRecorder:
                 self.inexact_chains += 1
         step_data = {}
         for a in agents:
-            pos, e, ag, _, _ = state[a]
+            p, e, ag, _, _ = state[a]
             d = deltas[a]
-            step_data[a] = {"position": pos, "energy": e, "energy_decay": d["decay"], "energy_movement": d["move"],
+            step_data[a] = {"position": p, "energy": e, "energy_decay": d["decay"], "energy_movement": d["move"],
                             "energy_eating": d["eat"], "energy_reproduction": d["repro"], "age": ag,
                             "offspring_count": self.agent_offspring_counts[a],
                             "offspring_ids": self.agent_live_offspring_ids.get(a, []), "parent": self.agent_parents.get(a)}
@@ -564,17 +581,6 @@ class TraitEventRecorder:
             role = "predator" if s == 0 else "prey"
             fraction = float(self.cfg.get("founder_genome", {}).get(role, {}).get("offspring_investment_fraction_mean", 0.35))
         return float(parent_energy) * fraction
-
-    def _child_energy_hint(self, a, rows, state, newborn):
-        """what a parent paid for this step's child (only used to choose between candidate prey)"""
-        if not rows.get(a, 0) & ROW_REPRODUCED:
-            return 0.0
-        if self.init_e is not None:
-            return self.init_e[0]
-        parents = [p for p in self.prev_agents if "predator" in p and p in state and rows.get(p, 0) & ROW_REPRODUCED]
-        kids = [k for k in newborn if "predator" in k]
-        k = parents.index(a)
-        return state[kids[k]][1] if k < len(kids) else 0.0
 
     def export(self, path):
         with open(path, "w", encoding="utf-8") as f:

@@ -102,7 +102,6 @@ def test_snapshot_restore_carries_the_exporters():
 
 
 TRAIT_CASES = sorted(os.path.basename(p)[len("trait_events_"):-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "trait_events_*.json.gz")))
-TRAIT_CASES = [c for c in TRAIT_CASES if not c.startswith("coop")]
 
 
 def _replay_trait(case):
