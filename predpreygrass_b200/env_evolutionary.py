@@ -804,6 +804,16 @@ class PredPreyGrassCadence(PredPreyGrassEco):
         self._all = np.ones(n_act, np.float32)
         self._stay_only = np.zeros(n_act, np.float32)
         self._stay_only[self._stay_action_index] = 1.0
+        if config.get("record_agent_events", True):  # agent_event_log, and per_step_agent_data with "record_step_data" (CAD:83,422)
+            from .event_log import TraitEventRecorder
+
+            self._events = TraitEventRecorder(config, self.action_to_move_tuple_agents, self.grid_size, "speed")
+
+    def _event_state(self):
+        """as the base class's, with the move accumulator (CAD:183-186) in the last place"""
+        state, grass = super()._event_state()
+        acc = self.agent_move_accumulator
+        return {a: v[:4] + (acc[a],) for a, v in state.items()}, grass
 
     def _mask_dicts(self, out, obs):
         """window + row flag -> the reference's observation dict (CAD:746-753)"""
@@ -823,6 +833,9 @@ class PredPreyGrassCadence(PredPreyGrassEco):
             st = self._read()
             for s in range(2):
                 self._episode_speeds[s].extend(float(v) for v in st["speed"][s])
+        if self._events is not None:
+            state, grass = self._event_state()
+            self._events.reset(state, self.agents, grass)
         return self._mask_dicts(out, obs), {}
 
     def step(self, action_dict):

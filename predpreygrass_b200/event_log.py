@@ -46,7 +46,9 @@ class EcoEventRecorder:
         self.cap_prey = float(g("max_energy_gain_per_prey", float("inf")))
         self.cap_grass = float(g("max_energy_gain_per_grass", float("inf")))
         self.init_e = (float(g("initial_energy_predator")), float(g("initial_energy_prey")))
-        self.max_age = g("max_agent_age", None)
+        self.max_age = {"predator": 120, "prey": 100}  # ECO:52-63: defaults for the roles a configured dict leaves out
+        if isinstance(g("max_agent_age"), dict):
+            self.max_age.update(g("max_agent_age"))
         self.carcass_age = g("carcass_only_predator_age", None)
         self.moves, self.G, self.thr = action_to_move, int(grid_size), float(speed_distance_threshold)
         self.jump_low, self.jump_high = int(g("slow_max_move_distance", 1)), int(g("fast_max_move_distance", 2))  # ECO:551-557
@@ -346,7 +348,17 @@ class TraitEventRecorder:
         g = config.get
         self.cfg, self.trait = config, trait
         mr, inv = trait == "metabolic_rate", trait == "offspring_investment_fraction"
-        if inv:
+        self.cad = trait == "speed"  # eco_evolutionary_cadence: the speed genome sets the move rate
+        if self.cad:
+            self.speed_coeff = float(g("metabolic_speed_coeff", 1.0))  # CAD:79
+            self.exponent = float(g("movement_speed_cost_exponent", 2.0))
+            self.max_cooldown = g("max_cooldown", 10)  # CAD:114
+            self.max_age = {"predator": 120, "prey": 100}  # CAD:59-70
+            if isinstance(g("max_agent_age"), dict):
+                self.max_age.update(g("max_agent_age"))
+            self.cap_grass = float(g("max_energy_gain_per_grass", float("inf")))  # CAD:912
+            self.record_step_data = bool(g("record_step_data", False))  # CAD:83,422
+        if inv or self.cad:
             self.loss = (g("energy_loss_per_step_predator"), g("energy_loss_per_step_prey"))  # INV:54-55
         else:
             self.loss = (g("basal_energy_cost_predator"), g("basal_energy_cost_prey"))  # MR:50-51
@@ -357,19 +369,29 @@ class TraitEventRecorder:
         self.cap_prey = float(g("max_energy_gain_per_prey", float("inf")))  # MR:64
         self.init_e = None if inv else (g("initial_energy_predator"), g("initial_energy_prey"))
         self.coop = trait == "cooperation_rate"
-        if self.coop:
-            self.cap_prey = float("inf")  # COOP:776-777: the whole prey
+        if self.coop or self.cad:
+            self.cap_prey = float("inf")  # COOP:776-777, CAD:856-857: the whole prey
         self.coop_range = int(g("cooperation_range", 2))  # COOP:93
-        self.sat_cd = -1 if self.coop else int(g("predator_satiation_cooldown", 0))  # MR:62
+        self.sat_cd = -1 if (self.coop or self.cad) else int(g("predator_satiation_cooldown", 0))  # MR:62
         self.moves, self.G = action_to_move, int(grid_size)
         self.reset({}, [], {})
 
-    def _cost(self, s, old, new):
-        """`_get_movement_energy_cost` (MR:516-523)"""
+    def _cost(self, s, old, new, speed=None):
+        """`_get_movement_energy_cost` (MR:516-523; CAD:598-606 with the factor speed ** exponent)"""
         distance = float(np.linalg.norm(np.array(new) - np.array(old)))
         if distance <= 0:
             return 0.0
+        if self.cad:
+            return self.move_cost[s] * distance * (1.0 if speed is None else float(speed) ** self.exponent)
         return self.move_cost[s] * distance
+
+    def _move_rate(self, speed):
+        """`_get_agent_move_rate` (CAD:556-578)"""
+        if speed is None:
+            return 1.0
+        normalized = max(0.0, min(1.0, float(speed)))
+        min_rate = 1.0 / float(self.max_cooldown)
+        return min_rate + normalized * (1.0 - min_rate)
 
     def _target(self, pos, action):
         """`_get_move` without the occupancy test (MR:617-630)"""
@@ -407,6 +429,8 @@ class TraitEventRecorder:
             "eating_events": [], "reproduction_events": [], "reward_events": [], "diet_events": [], "lifecycle_events": [],
             "genome": None if value is None else {self.trait: float(value)},
         }
+        if self.cad:
+            del self.agent_event_log[agent]["diet_events"]  # CAD:1327-1338
 
     def _finalize(self, agent, cause, step):
         """the event-log part of `_finalize_agent_record` (MR:1197-1234): a no-op for a record that is already closed"""
@@ -460,29 +484,43 @@ class TraitEventRecorder:
             s = 0 if is_pred(a) else 1
             rate = prev[a][3]
             decay = self.loss[s] * (float(rate) if rate is not None else 1.0) if self.scale_loss else self.loss[s]
+            if self.cad and rate is not None and self.speed_coeff > 0.0:
+                decay *= 1.0 + self.speed_coeff * float(rate)  # CAD:626-633
             E[a] = prev[a][1] - decay
             deltas[a] = {"decay": -decay, "move": 0.0, "eat": 0.0, "repro": 0.0}
             pos[a] = prev[a][0]
             cell[s][pos[a]] = np.float32(E[a])
+        termd = set()
+        if self.cad:  # CAD:638-650, 972-1000: age caps, after everybody's basal cost
+            for a in self.prev_agents:
+                limit = self.max_age.get("predator" if is_pred(a) else "prey")
+                if isinstance(limit, (int, float)) and limit >= 0 and prev[a][2] + 1 >= limit:
+                    termd.add(a)
+                    cell[0 if is_pred(a) else 1][pos[a]] = np.float32(0.0)
+                    self.agent_event_log[a]["lifecycle_events"].append({"t": int(t), "event": "max_age_reached", "age": int(prev[a][2] + 1)})
+                    self._finalize(a, "max_age", t)
         # Step 2 (MR:576-584)
         g_now = {c: [name, min(e + self.grass_gain, self.grass_max)] for c, (name, e) in self.prev_grass.items()}
         # Step 3 (MR:586-615): moves in the order of the action dict; a target whose own-species layer reads > 0 blocks
         for a, action in action_dict.items():
-            if a not in prev:
+            if a not in prev or a in termd:
                 continue
             s = 0 if is_pred(a) else 1
+            if self.cad:  # CAD:674-681: the move happens once the accumulator reaches 1
+                acc = prev[a][4] + self._move_rate(prev[a][3])
+                if acc < 1.0:
+                    continue
             old = pos[a]
             new = self._target(old, action)
             if cell[s].get(new, 0.0) > 0:
                 new = old
-            cost = self._cost(s, old, new)
+            cost = self._cost(s, old, new, prev[a][3])
             E[a] -= cost
             deltas[a]["move"] -= cost
             cell[s][old] = np.float32(0.0)
             cell[s][new] = np.float32(E[a])
             pos[a] = new
         # Step 4a (MR:274-280): starvation, `agent_energies` order
-        termd = set()
         for a in self.prev_agents:
             if E[a] <= 0:
                 termd.add(a)
@@ -495,12 +533,21 @@ class TraitEventRecorder:
             if g is None:
                 self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
                 continue
-            gain = self._donate(a, 1, float(g[1]), order, pos, E, termd) if self.coop else self._gain(float(g[1]), prev[a][3])
+            if self.cad:  # CAD:909-925: a capped bite, the rest stays on the patch
+                gain = min(float(g[1]), self.cap_grass)
+                rest = float(g[1]) - gain
+            else:
+                gain = self._donate(a, 1, float(g[1]), order, pos, E, termd) if self.coop else self._gain(float(g[1]), prev[a][3])
+                rest = 0.0
             E[a] += gain
             deltas[a]["eat"] = gain
-            g[1] = 0.0
+            g[1] = rest if rest > 0.0 else 0.0
             self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
-            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": g[0], "energy_after": float(E[a])})
+            if self.cad:
+                self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": g[0], "alive_before_bite": True,
+                                                                 "bite_size": float(gain), "energy_after": float(E[a])})
+            else:
+                self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": g[0], "energy_after": float(E[a])})
             if not rows.get(a, 0) & ROW_ATE:
                 self.inexact_chains += 1
         # Step 4c (MR:720-788): predators, predator_positions order.  The first prey of `agent_positions` on the cell is caught —
@@ -508,7 +555,14 @@ class TraitEventRecorder:
         for a in order[0]:
             if a in termd:
                 continue
-            q = next((o for o in order[1] if pos[o] == pos[a]), None)
+            if self.cad:  # CAD:837-848: the nearest prey within Chebyshev distance 1, the first of `agent_positions` on ties
+                q, best = None, None
+                for o in order[1]:
+                    d = max(abs(pos[a][0] - pos[o][0]), abs(pos[a][1] - pos[o][1]))
+                    if d <= 1 and (best is None or d < best):
+                        q, best = o, d
+            else:
+                q = next((o for o in order[1] if pos[o] == pos[a]), None)
             if q is not None and self.sat_cd >= 0 and t < self.sat_until.get(a, 0):
                 q = None  # still digesting (MR:734-740)
             if q is None:
@@ -525,7 +579,10 @@ class TraitEventRecorder:
             self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
             termd.add(q)
             self._finalize(q, "eaten", t)
-            self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "energy_after": float(E[a])})
+            if self.cad:
+                self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "bite_size": float(pe), "energy_after": float(E[a])})
+            else:
+                self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "energy_after": float(E[a])})
             if not rows.get(a, 0) & ROW_ATE:
                 self.inexact_chains += 1
         # what the device reports: who is gone, where the survivors stand
@@ -565,7 +622,8 @@ class TraitEventRecorder:
                             "energy_eating": d["eat"], "energy_reproduction": d["repro"], "age": ag,
                             "offspring_count": self.agent_offspring_counts[a],
                             "offspring_ids": self.agent_live_offspring_ids.get(a, []), "parent": self.agent_parents.get(a)}
-        self.per_step_agent_data.append(step_data)
+        if not self.cad or self.record_step_data:
+            self.per_step_agent_data.append(step_data)
         if time_limit:  # MR:453-454: every record still open is closed with the step counter already advanced
             for a in list(self.live_order):
                 self._finalize(a, "time_limit", int(t) + 1)

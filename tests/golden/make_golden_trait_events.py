@@ -25,12 +25,14 @@ sys.path.insert(0, REF)
 
 PKG = {"mr": "predpreygrass.evolutionary.eco_evolutionary_metabolic_rate",
        "inv": "predpreygrass.evolutionary.eco_evolutionary_investment",
-       "coop": "predpreygrass.evolutionary.eco_evolutionary_cooperation"}
+       "coop": "predpreygrass.evolutionary.eco_evolutionary_cooperation",
+       "cad": "predpreygrass.evolutionary.eco_evolutionary_cadence"}
 NAMES = ("predator", "prey")
-MAX_STEPS = {"mr_density_s5": 80, "mr_crowded_s1": 50, "inv_crowded_s4": 58, "coop_crowded_s3": 86, "mr_rich_s3": 60, "coop_share_s2": 40, "inv_nogenome_s6": 40}
+MAX_STEPS = {"mr_density_s5": 80, "mr_crowded_s1": 50, "inv_crowded_s4": 58, "coop_crowded_s3": 86, "mr_rich_s3": 60, "coop_share_s2": 40, "inv_nogenome_s6": 40, "cad_rich_s3": 60, "cad_crowded_s4": 60, "cad_nogenome_s6": 50}
 CASES = ("mr_default_s1", "mr_crowded_s1", "mr_density_s5", "mr_nogenome_s1", "mr_trunc_s2", "mr_rich_s3",
          "inv_default_s1", "inv_crowded_s4", "inv_nogenome_s6",
-         "coop_default_s1", "coop_crowded_s3", "coop_trunc_s4", "coop_share_s2")
+         "coop_default_s1", "coop_crowded_s3", "coop_trunc_s4", "coop_share_s2",
+         "cad_default_s1", "cad_aging_s5", "cad_crowded_s4", "cad_rich_s3", "cad_nogenome_s6", "cad_trunc_s7")
 
 
 def sha(arrs):
@@ -59,6 +61,8 @@ def main():
         z = np.load(os.path.join(HERE, case + ".npz"))
         cfg = json.loads(str(z["cfg_json"]))
         cfg.pop("variant", None)
+        if fam == "cad":
+            cfg["record_step_data"] = True  # CAD:83,422: per_step_agent_data is optional there
         env = mod.PredPreyGrass(cfg)
         env.reset(seed=int(z["seed"]))
         n, ended, metrics = 0, False, None
@@ -67,7 +71,8 @@ def main():
             acts = {f"{NAMES[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])}
             obs, rew, term, trunc, infos = env.step(acts)
             keys = sorted(obs, key=lambda a: (a.startswith("prey"), int(a.rsplit("_", 1)[1])))
-            assert np.array_equal(sha([obs[k] for k in keys]), z["obs_sha"][t]), (case, t)  # same episode as the recording
+            win = (lambda o: o["observations"]) if fam == "cad" else (lambda o: o)
+            assert np.array_equal(sha([win(obs[k]) for k in keys]), z["obs_sha"][t]), (case, t)  # same episode as the recording
             n = t + 1
             if term["__all__"] or trunc["__all__"]:
                 ended = True

@@ -105,13 +105,16 @@ TRAIT_CASES = sorted(os.path.basename(p)[len("trait_events_"):-len(".json.gz")] 
 
 
 def _replay_trait(case):
-    """the exporters of PredPreyGrassMetabolicRate / Investment against recordings of the unmodified reference classes
+    """the exporters of PredPreyGrassMetabolicRate / Investment / Cooperation / Cadence against recordings of the unmodified reference classes
     (tests/golden/trait_events_*.json.gz, made by tests/golden/make_golden_trait_events.py), and the order of the agent records"""
     from predpreygrass_b200 import env_evolutionary as E
 
     z, cfg = load_golden(case)
-    cls = {"mr": E.PredPreyGrassMetabolicRate, "inv": E.PredPreyGrassInvestment, "coop": E.PredPreyGrassCooperation}[cfg.pop("variant")]
+    cls = {"mr": E.PredPreyGrassMetabolicRate, "inv": E.PredPreyGrassInvestment, "coop": E.PredPreyGrassCooperation,
+           "cad": E.PredPreyGrassCadence}[cfg.pop("variant")]
     cfg["cap_live"] = (min(cfg["n_possible_predators"], 250), min(cfg["n_possible_prey"], 450))
+    if cls is E.PredPreyGrassCadence:
+        cfg["record_step_data"] = True  # CAD:83,422: per_step_agent_data is optional there
     want = json.loads(gzip.open(os.path.join(GOLDEN_DIR, f"trait_events_{case}.json.gz")).read())
     env = cls(cfg)
     env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})

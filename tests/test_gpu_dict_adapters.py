@@ -275,7 +275,7 @@ def test_cadence_dict_adapter_replays_reference_episode(name):
         if term["__all__"] or trunc["__all__"]:
             want = json.loads(str(z["metrics_json"]))
             got = infos["__all__"]["training_metrics"]
-            assert set(got) <= set(want), (name, sorted(set(got) - set(want)))
+            assert sorted(got) == sorted(want), (name, sorted(set(got) ^ set(want)))
             for k, v in got.items():
                 assert v == pytest.approx(want[k], rel=1e-9, abs=1e-12), (name, k, v, want[k])
             break
