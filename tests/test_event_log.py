@@ -156,3 +156,46 @@ def test_trait_event_log_host_logic_over_the_oracle(case, monkeypatch):
 @pytest.mark.parametrize("case", TRAIT_CASES)
 def test_trait_event_log_on_the_device(case):
     _replay_trait(case)
+
+
+_CROWDED = dict(grid_size=9, initial_num_grass=24, n_initial_active_predators=6, n_initial_active_prey=14,
+                predator_creation_energy_threshold=6.0, prey_creation_energy_threshold=4.5, energy_gain_per_step_grass=0.3,
+                predator_obs_range=5, prey_obs_range=7, n_possible_predators=300, n_possible_prey=400, max_steps=50)
+_RICH = dict(energy_gain_per_step_grass=0.3, prey_creation_energy_threshold=5.0, predator_creation_energy_threshold=8.0, max_steps=60)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("fam", ["eco", "mr", "inv", "coop", "cad"])
+def test_recorders_agree_with_the_backend_on_random_episodes(fam, seed, monkeypatch):
+    """Beyond the recordings: on seeded random episodes (crowded 9 x 9 worlds with shuffled action dicts, reproduction-heavy
+    worlds, carcasses / age caps / juvenile predators for ECO) the exporters' host replay must land on the backend's state every
+    step — who is gone, the survivors' cells and float64 energies, the eating / reproduction flags (`inexact_chains` == 0)."""
+    import predpreygrass_b200.batched as batched
+    from predpreygrass_b200 import config as Cfg
+    from predpreygrass_b200 import env_evolutionary as E
+    from tests.oracle_batch import OracleBatch
+
+    monkeypatch.setattr(batched, "BatchedPredPreyGrass", OracleBatch)
+    cls, base = {"eco": (E.PredPreyGrassEco, Cfg.ECO_CONFIG), "mr": (E.PredPreyGrassMetabolicRate, Cfg.METABOLIC_CONFIG),
+                 "inv": (E.PredPreyGrassInvestment, Cfg.INVESTMENT_CONFIG), "coop": (E.PredPreyGrassCooperation, Cfg.COOPERATION_CONFIG),
+                 "cad": (E.PredPreyGrassCadence, Cfg.CADENCE_CONFIG)}[fam]
+    over = dict(_CROWDED if seed % 2 else _RICH)
+    if fam == "eco":
+        over.update(max_energy_gain_per_prey=[1.0, 2.5, float("inf")][seed % 3], max_agent_age={"predator": [None, 30][seed % 2], "prey": 25},
+                    carcass_only_predator_age={"predator": [None, 5][seed % 2]})
+    cfg = dict(base, **over, cap_live=(250, 450), record_step_data=True)
+    env = cls(cfg)
+    rng = np.random.default_rng(100 + seed)
+    env.reset(seed=seed)
+    steps = 0
+    for _ in range(over["max_steps"]):
+        keys = list(env.agents)
+        if seed % 2:
+            rng.shuffle(keys)
+        *_, term, trunc, _ = env.step({a: int(rng.integers(env.action_spaces[a].n)) for a in keys})
+        steps += 1
+        if term["__all__"] or trunc["__all__"]:
+            break
+    assert steps >= 2 and env._events.inexact_chains == 0, (fam, seed, steps, env._events.inexact_chains)
+    assert len(env.per_step_agent_data) == steps and len(env.agent_event_log) >= len(env.per_step_agent_data[0])
+    env.close()
