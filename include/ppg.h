@@ -367,12 +367,13 @@ int ppg_random_actions(ppg_handle h, uint64_t seed, int32_t* actions_pred, int32
 int ppg_rollout_random(ppg_handle* handles, int32_t n_handles, void** cuda_streams, int32_t n_steps, uint64_t seed);
 
 /* Launch chain of a step (process-wide switch, returns the previous setting).  off (default): plain stream order between the
- * steps.  on (PPG_PDL_CHAIN=1; EXPERIMENTAL): the action kernel and the step kernel are launched with programmatic stream
- * serialization behind the observation kernel of the step before, i.e. their CTAs become resident in the slots that kernel's
- * tail leaves free and wait there (griddepcontrol.wait) until it has completed, which hides the launch ramp (+2 % on the BASE
- * configuration).  It is bit-exact only when the host synchronises between the steps: with several steps queued the
- * trajectories diverge from the oracle's (tests/test_gpu_rollout.py), so it is not used by anything that is measured or shipped.
- * ppg_rollout_random with n_handles > 1 always runs with the chain off.  No counterpart in the reference (there is no device). */
+ * steps.  on (PPG_PDL_CHAIN=1): the action kernel and the step kernel are launched with programmatic stream serialization
+ * behind the observation kernel of the step before, i.e. their CTAs become resident in the slots that kernel's tail leaves
+ * free and wait there (griddepcontrol.wait) until it has completed, which hides the launch ramp (+1 % on the BASE configuration).
+ * Results are identical (tests/test_gpu_rollout.py: 55 queued steps against the oracle, chain on and off); the switch is off by
+ * default because the last fix to this path (a load the compiler had hoisted above griddepcontrol.wait in the action kernels)
+ * landed after the round's measurements.  ppg_rollout_random with n_handles > 1 always runs with the chain off: a parked grid
+ * holds SM slots the other streams could use.  No counterpart in the reference (there is no device). */
 int ppg_set_pdl_chain(int32_t on);
 
 int ppg_get_buffers(ppg_handle h, ppg_buffers* out);

@@ -250,9 +250,9 @@ struct StepParams {
 #ifdef __CUDACC__
 extern int g_pdl_chain;  // ppg_api.cu: -1 = not read yet, 0 = off, 1 = on (ppg_set_pdl_chain)
 inline bool pdl_chain_enabled() {
-  // OFF by default: with the chain on and several steps queued without a host synchronisation the trajectories diverge from
-  // the oracle's (tests/test_gpu_rollout.py found it at the end of round 2; with a synchronisation per step, or with the chain
-  // off, they are bit-exact).  PPG_PDL_CHAIN=1 / ppg_set_pdl_chain(1) remain for experiments only.
+  // OFF by default (include/ppg.h ppg_set_pdl_chain): tests/test_gpu_rollout.py found at the end of round 2 that with the chain
+  // on and several steps queued the action kernels read a stale row count (a load hoisted above griddepcontrol.wait); that is
+  // fixed and tested, but everything measured in the round after the finding ran with the chain off.
   if (g_pdl_chain < 0) { const char* ev = getenv("PPG_PDL_CHAIN"); g_pdl_chain = ev ? (atoi(ev) != 0) : 0; }
   return g_pdl_chain != 0;
 }

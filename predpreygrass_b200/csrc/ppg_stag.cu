@@ -1106,7 +1106,12 @@ __global__ void ppg_random_actions_stag_kernel(const int32_t* __restrict__ n_row
                                                int ar0, int ar1) {
   allow_dependent_launch();       // PDL chain (see ppg_random_actions_kernel)
   wait_for_stream_predecessor();
-  const int n0 = n_rows[0] + n_rows[2], n1 = n_rows[1] + n_rows[3];
+  // read through a volatile pointer: as a plain load from a `const __restrict__` pointer the compiler hoisted n_rows[0] ABOVE
+  // griddepcontrol.wait (SASS: LDG.E.CONSTANT before ACQBULK), i.e. the row count of the step before was read while that
+  // step's kernels were still running — with the launch chain on and several steps queued the actions then covered the wrong
+  // number of rows (tests/test_gpu_rollout.py)
+  const volatile int32_t* const nr = n_rows;
+  const int n0 = nr[0] + nr[2], n1 = nr[1] + nr[3];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const int s = i >= n0;
     const int row = s ? i - n0 : i;

@@ -21,14 +21,14 @@ def _factory(variant):
     return lambda off: make_config(dict(STAG_CONFIG, max_steps=40), variant=VARIANT_STAG, cap_live=(64, 192), seed=9, env_index_base=off)
 
 
-# (variant, env groups, launch chain, steps per call).  The launch chain (ppg_set_pdl_chain) is OFF by default and in everything that
-# is measured: with it on, this test FAILED for every variant when the 55 steps were queued in one call (row counts drifting
-# from the oracle's after a few steps) and passed with one call — one host synchronisation — per step; both are kept here, the
-# failing combination as the documented reason for the default (xfail, not strict: it is a race).
+# (variant, env groups, launch chain, steps per call).  History of the launch chain (ppg_set_pdl_chain): this test FAILED for every
+# variant with the chain on and the 55 steps queued in one call (row counts drifting from the oracle's after a few steps) while
+# the per-step parity suite, which synchronises after every step, was green.  Cause (SASS): in the action kernels the compiler had
+# hoisted the load of n_rows[0] — a `const __restrict__` pointer — above griddepcontrol.wait, so the actions of step t+1 covered
+# the row count of step t-1 whenever the previous step's kernels were still running.  Fixed (volatile load after the wait); the
+# chain-on cases pass since and are part of the suite.  The chain stays off by default (include/ppg.h).
 CASES = [(v, g, 0, c) for v in ("base", "eco", "stag") for g in (1, 2) for c in (55, 1) if not (g == 2 and c == 1)]
-CASES += [(v, 1, 1, 1) for v in ("base", "eco", "stag")]
-CASES += [pytest.param(v, 1, 1, 55, marks=pytest.mark.xfail(strict=False, reason="launch chain with queued steps: not bit-exact (why it is off)"))
-          for v in ("base",)]
+CASES += [(v, 1, 1, c) for v in ("base", "eco", "stag") for c in (1, 55)]
 
 
 @pytest.mark.parametrize("variant,groups,pdl,chunk", CASES)
