@@ -456,6 +456,8 @@ def main():
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": cfgb, "groups": args.groups, "host_cores_bound": bound, "l2_note": res["l2_note"],
+            # launch chain between steps (include/ppg.h ppg_set_pdl_chain): off unless PPG_PDL_CHAIN=1, and never used with env groups
+            "launch_chain": "on" if (args.groups == 1 and os.environ.get("PPG_PDL_CHAIN", "0") not in ("", "0")) else "off",
             "env_steps_per_s": res["env_steps_per_s"],
             "mean_live_agents_per_env": res["mean_live_agents_per_env"],
             "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": res.get("e2e"), "e2e_device_policy": res.get("e2e_device_policy"),
