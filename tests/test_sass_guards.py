@@ -37,3 +37,8 @@ def test_no_global_access_before_griddepcontrol_wait():
             n += 1
     assert checked >= 30, checked  # every step kernel instantiation and both action kernels carry the wait
     assert not bad, bad
+    # the observation kernel triggers its dependents at its start and must itself wait for the step kernel before it exits
+    # (round-1 advisor finding): both instructions are in every instantiation
+    obs = re.split(r"Function : ", sass)
+    obs = [f for f in obs if f.startswith("_ZN3ppg14ppg_obs_kernel")]
+    assert len(obs) >= 6 and all("PREEXIT" in f and "ACQBULK" in f for f in obs), len(obs)
