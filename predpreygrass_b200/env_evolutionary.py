@@ -368,6 +368,27 @@ class PredPreyGrassEco(_RowDictEnv):
         if snapshot.get("episode_speeds") is not None:
             self._episode_speeds = copy.deepcopy(snapshot["episode_speeds"])
 
+    def get_all_agent_stats(self):
+        """ECO:1676-1682: copies of all agent records (`agent_stats_live` then `agent_stats_completed`), rebuilt by the event recorder"""
+        if self._events is None or not hasattr(self._events, "get_all_agent_stats"):
+            raise RuntimeError("agent records are kept by the event recorder (record_agent_events=False)")
+        return self._events.get_all_agent_stats()
+
+    def get_total_offspring_by_type(self):
+        """ECO:1705-1712"""
+        if self._events is None or not hasattr(self._events, "get_total_offspring_by_type"):
+            raise RuntimeError("agent records are kept by the event recorder (record_agent_events=False)")
+        return self._events.get_total_offspring_by_type()
+
+    def get_total_energy_by_type(self):
+        """ECO:1684-1703: total energy of the live predators, the live prey and the grass"""
+        st = self._read()
+        totals = {"predator": 0.0, "prey": 0.0, "grass": sum(float(e) for e in st["grass_energy"])}
+        for s, role in enumerate(("predator", "prey")):
+            for e in st["energy"][s]:
+                totals[role] += float(e)
+        return totals
+
     def export_agent_event_log(self, path):
         """ECO:1575-1597"""
         if self._events is None:

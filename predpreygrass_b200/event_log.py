@@ -411,6 +411,8 @@ class TraitEventRecorder:
         self.agent_parents, self.agent_offspring_counts, self.agent_live_offspring_ids = {}, {}, {}
         self.cumulative_reward = {}
         self.live_order, self.completed_order = [], []  # `agent_stats_live` / `agent_stats_completed` key order
+        self.stats = {}        # the records themselves
+        self.step_reward = {}  # `self.rewards` of the running step (what `_finalize_agent_record` adds once more, MR:1202-1204)
         self.sat_until = {}  # agent_satiation_until (MR:134)
         self.energy_donated, self.kin_donation = [0.0, 0.0], [0.0, 0.0]  # total_energy_donated / total_kin_donation (COOP:159-162)
         self.inexact_chains = 0
@@ -431,6 +433,19 @@ class TraitEventRecorder:
         }
         if self.cad:
             del self.agent_event_log[agent]["diet_events"]  # CAD:1327-1338
+        # `agent_stats_live[agent]` (MR:1166-1192, COOP:1183-1185, CAD:1339-1362)
+        rec = {"agent_id": agent, "birth_step": t, "parent": parent, "offspring_count": 0, "offspring_ids": self.agent_live_offspring_ids[agent],
+               "distance_traveled": 0.0, "movement_energy_spent": 0.0, "times_ate": 0, "energy_gained": 0.0, "avg_energy_sum": 0.0,
+               "avg_energy_steps": 0, "cumulative_reward": 0.0, "policy_group": "predator" if "predator" in agent else "prey",
+               "genome": None if value is None else {self.trait: float(value)}, "death_step": None, "death_cause": None, "avg_energy": 0.0}
+        if self.cad:
+            rec.update(max_age=self.max_age.get(rec["policy_group"]), age_expired_step=None)
+        else:
+            rec.update(offspring_initial_energy=0.0, reproduction_energy_invested_sum=0.0, reproduction_energy_invested_count=0,
+                       parent_energy_after_reproduction_sum=0.0, parent_energy_after_reproduction_count=0)
+        if self.coop:
+            rec.update(energy_donated=0.0, energy_donated_to_kin=0.0, energy_received=0.0)
+        self.stats[agent] = rec
 
     def _finalize(self, agent, cause, step):
         """the event-log part of `_finalize_agent_record` (MR:1197-1234): a no-op for a record that is already closed"""
@@ -438,6 +453,12 @@ class TraitEventRecorder:
             return
         self.live_order.remove(agent)
         self.completed_order.append(agent)
+        rec = self.stats[agent]
+        rec["cumulative_reward"] += self.step_reward.get(agent, 0.0)  # MR:1202-1204: the step's reward is added once more
+        rec["death_cause"] = cause
+        rec["death_step"] = step
+        rec["offspring_count"] = self.agent_offspring_counts.get(agent, rec["offspring_count"])
+        rec["avg_energy"] = rec["avg_energy_sum"] / max(rec["avg_energy_steps"], 1)
         evt = self.agent_event_log[agent]
         evt["death_step"] = step
         evt["death_cause"] = cause
@@ -445,6 +466,21 @@ class TraitEventRecorder:
 
     def record_order(self):
         return list(self.live_order) + list(self.completed_order)
+
+    def get_all_agent_stats(self):
+        """`get_all_agent_stats` (MR:1406-1412): copies of all agent records, live ones first"""
+        out = {}
+        for a in self.record_order():
+            rec = dict(self.stats[a])
+            rec["offspring_ids"] = list(rec["offspring_ids"])
+            out[a] = rec
+        return out
+
+    def get_total_offspring_by_type(self):
+        counts = {"predator": 0, "prey": 0}
+        for a in self.record_order():
+            counts[self.stats[a]["policy_group"]] += self.stats[a]["offspring_count"]
+        return counts
 
     def _donate(self, a, s, gain, order, pos, E, termd):
         """`_apply_cooperative_donation` (COOP:537-589): a cooperation_rate share of a positive gain goes, in equal parts, to the
@@ -463,9 +499,14 @@ class TraitEventRecorder:
         kin = 0.0
         for o in nbrs:
             E[o] += share
+            if o in self.live_order:
+                self.stats[o]["energy_received"] += share
             pa, pb = self.agent_parents.get(a), self.agent_parents.get(o)
             if o == pa or a == pb or (pa is not None and pa == pb):  # `_is_kin` (COOP:529-535)
                 kin += share
+        if a in self.live_order:
+            self.stats[a]["energy_donated"] += total
+            self.stats[a]["energy_donated_to_kin"] += kin
         self.energy_donated[s] += total
         self.kin_donation[s] += kin
         return gain - total
@@ -478,6 +519,7 @@ class TraitEventRecorder:
         is_pred = lambda a: "predator" in a  # noqa: E731
         order = ([a for a in self.prev_agents if is_pred(a)], [a for a in self.prev_agents if not is_pred(a)])  # *_positions order
         E, deltas, pos = {}, {}, {}
+        self.step_reward = {}
         cell = ({}, {})  # grid_world_state layers 0 / 1 (float32): what `_get_move` tests (MR:636)
         # Step 1 (MR:546-574): basal cost, ageing
         for a in self.prev_agents:
@@ -498,6 +540,8 @@ class TraitEventRecorder:
                     termd.add(a)
                     cell[0 if is_pred(a) else 1][pos[a]] = np.float32(0.0)
                     self.agent_event_log[a]["lifecycle_events"].append({"t": int(t), "event": "max_age_reached", "age": int(prev[a][2] + 1)})
+                    self.stats[a]["age_expired_step"] = int(t)  # CAD:985-988
+                    self.step_reward[a] = 0.0
                     self._finalize(a, "max_age", t)
         # Step 2 (MR:576-584)
         g_now = {c: [name, min(e + self.grass_gain, self.grass_max)] for c, (name, e) in self.prev_grass.items()}
@@ -520,10 +564,16 @@ class TraitEventRecorder:
             cell[s][old] = np.float32(0.0)
             cell[s][new] = np.float32(E[a])
             pos[a] = new
+            rec = self.stats[a]  # MR:609-614
+            rec["avg_energy_sum"] += E[a]
+            rec["avg_energy_steps"] += 1
+            rec["distance_traveled"] += float(np.linalg.norm(np.array(new) - np.array(old)))
+            rec["movement_energy_spent"] += cost
         # Step 4a (MR:274-280): starvation, `agent_energies` order
         for a in self.prev_agents:
             if E[a] <= 0:
                 termd.add(a)
+                self.step_reward[a] = 0  # MR:716
                 self._finalize(a, "starved", t)
         # Step 4b (MR:790-834): prey that are still alive eat the patch they stand on
         for a in order[1]:
@@ -531,7 +581,7 @@ class TraitEventRecorder:
                 continue
             g = g_now.get(pos[a])
             if g is None:
-                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+                self._reward(a, _role(cfg.get("reward_prey_step", 0.0), a))
                 continue
             if self.cad:  # CAD:909-925: a capped bite, the rest stays on the patch
                 gain = min(float(g[1]), self.cap_grass)
@@ -542,7 +592,9 @@ class TraitEventRecorder:
             E[a] += gain
             deltas[a]["eat"] = gain
             g[1] = rest if rest > 0.0 else 0.0
-            self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
+            self._reward(a, _role(cfg.get("reward_prey_eat_grass", 0.0), a))
+            self.stats[a]["times_ate"] += 1
+            self.stats[a]["energy_gained"] += gain
             if self.cad:
                 self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": g[0], "alive_before_bite": True,
                                                                  "bite_size": float(gain), "energy_after": float(E[a])})
@@ -566,7 +618,7 @@ class TraitEventRecorder:
             if q is not None and self.sat_cd >= 0 and t < self.sat_until.get(a, 0):
                 q = None  # still digesting (MR:734-740)
             if q is None:
-                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
+                self._reward(a, _role(cfg.get("reward_predator_step", 0.0), a))
                 if rows.get(a, 0) & ROW_ATE:
                     self.inexact_chains += 1
                 continue
@@ -576,8 +628,14 @@ class TraitEventRecorder:
             deltas[a]["eat"] = gain
             if self.sat_cd > 0:
                 self.sat_until[a] = int(t) + self.sat_cd  # MR:756-757
-            self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
+            self._reward(a, _role(cfg.get("reward_predator_catch_prey", 0.0), a))
+            self.stats[a]["times_ate"] += 1
+            self.stats[a]["energy_gained"] += gain
             termd.add(q)
+            penalty = _role(cfg.get("penalty_prey_caught", 0.0), q)  # MR:765-773
+            self.step_reward[q] = penalty
+            if q in self.live_order:
+                self.stats[q]["cumulative_reward"] += penalty
             self._finalize(q, "eaten", t)
             if self.cad:
                 self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "bite_size": float(pe), "energy_after": float(E[a])})
@@ -606,8 +664,16 @@ class TraitEventRecorder:
                     self.inexact_chains += 1
                 E[par] -= ce
                 deltas[par]["repro"] = -ce
+                self.stats[par]["offspring_count"] += 1
+                if not self.cad:  # MR:900-908
+                    self.stats[par]["reproduction_energy_invested_sum"] += ce
+                    self.stats[par]["reproduction_energy_invested_count"] += 1
+                    self.stats[par]["parent_energy_after_reproduction_sum"] += E[par]
+                    self.stats[par]["parent_energy_after_reproduction_count"] += 1
+                    self.stats[child]["offspring_initial_energy"] = ce
+                self.step_reward[child] = 0
                 r = _role(cfg.get(f"reproduction_reward_{role}", 0.0), par)
-                self.cumulative_reward[par] += r
+                self._reward(par, r)
                 self.agent_event_log[par]["reward_events"].append({"t": int(t), "reproduction_reward": float(r),
                                                                    "cumulative_reward": float(self.cumulative_reward[par])})
                 deltas[child] = {"decay": 0.0, "move": 0.0, "eat": 0.0, "repro": 0.0}
@@ -628,6 +694,12 @@ class TraitEventRecorder:
             for a in list(self.live_order):
                 self._finalize(a, "time_limit", int(t) + 1)
         self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+
+    def _reward(self, agent, r):
+        """`self.rewards[agent] = r` plus the running totals of the record and of the reward events"""
+        self.step_reward[agent] = r
+        self.cumulative_reward[agent] += r
+        self.stats[agent]["cumulative_reward"] += r
 
     def _offspring_energy(self, parent, s, parent_energy, value):
         """MR:897 / 984: the configured initial energy; INV:546-557: the parent's energy x its investment fraction"""

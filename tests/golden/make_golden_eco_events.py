@@ -65,7 +65,9 @@ def main():
             n = t + 1
             if term["__all__"] or trunc["__all__"]:
                 break
-        out = {"steps": n, "per_step_agent_data": plain(env.per_step_agent_data), "agent_event_log": plain(env.agent_event_log)}
+        out = {"steps": n, "per_step_agent_data": plain(env.per_step_agent_data), "agent_event_log": plain(env.agent_event_log),
+               "agent_stats": plain(env.get_all_agent_stats()), "energy_by_type": plain(env.get_total_energy_by_type()),
+               "offspring_by_type": plain(env.get_total_offspring_by_type())}
         path = os.path.join(HERE, f"eco_events_{case[4:]}.json.gz")
         with gzip.GzipFile(path, "wb", mtime=0) as f:
             f.write(json.dumps(out, sort_keys=True).encode())

@@ -80,6 +80,8 @@ def main():
                 break
         out = {"steps": n, "ended": ended, "per_step_agent_data": plain(env.per_step_agent_data), "agent_event_log": plain(env.agent_event_log),
                "record_order": [a for a, _ in env._iter_all_agent_records()],
+               "agent_stats": plain(env.get_all_agent_stats()), "energy_by_type": plain(env.get_total_energy_by_type()),
+               "offspring_by_type": plain(env.get_total_offspring_by_type()),
                "spearman": {k: float(v) for k, v in (metrics or {}).items() if "spearman" in k}}
         path = os.path.join(HERE, f"trait_events_{case}.json.gz")
         with gzip.GzipFile(path, "wb", mtime=0) as f:

@@ -136,6 +136,16 @@ def _replay_trait(case):
         for k in w:
             assert got_log[a][k] == w[k], (case, a, k, got_log[a][k], w[k])
     assert env._events.record_order() == want["record_order"], case
+    # get_all_agent_stats() (MR:1406-1412): every record, every field, in the reference's order
+    got_stats = _plain(env.get_all_agent_stats())
+    assert list(got_stats) == want["record_order"]
+    for a, w in want["agent_stats"].items():
+        assert sorted(got_stats[a]) == sorted(w), (case, a, sorted(set(got_stats[a]) ^ set(w)))
+        for k in w:
+            assert got_stats[a][k] == w[k], (case, a, k, got_stats[a][k], w[k])
+    assert env.get_total_offspring_by_type() == want["offspring_by_type"]
+    if not want["ended"]:
+        assert env.get_total_energy_by_type() == want["energy_by_type"]
     if want["ended"]:
         got = infos["__all__"]["training_metrics"]
         for k, v in want["spearman"].items():
