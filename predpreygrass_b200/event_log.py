@@ -92,6 +92,9 @@ class EcoEventRecorder:
         self.first_bite_step = {}
         self.inexact_chains = 0
         self.closed = set()  # agents whose record is finalized (no longer in `agent_stats_live`)
+        self.stats, self.step_reward = {}, {}  # `agent_stats_live` + `agent_stats_completed` records; `self.rewards` of the running step
+        self.live_order, self.completed_order = [], []
+        self.ambiguous_final_moves = 0  # agents that starved on a step whose move may or may not have been blocked (see get_all_agent_stats)
         self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
         for a in agents:
             self._register(a, None, 0, state[a][3])
@@ -102,6 +105,14 @@ class EcoEventRecorder:
         self.agent_live_offspring_ids[agent] = []
         self.cumulative_reward[agent] = 0.0
         self.lineage[agent] = [parent, 0, 0, False]
+        role = "predator" if "predator" in agent else "prey"
+        self.live_order.append(agent)
+        self.stats[agent] = {  # `agent_stats_live[agent]` (ECO:1501-1523)
+            "agent_id": agent, "birth_step": t, "parent": parent, "offspring_count": 0, "offspring_ids": self.agent_live_offspring_ids[agent],
+            "distance_traveled": 0.0, "movement_energy_spent": 0.0, "times_ate": 0, "energy_gained": 0.0, "avg_energy_sum": 0.0,
+            "avg_energy_steps": 0, "cumulative_reward": 0.0, "lineage_reward_total": 0.0, "policy_group": role,
+            "genome": None if speed is None else {"speed": float(speed)}, "death_step": None, "death_cause": None, "avg_energy": 0.0,
+            "max_age": self._limit(self.max_age, agent), "age_expired_step": None, "carcass_only_blocks": 0}
         self._lineage_alive(agent, True)  # `_handle_lineage_birth` (ECO:1462-1466)
         self.agent_event_log[agent] = {
             "agent_id": agent, "birth_step": t, "death_step": None, "parent_id": parent, "death_cause": None,
@@ -126,6 +137,16 @@ class EcoEventRecorder:
         `_handle_lineage_death` first (ECO:764, 1072; a bitten prey at its first bite, ECO:840, 846)"""
         self._lineage_alive(agent, False)
         self.closed.add(agent)
+        if agent in self.live_order:  # the record part of `_finalize_agent_record` (ECO:1536-1551)
+            self.live_order.remove(agent)
+            self.completed_order.append(agent)
+            rec = self.stats[agent]
+            rec["cumulative_reward"] += self.step_reward.get(agent, 0.0)  # the step's reward is added once more (ECO:1540-1542)
+            rec["death_cause"] = cause
+            if rec["death_step"] is None:
+                rec["death_step"] = step
+            rec["offspring_count"] = self.agent_offspring_counts.get(agent, rec["offspring_count"])
+            rec["avg_energy"] = rec["avg_energy_sum"] / max(rec["avg_energy_steps"], 1)
         evt = self.agent_event_log[agent]
         evt["death_step"] = self.first_bite_step.get(agent, step)
         evt["death_cause"] = cause
@@ -139,6 +160,8 @@ class EcoEventRecorder:
         agents = [a for a in self.prev_agents if a in state] + list(newborn)  # ECO:353-367
         is_pred = lambda a: "predator" in a  # noqa: E731
         E, deltas, age = {}, {}, {}
+        self.step_reward = {}
+        moved = {}  # dying agents: per candidate cell (distance, cost, energy after the move) for the record's movement totals
         gone = set()  # terminated so far in this step
         # Step 1 (ECO:582-614): basal loss, ageing, age cap
         for a in self.prev_agents:
@@ -154,6 +177,8 @@ class EcoEventRecorder:
             limit = self._limit(self.max_age, a)
             if not (s == 1 and prev[a][4]) and isinstance(limit, (int, float)) and limit >= 0 and age[a] >= limit:
                 self.agent_event_log[a]["lifecycle_events"].append({"t": int(t), "event": "max_age_reached", "age": int(age[a])})
+                self.stats[a]["age_expired_step"] = int(t)  # ECO:1076-1078
+                self.step_reward[a] = 0.0
                 self._finalize(a, "max_age", t)
                 gone.add(a)
         # Step 2 (ECO:616-624): grass regrowth
@@ -161,6 +186,12 @@ class EcoEventRecorder:
         # Step 3 (ECO:626-662): moves.  Survivors: old and new cell are known.  Agents that die in this step: the cells they
         # can have died on are kept as candidates (cell, energy) — the move target, or the old cell if the move was blocked;
         # terminated agents (age cap) and carcasses do not move.
+        # Whether the move of an agent that dies in this step was blocked is replayed on the own-species layer the reference tests
+        # (`grid_world_state[layer, target] > 0`, float32, ECO:684-686): every agent writes its cell after the basal loss
+        # (carcasses included, aged-out agents zero theirs), movers zero their old cell and write the new one.
+        cell = ({}, {})
+        for a in self.prev_agents:
+            cell[0 if is_pred(a) else 1][prev[a][0]] = np.float32(0.0 if a in gone else E[a])
         cand = {}
         for a, action in action_dict.items():
             if a not in prev or a in gone or (not is_pred(a) and prev[a][4]):
@@ -168,12 +199,22 @@ class EcoEventRecorder:
             s = 0 if is_pred(a) else 1
             old, spd = prev[a][0], prev[a][3]
             if a in state:
-                cost = self._cost(a, s, old, state[a][0], spd)
+                new = state[a][0]
+                cost = self._cost(a, s, old, new, spd)
                 E[a] -= cost
                 deltas[a]["move"] -= cost
+                self._moved(a, old, new, cost, E[a])
+                e_after = E[a]
             else:
-                tgt = self._target(old, action, spd)
-                cand[a] = [(tgt, E[a] - self._cost(a, s, old, tgt, spd))] + ([(old, E[a])] if tgt != old else [])
+                new = self._target(old, action, spd)
+                if cell[s].get(new, 0.0) > 0:
+                    new = old
+                c_t = self._cost(a, s, old, new, spd)
+                e_after = E[a] - c_t
+                cand[a] = [(new, e_after)]
+                moved[a] = {new: (old, new, c_t, e_after)}
+            cell[s][old] = np.float32(0.0)
+            cell[s][new] = np.float32(e_after)
         # Step 4a (ECO:314-319): starvation.  Predators that are gone and not aged out starved.  A prey that is gone stays
         # on the grid until Step 5, so a predator can still bite it (ECO:789-791 looks at `agent_positions`), whatever it
         # died of: every prey that is gone keeps its candidates for Step 4c.
@@ -185,6 +226,12 @@ class EcoEventRecorder:
                 cand[a] = [(prev[a][0], E[a])]
             if is_pred(a):
                 if a not in gone:
+                    if a in moved:  # which of its candidate cells it starved on: the one that leaves no energy
+                        opts = [v for v in moved[a].values() if v[3] <= 0] or list(moved[a].values())
+                        if len(opts) > 1:
+                            self.ambiguous_final_moves += 1
+                        self._moved(a, *opts[0])
+                    self.step_reward[a] = 0  # ECO:768
                     self._finalize(a, "starved", t)
                     gone.add(a)
             else:
@@ -194,7 +241,8 @@ class EcoEventRecorder:
             if is_pred(a) or a in gone:
                 continue
             if prev[a][4]:
-                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+                if a in state or E[a] > 0:  # a carcass that starved was terminated in Step 4a, before the prey engagements
+                    self._reward(a, _role(cfg.get("reward_prey_step", 0.0), a))
                 continue
             f = rows.get(a, 0)
             if a in state and f & ROW_ATE and state[a][0] in g_now:
@@ -202,7 +250,9 @@ class EcoEventRecorder:
                 bite = min(float(ge), self.cap_grass)
                 E[a] += bite
                 deltas[a]["eat"] = bite
-                self.cumulative_reward[a] += _role(cfg.get("reward_prey_eat_grass", 0.0), a)
+                self._reward(a, _role(cfg.get("reward_prey_eat_grass", 0.0), a))
+                self.stats[a]["times_ate"] += 1
+                self.stats[a]["energy_gained"] += bite
                 self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": name, "alive_before_bite": True,
                                                                  "bite_size": float(bite), "energy_after": float(E[a])})
             elif a in dead_prey and f & ROW_ATE:
@@ -215,7 +265,7 @@ class EcoEventRecorder:
                         c["e"] += bite
                         c["grass"] = (name, bite)
             elif a in state:
-                self.cumulative_reward[a] += _role(cfg.get("reward_prey_step", 0.0), a)
+                self._reward(a, _role(cfg.get("reward_prey_step", 0.0), a))
         # Step 4c (ECO:775-884): predators
         prey_at = {state[a][0]: a for a in state if not is_pred(a) and a in prev}
         eaten = {}
@@ -234,7 +284,8 @@ class EcoEventRecorder:
                 limit = self._limit(self.carcass_age, a)
                 if q is not None and not was_dead and isinstance(limit, (int, float)) and limit >= 0 and age[a] < limit:
                     self.agent_event_log[a]["diet_events"].append({"t": int(t), "event": "carcass_only_block", "prey_id": q, "age": int(age[a])})  # ECO:1035-1059
-                self.cumulative_reward[a] += _role(cfg.get("reward_predator_step", 0.0), a)
+                    self.stats[a]["carcass_only_blocks"] += 1
+                self._reward(a, _role(cfg.get("reward_predator_step", 0.0), a))
                 continue
             # which prey: a bitten one that is still there (carcass), else a prey that is gone and can have stood here
             q = prey_at.get(pos)
@@ -245,6 +296,8 @@ class EcoEventRecorder:
                 E[q] = pe - bite
                 if q not in self.first_bite_step:
                     self.first_bite_step[q] = int(t)  # ECO:836-838: the first bite freezes death_step
+                if self.stats[q]["death_step"] is None:
+                    self.stats[q]["death_step"] = int(t)
                 self._lineage_alive(q, False)  # ECO:839-840
             else:
                 if not gone_here:
@@ -257,7 +310,9 @@ class EcoEventRecorder:
                 eaten[q] = c
             E[a] += bite
             deltas[a]["eat"] = bite
-            self.cumulative_reward[a] += _role(cfg.get("reward_predator_catch_prey", 0.0), a)
+            self._reward(a, _role(cfg.get("reward_predator_catch_prey", 0.0), a))
+            self.stats[a]["times_ate"] += 1
+            self.stats[a]["energy_gained"] += bite
             self.agent_event_log[a]["eating_events"].append({"t": int(t), "id_eaten": q, "alive_before_bite": not was_dead,
                                                              "bite_size": float(bite), "energy_after": float(E[a])})
         for q, cs in dead_prey.items():
@@ -267,11 +322,31 @@ class EcoEventRecorder:
                                                                  "bite_size": float(c["grass"][1]), "energy_after": float(c["e"])})
             if q in gone:  # aged out: the cause stays (its record was closed in Step 1)
                 continue
-            if c is not None and c["e"] > 0:
+            was_eaten = c is not None and c["e"] > 0
+            if q in moved:  # the record's movement totals: the cell it was caught on, else the one it starved on
+                if was_eaten:
+                    opts = [v for k, v in moved[q].items() if k == c["cell"]]
+                else:
+                    opts = [v for v in moved[q].values() if v[3] <= 0] or list(moved[q].values())
+                    if len(opts) > 1:
+                        self.ambiguous_final_moves += 1
+                self._moved(q, *opts[0])
+            if was_eaten:
+                if not prev[q][4]:  # alive at the prey engagements (Step 4b): its meal or the step reward
+                    if c["grass"] is not None:
+                        self._reward(q, _role(cfg.get("reward_prey_eat_grass", 0.0), q))
+                        self.stats[q]["times_ate"] += 1
+                        self.stats[q]["energy_gained"] += c["grass"][1]
+                    else:
+                        self._reward(q, _role(cfg.get("reward_prey_step", 0.0), q))
+                penalty = _role(cfg.get("penalty_prey_caught", 0.0), q)  # ECO:851-861
+                self.step_reward[q] = penalty
+                self.stats[q]["cumulative_reward"] += penalty
                 self._finalize(q, "eaten", t)
             else:
                 if c is None and all(x["e"] > 0 for x in cs):
                     self.inexact_chains += 1  # gone, but it can neither have starved nor did a predator take it
+                self.step_reward[q] = 0  # ECO:768
                 self._finalize(q, "starved", t)
             gone.add(q)
         # Step 6 (ECO:1092-1270): births, predators first; the k-th newborn row of a species belongs to the k-th parent
@@ -288,8 +363,10 @@ class EcoEventRecorder:
                 self.agent_event_log[par]["reproduction_events"].append({"t": int(t), "child_id": child})
                 E[par] -= self.init_e[s]
                 deltas[par]["repro"] = -self.init_e[s]
+                self.stats[par]["offspring_count"] += 1
+                self.step_reward[child] = 0
                 r = _role(cfg.get(f"reproduction_reward_{role}", 0.0), par)
-                self.cumulative_reward[par] += r
+                self._reward(par, r)
                 self.agent_event_log[par]["reward_events"].append({"t": int(t), "reproduction_reward": float(r), "lineage_reward": 0.0,
                                                                    "cumulative_reward": float(self.cumulative_reward[par])})
                 deltas[child] = {"decay": 0.0, "move": 0.0, "eat": 0.0, "repro": 0.0}
@@ -303,8 +380,11 @@ class EcoEventRecorder:
             if delta == 0:
                 continue
             reward = _role(cfg.get("lineage_reward_coeff", 0.0), a) * float(delta)
+            self.stats[a]["lineage_reward_total"] += reward  # ECO:962-964
             if reward != 0:
                 self.cumulative_reward[a] += reward
+                self.stats[a]["cumulative_reward"] += reward
+                self.step_reward[a] = self.step_reward.get(a, 0.0) + reward
             self.agent_event_log[a]["reward_events"].append({"t": int(t), "reproduction_reward": 0.0, "lineage_reward": float(reward),
                                                              "cumulative_reward": float(self.cumulative_reward[a])})
         # the chain's end is the device's energy
@@ -322,9 +402,44 @@ class EcoEventRecorder:
                             "offspring_ids": self.agent_live_offspring_ids.get(a, []), "parent": self.agent_parents.get(a)}
         self.per_step_agent_data.append(step_data)
         if time_limit:  # ECO:478-479: every record still open is closed with the step counter already advanced
-            for a in agents:
+            for a in list(self.live_order):
                 self._finalize(a, "time_limit", int(t) + 1)
         self.prev, self.prev_agents, self.prev_grass = dict(state), list(agents), dict(grass)
+
+    def _reward(self, agent, r):
+        """`self.rewards[agent] = r` plus the running totals of the record and of the reward events"""
+        self.step_reward[agent] = r
+        self.cumulative_reward[agent] += r
+        if agent in self.stats:
+            self.stats[agent]["cumulative_reward"] += r
+
+    def _moved(self, agent, old, new, cost, energy_after):
+        """the record's part of a move (ECO:656-660)"""
+        rec = self.stats[agent]
+        rec["avg_energy_sum"] += energy_after
+        rec["avg_energy_steps"] += 1
+        rec["distance_traveled"] += float(np.linalg.norm(np.array(new) - np.array(old)))
+        rec["movement_energy_spent"] += cost
+
+    def record_order(self):
+        return list(self.live_order) + list(self.completed_order)
+
+    def get_all_agent_stats(self):
+        """`get_all_agent_stats` (ECO:1676-1682).  The records follow the reference's bookkeeping field by field; the one thing the
+        device does not report is whether the last move of an agent that STARVED was blocked — if both of its candidate cells
+        leave it without energy the record books the move as made and `ambiguous_final_moves` counts it."""
+        out = {}
+        for a in self.record_order():
+            rec = dict(self.stats[a])
+            rec["offspring_ids"] = list(rec["offspring_ids"])
+            out[a] = rec
+        return out
+
+    def get_total_offspring_by_type(self):
+        counts = {"predator": 0, "prey": 0}
+        for a in self.record_order():
+            counts[self.stats[a]["policy_group"]] += self.stats[a]["offspring_count"]
+        return counts
 
     def export(self, path):
         """`export_agent_event_log` (ECO:1575-1597)"""

@@ -50,6 +50,15 @@ def _replay(case):
     for a, w in want["agent_event_log"].items():
         for k in w:
             assert got_log[a][k] == w[k], (case, a, k, got_log[a][k], w[k])
+    # get_all_agent_stats() (ECO:1676-1682): every record, every field, in the reference's order
+    got_stats = _plain(env.get_all_agent_stats())
+    assert list(got_stats) == list(want["agent_stats_order"]) if "agent_stats_order" in want else sorted(got_stats) == sorted(want["agent_stats"])
+    for a, w in want["agent_stats"].items():
+        assert sorted(got_stats[a]) == sorted(w), (case, a, sorted(set(got_stats[a]) ^ set(w)))
+        for k in w:
+            assert got_stats[a][k] == w[k], (case, a, k, got_stats[a][k], w[k])
+    assert env._events.ambiguous_final_moves == 0
+    assert env.get_total_offspring_by_type() == want["offspring_by_type"]
     env.close()
 
 
