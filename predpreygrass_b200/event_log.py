@@ -15,8 +15,11 @@ where an agent that died this step stood when it died; a fully eaten prey is the
 two cells it can have ended on (its move target, or its old cell if the move was blocked), and the match is confirmed by
 the predator's energy.
 
-Not mirrored: `agent_stats_live/completed` (the per-agent totals behind `training_metrics` are device counters,
-`ppg_read_episode_eco`), lineage `reward_events` (the event log is built for `lineage_reward_coeff = 0`).
+The per-agent records of the reference (`agent_stats_live` / `agent_stats_completed`, read by the evaluation scripts through
+`get_all_agent_stats()`, ECO:1676-1682) are rebuilt alongside, field by field — distance, locomotion energy, meals, average energy,
+cumulative reward (with the step's reward that `_finalize_agent_record` adds once more, ECO:1540-1542), frozen death steps.
+Whether the last move of an agent that dies in a step was blocked is replayed on the own-species layer the reference tests
+(ECO:684-686).  Lineage `reward_events` are logged with the configured coefficient.
 """
 import json
 
