@@ -11,9 +11,9 @@ the state after it and the row flags, because the energy bookkeeping of ECO is a
 Each link is the reference's own float64 expression evaluated on the host with the same operands, so the deltas come out
 bit-identical; the chain's end is compared with the energy the device reports and a mismatch is counted in
 `inexact_chains` (0 on every recording of tests/golden/eco_events_*.json.gz).  The only thing the device does not report is
-where an agent that died this step stood when it died; a fully eaten prey is therefore matched to its predator through the
-two cells it can have ended on (its move target, or its old cell if the move was blocked), and the match is confirmed by
-the predator's energy.
+where an agent that died this step stood when it died; its move is therefore replayed on the host (target cell, or the old
+cell if the own-species layer blocked it), a fully eaten prey is matched to its predator through that cell, and the match is
+confirmed by the predator's energy.
 
 The per-agent records of the reference (`agent_stats_live` / `agent_stats_completed`, read by the evaluation scripts through
 `get_all_agent_stats()`, ECO:1676-1682) are rebuilt alongside, field by field — distance, locomotion energy, meals, average energy,
