@@ -41,3 +41,35 @@ def test_trait_adapter_over_the_oracle(name):
 @pytest.mark.parametrize("name", golden_cases(("cad",)))
 def test_cadence_adapter_over_the_oracle(name):
     G.test_cadence_dict_adapter_replays_reference_episode(name)
+
+
+@pytest.mark.parametrize("name", ["coop_crowded_s3", "mr_default_s1"])
+def test_trait_adapter_without_the_event_recorder(name):
+    """`record_agent_events: False`: no per-step host replay — the exporters are empty, `get_all_agent_stats()` raises, and
+    `training_metrics` leaves out exactly the keys that need the recorder (rank correlations, kinship)"""
+    import json
+
+    from predpreygrass_b200 import env_evolutionary as E
+    from tests.helpers import load_golden
+
+    z, cfg = load_golden(name)
+    cls = {"mr": E.PredPreyGrassMetabolicRate, "coop": E.PredPreyGrassCooperation}[cfg.pop("variant")]
+    cfg.update(cap_live=(250, 450), record_agent_events=False)
+    env = cls(cfg)
+    env.reset(seed=int(z["seed"]), options={"ppg_tape": (z["fallback_cells"], z["step_reals"])})
+    names = ("predator", "prey")
+    got = None
+    for t in range(len(z["steps"])):
+        a0, a1 = z["act_off"][t], z["act_off"][t + 1]
+        *_, term, trunc, infos = env.step({f"{names[s]}_{i}": int(v) for s, i, v in zip(z["act_s"][a0:a1], z["act_id"][a0:a1], z["act_v"][a0:a1])})
+        if term["__all__"] or trunc["__all__"]:
+            got = infos["__all__"]["training_metrics"]
+            break
+    want = json.loads(str(z["metrics_json"]))
+    missing = set(want) - set(got)
+    assert missing and all("spearman" in k or "relatedness" in k for k in missing), sorted(missing)
+    assert all(got[k] == pytest.approx(want[k], rel=1e-9, abs=1e-12) for k in got)
+    assert env.per_step_agent_data == [] and env.agent_event_log == {}
+    with pytest.raises(RuntimeError):
+        env.get_all_agent_stats()
+    env.close()
