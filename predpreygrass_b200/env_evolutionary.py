@@ -1053,6 +1053,16 @@ class PredPreyGrassStag(_RowDictEnv):
         infos["__all__"] = g
         return infos
 
+    def get_total_energy_by_type(self):
+        """STAG:1964-1997: total energy of the live predators / prey (also per type) and of the grass"""
+        totals = {"predator": 0.0, "prey": 0.0, "grass": sum(self.grass_energies.values()), "type_1_predator": 0.0,
+                  "type_2_predator": 0.0, "type_1_prey": 0.0, "type_2_prey": 0.0}
+        for agent, energy in self.agent_energies.items():
+            role = "predator" if "predator" in agent else "prey"
+            totals[role] += energy
+            totals[("type_1_" if "type_1" in agent else "type_2_") + role] += energy
+        return totals
+
     # STAG attributes
     @property
     def active_num_predators(self):

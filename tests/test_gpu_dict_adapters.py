@@ -137,6 +137,15 @@ def test_stag_dict_adapter_replays_reference_episode(name):
         pos, en, age = env.agent_positions, env.agent_energies, env.agent_ages
         assert list(pos) != [] and sorted(pos) == sorted(want), (name, t)
         assert all((pos[k], en[k], age[k]) == want[k] for k in want), (name, t)
+        # get_total_energy_by_type (STAG:1964-1997), the reference's sums over its own dict order
+        tot = {"predator": 0.0, "prey": 0.0, "grass": sum(float(e) for e in z["grass_e"][t]), "type_1_predator": 0.0, "type_2_predator": 0.0,
+               "type_1_prey": 0.0, "type_2_prey": 0.0}
+        for s, i, e in zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_e"][s0:s1]):
+            k = key(s, i)
+            role = "predator" if "predator" in k else "prey"
+            tot[role] += float(e)
+            tot[k[:7] + role] += float(e)
+        assert env.get_total_energy_by_type() == pytest.approx(tot, rel=1e-12, abs=0.0), (name, t)
         face, trait = env.predator_facing, env.predator_cooperation_trait
         for s, i, f, v in zip(z["st_s"][s0:s1], z["st_id"][s0:s1], z["st_face"][s0:s1], z["st_trait"][s0:s1]):
             if s == 0:
